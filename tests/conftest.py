@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "tacotron2-vae_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    has_gpu = torch.cuda.is_available()
+    has_ref = os.path.isfile("/root/reference/model.py")
+    for it in items:
+        if "gpu" in it.keywords and not has_gpu:
+            it.add_marker(pytest.mark.skip(reason="no CUDA device"))
+        if "reference" in it.keywords and not has_ref:
+            it.add_marker(pytest.mark.skip(reason="/root/reference not present"))
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
