@@ -1,0 +1,220 @@
+/* t2v_b200 -- C ABI of the B200-native Tacotron2-VAE hot path (libt2v_b200.so).
+ *
+ * The reference (jinhan/tacotron2-vae) has no FFI layer: its hot path is PyTorch modules (model.py, modules.py,
+ * layers.py, stft.py, loss_function.py, distributed.py).  This header is the boundary a maintainer binds instead
+ * (ctypes stub in INTEGRATION.md): plain device pointers, sizes and a cudaStream_t -- no torch types.  Each entry
+ * names the reference code it replaces (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 (or int64 where stated) owned by the caller; the library never
+ *     allocates, frees or retains device memory;
+ *   - every call only enqueues work on `stream` (no host synchronisation) and returns
+ *       0  ok | <0 argument error, nothing launched | >0 cudaError_t ;  t2v_last_error() has the message;
+ *   - "padded channels-last" = a reference [B,C,T] tensor stored as rows [B*(T+4), C], two zero rows before and
+ *     after each utterance;  "tb rows" = time-major rows (t*B + b);
+ *   - dropout sites take an explicit keep-mask (float 0/1) or, when it is NULL, a counter-based RNG keyed by
+ *     (seed, site, logical index) that t2v_materialize_mask() reproduces for the test oracle.
+ */
+#ifndef T2V_B200_H
+#define T2V_B200_H
+#include <cuda_runtime_api.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library state ---------------------------------------------------------------------------------------- */
+const char* t2v_last_error(void);
+int t2v_version(void);
+unsigned long long t2v_launch_count(void);      /* kernels launched by this library since the last reset */
+void t2v_reset_launch_count(void);
+
+/* ---- GEMMs: every nn.Linear / Conv1d / LSTM-cell matmul of model.py goes through one of these two ------------ */
+/* exact fp32 FFMA, fully strided: C[m,n] = alpha*sum_k A[m*a_rs+k*a_cs]*B[n*b_rs+k*b_cs] + beta*C + bias[n] */
+int t2v_gemm_f32(const float* A, long long a_rs, long long a_cs, const float* B, long long b_rs, long long b_cs,
+                 float* C, long long c_rs, int M, int N, int K, float alpha, float beta, const float* bias, int batch,
+                 long long a_bs, long long b_bs, long long c_bs, cudaStream_t stream);
+/* tcgen05 (TMA + TMEM) GEMM, both operands K-major; see csrc/gemm_tc.cu for the "taps" (row-shifted K segments). */
+int t2v_gemm_tc(const void* A, long long lda, long long a_rows, long long a_inner, const void* B, long long ldb,
+                long long b_rows, long long b_inner, float* D, long long ldd, const float* bias, int M, int N, int k_sub,
+                int taps, int a_tap_rowshift, int b_tap_stride, int a_k0, int b_k0, int esize, int splits,
+                long long split_stride, int epi_atomic, float alpha, int bn_hint, cudaStream_t stream);
+
+/* ---- text embedding (model.py:474,528) -- integer gather, bit exact ------------------------------------------- */
+int t2v_embedding_fwd(const long long* ids, const float* table, float* out_padded, int B, int T, int C, int n_symbols,
+                      cudaStream_t stream);
+int t2v_embedding_bwd(const long long* ids, const float* dout_padded, float* dtable, int B, int T, int C,
+                      cudaStream_t stream);
+
+/* ---- BatchNorm1d/2d + activation + dropout (model.py:143-146,176-177; modules.py:69-71) ------------------------ */
+int t2v_col_stats(const float* x, long long rows, int C, int period, int lo, int hi, int mode, double* out0,
+                  double* out1, cudaStream_t stream);
+int t2v_bn_finalize(const double* sum, const double* sumsq, double n, int C, float eps, float momentum, float* mean,
+                    float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked,
+                    cudaStream_t stream);
+int t2v_bn_eval_prepare(const float* running_mean, const float* running_var, int C, float eps, float* mean,
+                        float* invstd, cudaStream_t stream);
+int t2v_bn_act_fwd(const float* y, float* out, long long rows, int C, int period, int lo, int hi, const float* mean,
+                   const float* invstd, const float* gamma, const float* beta, int act, const float* drop_mask,
+                   unsigned long long seed, unsigned int site, float p, int T, cudaStream_t stream);
+int t2v_bn_act_bwd_reduce(const float* dout, const float* y, long long rows, int C, int period, int lo, int hi,
+                          const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
+                          const float* drop_mask, unsigned long long seed, unsigned int site, float p, int T,
+                          double* dbeta_sum, double* dgamma_sum, cudaStream_t stream);
+int t2v_bn_act_bwd_apply(const float* dout, const float* y, float* dy, long long rows, int C, int period, int lo, int hi,
+                         const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
+                         const float* drop_mask, unsigned long long seed, unsigned int site, float p, int T,
+                         const double* dbeta_sum, const double* dgamma_sum, double n, int use_batch_stats,
+                         cudaStream_t stream);
+int t2v_double_to_float(const double* src, float* dst, int n, float beta, cudaStream_t stream);
+
+/* ---- layout / packing helpers ------------------------------------------------------------------------------------ */
+int t2v_copy2d(const float* src, long long s_rs, long long s_cs, float* dst, long long d_rs, long long rows, int cols,
+               float beta, cudaStream_t stream);
+int t2v_transpose(const float* in, long long i_ld, float* out, long long o_ld, long long rows, int cols,
+                  cudaStream_t stream);
+int t2v_conv1d_pack(const float* w, float* out, int Co, int Ci, int K, int flip, cudaStream_t stream);
+int t2v_conv1d_unpack_grad(const float* gk, float* gw, int Co, int Ci, int K, float beta, cudaStream_t stream);
+int t2v_axpby(const float* x, float a, float* y, float b, long long n, cudaStream_t stream);
+int t2v_bcast_add_rows(float* y, const float* v, long long rows, int C, int rows_per_batch, cudaStream_t stream);
+int t2v_sum_rows_per_batch(const float* x, float* out, int B, int rows_per_batch, int C, float beta, cudaStream_t stream);
+int t2v_sum_parts(const float* parts, int n_parts, long long part_stride, float* dst, long long n, cudaStream_t stream);
+int t2v_fill(float* x, long long n, float v, cudaStream_t stream);
+int t2v_bct_to_padded(const float* in, float* out, int B, int C, int T, float beta, cudaStream_t stream);
+int t2v_padded_to_bct(const float* in1, const float* in2, float* out, int B, int C, int T, const long long* lens,
+                      float fill, cudaStream_t stream);
+int t2v_rows_tb_to_padded(const float* rows, long long ld, float* out, int B, int C, int T, cudaStream_t stream);
+int t2v_padded_to_rows_tb(const float* p1, const float* p2, const float* dgate, float* rows, long long ld, int B, int C,
+                          int T, cudaStream_t stream);
+int t2v_bct_to_rows_tb_shift(const float* tgt, float* rows, int B, int C, int T, cudaStream_t stream);
+int t2v_gate_from_rows(const float* rows, long long ld, int col, float* gate, int B, int T, const long long* lens,
+                       float fill, cudaStream_t stream);
+int t2v_mask_padded_rows(float* x, int B, int C, int T, const long long* lens, cudaStream_t stream); /* model.py:515 */
+int t2v_unpad_add(const float* in_padded, const float* add_vec, float* out, int B, int T, int C, cudaStream_t stream);
+
+/* ---- Prenet pointwise (model.py:91-102) and dropout-mask materialisation for the oracle ------------------------- */
+int t2v_relu_drop_fwd(const float* x, float* out, long long o_rs, long long rows, int C, const float* mask,
+                      unsigned long long seed, unsigned int site, float p, unsigned long long idx_base,
+                      cudaStream_t stream);
+int t2v_relu_drop_bwd(const float* x, const float* dout, long long do_rs, float* dx, long long rows, int C,
+                      const float* mask, unsigned long long seed, unsigned int site, float p,
+                      unsigned long long idx_base, cudaStream_t stream);
+int t2v_materialize_mask(float* out, long long n, unsigned long long seed, unsigned int site, float p,
+                         unsigned long long idx_base, cudaStream_t stream);
+
+/* ---- recurrent cells: nn.LSTM / nn.LSTMCell / nn.GRU pointwise (model.py:171-190,357-381; modules.py:60-78) ----- */
+int t2v_lstm_pointwise_fwd(const float* parts, int n_parts, long long part_stride, long long parts_rs, const float* pre,
+                           long long pre_rs, const float* b1, const float* b2, const float* c_prev, long long cprev_rs,
+                           float* h_out, long long hout_rs, float* h_out2, long long hout2_rs, float* c_out,
+                           long long cout_rs, float* gates_save, float* cpre_save, float* seq_out, long long seq_rs,
+                           const float* mask_h, const float* mask_c, unsigned long long seed, unsigned int site_h,
+                           unsigned int site_c, float p, unsigned long long drop_base, const long long* lens, int t,
+                           int B, int H, cudaStream_t stream);
+int t2v_lstm_pointwise_bwd(const float* dh1, long long dh1_rs, const float* dh2, long long dh2_rs, const float* dh3,
+                           long long dh3_rs, float* dc, const float* gates_save, const float* cpre_save,
+                           const float* c_prev, long long cprev_rs, float* dgates, long long dg_rs, const float* mask_h,
+                           const float* mask_c, unsigned long long seed, unsigned int site_h, unsigned int site_c,
+                           float p, unsigned long long drop_base, const long long* lens, int t, int B, int H,
+                           cudaStream_t stream);
+int t2v_gru_pointwise_fwd(const float* gi, long long gi_rs, const float* gh, const float* b_ih, const float* b_hh, const float* h_prev,
+                          float* h_out, float* save, int B, int H, cudaStream_t stream);
+int t2v_gru_pointwise_bwd(const float* dh, const float* save, const float* h_prev, float* dgi, long long dgi_rs, float* dgh,
+                          float* dh_prev, int B, int H, cudaStream_t stream);
+int t2v_vae_reparam_fwd(const float* mulv, const float* eps, float* z, int B, int Z, int training, cudaStream_t stream);
+int t2v_vae_reparam_bwd(const float* mulv, const float* eps, const float* dz, const float* dmu_ext, const float* dlv_ext,
+                        float* dmulv, int B, int Z, int training, cudaStream_t stream);
+
+/* ---- reference encoder im2col (CoordConv.py:37-74 + modules.py:45-71) ------------------------------------------- */
+int t2v_im2col_3x3s2(const float* x, float* col, int N, int H, int W, int Ci, int coord, cudaStream_t stream);
+int t2v_col2im_3x3s2(const float* dcol, float* dx, int N, int H, int W, int Ci, cudaStream_t stream);
+
+/* ---- fused location-sensitive attention step (model.py:31-88, 366-374) ------------------------------------------ */
+int t2v_attn_step_fwd(const float* qparts, int n_qparts, long long qpart_stride, const float* w_prev, long long wprev_rs,
+                      const float* cum_in, float* cum_out, const float* pmem, const float* mem, const float* w_conv,
+                      const float* w_loc, const float* v, const long long* lens, float mask_value, float* w_out,
+                      long long wout_rs, float* ctx_out1, long long ctx1_rs, float* ctx_out2, long long ctx2_rs,
+                      float* a_save, int B, int Ti, cudaStream_t stream);
+int t2v_attn_step_bwd(const float* dctx1, long long dctx1_rs, const float* dctx2, long long dctx2_rs, const float* dctx3,
+                      long long dctx3_rs, const float* dw_in, float* dw_out, float* gcum, const float* w, long long w_rs,
+                      const float* w_prev, long long wprev_rs, const float* cum_in, const float* a_save, const float* mem,
+                      const float* w_conv, const float* w_loc, const float* v, const long long* lens, float* dmem,
+                      float* dpmem, float* dq, float* dv_part, float* dwloc_part, float* dwconv_part, int B, int Ti,
+                      cudaStream_t stream);
+
+/* ---- the decoder time loop: Decoder.decode / Decoder.forward / Decoder.inference (model.py:346-464) ------------- */
+typedef struct T2VDecoderSeq {
+  int B, Ti, To;                 /* batch, padded text length, number of decoder steps the buffers hold */
+  int use_tc;                    /* 0: exact fp32 FFMA GEMMs ; 1: tcgen05 tf32 GEMMs */
+  int training;                  /* dropout p_att/p_dec on h AND c of both cells (model.py:361-364,378-381) */
+  float p_att, p_dec;
+  unsigned long long seed;       /* RNG seed when drop_masks == NULL */
+  const float* drop_masks;       /* [To,4,B,1024] keep masks (att_h, att_c, dec_h, dec_c) or NULL */
+  float mask_value;              /* attention score_mask_value */
+  const long long* in_lens;      /* [B] text lengths (attention mask) or NULL */
+  const float *Wa, *ba1, *ba2;   /* attention_rnn: [4096,1792] = [weight_ih | weight_hh], bias_ih, bias_hh */
+  const float *Wd, *bd1, *bd2;   /* decoder_rnn:   [4096,2560] */
+  const float *Wq, *Wconv, *Wloc, *v;   /* query_layer [128,1024], location conv [32,2,31], dense [128,32], v [128] */
+  const float *mem, *pmem;       /* encoder outputs [B,Ti,512], processed memory [B,Ti,128] */
+  float *XA, *XD;                /* [(To+1),B,1792] = [prenet_t | ctx_{t-1} | h_att_{t-1}] ; [(To+1),B,2560] = [h_att_t | ctx_t | h_dec_{t-1}] */
+  float *CA, *CD;                /* [(To+1),B,1024] cell states, slot t = state before step t */
+  float *CUM;                    /* [(To+1),B,Ti] cumulative attention weights before step t */
+  float *align;                  /* [B,To,Ti] */
+  float *GA, *GD, *CPA, *CPD;    /* saved gates [To,B,4096] / pre-dropout cells [To,B,1024]; NULL at inference */
+  float *ASAVE;                  /* [To,B,Ti,128] tanh activations; NULL at inference */
+  float *parts, *qparts;         /* split-K workspaces: >= 8*B*4096 and 8*B*128 floats */
+} T2VDecoderSeq;
+int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);
+
+typedef struct T2VDecoderBwd {
+  T2VDecoderSeq f;               /* the forward description (same buffers) */
+  const float *WaT, *WdT, *WqT;  /* transposed weights [1792,4096], [2560,4096], [1024,128] */
+  const float *DHC;              /* [To,B,1536] grad wrt [h_dec_t | ctx_t] from linear_projection/gate_layer */
+  float *DGA, *DGD;              /* out: pre-activation gate grads [To,B,4096] */
+  float *DXA;                    /* out: grad wrt XA rows [To,B,1792] */
+  float *DXD;                    /* ring [2,B,2560] */
+  float *dCa, *dCd;              /* [B,1024] running cell-state grads (zero-initialised by caller) */
+  float *dwprev;                 /* ring [2,B,Ti] */
+  float *gcum;                   /* [B,Ti] zero-initialised */
+  float *dmem, *dpmem;           /* [B,Ti,512], [B,Ti,128] accumulators (zero-initialised) */
+  float *DQ;                     /* out [To,B,128] */
+  float *dHq;                    /* scratch [B,1024] */
+  float *dv_part, *dwloc_part, *dwconv_part;   /* [B,128], [B,128,32], [B,32,2,31] accumulators (zero-initialised) */
+} T2VDecoderBwd;
+int t2v_decoder_bwd_steps(const T2VDecoderBwd* s, int t_hi, int t_lo, cudaStream_t stream);  /* t = t_hi-1 .. t_lo */
+
+typedef struct T2VDecoderInfer {
+  T2VDecoderSeq f;
+  const float *Wp1, *Wp2;        /* prenet [256,80], [256,256] */
+  const float *Wpg, *bpg;        /* [81,1536] = [linear_projection ; gate_layer], bias [81] */
+  const float *prenet_masks;     /* [n,2,B,256] or NULL (RNG; prenet dropout is always on, model.py:101) */
+  float *O;                      /* [n,B,84] mel(80)+gate(1) rows, time-major */
+  float *P1;                     /* scratch [B,256] x2 */
+  float gate_threshold;
+  int *n_frames;                 /* [B] first step whose sigmoid(gate) > threshold (+1), or n if never */
+} T2VDecoderInfer;
+int t2v_decoder_infer_steps(const T2VDecoderInfer* s, int t_begin, int t_end, cudaStream_t stream);
+
+/* ---- loss (loss_function.py:27-45) -------------------------------------------------------------------------------- */
+int t2v_loss_fwd(const float* mel, const float* post, const float* tgt, long long n_mel, const float* gate,
+                 const float* gtgt, long long n_gate, const float* mu, const float* logvar, long long n_z,
+                 float kl_weight, double* acc, float* out, cudaStream_t stream);
+int t2v_loss_bwd(const float* mel, const float* post, const float* tgt, long long n_mel, const float* gate,
+                 const float* gtgt, long long n_gate, const float* mu, const float* logvar, long long n_z,
+                 float kl_weight, const float* gout, float* dmel, float* dpost, float* dgate, float* dmu, float* dlogvar,
+                 cudaStream_t stream);
+
+/* ---- STFT / mel front-end pieces (stft.py:77-105, layers.py:75-92, audio_processing.py:77-83) ------------------- */
+int t2v_reflect_pad(const float* wav, float* out, int B, int S, int pad, long long ld, cudaStream_t stream);
+int t2v_stft_mag(const float* ft, long long ft_ld, float* mag, long long mag_ld, long long rows, int nb, cudaStream_t stream);
+int t2v_mel_log(const float* mel, long long mel_ld, float* out, int B, int n_mel, int n_frames, long long rows_per_batch,
+                float clip, cudaStream_t stream);
+
+/* ---- optimiser: clip_grad_norm_ + Adam(L2 weight decay) fused (train.py:171-172,226-229) ------------------------ */
+int t2v_grad_sumsq(const float* g, long long n, float gscale, double* sumsq, cudaStream_t stream);
+int t2v_adam_clip_step(float* p, float* g, float* m, float* v, long long n, const double* sumsq, float gscale,
+                       float max_norm, float lr, float beta1, float beta2, float eps, float wd, int step, float* norm_out,
+                       cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

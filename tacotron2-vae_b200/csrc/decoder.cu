@@ -1,0 +1,221 @@
+// The decoder time loop (reference Decoder.decode / forward / inference, model.py:346-464) driven from C: per step
+//   gates_a = XA[t] Wa^T -> LSTM cell (+dropout on h and c) -> q = h_att Wq^T -> fused attention -> gates_d = XD[t] Wd^T
+//   -> LSTM cell, with every step's GEMM operand rows living in two time-major sequence buffers
+//     XA[t] = [prenet_t | ctx_{t-1} | h_att_{t-1}]   (1792 wide = the attention_rnn input ++ hidden, model.py:357-359)
+//     XD[t] = [h_att_t  | ctx_t     | h_dec_{t-1}]   (2560 wide = the decoder_rnn input ++ hidden,  model.py:375-377)
+// so the concatenations of the reference become "write the result where the next GEMM reads it", and the same
+// buffers are the saved activations of the batched weight-gradient GEMMs.  linear_projection / gate_layer are
+// deferred to one GEMM over all steps under teacher forcing (nothing in the loop consumes them).
+#include "t2v_common.cuh"
+#include "gemm_tc.h"
+#include "../../include/t2v_b200.h"
+
+namespace {
+
+constexpr int H = 1024, XA_W = 1792, XD_W = 2560, AD = 128, ED = 512, PD = 256;
+constexpr unsigned SITE_ATT_H = 10, SITE_ATT_C = 11, SITE_DEC_H = 12, SITE_DEC_C = 13, SITE_PRENET0 = 3, SITE_PRENET1 = 4;
+
+struct StepGemm {
+  bool tc;
+  T2VGemmTcPlan plan;
+  const float* A; long long lda; int a_k0;
+  const float* W; long long ldw;
+  int M, N, K, splits;
+  long long split_stride, ldd;
+};
+
+// D[parts][M][N] = A[a_row0 + m, a_k0 + k] * W[n, k]
+int setup_gemm(StepGemm* g, bool tc, const float* A, long long lda, long long a_rows, int a_k0, const float* W,
+               long long ldw, int M, int N, int K, int splits, long long ldd = 0) {
+  if (ldd == 0) ldd = N;
+  g->ldd = ldd;
+  g->tc = tc; g->A = A; g->lda = lda; g->a_k0 = a_k0; g->W = W; g->ldw = ldw; g->M = M; g->N = N; g->K = K;
+  g->split_stride = (long long)M * ldd;
+  if (tc) {
+    const int total = t2v_ceil_div(K, 32);
+    while (splits > 1 && total % splits) --splits;
+    g->splits = splits;
+    // inner extents are the true K so that TMA zero-fills the tail chunk on both operands
+    return t2v_gemm_tc_plan(&g->plan, A, lda, a_rows, (long long)a_k0 + K, W, ldw, N, K, ldd, M, N, K, 1, 0, 0, a_k0, 0, 4,
+                            splits, g->split_stride, 0, 1.f, 128);
+  }
+  g->splits = 1;
+  return 0;
+}
+int run_gemm(const StepGemm* g, long long a_row0, float* D, cudaStream_t st) {
+  if (g->tc) return t2v_gemm_tc_run(&g->plan, (int)a_row0, 0, D, nullptr, st);
+  return t2v_gemm_f32(g->A + a_row0 * g->lda + g->a_k0, g->lda, 1, g->W, g->ldw, 1, D, g->ldd, g->M, g->N, g->K, 1.f,
+                      0.f, nullptr, 1, 0, 0, 0, st);
+}
+#define CHK(expr) do { int r__ = (expr); if (r__) return r__; } while (0)
+
+struct FwdPlans { StepGemm ga, gq, gd; };
+
+int make_fwd_plans(const T2VDecoderSeq* s, FwdPlans* P) {
+  const bool tc = s->use_tc != 0;
+  const long long rows = (long long)(s->To + 1) * s->B;
+  CHK(setup_gemm(&P->ga, tc, s->XA, XA_W, rows, 0, s->Wa, XA_W, s->B, 4 * H, XA_W, 4));
+  CHK(setup_gemm(&P->gq, tc, s->XD, XD_W, rows, 0, s->Wq, H, s->B, AD, H, 8));
+  CHK(setup_gemm(&P->gd, tc, s->XD, XD_W, rows, 0, s->Wd, XD_W, s->B, 4 * H, XD_W, 4));
+  return 0;
+}
+
+// one decoder step t (everything of Decoder.decode except the deferred projection)
+int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) {
+  const int B = s->B, Ti = s->Ti;
+  const long long r0 = (long long)t * B, r1 = (long long)(t + 1) * B;
+  const float p_att = s->training ? s->p_att : 0.f, p_dec = s->training ? s->p_dec : 0.f;
+  const float* mk = s->drop_masks ? s->drop_masks + (long long)t * 4 * B * H : nullptr;
+  const unsigned long long dbase = s->drop_masks ? 0ull : (unsigned long long)t * B * H;
+  // attention LSTM
+  CHK(run_gemm(&P->ga, r0, s->parts, st));
+  CHK(t2v_lstm_pointwise_fwd(s->parts, P->ga.splits, P->ga.split_stride, 4 * H, nullptr, 0, s->ba1, s->ba2,
+                             s->CA + r0 * H, H,
+                             s->XA + r1 * XA_W + (PD + ED), XA_W,          // h_att -> next step's recurrent input
+                             s->XD + r0 * XD_W, XD_W,                      // h_att -> decoder_rnn input / query
+                             s->CA + r1 * H, H,
+                             s->GA ? s->GA + r0 * 4 * H : nullptr, s->CPA ? s->CPA + r0 * H : nullptr, nullptr, 0,
+                             mk, mk ? mk + (long long)B * H : nullptr, s->seed, SITE_ATT_H, SITE_ATT_C, p_att, dbase,
+                             nullptr, 0, B, H, st));
+  // query projection + fused attention
+  CHK(run_gemm(&P->gq, r0, s->qparts, st));
+  CHK(t2v_attn_step_fwd(s->qparts, P->gq.splits, P->gq.split_stride,
+                        t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr, (long long)s->To * Ti,
+                        s->CUM + r0 * Ti, s->CUM + r1 * Ti, s->pmem, s->mem, s->Wconv, s->Wloc, s->v, s->in_lens,
+                        s->mask_value, s->align + (long long)t * Ti, (long long)s->To * Ti,
+                        s->XD + r0 * XD_W + H, XD_W,                       // ctx_t -> decoder_rnn input
+                        s->XA + r1 * XA_W + PD, XA_W,                      // ctx_t -> next attention_rnn input
+                        s->ASAVE ? s->ASAVE + r0 * Ti * AD : nullptr, B, Ti, st));
+  // decoder LSTM
+  CHK(run_gemm(&P->gd, r0, s->parts, st));
+  CHK(t2v_lstm_pointwise_fwd(s->parts, P->gd.splits, P->gd.split_stride, 4 * H, nullptr, 0, s->bd1, s->bd2,
+                             s->CD + r0 * H, H,
+                             s->XD + r1 * XD_W + (H + ED), XD_W,           // h_dec -> next step's recurrent input
+                             nullptr, 0, s->CD + r1 * H, H,
+                             s->GD ? s->GD + r0 * 4 * H : nullptr, s->CPD ? s->CPD + r0 * H : nullptr, nullptr, 0,
+                             mk ? mk + 2LL * B * H : nullptr, mk ? mk + 3LL * B * H : nullptr, s->seed, SITE_DEC_H,
+                             SITE_DEC_C, p_dec, dbase, nullptr, 0, B, H, st));
+  return 0;
+}
+
+__global__ void stop_flags_kernel(const float* __restrict__ O, long long ld, int col, float thr, int t, int B,
+                                  int* __restrict__ n_frames) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float g = O[(long long)b * ld + col];
+  if (n_frames[b] < 0 && 1.f / (1.f + expf(-g)) > thr) n_frames[b] = t + 1;
+}
+
+}  // namespace
+
+T2V_API int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream) {
+  T2V_ARG_CHECK(s && s->B > 0 && s->Ti > 0 && s->To > 0, "shape");
+  T2V_ARG_CHECK(t_begin >= 0 && t_end <= s->To && t_begin <= t_end, "step range");
+  FwdPlans P;
+  CHK(make_fwd_plans(s, &P));
+  for (int t = t_begin; t < t_end; ++t) CHK(fwd_step(s, &P, t, stream));
+  return 0;
+}
+
+T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStream_t st) {
+  const T2VDecoderSeq* s = &d->f;
+  T2V_ARG_CHECK(s->B > 0 && s->Ti > 0 && s->To > 0, "shape");
+  T2V_ARG_CHECK(t_lo >= 0 && t_hi <= s->To && t_lo <= t_hi, "step range");
+  const bool tc = s->use_tc != 0;
+  const int B = s->B, Ti = s->Ti, To = s->To;
+  const float p_att = s->training ? s->p_att : 0.f, p_dec = s->training ? s->p_dec : 0.f;
+  StepGemm gxd, gxa, ghq;
+  const long long rows = (long long)To * B;
+  CHK(setup_gemm(&gxd, tc, d->DGD, 4 * H, rows, 0, d->WdT, 4 * H, B, XD_W, 4 * H, 8));
+  CHK(setup_gemm(&gxa, tc, d->DGA, 4 * H, rows, 0, d->WaT, 4 * H, B, XA_W, 4 * H, 8));
+  CHK(setup_gemm(&ghq, tc, d->DQ, AD, rows, 0, d->WqT, AD, B, H, AD, 1));
+  for (int t = t_hi - 1; t >= t_lo; --t) {
+    const long long r0 = (long long)t * B, r1 = (long long)(t + 1) * B;
+    const bool has_next = (t + 1 < To);
+    float* dxd = d->DXD + (long long)(t & 1) * B * XD_W;
+    const float* dxd_next = d->DXD + (long long)((t + 1) & 1) * B * XD_W;
+    const float* mk = s->drop_masks ? s->drop_masks + (long long)t * 4 * B * H : nullptr;
+    const unsigned long long dbase = s->drop_masks ? 0ull : (unsigned long long)t * B * H;
+    // decoder LSTM cell backward
+    CHK(t2v_lstm_pointwise_bwd(d->DHC + r0 * (H + ED), H + ED, has_next ? dxd_next + (H + ED) : nullptr, XD_W, nullptr, 0,
+                               d->dCd, s->GD + r0 * 4 * H, s->CPD + r0 * H, s->CD + r0 * H, H, d->DGD + r0 * 4 * H, 4 * H,
+                               mk ? mk + 2LL * B * H : nullptr, mk ? mk + 3LL * B * H : nullptr, s->seed, SITE_DEC_H,
+                               SITE_DEC_C, p_dec, dbase, nullptr, 0, B, H, st));
+    CHK(run_gemm(&gxd, r0, s->parts, st));
+    CHK(t2v_sum_parts(s->parts, gxd.splits, gxd.split_stride, dxd, (long long)B * XD_W, st));
+    // attention backward
+    CHK(t2v_attn_step_bwd(dxd + H, XD_W, d->DHC + r0 * (H + ED) + H, H + ED,
+                          has_next ? d->DXA + r1 * XA_W + PD : nullptr, XA_W,
+                          has_next ? d->dwprev + (long long)((t + 1) & 1) * B * Ti : nullptr,
+                          d->dwprev + (long long)(t & 1) * B * Ti, d->gcum, s->align + (long long)t * Ti,
+                          (long long)To * Ti, t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr, (long long)To * Ti,
+                          s->CUM + r0 * Ti, s->ASAVE + r0 * Ti * AD, s->mem, s->Wconv, s->Wloc, s->v, s->in_lens, d->dmem,
+                          d->dpmem, d->DQ + r0 * AD, d->dv_part, d->dwloc_part, d->dwconv_part, B, Ti, st));
+    CHK(run_gemm(&ghq, r0, d->dHq, st));
+    // attention LSTM cell backward
+    CHK(t2v_lstm_pointwise_bwd(dxd, XD_W, has_next ? d->DXA + r1 * XA_W + (PD + ED) : nullptr, XA_W, d->dHq, H, d->dCa,
+                               s->GA + r0 * 4 * H, s->CPA + r0 * H, s->CA + r0 * H, H, d->DGA + r0 * 4 * H, 4 * H, mk,
+                               mk ? mk + (long long)B * H : nullptr, s->seed, SITE_ATT_H, SITE_ATT_C, p_att, dbase,
+                               nullptr, 0, B, H, st));
+    CHK(run_gemm(&gxa, r0, s->parts, st));
+    CHK(t2v_sum_parts(s->parts, gxa.splits, gxa.split_stride, d->DXA + r0 * XA_W, (long long)B * XA_W, st));
+  }
+  return 0;
+}
+
+// free-running decode (Decoder.inference, model.py:428-464; the notebook / synthesizer.py:139-154 loop), batched,
+// with per-row stop bookkeeping on the device instead of a host sync per step
+T2V_API int t2v_decoder_infer_steps(const T2VDecoderInfer* d, int t_begin, int t_end, cudaStream_t st) {
+  const T2VDecoderSeq* s = &d->f;
+  T2V_ARG_CHECK(s->B > 0 && s->Ti > 0 && s->To > 0, "shape");
+  T2V_ARG_CHECK(t_begin >= 0 && t_end <= s->To && t_begin <= t_end, "step range");
+  const bool tc = s->use_tc != 0;
+  const int B = s->B;
+  FwdPlans P;
+  CHK(make_fwd_plans(s, &P));
+  const long long rows = (long long)(s->To + 1) * B;
+  StepGemm gp1, gp2, gph, gpc;
+  // prenet layer 1 reads the previous step's mel from O (84-wide rows), layer 2 reads P1
+  CHK(setup_gemm(&gp1, tc, d->O, 84, (long long)s->To * B, 0, d->Wp1, 80, B, PD, 80, 1));
+  CHK(setup_gemm(&gp2, tc, d->P1 + (long long)B * PD, PD, B, 0, d->Wp2, PD, B, PD, PD, 1));
+  CHK(setup_gemm(&gph, tc, s->XD, XD_W, rows, H + ED, d->Wpg, H + ED, B, 81, H, 1, 84));
+  CHK(setup_gemm(&gpc, tc, s->XD, XD_W, rows, H, d->Wpg + H, H + ED, B, 81, ED, 1, 84));
+  float* p1 = d->P1;                       // [B,256] pre-activation scratch
+  float* p1a = d->P1 + (long long)B * PD;  // [B,256] layer-1 output
+  for (int t = t_begin; t < t_end; ++t) {
+    const long long r0 = (long long)t * B, r1 = (long long)(t + 1) * B;
+    float* xa_pre = s->XA + r0 * XA_W;
+    const float* pm = d->prenet_masks ? d->prenet_masks + (long long)t * 2 * B * PD : nullptr;
+    const unsigned long long pbase = pm ? 0ull : (unsigned long long)t * B * PD;
+    if (t == 0) {
+      // go frame is all zeros (model.py:241-247): relu(0 W) = 0 -> layer 1 output is 0
+      CHK(t2v_fill(p1a, (long long)B * PD, 0.f, st));
+    } else {
+      CHK(run_gemm(&gp1, r0 - B, p1, st));
+      CHK(t2v_relu_drop_fwd(p1, p1a, PD, B, PD, pm, s->seed, SITE_PRENET0, 0.5f, pbase, st));
+    }
+    CHK(run_gemm(&gp2, 0, p1, st));
+    CHK(t2v_relu_drop_fwd(p1, xa_pre, XA_W, B, PD, pm ? pm + (long long)B * PD : nullptr, s->seed, SITE_PRENET1, 0.5f,
+                          pbase, st));
+    CHK(fwd_step(s, &P, t, st));
+    // mel/gate projection of [h_dec_t | ctx_t]
+    float* o = d->O + r0 * 84;
+    if (tc) {
+      CHK(t2v_gemm_tc_run(&gph.plan, (int)r1, 0, o, d->bpg, st));
+      T2VGemmTcPlan acc = gpc.plan;
+      acc.p.epi_atomic = 1;
+      CHK(t2v_gemm_tc_run(&acc, (int)r0, 0, o, nullptr, st));
+    } else {
+      CHK(t2v_gemm_f32(s->XD + r1 * XD_W + (H + ED), XD_W, 1, d->Wpg, H + ED, 1, o, 84, B, 81, H, 1.f, 0.f, d->bpg, 1, 0,
+                       0, 0, st));
+      CHK(t2v_gemm_f32(s->XD + r0 * XD_W + H, XD_W, 1, d->Wpg + H, H + ED, 1, o, 84, B, 81, ED, 1.f, 1.f, nullptr, 1, 0,
+                       0, 0, st));
+    }
+    if (d->n_frames) {
+      stop_flags_kernel<<<t2v_ceil_div(B, 128), 128, 0, st>>>(o, 84, 80, d->gate_threshold, t, B, d->n_frames);
+      T2V_COUNT_LAUNCH();
+      T2V_LAUNCH_CHECK();
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,335 @@
+// tcgen05 GEMM for sm_100a:  D[M,N] (fp32) = alpha * A[M,K] * B[N,K]^T (+bias[n]) , both operands K-major.
+//
+//   * operands staged global->shared by TMA (cp.async.bulk.tensor.2d, 128B swizzle) through a STAGES-deep
+//     mbarrier ring; one elected thread issues tcgen05.mma (cta_group::1, M=128, N=BN, 32 bytes of K per
+//     instruction); the fp32 accumulator lives in TMEM and is read back with tcgen05.ld by 4 epilogue warps.
+//   * element type: bf16 (kind::f16) or fp32-storage/tf32-math (kind::tf32) -- the kernel is byte-generic.
+//   * "taps": the K loop can walk several row-shifted views of A (k-iteration (tap, chunk) reads A rows
+//     m0+tap*rowshift..), which turns a zero-padded channels-last Conv1d (Postnet / Encoder, reference
+//     model.py:105-177) and the STFT framing (stft.py:91-95) into plain GEMMs without an im2col buffer.
+//   * split-K over blockIdx.z: partial tiles are either stored to D + z*split_stride or atomically added.
+#include "t2v_common.cuh"
+#include "gemm_tc.h"
+
+namespace {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded spin: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU box
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+template <bool kTF32>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (kTF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 B apart (SBO); LBO unused (=1)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version for sm_100
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr int kBM = 128;
+
+template <int BN, int ESIZE, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+  constexpr int BK = 128 / ESIZE;           // elements per 128-byte swizzle row
+  constexpr int A_BYTES = kBM * 128;
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_holder = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+  const int it0 = blockIdx.z * p.iters_per_split;
+  const int n_it = p.iters_per_split;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                 "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        const int g = it0 + it;
+        const int tap = g / p.chunks_per_tap;
+        const int chunk = g - tap * p.chunks_per_tap;
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        tma_load_2d(sa, &tmA, p.a_k0 + chunk * BK, p.a_row0 + m0 + tap * p.a_tap_rowshift, &full[s]);
+        tma_load_2d(sa + A_BYTES, &tmB, p.b_k0 + tap * p.b_tap_stride + chunk * BK, p.b_row0 + n0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A/B format, K-major both, N>>3, M>>4
+      constexpr uint32_t fmt = (ESIZE == 4) ? 2u : 1u;   // TF32 : BF16
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(kBM >> 4) << 24);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_kmajor_sw128_desc(sa);
+        const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // 4 x 32 bytes of K per 128-byte row
+          tc_mma<ESIZE == 4>(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                             (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty[s]);          // frees the smem slot when these MMAs retire
+      }
+      tc_commit(tmem_full);            // accumulator complete
+    }
+  } else {
+    // epilogue warps 2..5: warp w may touch TMEM lanes 32*(w%4) .. +31
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    float* drow = p.D + (long long)blockIdx.z * p.split_stride + (long long)row * p.ldd;
+    const bool vec_ok = ((p.ldd & 3) == 0) && ((((uintptr_t)p.D) & 15) == 0) && ((p.split_stride & 3) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (row < p.M) {
+        const int col0 = n0 + c0;
+        if (!p.epi_atomic && vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[j + 0]) * p.alpha;
+            o.y = __uint_as_float(v[j + 1]) * p.alpha;
+            o.z = __uint_as_float(v[j + 2]) * p.alpha;
+            o.w = __uint_as_float(v[j + 3]) * p.alpha;
+            if (p.bias && blockIdx.z == 0) {
+              o.x += p.bias[col0 + j + 0]; o.y += p.bias[col0 + j + 1];
+              o.z += p.bias[col0 + j + 2]; o.w += p.bias[col0 + j + 3];
+            }
+            *reinterpret_cast<float4*>(drow + col0 + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < p.N) {
+              float o = __uint_as_float(v[j]) * p.alpha;
+              if (p.bias && blockIdx.z == 0) o += p.bias[col];
+              if (p.epi_atomic) atomicAdd(drow + col, o);
+              else drow[col] = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+template <int BN, int ESIZE>
+constexpr int stages_for() { return (BN == 256) ? 4 : (BN == 128 ? 6 : 8); }
+
+template <int BN, int ESIZE>
+int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcParams& p, int splits, cudaStream_t st) {
+  constexpr int STAGES = stages_for<BN, ESIZE>();
+  constexpr int smem = STAGES * (kBM * 128 + BN * 128) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, ESIZE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(t2v_ceil_div(p.M, kBM), t2v_ceil_div(p.N, BN), splits);
+  gemm_tc_kernel<BN, ESIZE, STAGES><<<grid, 192, smem, st>>>(tmA, tmB, p);
+  T2V_COUNT_LAUNCH();
+  T2V_LAUNCH_CHECK();
+  return 0;
+}
+
+int encode_2d(CUtensorMap* map, const void* base, int esize, long long inner, long long rows, long long row_stride_elems,
+              int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) { t2v_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -2; }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(row_stride_elems * esize)};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = (esize == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    t2v_set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld rows=%lld stride=%lld esize=%d)", (int)r,
+                  inner, rows, row_stride_elems, esize);
+    return -3;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// D[M,N] = alpha * sum_{tap,k} A[a_row0 + m + tap*a_tap_rowshift, a_k0 + k] * B[b_row0 + n, b_k0 + tap*b_tap_stride + k] (+ bias[n])
+//   A: `a_rows` x `a_inner` elements, row stride lda; B: `b_rows` rows of `b_inner` elements, row stride ldb.
+//   esize 4 => fp32 storage / tf32 math, esize 2 => bf16.  splits>1: partial sums go to D + z*split_stride
+//   (epi_atomic=0) or are atomically added into D (epi_atomic=1; caller pre-initialises D).
+int t2v_gemm_tc_plan(T2VGemmTcPlan* plan, const void* A, long long lda, long long a_rows, long long a_inner, const void* B,
+                     long long ldb, long long b_rows, long long b_inner, long long ldd, int M, int N, int k_sub, int taps,
+                     int a_tap_rowshift, int b_tap_stride, int a_k0, int b_k0, int esize, int splits,
+                     long long split_stride, int epi_atomic, float alpha, int bn_hint) {
+  T2V_ARG_CHECK(esize == 4 || esize == 2, "esize must be 4 (tf32) or 2 (bf16)");
+  T2V_ARG_CHECK(M > 0 && N > 0 && k_sub > 0 && taps >= 1 && splits >= 1, "shape");
+  T2V_ARG_CHECK((((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "operand base must be 16-byte aligned");
+  T2V_ARG_CHECK((lda * esize) % 16 == 0 && (ldb * esize) % 16 == 0, "row strides must be multiples of 16 bytes");
+  const int BK = 128 / esize;
+  const int cpt = t2v_ceil_div(k_sub, BK);
+  const int total = cpt * taps;
+  T2V_ARG_CHECK(total % splits == 0, "split count must divide the K iteration count");
+  T2V_ARG_CHECK(splits == 1 || epi_atomic || split_stride > 0, "split_stride required for partial stores");
+  int BN = bn_hint;
+  if (BN != 64 && BN != 128 && BN != 256) BN = (N <= 64) ? 64 : 128;
+  int r = encode_2d(&plan->tmA, A, esize, a_inner, a_rows, lda, kBM);
+  if (r) return r;
+  r = encode_2d(&plan->tmB, B, esize, b_inner, b_rows, ldb, BN);
+  if (r) return r;
+  GemmTcParams& p = plan->p;
+  p.D = nullptr; p.ldd = ldd; p.split_stride = split_stride; p.bias = nullptr; p.M = M; p.N = N;
+  p.iters_per_split = total / splits; p.chunks_per_tap = cpt; p.a_tap_rowshift = a_tap_rowshift;
+  p.b_tap_stride = b_tap_stride; p.epi_atomic = epi_atomic; p.alpha = alpha;
+  p.a_row0 = 0; p.b_row0 = 0; p.a_k0 = a_k0; p.b_k0 = b_k0;
+  plan->BN = BN; plan->esize = esize; plan->splits = splits;
+  return 0;
+}
+
+int t2v_gemm_tc_run(const T2VGemmTcPlan* plan, int a_row0, int b_row0, float* D, const float* bias, cudaStream_t stream) {
+  GemmTcParams p = plan->p;
+  p.a_row0 = a_row0; p.b_row0 = b_row0; p.D = D; p.bias = bias;
+  const int BN = plan->BN, splits = plan->splits;
+  if (plan->esize == 4) {
+    if (BN == 64) return launch_gemm_tc<64, 4>(plan->tmA, plan->tmB, p, splits, stream);
+    if (BN == 128) return launch_gemm_tc<128, 4>(plan->tmA, plan->tmB, p, splits, stream);
+    return launch_gemm_tc<256, 4>(plan->tmA, plan->tmB, p, splits, stream);
+  } else {
+    if (BN == 64) return launch_gemm_tc<64, 2>(plan->tmA, plan->tmB, p, splits, stream);
+    if (BN == 128) return launch_gemm_tc<128, 2>(plan->tmA, plan->tmB, p, splits, stream);
+    return launch_gemm_tc<256, 2>(plan->tmA, plan->tmB, p, splits, stream);
+  }
+}
+
+T2V_API int t2v_gemm_tc(const void* A, long long lda, long long a_rows, long long a_inner, const void* B, long long ldb,
+                        long long b_rows, long long b_inner, float* D, long long ldd, const float* bias, int M, int N,
+                        int k_sub, int taps, int a_tap_rowshift, int b_tap_stride, int a_k0, int b_k0, int esize,
+                        int splits, long long split_stride, int epi_atomic, float alpha, int bn_hint,
+                        cudaStream_t stream) {
+  T2VGemmTcPlan plan;
+  int r = t2v_gemm_tc_plan(&plan, A, lda, a_rows, a_inner, B, ldb, b_rows, b_inner, ldd, M, N, k_sub, taps, a_tap_rowshift,
+                           b_tap_stride, a_k0, b_k0, esize, splits, split_stride, epi_atomic, alpha, bn_hint);
+  if (r) return r;
+  return t2v_gemm_tc_run(&plan, 0, 0, D, bias, stream);
+}

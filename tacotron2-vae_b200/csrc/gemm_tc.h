@@ -1,0 +1,30 @@
+// Internal C++ interface of the tcgen05 GEMM (gemm_tc.cu): a "plan" holds the two TMA tensor maps and the launch
+// parameters so that a time loop can re-launch the same GEMM on successive row blocks without re-encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+struct GemmTcParams {
+  float* D;
+  long long ldd;
+  long long split_stride;
+  const float* bias;
+  int M, N;
+  int iters_per_split;
+  int chunks_per_tap;
+  int a_tap_rowshift;
+  int b_tap_stride;
+  int epi_atomic;
+  float alpha;
+  int a_row0, b_row0, a_k0, b_k0;
+};
+struct T2VGemmTcPlan {
+  CUtensorMap tmA, tmB;
+  GemmTcParams p;
+  int BN, esize, splits;
+};
+int t2v_gemm_tc_plan(T2VGemmTcPlan* plan, const void* A, long long lda, long long a_rows, long long a_inner, const void* B,
+                     long long ldb, long long b_rows, long long b_inner, long long ldd, int M, int N, int k_sub, int taps,
+                     int a_tap_rowshift, int b_tap_stride, int a_k0, int b_k0, int esize, int splits,
+                     long long split_stride, int epi_atomic, float alpha, int bn_hint);
+int t2v_gemm_tc_run(const T2VGemmTcPlan* plan, int a_row0, int b_row0, float* D, const float* bias, cudaStream_t stream);

@@ -1,0 +1,656 @@
+// Memory-bound kernels of the hot path: embedding gather, BatchNorm (1d over padded channels-last rows and 2d
+// over NHWC rows -- same kernels), activation+dropout, weight (re)packing, transposes, LSTM / GRU cell pointwise
+// math (forward + backward), broadcast add / reductions.  All activations are fp32, channels-last.
+//
+// Layout convention for Conv1d stacks (Encoder model.py:159-177, Postnet model.py:105-148): a tensor the
+// reference holds as [B, C, T] is stored as rows [B*(T+4), C] with two zero rows on each side of every
+// utterance ("padded channels-last"), so that a k=5/p=2 convolution is a GEMM over overlapping row windows.
+#include "t2v_common.cuh"
+
+namespace {
+
+// valid-row predicate of a padded row space: row r is valid iff lo <= (r % period) < hi
+struct RowSpace {
+  int period, lo, hi;
+  __device__ __forceinline__ bool valid(long long r) const {
+    int x = (int)(r % period);
+    return x >= lo && x < hi;
+  }
+};
+
+// ------------------------------------------------------------------------------------------ embedding
+__global__ void embedding_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
+                                     float* __restrict__ out, int B, int T, int C, int n_symbols) {
+  // one block per (b,t); out row = b*(T+4)+2+t
+  const int bt = blockIdx.x;
+  const int b = bt / T, t = bt % T;
+  long long id = ids[bt];
+  if (id < 0 || id >= n_symbols) __trap();   // nn.Embedding raises on out-of-range ids
+  const float4* src = reinterpret_cast<const float4*>(table + id * C);
+  float4* dst = reinterpret_cast<float4*>(out + ((long long)b * (T + 4) + 2 + t) * C);
+  for (int i = threadIdx.x; i < C / 4; i += blockDim.x) dst[i] = src[i];
+}
+__global__ void embedding_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dout,
+                                     float* __restrict__ dtable, int B, int T, int C) {
+  const int bt = blockIdx.x;
+  const int b = bt / T, t = bt % T;
+  long long id = ids[bt];
+  const float* src = dout + ((long long)b * (T + 4) + 2 + t) * C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dtable + id * C + i, src[i]);
+}
+
+// ------------------------------------------------------------------------------------------ column reductions
+// MODE 0: sum x, sum x^2          (BatchNorm statistics)
+// MODE 1: sum g, sum g*xhat       (BatchNorm backward: dbeta, dgamma), g = act'/dropout-scaled upstream grad
+// MODE 2: sum x only              (bias gradients)
+struct BnCtx {
+  const float* y;        // pre-BN tensor (conv output), rows x C
+  const float* mean;     // [C]
+  const float* invstd;   // [C]
+  const float* gamma;
+  const float* beta;
+  int act;               // 0 none, 1 relu, 2 tanh
+  T2VDrop drop;
+  int T;                 // frames per utterance for the dropout index ((b*C+c)*T+t); rows b*period+lo+t
+};
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  return act == 1 ? fmaxf(v, 0.f) : (act == 2 ? tanhf(v) : v);
+}
+__device__ __forceinline__ float act_grad(float pre, int act) {
+  if (act == 1) return pre > 0.f ? 1.f : 0.f;
+  if (act == 2) { float t = tanhf(pre); return 1.f - t * t; }
+  return 1.f;
+}
+__device__ __forceinline__ uint64_t drop_index(const RowSpace& rs, long long r, int c, int C, int T) {
+  long long b = r / rs.period;
+  int t = (int)(r % rs.period) - rs.lo;
+  return ((uint64_t)b * C + c) * (uint64_t)T + t;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+colreduce_kernel(const float* __restrict__ x, long long rows, int C, RowSpace rs, int rows_per_block, BnCtx ctx,
+                 double* __restrict__ out0, double* __restrict__ out1) {
+  // block (32, 8): x -> channel, y -> row phase
+  __shared__ float s0[8][33], s1[8][33];
+  const int c = blockIdx.y * 32 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    float mean = 0.f, invstd = 0.f, gamma = 0.f, beta = 0.f;
+    if (MODE == 1) { mean = ctx.mean[c]; invstd = ctx.invstd[c]; gamma = ctx.gamma[c]; beta = ctx.beta[c]; }
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      if (!rs.valid(r)) continue;
+      const float v = x[r * C + c];
+      if (MODE == 0) { a0 += v; a1 += v * v; }
+      else if (MODE == 2) { a0 += v; }
+      else {
+        const float xhat = (ctx.y[r * C + c] - mean) * invstd;
+        const float pre = gamma * xhat + beta;
+        const float g = v * act_grad(pre, ctx.act) * t2v_keep_scale(ctx.drop, drop_index(rs, r, c, C, ctx.T));
+        a0 += g; a1 += g * xhat;
+      }
+    }
+  }
+  s0[threadIdx.y][threadIdx.x] = a0;
+  s1[threadIdx.y][threadIdx.x] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t0 += s0[i][threadIdx.x]; t1 += s1[i][threadIdx.x]; }
+    atomicAdd(out0 + c, (double)t0);
+    if (MODE != 2) atomicAdd(out1 + c, (double)t1);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double n, int C,
+                                   float eps, float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches_tracked) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const double m = sum[c] / n;
+    double var = sumsq[c] / n - m * m;
+    if (var < 0) var = 0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      const double unbiased = var * (n / (n > 1 ? n - 1 : 1));
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+}
+__global__ void bn_eval_prepare_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                       int C, float eps, float* __restrict__ mean, float* __restrict__ invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { mean[c] = running_mean[c]; invstd[c] = rsqrtf(running_var[c] + eps); }
+}
+
+// out = dropout(act(gamma*(y-mean)*invstd+beta)) on valid rows, 0 on pad rows
+__global__ void bn_act_fwd_kernel(const float* __restrict__ y, float* __restrict__ out, long long rows, int C,
+                                  RowSpace rs, BnCtx ctx) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index
+  const long long total4 = rows * C / 4;
+  if (i4 >= total4) return;
+  const long long r = (i4 * 4) / C;
+  const int c = (int)((i4 * 4) % C);
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rs.valid(r)) {
+    const float4 v = reinterpret_cast<const float4*>(y)[i4];
+    float in[4] = {v.x, v.y, v.z, v.w}, res[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float pre = ctx.gamma[c + j] * ((in[j] - ctx.mean[c + j]) * ctx.invstd[c + j]) + ctx.beta[c + j];
+      res[j] = act_fwd(pre, ctx.act) * t2v_keep_scale(ctx.drop, drop_index(rs, r, c + j, C, ctx.T));
+    }
+    o = make_float4(res[0], res[1], res[2], res[3]);
+  }
+  reinterpret_cast<float4*>(out)[i4] = o;
+}
+
+// training-mode BN backward (given dgamma/dbeta sums): dy = gamma*invstd*(g - dbeta/n - xhat*dgamma/n); 0 on pad rows
+// eval-mode (use_batch_stats=0): dy = gamma*invstd*g
+__global__ void bn_act_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dy, long long rows, int C,
+                                  RowSpace rs, BnCtx ctx, const double* __restrict__ dbeta_sum,
+                                  const double* __restrict__ dgamma_sum, double n, int use_batch_stats) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total4 = rows * C / 4;
+  if (i4 >= total4) return;
+  const long long r = (i4 * 4) / C;
+  const int c = (int)((i4 * 4) % C);
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rs.valid(r)) {
+    const float4 gv = reinterpret_cast<const float4*>(dout)[i4];
+    const float4 yv = reinterpret_cast<const float4*>(ctx.y)[i4];
+    float gin[4] = {gv.x, gv.y, gv.z, gv.w}, yin[4] = {yv.x, yv.y, yv.z, yv.w}, res[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float invstd = ctx.invstd[c + j], gamma = ctx.gamma[c + j];
+      const float xhat = (yin[j] - ctx.mean[c + j]) * invstd;
+      const float pre = gamma * xhat + ctx.beta[c + j];
+      const float g = gin[j] * act_grad(pre, ctx.act) * t2v_keep_scale(ctx.drop, drop_index(rs, r, c + j, C, ctx.T));
+      if (use_batch_stats)
+        res[j] = gamma * invstd * (g - (float)(dbeta_sum[c + j] / n) - xhat * (float)(dgamma_sum[c + j] / n));
+      else
+        res[j] = gamma * invstd * g;
+    }
+    o = make_float4(res[0], res[1], res[2], res[3]);
+  }
+  reinterpret_cast<float4*>(dy)[i4] = o;
+}
+
+__global__ void double_to_float_acc_kernel(const double* __restrict__ src, float* __restrict__ dst, int n, float beta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (beta != 0.f ? beta * dst[i] : 0.f) + (float)src[i];
+}
+
+// ------------------------------------------------------------------------------------------ layout helpers
+// generic strided 2-level copy: dst[r*d_rs + c] = src[r*s_rs + c*s_cs] (+ optional accumulate)
+__global__ void copy2d_kernel(const float* __restrict__ src, long long s_rs, long long s_cs, float* __restrict__ dst,
+                              long long d_rs, long long rows, int cols, float beta) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  const int c = (int)(i % cols);
+  const float v = src[r * s_rs + c * s_cs];
+  float* d = dst + r * d_rs + c;
+  *d = (beta != 0.f) ? beta * (*d) + v : v;
+}
+// tiled transpose: out[c*o_ld + r] = in[r*i_ld + c]
+__global__ void transpose_kernel(const float* __restrict__ in, long long i_ld, float* __restrict__ out, long long o_ld,
+                                 long long rows, int cols) {
+  __shared__ float tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const long long r = r0 + j;
+    const int c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? in[r * i_ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j;
+    const long long r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(long long)c * o_ld + r] = tile[threadIdx.x][j];
+  }
+}
+// Conv1d weight [Co,Ci,K] -> tap-major [Co, K*Ci] (flip=0) or dgrad form [Ci, K*Co] with taps reversed (flip=1)
+__global__ void conv1d_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int Co, int Ci, int K, int flip) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Co * Ci * K) return;
+  const int k = (int)(i % K);
+  const int ci = (int)((i / K) % Ci);
+  const int co = (int)(i / ((long long)K * Ci));
+  if (!flip) out[((long long)co * K + k) * Ci + ci] = w[i];
+  else out[((long long)ci * K + (K - 1 - k)) * Co + co] = w[i];
+}
+// gradient in tap-major form [Co, K*Ci] -> accumulate into [Co,Ci,K]
+__global__ void conv1d_unpack_grad_kernel(const float* __restrict__ gk, float* __restrict__ gw, int Co, int Ci, int K,
+                                          float beta) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Co * Ci * K) return;
+  const int k = (int)(i % K);
+  const int ci = (int)((i / K) % Ci);
+  const int co = (int)(i / ((long long)K * Ci));
+  const float v = gk[((long long)co * K + k) * Ci + ci];
+  gw[i] = (beta != 0.f ? beta * gw[i] : 0.f) + v;
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, float a, float* __restrict__ y, float b, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * x[i] + (b != 0.f ? b * y[i] : 0.f);
+}
+// y[r, c] += v[b(r), c] where b(r) = r / rows_per_batch (style broadcast-add, model.py:536-537); valid rows only
+__global__ void bcast_add_rows_kernel(float* __restrict__ y, const float* __restrict__ v, long long rows, int C,
+                                      int rows_per_batch) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = (int)(i % C);
+  y[i] += v[(r / rows_per_batch) * C + c];
+}
+// out[b, c] = sum_{r in batch b} x[r, c]
+__global__ void sum_rows_per_batch_kernel(const float* __restrict__ x, float* __restrict__ out, int rows_per_batch,
+                                          int C, float beta) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    const float* p = x + (long long)b * rows_per_batch * C + c;
+    for (int r = 0; r < rows_per_batch; ++r) a += p[(long long)r * C];
+    float* o = out + (long long)b * C + c;
+    *o = (beta != 0.f ? beta * (*o) : 0.f) + a;
+  }
+}
+// sums `n_parts` partial buffers (stride part_stride) into dst (+ optional second/third plain sources)
+__global__ void sum_parts_kernel(const float* __restrict__ parts, int n_parts, long long part_stride,
+                                 float* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int p = 0; p < n_parts; ++p) a += parts[p * part_stride + i];
+  dst[i] = a;
+}
+// relu + dropout pointwise (Prenet, model.py:101): out = relu(x) * keep/(1-p); logical idx = row*C+c + idx_base
+__global__ void relu_drop_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, long long o_rs,
+                                     long long rows, int C, T2VDrop drop, unsigned long long idx_base) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = (int)(i % C);
+  out[r * o_rs + c] = fmaxf(x[i], 0.f) * t2v_keep_scale(drop, idx_base + (uint64_t)i);
+}
+// dx = dout * 1[x>0] * keep/(1-p)
+__global__ void relu_drop_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, long long do_rs,
+                                     float* __restrict__ dx, long long rows, int C, T2VDrop drop,
+                                     unsigned long long idx_base) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = (int)(i % C);
+  dx[i] = (x[i] > 0.f) ? dout[r * do_rs + c] * t2v_keep_scale(drop, idx_base + (uint64_t)i) : 0.f;
+}
+__global__ void materialize_mask_kernel(float* __restrict__ out, long long n, T2VDrop drop, unsigned long long idx_base) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (t2v_uniform(drop.seed, drop.site, idx_base + (uint64_t)i) >= drop.p) ? 1.f : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------ LSTM / GRU cells
+struct LstmFwdArgs {
+  const float* parts; int n_parts; long long part_stride; long long parts_rs;   // gate pre-activations [B,4H] x n_parts
+  const float* pre; long long pre_rs;                                           // optional extra [B,4H]
+  const float* b1; const float* b2;                                             // [4H] optional
+  const float* c_prev; long long cprev_rs;
+  float* h_out; long long hout_rs;        // post-dropout h (nullable)
+  float* h_out2; long long hout2_rs;      // second destination of h (nullable)
+  float* c_out; long long cout_rs;        // post-dropout c
+  float* gates_save;                      // [B,4H] activated i,f,g,o (nullable)
+  float* cpre_save;                       // [B,H] c' before dropout (nullable)
+  float* seq_out; long long seq_rs;       // packed mode: out[b] row pointer base (h or 0)
+  T2VDrop drop_h, drop_c; unsigned long long drop_base;
+  const long long* lens; int t;           // packed mode (nullable lens => every row live)
+  int B, H;
+};
+__global__ void lstm_pointwise_fwd_kernel(LstmFwdArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.B * a.H) return;
+  const int b = i / a.H, j = i % a.H;
+  const bool live = (a.lens == nullptr) || (a.t < a.lens[b]);
+  if (!live) {
+    if (a.seq_out) a.seq_out[b * a.seq_rs + j] = 0.f;
+    if (a.gates_save) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) a.gates_save[(long long)b * 4 * a.H + g * a.H + j] = 0.f;
+    }
+    if (a.cpre_save) a.cpre_save[(long long)b * a.H + j] = 0.f;
+    return;
+  }
+  float g4[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = g * a.H + j;
+    float v = 0.f;
+    for (int p = 0; p < a.n_parts; ++p) v += a.parts[p * a.part_stride + b * a.parts_rs + col];
+    if (a.pre) v += a.pre[b * a.pre_rs + col];
+    if (a.b1) v += a.b1[col];
+    if (a.b2) v += a.b2[col];
+    g4[g] = v;
+  }
+  const float ig = t2v_sigmoid(g4[0]), fg = t2v_sigmoid(g4[1]), gg = tanhf(g4[2]), og = t2v_sigmoid(g4[3]);
+  const float cp = a.c_prev[b * a.cprev_rs + j];
+  const float c2 = fg * cp + ig * gg;
+  const float h2 = og * tanhf(c2);
+  const uint64_t idx = a.drop_base + (uint64_t)b * a.H + j;
+  const float hd = h2 * t2v_keep_scale(a.drop_h, idx);
+  const float cd = c2 * t2v_keep_scale(a.drop_c, idx);
+  if (a.h_out) a.h_out[b * a.hout_rs + j] = hd;
+  if (a.h_out2) a.h_out2[b * a.hout2_rs + j] = hd;
+  a.c_out[b * a.cout_rs + j] = cd;
+  if (a.seq_out) a.seq_out[b * a.seq_rs + j] = hd;
+  if (a.gates_save) {
+    float* gs = a.gates_save + (long long)b * 4 * a.H + j;
+    gs[0] = ig; gs[a.H] = fg; gs[2 * a.H] = gg; gs[3 * a.H] = og;
+  }
+  if (a.cpre_save) a.cpre_save[(long long)b * a.H + j] = c2;
+}
+
+struct LstmBwdArgs {
+  const float* dh1; long long dh1_rs;     // grads wrt post-dropout h (up to 3 sources, nullable)
+  const float* dh2; long long dh2_rs;
+  const float* dh3; long long dh3_rs;
+  float* dc;                              // [B,H] in: grad wrt post-dropout c ; out: grad wrt c_prev (in place)
+  const float* gates_save; const float* cpre_save;
+  const float* c_prev; long long cprev_rs;
+  float* dgates; long long dg_rs;         // [B,4H] pre-activation grads
+  T2VDrop drop_h, drop_c; unsigned long long drop_base;
+  const long long* lens; int t;
+  int B, H;
+};
+__global__ void lstm_pointwise_bwd_kernel(LstmBwdArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.B * a.H) return;
+  const int b = i / a.H, j = i % a.H;
+  float* dg = a.dgates + b * a.dg_rs + j;
+  const bool live = (a.lens == nullptr) || (a.t < a.lens[b]);
+  if (!live) {   // dead step of a packed sequence: no dependence on anything
+    dg[0] = 0.f; dg[a.H] = 0.f; dg[2 * a.H] = 0.f; dg[3 * a.H] = 0.f;
+    return;      // dc (state gradient) passes through unchanged
+  }
+  float dh = 0.f;
+  if (a.dh1) dh += a.dh1[b * a.dh1_rs + j];
+  if (a.dh2) dh += a.dh2[b * a.dh2_rs + j];
+  if (a.dh3) dh += a.dh3[b * a.dh3_rs + j];
+  const uint64_t idx = a.drop_base + (uint64_t)b * a.H + j;
+  dh *= t2v_keep_scale(a.drop_h, idx);
+  const float* gs = a.gates_save + (long long)b * 4 * a.H + j;
+  const float ig = gs[0], fg = gs[a.H], gg = gs[2 * a.H], og = gs[3 * a.H];
+  const float c2 = a.cpre_save[(long long)b * a.H + j];
+  const float tc = tanhf(c2);
+  float dc = a.dc[(long long)b * a.H + j] * t2v_keep_scale(a.drop_c, idx) + dh * og * (1.f - tc * tc);
+  const float cp = a.c_prev[b * a.cprev_rs + j];
+  dg[0] = dc * gg * ig * (1.f - ig);
+  dg[a.H] = dc * cp * fg * (1.f - fg);
+  dg[2 * a.H] = dc * ig * (1.f - gg * gg);
+  dg[3 * a.H] = dh * tc * og * (1.f - og);
+  a.dc[(long long)b * a.H + j] = dc * fg;
+}
+
+// GRU cell (modules.py:60-62 / nn.GRU): gi = x W_ih^T (+b_ih), gh = h W_hh^T (+b_hh) given as [B,3H] each
+__global__ void gru_pointwise_fwd_kernel(const float* __restrict__ gi, long long gi_rs, const float* __restrict__ gh,
+                                         const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                         const float* __restrict__ h_prev, float* __restrict__ h_out,
+                                         float* __restrict__ save /* [B,4H]: r,z,n,ghn */, int B, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, j = i % H;
+  const float* gib = gi + (long long)b * gi_rs;
+  const float* ghb = gh + (long long)b * 3 * H;
+  const float r = t2v_sigmoid(gib[j] + b_ih[j] + ghb[j] + b_hh[j]);
+  const float z = t2v_sigmoid(gib[H + j] + b_ih[H + j] + ghb[H + j] + b_hh[H + j]);
+  const float ghn = ghb[2 * H + j] + b_hh[2 * H + j];
+  const float n = tanhf(gib[2 * H + j] + b_ih[2 * H + j] + r * ghn);
+  const float hp = h_prev[i];
+  h_out[i] = (1.f - z) * n + z * hp;
+  float* s = save + (long long)b * 4 * H + j;
+  s[0] = r; s[H] = z; s[2 * H] = n; s[3 * H] = ghn;
+}
+// in: dh [B,H] (grad wrt h_out).  out: dgi [B,3H], dgh [B,3H], dh_prev_direct [B,H] (= dh*z; caller adds dgh*W_hh)
+__global__ void gru_pointwise_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ save,
+                                         const float* __restrict__ h_prev, float* __restrict__ dgi, long long dgi_rs,
+                                         float* __restrict__ dgh, float* __restrict__ dh_prev, int B, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, j = i % H;
+  const float* s = save + (long long)b * 4 * H + j;
+  const float r = s[0], z = s[H], n = s[2 * H], ghn = s[3 * H];
+  const float d = dh[i];
+  const float hp = h_prev[i];
+  const float dn = d * (1.f - z) * (1.f - n * n);
+  const float dz = d * (hp - n) * z * (1.f - z);
+  const float dr = dn * ghn * r * (1.f - r);
+  float* a = dgi + (long long)b * dgi_rs + j;
+  float* c = dgh + (long long)b * 3 * H + j;
+  a[0] = dr; a[H] = dz; a[2 * H] = dn;
+  c[0] = dr; c[H] = dz; c[2 * H] = dn * r;
+  dh_prev[i] = d * z;
+}
+
+// VAE head (modules.py:16-22): z = mu + eps*exp(.5*logvar) (training) ; mulv = [mu | logvar] rows of 64
+__global__ void vae_reparam_fwd_kernel(const float* __restrict__ mulv, const float* __restrict__ eps,
+                                       float* __restrict__ z, int B, int Z, int training) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Z) return;
+  const int b = i / Z, j = i % Z;
+  const float mu = mulv[b * 2 * Z + j], lv = mulv[b * 2 * Z + Z + j];
+  z[i] = training ? (eps ? eps[i] : 0.f) * expf(0.5f * lv) + mu : mu;
+}
+// dmulv = [dmu_ext + dz | dlogvar_ext + dz*eps*.5*exp(.5 lv)]
+__global__ void vae_reparam_bwd_kernel(const float* __restrict__ mulv, const float* __restrict__ eps,
+                                       const float* __restrict__ dz, const float* __restrict__ dmu_ext,
+                                       const float* __restrict__ dlv_ext, float* __restrict__ dmulv, int B, int Z,
+                                       int training) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Z) return;
+  const int b = i / Z, j = i % Z;
+  const float lv = mulv[b * 2 * Z + Z + j];
+  const float e = (training && eps) ? eps[i] : 0.f;
+  dmulv[b * 2 * Z + j] = dz[i] + (dmu_ext ? dmu_ext[i] : 0.f);
+  dmulv[b * 2 * Z + Z + j] = (training ? dz[i] * e * 0.5f * expf(0.5f * lv) : 0.f) + (dlv_ext ? dlv_ext[i] : 0.f);
+}
+
+inline RowSpace mk_rs(int period, int lo, int hi) { RowSpace r; r.period = period; r.lo = lo; r.hi = hi; return r; }
+inline T2VDrop mk_drop(const float* mask, unsigned long long seed, unsigned int site, float p) {
+  T2VDrop d; d.mask = mask; d.seed = seed; d.site = site; d.p = p; return d;
+}
+inline BnCtx mk_ctx(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                    int act, T2VDrop d, int T) {
+  BnCtx c; c.y = y; c.mean = mean; c.invstd = invstd; c.gamma = gamma; c.beta = beta; c.act = act; c.drop = d; c.T = T;
+  return c;
+}
+inline unsigned grid1d(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace
+
+#define LAUNCH_END() do { T2V_COUNT_LAUNCH(); T2V_LAUNCH_CHECK(); return 0; } while (0)
+
+T2V_API int t2v_embedding_fwd(const long long* ids, const float* table, float* out, int B, int T, int C, int n_symbols,
+                              cudaStream_t st) {
+  T2V_ARG_CHECK(C % 4 == 0 && B > 0 && T > 0, "shape");
+  embedding_fwd_kernel<<<B * T, 128, 0, st>>>(ids, table, out, B, T, C, n_symbols);
+  LAUNCH_END();
+}
+T2V_API int t2v_embedding_bwd(const long long* ids, const float* dout, float* dtable, int B, int T, int C, cudaStream_t st) {
+  embedding_bwd_kernel<<<B * T, 128, 0, st>>>(ids, dout, dtable, B, T, C);
+  LAUNCH_END();
+}
+
+// column sums over valid rows: mode 0 -> (sum, sumsq) ; mode 2 -> (sum).  out buffers are double[C], pre-zeroed by caller.
+T2V_API int t2v_col_stats(const float* x, long long rows, int C, int period, int lo, int hi, int mode, double* out0,
+                          double* out1, cudaStream_t st) {
+  T2V_ARG_CHECK(mode == 0 || mode == 2, "mode");
+  const int rpb = 256;
+  dim3 grid(t2v_ceil_div(rows, rpb), t2v_ceil_div(C, 32)), block(32, 8);
+  BnCtx ctx; memset(&ctx, 0, sizeof(ctx));
+  if (mode == 0) colreduce_kernel<0><<<grid, block, 0, st>>>(x, rows, C, mk_rs(period, lo, hi), rpb, ctx, out0, out1);
+  else colreduce_kernel<2><<<grid, block, 0, st>>>(x, rows, C, mk_rs(period, lo, hi), rpb, ctx, out0, out1);
+  LAUNCH_END();
+}
+T2V_API int t2v_bn_finalize(const double* sum, const double* sumsq, double n, int C, float eps, float momentum,
+                            float* mean, float* invstd, float* running_mean, float* running_var,
+                            long long* num_batches_tracked, cudaStream_t st) {
+  bn_finalize_kernel<<<t2v_ceil_div(C, 128), 128, 0, st>>>(sum, sumsq, n, C, eps, momentum, mean, invstd, running_mean,
+                                                         running_var, num_batches_tracked);
+  LAUNCH_END();
+}
+T2V_API int t2v_bn_eval_prepare(const float* running_mean, const float* running_var, int C, float eps, float* mean,
+                                float* invstd, cudaStream_t st) {
+  bn_eval_prepare_kernel<<<t2v_ceil_div(C, 128), 128, 0, st>>>(running_mean, running_var, C, eps, mean, invstd);
+  LAUNCH_END();
+}
+T2V_API int t2v_bn_act_fwd(const float* y, float* out, long long rows, int C, int period, int lo, int hi,
+                           const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
+                           const float* drop_mask, unsigned long long seed, unsigned int site, float p, int T,
+                           cudaStream_t st) {
+  T2V_ARG_CHECK(C % 4 == 0, "C must be a multiple of 4");
+  BnCtx ctx = mk_ctx(y, mean, invstd, gamma, beta, act, mk_drop(drop_mask, seed, site, p), T);
+  bn_act_fwd_kernel<<<grid1d(rows * C / 4, 256), 256, 0, st>>>(y, out, rows, C, mk_rs(period, lo, hi), ctx);
+  LAUNCH_END();
+}
+// pass 1 of BN backward: dbeta_sum / dgamma_sum (double[C], pre-zeroed)
+T2V_API int t2v_bn_act_bwd_reduce(const float* dout, const float* y, long long rows, int C, int period, int lo, int hi,
+                                  const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
+                                  const float* drop_mask, unsigned long long seed, unsigned int site, float p, int T,
+                                  double* dbeta_sum, double* dgamma_sum, cudaStream_t st) {
+  const int rpb = 256;
+  dim3 grid(t2v_ceil_div(rows, rpb), t2v_ceil_div(C, 32)), block(32, 8);
+  BnCtx ctx = mk_ctx(y, mean, invstd, gamma, beta, act, mk_drop(drop_mask, seed, site, p), T);
+  colreduce_kernel<1><<<grid, block, 0, st>>>(dout, rows, C, mk_rs(period, lo, hi), rpb, ctx, dbeta_sum, dgamma_sum);
+  LAUNCH_END();
+}
+T2V_API int t2v_bn_act_bwd_apply(const float* dout, const float* y, float* dy, long long rows, int C, int period, int lo,
+                                 int hi, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                 int act, const float* drop_mask, unsigned long long seed, unsigned int site, float p,
+                                 int T, const double* dbeta_sum, const double* dgamma_sum, double n,
+                                 int use_batch_stats, cudaStream_t st) {
+  T2V_ARG_CHECK(C % 4 == 0, "C must be a multiple of 4");
+  BnCtx ctx = mk_ctx(y, mean, invstd, gamma, beta, act, mk_drop(drop_mask, seed, site, p), T);
+  bn_act_bwd_kernel<<<grid1d(rows * C / 4, 256), 256, 0, st>>>(dout, dy, rows, C, mk_rs(period, lo, hi), ctx, dbeta_sum,
+                                                              dgamma_sum, n, use_batch_stats);
+  LAUNCH_END();
+}
+T2V_API int t2v_double_to_float(const double* src, float* dst, int n, float beta, cudaStream_t st) {
+  double_to_float_acc_kernel<<<t2v_ceil_div(n, 128), 128, 0, st>>>(src, dst, n, beta);
+  LAUNCH_END();
+}
+T2V_API int t2v_copy2d(const float* src, long long s_rs, long long s_cs, float* dst, long long d_rs, long long rows,
+                       int cols, float beta, cudaStream_t st) {
+  copy2d_kernel<<<grid1d(rows * cols, 256), 256, 0, st>>>(src, s_rs, s_cs, dst, d_rs, rows, cols, beta);
+  LAUNCH_END();
+}
+T2V_API int t2v_transpose(const float* in, long long i_ld, float* out, long long o_ld, long long rows, int cols,
+                          cudaStream_t st) {
+  dim3 grid(t2v_ceil_div(rows, 32), t2v_ceil_div(cols, 32)), block(32, 8);
+  T2V_ARG_CHECK(grid.y <= 65535, "cols too large");
+  transpose_kernel<<<grid, block, 0, st>>>(in, i_ld, out, o_ld, rows, cols);
+  LAUNCH_END();
+}
+T2V_API int t2v_conv1d_pack(const float* w, float* out, int Co, int Ci, int K, int flip, cudaStream_t st) {
+  conv1d_pack_kernel<<<grid1d((long long)Co * Ci * K, 256), 256, 0, st>>>(w, out, Co, Ci, K, flip);
+  LAUNCH_END();
+}
+T2V_API int t2v_conv1d_unpack_grad(const float* gk, float* gw, int Co, int Ci, int K, float beta, cudaStream_t st) {
+  conv1d_unpack_grad_kernel<<<grid1d((long long)Co * Ci * K, 256), 256, 0, st>>>(gk, gw, Co, Ci, K, beta);
+  LAUNCH_END();
+}
+T2V_API int t2v_axpby(const float* x, float a, float* y, float b, long long n, cudaStream_t st) {
+  axpby_kernel<<<grid1d(n, 256), 256, 0, st>>>(x, a, y, b, n);
+  LAUNCH_END();
+}
+T2V_API int t2v_bcast_add_rows(float* y, const float* v, long long rows, int C, int rows_per_batch, cudaStream_t st) {
+  bcast_add_rows_kernel<<<grid1d(rows * C, 256), 256, 0, st>>>(y, v, rows, C, rows_per_batch);
+  LAUNCH_END();
+}
+T2V_API int t2v_sum_rows_per_batch(const float* x, float* out, int B, int rows_per_batch, int C, float beta,
+                                   cudaStream_t st) {
+  sum_rows_per_batch_kernel<<<B, 256, 0, st>>>(x, out, rows_per_batch, C, beta);
+  LAUNCH_END();
+}
+T2V_API int t2v_sum_parts(const float* parts, int n_parts, long long part_stride, float* dst, long long n, cudaStream_t st) {
+  sum_parts_kernel<<<grid1d(n, 256), 256, 0, st>>>(parts, n_parts, part_stride, dst, n);
+  LAUNCH_END();
+}
+T2V_API int t2v_relu_drop_fwd(const float* x, float* out, long long o_rs, long long rows, int C, const float* mask,
+                              unsigned long long seed, unsigned int site, float p, unsigned long long idx_base,
+                              cudaStream_t st) {
+  relu_drop_fwd_kernel<<<grid1d(rows * C, 256), 256, 0, st>>>(x, out, o_rs, rows, C, mk_drop(mask, seed, site, p), idx_base);
+  LAUNCH_END();
+}
+T2V_API int t2v_relu_drop_bwd(const float* x, const float* dout, long long do_rs, float* dx, long long rows, int C,
+                              const float* mask, unsigned long long seed, unsigned int site, float p,
+                              unsigned long long idx_base, cudaStream_t st) {
+  relu_drop_bwd_kernel<<<grid1d(rows * C, 256), 256, 0, st>>>(x, dout, do_rs, dx, rows, C, mk_drop(mask, seed, site, p),
+                                                             idx_base);
+  LAUNCH_END();
+}
+T2V_API int t2v_materialize_mask(float* out, long long n, unsigned long long seed, unsigned int site, float p,
+                                 unsigned long long idx_base, cudaStream_t st) {
+  materialize_mask_kernel<<<grid1d(n, 256), 256, 0, st>>>(out, n, mk_drop(nullptr, seed, site, p), idx_base);
+  LAUNCH_END();
+}
+
+T2V_API int t2v_lstm_pointwise_fwd(const float* parts, int n_parts, long long part_stride, long long parts_rs,
+                                   const float* pre, long long pre_rs, const float* b1, const float* b2,
+                                   const float* c_prev, long long cprev_rs, float* h_out, long long hout_rs,
+                                   float* h_out2, long long hout2_rs, float* c_out, long long cout_rs,
+                                   float* gates_save, float* cpre_save, float* seq_out, long long seq_rs,
+                                   const float* mask_h, const float* mask_c, unsigned long long seed,
+                                   unsigned int site_h, unsigned int site_c, float p, unsigned long long drop_base,
+                                   const long long* lens, int t, int B, int H, cudaStream_t st) {
+  LstmFwdArgs a;
+  a.parts = parts; a.n_parts = n_parts; a.part_stride = part_stride; a.parts_rs = parts_rs;
+  a.pre = pre; a.pre_rs = pre_rs; a.b1 = b1; a.b2 = b2; a.c_prev = c_prev; a.cprev_rs = cprev_rs;
+  a.h_out = h_out; a.hout_rs = hout_rs; a.h_out2 = h_out2; a.hout2_rs = hout2_rs; a.c_out = c_out; a.cout_rs = cout_rs;
+  a.gates_save = gates_save; a.cpre_save = cpre_save; a.seq_out = seq_out; a.seq_rs = seq_rs;
+  a.drop_h = mk_drop(mask_h, seed, site_h, p); a.drop_c = mk_drop(mask_c, seed, site_c, p); a.drop_base = drop_base;
+  a.lens = lens; a.t = t; a.B = B; a.H = H;
+  lstm_pointwise_fwd_kernel<<<grid1d((long long)B * H, 256), 256, 0, st>>>(a);
+  LAUNCH_END();
+}
+T2V_API int t2v_lstm_pointwise_bwd(const float* dh1, long long dh1_rs, const float* dh2, long long dh2_rs,
+                                   const float* dh3, long long dh3_rs, float* dc, const float* gates_save,
+                                   const float* cpre_save, const float* c_prev, long long cprev_rs, float* dgates,
+                                   long long dg_rs, const float* mask_h, const float* mask_c, unsigned long long seed,
+                                   unsigned int site_h, unsigned int site_c, float p, unsigned long long drop_base,
+                                   const long long* lens, int t, int B, int H, cudaStream_t st) {
+  LstmBwdArgs a;
+  a.dh1 = dh1; a.dh1_rs = dh1_rs; a.dh2 = dh2; a.dh2_rs = dh2_rs; a.dh3 = dh3; a.dh3_rs = dh3_rs; a.dc = dc;
+  a.gates_save = gates_save; a.cpre_save = cpre_save; a.c_prev = c_prev; a.cprev_rs = cprev_rs; a.dgates = dgates;
+  a.dg_rs = dg_rs; a.drop_h = mk_drop(mask_h, seed, site_h, p); a.drop_c = mk_drop(mask_c, seed, site_c, p);
+  a.drop_base = drop_base; a.lens = lens; a.t = t; a.B = B; a.H = H;
+  lstm_pointwise_bwd_kernel<<<grid1d((long long)B * H, 256), 256, 0, st>>>(a);
+  LAUNCH_END();
+}
+T2V_API int t2v_gru_pointwise_fwd(const float* gi, long long gi_rs, const float* gh, const float* b_ih, const float* b_hh,
+                                  const float* h_prev, float* h_out, float* save, int B, int H, cudaStream_t st) {
+  gru_pointwise_fwd_kernel<<<grid1d((long long)B * H, 256), 256, 0, st>>>(gi, gi_rs, gh, b_ih, b_hh, h_prev, h_out, save, B, H);
+  LAUNCH_END();
+}
+T2V_API int t2v_gru_pointwise_bwd(const float* dh, const float* save, const float* h_prev, float* dgi, long long dgi_rs,
+                                  float* dgh, float* dh_prev, int B, int H, cudaStream_t st) {
+  gru_pointwise_bwd_kernel<<<grid1d((long long)B * H, 256), 256, 0, st>>>(dh, save, h_prev, dgi, dgi_rs, dgh, dh_prev, B, H);
+  LAUNCH_END();
+}
+T2V_API int t2v_vae_reparam_fwd(const float* mulv, const float* eps, float* z, int B, int Z, int training, cudaStream_t st) {
+  vae_reparam_fwd_kernel<<<grid1d((long long)B * Z, 128), 128, 0, st>>>(mulv, eps, z, B, Z, training);
+  LAUNCH_END();
+}
+T2V_API int t2v_vae_reparam_bwd(const float* mulv, const float* eps, const float* dz, const float* dmu_ext,
+                                const float* dlv_ext, float* dmulv, int B, int Z, int training, cudaStream_t st) {
+  vae_reparam_bwd_kernel<<<grid1d((long long)B * Z, 128), 128, 0, st>>>(mulv, eps, dz, dmu_ext, dlv_ext, dmulv, B, Z, training);
+  LAUNCH_END();
+}

@@ -1,0 +1,102 @@
+// Shared helpers for the t2v_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define T2V_API extern "C" __attribute__((visibility("default")))
+
+// ---- error reporting: 0 ok, <0 argument error (nothing launched), >0 cudaError_t passthrough ----
+void t2v_set_error(const char* fmt, ...);
+#define T2V_ARG_CHECK(cond, msg)                                                    \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      t2v_set_error("%s:%d: argument check failed: %s (%s)", __FILE__, __LINE__, #cond, msg); \
+      return -1;                                                                    \
+    }                                                                               \
+  } while (0)
+#define T2V_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      t2v_set_error("%s:%d: CUDA error %d: %s", __FILE__, __LINE__, (int)e__, cudaGetErrorString(e__)); \
+      return (int)e__;                                                              \
+    }                                                                               \
+  } while (0)
+#define T2V_CUDA_CHECK(expr)                                                        \
+  do {                                                                              \
+    cudaError_t e__ = (expr);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      t2v_set_error("%s:%d: %s -> CUDA error %d: %s", __FILE__, __LINE__, #expr, (int)e__, cudaGetErrorString(e__)); \
+      return (int)e__;                                                              \
+    }                                                                               \
+  } while (0)
+
+// counts kernel launches made by this library (bench.py reports it as gpu_launches)
+extern unsigned long long g_t2v_launches;
+#define T2V_COUNT_LAUNCH() (++g_t2v_launches)
+
+static inline int t2v_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- counter-based dropout RNG: keep(seed, site, idx) is a pure function, so forward, backward and
+// the mask-materialisation kernel used by the tests all see the same bits ----
+__host__ __device__ __forceinline__ uint32_t t2v_hash32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return (uint32_t)(x >> 11);
+}
+// uniform in [0,1) with 24 bits
+__host__ __device__ __forceinline__ float t2v_uniform(uint64_t seed, uint32_t site, uint64_t idx) {
+  uint64_t key = seed * 0x9E3779B97F4A7C15ULL + ((uint64_t)site << 40) + idx;
+  return (float)(t2v_hash32(key) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+}
+
+// A dropout site: either an explicit keep-mask (float 0/1, element strides given by the kernel) or the RNG.
+struct T2VDrop {
+  const float* mask;   // nullable
+  uint64_t seed;
+  uint32_t site;
+  float p;             // drop probability; p<=0 => identity
+};
+__device__ __forceinline__ float t2v_keep_scale(const T2VDrop& d, uint64_t logical_idx) {
+  if (d.p <= 0.f) return 1.f;
+  float keep = d.mask ? d.mask[logical_idx] : (t2v_uniform(d.seed, d.site, logical_idx) >= d.p ? 1.f : 0.f);
+  return keep * (1.f / (1.f - d.p));
+}
+
+__device__ __forceinline__ float t2v_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `red` must hold >= 32 floats; all threads get the result
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}

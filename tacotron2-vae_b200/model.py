@@ -1,0 +1,330 @@
+"""Tacotron2-VAE on the B200 engine -- same public surface as the reference's model.py.
+
+What callers rely on (train.py:81-213, logger.py:24-29, synthesizer.py:99-159, inference.ipynb cells 9-28):
+  * class / attribute tree and state_dict keys -- checkpoints of the reference load unchanged;
+  * Tacotron2.parse_batch / parse_input / parse_output / forward -> [mel, mel_post, gate, align, mu, logvar, z, emotions];
+  * the step-wise inference calls: transcript_embedding(ids), encoder.inference(x), vae_gst(mel), vae_gst.fc3(z),
+    decoder.get_go_frame / initialize_decoder_states / prenet / decode / parse_decoder_outputs, postnet(mel);
+  * NEW: Tacotron2.inference(...) -- batched free-running decode with device-side stop bookkeeping.
+None of these run torch arithmetic: forward+backward is one autograd.Function over the CUDA engine (t2v.functions);
+the modules below only hold parameters in the reference's layout."""
+import weakref
+from math import sqrt
+
+import torch
+from torch import nn
+
+from fp16_optimizer import fp16_to_fp32, fp32_to_fp16
+from layers import BatchNormParams, ConvNorm, LinearNorm
+from modules import VAE_GST
+from t2v import engine as _engine
+from t2v import functions as _functions
+from t2v import infer as _infer
+from utils import get_mask_from_lengths, to_gpu
+
+drop_rate = 0.5
+
+
+class _RootLink(object):
+    """lets a sub-module reach the Tacotron2 that owns it (parameters are addressed by their full names)"""
+    _root = None
+
+    def _r(self):
+        root = self._root() if self._root is not None else None
+        if root is None:
+            raise RuntimeError("this module must be used as part of a Tacotron2 model")
+        return root
+
+
+class LocationLayer(nn.Module):
+    def __init__(self, attention_n_filters, attention_kernel_size, attention_dim):
+        super().__init__()
+        self.location_conv = ConvNorm(2, attention_n_filters, kernel_size=attention_kernel_size,
+                                      padding=(attention_kernel_size - 1) // 2, bias=False)
+        self.location_dense = LinearNorm(attention_n_filters, attention_dim, bias=False, w_init_gain="tanh")
+
+
+class Attention(nn.Module):
+    """Parameters of the location-sensitive attention (model.py:31-88); computed by the fused t2v attention kernel."""
+
+    def __init__(self, attention_rnn_dim, embedding_dim, attention_dim, attention_location_n_filters,
+                 attention_location_kernel_size):
+        super().__init__()
+        self.query_layer = LinearNorm(attention_rnn_dim, attention_dim, bias=False, w_init_gain="tanh")
+        self.memory_layer = LinearNorm(embedding_dim, attention_dim, bias=False, w_init_gain="tanh")
+        self.v = LinearNorm(attention_dim, 1, bias=False)
+        self.location_layer = LocationLayer(attention_location_n_filters, attention_location_kernel_size, attention_dim)
+        self.score_mask_value = -float("inf")
+
+
+class Prenet(nn.Module, _RootLink):
+    def __init__(self, in_dim, sizes):
+        super().__init__()
+        self.layers = nn.ModuleList([LinearNorm(i, o, bias=False) for i, o in zip([in_dim] + sizes[:-1], sizes)])
+        self._calls = 0
+
+    def forward(self, x):
+        root = self._r()
+        self._calls += 1
+        return _infer.prenet(root._state(), x, None, seed=root._seed + 7919 * self._calls, base=0)
+
+
+class Postnet(nn.Module, _RootLink):
+    def __init__(self, hparams):
+        super().__init__()
+        k, n = hparams.postnet_kernel_size, hparams.postnet_n_convolutions
+        dims = [hparams.n_mel_channels] + [hparams.postnet_embedding_dim] * (n - 1) + [hparams.n_mel_channels]
+        self.convolutions = nn.ModuleList()
+        for i in range(n):
+            gain = "tanh" if i < n - 1 else "linear"
+            self.convolutions.append(nn.Sequential(
+                ConvNorm(dims[i], dims[i + 1], kernel_size=k, padding=(k - 1) // 2, w_init_gain=gain),
+                BatchNormParams(dims[i + 1])))
+
+    def forward(self, x):
+        root = self._r()
+        return _infer.postnet(root._ops(), root._state(), x, self.training, seed=root._next_seed())
+
+
+class _LSTMParams(nn.Module):
+    def __init__(self, input_size, hidden_size, bidirectional):
+        super().__init__()
+        k = 1.0 / sqrt(hidden_size)
+        for sfx in ("", "_reverse") if bidirectional else ("",):
+            for name, shape in (("weight_ih_l0", (4 * hidden_size, input_size)), ("weight_hh_l0", (4 * hidden_size, hidden_size)),
+                                ("bias_ih_l0", (4 * hidden_size,)), ("bias_hh_l0", (4 * hidden_size,))):
+                setattr(self, name + sfx, nn.Parameter(torch.empty(*shape).uniform_(-k, k)))
+
+    def flatten_parameters(self):
+        pass
+
+
+class _LSTMCellParams(nn.Module):
+    def __init__(self, input_size, hidden_size):
+        super().__init__()
+        k = 1.0 / sqrt(hidden_size)
+        for name, shape in (("weight_ih", (4 * hidden_size, input_size)), ("weight_hh", (4 * hidden_size, hidden_size)),
+                            ("bias_ih", (4 * hidden_size,)), ("bias_hh", (4 * hidden_size,))):
+            setattr(self, name, nn.Parameter(torch.empty(*shape).uniform_(-k, k)))
+
+
+class Encoder(nn.Module, _RootLink):
+    def __init__(self, hparams):
+        super().__init__()
+        d, k = hparams.encoder_embedding_dim, hparams.encoder_kernel_size
+        self.convolutions = nn.ModuleList([
+            nn.Sequential(ConvNorm(d, d, kernel_size=k, padding=(k - 1) // 2, w_init_gain="relu"), BatchNormParams(d))
+            for _ in range(hparams.encoder_n_convolutions)])
+        self.lstm = _LSTMParams(d, d // 2, bidirectional=True)
+
+    def inference(self, x):
+        root = self._r()
+        return _infer.encoder_inference(root._ops(), root._state(), x, self.training)
+
+    def forward(self, x, input_lengths):
+        raise RuntimeError("Encoder.forward runs inside Tacotron2.forward (one fused autograd function); "
+                           "use Tacotron2.forward for training or Encoder.inference for synthesis")
+
+
+class Decoder(nn.Module, _RootLink):
+    def __init__(self, hparams):
+        super().__init__()
+        assert hparams.n_frames_per_step == 1, "only n_frames_per_step=1 is supported (as in the reference, hparams.py:87)"
+        self.n_mel_channels = hparams.n_mel_channels
+        self.n_frames_per_step = hparams.n_frames_per_step
+        self.encoder_embedding_dim = hparams.encoder_embedding_dim
+        self.attention_rnn_dim = hparams.attention_rnn_dim
+        self.decoder_rnn_dim = hparams.decoder_rnn_dim
+        self.prenet_dim = hparams.prenet_dim
+        self.max_decoder_steps = hparams.max_decoder_steps
+        self.gate_threshold = hparams.gate_threshold
+        self.p_attention_dropout = hparams.p_attention_dropout
+        self.p_decoder_dropout = hparams.p_decoder_dropout
+        self.prenet = Prenet(hparams.n_mel_channels * hparams.n_frames_per_step, [hparams.prenet_dim, hparams.prenet_dim])
+        self.attention_rnn = _LSTMCellParams(hparams.prenet_dim + self.encoder_embedding_dim, hparams.attention_rnn_dim)
+        self.attention_layer = Attention(hparams.attention_rnn_dim, self.encoder_embedding_dim, hparams.attention_dim,
+                                         hparams.attention_location_n_filters, hparams.attention_location_kernel_size)
+        self.decoder_rnn = _LSTMCellParams(hparams.attention_rnn_dim + self.encoder_embedding_dim, hparams.decoder_rnn_dim)
+        self.linear_projection = LinearNorm(hparams.decoder_rnn_dim + self.encoder_embedding_dim,
+                                            hparams.n_mel_channels * hparams.n_frames_per_step)
+        self.gate_layer = LinearNorm(hparams.decoder_rnn_dim + self.encoder_embedding_dim, 1, bias=True, w_init_gain="sigmoid")
+        self._session = None
+
+    # ---- step-wise inference surface (model.py:232-389; synthesizer.py:139-154) ----
+    def get_go_frame(self, memory):
+        return memory.new_zeros(memory.size(0), self.n_mel_channels * self.n_frames_per_step)
+
+    def initialize_decoder_states(self, memory, mask):
+        root = self._r()
+        in_len = None
+        if mask is not None:                       # mask: True at padded text positions
+            in_len = (~mask).sum(1)
+        self._session = _infer.DecoderSession(root._ops(), root._state(), memory, in_len, self.max_decoder_steps,
+                                              training=self.training, seed=root._next_seed(),
+                                              mask_value=self.attention_layer.score_mask_value)
+        self.memory = memory
+        self.mask = mask
+
+    def decode(self, decoder_input):
+        if self._session is None:
+            raise RuntimeError("call initialize_decoder_states(memory, mask) first")
+        return self._session.step(decoder_input)
+
+    def parse_decoder_outputs(self, mel_outputs, gate_outputs, alignments):
+        alignments = torch.stack(alignments).transpose(0, 1)
+        gate_outputs = torch.stack(gate_outputs)
+        if gate_outputs.dim() == 1:
+            gate_outputs = gate_outputs.unsqueeze(1)
+        gate_outputs = gate_outputs.transpose(0, 1).contiguous()
+        mel_outputs = torch.stack(mel_outputs).transpose(0, 1).contiguous()
+        mel_outputs = mel_outputs.view(mel_outputs.size(0), -1, self.n_mel_channels).transpose(1, 2)
+        return mel_outputs, gate_outputs, alignments
+
+    def inference(self, memory, n_steps=None):
+        """Decoder.inference (model.py:428-464).  With n_steps=None it stops on the gate like the reference (B=1);
+        with n_steps it runs that many steps for any batch size (device-side stop bookkeeping)."""
+        root = self._r()
+        self.initialize_decoder_states(memory, mask=None)
+        s = self._session
+        if n_steps is None:
+            if memory.size(0) != 1:
+                raise RuntimeError("gate-terminated decoding is defined for batch 1 (model.py:453); pass n_steps")
+            n_steps = self.max_decoder_steps
+            done = 0
+            while done < n_steps:
+                chunk = min(32, n_steps - done)
+                nfr = s.run_free(chunk, self.gate_threshold, seed=root._next_seed())
+                done += chunk
+                hit = int(nfr[0].item())
+                if hit > 0:
+                    return s.outputs(hit)
+            print("Warning! Reached max decoder steps")
+            return s.outputs(done)
+        s.run_free(int(n_steps), self.gate_threshold, seed=root._next_seed())
+        return s.outputs(int(n_steps))
+
+    def forward(self, memory, decoder_inputs, memory_lengths):
+        raise RuntimeError("Decoder.forward runs inside Tacotron2.forward (one fused autograd function)")
+
+
+class _Embedding(nn.Module, _RootLink):
+    def __init__(self, n, d):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(n, d))
+
+    def forward(self, ids):
+        return _infer.embedding(self._r()._state(), ids)
+
+
+class _FunctionConfig(object):
+    pass
+
+
+class Tacotron2(nn.Module):
+    def __init__(self, hparams):
+        super().__init__()
+        self.mask_padding = hparams.mask_padding
+        self.fp16_run = hparams.fp16_run
+        self.n_mel_channels = hparams.n_mel_channels
+        self.n_frames_per_step = hparams.n_frames_per_step
+        self.transcript_embedding = _Embedding(hparams.n_symbols, hparams.symbols_embedding_dim)
+        self.speaker_embedding = LinearNorm(hparams.n_speakers, hparams.speaker_embedding_dim, bias=True, w_init_gain="tanh")
+        self.emotion_embedding = LinearNorm(hparams.n_emotions, hparams.emotion_embedding_dim, bias=True, w_init_gain="tanh")
+        val = sqrt(3.0) * sqrt(2.0 / (hparams.n_symbols + hparams.symbols_embedding_dim))
+        self.transcript_embedding.weight.data.uniform_(-val, val)
+        self.encoder = Encoder(hparams)
+        self.decoder = Decoder(hparams)
+        self.postnet = Postnet(hparams)
+        self.vae_gst = VAE_GST(hparams)
+        ref = weakref.ref(self)
+        for m in (self.transcript_embedding, self.encoder, self.decoder, self.decoder.prenet, self.postnet, self.vae_gst):
+            object.__setattr__(m, "_root", ref)
+        self.precision = _infer.default_precision()      # "tf32" (tcgen05) or "fp32" (exact FFMA)
+        self._seed = int(getattr(hparams, "seed", 1234))
+        self._step = 0
+        self._rand = None                                 # explicit dropout masks / eps for parity tests
+        self.last_context = None
+
+    # ---- engine plumbing ----
+    _DEAD = ("speaker_embedding.", "emotion_embedding.", "vae_gst.ref_encoder.convs.0.weight", "vae_gst.ref_encoder.convs.0.bias")
+
+    def _ops(self):
+        return _engine.Ops(self.precision)
+
+    def _state(self):
+        return _infer.state_tensors(self)
+
+    def _next_seed(self):
+        self._step += 1
+        return self._seed * 1000003 + self._step
+
+    def half(self):
+        raise RuntimeError("fp16_run/.half() is not used on the B200 engine (fp32 master weights, tf32/bf16 operands)")
+
+    # ---- reference surface ----
+    def parse_batch(self, batch):
+        text_padded, input_lengths, mel_padded, gate_padded, output_lengths, speakers, emotions = batch
+        max_len = int(torch.max(input_lengths).item())            # lengths arrive on the host: no device sync
+        x = (to_gpu(text_padded).long(), to_gpu(input_lengths).long(), to_gpu(mel_padded).float(), max_len,
+             to_gpu(output_lengths).long(), to_gpu(speakers).float(), to_gpu(emotions).float())
+        return x, (x[2], to_gpu(gate_padded).float())
+
+    def parse_input(self, inputs):
+        return fp32_to_fp16(inputs) if self.fp16_run else inputs
+
+    def parse_output(self, outputs, output_lengths=None):
+        """Masking (model.py:509-520) happens inside the engine (it also has to reach the tensor saved for Postnet
+        conv-0's weight gradient, quirk Q10); kept for API compatibility."""
+        return fp16_to_fp32(outputs) if self.fp16_run else outputs
+
+    def forward(self, inputs):
+        text, input_lengths, targets, _, output_lengths, speakers, emotions = self.parse_input(inputs)
+        if not text.is_cuda:
+            raise RuntimeError("Tacotron2.forward needs CUDA tensors: the engine is libt2v_b200.so, there is no CPU path")
+        cfg = _FunctionConfig()
+        named = [(k, v) for k, v in self.named_parameters() if not k.startswith(self._DEAD)]
+        cfg.names = [k for k, _ in named]
+        cfg.buffers = dict(self.named_buffers())
+        cfg.ops = self._ops()
+        cfg.training = self.training
+        cfg.rand = self._rand
+        cfg.seed = self._next_seed()
+        cfg.mask_padding = bool(self.mask_padding)
+        cfg.mask_value = float(self.decoder.attention_layer.score_mask_value)
+        for k, v in named:
+            if v.dtype != torch.float32 or not v.is_contiguous() or not v.is_cuda:
+                raise RuntimeError("parameter %s must be a contiguous fp32 CUDA tensor" % k)
+        outs = _functions.Tacotron2Function.apply(cfg, text.long().contiguous(), input_lengths.long().contiguous(),
+                                                  targets.float().contiguous(), output_lengths.long().contiguous(),
+                                                  *[v for _, v in named])
+        return self.parse_output(list(outs) + [emotions], output_lengths)
+
+    @torch.no_grad()
+    def inference(self, text_ids, ref_mel=None, z=None, n_steps=None):
+        """Batched synthesis: text ids [B,Ti] + (reference mel [B,80,T] | latent z [B,32]) -> mel, mel_post, gate,
+        alignments.  n_steps=None stops on the gate (B=1, like model.py:428-464); otherwise runs n_steps steps."""
+        emb = self.transcript_embedding(text_ids).transpose(1, 2)
+        enc = self.encoder.inference(emb)
+        if z is not None:
+            style = self.vae_gst.fc3(z)
+        else:
+            style, _, _, _ = self.vae_gst(ref_mel)
+        memory = _add_style(enc, style)                    # model.py:536-537
+        mel, gate, align = self.decoder.inference(memory, n_steps)
+        mel_post = _residual(mel, self.postnet(mel))
+        return mel, mel_post, gate, align
+
+
+def _add_style(enc, style):
+    from t2v._lib import call as L
+    out = enc.contiguous().clone()
+    B, Ti, C = out.shape
+    L("t2v_bcast_add_rows", out, style.contiguous(), B * Ti, C, Ti)
+    return out
+
+
+def _residual(a, b):
+    from t2v._lib import call as L
+    out = b.contiguous().clone()
+    L("t2v_axpby", a.contiguous(), 1.0, out, 1.0, out.numel())
+    return out

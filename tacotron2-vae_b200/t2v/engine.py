@@ -1,0 +1,697 @@
+"""Forward / backward orchestration of the sm_100a kernels behind model.Tacotron2.
+
+Every arithmetic step of the hot path is a call into libt2v_b200.so (t2v._lib); torch is used only to allocate device
+buffers and to carry pointers.  Two precision modes:
+   "fp32"  every GEMM on the exact FFMA kernel (t2v_gemm_f32)                 -- tight parity mode
+   "tf32"  the large GEMMs on the tcgen05/TMA kernel (t2v_gemm_tc, tf32 math) -- the fast mode
+Layouts: Conv1d stacks use padded channels-last rows [B*(T+4), C]; the decoder uses time-major rows (t*B+b).
+
+Reference map (file:line in the reference tree):
+   encoder_forward   model.py:151-203      refenc_forward   modules.py:34-85 + CoordConv.py:37-74,142-161
+   vae_head          modules.py:8-31       prenet           model.py:91-102
+   decoder           model.py:206-464      postnet          model.py:105-148
+   outputs/masking   model.py:509-547      (loss: loss_function.py -> t2v/functions.py)
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import call as L
+
+F32 = torch.float32
+SITE_ENC, SITE_PRENET, SITE_POST = 0, 3, 20          # dropout RNG site ids (decoder uses 10..13 in decoder.cu)
+_ctypes = _lib.ctypes
+
+
+def _p(t, off_elems=0):
+    """raw device pointer (int) of tensor `t` advanced by off_elems fp32 elements"""
+    return t.data_ptr() + 4 * off_elems
+
+
+def _zeros(*shape, device, dtype=F32):
+    return torch.zeros(*shape, device=device, dtype=dtype)
+
+
+def _empty(*shape, device, dtype=F32):
+    return torch.empty(*shape, device=device, dtype=dtype)
+
+
+def _ceil4(n):
+    return (n + 3) // 4 * 4
+
+
+class Ops(object):
+    """GEMM front-end that picks the kernel for the precision mode."""
+
+    def __init__(self, precision="fp32"):
+        assert precision in ("fp32", "tf32")
+        self.precision = precision
+        self.tc = precision == "tf32"
+
+    # ---- generic strided fp32 GEMM (always exact) ----
+    @staticmethod
+    def gemm(A, a_rs, a_cs, Bm, b_rs, b_cs, C, c_rs, M, N, K, alpha=1.0, beta=0.0, bias=None):
+        L("t2v_gemm_f32", A, a_rs, a_cs, Bm, b_rs, b_cs, C, c_rs, M, N, K, alpha, beta, bias, 1, 0, 0, 0)
+
+    @staticmethod
+    def _tc_ok(*ptr_ld):
+        for ptr, ld in ptr_ld:
+            p = ptr if isinstance(ptr, int) else ptr.data_ptr()
+            if p % 16 or (ld * 4) % 16:
+                return False
+        return True
+
+    # out[M,N] = x[M,K] @ W[N,K]^T (+bias) (+= if accumulate)
+    def linear(self, x, lda, W, ldw, out, ldd, M, N, K, bias=None, accumulate=False, a_rows=None, force_exact=False):
+        if self.tc and not force_exact and self._tc_ok((x, lda), (W, ldw)) and M >= 1:
+            L("t2v_gemm_tc", x, lda, a_rows or M, K, W, ldw, N, K, out, ldd, bias, M, N, K, 1, 0, 0, 0, 0, 4, 1, 0,
+              1 if accumulate else 0, 1.0, 128)
+        else:
+            self.gemm(x, lda, 1, W, ldw, 1, out, ldd, M, N, K, 1.0, 1.0 if accumulate else 0.0, bias)
+
+    # dx[M,K] = dy[M,N] @ W[N,K]
+    def linear_dx(self, dy, ldy, W, ldw, dx, lddx, M, N, K, accumulate=False, force_exact=False):
+        dev_ok = self.tc and not force_exact and self._tc_ok((dy, ldy)) and isinstance(W, torch.Tensor)
+        if dev_ok:
+            Np = _ceil4(N)
+            WT = _zeros(K, Np, device=W.device)
+            L("t2v_transpose", W, ldw, WT, Np, N, K)
+            L("t2v_gemm_tc", dy, ldy, M, N, WT, Np, K, N, dx, lddx, None, M, K, N, 1, 0, 0, 0, 0, 4, 1, 0,
+              1 if accumulate else 0, 1.0, 128)
+        else:
+            self.gemm(dy, ldy, 1, W, 1, ldw, dx, lddx, M, K, N, 1.0, 1.0 if accumulate else 0.0, None)
+
+    # dW[N,K] = dy[M,N]^T @ x[M,K]   (reduction over the M rows); dW must be zero-initialised unless accumulate
+    def linear_dw(self, dy, ldy, x, ldx, dW, lddw, M, N, K, accumulate=False, device=None, force_exact=False):
+        if self.tc and not force_exact and M >= 256 and device is not None:
+            Mp = _ceil4(M)
+            dyT = _empty(N, Mp, device=device)
+            xT = _empty(K, Mp, device=device)
+            L("t2v_transpose", dy, ldy, dyT, Mp, M, N)
+            L("t2v_transpose", x, ldx, xT, Mp, M, K)
+            self._tc_reduce_rows(dyT, Mp, N, 0, xT, Mp, K, 0, dW, lddw, M, accumulate)
+        else:
+            self.gemm(dy, 1, ldy, x, 1, ldx, dW, lddw, N, K, M, 1.0, 1.0 if accumulate else 0.0, None)
+
+    @staticmethod
+    def _tc_reduce_rows(AT, lda, n_a, a_k0, BT, ldb, n_b, b_k0, D, ldd, Mred, accumulate, a_inner=None, b_inner=None):
+        """D[n_a, n_b] (+)= sum_r AT[:, a_k0+r] * BT[:, b_k0+r], r < Mred, with split-K sized to fill the SMs."""
+        iters = (Mred + 31) // 32
+        tiles = ((n_a + 127) // 128) * ((n_b + 127) // 128)
+        want = max(1, min(iters, int(round(296.0 / tiles))))
+        splits = 1
+        for s in range(want, 0, -1):
+            if iters % s == 0:
+                splits = s
+                break
+        atomic = 1 if (splits > 1 or accumulate) else 0     # destination must be zero-initialised by the caller
+        L("t2v_gemm_tc", AT, lda, n_a, a_inner or (a_k0 + Mred), BT, ldb, n_b, b_inner or (b_k0 + Mred), D, ldd, None, n_a, n_b,
+          Mred, 1, 0, 0, a_k0, b_k0, 4, splits, 0, atomic, 1.0, 128)
+        return splits
+
+
+# ======================================================================================================= helpers
+def _bn_forward(ops, Y, Xout, rows, C, period, lo, hi, n_valid, P, pre, training, act, mask, seed, site, p, T, dev,
+                update_running=True):
+    """BatchNorm (batch stats in training, running stats in eval) + activation + dropout.  Returns (mean, invstd)."""
+    mean = _empty(C, device=dev)
+    invstd = _empty(C, device=dev)
+    if training:
+        sums = _zeros(2, C, device=dev, dtype=torch.float64)
+        L("t2v_col_stats", Y, rows, C, period, lo, hi, 0, sums[0], sums[1])
+        L("t2v_bn_finalize", sums[0], sums[1], float(n_valid), C, 1e-5, 0.1, mean, invstd,
+          P[pre + ".running_mean"] if update_running else None, P[pre + ".running_var"] if update_running else None,
+          P[pre + ".num_batches_tracked"] if update_running else None)
+    else:
+        L("t2v_bn_eval_prepare", P[pre + ".running_mean"], P[pre + ".running_var"], C, 1e-5, mean, invstd)
+    L("t2v_bn_act_fwd", Y, Xout, rows, C, period, lo, hi, mean, invstd, P[pre + ".weight"], P[pre + ".bias"], act,
+      mask, seed, site, p, T)
+    return mean, invstd
+
+
+def _bn_backward(dOut, Y, dY, rows, C, period, lo, hi, n_valid, P, pre, training, act, mask, seed, site, p, T, dev, grads):
+    sums = _zeros(2, C, device=dev, dtype=torch.float64)
+    mean, invstd = Y.mean_invstd
+    L("t2v_bn_act_bwd_reduce", dOut, Y.t, rows, C, period, lo, hi, mean, invstd, P[pre + ".weight"], P[pre + ".bias"], act,
+      mask, seed, site, p, T, sums[0], sums[1])
+    gw = _empty(C, device=dev)
+    gb = _empty(C, device=dev)
+    L("t2v_double_to_float", sums[1], gw, C, 0.0)
+    L("t2v_double_to_float", sums[0], gb, C, 0.0)
+    grads[pre + ".weight"] = gw
+    grads[pre + ".bias"] = gb
+    L("t2v_bn_act_bwd_apply", dOut, Y.t, dY, rows, C, period, lo, hi, mean, invstd, P[pre + ".weight"], P[pre + ".bias"],
+      act, mask, seed, site, p, T, sums[0], sums[1], float(n_valid), 1 if training else 0)
+
+
+def _colsum(x, rows, C, period, lo, hi, dev, ld=None):
+    acc = _zeros(C, device=dev, dtype=torch.float64)
+    L("t2v_col_stats", x, rows, C, period, lo, hi, 2, acc, None)
+    out = _empty(C, device=dev)
+    L("t2v_double_to_float", acc, out, C, 0.0)
+    return out
+
+
+class _Saved(object):
+    """pre-BN tensor + its statistics"""
+
+    def __init__(self, t, mean_invstd):
+        self.t = t
+        self.mean_invstd = mean_invstd
+
+
+# ======================================================================================================= conv1d stacks
+def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, seed, site0, dev):
+    """k=5/p=2 Conv1d + BatchNorm1d + act + dropout(.5) layers over padded channels-last rows (Encoder
+    model.py:159-177, Postnet model.py:105-148).  X: [B*(T+4), chans[0]].  Returns (out, saved)."""
+    Tp = T + 4
+    R = B * Tp
+    M = R - 4
+    saved = []
+    for i in range(len(chans) - 1):
+        Ci, Co = chans[i], chans[i + 1]
+        pre = "%s.%d" % (prefix, i)
+        W = P[pre + ".0.conv.weight"]
+        Wk = _empty(Co, 5 * Ci, device=dev)
+        L("t2v_conv1d_pack", W, Wk, Co, Ci, 5, 0)
+        Y = _zeros(R, Co, device=dev)
+        if ops.tc:
+            L("t2v_gemm_tc", X, Ci, R, Ci, Wk, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co, P[pre + ".0.conv.bias"], M, Co, Ci, 5, 1,
+              Ci, 0, 0, 4, 1, 0, 0, 1.0, 128)
+        else:
+            ops.gemm(X, Ci, 1, Wk, 5 * Ci, 1, _p(Y, 2 * Co), Co, M, Co, 5 * Ci, 1.0, 0.0, P[pre + ".0.conv.bias"])
+        Xn = _empty(R, Co, device=dev)
+        p = 0.5 if training else 0.0
+        mask = None if masks is None else masks[i]
+        mi = _bn_forward(ops, Y, Xn, R, Co, Tp, 2, 2 + T, B * T, P, pre + ".1", training, acts[i], mask, seed, site0 + i, p, T, dev)
+        saved.append(dict(X=X, Y=_Saved(Y, mi), mask=mask, p=p, Ci=Ci, Co=Co, act=acts[i], W=W))
+        X = Xn
+    return X, saved
+
+
+def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0, dev, grads, need_dx):
+    Tp = T + 4
+    R = B * Tp
+    M = R - 4
+    for i in range(len(saved) - 1, -1, -1):
+        s = saved[i]
+        Ci, Co = s["Ci"], s["Co"]
+        pre = "%s.%d" % (prefix, i)
+        dY = _empty(R, Co, device=dev)
+        _bn_backward(dOut, s["Y"], dY, R, Co, Tp, 2, 2 + T, B * T, P, pre + ".1", training, s["act"], s["mask"], seed,
+                     site0 + i, s["p"], T, dev, grads)
+        grads[pre + ".0.conv.bias"] = _colsum(dY, R, Co, Tp, 2, 2 + T, dev)
+        # weight gradient in tap-major form: dWk[co, tap*Ci+ci] = sum_r dY[r+2, co] * X[r+tap, ci]
+        dWk = _zeros(Co, 5 * Ci, device=dev)
+        if ops.tc:
+            Rp = _ceil4(R)
+            dyT = _empty(Co, Rp, device=dev)
+            xT = _empty(Ci, Rp, device=dev)
+            L("t2v_transpose", dY, Co, dyT, Rp, R, Co)
+            L("t2v_transpose", s["X"], Ci, xT, Rp, R, Ci)
+            for tap in range(5):
+                Ops._tc_reduce_rows(dyT, Rp, Co, 2, xT, Rp, Ci, tap, _p(dWk, tap * Ci), 5 * Ci, M, True, a_inner=R, b_inner=R)
+        else:
+            ops.gemm(_p(dY, 2 * Co), 1, Co, s["X"], 1, Ci, dWk, 5 * Ci, Co, 5 * Ci, M, 1.0, 0.0, None)
+        gW = _empty(Co, Ci, 5, device=dev)
+        L("t2v_conv1d_unpack_grad", dWk, gW, Co, Ci, 5, 0.0)
+        grads[pre + ".0.conv.weight"] = gW
+        if i > 0 or need_dx:
+            Wd = _empty(Ci, 5 * Co, device=dev)
+            L("t2v_conv1d_pack", s["W"], Wd, Co, Ci, 5, 1)
+            dX = _zeros(R, Ci, device=dev)
+            if ops.tc:
+                L("t2v_gemm_tc", dY, Co, R, Co, Wd, 5 * Co, Ci, 5 * Co, _p(dX, 2 * Ci), Ci, None, M, Ci, Co, 5, 1, Co, 0, 0, 4,
+                  1, 0, 0, 1.0, 128)
+            else:
+                ops.gemm(dY, Co, 1, Wd, 5 * Co, 1, _p(dX, 2 * Ci), Ci, M, Ci, 5 * Co, 1.0, 0.0, None)
+            dOut = dX
+    return dOut
+
+
+# ======================================================================================================= encoder
+def embedding_forward(P, text, dev):
+    """nn.Embedding gather (model.py:474,528) into padded channels-last rows [B*(Ti+4),512]; bit exact."""
+    B, Ti = text.shape
+    X0 = _zeros(B * (Ti + 4), 512, device=dev)
+    L("t2v_embedding_fwd", text, P["transcript_embedding.weight"], X0, B, Ti, 512, P["transcript_embedding.weight"].shape[0])
+    return X0
+
+
+def encoder_forward(ops, P, text, in_len, training, masks, seed, dev, packed=True, X0=None, shape=None):
+    """Embedding + 3x(conv,BN,ReLU,dropout) + BiLSTM (model.py:151-203, 528-531).
+    text [B,Ti] int64 (or X0 = already-embedded padded rows with shape=(B,Ti)).
+    Returns (HoutP [B*(Ti+4),512] padded LSTM outputs, ctx)."""
+    B, Ti = shape if X0 is not None else text.shape
+    Tp = Ti + 4
+    R = B * Tp
+    if X0 is None:
+        X0 = embedding_forward(P, text, dev)
+    X3, conv_saved = conv_stack_forward(ops, P, "encoder.convolutions", X0, B, Ti, [512] * 4, [1, 1, 1], training, masks,
+                                        seed, SITE_ENC, dev)
+    Hh = 256
+    lens = in_len if packed else None
+    HoutP = _zeros(R, 512, device=dev)
+    GS = _zeros(2, Ti, B, 4 * Hh, device=dev)
+    CS = _zeros(2, Ti + 2, B, Hh, device=dev)          # slot t+1 = cell after time t; slots 0 and Ti+1 stay zero
+    GX = []
+    for d, sfx in enumerate(("", "_reverse")):
+        gx = _empty(R, 4 * Hh, device=dev)
+        ops.linear(X3, 512, P["encoder.lstm.weight_ih_l0" + sfx], 512, gx, 4 * Hh, R, 4 * Hh, 512,
+                   bias=P["encoder.lstm.bias_ih_l0" + sfx])
+        GX.append(gx)
+    hst = _zeros(2, B, Hh, device=dev)
+    cst = _zeros(2, B, Hh, device=dev)
+    rec = _empty(2, B, 4 * Hh, device=dev)
+    for s in range(Ti):
+        for d, sfx in enumerate(("", "_reverse")):
+            t = s if d == 0 else Ti - 1 - s
+            ops.gemm(hst[d], Hh, 1, P["encoder.lstm.weight_hh_l0" + sfx], Hh, 1, rec[d], 4 * Hh, B, 4 * Hh, Hh)
+            L("t2v_lstm_pointwise_fwd", rec[d], 1, 0, 4 * Hh, _p(GX[d], (2 + t) * 4 * Hh), Tp * 4 * Hh, None,
+              P["encoder.lstm.bias_hh_l0" + sfx], cst[d], Hh, hst[d], Hh, None, 0, cst[d], Hh, GS[d, t], CS[d, t + 1],
+              _p(HoutP, (2 + t) * 512 + d * Hh), Tp * 512, None, None, 0, 0, 0, 0.0, 0, lens, t, B, Hh)
+    ctx = dict(B=B, Ti=Ti, text=text, in_len=lens, conv=conv_saved, X3=X3, GS=GS, CS=CS, HoutP=HoutP)
+    return HoutP, ctx
+
+
+def encoder_backward(ops, P, dmem, ctx, training, seed, dev, grads):
+    """dmem: [B,Ti,512] gradient wrt the (compact) encoder outputs."""
+    B, Ti = ctx["B"], ctx["Ti"]
+    Tp, Hh = Ti + 4, 256
+    R = B * Tp
+    lens = ctx["in_len"]
+    HoutP, GS, CS, X3 = ctx["HoutP"], ctx["GS"], ctx["CS"], ctx["X3"]
+    dX3 = _zeros(R, 512, device=dev)
+    for d, sfx in enumerate(("", "_reverse")):
+        Whh = P["encoder.lstm.weight_hh_l0" + sfx]
+        DG = _zeros(R, 4 * Hh, device=dev)
+        dh = _zeros(B, Hh, device=dev)
+        dc = _zeros(B, Hh, device=dev)
+        order = range(Ti - 1, -1, -1) if d == 0 else range(Ti)
+        for t in order:
+            cprev = CS[d, t] if d == 0 else CS[d, t + 2]          # cell after the previous step of this direction
+            L("t2v_lstm_pointwise_bwd", _p(dmem, t * 512 + d * Hh), Ti * 512, dh, Hh, None, 0, dc, GS[d, t], CS[d, t + 1],
+              cprev, Hh, _p(DG, (2 + t) * 4 * Hh), Tp * 4 * Hh, None, None, 0, 0, 0, 0.0, 0, lens, t, B, Hh)
+            # dh_prev = dgates_t @ W_hh
+            ops.gemm(_p(DG, (2 + t) * 4 * Hh), Tp * 4 * Hh, 1, Whh, 1, Hh, dh, Hh, B, Hh, 4 * Hh)
+        # batched weight grads; h_prev of row r is HoutP[r -/+ 1] (zero pad rows make the boundaries right)
+        gWhh = _empty(4 * Hh, Hh, device=dev)
+        if d == 0:
+            ops.gemm(_p(DG, 4 * Hh), 1, 4 * Hh, HoutP, 1, 512, gWhh, Hh, 4 * Hh, Hh, R - 1)
+        else:
+            ops.gemm(DG, 1, 4 * Hh, _p(HoutP, 512 + Hh), 1, 512, gWhh, Hh, 4 * Hh, Hh, R - 1)
+        grads["encoder.lstm.weight_hh_l0" + sfx] = gWhh
+        gWih = _zeros(4 * Hh, 512, device=dev)
+        ops.linear_dw(DG, 4 * Hh, X3, 512, gWih, 512, R, 4 * Hh, 512, device=dev)
+        grads["encoder.lstm.weight_ih_l0" + sfx] = gWih
+        gb = _colsum(DG, R, 4 * Hh, 1, 0, 1, dev)
+        grads["encoder.lstm.bias_ih_l0" + sfx] = gb
+        grads["encoder.lstm.bias_hh_l0" + sfx] = gb.clone()
+        ops.linear_dx(DG, 4 * Hh, P["encoder.lstm.weight_ih_l0" + sfx], 512, dX3, 512, R, 4 * Hh, 512, accumulate=(d == 1))
+    dX0 = conv_stack_backward(ops, P, "encoder.convolutions", dX3, ctx["conv"], B, Ti, training, seed, SITE_ENC, dev, grads,
+                              need_dx=True)
+    gE = torch.zeros_like(P["transcript_embedding.weight"])
+    L("t2v_embedding_bwd", ctx["text"], dX0, gE, B, Ti, 512)
+    grads["transcript_embedding.weight"] = gE
+
+
+# ======================================================================================================= reference encoder
+_REF = "vae_gst.ref_encoder."
+
+
+def refenc_forward(ops, P, mel, training, dev):
+    """mel [N,80,T] contiguous, reinterpreted as NHWC [N,T,80,1] (the reference's .view, quirk Q1);
+    CoordConv + 6x(conv3x3 s2, BN2d, ReLU) + GRU -> last hidden [N,256] (modules.py:65-80)."""
+    N, n_mel, T = mel.shape
+    Hc, Wc, Ci = T, n_mel, 1
+    x = mel
+    filters = [P[_REF + "convs.%d.%s" % (i, "conv.weight" if i == 0 else "weight")].shape[0] for i in range(6)]
+    layers = []
+    for i in range(6):
+        Ho, Wo = (Hc - 1) // 2 + 1, (Wc - 1) // 2 + 1
+        Ct = 4 if i == 0 else Ci
+        Co = filters[i]
+        rows = N * Ho * Wo
+        col = _empty(rows, 9 * Ct, device=dev)
+        L("t2v_im2col_3x3s2", x, col, N, Hc, Wc, Ci, 1 if i == 0 else 0)
+        wname = _REF + ("convs.0.conv" if i == 0 else "convs.%d" % i)
+        Wk = _empty(Co, 9 * Ct, device=dev)
+        L("t2v_conv1d_pack", P[wname + ".weight"], Wk, Co, Ct, 9, 0)
+        Y = _empty(rows, Co, device=dev)
+        ops.linear(col, 9 * Ct, Wk, 9 * Ct, Y, Co, rows, Co, 9 * Ct, bias=P[wname + ".bias"])
+        Xn = _empty(rows, Co, device=dev)
+        mi = _bn_forward(ops, Y, Xn, rows, Co, 1, 0, 1, rows, P, _REF + "bns.%d" % i, training, 1, None, 0, 0, 0.0, 1, dev)
+        layers.append(dict(col=col, Wk=Wk, Y=_Saved(Y, mi), rows=rows, Ct=Ct, Co=Co, H=Hc, W=Wc, Ci=Ci, wname=wname))
+        x, Hc, Wc, Ci = Xn, Ho, Wo, Co
+    Tq, Wq, Cq = Hc, Wc, Ci                       # GRU sequence length, remaining mel bins, channels
+    Fin = Wq * Cq
+    Hh = P[_REF + "gru.weight_hh_l0"].shape[1]
+    # reference feature order is c*W'+w (modules.py:73-76); ours is w*C+c -> permute the input weight columns
+    Wih = _empty(3 * Hh, Fin, device=dev)
+    L("t2v_conv1d_pack", P[_REF + "gru.weight_ih_l0"], Wih, 3 * Hh, Cq, Wq, 0)
+    GI = _empty(N * Tq, 3 * Hh, device=dev)
+    ops.linear(x, Fin, Wih, Fin, GI, 3 * Hh, N * Tq, 3 * Hh, Fin)
+    HS = _zeros(Tq + 1, N, Hh, device=dev)
+    SV = _empty(Tq, N, 4 * Hh, device=dev)
+    gh = _empty(N, 3 * Hh, device=dev)
+    for t in range(Tq):
+        ops.gemm(HS[t], Hh, 1, P[_REF + "gru.weight_hh_l0"], Hh, 1, gh, 3 * Hh, N, 3 * Hh, Hh)
+        L("t2v_gru_pointwise_fwd", _p(GI, t * 3 * Hh), Tq * 3 * Hh, gh, P[_REF + "gru.bias_ih_l0"], P[_REF + "gru.bias_hh_l0"],
+          HS[t], HS[t + 1], SV[t], N, Hh)
+    ctx = dict(N=N, layers=layers, X6=x, Tq=Tq, Wq=Wq, Cq=Cq, Fin=Fin, Hh=Hh, Wih=Wih, HS=HS, SV=SV)
+    return HS[Tq], ctx
+
+
+def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
+    N, Tq, Hh, Fin = ctx["N"], ctx["Tq"], ctx["Hh"], ctx["Fin"]
+    HS, SV = ctx["HS"], ctx["SV"]
+    Whh = P[_REF + "gru.weight_hh_l0"]
+    DGI = _empty(N * Tq, 3 * Hh, device=dev)
+    dgh = _empty(N, 3 * Hh, device=dev)
+    dh = dh_last.clone()
+    dhp = _empty(N, Hh, device=dev)
+    gWhh = _zeros(3 * Hh, Hh, device=dev)
+    bh_acc = _zeros(3 * Hh, device=dev, dtype=torch.float64)
+    for t in range(Tq - 1, -1, -1):
+        L("t2v_gru_pointwise_bwd", dh, SV[t], HS[t], _p(DGI, t * 3 * Hh), Tq * 3 * Hh, dgh, dhp, N, Hh)
+        ops.gemm(dgh, 3 * Hh, 1, Whh, 1, Hh, dhp, Hh, N, Hh, 3 * Hh, 1.0, 1.0)          # dh_prev += dgh @ W_hh
+        ops.gemm(dgh, 1, 3 * Hh, HS[t], 1, Hh, gWhh, Hh, 3 * Hh, Hh, N, 1.0, 1.0)        # dW_hh += dgh^T h_prev
+        L("t2v_col_stats", dgh, N, 3 * Hh, 1, 0, 1, 2, bh_acc, None)
+        dh, dhp = dhp, dh
+    grads[_REF + "gru.weight_hh_l0"] = gWhh
+    gbh = _empty(3 * Hh, device=dev)
+    L("t2v_double_to_float", bh_acc, gbh, 3 * Hh, 0.0)
+    grads[_REF + "gru.bias_hh_l0"] = gbh
+    grads[_REF + "gru.bias_ih_l0"] = _colsum(DGI, N * Tq, 3 * Hh, 1, 0, 1, dev)
+    gWihp = _zeros(3 * Hh, Fin, device=dev)
+    ops.linear_dw(DGI, 3 * Hh, ctx["X6"], Fin, gWihp, Fin, N * Tq, 3 * Hh, Fin, device=dev)
+    gWih = _empty(3 * Hh, Fin, device=dev)
+    L("t2v_conv1d_unpack_grad", gWihp, gWih, 3 * Hh, ctx["Cq"], ctx["Wq"], 0.0)
+    grads[_REF + "gru.weight_ih_l0"] = gWih
+    dX = _empty(N * Tq, Fin, device=dev)
+    ops.linear_dx(DGI, 3 * Hh, ctx["Wih"], Fin, dX, Fin, N * Tq, 3 * Hh, Fin)
+    for i in range(5, -1, -1):
+        ly = ctx["layers"][i]
+        rows, Co, Ct = ly["rows"], ly["Co"], ly["Ct"]
+        dY = _empty(rows, Co, device=dev)
+        _bn_backward(dX, ly["Y"], dY, rows, Co, 1, 0, 1, rows, P, _REF + "bns.%d" % i, training, 1, None, 0, 0, 0.0, 1, dev, grads)
+        grads[ly["wname"] + ".bias"] = _colsum(dY, rows, Co, 1, 0, 1, dev)
+        dWk = _zeros(Co, 9 * Ct, device=dev)
+        ops.linear_dw(dY, Co, ly["col"], 9 * Ct, dWk, 9 * Ct, rows, Co, 9 * Ct, device=dev)
+        gW = torch.empty_like(P[ly["wname"] + ".weight"])
+        L("t2v_conv1d_unpack_grad", dWk, gW, Co, Ct, 9, 0.0)
+        grads[ly["wname"] + ".weight"] = gW
+        if i > 0:
+            dcol = _empty(rows, 9 * Ct, device=dev)
+            ops.linear_dx(dY, Co, ly["Wk"], 9 * Ct, dcol, 9 * Ct, rows, Co, 9 * Ct)
+            dX = _empty(N * ly["H"] * ly["W"], ly["Ci"], device=dev)
+            L("t2v_col2im_3x3s2", dcol, dX, N, ly["H"], ly["W"], ly["Ci"])
+
+
+def vae_forward(ops, P, mel, training, eps, dev):
+    """VAE_GST.forward (modules.py:24-31): returns style [N,512], mulv [N,64] = [mu|logvar], z [N,32], ctx."""
+    h, rctx = refenc_forward(ops, P, mel, training, dev)
+    N = mel.shape[0]
+    Z = P["vae_gst.fc1.weight"].shape[0]
+    Hh = h.shape[1]
+    Wmulv = torch.cat((P["vae_gst.fc1.weight"], P["vae_gst.fc2.weight"]), 0).contiguous()      # pointer plumbing only
+    bmulv = torch.cat((P["vae_gst.fc1.bias"], P["vae_gst.fc2.bias"]), 0).contiguous()
+    mulv = _empty(N, 2 * Z, device=dev)
+    ops.linear(h, Hh, Wmulv, Hh, mulv, 2 * Z, N, 2 * Z, Hh, bias=bmulv, force_exact=True)
+    z = _empty(N, Z, device=dev)
+    L("t2v_vae_reparam_fwd", mulv, eps, z, N, Z, 1 if training else 0)
+    E = P["vae_gst.fc3.weight"].shape[0]
+    style = _empty(N, E, device=dev)
+    ops.linear(z, Z, P["vae_gst.fc3.weight"], Z, style, E, N, E, Z, bias=P["vae_gst.fc3.bias"], force_exact=True)
+    ctx = dict(N=N, Z=Z, Hh=Hh, E=E, h=h, Wmulv=Wmulv, mulv=mulv, z=z, eps=eps, ref=rctx, training=training)
+    return style, mulv, z, ctx
+
+
+def fc3_forward(ops, P, z, dev):
+    """model.vae_gst.fc3(z) (inference.ipynb cell 22 / synthesizer.py:131)."""
+    N, Z = z.shape
+    E = P["vae_gst.fc3.weight"].shape[0]
+    style = _empty(N, E, device=dev)
+    ops.linear(z.contiguous(), Z, P["vae_gst.fc3.weight"], Z, style, E, N, E, Z, bias=P["vae_gst.fc3.bias"], force_exact=True)
+    return style
+
+
+def vae_backward(ops, P, dstyle, dmu, dlogvar, ctx, dev, grads):
+    N, Z, Hh, E = ctx["N"], ctx["Z"], ctx["Hh"], ctx["E"]
+    dz = _empty(N, Z, device=dev)
+    ops.gemm(dstyle, E, 1, P["vae_gst.fc3.weight"], 1, Z, dz, Z, N, Z, E)
+    g3 = _empty(E, Z, device=dev)
+    ops.gemm(dstyle, 1, E, ctx["z"], 1, Z, g3, Z, E, Z, N)
+    grads["vae_gst.fc3.weight"] = g3
+    grads["vae_gst.fc3.bias"] = _colsum(dstyle, N, E, 1, 0, 1, dev)
+    dmulv = _empty(N, 2 * Z, device=dev)
+    L("t2v_vae_reparam_bwd", ctx["mulv"], ctx["eps"], dz, dmu, dlogvar, dmulv, N, Z, 1 if ctx["training"] else 0)
+    gW = _empty(2 * Z, Hh, device=dev)
+    ops.gemm(dmulv, 1, 2 * Z, ctx["h"], 1, Hh, gW, Hh, 2 * Z, Hh, N)
+    gb = _colsum(dmulv, N, 2 * Z, 1, 0, 1, dev)
+    grads["vae_gst.fc1.weight"], grads["vae_gst.fc2.weight"] = gW[:Z].contiguous(), gW[Z:].contiguous()
+    grads["vae_gst.fc1.bias"], grads["vae_gst.fc2.bias"] = gb[:Z].contiguous(), gb[Z:].contiguous()
+    dh = _empty(N, Hh, device=dev)
+    ops.gemm(dmulv, 2 * Z, 1, ctx["Wmulv"], 1, Hh, dh, Hh, N, Hh, 2 * Z)
+    refenc_backward(ops, P, dh, ctx["ref"], ctx["training"], dev, grads)
+
+
+# ======================================================================================================= decoder
+_D = "decoder."
+_A = "decoder.attention_layer."
+
+
+def pack_decoder_weights(P, dev):
+    Wa = _empty(4096, 1792, device=dev)
+    L("t2v_copy2d", P[_D + "attention_rnn.weight_ih"], 768, 1, Wa, 1792, 4096, 768, 0.0)
+    L("t2v_copy2d", P[_D + "attention_rnn.weight_hh"], 1024, 1, _p(Wa, 768), 1792, 4096, 1024, 0.0)
+    Wd = _empty(4096, 2560, device=dev)
+    L("t2v_copy2d", P[_D + "decoder_rnn.weight_ih"], 1536, 1, Wd, 2560, 4096, 1536, 0.0)
+    L("t2v_copy2d", P[_D + "decoder_rnn.weight_hh"], 1024, 1, _p(Wd, 1536), 2560, 4096, 1024, 0.0)
+    Wpg = _empty(81, 1536, device=dev)
+    L("t2v_copy2d", P[_D + "linear_projection.linear_layer.weight"], 1536, 1, Wpg, 1536, 80, 1536, 0.0)
+    L("t2v_copy2d", P[_D + "gate_layer.linear_layer.weight"], 1536, 1, _p(Wpg, 80 * 1536), 1536, 1, 1536, 0.0)
+    bpg = _empty(81, device=dev)
+    L("t2v_copy2d", P[_D + "linear_projection.linear_layer.bias"], 80, 1, bpg, 80, 1, 80, 0.0)
+    L("t2v_copy2d", P[_D + "gate_layer.linear_layer.bias"], 1, 1, _p(bpg, 80), 1, 1, 1, 0.0)
+    return Wa, Wd, Wpg, bpg
+
+
+def _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_value, in_len, mem, pmem, buf):
+    S.B, S.Ti, S.To = B, Ti, To
+    S.use_tc = 1 if ops.tc else 0
+    S.training = 1 if training else 0
+    S.p_att, S.p_dec = 0.1, 0.1
+    S.seed = seed
+    S.drop_masks = _lib.ptr(drop_masks)
+    S.mask_value = mask_value
+    S.in_lens = _lib.ptr(in_len)
+    S.Wa, S.Wd = W["Wa"].data_ptr(), W["Wd"].data_ptr()
+    S.ba1, S.ba2 = P[_D + "attention_rnn.bias_ih"].data_ptr(), P[_D + "attention_rnn.bias_hh"].data_ptr()
+    S.bd1, S.bd2 = P[_D + "decoder_rnn.bias_ih"].data_ptr(), P[_D + "decoder_rnn.bias_hh"].data_ptr()
+    S.Wq = P[_A + "query_layer.linear_layer.weight"].data_ptr()
+    S.Wconv = P[_A + "location_layer.location_conv.conv.weight"].data_ptr()
+    S.Wloc = P[_A + "location_layer.location_dense.linear_layer.weight"].data_ptr()
+    S.v = P[_A + "v.linear_layer.weight"].data_ptr()
+    S.mem, S.pmem = mem.data_ptr(), pmem.data_ptr()
+    for k in ("XA", "XD", "CA", "CD", "CUM", "align", "GA", "GD", "CPA", "CPD", "ASAVE", "parts", "qparts"):
+        setattr(S, k, _lib.ptr(buf.get(k)))
+
+
+def alloc_decoder_buffers(B, Ti, To, dev, save=True):
+    buf = dict(XA=_zeros((To + 1) * B, 1792, device=dev), XD=_zeros((To + 1) * B, 2560, device=dev),
+               CA=_zeros((To + 1) * B, 1024, device=dev), CD=_zeros((To + 1) * B, 1024, device=dev),
+               CUM=_zeros((To + 1) * B, Ti, device=dev), align=_zeros(B, To, Ti, device=dev),
+               parts=_empty(8 * B * 4096, device=dev), qparts=_empty(8 * B * 128, device=dev))
+    if save:
+        buf.update(GA=_empty(To * B, 4096, device=dev), GD=_empty(To * B, 4096, device=dev),
+                   CPA=_empty(To * B, 1024, device=dev), CPD=_empty(To * B, 1024, device=dev),
+                   ASAVE=_empty(To * B * Ti, 128, device=dev))
+    return buf
+
+
+def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, drop_masks, seed, mask_value, dev):
+    """Teacher-forced Decoder.forward (model.py:391-426).  memory [B,Ti,512]; mel_tgt [B,80,To].
+    Returns O [To*B,84] (mel|gate rows, time-major), alignments [B,To,Ti], ctx."""
+    B, Ti, _ = memory.shape
+    To = mel_tgt.shape[2]
+    W = {}
+    W["Wa"], W["Wd"], W["Wpg"], W["bpg"] = pack_decoder_weights(P, dev)
+    pmem = _empty(B * Ti, 128, device=dev)
+    ops.linear(memory, 512, P[_A + "memory_layer.linear_layer.weight"], 512, pmem, 128, B * Ti, 128, 512)
+    buf = alloc_decoder_buffers(B, Ti, To, dev, save=True)
+    # prenet over the go frame + all teacher frames (model.py:406-409); dropout always on (model.py:101)
+    Fr = _empty((To + 1) * B, 80, device=dev)
+    L("t2v_bct_to_rows_tb_shift", mel_tgt, Fr, B, 80, To)
+    n = (To + 1) * B
+    P1pre = _empty(n, 256, device=dev)
+    ops.linear(Fr, 80, P[_D + "prenet.layers.0.linear_layer.weight"], 80, P1pre, 256, n, 256, 80)
+    P1 = _empty(n, 256, device=dev)
+    m0 = None if prenet_masks is None else prenet_masks[0]
+    m1 = None if prenet_masks is None else prenet_masks[1]
+    L("t2v_relu_drop_fwd", P1pre, P1, 256, n, 256, m0, seed, SITE_PRENET, 0.5, 0)
+    P2pre = _empty(n, 256, device=dev)
+    ops.linear(P1, 256, P[_D + "prenet.layers.1.linear_layer.weight"], 256, P2pre, 256, n, 256, 256)
+    L("t2v_relu_drop_fwd", P2pre, buf["XA"], 1792, n, 256, m1, seed, SITE_PRENET + 1, 0.5, 0)
+    S = _lib.T2VDecoderSeq()
+    _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_value, in_len, memory, pmem, buf)
+    L("t2v_decoder_fwd_steps", S, 0, To)
+    # deferred mel/gate projection of [h_dec_t | ctx_t] for all steps (model.py:383-388)
+    O = _zeros(To * B, 84, device=dev)
+    ops.linear(_p(buf["XD"], B * 2560 + 1536), 2560, W["Wpg"], 1536, O, 84, To * B, 81, 1024, bias=W["bpg"], a_rows=To * B)
+    ops.linear(_p(buf["XD"], 1024), 2560, _p(W["Wpg"], 1024), 1536, O, 84, To * B, 81, 512, accumulate=True, a_rows=To * B)
+    ctx = dict(B=B, Ti=Ti, To=To, W=W, pmem=pmem, memory=memory, buf=buf, S=S, Fr=Fr, P1pre=P1pre, P1=P1, P2pre=P2pre,
+               m0=m0, m1=m1, seed=seed, O=O)
+    return O, buf["align"], ctx
+
+
+def decoder_backward(ops, P, dO, ctx, dev, grads):
+    """dO [To*B,84] grad wrt the mel|gate rows.  Returns dmemory [B,Ti,512]."""
+    B, Ti, To, W, buf = ctx["B"], ctx["Ti"], ctx["To"], ctx["W"], ctx["buf"]
+    n = To * B
+    XA, XD = buf["XA"], buf["XD"]
+    # projection backward
+    DHC = _empty(n, 1536, device=dev)
+    ops.linear_dx(dO, 84, W["Wpg"], 1536, DHC, 1536, n, 81, 1536)
+    gWpg = _zeros(81, 1536, device=dev)
+    ops.linear_dw(dO, 84, _p(XD, B * 2560 + 1536), 2560, gWpg, 1536, n, 81, 1024, device=dev)
+    ops.linear_dw(dO, 84, _p(XD, 1024), 2560, _p(gWpg, 1024), 1536, n, 81, 512, device=dev)
+    gbpg = _colsum(dO, n, 84, 1, 0, 1, dev)
+    grads[_D + "linear_projection.linear_layer.weight"] = gWpg[:80].contiguous()
+    grads[_D + "gate_layer.linear_layer.weight"] = gWpg[80:81].contiguous()
+    grads[_D + "linear_projection.linear_layer.bias"] = gbpg[:80].contiguous()
+    grads[_D + "gate_layer.linear_layer.bias"] = gbpg[80:81].contiguous()
+    # reverse time loop
+    Wq = P[_A + "query_layer.linear_layer.weight"]
+    WaT = _empty(1792, 4096, device=dev)
+    WdT = _empty(2560, 4096, device=dev)
+    WqT = _empty(1024, 128, device=dev)
+    L("t2v_transpose", W["Wa"], 1792, WaT, 4096, 4096, 1792)
+    L("t2v_transpose", W["Wd"], 2560, WdT, 4096, 4096, 2560)
+    L("t2v_transpose", Wq, 1024, WqT, 128, 128, 1024)
+    D = _lib.T2VDecoderBwd()
+    _ctypes.memmove(_ctypes.addressof(D.f), _ctypes.addressof(ctx["S"]), _ctypes.sizeof(_lib.T2VDecoderSeq))
+    t = dict(WaT=WaT, WdT=WdT, WqT=WqT, DHC=DHC, DGA=_empty(n, 4096, device=dev), DGD=_empty(n, 4096, device=dev),
+             DXA=_empty(n, 1792, device=dev), DXD=_zeros(2 * B, 2560, device=dev), dCa=_zeros(B, 1024, device=dev),
+             dCd=_zeros(B, 1024, device=dev), dwprev=_zeros(2 * B, Ti, device=dev), gcum=_zeros(B, Ti, device=dev),
+             dmem=_zeros(B * Ti, 512, device=dev), dpmem=_zeros(B * Ti, 128, device=dev), DQ=_empty(n, 128, device=dev),
+             dHq=_empty(B, 1024, device=dev), dv_part=_zeros(B, 128, device=dev), dwloc_part=_zeros(B, 128 * 32, device=dev),
+             dwconv_part=_zeros(B, 32 * 2 * 31, device=dev))
+    for k, v in t.items():
+        setattr(D, k, v.data_ptr())
+    L("t2v_decoder_bwd_steps", D, To, 0)
+    # batched weight gradients over all steps
+    gWa = _zeros(4096, 1792, device=dev)
+    ops.linear_dw(t["DGA"], 4096, XA, 1792, gWa, 1792, n, 4096, 1792, device=dev)
+    gWd = _zeros(4096, 2560, device=dev)
+    ops.linear_dw(t["DGD"], 4096, XD, 2560, gWd, 2560, n, 4096, 2560, device=dev)
+    grads[_D + "attention_rnn.weight_ih"] = gWa[:, :768].contiguous()
+    grads[_D + "attention_rnn.weight_hh"] = gWa[:, 768:].contiguous()
+    grads[_D + "decoder_rnn.weight_ih"] = gWd[:, :1536].contiguous()
+    grads[_D + "decoder_rnn.weight_hh"] = gWd[:, 1536:].contiguous()
+    gba = _colsum(t["DGA"], n, 4096, 1, 0, 1, dev)
+    gbd = _colsum(t["DGD"], n, 4096, 1, 0, 1, dev)
+    grads[_D + "attention_rnn.bias_ih"], grads[_D + "attention_rnn.bias_hh"] = gba, gba.clone()
+    grads[_D + "decoder_rnn.bias_ih"], grads[_D + "decoder_rnn.bias_hh"] = gbd, gbd.clone()
+    gWq = _zeros(128, 1024, device=dev)
+    ops.linear_dw(t["DQ"], 128, XD, 2560, gWq, 1024, n, 128, 1024, device=dev)
+    grads[_A + "query_layer.linear_layer.weight"] = gWq
+    for name, part, cols in ((_A + "v.linear_layer.weight", t["dv_part"], 128),
+                             (_A + "location_layer.location_dense.linear_layer.weight", t["dwloc_part"], 128 * 32),
+                             (_A + "location_layer.location_conv.conv.weight", t["dwconv_part"], 32 * 2 * 31)):
+        g = _empty(cols, device=dev)
+        L("t2v_sum_rows_per_batch", part, g, 1, B, cols, 0.0)
+        grads[name] = g.view_as(P[name])
+    # prenet backward (model.py:91-102)
+    dP2pre = _empty(n, 256, device=dev)
+    L("t2v_relu_drop_bwd", ctx["P2pre"], t["DXA"], 1792, dP2pre, n, 256, ctx["m1"], ctx["seed"], SITE_PRENET + 1, 0.5, 0)
+    g2 = _zeros(256, 256, device=dev)
+    ops.linear_dw(dP2pre, 256, ctx["P1"], 256, g2, 256, n, 256, 256, device=dev)
+    grads[_D + "prenet.layers.1.linear_layer.weight"] = g2
+    dP1 = _empty(n, 256, device=dev)
+    ops.linear_dx(dP2pre, 256, P[_D + "prenet.layers.1.linear_layer.weight"], 256, dP1, 256, n, 256, 256)
+    dP1pre = _empty(n, 256, device=dev)
+    L("t2v_relu_drop_bwd", ctx["P1pre"], dP1, 256, dP1pre, n, 256, ctx["m0"], ctx["seed"], SITE_PRENET, 0.5, 0)
+    g1 = _zeros(256, 80, device=dev)
+    ops.linear_dw(dP1pre, 256, ctx["Fr"], 80, g1, 80, n, 256, 80, device=dev)
+    grads[_D + "prenet.layers.0.linear_layer.weight"] = g1
+    # memory_layer backward; dmemory = dmem(ctx path) + dpmem @ W_m
+    Wm = P[_A + "memory_layer.linear_layer.weight"]
+    gWm = _zeros(128, 512, device=dev)
+    ops.linear_dw(t["dpmem"], 128, ctx["memory"], 512, gWm, 512, B * Ti, 128, 512, device=dev)
+    grads[_A + "memory_layer.linear_layer.weight"] = gWm
+    ops.linear_dx(t["dpmem"], 128, Wm, 512, t["dmem"], 512, B * Ti, 128, 512, accumulate=True)
+    return t["dmem"].view(B, Ti, 512)
+
+
+# ======================================================================================================= postnet + outputs
+def postnet_forward(ops, P, X0p, B, To, training, masks, seed, dev):
+    return conv_stack_forward(ops, P, "postnet.convolutions", X0p, B, To, [80, 512, 512, 512, 512, 80], [2, 2, 2, 2, 0],
+                              training, masks, seed, SITE_POST, dev)
+
+
+class TrainContext(object):
+    pass
+
+
+def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=None, seed=0, mask_padding=True,
+                  mask_value=-float("inf")):
+    """Tacotron2.forward + parse_output (model.py:509-547).  `rand`: None (RNG dropout from `seed`) or an object with
+    .enc/.prenet/.dec/.post/.eps explicit keep masks (reference layouts, see oracle/port.py Rand)."""
+    dev = text.device
+    B, Ti = text.shape
+    To = mel_tgt.shape[2]
+    c = TrainContext()
+    c.B, c.Ti, c.To, c.training, c.seed, c.rand = B, Ti, To, training, seed, rand
+    g = (lambda name: None) if rand is None else (lambda name: getattr(rand, name))
+    HoutP, c.enc = encoder_forward(ops, P, text, in_len, training, g("enc"), seed, dev, packed=True)
+    eps = g("eps")
+    if training and eps is None:
+        eps = torch.empty(B, P["vae_gst.fc1.weight"].shape[0], device=dev, dtype=F32)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed + 977)
+        eps.normal_(generator=gen)
+    style, mulv, z, c.vae = vae_forward(ops, P, mel_tgt, training, eps, dev)
+    memory = _empty(B, Ti, 512, device=dev)
+    L("t2v_unpad_add", HoutP, style, memory, B, Ti, 512)                         # model.py:536-537
+    O, align, c.dec = decoder_forward(ops, P, memory, mel_tgt, in_len, training, g("prenet"), g("dec"), seed, mask_value, dev)
+    X0p = _zeros(B * (To + 4), 80, device=dev)
+    L("t2v_rows_tb_to_padded", O, 84, X0p, B, 80, To)
+    Y5, c.post = postnet_forward(ops, P, X0p, B, To, training, g("post"), seed, dev)
+    lens = out_len if mask_padding else None
+    mel = _empty(B, 80, To, device=dev)
+    mel_post = _empty(B, 80, To, device=dev)
+    gate = _empty(B, To, device=dev)
+    L("t2v_padded_to_bct", X0p, None, mel, B, 80, To, lens, 0.0)
+    L("t2v_padded_to_bct", X0p, Y5, mel_post, B, 80, To, lens, 0.0)
+    L("t2v_gate_from_rows", O, 84, 80, gate, B, To, lens, 1000.0)
+    if mask_padding:
+        L("t2v_mask_padded_rows", X0p, B, 80, To, out_len)      # Postnet conv-0's saved input becomes the masked mel (Q10)
+    Z = c.vae["Z"]
+    mu = mulv[:, :Z].contiguous()
+    logvar = mulv[:, Z:].contiguous()
+    return [mel, mel_post, gate, align, mu, logvar, z], c
+
+
+def backward_train(ops, P, c, dmel, dpost, dgate, dmu, dlogvar):
+    """Gradients of every live parameter given the output gradients (reference layouts)."""
+    dev = dmel.device
+    B, Ti, To = c.B, c.Ti, c.To
+    grads = {}
+    R = B * (To + 4)
+    dY5 = _zeros(R, 80, device=dev)
+    L("t2v_bct_to_padded", dpost, dY5, B, 80, To, 0.0)
+    dX0 = conv_stack_backward(ops, P, "postnet.convolutions", dY5, c.post, B, To, c.training, c.seed, SITE_POST, dev, grads,
+                              need_dx=True)
+    dres = _zeros(R, 80, device=dev)                      # dmel + dpost (residual, model.py:543)
+    L("t2v_bct_to_padded", dmel, dres, B, 80, To, 0.0)
+    L("t2v_bct_to_padded", dpost, dres, B, 80, To, 1.0)
+    dO = _empty(To * B, 84, device=dev)
+    L("t2v_padded_to_rows_tb", dX0, dres, dgate, dO, 84, B, 80, To)
+    dmem = decoder_backward(ops, P, dO, c.dec, dev, grads)
+    dstyle = _empty(B, 512, device=dev)
+    L("t2v_sum_rows_per_batch", dmem, dstyle, B, Ti, 512, 0.0)
+    vae_backward(ops, P, dstyle, dmu, dlogvar, c.vae, dev, grads)
+    encoder_backward(ops, P, dmem, c.enc, c.training, c.seed, dev, grads)
+    return grads

@@ -1,0 +1,163 @@
+"""Parity of the CUDA engine (through model.Tacotron2 / the C ABI) with the oracle: committed golden fixtures made
+from the real reference + the CPU restatement (oracle/port.py) on the same seeded inputs.
+Tolerances (north star: 1e-3 relative on mel outputs; bit exact on integer paths):
+    fp32 mode (FFMA GEMMs):        outputs rel-L1 <= 2e-5, grads rel-L2 <= 1e-3 (conv biases in front of a BN: noise)
+    tf32 mode (tcgen05 GEMMs):     outputs rel-L1 <= 1e-3 on mel / mel_post (stated per assert below)"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(precision, seed=1234):
+    import model as t2v_model
+    from hparams import create_hparams
+    hp = create_hparams("anneal_function=constant")
+    m = t2v_model.Tacotron2(hp)
+    m.load_state_dict(port.init_params(seed))
+    m = m.cuda()
+    m.precision = precision
+    return m, hp
+
+
+def _rand_to(rand, dev):
+    r = port.Rand()
+    r.enc = [x.to(dev) for x in rand.enc]
+    r.prenet = [x.to(dev) for x in rand.prenet]
+    r.dec = rand.dec.to(dev)
+    r.post = [x.to(dev) for x in rand.post]
+    r.eps = rand.eps.to(dev)
+    return r
+
+
+def _l1(a, b):
+    return float((a - b).abs().sum() / (b.abs().sum() + 1e-30))
+
+
+@pytest.mark.parametrize("precision,tag,B,Ti,To", [("fp32", "b3", 3, 20, 30), ("fp32", "b4", 4, 40, 64),
+                                                   ("tf32", "b3", 3, 20, 30), ("tf32", "b4", 4, 40, 64)])
+def test_train_step_matches_golden(golden_dir, precision, tag, B, Ti, To):
+    from loss_function import Tacotron2Loss_VAE
+    G = np.load(os.path.join(golden_dir, "train_step_%s.npz" % tag))
+    m, hp = _model(precision)
+    m.train()
+    batch = port.synthetic_batch(B, Ti, To, seed=0)
+    m._rand = _rand_to(port.Rand.draw(B, Ti, To, seed=1), "cuda")
+    x, y = m.parse_batch(batch)
+    out = m(x)
+    loss, recon, kl, klw = Tacotron2Loss_VAE(hp)(out, y, 0)
+    loss.backward()
+    otol = 2e-5 if precision == "fp32" else 1e-3
+    for n, o in zip(("mel", "mel_post", "gate", "align", "mu", "logvar", "z"), out[:7]):
+        ref = torch.from_numpy(G[n])
+        err = _l1(o.detach().cpu(), ref)
+        assert err <= (otol if n != "gate" else otol * 5), (n, err)
+    out_len = batch[4]
+    for b in range(B):                                   # padded frames exactly 0, gate exactly 1e3 (model.py:515-517)
+        assert float(out[0][b, :, int(out_len[b]):].abs().sum()) == 0.0
+        assert float(out[1][b, :, int(out_len[b]):].abs().sum()) == 0.0
+        assert bool((out[2][b, int(out_len[b]):] == 1e3).all())
+    ltol = 1e-5 if precision == "fp32" else 1e-3
+    assert abs(loss.item() - float(G["loss"])) <= ltol * abs(float(G["loss"]))
+    assert abs(kl.item() - float(G["kl"])) <= 10 * ltol * abs(float(G["kl"]))
+    gtol = 1e-3 if precision == "fp32" else 3e-2
+    total = float(np.sqrt(np.sum(np.maximum(G["grad_norms"], 0) ** 2)))
+    params = dict(m.named_parameters())
+    worst = 0.0
+    for k, gn in zip(G["grad_names"], G["grad_norms"]):
+        g = params[str(k)].grad
+        if gn < 0:
+            assert g is None, k                         # dead parameters (quirk Q6)
+            continue
+        assert g is not None, k
+        d = abs(float(g.norm()) - gn)
+        assert d <= gtol * gn + 1e-6 * total, (k, float(g.norm()), gn)
+        worst = max(worst, d / (gn + 1e-6 * total))
+    for k in G.files:
+        if k.startswith("grad::"):
+            g = params[k[6:]].grad.cpu()
+            ref = torch.from_numpy(G[k])
+            assert float((g - ref).norm() / ref.norm()) < gtol, k       # includes Postnet conv-0 (quirk Q10)
+        if k.startswith("buf::"):
+            buf = dict(m.named_buffers())[k[5:]].cpu().float()
+            assert torch.allclose(buf, torch.from_numpy(G[k]).float(), rtol=1e-3, atol=1e-4), k
+
+
+def test_rng_dropout_replays_in_oracle():
+    """Production mode (counter-based RNG inside the kernels): materialise the same masks with t2v_materialize_mask,
+    feed them to the CPU oracle, and compare."""
+    from t2v._lib import call as L
+    B, Ti, To = 2, 16, 24
+    m, hp = _model("fp32")
+    m.train()
+    batch = port.synthetic_batch(B, Ti, To, seed=3)
+    x, y = m.parse_batch(batch)
+    out = m(x)
+    seed = m._seed * 1000003 + m._step
+    dev = "cuda"
+
+    def mask(shape, site, p, base=0):
+        t = torch.empty(*shape, device=dev)
+        L("t2v_materialize_mask", t, t.numel(), seed, site, p, base)
+        return t.cpu()
+    r = port.Rand()
+    r.enc = [mask((B, 512, Ti), i, 0.5) for i in range(3)]
+    r.prenet = [mask((To + 1, B, 256), 3 + i, 0.5) for i in range(2)]
+    dec = torch.empty(To, 4, B, 1024)
+    for t in range(To):
+        for j in range(4):
+            dec[t, j] = mask((B, 1024), 10 + j, 0.1, base=t * B * 1024)
+    r.dec = dec
+    r.post = [mask((B, 512, To), 20 + i, 0.5) for i in range(4)] + [mask((B, 80, To), 24, 0.5)]
+    gen = torch.Generator(device=dev); gen.manual_seed(seed + 977)
+    r.eps = torch.empty(B, 32, device=dev).normal_(generator=gen).cpu()
+    P = port.init_params(1234)
+    with torch.no_grad():
+        ref = port.tacotron2_forward(P, batch[0], batch[1], batch[2], batch[4], True, r)
+    for n, o, rr in zip(("mel", "mel_post", "gate", "align"), out[:4], ref[:4]):
+        assert _l1(o.detach().cpu(), rr) < 5e-5, n
+
+
+def test_inference_c1_matches_golden(golden_dir):
+    """Config 1: single utterance through the notebook-style sub-module calls, 200 manual decoder steps."""
+    G = np.load(os.path.join(golden_dir, "inference_c1.npz"))
+    m, hp = _model("fp32")
+    m.eval()
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(2, 79, (1, 40), generator=g); ids[0, -1] = 1
+    refmel = torch.randn(1, 80, 200, generator=g)
+    pm = (torch.rand(200, 2, 1, 256, generator=g) >= 0.5).float().cuda()
+    with torch.no_grad():
+        emb = m.transcript_embedding(ids.cuda()).transpose(1, 2)
+        enc = m.encoder.inference(emb)
+        style, mu, logvar, z = m.vae_gst(refmel.cuda())
+        from model import _add_style
+        mem = _add_style(enc, style)
+        dec = m.decoder
+        dec.initialize_decoder_states(mem, mask=None)
+        nfr = dec._session.run_free(200, 0.5, prenet_masks=pm.contiguous())
+        mel, gate, align = dec._session.outputs(200)
+        post = m.postnet(mel)
+    assert _l1(enc.cpu(), torch.from_numpy(G["enc"])) < 1e-5
+    assert _l1(style.cpu(), torch.from_numpy(G["style"])) < 1e-5
+    assert _l1(mel.cpu(), torch.from_numpy(G["mel"])) < 1e-3
+    assert _l1(align.cpu(), torch.from_numpy(G["align"])) < 1e-3
+    assert _l1((post + mel).cpu(), torch.from_numpy(G["mel_post"])) < 1e-3
+    assert tuple(gate.shape) == (1, 200, 1)
+
+
+def test_stft_mel_matches_golden(golden_dir):
+    from layers import TacotronSTFT
+    G = np.load(os.path.join(golden_dir, "stft_mel.npz"))
+    st = TacotronSTFT(1024, 256, 1024, 80, 16000, 0.0, 8000.0).cuda()
+    g = torch.Generator().manual_seed(3)
+    wav = torch.rand(2, 16000, generator=g) * 2 - 1
+    wav[1] *= torch.linspace(0, 1, 16000)
+    mel = st.mel_spectrogram(wav.cuda())
+    assert np.allclose(st.mel_basis.cpu().numpy(), G["mel_basis"], rtol=1e-6, atol=1e-8)
+    assert torch.allclose(mel.cpu(), torch.from_numpy(G["mel"]), rtol=1e-3, atol=1e-3)

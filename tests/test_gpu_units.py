@@ -1,0 +1,203 @@
+"""Kernel-level checks on the B200 (all through the C ABI in include/t2v_b200.h via t2v._lib)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from t2v import _lib
+    _lib.lib()
+    return _lib.call
+
+
+def _rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_gemm_f32_strided(L):
+    torch.manual_seed(0)
+    dev = "cuda"
+    for (M, N, K) in [(64, 81, 1536), (300, 130, 77), (5, 4096, 1792)]:
+        A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); bias = torch.randn(N, device=dev)
+        C = torch.empty(M, N, device=dev)
+        L("t2v_gemm_f32", A, K, 1, B, K, 1, C, N, M, N, K, 1.0, 0.0, bias, 1, 0, 0, 0)
+        ref = (A.double() @ B.double().t() + bias.double()).float()
+        assert _rel(C, ref) < 1e-5
+        # transposed access of both operands + accumulate
+        At = A.t().contiguous(); Bt = B.t().contiguous()
+        C2 = ref.clone()
+        L("t2v_gemm_f32", At, 1, M, Bt, 1, N, C2, N, M, N, K, 0.5, 1.0, None, 1, 0, 0, 0)
+        ref2 = ref + 0.5 * (A.double() @ B.double().t()).float()
+        assert _rel(C2, ref2) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 128, 128), (256, 64, 96, 64), (1000, 300, 1792, 128), (64, 4096, 2560, 128),
+                                      (515, 81, 1024, 128), (700, 512, 80, 256)])
+def test_gemm_tc_tf32_plain(L, M, N, K, bn):
+    torch.manual_seed(1)
+    dev = "cuda"
+    A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); bias = torch.randn(N, device=dev)
+    D = torch.full((M, N), float("nan"), device=dev)
+    L("t2v_gemm_tc", A, K, M, K, B, K, N, K, D, N, bias, M, N, K, 1, 0, 0, 0, 0, 4, 1, 0, 0, 1.0, bn)
+    torch.cuda.synchronize()
+    ref = (A.double() @ B.double().t() + bias.double()).float()
+    err = _rel(D, ref)
+    assert err < 2e-3, err          # tf32 operands (10-bit mantissa), fp32 accumulate
+
+
+def test_gemm_tc_split_k_and_atomic(L):
+    torch.manual_seed(2)
+    dev = "cuda"
+    M, N, K = 64, 4096, 1792
+    A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev)
+    parts = torch.empty(4, M, N, device=dev)
+    L("t2v_gemm_tc", A, K, M, K, B, K, N, K, parts, N, None, M, N, K, 1, 0, 0, 0, 0, 4, 4, M * N, 0, 1.0, 128)
+    ref = (A.double() @ B.double().t()).float()
+    assert _rel(parts.sum(0), ref) < 2e-3
+    D = torch.zeros(M, N, device=dev)
+    L("t2v_gemm_tc", A, K, M, K, B, K, N, K, D, N, None, M, N, K, 1, 0, 0, 0, 0, 4, 8, 0, 1, 1.0, 128)
+    assert _rel(D, ref) < 2e-3
+
+
+def test_gemm_tc_taps_is_conv1d(L):
+    """k=5/p=2 Conv1d over padded channels-last rows == F.conv1d (reference model.py:105-177 layers)."""
+    torch.manual_seed(3)
+    dev = "cuda"
+    for (B, T, Ci, Co) in [(3, 37, 80, 512), (2, 50, 512, 80), (4, 30, 512, 512)]:
+        x = torch.randn(B, Ci, T, device=dev); w = torch.randn(Co, Ci, 5, device=dev) * 0.05; b = torch.randn(Co, device=dev)
+        Tp = T + 4
+        X = torch.zeros(B * Tp, Ci, device=dev)
+        L("t2v_bct_to_padded", x, X, B, Ci, T, 0.0)
+        Wk = torch.empty(Co, 5 * Ci, device=dev)
+        L("t2v_conv1d_pack", w, Wk, Co, Ci, 5, 0)
+        ref = torch.nn.functional.conv1d(x.cpu(), w.cpu(), b.cpu(), padding=2)
+        for mode in ("f32", "tc"):
+            Y = torch.zeros(B * Tp, Co, device=dev)
+            M = B * Tp - 4
+            if mode == "tc":
+                L("t2v_gemm_tc", X, Ci, B * Tp, Ci, Wk, 5 * Ci, Co, 5 * Ci, Y.data_ptr() + 8 * Co, Co, b, M, Co, Ci, 5, 1, Ci, 0, 0,
+                  4, 1, 0, 0, 1.0, 128)
+            else:
+                L("t2v_gemm_f32", X, Ci, 1, Wk, 5 * Ci, 1, Y.data_ptr() + 8 * Co, Co, M, Co, 5 * Ci, 1.0, 0.0, b, 1, 0, 0, 0)
+            out = torch.empty(B, Co, T, device=dev)
+            L("t2v_padded_to_bct", Y, None, out, B, Co, T, None, 0.0)
+            err = _rel(out.cpu(), ref)
+            assert err < (2e-3 if mode == "tc" else 1e-5), (mode, err)
+
+
+def test_bn_act_dropout_matches_torch(L):
+    torch.manual_seed(4)
+    dev = "cuda"
+    B, C, T = 3, 512, 21
+    x = torch.randn(B, C, T, device=dev) * 2 + 0.5
+    mask = (torch.rand(B, C, T, device=dev) >= 0.5).float()
+    gamma = torch.rand(C, device=dev) + 0.5; beta = torch.randn(C, device=dev) * 0.1
+    Tp = T + 4
+    Y = torch.zeros(B * Tp, C, device=dev)
+    L("t2v_bct_to_padded", x, Y, B, C, T, 0.0)
+    sums = torch.zeros(2, C, device=dev, dtype=torch.float64)
+    L("t2v_col_stats", Y, B * Tp, C, Tp, 2, 2 + T, 0, sums[0], sums[1])
+    mean = torch.empty(C, device=dev); invstd = torch.empty(C, device=dev)
+    rm = torch.zeros(C, device=dev); rv = torch.ones(C, device=dev); nbt = torch.zeros((), device=dev, dtype=torch.long)
+    L("t2v_bn_finalize", sums[0], sums[1], float(B * T), C, 1e-5, 0.1, mean, invstd, rm, rv, nbt)
+    out = torch.empty_like(Y)
+    L("t2v_bn_act_fwd", Y, out, B * Tp, C, Tp, 2, 2 + T, mean, invstd, gamma, beta, 2, mask, 0, 0, 0.5, T)
+    o = torch.empty(B, C, T, device=dev)
+    L("t2v_padded_to_bct", out, None, o, B, C, T, None, 0.0)
+    xr = x.cpu().double().requires_grad_(True)
+    bn = torch.nn.functional.batch_norm(xr, None, None, gamma.cpu().double(), beta.cpu().double(), True, 0.1, 1e-5)
+    ref = torch.tanh(bn) * mask.cpu().double() * 2.0
+    assert _rel(o.cpu().double(), ref.detach()) < 1e-5
+    assert int(nbt) == 1
+    assert torch.allclose(rm.cpu(), 0.1 * x.cpu().mean((0, 2)), atol=1e-5)
+    assert torch.allclose(rv.cpu(), 0.9 + 0.1 * x.cpu().var((0, 2), unbiased=True), rtol=1e-4, atol=1e-5)
+    # backward
+    g = torch.randn(B, C, T, device=dev)
+    ref.backward(g.cpu().double())
+    G = torch.zeros(B * Tp, C, device=dev)
+    L("t2v_bct_to_padded", g, G, B, C, T, 0.0)
+    s2 = torch.zeros(2, C, device=dev, dtype=torch.float64)
+    L("t2v_bn_act_bwd_reduce", G, Y, B * Tp, C, Tp, 2, 2 + T, mean, invstd, gamma, beta, 2, mask, 0, 0, 0.5, T, s2[0], s2[1])
+    dY = torch.empty_like(Y)
+    L("t2v_bn_act_bwd_apply", G, Y, dY, B * Tp, C, Tp, 2, 2 + T, mean, invstd, gamma, beta, 2, mask, 0, 0, 0.5, T, s2[0], s2[1],
+      float(B * T), 1)
+    dx = torch.empty(B, C, T, device=dev)
+    L("t2v_padded_to_bct", dY, None, dx, B, C, T, None, 0.0)
+    assert _rel(dx.cpu().double(), xr.grad) < 1e-4
+    assert float(dY.view(B, Tp, C)[:, :2].abs().sum()) == 0.0
+
+
+def test_embedding_bit_exact(L):
+    dev = "cuda"
+    torch.manual_seed(5)
+    ids = torch.randint(0, 80, (4, 33), device=dev)
+    table = torch.randn(80, 512, device=dev)
+    out = torch.zeros(4 * 37, 512, device=dev)
+    L("t2v_embedding_fwd", ids, table, out, 4, 33, 512, 80)
+    ref = table.cpu()[ids.cpu()]
+    assert torch.equal(out.view(4, 37, 512)[:, 2:35].cpu(), ref)
+
+
+def test_attention_step_matches_port(L):
+    from oracle import port
+    torch.manual_seed(6)
+    dev = "cuda"
+    B, Ti = 5, 47
+    P = port.init_params(11)
+    pre = "decoder.attention_layer."
+    mem = torch.randn(B, Ti, 512); q = torch.randn(B, 128)
+    wprev = torch.softmax(torch.randn(B, Ti), 1); cum = torch.rand(B, Ti)
+    lens = torch.tensor([47, 40, 33, 20, 9])
+    pmem = mem @ P[pre + "memory_layer.linear_layer.weight"].t()
+    wcat = torch.stack((wprev, cum), 1)
+    loc = torch.nn.functional.conv1d(wcat, P[pre + "location_layer.location_conv.conv.weight"], padding=15)
+    loc = loc.transpose(1, 2) @ P[pre + "location_layer.location_dense.linear_layer.weight"].t()
+    a_ref = torch.tanh(q.unsqueeze(1) + loc + pmem)
+    e = (a_ref @ P[pre + "v.linear_layer.weight"].t()).squeeze(-1)
+    e = e.masked_fill(~(torch.arange(Ti)[None] < lens[:, None]), -float("inf"))
+    w_ref = torch.softmax(e, 1)
+    ctx_ref = torch.bmm(w_ref.unsqueeze(1), mem).squeeze(1)
+    g = lambda t: t.to(dev).contiguous()
+    w_out = torch.empty(B, Ti, device=dev); cum_out = torch.empty(B, Ti, device=dev)
+    c1 = torch.empty(B, 512, device=dev); c2 = torch.empty(B, 600, device=dev); a_save = torch.empty(B, Ti, 128, device=dev)
+    L("t2v_attn_step_fwd", g(q), 1, 0, g(wprev), Ti, g(cum), cum_out, g(pmem), g(mem),
+      g(P[pre + "location_layer.location_conv.conv.weight"]), g(P[pre + "location_layer.location_dense.linear_layer.weight"]),
+      g(P[pre + "v.linear_layer.weight"]), g(lens), -float("inf"), w_out, Ti, c1, 512, c2, 600, a_save, B, Ti)
+    assert torch.allclose(w_out.cpu(), w_ref, atol=2e-6)
+    assert torch.allclose(c1.cpu(), ctx_ref, atol=1e-5)
+    assert torch.equal(c2[:, :512], c1)
+    assert torch.allclose(cum_out.cpu(), cum + w_ref, atol=2e-6)
+    assert torch.allclose(a_save.cpu(), a_ref, atol=1e-5)
+
+
+def test_loss_and_adam_match_torch(L):
+    torch.manual_seed(7)
+    dev = "cuda"
+    B, To = 3, 19
+    mel = torch.randn(B, 80, To); post = torch.randn(B, 80, To); tgt = torch.randn(B, 80, To)
+    gate = torch.randn(B, To) * 3; gt = (torch.rand(B, To) > 0.7).float(); mu = torch.randn(B, 32); lv = torch.randn(B, 32) * 0.3
+    acc = torch.zeros(4, device=dev, dtype=torch.float64); out = torch.empty(3, device=dev)
+    g = lambda t: t.to(dev)
+    L("t2v_loss_fwd", g(mel), g(post), g(tgt), mel.numel(), g(gate), g(gt), gate.numel(), g(mu), g(lv), mu.numel(), 0.001, acc, out)
+    recon = ((mel - tgt) ** 2).mean() + ((post - tgt) ** 2).mean() + torch.nn.functional.binary_cross_entropy_with_logits(gate, gt)
+    kl = -0.5 * torch.sum(1 + lv - mu ** 2 - lv.exp())
+    assert torch.allclose(out.cpu(), torch.stack([recon + 0.001 * kl, recon, kl]), rtol=1e-5)
+    # fused clip + Adam vs torch
+    n = 10007
+    p = torch.randn(n); gr = torch.randn(n) * 0.1
+    pt = p.clone().requires_grad_(True); pt.grad = gr.clone()
+    opt = torch.optim.Adam([pt], lr=1e-3, weight_decay=1e-6)
+    pd, gd = g(p.clone()), g(gr.clone()); m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+    ss = torch.zeros(1, device=dev, dtype=torch.float64); norm = torch.zeros(1, device=dev)
+    for step in (1, 2, 3):
+        tn = torch.nn.utils.clip_grad_norm_([pt], 1.0)
+        opt.step()
+        L("t2v_grad_sumsq", gd, n, 1.0, ss)
+        L("t2v_adam_clip_step", pd, gd, m, v, n, ss, 1.0, 1.0, 1e-3, 0.9, 0.999, 1e-8, 1e-6, step, norm)
+        if step == 1:
+            assert abs(float(norm) - float(tn)) < 1e-4 * float(tn)
+        pt.grad = gr.clone(); gd.copy_(g(gr))
+    assert torch.allclose(pd.cpu(), pt.detach(), rtol=1e-5, atol=1e-6)
