@@ -41,7 +41,7 @@ int t2v_gemm_tc(const void* A, long long lda, long long a_rows, long long a_inne
 
 /* ---- text embedding (model.py:474,528) -- integer gather, bit exact ------------------------------------------- */
 int t2v_embedding_fwd(const long long* ids, const float* table, float* out_padded, int B, int T, int C, int n_symbols,
-                      cudaStream_t stream);
+                      int rnd, cudaStream_t stream);
 int t2v_embedding_bwd(const long long* ids, const float* dout_padded, float* dtable, int B, int T, int C,
                       cudaStream_t stream);
 
@@ -55,7 +55,7 @@ int t2v_bn_eval_prepare(const float* running_mean, const float* running_var, int
                         float* invstd, cudaStream_t stream);
 int t2v_bn_act_fwd(const float* y, float* out, long long rows, int C, int period, int lo, int hi, const float* mean,
                    const float* invstd, const float* gamma, const float* beta, int act, const float* drop_mask,
-                   unsigned long long seed, unsigned int site, float p, int T, cudaStream_t stream);
+                   unsigned long long seed, unsigned int site, float p, int T, int rnd, cudaStream_t stream);
 int t2v_bn_act_bwd_reduce(const float* dout, const float* y, long long rows, int C, int period, int lo, int hi,
                           const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
                           const float* drop_mask, unsigned long long seed, unsigned int site, float p, int T,
@@ -64,15 +64,15 @@ int t2v_bn_act_bwd_apply(const float* dout, const float* y, float* dy, long long
                          const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
                          const float* drop_mask, unsigned long long seed, unsigned int site, float p, int T,
                          const double* dbeta_sum, const double* dgamma_sum, double n, int use_batch_stats,
-                         cudaStream_t stream);
+                         int rnd, cudaStream_t stream);
 int t2v_double_to_float(const double* src, float* dst, int n, float beta, cudaStream_t stream);
 
 /* ---- layout / packing helpers ------------------------------------------------------------------------------------ */
 int t2v_copy2d(const float* src, long long s_rs, long long s_cs, float* dst, long long d_rs, long long rows, int cols,
-               float beta, cudaStream_t stream);
-int t2v_transpose(const float* in, long long i_ld, float* out, long long o_ld, long long rows, int cols,
+               float beta, int rnd, cudaStream_t stream);
+int t2v_transpose(const float* in, long long i_ld, float* out, long long o_ld, long long rows, int cols, int rnd,
                   cudaStream_t stream);
-int t2v_conv1d_pack(const float* w, float* out, int Co, int Ci, int K, int flip, cudaStream_t stream);
+int t2v_conv1d_pack(const float* w, float* out, int Co, int Ci, int K, int flip, int rnd, cudaStream_t stream);
 int t2v_conv1d_unpack_grad(const float* gk, float* gw, int Co, int Ci, int K, float beta, cudaStream_t stream);
 int t2v_axpby(const float* x, float a, float* y, float b, long long n, cudaStream_t stream);
 int t2v_bcast_add_rows(float* y, const float* v, long long rows, int C, int rows_per_batch, cudaStream_t stream);
@@ -82,22 +82,24 @@ int t2v_fill(float* x, long long n, float v, cudaStream_t stream);
 int t2v_bct_to_padded(const float* in, float* out, int B, int C, int T, float beta, cudaStream_t stream);
 int t2v_padded_to_bct(const float* in1, const float* in2, float* out, int B, int C, int T, const long long* lens,
                       float fill, cudaStream_t stream);
-int t2v_rows_tb_to_padded(const float* rows, long long ld, float* out, int B, int C, int T, cudaStream_t stream);
+int t2v_rows_tb_to_padded(const float* rows, long long ld, float* out, int B, int C, int T, int rnd, cudaStream_t stream);
 int t2v_padded_to_rows_tb(const float* p1, const float* p2, const float* dgate, float* rows, long long ld, int B, int C,
-                          int T, cudaStream_t stream);
-int t2v_bct_to_rows_tb_shift(const float* tgt, float* rows, int B, int C, int T, cudaStream_t stream);
+                          int T, int rnd, cudaStream_t stream);
+int t2v_bct_to_rows_tb_shift(const float* tgt, float* rows, int B, int C, int T, int rnd, cudaStream_t stream);
 int t2v_gate_from_rows(const float* rows, long long ld, int col, float* gate, int B, int T, const long long* lens,
                        float fill, cudaStream_t stream);
 int t2v_mask_padded_rows(float* x, int B, int C, int T, const long long* lens, cudaStream_t stream); /* model.py:515 */
-int t2v_unpad_add(const float* in_padded, const float* add_vec, float* out, int B, int T, int C, cudaStream_t stream);
+int t2v_unpad_add(const float* in_padded, const float* add_vec, float* out, int B, int T, int C, int rnd,
+                  cudaStream_t stream);
+int t2v_round_tf32(float* x, long long n, cudaStream_t stream);   /* in-place round-to-nearest onto the tf32 grid */
 
 /* ---- Prenet pointwise (model.py:91-102) and dropout-mask materialisation for the oracle ------------------------- */
 int t2v_relu_drop_fwd(const float* x, float* out, long long o_rs, long long rows, int C, const float* mask,
                       unsigned long long seed, unsigned int site, float p, unsigned long long idx_base,
-                      cudaStream_t stream);
+                      int rnd, cudaStream_t stream);
 int t2v_relu_drop_bwd(const float* x, const float* dout, long long do_rs, float* dx, long long rows, int C,
                       const float* mask, unsigned long long seed, unsigned int site, float p,
-                      unsigned long long idx_base, cudaStream_t stream);
+                      unsigned long long idx_base, int rnd, cudaStream_t stream);
 int t2v_materialize_mask(float* out, long long n, unsigned long long seed, unsigned int site, float p,
                          unsigned long long idx_base, cudaStream_t stream);
 
@@ -108,23 +110,23 @@ int t2v_lstm_pointwise_fwd(const float* parts, int n_parts, long long part_strid
                            long long cout_rs, float* gates_save, float* cpre_save, float* seq_out, long long seq_rs,
                            const float* mask_h, const float* mask_c, unsigned long long seed, unsigned int site_h,
                            unsigned int site_c, float p, unsigned long long drop_base, const long long* lens, int t,
-                           int B, int H, cudaStream_t stream);
+                           int B, int H, int rnd, cudaStream_t stream);
 int t2v_lstm_pointwise_bwd(const float* dh1, long long dh1_rs, const float* dh2, long long dh2_rs, const float* dh3,
                            long long dh3_rs, float* dc, const float* gates_save, const float* cpre_save,
                            const float* c_prev, long long cprev_rs, float* dgates, long long dg_rs, const float* mask_h,
                            const float* mask_c, unsigned long long seed, unsigned int site_h, unsigned int site_c,
                            float p, unsigned long long drop_base, const long long* lens, int t, int B, int H,
-                           cudaStream_t stream);
+                           int rnd, cudaStream_t stream);
 int t2v_gru_pointwise_fwd(const float* gi, long long gi_rs, const float* gh, const float* b_ih, const float* b_hh, const float* h_prev,
                           float* h_out, float* save, int B, int H, cudaStream_t stream);
 int t2v_gru_pointwise_bwd(const float* dh, const float* save, const float* h_prev, float* dgi, long long dgi_rs, float* dgh,
-                          float* dh_prev, int B, int H, cudaStream_t stream);
+                          float* dh_prev, int B, int H, int rnd, cudaStream_t stream);
 int t2v_vae_reparam_fwd(const float* mulv, const float* eps, float* z, int B, int Z, int training, cudaStream_t stream);
 int t2v_vae_reparam_bwd(const float* mulv, const float* eps, const float* dz, const float* dmu_ext, const float* dlv_ext,
                         float* dmulv, int B, int Z, int training, cudaStream_t stream);
 
 /* ---- reference encoder im2col (CoordConv.py:37-74 + modules.py:45-71) ------------------------------------------- */
-int t2v_im2col_3x3s2(const float* x, float* col, int N, int H, int W, int Ci, int coord, cudaStream_t stream);
+int t2v_im2col_3x3s2(const float* x, float* col, int N, int H, int W, int Ci, int coord, int rnd, cudaStream_t stream);
 int t2v_col2im_3x3s2(const float* dcol, float* dx, int N, int H, int W, int Ci, cudaStream_t stream);
 
 /* ---- fused location-sensitive attention step (model.py:31-88, 366-374) ------------------------------------------ */
@@ -132,13 +134,13 @@ int t2v_attn_step_fwd(const float* qparts, int n_qparts, long long qpart_stride,
                       const float* cum_in, float* cum_out, const float* pmem, const float* mem, const float* w_conv,
                       const float* w_loc, const float* v, const long long* lens, float mask_value, float* w_out,
                       long long wout_rs, float* ctx_out1, long long ctx1_rs, float* ctx_out2, long long ctx2_rs,
-                      float* a_save, int B, int Ti, cudaStream_t stream);
+                      float* a_save, int B, int Ti, int rnd, cudaStream_t stream);
 int t2v_attn_step_bwd(const float* dctx1, long long dctx1_rs, const float* dctx2, long long dctx2_rs, const float* dctx3,
                       long long dctx3_rs, const float* dw_in, float* dw_out, float* gcum, const float* w, long long w_rs,
                       const float* w_prev, long long wprev_rs, const float* cum_in, const float* a_save, const float* mem,
                       const float* w_conv, const float* w_loc, const float* v, const long long* lens, float* dmem,
                       float* dpmem, float* dq, float* dv_part, float* dwloc_part, float* dwconv_part, int B, int Ti,
-                      cudaStream_t stream);
+                      int rnd, cudaStream_t stream);
 
 /* ---- the decoder time loop: Decoder.decode / Decoder.forward / Decoder.inference (model.py:346-464) ------------- */
 typedef struct T2VDecoderSeq {

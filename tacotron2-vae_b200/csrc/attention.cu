@@ -32,6 +32,7 @@ struct AttnFwdArgs {
   float* ctx_out2; long long ctx2_rs;
   float* a_save;            // [B,Ti,AD] tanh activations (nullable)
   int B, Ti;
+  int rnd;                  // round the context to tf32 on store (tensor-core GEMM operand)
 };
 
 __global__ void __launch_bounds__(256) attn_step_fwd_kernel(AttnFwdArgs p) {
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(256) attn_step_fwd_kernel(AttnFwdArgs p) {
       c1 = fmaf(w, mrow[(long long)ti * ED + 256 + tid], c1);
     }
   }
+  c0 = t2v_rnd(c0, p.rnd); c1 = t2v_rnd(c1, p.rnd);
   if (p.ctx_out1) { p.ctx_out1[b * p.ctx1_rs + tid] = c0; p.ctx_out1[b * p.ctx1_rs + 256 + tid] = c1; }
   if (p.ctx_out2) { p.ctx_out2[b * p.ctx2_rs + tid] = c0; p.ctx_out2[b * p.ctx2_rs + 256 + tid] = c1; }
 }
@@ -157,6 +159,7 @@ struct AttnBwdArgs {
   float* dwloc_part;        // [B,AD,NF]  +=
   float* dwconv_part;       // [B,NF,2,KS] +=
   int B, Ti;
+  int rnd;
 };
 
 __global__ void __launch_bounds__(256) attn_step_bwd_kernel(AttnBwdArgs p) {
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(256) attn_step_bwd_kernel(AttnBwdArgs p) {
   }
   __syncthreads();
   for (int i = tid; i < AD; i += 256) {
-    p.dq[(long long)b * AD + i] = dqs[i];
+    p.dq[(long long)b * AD + i] = t2v_rnd(dqs[i], p.rnd);
     p.dv_part[(long long)b * AD + i] += dvs[i];
   }
   // (5) dWconv[c][ch][k] += sum_ti df[ti][c] * wcat[ch][ti+k]
@@ -349,7 +352,7 @@ T2V_API int t2v_attn_step_fwd(const float* qparts, int n_qparts, long long qpart
                               const float* mem, const float* w_conv, const float* w_loc, const float* v,
                               const long long* lens, float mask_value, float* w_out, long long wout_rs, float* ctx_out1,
                               long long ctx1_rs, float* ctx_out2, long long ctx2_rs, float* a_save, int B, int Ti,
-                              cudaStream_t st) {
+                              int rnd, cudaStream_t st) {
   T2V_ARG_CHECK(B > 0 && Ti > 0, "shape");
   const size_t smem = attn_fwd_smem(Ti);
   T2V_ARG_CHECK(smem <= 220 * 1024, "Ti too large for the fused attention kernel");
@@ -362,7 +365,7 @@ T2V_API int t2v_attn_step_fwd(const float* qparts, int n_qparts, long long qpart
   a.qparts = qparts; a.n_qparts = n_qparts; a.qpart_stride = qpart_stride; a.w_prev = w_prev; a.wprev_rs = wprev_rs;
   a.cum_in = cum_in; a.cum_out = cum_out; a.pmem = pmem; a.mem = mem; a.w_conv = w_conv; a.w_loc = w_loc; a.v = v;
   a.lens = lens; a.mask_value = mask_value; a.w_out = w_out; a.wout_rs = wout_rs; a.ctx_out1 = ctx_out1;
-  a.ctx1_rs = ctx1_rs; a.ctx_out2 = ctx_out2; a.ctx2_rs = ctx2_rs; a.a_save = a_save; a.B = B; a.Ti = Ti;
+  a.ctx1_rs = ctx1_rs; a.ctx_out2 = ctx_out2; a.ctx2_rs = ctx2_rs; a.a_save = a_save; a.B = B; a.Ti = Ti; a.rnd = rnd;
   attn_step_fwd_kernel<<<B, 256, smem, st>>>(a);
   T2V_COUNT_LAUNCH();
   T2V_LAUNCH_CHECK();
@@ -375,7 +378,7 @@ T2V_API int t2v_attn_step_bwd(const float* dctx1, long long dctx1_rs, const floa
                               const float* cum_in, const float* a_save, const float* mem, const float* w_conv,
                               const float* w_loc, const float* v, const long long* lens, float* dmem, float* dpmem,
                               float* dq, float* dv_part, float* dwloc_part, float* dwconv_part, int B, int Ti,
-                              cudaStream_t st) {
+                              int rnd, cudaStream_t st) {
   T2V_ARG_CHECK(B > 0 && Ti > 0, "shape");
   const size_t smem = attn_bwd_smem(Ti);
   T2V_ARG_CHECK(smem <= 220 * 1024, "Ti too large for the fused attention backward kernel");
@@ -389,7 +392,7 @@ T2V_API int t2v_attn_step_bwd(const float* dctx1, long long dctx1_rs, const floa
   a.dw_in = dw_in; a.dw_out = dw_out; a.gcum = gcum; a.w = w; a.w_rs = w_rs; a.w_prev = w_prev; a.wprev_rs = wprev_rs;
   a.cum_in = cum_in; a.a_save = a_save; a.mem = mem; a.w_conv = w_conv; a.w_loc = w_loc; a.v = v; a.lens = lens;
   a.dmem = dmem; a.dpmem = dpmem; a.dq = dq; a.dv_part = dv_part; a.dwloc_part = dwloc_part;
-  a.dwconv_part = dwconv_part; a.B = B; a.Ti = Ti;
+  a.dwconv_part = dwconv_part; a.B = B; a.Ti = Ti; a.rnd = rnd;
   attn_step_bwd_kernel<<<B, 256, smem, st>>>(a);
   T2V_COUNT_LAUNCH();
   T2V_LAUNCH_CHECK();

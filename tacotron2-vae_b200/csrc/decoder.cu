@@ -76,7 +76,7 @@ int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) 
                              s->CA + r1 * H, H,
                              s->GA ? s->GA + r0 * 4 * H : nullptr, s->CPA ? s->CPA + r0 * H : nullptr, nullptr, 0,
                              mk, mk ? mk + (long long)B * H : nullptr, s->seed, SITE_ATT_H, SITE_ATT_C, p_att, dbase,
-                             nullptr, 0, B, H, st));
+                             nullptr, 0, B, H, s->use_tc, st));
   // query projection + fused attention
   CHK(run_gemm(&P->gq, r0, s->qparts, st));
   CHK(t2v_attn_step_fwd(s->qparts, P->gq.splits, P->gq.split_stride,
@@ -85,7 +85,7 @@ int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) 
                         s->mask_value, s->align + (long long)t * Ti, (long long)s->To * Ti,
                         s->XD + r0 * XD_W + H, XD_W,                       // ctx_t -> decoder_rnn input
                         s->XA + r1 * XA_W + PD, XA_W,                      // ctx_t -> next attention_rnn input
-                        s->ASAVE ? s->ASAVE + r0 * Ti * AD : nullptr, B, Ti, st));
+                        s->ASAVE ? s->ASAVE + r0 * Ti * AD : nullptr, B, Ti, s->use_tc, st));
   // decoder LSTM
   CHK(run_gemm(&P->gd, r0, s->parts, st));
   CHK(t2v_lstm_pointwise_fwd(s->parts, P->gd.splits, P->gd.split_stride, 4 * H, nullptr, 0, s->bd1, s->bd2,
@@ -94,7 +94,7 @@ int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) 
                              nullptr, 0, s->CD + r1 * H, H,
                              s->GD ? s->GD + r0 * 4 * H : nullptr, s->CPD ? s->CPD + r0 * H : nullptr, nullptr, 0,
                              mk ? mk + 2LL * B * H : nullptr, mk ? mk + 3LL * B * H : nullptr, s->seed, SITE_DEC_H,
-                             SITE_DEC_C, p_dec, dbase, nullptr, 0, B, H, st));
+                             SITE_DEC_C, p_dec, dbase, nullptr, 0, B, H, s->use_tc, st));
   return 0;
 }
 
@@ -140,7 +140,7 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
     CHK(t2v_lstm_pointwise_bwd(d->DHC + r0 * (H + ED), H + ED, has_next ? dxd_next + (H + ED) : nullptr, XD_W, nullptr, 0,
                                d->dCd, s->GD + r0 * 4 * H, s->CPD + r0 * H, s->CD + r0 * H, H, d->DGD + r0 * 4 * H, 4 * H,
                                mk ? mk + 2LL * B * H : nullptr, mk ? mk + 3LL * B * H : nullptr, s->seed, SITE_DEC_H,
-                               SITE_DEC_C, p_dec, dbase, nullptr, 0, B, H, st));
+                               SITE_DEC_C, p_dec, dbase, nullptr, 0, B, H, s->use_tc, st));
     CHK(run_gemm(&gxd, r0, s->parts, st));
     CHK(t2v_sum_parts(s->parts, gxd.splits, gxd.split_stride, dxd, (long long)B * XD_W, st));
     // attention backward
@@ -150,13 +150,13 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
                           d->dwprev + (long long)(t & 1) * B * Ti, d->gcum, s->align + (long long)t * Ti,
                           (long long)To * Ti, t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr, (long long)To * Ti,
                           s->CUM + r0 * Ti, s->ASAVE + r0 * Ti * AD, s->mem, s->Wconv, s->Wloc, s->v, s->in_lens, d->dmem,
-                          d->dpmem, d->DQ + r0 * AD, d->dv_part, d->dwloc_part, d->dwconv_part, B, Ti, st));
+                          d->dpmem, d->DQ + r0 * AD, d->dv_part, d->dwloc_part, d->dwconv_part, B, Ti, s->use_tc, st));
     CHK(run_gemm(&ghq, r0, d->dHq, st));
     // attention LSTM cell backward
     CHK(t2v_lstm_pointwise_bwd(dxd, XD_W, has_next ? d->DXA + r1 * XA_W + (PD + ED) : nullptr, XA_W, d->dHq, H, d->dCa,
                                s->GA + r0 * 4 * H, s->CPA + r0 * H, s->CA + r0 * H, H, d->DGA + r0 * 4 * H, 4 * H, mk,
                                mk ? mk + (long long)B * H : nullptr, s->seed, SITE_ATT_H, SITE_ATT_C, p_att, dbase,
-                               nullptr, 0, B, H, st));
+                               nullptr, 0, B, H, s->use_tc, st));
     CHK(run_gemm(&gxa, r0, s->parts, st));
     CHK(t2v_sum_parts(s->parts, gxa.splits, gxa.split_stride, d->DXA + r0 * XA_W, (long long)B * XA_W, st));
   }
@@ -192,11 +192,11 @@ T2V_API int t2v_decoder_infer_steps(const T2VDecoderInfer* d, int t_begin, int t
       CHK(t2v_fill(p1a, (long long)B * PD, 0.f, st));
     } else {
       CHK(run_gemm(&gp1, r0 - B, p1, st));
-      CHK(t2v_relu_drop_fwd(p1, p1a, PD, B, PD, pm, s->seed, SITE_PRENET0, 0.5f, pbase, st));
+      CHK(t2v_relu_drop_fwd(p1, p1a, PD, B, PD, pm, s->seed, SITE_PRENET0, 0.5f, pbase, s->use_tc, st));
     }
     CHK(run_gemm(&gp2, 0, p1, st));
     CHK(t2v_relu_drop_fwd(p1, xa_pre, XA_W, B, PD, pm ? pm + (long long)B * PD : nullptr, s->seed, SITE_PRENET1, 0.5f,
-                          pbase, st));
+                          pbase, s->use_tc, st));
     CHK(fwd_step(s, &P, t, st));
     // mel/gate projection of [h_dec_t | ctx_t]
     float* o = d->O + r0 * 84;

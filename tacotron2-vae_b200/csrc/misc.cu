@@ -37,18 +37,18 @@ __global__ void padded_to_bct_kernel(const float* __restrict__ in1, const float*
 }
 // rows (t*B+b) x ld  ->  padded channels-last [B,T+4,C]  (first C columns)
 __global__ void rows_tb_to_padded_kernel(const float* __restrict__ rows, long long ld, float* __restrict__ out, int B,
-                                         int C, int T) {
+                                         int C, int T, int rnd) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * C * T) return;
   const int c = (int)(i % C);
   const int b = (int)((i / C) % B);
   const int t = (int)(i / ((long long)C * B));
-  out[((long long)b * (T + 4) + 2 + t) * C + c] = rows[((long long)t * B + b) * ld + c];
+  out[((long long)b * (T + 4) + 2 + t) * C + c] = t2v_rnd(rows[((long long)t * B + b) * ld + c], rnd);
 }
 // drows[(t*B+b)*ld + c] = dpad1[b,2+t,c] + dpad2[b,2+t,c]   (c < C) ; column C = dgate[b,t] ; columns C+1..ld-1 = 0
 __global__ void padded_to_rows_tb_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                                          const float* __restrict__ dgate, float* __restrict__ rows, long long ld, int B,
-                                         int C, int T) {
+                                         int C, int T, int rnd) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * T * ld) return;
   const int c = (int)(i % ld);
@@ -61,16 +61,17 @@ __global__ void padded_to_rows_tb_kernel(const float* __restrict__ p1, const flo
   } else if (c == C && dgate) {
     v = dgate[(long long)b * T + t];
   }
-  rows[i] = v;
+  rows[i] = t2v_rnd(v, rnd);
 }
 // teacher-forcing frames: rows[((t+1)*B+b)*C + c] = tgt[b,c,t] ; rows[0..B) = 0 (go frame, model.py:406-408)
-__global__ void bct_to_rows_tb_shift_kernel(const float* __restrict__ tgt, float* __restrict__ rows, int B, int C, int T) {
+__global__ void bct_to_rows_tb_shift_kernel(const float* __restrict__ tgt, float* __restrict__ rows, int B, int C, int T,
+                                            int rnd) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)(T + 1) * B * C) return;
   const int c = (int)(i % C);
   const int b = (int)((i / C) % B);
   const int t = (int)(i / ((long long)C * B));
-  rows[i] = (t == 0) ? 0.f : tgt[((long long)b * C + c) * T + (t - 1)];
+  rows[i] = (t == 0) ? 0.f : t2v_rnd(tgt[((long long)b * C + c) * T + (t - 1)], rnd);
 }
 // gate[b,t] = t < len[b] ? rows[(t*B+b)*ld + col] : fill
 __global__ void gate_from_rows_kernel(const float* __restrict__ rows, long long ld, int col, float* __restrict__ gate,
@@ -94,20 +95,20 @@ __global__ void mask_padded_rows_kernel(float* __restrict__ x, int B, int C, int
 // out[b,t,c] = in[b,2+t,c] + add_vec[b,c]   (padded channels-last -> compact, + per-utterance vector: the style
 // broadcast-add of model.py:536-537; add_vec may be NULL)
 __global__ void unpad_add_kernel(const float* __restrict__ in, const float* __restrict__ addv, float* __restrict__ out,
-                                 int B, int T, int C) {
+                                 int B, int T, int C, int rnd) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * T * C) return;
   const int c = (int)(i % C);
   const int t = (int)((i / C) % T);
   const int b = (int)(i / ((long long)C * T));
-  out[i] = in[((long long)b * (T + 4) + 2 + t) * C + c] + (addv ? addv[(long long)b * C + c] : 0.f);
+  out[i] = t2v_rnd(in[((long long)b * (T + 4) + 2 + t) * C + c] + (addv ? addv[(long long)b * C + c] : 0.f), rnd);
 }
 
 // ---------------------------------------------------------------------------------------- reference encoder
 // im2col for 3x3 / stride 2 / pad 1 over NHWC; col[(n,ho,wo), (kh*3+kw)*Ct + c].  coord=1: the input has one real
 // channel and channels 1..3 are the CoordConv xx/yy/rr planes generated on the fly.
 __global__ void im2col_3x3s2_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int H, int W, int Ci,
-                                    int Ho, int Wo, int coord) {
+                                    int Ho, int Wo, int coord, int rnd) {
   const int Ct = coord ? 4 : Ci;
   const long long total = (long long)N * Ho * Wo * 9 * Ct;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,7 +128,7 @@ __global__ void im2col_3x3s2_kernel(const float* __restrict__ x, float* __restri
       v = (c == 1) ? xx : (c == 2 ? yy : sqrtf((xx - 0.5f) * (xx - 0.5f) + (yy - 0.5f) * (yy - 0.5f)));
     }
   }
-  col[i] = v;
+  col[i] = t2v_rnd(v, rnd);
 }
 // adjoint: dx[n,h,w,c] = sum over (kh,kw) with matching output pixel of dcol
 __global__ void col2im_3x3s2_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int N, int H, int W, int Ci,
@@ -290,6 +291,9 @@ __global__ void adam_clip_kernel(float* __restrict__ p, float* __restrict__ g, f
     p[i] -= step * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
   }
 }
+__global__ void round_tf32_kernel(float* __restrict__ x, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = t2v_tf32(x[i]);
+}
 __global__ void fill_kernel(float* __restrict__ x, long long n, float v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = v;
 }
@@ -306,17 +310,17 @@ T2V_API int t2v_padded_to_bct(const float* in1, const float* in2, float* out, in
   padded_to_bct_kernel<<<grid1d((long long)B * C * T, 256), 256, 0, st>>>(in1, in2, out, B, C, T, lens, fill);
   LAUNCH_END();
 }
-T2V_API int t2v_rows_tb_to_padded(const float* rows, long long ld, float* out, int B, int C, int T, cudaStream_t st) {
-  rows_tb_to_padded_kernel<<<grid1d((long long)B * C * T, 256), 256, 0, st>>>(rows, ld, out, B, C, T);
+T2V_API int t2v_rows_tb_to_padded(const float* rows, long long ld, float* out, int B, int C, int T, int rnd, cudaStream_t st) {
+  rows_tb_to_padded_kernel<<<grid1d((long long)B * C * T, 256), 256, 0, st>>>(rows, ld, out, B, C, T, rnd);
   LAUNCH_END();
 }
 T2V_API int t2v_padded_to_rows_tb(const float* p1, const float* p2, const float* dgate, float* rows, long long ld, int B,
-                                  int C, int T, cudaStream_t st) {
-  padded_to_rows_tb_kernel<<<grid1d((long long)B * T * ld, 256), 256, 0, st>>>(p1, p2, dgate, rows, ld, B, C, T);
+                                  int C, int T, int rnd, cudaStream_t st) {
+  padded_to_rows_tb_kernel<<<grid1d((long long)B * T * ld, 256), 256, 0, st>>>(p1, p2, dgate, rows, ld, B, C, T, rnd);
   LAUNCH_END();
 }
-T2V_API int t2v_bct_to_rows_tb_shift(const float* tgt, float* rows, int B, int C, int T, cudaStream_t st) {
-  bct_to_rows_tb_shift_kernel<<<grid1d((long long)(T + 1) * B * C, 256), 256, 0, st>>>(tgt, rows, B, C, T);
+T2V_API int t2v_bct_to_rows_tb_shift(const float* tgt, float* rows, int B, int C, int T, int rnd, cudaStream_t st) {
+  bct_to_rows_tb_shift_kernel<<<grid1d((long long)(T + 1) * B * C, 256), 256, 0, st>>>(tgt, rows, B, C, T, rnd);
   LAUNCH_END();
 }
 T2V_API int t2v_gate_from_rows(const float* rows, long long ld, int col, float* gate, int B, int T, const long long* lens,
@@ -328,13 +332,14 @@ T2V_API int t2v_mask_padded_rows(float* x, int B, int C, int T, const long long*
   mask_padded_rows_kernel<<<grid1d((long long)B * C * T, 256), 256, 0, st>>>(x, B, C, T, lens);
   LAUNCH_END();
 }
-T2V_API int t2v_unpad_add(const float* in_padded, const float* add_vec, float* out, int B, int T, int C, cudaStream_t st) {
-  unpad_add_kernel<<<grid1d((long long)B * T * C, 256), 256, 0, st>>>(in_padded, add_vec, out, B, T, C);
+T2V_API int t2v_unpad_add(const float* in_padded, const float* add_vec, float* out, int B, int T, int C, int rnd,
+                          cudaStream_t st) {
+  unpad_add_kernel<<<grid1d((long long)B * T * C, 256), 256, 0, st>>>(in_padded, add_vec, out, B, T, C, rnd);
   LAUNCH_END();
 }
-T2V_API int t2v_im2col_3x3s2(const float* x, float* col, int N, int H, int W, int Ci, int coord, cudaStream_t st) {
+T2V_API int t2v_im2col_3x3s2(const float* x, float* col, int N, int H, int W, int Ci, int coord, int rnd, cudaStream_t st) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Ct = coord ? 4 : Ci;
-  im2col_3x3s2_kernel<<<grid1d((long long)N * Ho * Wo * 9 * Ct, 256), 256, 0, st>>>(x, col, N, H, W, Ci, Ho, Wo, coord);
+  im2col_3x3s2_kernel<<<grid1d((long long)N * Ho * Wo * 9 * Ct, 256), 256, 0, st>>>(x, col, N, H, W, Ci, Ho, Wo, coord, rnd);
   LAUNCH_END();
 }
 T2V_API int t2v_col2im_3x3s2(const float* dcol, float* dx, int N, int H, int W, int Ci, cudaStream_t st) {
@@ -388,6 +393,10 @@ T2V_API int t2v_adam_clip_step(float* p, float* g, float* m, float* v, long long
   T2V_ARG_CHECK(step >= 1, "step counts from 1");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adam_clip_kernel<<<1184, 256, 0, st>>>(p, g, m, v, n, sumsq, gscale, max_norm, lr, beta1, beta2, eps, wd, bc1, bc2, norm_out);
+  LAUNCH_END();
+}
+T2V_API int t2v_round_tf32(float* x, long long n, cudaStream_t st) {
+  round_tf32_kernel<<<1184, 256, 0, st>>>(x, n);
   LAUNCH_END();
 }
 T2V_API int t2v_fill(float* x, long long n, float v, cudaStream_t st) {

@@ -20,7 +20,7 @@ struct RowSpace {
 
 // ------------------------------------------------------------------------------------------ embedding
 __global__ void embedding_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
-                                     float* __restrict__ out, int B, int T, int C, int n_symbols) {
+                                     float* __restrict__ out, int B, int T, int C, int n_symbols, int rnd) {
   // one block per (b,t); out row = b*(T+4)+2+t
   const int bt = blockIdx.x;
   const int b = bt / T, t = bt % T;
@@ -28,7 +28,11 @@ __global__ void embedding_fwd_kernel(const long long* __restrict__ ids, const fl
   if (id < 0 || id >= n_symbols) __trap();   // nn.Embedding raises on out-of-range ids
   const float4* src = reinterpret_cast<const float4*>(table + id * C);
   float4* dst = reinterpret_cast<float4*>(out + ((long long)b * (T + 4) + 2 + t) * C);
-  for (int i = threadIdx.x; i < C / 4; i += blockDim.x) dst[i] = src[i];
+  for (int i = threadIdx.x; i < C / 4; i += blockDim.x) {
+    float4 v = src[i];
+    v.x = t2v_rnd(v.x, rnd); v.y = t2v_rnd(v.y, rnd); v.z = t2v_rnd(v.z, rnd); v.w = t2v_rnd(v.w, rnd);
+    dst[i] = v;
+  }
 }
 __global__ void embedding_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dout,
                                      float* __restrict__ dtable, int B, int T, int C) {
@@ -134,7 +138,7 @@ __global__ void bn_eval_prepare_kernel(const float* __restrict__ running_mean, c
 
 // out = dropout(act(gamma*(y-mean)*invstd+beta)) on valid rows, 0 on pad rows
 __global__ void bn_act_fwd_kernel(const float* __restrict__ y, float* __restrict__ out, long long rows, int C,
-                                  RowSpace rs, BnCtx ctx) {
+                                  RowSpace rs, BnCtx ctx, int rnd) {
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index
   const long long total4 = rows * C / 4;
   if (i4 >= total4) return;
@@ -147,7 +151,7 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ y, float* __restrict
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float pre = ctx.gamma[c + j] * ((in[j] - ctx.mean[c + j]) * ctx.invstd[c + j]) + ctx.beta[c + j];
-      res[j] = act_fwd(pre, ctx.act) * t2v_keep_scale(ctx.drop, drop_index(rs, r, c + j, C, ctx.T));
+      res[j] = t2v_rnd(act_fwd(pre, ctx.act) * t2v_keep_scale(ctx.drop, drop_index(rs, r, c + j, C, ctx.T)), rnd);
     }
     o = make_float4(res[0], res[1], res[2], res[3]);
   }
@@ -158,7 +162,7 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ y, float* __restrict
 // eval-mode (use_batch_stats=0): dy = gamma*invstd*g
 __global__ void bn_act_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dy, long long rows, int C,
                                   RowSpace rs, BnCtx ctx, const double* __restrict__ dbeta_sum,
-                                  const double* __restrict__ dgamma_sum, double n, int use_batch_stats) {
+                                  const double* __restrict__ dgamma_sum, double n, int use_batch_stats, int rnd) {
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total4 = rows * C / 4;
   if (i4 >= total4) return;
@@ -179,6 +183,7 @@ __global__ void bn_act_bwd_kernel(const float* __restrict__ dout, float* __restr
         res[j] = gamma * invstd * (g - (float)(dbeta_sum[c + j] / n) - xhat * (float)(dgamma_sum[c + j] / n));
       else
         res[j] = gamma * invstd * g;
+      res[j] = t2v_rnd(res[j], rnd);
     }
     o = make_float4(res[0], res[1], res[2], res[3]);
   }
@@ -193,18 +198,18 @@ __global__ void double_to_float_acc_kernel(const double* __restrict__ src, float
 // ------------------------------------------------------------------------------------------ layout helpers
 // generic strided 2-level copy: dst[r*d_rs + c] = src[r*s_rs + c*s_cs] (+ optional accumulate)
 __global__ void copy2d_kernel(const float* __restrict__ src, long long s_rs, long long s_cs, float* __restrict__ dst,
-                              long long d_rs, long long rows, int cols, float beta) {
+                              long long d_rs, long long rows, int cols, float beta, int rnd) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const long long r = i / cols;
   const int c = (int)(i % cols);
-  const float v = src[r * s_rs + c * s_cs];
+  const float v = t2v_rnd(src[r * s_rs + c * s_cs], rnd);
   float* d = dst + r * d_rs + c;
   *d = (beta != 0.f) ? beta * (*d) + v : v;
 }
 // tiled transpose: out[c*o_ld + r] = in[r*i_ld + c]
 __global__ void transpose_kernel(const float* __restrict__ in, long long i_ld, float* __restrict__ out, long long o_ld,
-                                 long long rows, int cols) {
+                                 long long rows, int cols, int rnd) {
   __shared__ float tile[32][33];
   const long long r0 = (long long)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
@@ -217,18 +222,20 @@ __global__ void transpose_kernel(const float* __restrict__ in, long long i_ld, f
   for (int j = threadIdx.y; j < 32; j += 8) {
     const int c = c0 + j;
     const long long r = r0 + threadIdx.x;
-    if (r < rows && c < cols) out[(long long)c * o_ld + r] = tile[threadIdx.x][j];
+    if (r < rows && c < cols) out[(long long)c * o_ld + r] = t2v_rnd(tile[threadIdx.x][j], rnd);
   }
 }
 // Conv1d weight [Co,Ci,K] -> tap-major [Co, K*Ci] (flip=0) or dgrad form [Ci, K*Co] with taps reversed (flip=1)
-__global__ void conv1d_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int Co, int Ci, int K, int flip) {
+__global__ void conv1d_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int Co, int Ci, int K, int flip,
+                                   int rnd) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Co * Ci * K) return;
   const int k = (int)(i % K);
   const int ci = (int)((i / K) % Ci);
   const int co = (int)(i / ((long long)K * Ci));
-  if (!flip) out[((long long)co * K + k) * Ci + ci] = w[i];
-  else out[((long long)ci * K + (K - 1 - k)) * Co + co] = w[i];
+  const float v = t2v_rnd(w[i], rnd);
+  if (!flip) out[((long long)co * K + k) * Ci + ci] = v;
+  else out[((long long)ci * K + (K - 1 - k)) * Co + co] = v;
 }
 // gradient in tap-major form [Co, K*Ci] -> accumulate into [Co,Ci,K]
 __global__ void conv1d_unpack_grad_kernel(const float* __restrict__ gk, float* __restrict__ gw, int Co, int Ci, int K,
@@ -278,22 +285,22 @@ __global__ void sum_parts_kernel(const float* __restrict__ parts, int n_parts, l
 }
 // relu + dropout pointwise (Prenet, model.py:101): out = relu(x) * keep/(1-p); logical idx = row*C+c + idx_base
 __global__ void relu_drop_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, long long o_rs,
-                                     long long rows, int C, T2VDrop drop, unsigned long long idx_base) {
+                                     long long rows, int C, T2VDrop drop, unsigned long long idx_base, int rnd) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
   const long long r = i / C;
   const int c = (int)(i % C);
-  out[r * o_rs + c] = fmaxf(x[i], 0.f) * t2v_keep_scale(drop, idx_base + (uint64_t)i);
+  out[r * o_rs + c] = t2v_rnd(fmaxf(x[i], 0.f) * t2v_keep_scale(drop, idx_base + (uint64_t)i), rnd);
 }
 // dx = dout * 1[x>0] * keep/(1-p)
 __global__ void relu_drop_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, long long do_rs,
                                      float* __restrict__ dx, long long rows, int C, T2VDrop drop,
-                                     unsigned long long idx_base) {
+                                     unsigned long long idx_base, int rnd) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
   const long long r = i / C;
   const int c = (int)(i % C);
-  dx[i] = (x[i] > 0.f) ? dout[r * do_rs + c] * t2v_keep_scale(drop, idx_base + (uint64_t)i) : 0.f;
+  dx[i] = (x[i] > 0.f) ? t2v_rnd(dout[r * do_rs + c] * t2v_keep_scale(drop, idx_base + (uint64_t)i), rnd) : 0.f;
 }
 __global__ void materialize_mask_kernel(float* __restrict__ out, long long n, T2VDrop drop, unsigned long long idx_base) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,6 +322,7 @@ struct LstmFwdArgs {
   T2VDrop drop_h, drop_c; unsigned long long drop_base;
   const long long* lens; int t;           // packed mode (nullable lens => every row live)
   int B, H;
+  int rnd;                                // round h to tf32 on store (it is a tensor-core GEMM operand)
 };
 __global__ void lstm_pointwise_fwd_kernel(LstmFwdArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,7 +354,7 @@ __global__ void lstm_pointwise_fwd_kernel(LstmFwdArgs a) {
   const float c2 = fg * cp + ig * gg;
   const float h2 = og * tanhf(c2);
   const uint64_t idx = a.drop_base + (uint64_t)b * a.H + j;
-  const float hd = h2 * t2v_keep_scale(a.drop_h, idx);
+  const float hd = t2v_rnd(h2 * t2v_keep_scale(a.drop_h, idx), a.rnd);
   const float cd = c2 * t2v_keep_scale(a.drop_c, idx);
   if (a.h_out) a.h_out[b * a.hout_rs + j] = hd;
   if (a.h_out2) a.h_out2[b * a.hout2_rs + j] = hd;
@@ -370,6 +378,7 @@ struct LstmBwdArgs {
   T2VDrop drop_h, drop_c; unsigned long long drop_base;
   const long long* lens; int t;
   int B, H;
+  int rnd;
 };
 __global__ void lstm_pointwise_bwd_kernel(LstmBwdArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,10 +402,10 @@ __global__ void lstm_pointwise_bwd_kernel(LstmBwdArgs a) {
   const float tc = tanhf(c2);
   float dc = a.dc[(long long)b * a.H + j] * t2v_keep_scale(a.drop_c, idx) + dh * og * (1.f - tc * tc);
   const float cp = a.c_prev[b * a.cprev_rs + j];
-  dg[0] = dc * gg * ig * (1.f - ig);
-  dg[a.H] = dc * cp * fg * (1.f - fg);
-  dg[2 * a.H] = dc * ig * (1.f - gg * gg);
-  dg[3 * a.H] = dh * tc * og * (1.f - og);
+  dg[0] = t2v_rnd(dc * gg * ig * (1.f - ig), a.rnd);
+  dg[a.H] = t2v_rnd(dc * cp * fg * (1.f - fg), a.rnd);
+  dg[2 * a.H] = t2v_rnd(dc * ig * (1.f - gg * gg), a.rnd);
+  dg[3 * a.H] = t2v_rnd(dh * tc * og * (1.f - og), a.rnd);
   a.dc[(long long)b * a.H + j] = dc * fg;
 }
 
@@ -422,7 +431,7 @@ __global__ void gru_pointwise_fwd_kernel(const float* __restrict__ gi, long long
 // in: dh [B,H] (grad wrt h_out).  out: dgi [B,3H], dgh [B,3H], dh_prev_direct [B,H] (= dh*z; caller adds dgh*W_hh)
 __global__ void gru_pointwise_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ save,
                                          const float* __restrict__ h_prev, float* __restrict__ dgi, long long dgi_rs,
-                                         float* __restrict__ dgh, float* __restrict__ dh_prev, int B, int H) {
+                                         float* __restrict__ dgh, float* __restrict__ dh_prev, int B, int H, int rnd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * H) return;
   const int b = i / H, j = i % H;
@@ -435,7 +444,7 @@ __global__ void gru_pointwise_bwd_kernel(const float* __restrict__ dh, const flo
   const float dr = dn * ghn * r * (1.f - r);
   float* a = dgi + (long long)b * dgi_rs + j;
   float* c = dgh + (long long)b * 3 * H + j;
-  a[0] = dr; a[H] = dz; a[2 * H] = dn;
+  a[0] = t2v_rnd(dr, rnd); a[H] = t2v_rnd(dz, rnd); a[2 * H] = t2v_rnd(dn, rnd);
   c[0] = dr; c[H] = dz; c[2 * H] = dn * r;
   dh_prev[i] = d * z;
 }
@@ -479,9 +488,9 @@ inline unsigned grid1d(long long n, int block) { return (unsigned)((n + block - 
 #define LAUNCH_END() do { T2V_COUNT_LAUNCH(); T2V_LAUNCH_CHECK(); return 0; } while (0)
 
 T2V_API int t2v_embedding_fwd(const long long* ids, const float* table, float* out, int B, int T, int C, int n_symbols,
-                              cudaStream_t st) {
+                              int rnd, cudaStream_t st) {
   T2V_ARG_CHECK(C % 4 == 0 && B > 0 && T > 0, "shape");
-  embedding_fwd_kernel<<<B * T, 128, 0, st>>>(ids, table, out, B, T, C, n_symbols);
+  embedding_fwd_kernel<<<B * T, 128, 0, st>>>(ids, table, out, B, T, C, n_symbols, rnd);
   LAUNCH_END();
 }
 T2V_API int t2v_embedding_bwd(const long long* ids, const float* dout, float* dtable, int B, int T, int C, cudaStream_t st) {
@@ -515,10 +524,10 @@ T2V_API int t2v_bn_eval_prepare(const float* running_mean, const float* running_
 T2V_API int t2v_bn_act_fwd(const float* y, float* out, long long rows, int C, int period, int lo, int hi,
                            const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
                            const float* drop_mask, unsigned long long seed, unsigned int site, float p, int T,
-                           cudaStream_t st) {
+                           int rnd, cudaStream_t st) {
   T2V_ARG_CHECK(C % 4 == 0, "C must be a multiple of 4");
   BnCtx ctx = mk_ctx(y, mean, invstd, gamma, beta, act, mk_drop(drop_mask, seed, site, p), T);
-  bn_act_fwd_kernel<<<grid1d(rows * C / 4, 256), 256, 0, st>>>(y, out, rows, C, mk_rs(period, lo, hi), ctx);
+  bn_act_fwd_kernel<<<grid1d(rows * C / 4, 256), 256, 0, st>>>(y, out, rows, C, mk_rs(period, lo, hi), ctx, rnd);
   LAUNCH_END();
 }
 // pass 1 of BN backward: dbeta_sum / dgamma_sum (double[C], pre-zeroed)
@@ -536,11 +545,11 @@ T2V_API int t2v_bn_act_bwd_apply(const float* dout, const float* y, float* dy, l
                                  int hi, const float* mean, const float* invstd, const float* gamma, const float* beta,
                                  int act, const float* drop_mask, unsigned long long seed, unsigned int site, float p,
                                  int T, const double* dbeta_sum, const double* dgamma_sum, double n,
-                                 int use_batch_stats, cudaStream_t st) {
+                                 int use_batch_stats, int rnd, cudaStream_t st) {
   T2V_ARG_CHECK(C % 4 == 0, "C must be a multiple of 4");
   BnCtx ctx = mk_ctx(y, mean, invstd, gamma, beta, act, mk_drop(drop_mask, seed, site, p), T);
   bn_act_bwd_kernel<<<grid1d(rows * C / 4, 256), 256, 0, st>>>(dout, dy, rows, C, mk_rs(period, lo, hi), ctx, dbeta_sum,
-                                                              dgamma_sum, n, use_batch_stats);
+                                                              dgamma_sum, n, use_batch_stats, rnd);
   LAUNCH_END();
 }
 T2V_API int t2v_double_to_float(const double* src, float* dst, int n, float beta, cudaStream_t st) {
@@ -548,19 +557,19 @@ T2V_API int t2v_double_to_float(const double* src, float* dst, int n, float beta
   LAUNCH_END();
 }
 T2V_API int t2v_copy2d(const float* src, long long s_rs, long long s_cs, float* dst, long long d_rs, long long rows,
-                       int cols, float beta, cudaStream_t st) {
-  copy2d_kernel<<<grid1d(rows * cols, 256), 256, 0, st>>>(src, s_rs, s_cs, dst, d_rs, rows, cols, beta);
+                       int cols, float beta, int rnd, cudaStream_t st) {
+  copy2d_kernel<<<grid1d(rows * cols, 256), 256, 0, st>>>(src, s_rs, s_cs, dst, d_rs, rows, cols, beta, rnd);
   LAUNCH_END();
 }
 T2V_API int t2v_transpose(const float* in, long long i_ld, float* out, long long o_ld, long long rows, int cols,
-                          cudaStream_t st) {
+                          int rnd, cudaStream_t st) {
   dim3 grid(t2v_ceil_div(rows, 32), t2v_ceil_div(cols, 32)), block(32, 8);
   T2V_ARG_CHECK(grid.y <= 65535, "cols too large");
-  transpose_kernel<<<grid, block, 0, st>>>(in, i_ld, out, o_ld, rows, cols);
+  transpose_kernel<<<grid, block, 0, st>>>(in, i_ld, out, o_ld, rows, cols, rnd);
   LAUNCH_END();
 }
-T2V_API int t2v_conv1d_pack(const float* w, float* out, int Co, int Ci, int K, int flip, cudaStream_t st) {
-  conv1d_pack_kernel<<<grid1d((long long)Co * Ci * K, 256), 256, 0, st>>>(w, out, Co, Ci, K, flip);
+T2V_API int t2v_conv1d_pack(const float* w, float* out, int Co, int Ci, int K, int flip, int rnd, cudaStream_t st) {
+  conv1d_pack_kernel<<<grid1d((long long)Co * Ci * K, 256), 256, 0, st>>>(w, out, Co, Ci, K, flip, rnd);
   LAUNCH_END();
 }
 T2V_API int t2v_conv1d_unpack_grad(const float* gk, float* gw, int Co, int Ci, int K, float beta, cudaStream_t st) {
@@ -586,15 +595,15 @@ T2V_API int t2v_sum_parts(const float* parts, int n_parts, long long part_stride
 }
 T2V_API int t2v_relu_drop_fwd(const float* x, float* out, long long o_rs, long long rows, int C, const float* mask,
                               unsigned long long seed, unsigned int site, float p, unsigned long long idx_base,
-                              cudaStream_t st) {
-  relu_drop_fwd_kernel<<<grid1d(rows * C, 256), 256, 0, st>>>(x, out, o_rs, rows, C, mk_drop(mask, seed, site, p), idx_base);
+                              int rnd, cudaStream_t st) {
+  relu_drop_fwd_kernel<<<grid1d(rows * C, 256), 256, 0, st>>>(x, out, o_rs, rows, C, mk_drop(mask, seed, site, p), idx_base, rnd);
   LAUNCH_END();
 }
 T2V_API int t2v_relu_drop_bwd(const float* x, const float* dout, long long do_rs, float* dx, long long rows, int C,
                               const float* mask, unsigned long long seed, unsigned int site, float p,
-                              unsigned long long idx_base, cudaStream_t st) {
+                              unsigned long long idx_base, int rnd, cudaStream_t st) {
   relu_drop_bwd_kernel<<<grid1d(rows * C, 256), 256, 0, st>>>(x, dout, do_rs, dx, rows, C, mk_drop(mask, seed, site, p),
-                                                             idx_base);
+                                                             idx_base, rnd);
   LAUNCH_END();
 }
 T2V_API int t2v_materialize_mask(float* out, long long n, unsigned long long seed, unsigned int site, float p,
@@ -610,8 +619,9 @@ T2V_API int t2v_lstm_pointwise_fwd(const float* parts, int n_parts, long long pa
                                    float* gates_save, float* cpre_save, float* seq_out, long long seq_rs,
                                    const float* mask_h, const float* mask_c, unsigned long long seed,
                                    unsigned int site_h, unsigned int site_c, float p, unsigned long long drop_base,
-                                   const long long* lens, int t, int B, int H, cudaStream_t st) {
+                                   const long long* lens, int t, int B, int H, int rnd, cudaStream_t st) {
   LstmFwdArgs a;
+  a.rnd = rnd;
   a.parts = parts; a.n_parts = n_parts; a.part_stride = part_stride; a.parts_rs = parts_rs;
   a.pre = pre; a.pre_rs = pre_rs; a.b1 = b1; a.b2 = b2; a.c_prev = c_prev; a.cprev_rs = cprev_rs;
   a.h_out = h_out; a.hout_rs = hout_rs; a.h_out2 = h_out2; a.hout2_rs = hout2_rs; a.c_out = c_out; a.cout_rs = cout_rs;
@@ -626,8 +636,9 @@ T2V_API int t2v_lstm_pointwise_bwd(const float* dh1, long long dh1_rs, const flo
                                    const float* cpre_save, const float* c_prev, long long cprev_rs, float* dgates,
                                    long long dg_rs, const float* mask_h, const float* mask_c, unsigned long long seed,
                                    unsigned int site_h, unsigned int site_c, float p, unsigned long long drop_base,
-                                   const long long* lens, int t, int B, int H, cudaStream_t st) {
+                                   const long long* lens, int t, int B, int H, int rnd, cudaStream_t st) {
   LstmBwdArgs a;
+  a.rnd = rnd;
   a.dh1 = dh1; a.dh1_rs = dh1_rs; a.dh2 = dh2; a.dh2_rs = dh2_rs; a.dh3 = dh3; a.dh3_rs = dh3_rs; a.dc = dc;
   a.gates_save = gates_save; a.cpre_save = cpre_save; a.c_prev = c_prev; a.cprev_rs = cprev_rs; a.dgates = dgates;
   a.dg_rs = dg_rs; a.drop_h = mk_drop(mask_h, seed, site_h, p); a.drop_c = mk_drop(mask_c, seed, site_c, p);
@@ -641,8 +652,8 @@ T2V_API int t2v_gru_pointwise_fwd(const float* gi, long long gi_rs, const float*
   LAUNCH_END();
 }
 T2V_API int t2v_gru_pointwise_bwd(const float* dh, const float* save, const float* h_prev, float* dgi, long long dgi_rs,
-                                  float* dgh, float* dh_prev, int B, int H, cudaStream_t st) {
-  gru_pointwise_bwd_kernel<<<grid1d((long long)B * H, 256), 256, 0, st>>>(dh, save, h_prev, dgi, dgi_rs, dgh, dh_prev, B, H);
+                                  float* dgh, float* dh_prev, int B, int H, int rnd, cudaStream_t st) {
+  gru_pointwise_bwd_kernel<<<grid1d((long long)B * H, 256), 256, 0, st>>>(dh, save, h_prev, dgi, dgi_rs, dgh, dh_prev, B, H, rnd);
   LAUNCH_END();
 }
 T2V_API int t2v_vae_reparam_fwd(const float* mulv, const float* eps, float* z, int B, int Z, int training, cudaStream_t st) {

@@ -67,6 +67,15 @@ __device__ __forceinline__ float t2v_keep_scale(const T2VDrop& d, uint64_t logic
   return keep * (1.f / (1.f - d.p));
 }
 
+// round-to-nearest to the tf32 grid (10-bit mantissa): tcgen05 kind::tf32 TRUNCATES fp32 operands, which biases every
+// dot product by ~-1e-3; kernels that produce GEMM operands for the tensor-core path round them on store instead.
+__device__ __forceinline__ float t2v_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float t2v_rnd(float x, int flag) { return flag ? t2v_tf32(x) : x; }
+
 __device__ __forceinline__ float t2v_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

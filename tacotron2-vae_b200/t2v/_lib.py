@@ -73,6 +73,7 @@ def load_library(path=LIB_PATH):
 
 
 _lib = None
+_DEBUG_SYNC = bool(int(os.environ.get("T2V_DEBUG_SYNC", "0")))
 
 
 def lib():
@@ -107,6 +108,11 @@ def call(name, *args):
     r = getattr(lib(), name)(*conv)
     if r != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, r, lib().t2v_last_error().decode()))
+    if _DEBUG_SYNC:
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:       # noqa: BLE001
+            raise RuntimeError("%s%r -> device fault: %s" % (name, tuple(a for a in args if not isinstance(a, torch.Tensor)), e))
 
 
 def launch_count():

@@ -20,6 +20,20 @@ from . import _lib
 from ._lib import call as L
 
 F32 = torch.float32
+_TRACE = bool(int(__import__("os").environ.get("T2V_TRACE", "0")))
+_t_last = [None]
+
+
+def _trace(label):
+    """T2V_TRACE=1: synchronise and print the wall time since the previous trace point (debug / coarse profiling)"""
+    if not _TRACE:
+        return
+    import time
+    torch.cuda.synchronize()
+    now = time.perf_counter()
+    if _t_last[0] is not None and label:
+        print("[t2v] %-28s %9.3f ms" % (label, (now - _t_last[0]) * 1e3), flush=True)
+    _t_last[0] = now
 SITE_ENC, SITE_PRENET, SITE_POST = 0, 3, 20          # dropout RNG site ids (decoder uses 10..13 in decoder.cu)
 _ctypes = _lib.ctypes
 
@@ -48,6 +62,15 @@ class Ops(object):
         assert precision in ("fp32", "tf32")
         self.precision = precision
         self.tc = precision == "tf32"
+        self.R = 1 if self.tc else 0       # producers round tensor-core operands to the tf32 grid on store
+
+    def wr(self, W):
+        """weights consumed directly by a tensor-core GEMM: tf32-rounded copy (tcgen05 truncates otherwise)"""
+        if not self.tc:
+            return W
+        Wc = W.detach().clone()
+        L("t2v_round_tf32", Wc, Wc.numel())
+        return Wc
 
     # ---- generic strided fp32 GEMM (always exact) ----
     @staticmethod
@@ -76,7 +99,7 @@ class Ops(object):
         if dev_ok:
             Np = _ceil4(N)
             WT = _zeros(K, Np, device=W.device)
-            L("t2v_transpose", W, ldw, WT, Np, N, K)
+            L("t2v_transpose", W, ldw, WT, Np, N, K, 1)
             L("t2v_gemm_tc", dy, ldy, M, N, WT, Np, K, N, dx, lddx, None, M, K, N, 1, 0, 0, 0, 0, 4, 1, 0,
               1 if accumulate else 0, 1.0, 128)
         else:
@@ -88,8 +111,8 @@ class Ops(object):
             Mp = _ceil4(M)
             dyT = _empty(N, Mp, device=device)
             xT = _empty(K, Mp, device=device)
-            L("t2v_transpose", dy, ldy, dyT, Mp, M, N)
-            L("t2v_transpose", x, ldx, xT, Mp, M, K)
+            L("t2v_transpose", dy, ldy, dyT, Mp, M, N, 1)
+            L("t2v_transpose", x, ldx, xT, Mp, M, K, 1)
             self._tc_reduce_rows(dyT, Mp, N, 0, xT, Mp, K, 0, dW, lddw, M, accumulate)
         else:
             self.gemm(dy, 1, ldy, x, 1, ldx, dW, lddw, N, K, M, 1.0, 1.0 if accumulate else 0.0, None)
@@ -113,7 +136,7 @@ class Ops(object):
 
 # ======================================================================================================= helpers
 def _bn_forward(ops, Y, Xout, rows, C, period, lo, hi, n_valid, P, pre, training, act, mask, seed, site, p, T, dev,
-                update_running=True):
+                update_running=True, rnd=0):
     """BatchNorm (batch stats in training, running stats in eval) + activation + dropout.  Returns (mean, invstd)."""
     mean = _empty(C, device=dev)
     invstd = _empty(C, device=dev)
@@ -126,11 +149,12 @@ def _bn_forward(ops, Y, Xout, rows, C, period, lo, hi, n_valid, P, pre, training
     else:
         L("t2v_bn_eval_prepare", P[pre + ".running_mean"], P[pre + ".running_var"], C, 1e-5, mean, invstd)
     L("t2v_bn_act_fwd", Y, Xout, rows, C, period, lo, hi, mean, invstd, P[pre + ".weight"], P[pre + ".bias"], act,
-      mask, seed, site, p, T)
+      mask, seed, site, p, T, rnd)
     return mean, invstd
 
 
-def _bn_backward(dOut, Y, dY, rows, C, period, lo, hi, n_valid, P, pre, training, act, mask, seed, site, p, T, dev, grads):
+def _bn_backward(dOut, Y, dY, rows, C, period, lo, hi, n_valid, P, pre, training, act, mask, seed, site, p, T, dev, grads,
+                 rnd=0):
     sums = _zeros(2, C, device=dev, dtype=torch.float64)
     mean, invstd = Y.mean_invstd
     L("t2v_bn_act_bwd_reduce", dOut, Y.t, rows, C, period, lo, hi, mean, invstd, P[pre + ".weight"], P[pre + ".bias"], act,
@@ -142,7 +166,7 @@ def _bn_backward(dOut, Y, dY, rows, C, period, lo, hi, n_valid, P, pre, training
     grads[pre + ".weight"] = gw
     grads[pre + ".bias"] = gb
     L("t2v_bn_act_bwd_apply", dOut, Y.t, dY, rows, C, period, lo, hi, mean, invstd, P[pre + ".weight"], P[pre + ".bias"],
-      act, mask, seed, site, p, T, sums[0], sums[1], float(n_valid), 1 if training else 0)
+      act, mask, seed, site, p, T, sums[0], sums[1], float(n_valid), 1 if training else 0, rnd)
 
 
 def _colsum(x, rows, C, period, lo, hi, dev, ld=None):
@@ -162,7 +186,7 @@ class _Saved(object):
 
 
 # ======================================================================================================= conv1d stacks
-def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, seed, site0, dev):
+def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, seed, site0, dev, round_last=True):
     """k=5/p=2 Conv1d + BatchNorm1d + act + dropout(.5) layers over padded channels-last rows (Encoder
     model.py:159-177, Postnet model.py:105-148).  X: [B*(T+4), chans[0]].  Returns (out, saved)."""
     Tp = T + 4
@@ -174,7 +198,7 @@ def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, se
         pre = "%s.%d" % (prefix, i)
         W = P[pre + ".0.conv.weight"]
         Wk = _empty(Co, 5 * Ci, device=dev)
-        L("t2v_conv1d_pack", W, Wk, Co, Ci, 5, 0)
+        L("t2v_conv1d_pack", W, Wk, Co, Ci, 5, 0, ops.R)
         Y = _zeros(R, Co, device=dev)
         if ops.tc:
             L("t2v_gemm_tc", X, Ci, R, Ci, Wk, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co, P[pre + ".0.conv.bias"], M, Co, Ci, 5, 1,
@@ -184,7 +208,9 @@ def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, se
         Xn = _empty(R, Co, device=dev)
         p = 0.5 if training else 0.0
         mask = None if masks is None else masks[i]
-        mi = _bn_forward(ops, Y, Xn, R, Co, Tp, 2, 2 + T, B * T, P, pre + ".1", training, acts[i], mask, seed, site0 + i, p, T, dev)
+        last = i == len(chans) - 2
+        mi = _bn_forward(ops, Y, Xn, R, Co, Tp, 2, 2 + T, B * T, P, pre + ".1", training, acts[i], mask, seed, site0 + i, p, T, dev,
+                         rnd=ops.R if (round_last or not last) else 0)
         saved.append(dict(X=X, Y=_Saved(Y, mi), mask=mask, p=p, Ci=Ci, Co=Co, act=acts[i], W=W))
         X = Xn
     return X, saved
@@ -200,18 +226,20 @@ def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0
         pre = "%s.%d" % (prefix, i)
         dY = _empty(R, Co, device=dev)
         _bn_backward(dOut, s["Y"], dY, R, Co, Tp, 2, 2 + T, B * T, P, pre + ".1", training, s["act"], s["mask"], seed,
-                     site0 + i, s["p"], T, dev, grads)
+                     site0 + i, s["p"], T, dev, grads, rnd=ops.R)
         grads[pre + ".0.conv.bias"] = _colsum(dY, R, Co, Tp, 2, 2 + T, dev)
         # weight gradient in tap-major form: dWk[co, tap*Ci+ci] = sum_r dY[r+2, co] * X[r+tap, ci]
         dWk = _zeros(Co, 5 * Ci, device=dev)
         if ops.tc:
-            Rp = _ceil4(R)
-            dyT = _empty(Co, Rp, device=dev)
-            xT = _empty(Ci, Rp, device=dev)
-            L("t2v_transpose", dY, Co, dyT, Rp, R, Co)
-            L("t2v_transpose", s["X"], Ci, xT, Rp, R, Ci)
+            # K-major operands for the row reduction: dyT[co, r] = dY[r+2, co]; xT[ci, r] = X[r+tap, ci].  The tap shift is
+            # applied while transposing because TMA needs 16-byte aligned inner coordinates.
+            Mp = _ceil4(M)
+            dyT = _zeros(Co, Mp, device=dev)
+            L("t2v_transpose", _p(dY, 2 * Co), Co, dyT, Mp, M, Co, 1)
+            xT = _zeros(Ci, Mp, device=dev)
             for tap in range(5):
-                Ops._tc_reduce_rows(dyT, Rp, Co, 2, xT, Rp, Ci, tap, _p(dWk, tap * Ci), 5 * Ci, M, True, a_inner=R, b_inner=R)
+                L("t2v_transpose", _p(s["X"], tap * Ci), Ci, xT, Mp, M, Ci, 1)
+                Ops._tc_reduce_rows(dyT, Mp, Co, 0, xT, Mp, Ci, 0, _p(dWk, tap * Ci), 5 * Ci, M, True)
         else:
             ops.gemm(_p(dY, 2 * Co), 1, Co, s["X"], 1, Ci, dWk, 5 * Ci, Co, 5 * Ci, M, 1.0, 0.0, None)
         gW = _empty(Co, Ci, 5, device=dev)
@@ -219,7 +247,7 @@ def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0
         grads[pre + ".0.conv.weight"] = gW
         if i > 0 or need_dx:
             Wd = _empty(Ci, 5 * Co, device=dev)
-            L("t2v_conv1d_pack", s["W"], Wd, Co, Ci, 5, 1)
+            L("t2v_conv1d_pack", s["W"], Wd, Co, Ci, 5, 1, ops.R)
             dX = _zeros(R, Ci, device=dev)
             if ops.tc:
                 L("t2v_gemm_tc", dY, Co, R, Co, Wd, 5 * Co, Ci, 5 * Co, _p(dX, 2 * Ci), Ci, None, M, Ci, Co, 5, 1, Co, 0, 0, 4,
@@ -231,11 +259,11 @@ def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0
 
 
 # ======================================================================================================= encoder
-def embedding_forward(P, text, dev):
+def embedding_forward(P, text, dev, rnd=0):
     """nn.Embedding gather (model.py:474,528) into padded channels-last rows [B*(Ti+4),512]; bit exact."""
     B, Ti = text.shape
     X0 = _zeros(B * (Ti + 4), 512, device=dev)
-    L("t2v_embedding_fwd", text, P["transcript_embedding.weight"], X0, B, Ti, 512, P["transcript_embedding.weight"].shape[0])
+    L("t2v_embedding_fwd", text, P["transcript_embedding.weight"], X0, B, Ti, 512, P["transcript_embedding.weight"].shape[0], rnd)
     return X0
 
 
@@ -247,7 +275,7 @@ def encoder_forward(ops, P, text, in_len, training, masks, seed, dev, packed=Tru
     Tp = Ti + 4
     R = B * Tp
     if X0 is None:
-        X0 = embedding_forward(P, text, dev)
+        X0 = embedding_forward(P, text, dev, ops.R)
     X3, conv_saved = conv_stack_forward(ops, P, "encoder.convolutions", X0, B, Ti, [512] * 4, [1, 1, 1], training, masks,
                                         seed, SITE_ENC, dev)
     Hh = 256
@@ -258,7 +286,7 @@ def encoder_forward(ops, P, text, in_len, training, masks, seed, dev, packed=Tru
     GX = []
     for d, sfx in enumerate(("", "_reverse")):
         gx = _empty(R, 4 * Hh, device=dev)
-        ops.linear(X3, 512, P["encoder.lstm.weight_ih_l0" + sfx], 512, gx, 4 * Hh, R, 4 * Hh, 512,
+        ops.linear(X3, 512, ops.wr(P["encoder.lstm.weight_ih_l0" + sfx]), 512, gx, 4 * Hh, R, 4 * Hh, 512,
                    bias=P["encoder.lstm.bias_ih_l0" + sfx])
         GX.append(gx)
     hst = _zeros(2, B, Hh, device=dev)
@@ -270,7 +298,7 @@ def encoder_forward(ops, P, text, in_len, training, masks, seed, dev, packed=Tru
             ops.gemm(hst[d], Hh, 1, P["encoder.lstm.weight_hh_l0" + sfx], Hh, 1, rec[d], 4 * Hh, B, 4 * Hh, Hh)
             L("t2v_lstm_pointwise_fwd", rec[d], 1, 0, 4 * Hh, _p(GX[d], (2 + t) * 4 * Hh), Tp * 4 * Hh, None,
               P["encoder.lstm.bias_hh_l0" + sfx], cst[d], Hh, hst[d], Hh, None, 0, cst[d], Hh, GS[d, t], CS[d, t + 1],
-              _p(HoutP, (2 + t) * 512 + d * Hh), Tp * 512, None, None, 0, 0, 0, 0.0, 0, lens, t, B, Hh)
+              _p(HoutP, (2 + t) * 512 + d * Hh), Tp * 512, None, None, 0, 0, 0, 0.0, 0, lens, t, B, Hh, 0)
     ctx = dict(B=B, Ti=Ti, text=text, in_len=lens, conv=conv_saved, X3=X3, GS=GS, CS=CS, HoutP=HoutP)
     return HoutP, ctx
 
@@ -292,7 +320,7 @@ def encoder_backward(ops, P, dmem, ctx, training, seed, dev, grads):
         for t in order:
             cprev = CS[d, t] if d == 0 else CS[d, t + 2]          # cell after the previous step of this direction
             L("t2v_lstm_pointwise_bwd", _p(dmem, t * 512 + d * Hh), Ti * 512, dh, Hh, None, 0, dc, GS[d, t], CS[d, t + 1],
-              cprev, Hh, _p(DG, (2 + t) * 4 * Hh), Tp * 4 * Hh, None, None, 0, 0, 0, 0.0, 0, lens, t, B, Hh)
+              cprev, Hh, _p(DG, (2 + t) * 4 * Hh), Tp * 4 * Hh, None, None, 0, 0, 0, 0.0, 0, lens, t, B, Hh, 0)
             # dh_prev = dgates_t @ W_hh
             ops.gemm(_p(DG, (2 + t) * 4 * Hh), Tp * 4 * Hh, 1, Whh, 1, Hh, dh, Hh, B, Hh, 4 * Hh)
         # batched weight grads; h_prev of row r is HoutP[r -/+ 1] (zero pad rows make the boundaries right)
@@ -304,8 +332,10 @@ def encoder_backward(ops, P, dmem, ctx, training, seed, dev, grads):
         grads["encoder.lstm.weight_hh_l0" + sfx] = gWhh
         gWih = _zeros(4 * Hh, 512, device=dev)
         ops.linear_dw(DG, 4 * Hh, X3, 512, gWih, 512, R, 4 * Hh, 512, device=dev)
-        grads["encoder.lstm.weight_ih_l0" + sfx] = gWih
         gb = _colsum(DG, R, 4 * Hh, 1, 0, 1, dev)
+        if ops.tc:
+            L("t2v_round_tf32", DG, DG.numel())
+        grads["encoder.lstm.weight_ih_l0" + sfx] = gWih
         grads["encoder.lstm.bias_ih_l0" + sfx] = gb
         grads["encoder.lstm.bias_hh_l0" + sfx] = gb.clone()
         ops.linear_dx(DG, 4 * Hh, P["encoder.lstm.weight_ih_l0" + sfx], 512, dX3, 512, R, 4 * Hh, 512, accumulate=(d == 1))
@@ -334,14 +364,15 @@ def refenc_forward(ops, P, mel, training, dev):
         Co = filters[i]
         rows = N * Ho * Wo
         col = _empty(rows, 9 * Ct, device=dev)
-        L("t2v_im2col_3x3s2", x, col, N, Hc, Wc, Ci, 1 if i == 0 else 0)
+        L("t2v_im2col_3x3s2", x, col, N, Hc, Wc, Ci, 1 if i == 0 else 0, ops.R)
         wname = _REF + ("convs.0.conv" if i == 0 else "convs.%d" % i)
         Wk = _empty(Co, 9 * Ct, device=dev)
-        L("t2v_conv1d_pack", P[wname + ".weight"], Wk, Co, Ct, 9, 0)
+        L("t2v_conv1d_pack", P[wname + ".weight"], Wk, Co, Ct, 9, 0, ops.R)
         Y = _empty(rows, Co, device=dev)
         ops.linear(col, 9 * Ct, Wk, 9 * Ct, Y, Co, rows, Co, 9 * Ct, bias=P[wname + ".bias"])
         Xn = _empty(rows, Co, device=dev)
-        mi = _bn_forward(ops, Y, Xn, rows, Co, 1, 0, 1, rows, P, _REF + "bns.%d" % i, training, 1, None, 0, 0, 0.0, 1, dev)
+        mi = _bn_forward(ops, Y, Xn, rows, Co, 1, 0, 1, rows, P, _REF + "bns.%d" % i, training, 1, None, 0, 0, 0.0, 1, dev,
+                         rnd=ops.R if i == 5 else 0)
         layers.append(dict(col=col, Wk=Wk, Y=_Saved(Y, mi), rows=rows, Ct=Ct, Co=Co, H=Hc, W=Wc, Ci=Ci, wname=wname))
         x, Hc, Wc, Ci = Xn, Ho, Wo, Co
     Tq, Wq, Cq = Hc, Wc, Ci                       # GRU sequence length, remaining mel bins, channels
@@ -349,7 +380,7 @@ def refenc_forward(ops, P, mel, training, dev):
     Hh = P[_REF + "gru.weight_hh_l0"].shape[1]
     # reference feature order is c*W'+w (modules.py:73-76); ours is w*C+c -> permute the input weight columns
     Wih = _empty(3 * Hh, Fin, device=dev)
-    L("t2v_conv1d_pack", P[_REF + "gru.weight_ih_l0"], Wih, 3 * Hh, Cq, Wq, 0)
+    L("t2v_conv1d_pack", P[_REF + "gru.weight_ih_l0"], Wih, 3 * Hh, Cq, Wq, 0, ops.R)
     GI = _empty(N * Tq, 3 * Hh, device=dev)
     ops.linear(x, Fin, Wih, Fin, GI, 3 * Hh, N * Tq, 3 * Hh, Fin)
     HS = _zeros(Tq + 1, N, Hh, device=dev)
@@ -374,7 +405,7 @@ def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
     gWhh = _zeros(3 * Hh, Hh, device=dev)
     bh_acc = _zeros(3 * Hh, device=dev, dtype=torch.float64)
     for t in range(Tq - 1, -1, -1):
-        L("t2v_gru_pointwise_bwd", dh, SV[t], HS[t], _p(DGI, t * 3 * Hh), Tq * 3 * Hh, dgh, dhp, N, Hh)
+        L("t2v_gru_pointwise_bwd", dh, SV[t], HS[t], _p(DGI, t * 3 * Hh), Tq * 3 * Hh, dgh, dhp, N, Hh, ops.R)
         ops.gemm(dgh, 3 * Hh, 1, Whh, 1, Hh, dhp, Hh, N, Hh, 3 * Hh, 1.0, 1.0)          # dh_prev += dgh @ W_hh
         ops.gemm(dgh, 1, 3 * Hh, HS[t], 1, Hh, gWhh, Hh, 3 * Hh, Hh, N, 1.0, 1.0)        # dW_hh += dgh^T h_prev
         L("t2v_col_stats", dgh, N, 3 * Hh, 1, 0, 1, 2, bh_acc, None)
@@ -395,7 +426,8 @@ def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
         ly = ctx["layers"][i]
         rows, Co, Ct = ly["rows"], ly["Co"], ly["Ct"]
         dY = _empty(rows, Co, device=dev)
-        _bn_backward(dX, ly["Y"], dY, rows, Co, 1, 0, 1, rows, P, _REF + "bns.%d" % i, training, 1, None, 0, 0, 0.0, 1, dev, grads)
+        _bn_backward(dX, ly["Y"], dY, rows, Co, 1, 0, 1, rows, P, _REF + "bns.%d" % i, training, 1, None, 0, 0, 0.0, 1, dev, grads,
+                     rnd=ops.R)
         grads[ly["wname"] + ".bias"] = _colsum(dY, rows, Co, 1, 0, 1, dev)
         dWk = _zeros(Co, 9 * Ct, device=dev)
         ops.linear_dw(dY, Co, ly["col"], 9 * Ct, dWk, 9 * Ct, rows, Co, 9 * Ct, device=dev)
@@ -462,19 +494,19 @@ _D = "decoder."
 _A = "decoder.attention_layer."
 
 
-def pack_decoder_weights(P, dev):
+def pack_decoder_weights(P, dev, R=0):
     Wa = _empty(4096, 1792, device=dev)
-    L("t2v_copy2d", P[_D + "attention_rnn.weight_ih"], 768, 1, Wa, 1792, 4096, 768, 0.0)
-    L("t2v_copy2d", P[_D + "attention_rnn.weight_hh"], 1024, 1, _p(Wa, 768), 1792, 4096, 1024, 0.0)
+    L("t2v_copy2d", P[_D + "attention_rnn.weight_ih"], 768, 1, Wa, 1792, 4096, 768, 0.0, R)
+    L("t2v_copy2d", P[_D + "attention_rnn.weight_hh"], 1024, 1, _p(Wa, 768), 1792, 4096, 1024, 0.0, R)
     Wd = _empty(4096, 2560, device=dev)
-    L("t2v_copy2d", P[_D + "decoder_rnn.weight_ih"], 1536, 1, Wd, 2560, 4096, 1536, 0.0)
-    L("t2v_copy2d", P[_D + "decoder_rnn.weight_hh"], 1024, 1, _p(Wd, 1536), 2560, 4096, 1024, 0.0)
+    L("t2v_copy2d", P[_D + "decoder_rnn.weight_ih"], 1536, 1, Wd, 2560, 4096, 1536, 0.0, R)
+    L("t2v_copy2d", P[_D + "decoder_rnn.weight_hh"], 1024, 1, _p(Wd, 1536), 2560, 4096, 1024, 0.0, R)
     Wpg = _empty(81, 1536, device=dev)
-    L("t2v_copy2d", P[_D + "linear_projection.linear_layer.weight"], 1536, 1, Wpg, 1536, 80, 1536, 0.0)
-    L("t2v_copy2d", P[_D + "gate_layer.linear_layer.weight"], 1536, 1, _p(Wpg, 80 * 1536), 1536, 1, 1536, 0.0)
+    L("t2v_copy2d", P[_D + "linear_projection.linear_layer.weight"], 1536, 1, Wpg, 1536, 80, 1536, 0.0, R)
+    L("t2v_copy2d", P[_D + "gate_layer.linear_layer.weight"], 1536, 1, _p(Wpg, 80 * 1536), 1536, 1, 1536, 0.0, R)
     bpg = _empty(81, device=dev)
-    L("t2v_copy2d", P[_D + "linear_projection.linear_layer.bias"], 80, 1, bpg, 80, 1, 80, 0.0)
-    L("t2v_copy2d", P[_D + "gate_layer.linear_layer.bias"], 1, 1, _p(bpg, 80), 1, 1, 1, 0.0)
+    L("t2v_copy2d", P[_D + "linear_projection.linear_layer.bias"], 80, 1, bpg, 80, 1, 80, 0.0, 0)
+    L("t2v_copy2d", P[_D + "gate_layer.linear_layer.bias"], 1, 1, _p(bpg, 80), 1, 1, 1, 0.0, 0)
     return Wa, Wd, Wpg, bpg
 
 
@@ -490,7 +522,7 @@ def _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_v
     S.Wa, S.Wd = W["Wa"].data_ptr(), W["Wd"].data_ptr()
     S.ba1, S.ba2 = P[_D + "attention_rnn.bias_ih"].data_ptr(), P[_D + "attention_rnn.bias_hh"].data_ptr()
     S.bd1, S.bd2 = P[_D + "decoder_rnn.bias_ih"].data_ptr(), P[_D + "decoder_rnn.bias_hh"].data_ptr()
-    S.Wq = P[_A + "query_layer.linear_layer.weight"].data_ptr()
+    S.Wq = W["Wq"].data_ptr()
     S.Wconv = P[_A + "location_layer.location_conv.conv.weight"].data_ptr()
     S.Wloc = P[_A + "location_layer.location_dense.linear_layer.weight"].data_ptr()
     S.v = P[_A + "v.linear_layer.weight"].data_ptr()
@@ -517,26 +549,29 @@ def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, dro
     B, Ti, _ = memory.shape
     To = mel_tgt.shape[2]
     W = {}
-    W["Wa"], W["Wd"], W["Wpg"], W["bpg"] = pack_decoder_weights(P, dev)
+    W["Wa"], W["Wd"], W["Wpg"], W["bpg"] = pack_decoder_weights(P, dev, ops.R)
+    W["Wq"] = ops.wr(P[_A + "query_layer.linear_layer.weight"])
     pmem = _empty(B * Ti, 128, device=dev)
-    ops.linear(memory, 512, P[_A + "memory_layer.linear_layer.weight"], 512, pmem, 128, B * Ti, 128, 512)
+    ops.linear(memory, 512, ops.wr(P[_A + "memory_layer.linear_layer.weight"]), 512, pmem, 128, B * Ti, 128, 512)
     buf = alloc_decoder_buffers(B, Ti, To, dev, save=True)
     # prenet over the go frame + all teacher frames (model.py:406-409); dropout always on (model.py:101)
     Fr = _empty((To + 1) * B, 80, device=dev)
-    L("t2v_bct_to_rows_tb_shift", mel_tgt, Fr, B, 80, To)
+    L("t2v_bct_to_rows_tb_shift", mel_tgt, Fr, B, 80, To, ops.R)
     n = (To + 1) * B
     P1pre = _empty(n, 256, device=dev)
-    ops.linear(Fr, 80, P[_D + "prenet.layers.0.linear_layer.weight"], 80, P1pre, 256, n, 256, 80)
+    ops.linear(Fr, 80, ops.wr(P[_D + "prenet.layers.0.linear_layer.weight"]), 80, P1pre, 256, n, 256, 80)
     P1 = _empty(n, 256, device=dev)
     m0 = None if prenet_masks is None else prenet_masks[0]
     m1 = None if prenet_masks is None else prenet_masks[1]
-    L("t2v_relu_drop_fwd", P1pre, P1, 256, n, 256, m0, seed, SITE_PRENET, 0.5, 0)
+    L("t2v_relu_drop_fwd", P1pre, P1, 256, n, 256, m0, seed, SITE_PRENET, 0.5, 0, ops.R)
     P2pre = _empty(n, 256, device=dev)
-    ops.linear(P1, 256, P[_D + "prenet.layers.1.linear_layer.weight"], 256, P2pre, 256, n, 256, 256)
-    L("t2v_relu_drop_fwd", P2pre, buf["XA"], 1792, n, 256, m1, seed, SITE_PRENET + 1, 0.5, 0)
+    ops.linear(P1, 256, ops.wr(P[_D + "prenet.layers.1.linear_layer.weight"]), 256, P2pre, 256, n, 256, 256)
+    L("t2v_relu_drop_fwd", P2pre, buf["XA"], 1792, n, 256, m1, seed, SITE_PRENET + 1, 0.5, 0, ops.R)
     S = _lib.T2VDecoderSeq()
     _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_value, in_len, memory, pmem, buf)
+    _trace("  fwd prenet+pack")
     L("t2v_decoder_fwd_steps", S, 0, To)
+    _trace("  fwd decoder loop")
     # deferred mel/gate projection of [h_dec_t | ctx_t] for all steps (model.py:383-388)
     O = _zeros(To * B, 84, device=dev)
     ops.linear(_p(buf["XD"], B * 2560 + 1536), 2560, W["Wpg"], 1536, O, 84, To * B, 81, 1024, bias=W["bpg"], a_rows=To * B)
@@ -563,13 +598,14 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
     grads[_D + "linear_projection.linear_layer.bias"] = gbpg[:80].contiguous()
     grads[_D + "gate_layer.linear_layer.bias"] = gbpg[80:81].contiguous()
     # reverse time loop
-    Wq = P[_A + "query_layer.linear_layer.weight"]
+    Wq = W["Wq"]
     WaT = _empty(1792, 4096, device=dev)
     WdT = _empty(2560, 4096, device=dev)
     WqT = _empty(1024, 128, device=dev)
-    L("t2v_transpose", W["Wa"], 1792, WaT, 4096, 4096, 1792)
-    L("t2v_transpose", W["Wd"], 2560, WdT, 4096, 4096, 2560)
-    L("t2v_transpose", Wq, 1024, WqT, 128, 128, 1024)
+    L("t2v_transpose", W["Wa"], 1792, WaT, 4096, 4096, 1792, 0)
+    L("t2v_transpose", W["Wd"], 2560, WdT, 4096, 4096, 2560, 0)
+    L("t2v_transpose", Wq, 1024, WqT, 128, 128, 1024, 0)
+    _trace("  bwd proj")
     D = _lib.T2VDecoderBwd()
     _ctypes.memmove(_ctypes.addressof(D.f), _ctypes.addressof(ctx["S"]), _ctypes.sizeof(_lib.T2VDecoderSeq))
     t = dict(WaT=WaT, WdT=WdT, WqT=WqT, DHC=DHC, DGA=_empty(n, 4096, device=dev), DGD=_empty(n, 4096, device=dev),
@@ -581,6 +617,7 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
     for k, v in t.items():
         setattr(D, k, v.data_ptr())
     L("t2v_decoder_bwd_steps", D, To, 0)
+    _trace("  bwd decoder loop")
     # batched weight gradients over all steps
     gWa = _zeros(4096, 1792, device=dev)
     ops.linear_dw(t["DGA"], 4096, XA, 1792, gWa, 1792, n, 4096, 1792, device=dev)
@@ -603,22 +640,25 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
         g = _empty(cols, device=dev)
         L("t2v_sum_rows_per_batch", part, g, 1, B, cols, 0.0)
         grads[name] = g.view_as(P[name])
+    _trace("  bwd decoder dW")
     # prenet backward (model.py:91-102)
     dP2pre = _empty(n, 256, device=dev)
-    L("t2v_relu_drop_bwd", ctx["P2pre"], t["DXA"], 1792, dP2pre, n, 256, ctx["m1"], ctx["seed"], SITE_PRENET + 1, 0.5, 0)
+    L("t2v_relu_drop_bwd", ctx["P2pre"], t["DXA"], 1792, dP2pre, n, 256, ctx["m1"], ctx["seed"], SITE_PRENET + 1, 0.5, 0, ops.R)
     g2 = _zeros(256, 256, device=dev)
     ops.linear_dw(dP2pre, 256, ctx["P1"], 256, g2, 256, n, 256, 256, device=dev)
     grads[_D + "prenet.layers.1.linear_layer.weight"] = g2
     dP1 = _empty(n, 256, device=dev)
     ops.linear_dx(dP2pre, 256, P[_D + "prenet.layers.1.linear_layer.weight"], 256, dP1, 256, n, 256, 256)
     dP1pre = _empty(n, 256, device=dev)
-    L("t2v_relu_drop_bwd", ctx["P1pre"], dP1, 256, dP1pre, n, 256, ctx["m0"], ctx["seed"], SITE_PRENET, 0.5, 0)
+    L("t2v_relu_drop_bwd", ctx["P1pre"], dP1, 256, dP1pre, n, 256, ctx["m0"], ctx["seed"], SITE_PRENET, 0.5, 0, ops.R)
     g1 = _zeros(256, 80, device=dev)
     ops.linear_dw(dP1pre, 256, ctx["Fr"], 80, g1, 80, n, 256, 80, device=dev)
     grads[_D + "prenet.layers.0.linear_layer.weight"] = g1
     # memory_layer backward; dmemory = dmem(ctx path) + dpmem @ W_m
     Wm = P[_A + "memory_layer.linear_layer.weight"]
     gWm = _zeros(128, 512, device=dev)
+    if ops.tc:
+        L("t2v_round_tf32", t["dpmem"], t["dpmem"].numel())
     ops.linear_dw(t["dpmem"], 128, ctx["memory"], 512, gWm, 512, B * Ti, 128, 512, device=dev)
     grads[_A + "memory_layer.linear_layer.weight"] = gWm
     ops.linear_dx(t["dpmem"], 128, Wm, 512, t["dmem"], 512, B * Ti, 128, 512, accumulate=True)
@@ -628,7 +668,7 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
 # ======================================================================================================= postnet + outputs
 def postnet_forward(ops, P, X0p, B, To, training, masks, seed, dev):
     return conv_stack_forward(ops, P, "postnet.convolutions", X0p, B, To, [80, 512, 512, 512, 512, 80], [2, 2, 2, 2, 0],
-                              training, masks, seed, SITE_POST, dev)
+                              training, masks, seed, SITE_POST, dev, round_last=False)
 
 
 class TrainContext(object):
@@ -645,6 +685,7 @@ def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=No
     c = TrainContext()
     c.B, c.Ti, c.To, c.training, c.seed, c.rand = B, Ti, To, training, seed, rand
     g = (lambda name: None) if rand is None else (lambda name: getattr(rand, name))
+    _trace("")
     HoutP, c.enc = encoder_forward(ops, P, text, in_len, training, g("enc"), seed, dev, packed=True)
     eps = g("eps")
     if training and eps is None:
@@ -652,13 +693,21 @@ def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=No
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed + 977)
         eps.normal_(generator=gen)
+    _trace("fwd encoder")
     style, mulv, z, c.vae = vae_forward(ops, P, mel_tgt, training, eps, dev)
+    _trace("fwd vae/ref-encoder")
     memory = _empty(B, Ti, 512, device=dev)
-    L("t2v_unpad_add", HoutP, style, memory, B, Ti, 512)                         # model.py:536-537
+    L("t2v_unpad_add", HoutP, style, memory, B, Ti, 512, ops.R)                  # model.py:536-537
     O, align, c.dec = decoder_forward(ops, P, memory, mel_tgt, in_len, training, g("prenet"), g("dec"), seed, mask_value, dev)
+    _trace("fwd decoder")
     X0p = _zeros(B * (To + 4), 80, device=dev)
-    L("t2v_rows_tb_to_padded", O, 84, X0p, B, 80, To)
-    Y5, c.post = postnet_forward(ops, P, X0p, B, To, training, g("post"), seed, dev)
+    L("t2v_rows_tb_to_padded", O, 84, X0p, B, 80, To, 0)
+    X0r = X0p                                             # Postnet conv-0 operand (tf32-rounded copy in the tensor-core mode)
+    if ops.tc:
+        X0r = _zeros(B * (To + 4), 80, device=dev)
+        L("t2v_rows_tb_to_padded", O, 84, X0r, B, 80, To, 1)
+    Y5, c.post = postnet_forward(ops, P, X0r, B, To, training, g("post"), seed, dev)
+    _trace("fwd postnet")
     lens = out_len if mask_padding else None
     mel = _empty(B, 80, To, device=dev)
     mel_post = _empty(B, 80, To, device=dev)
@@ -667,7 +716,7 @@ def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=No
     L("t2v_padded_to_bct", X0p, Y5, mel_post, B, 80, To, lens, 0.0)
     L("t2v_gate_from_rows", O, 84, 80, gate, B, To, lens, 1000.0)
     if mask_padding:
-        L("t2v_mask_padded_rows", X0p, B, 80, To, out_len)      # Postnet conv-0's saved input becomes the masked mel (Q10)
+        L("t2v_mask_padded_rows", X0r, B, 80, To, out_len)      # Postnet conv-0's saved input becomes the masked mel (Q10)
     Z = c.vae["Z"]
     mu = mulv[:, :Z].contiguous()
     logvar = mulv[:, Z:].contiguous()
@@ -680,18 +729,23 @@ def backward_train(ops, P, c, dmel, dpost, dgate, dmu, dlogvar):
     B, Ti, To = c.B, c.Ti, c.To
     grads = {}
     R = B * (To + 4)
+    _trace("")
     dY5 = _zeros(R, 80, device=dev)
     L("t2v_bct_to_padded", dpost, dY5, B, 80, To, 0.0)
     dX0 = conv_stack_backward(ops, P, "postnet.convolutions", dY5, c.post, B, To, c.training, c.seed, SITE_POST, dev, grads,
                               need_dx=True)
+    _trace("bwd postnet")
     dres = _zeros(R, 80, device=dev)                      # dmel + dpost (residual, model.py:543)
     L("t2v_bct_to_padded", dmel, dres, B, 80, To, 0.0)
     L("t2v_bct_to_padded", dpost, dres, B, 80, To, 1.0)
     dO = _empty(To * B, 84, device=dev)
-    L("t2v_padded_to_rows_tb", dX0, dres, dgate, dO, 84, B, 80, To)
+    L("t2v_padded_to_rows_tb", dX0, dres, dgate, dO, 84, B, 80, To, ops.R)
     dmem = decoder_backward(ops, P, dO, c.dec, dev, grads)
+    _trace("bwd decoder")
     dstyle = _empty(B, 512, device=dev)
     L("t2v_sum_rows_per_batch", dmem, dstyle, B, Ti, 512, 0.0)
     vae_backward(ops, P, dstyle, dmu, dlogvar, c.vae, dev, grads)
+    _trace("bwd vae/ref-encoder")
     encoder_backward(ops, P, dmem, c.enc, c.training, c.seed, dev, grads)
+    _trace("bwd encoder")
     return grads

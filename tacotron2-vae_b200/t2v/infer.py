@@ -50,7 +50,7 @@ def embedding(P, ids):
     B, Ti = ids.shape
     X0 = engine.embedding_forward(P, ids, ids.device)
     out = torch.empty(B, Ti, 512, device=ids.device)
-    L("t2v_unpad_add", X0, None, out, B, Ti, 512)
+    L("t2v_unpad_add", X0, None, out, B, Ti, 512, 0)
     return out
 
 
@@ -64,7 +64,7 @@ def encoder_inference(ops, P, x_bct, training):
     L("t2v_bct_to_padded", x, X0, B, C, Ti, 0.0)
     HoutP, _ = engine.encoder_forward(ops, P, None, None, training, None, 0, dev, packed=False, X0=X0, shape=(B, Ti))
     out = torch.empty(B, Ti, 512, device=dev)
-    L("t2v_unpad_add", HoutP, None, out, B, Ti, 512)
+    L("t2v_unpad_add", HoutP, None, out, B, Ti, 512, 0)
     return out
 
 
@@ -106,7 +106,7 @@ def prenet(P, x, masks=None, seed=0, base=0):
         engine.Ops.gemm(h, h.shape[1], 1, W, W.shape[1], 1, pre, W.shape[0], n, W.shape[0], W.shape[1])
         out = torch.empty_like(pre)
         m = None if masks is None else masks[i].contiguous().float()
-        L("t2v_relu_drop_fwd", pre, out, W.shape[0], n, W.shape[0], m, seed, engine.SITE_PRENET + i, 0.5, base)
+        L("t2v_relu_drop_fwd", pre, out, W.shape[0], n, W.shape[0], m, seed, engine.SITE_PRENET + i, 0.5, base, 0)
         h = out
     return h.view(*lead, h.shape[1])
 
@@ -124,10 +124,11 @@ class DecoderSession(object):
         dev = memory.device
         self.dev = dev
         self.W = {}
-        self.W["Wa"], self.W["Wd"], self.W["Wpg"], self.W["bpg"] = engine.pack_decoder_weights(P, dev)
+        self.W["Wa"], self.W["Wd"], self.W["Wpg"], self.W["bpg"] = engine.pack_decoder_weights(P, dev, ops.R)
+        self.W["Wq"] = ops.wr(P["decoder.attention_layer.query_layer.linear_layer.weight"])
         self.memory = memory
         self.pmem = torch.empty(self.B * self.Ti, 128, device=dev)
-        ops.linear(memory, 512, P["decoder.attention_layer.memory_layer.linear_layer.weight"], 512, self.pmem, 128,
+        ops.linear(memory, 512, ops.wr(P["decoder.attention_layer.memory_layer.linear_layer.weight"]), 512, self.pmem, 128,
                    self.B * self.Ti, 128, 512)
         self.buf = engine.alloc_decoder_buffers(self.B, self.Ti, self.To, dev, save=False)
         self.O = torch.zeros(self.To * self.B, 84, device=dev)
@@ -142,7 +143,7 @@ class DecoderSession(object):
             raise RuntimeError("decoder session exhausted (%d steps)" % self.To)
         B, t = self.B, self.t
         x = prenet_out.contiguous().float()
-        L("t2v_copy2d", x, 256, 1, engine._p(self.buf["XA"], t * B * 1792), 1792, B, 256, 0.0)
+        L("t2v_copy2d", x, 256, 1, engine._p(self.buf["XA"], t * B * 1792), 1792, B, 256, 0.0, self.ops.R)
         L("t2v_decoder_fwd_steps", self.S, t, t + 1)
         o = engine._p(self.O, t * B * 84)
         XD = self.buf["XD"]
@@ -162,8 +163,9 @@ class DecoderSession(object):
         D.f.seed = seed
         P1 = torch.empty(2 * B, 256, device=self.dev)
         nfr = torch.full((B,), -1, device=self.dev, dtype=torch.int32)
-        D.Wp1 = P["decoder.prenet.layers.0.linear_layer.weight"].data_ptr()
-        D.Wp2 = P["decoder.prenet.layers.1.linear_layer.weight"].data_ptr()
+        Wp1 = self.ops.wr(P["decoder.prenet.layers.0.linear_layer.weight"])
+        Wp2 = self.ops.wr(P["decoder.prenet.layers.1.linear_layer.weight"])
+        D.Wp1, D.Wp2 = Wp1.data_ptr(), Wp2.data_ptr()
         D.Wpg, D.bpg = self.W["Wpg"].data_ptr(), self.W["bpg"].data_ptr()
         D.prenet_masks = _lib.ptr(prenet_masks)
         D.O, D.P1 = self.O.data_ptr(), P1.data_ptr()
@@ -171,7 +173,7 @@ class DecoderSession(object):
         D.n_frames = nfr.data_ptr()
         L("t2v_decoder_infer_steps", D, self.t, self.t + n_steps)
         self.t += n_steps
-        self._keep = (P1, prenet_masks)
+        self._keep = (P1, prenet_masks, Wp1, Wp2)
         return nfr
 
     def outputs(self, n=None):

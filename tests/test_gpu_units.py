@@ -72,7 +72,7 @@ def test_gemm_tc_taps_is_conv1d(L):
         X = torch.zeros(B * Tp, Ci, device=dev)
         L("t2v_bct_to_padded", x, X, B, Ci, T, 0.0)
         Wk = torch.empty(Co, 5 * Ci, device=dev)
-        L("t2v_conv1d_pack", w, Wk, Co, Ci, 5, 0)
+        L("t2v_conv1d_pack", w, Wk, Co, Ci, 5, 0, 0)
         ref = torch.nn.functional.conv1d(x.cpu(), w.cpu(), b.cpu(), padding=2)
         for mode in ("f32", "tc"):
             Y = torch.zeros(B * Tp, Co, device=dev)
@@ -104,7 +104,7 @@ def test_bn_act_dropout_matches_torch(L):
     rm = torch.zeros(C, device=dev); rv = torch.ones(C, device=dev); nbt = torch.zeros((), device=dev, dtype=torch.long)
     L("t2v_bn_finalize", sums[0], sums[1], float(B * T), C, 1e-5, 0.1, mean, invstd, rm, rv, nbt)
     out = torch.empty_like(Y)
-    L("t2v_bn_act_fwd", Y, out, B * Tp, C, Tp, 2, 2 + T, mean, invstd, gamma, beta, 2, mask, 0, 0, 0.5, T)
+    L("t2v_bn_act_fwd", Y, out, B * Tp, C, Tp, 2, 2 + T, mean, invstd, gamma, beta, 2, mask, 0, 0, 0.5, T, 0)
     o = torch.empty(B, C, T, device=dev)
     L("t2v_padded_to_bct", out, None, o, B, C, T, None, 0.0)
     xr = x.cpu().double().requires_grad_(True)
@@ -123,7 +123,7 @@ def test_bn_act_dropout_matches_torch(L):
     L("t2v_bn_act_bwd_reduce", G, Y, B * Tp, C, Tp, 2, 2 + T, mean, invstd, gamma, beta, 2, mask, 0, 0, 0.5, T, s2[0], s2[1])
     dY = torch.empty_like(Y)
     L("t2v_bn_act_bwd_apply", G, Y, dY, B * Tp, C, Tp, 2, 2 + T, mean, invstd, gamma, beta, 2, mask, 0, 0, 0.5, T, s2[0], s2[1],
-      float(B * T), 1)
+      float(B * T), 1, 0)
     dx = torch.empty(B, C, T, device=dev)
     L("t2v_padded_to_bct", dY, None, dx, B, C, T, None, 0.0)
     assert _rel(dx.cpu().double(), xr.grad) < 1e-4
@@ -136,7 +136,7 @@ def test_embedding_bit_exact(L):
     ids = torch.randint(0, 80, (4, 33), device=dev)
     table = torch.randn(80, 512, device=dev)
     out = torch.zeros(4 * 37, 512, device=dev)
-    L("t2v_embedding_fwd", ids, table, out, 4, 33, 512, 80)
+    L("t2v_embedding_fwd", ids, table, out, 4, 33, 512, 80, 0)
     ref = table.cpu()[ids.cpu()]
     assert torch.equal(out.view(4, 37, 512)[:, 2:35].cpu(), ref)
 
@@ -165,7 +165,7 @@ def test_attention_step_matches_port(L):
     c1 = torch.empty(B, 512, device=dev); c2 = torch.empty(B, 600, device=dev); a_save = torch.empty(B, Ti, 128, device=dev)
     L("t2v_attn_step_fwd", g(q), 1, 0, g(wprev), Ti, g(cum), cum_out, g(pmem), g(mem),
       g(P[pre + "location_layer.location_conv.conv.weight"]), g(P[pre + "location_layer.location_dense.linear_layer.weight"]),
-      g(P[pre + "v.linear_layer.weight"]), g(lens), -float("inf"), w_out, Ti, c1, 512, c2, 600, a_save, B, Ti)
+      g(P[pre + "v.linear_layer.weight"]), g(lens), -float("inf"), w_out, Ti, c1, 512, c2, 600, a_save, B, Ti, 0)
     assert torch.allclose(w_out.cpu(), w_ref, atol=2e-6)
     assert torch.allclose(c1.cpu(), ctx_ref, atol=1e-5)
     assert torch.equal(c2[:, :512], c1)
