@@ -369,11 +369,13 @@ def refenc_forward(ops, P, mel, training, dev):
         Wk = _empty(Co, 9 * Ct, device=dev)
         L("t2v_conv1d_pack", P[wname + ".weight"], Wk, Co, Ct, 9, 0, ops.R)
         Y = _empty(rows, Co, device=dev)
-        ops.linear(col, 9 * Ct, Wk, 9 * Ct, Y, Co, rows, Co, 9 * Ct, bias=P[wname + ".bias"])
+        # late layers normalise over very few samples (BN2d over N*H'*W' positions): keep them exact
+        exact = rows < 100000
+        ops.linear(col, 9 * Ct, Wk, 9 * Ct, Y, Co, rows, Co, 9 * Ct, bias=P[wname + ".bias"], force_exact=exact)
         Xn = _empty(rows, Co, device=dev)
         mi = _bn_forward(ops, Y, Xn, rows, Co, 1, 0, 1, rows, P, _REF + "bns.%d" % i, training, 1, None, 0, 0, 0.0, 1, dev,
                          rnd=ops.R if i == 5 else 0)
-        layers.append(dict(col=col, Wk=Wk, Y=_Saved(Y, mi), rows=rows, Ct=Ct, Co=Co, H=Hc, W=Wc, Ci=Ci, wname=wname))
+        layers.append(dict(col=col, Wk=Wk, Y=_Saved(Y, mi), rows=rows, Ct=Ct, Co=Co, H=Hc, W=Wc, Ci=Ci, wname=wname, exact=exact))
         x, Hc, Wc, Ci = Xn, Ho, Wo, Co
     Tq, Wq, Cq = Hc, Wc, Ci                       # GRU sequence length, remaining mel bins, channels
     Fin = Wq * Cq
@@ -382,7 +384,7 @@ def refenc_forward(ops, P, mel, training, dev):
     Wih = _empty(3 * Hh, Fin, device=dev)
     L("t2v_conv1d_pack", P[_REF + "gru.weight_ih_l0"], Wih, 3 * Hh, Cq, Wq, 0, ops.R)
     GI = _empty(N * Tq, 3 * Hh, device=dev)
-    ops.linear(x, Fin, Wih, Fin, GI, 3 * Hh, N * Tq, 3 * Hh, Fin)
+    ops.linear(x, Fin, Wih, Fin, GI, 3 * Hh, N * Tq, 3 * Hh, Fin, force_exact=True)
     HS = _zeros(Tq + 1, N, Hh, device=dev)
     SV = _empty(Tq, N, 4 * Hh, device=dev)
     gh = _empty(N, 3 * Hh, device=dev)
@@ -416,12 +418,12 @@ def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
     grads[_REF + "gru.bias_hh_l0"] = gbh
     grads[_REF + "gru.bias_ih_l0"] = _colsum(DGI, N * Tq, 3 * Hh, 1, 0, 1, dev)
     gWihp = _zeros(3 * Hh, Fin, device=dev)
-    ops.linear_dw(DGI, 3 * Hh, ctx["X6"], Fin, gWihp, Fin, N * Tq, 3 * Hh, Fin, device=dev)
+    ops.linear_dw(DGI, 3 * Hh, ctx["X6"], Fin, gWihp, Fin, N * Tq, 3 * Hh, Fin, device=dev, force_exact=True)
     gWih = _empty(3 * Hh, Fin, device=dev)
     L("t2v_conv1d_unpack_grad", gWihp, gWih, 3 * Hh, ctx["Cq"], ctx["Wq"], 0.0)
     grads[_REF + "gru.weight_ih_l0"] = gWih
     dX = _empty(N * Tq, Fin, device=dev)
-    ops.linear_dx(DGI, 3 * Hh, ctx["Wih"], Fin, dX, Fin, N * Tq, 3 * Hh, Fin)
+    ops.linear_dx(DGI, 3 * Hh, ctx["Wih"], Fin, dX, Fin, N * Tq, 3 * Hh, Fin, force_exact=True)
     for i in range(5, -1, -1):
         ly = ctx["layers"][i]
         rows, Co, Ct = ly["rows"], ly["Co"], ly["Ct"]
@@ -430,13 +432,13 @@ def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
                      rnd=ops.R)
         grads[ly["wname"] + ".bias"] = _colsum(dY, rows, Co, 1, 0, 1, dev)
         dWk = _zeros(Co, 9 * Ct, device=dev)
-        ops.linear_dw(dY, Co, ly["col"], 9 * Ct, dWk, 9 * Ct, rows, Co, 9 * Ct, device=dev)
+        ops.linear_dw(dY, Co, ly["col"], 9 * Ct, dWk, 9 * Ct, rows, Co, 9 * Ct, device=dev, force_exact=ly["exact"])
         gW = torch.empty_like(P[ly["wname"] + ".weight"])
         L("t2v_conv1d_unpack_grad", dWk, gW, Co, Ct, 9, 0.0)
         grads[ly["wname"] + ".weight"] = gW
         if i > 0:
             dcol = _empty(rows, 9 * Ct, device=dev)
-            ops.linear_dx(dY, Co, ly["Wk"], 9 * Ct, dcol, 9 * Ct, rows, Co, 9 * Ct)
+            ops.linear_dx(dY, Co, ly["Wk"], 9 * Ct, dcol, 9 * Ct, rows, Co, 9 * Ct, force_exact=ly["exact"])
             dX = _empty(N * ly["H"] * ly["W"], ly["Ci"], device=dev)
             L("t2v_col2im_3x3s2", dcol, dX, N, ly["H"], ly["W"], ly["Ci"])
 
