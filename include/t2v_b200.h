@@ -27,6 +27,7 @@ const char* t2v_last_error(void);
 int t2v_version(void);
 unsigned long long t2v_launch_count(void);      /* kernels launched by this library since the last reset */
 void t2v_reset_launch_count(void);
+void t2v_add_launch_count(unsigned long long n);   /* account for launches replayed from a captured CUDA graph */
 
 /* ---- GEMMs: every nn.Linear / Conv1d / LSTM-cell matmul of model.py goes through one of these two ------------ */
 /* exact fp32 FFMA, fully strided: C[m,n] = alpha*sum_k A[m*a_rs+k*a_cs]*B[n*b_rs+k*b_cs] + beta*C + bias[n] */
@@ -91,7 +92,10 @@ int t2v_gate_from_rows(const float* rows, long long ld, int col, float* gate, in
 int t2v_mask_padded_rows(float* x, int B, int C, int T, const long long* lens, cudaStream_t stream); /* model.py:515 */
 int t2v_unpad_add(const float* in_padded, const float* add_vec, float* out, int B, int T, int C, int rnd,
                   cudaStream_t stream);
-int t2v_round_tf32(float* x, long long n, cudaStream_t stream);   /* in-place round-to-nearest onto the tf32 grid */
+int t2v_round_tf32(float* x, long long n, cudaStream_t stream);
+/* standard-normal samples from the counter-based RNG (the VAE eps, modules.py:19).  Every `seed` argument of this ABI is a
+   value or, with bit 63 set, a device pointer to the value (so CUDA-graph replays can change it). */
+int t2v_randn(float* out, long long n, unsigned long long seed, unsigned int site, cudaStream_t stream);   /* in-place round-to-nearest onto the tf32 grid */
 
 /* ---- Prenet pointwise (model.py:91-102) and dropout-mask materialisation for the oracle ------------------------- */
 int t2v_relu_drop_fwd(const float* x, float* out, long long o_rs, long long rows, int C, const float* mask,
@@ -142,6 +146,20 @@ int t2v_attn_step_bwd(const float* dctx1, long long dctx1_rs, const float* dctx2
                       float* dpmem, float* dq, float* dv_part, float* dwloc_part, float* dwconv_part, int B, int Ti,
                       int rnd, cudaStream_t stream);
 
+/* version 2 of the attention step: work spread over (utterance x text-chunk) and (utterance x channel-chunk) CTAs */
+int t2v_attn2_chunks(int Ti);
+int t2v_attn2_fwd(const float* qparts, int n_qparts, long long qpart_stride, const float* w_prev, long long wprev_rs,
+                  const float* cum_in, float* cum_out, const float* pmem, const float* mem, const float* w_conv,
+                  const float* w_loc, const float* v, const long long* lens, float mask_value, float* e_buf, float* w_out,
+                  long long wout_rs, float* ctx_out1, long long ctx1_rs, float* ctx_out2, long long ctx2_rs, float* a_save,
+                  int B, int Ti, int rnd, cudaStream_t stream);
+int t2v_attn2_bwd(const float* dctx1, long long dctx1_rs, const float* dctx2, long long dctx2_rs, const float* dctx3,
+                  long long dctx3_rs, float* dctx_out, const float* dw_in, float* dw_out, const float* gcum_prev,
+                  float* gcum_next, float* dw_part, const float* w, long long w_rs, const float* w_prev, long long wprev_rs,
+                  const float* cum_in, const float* a_save, const float* mem, const float* w_conv, const float* w_loc,
+                  const float* v, const long long* lens, float* dpmem, float* dq, float* dv_part, float* dwloc_part,
+                  float* dwconv_part, int B, int Ti, cudaStream_t stream);
+
 /* ---- the decoder time loop: Decoder.decode / Decoder.forward / Decoder.inference (model.py:346-464) ------------- */
 typedef struct T2VDecoderSeq {
   int B, Ti, To;                 /* batch, padded text length, number of decoder steps the buffers hold */
@@ -163,6 +181,7 @@ typedef struct T2VDecoderSeq {
   float *GA, *GD, *CPA, *CPD;    /* saved gates [To,B,4096] / pre-dropout cells [To,B,1024]; NULL at inference */
   float *ASAVE;                  /* [To,B,Ti,128] tanh activations; NULL at inference */
   float *parts, *qparts;         /* split-K workspaces: >= 8*B*4096 and 8*B*128 floats */
+  float *ebuf;                   /* [B,Ti] attention energies scratch */
 } T2VDecoderSeq;
 int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);
 
@@ -175,11 +194,13 @@ typedef struct T2VDecoderBwd {
   float *DXD;                    /* ring [2,B,2560] */
   float *dCa, *dCd;              /* [B,1024] running cell-state grads (zero-initialised by caller) */
   float *dwprev;                 /* ring [2,B,Ti] */
-  float *gcum;                   /* [B,Ti] zero-initialised */
-  float *dmem, *dpmem;           /* [B,Ti,512], [B,Ti,128] accumulators (zero-initialised) */
-  float *DQ;                     /* out [To,B,128] */
+  float *gcum;                   /* ring [2,B,Ti] zero-initialised */
+  float *dpmem;                  /* [B,Ti,128] accumulator (zero-initialised) */
+  float *DCTX;                   /* out [To,B,512] total grad wrt ctx_t (d(memory) is one batched GEMM after the loop) */
+  float *dw_part;                /* scratch [4,B,Ti] */
+  float *DQ;                     /* out [To,B,128], zero-initialised (accumulated with atomics) */
   float *dHq;                    /* scratch [B,1024] */
-  float *dv_part, *dwloc_part, *dwconv_part;   /* [B,128], [B,128,32], [B,32,2,31] accumulators (zero-initialised) */
+  float *dv_part, *dwloc_part, *dwconv_part;   /* [B*nchunk,128], [B*nchunk,128*32], [B*nchunk,32*2*31] accumulators (zero-init), nchunk = t2v_attn2_chunks(Ti) */
 } T2VDecoderBwd;
 int t2v_decoder_bwd_steps(const T2VDecoderBwd* s, int t_hi, int t_lo, cudaStream_t stream);  /* t = t_hi-1 .. t_lo */
 

@@ -16,3 +16,4 @@ T2V_API const char* t2v_last_error(void) { return g_err; }
 T2V_API int t2v_version(void) { return 100; }
 T2V_API unsigned long long t2v_launch_count(void) { return g_t2v_launches; }
 T2V_API void t2v_reset_launch_count(void) { g_t2v_launches = 0; }
+T2V_API void t2v_add_launch_count(unsigned long long n) { g_t2v_launches += n; }   /* launches replayed from a CUDA graph */

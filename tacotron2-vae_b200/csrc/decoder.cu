@@ -7,6 +7,7 @@
 // buffers are the saved activations of the batched weight-gradient GEMMs.  linear_projection / gate_layer are
 // deferred to one GEMM over all steps under teacher forcing (nothing in the loop consumes them).
 #include "t2v_common.cuh"
+#include <stdlib.h>
 #include "gemm_tc.h"
 #include "../../include/t2v_b200.h"
 
@@ -49,6 +50,43 @@ int run_gemm(const StepGemm* g, long long a_row0, float* D, cudaStream_t st) {
 }
 #define CHK(expr) do { int r__ = (expr); if (r__) return r__; } while (0)
 
+// T2V_STEP_PROFILE=1: CUDA events after every launch of a few mid-sequence steps; averages printed to stderr.
+struct StepProfiler {
+  static constexpr int MAXE = 16, NSTEPS = 16;
+  bool on = false; int t_first = 0, slot = 0, step = -1, nslots = 0;
+  cudaEvent_t ev[NSTEPS][MAXE + 1];
+  const char* names[MAXE];
+  void begin(int t_begin, int t_end) {
+    on = getenv("T2V_STEP_PROFILE") != nullptr && (t_end - t_begin) >= NSTEPS + 8;
+    if (!on) return;
+    nslots = 0;
+    t_first = t_begin + 4;
+    for (int i = 0; i < NSTEPS; ++i) for (int j = 0; j <= MAXE; ++j) cudaEventCreate(&ev[i][j]);
+  }
+  bool active(int idx) const { return on && idx >= 0 && idx < NSTEPS; }
+  void step_begin(int idx, cudaStream_t st) { step = idx; slot = 0; if (active(step)) cudaEventRecord(ev[step][0], st); }
+  void mark(const char* name, cudaStream_t st) {
+    if (!active(step) || slot >= MAXE) return;
+    names[slot] = name; ++slot; cudaEventRecord(ev[step][slot], st); if (slot > nslots) nslots = slot;
+  }
+  void end(const char* title, cudaStream_t st) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[t2v step profile] %s (avg over %d steps, event-to-event us)\n", title, NSTEPS);
+    float total = 0;
+    for (int j = 0; j < nslots; ++j) {
+      float acc = 0;
+      for (int i = 0; i < NSTEPS; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i][j], ev[i][j + 1]); acc += ms; }
+      fprintf(stderr, "   %-22s %8.2f\n", names[j], acc * 1e3f / NSTEPS);
+      total += acc * 1e3f / NSTEPS;
+    }
+    fprintf(stderr, "   %-22s %8.2f\n", "sum", total);
+    for (int i = 0; i < NSTEPS; ++i) for (int j = 0; j <= MAXE; ++j) cudaEventDestroy(ev[i][j]);
+  }
+};
+static StepProfiler g_prof;
+#define PMARK(name) g_prof.mark(name, st)
+
 struct FwdPlans { StepGemm ga, gq, gd; };
 
 int make_fwd_plans(const T2VDecoderSeq* s, FwdPlans* P) {
@@ -69,6 +107,7 @@ int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) 
   const unsigned long long dbase = s->drop_masks ? 0ull : (unsigned long long)t * B * H;
   // attention LSTM
   CHK(run_gemm(&P->ga, r0, s->parts, st));
+  PMARK("gemm_att");
   CHK(t2v_lstm_pointwise_fwd(s->parts, P->ga.splits, P->ga.split_stride, 4 * H, nullptr, 0, s->ba1, s->ba2,
                              s->CA + r0 * H, H,
                              s->XA + r1 * XA_W + (PD + ED), XA_W,          // h_att -> next step's recurrent input
@@ -77,17 +116,20 @@ int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) 
                              s->GA ? s->GA + r0 * 4 * H : nullptr, s->CPA ? s->CPA + r0 * H : nullptr, nullptr, 0,
                              mk, mk ? mk + (long long)B * H : nullptr, s->seed, SITE_ATT_H, SITE_ATT_C, p_att, dbase,
                              nullptr, 0, B, H, s->use_tc, st));
+  PMARK("cell_att");
   // query projection + fused attention
   CHK(run_gemm(&P->gq, r0, s->qparts, st));
-  CHK(t2v_attn_step_fwd(s->qparts, P->gq.splits, P->gq.split_stride,
-                        t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr, (long long)s->To * Ti,
-                        s->CUM + r0 * Ti, s->CUM + r1 * Ti, s->pmem, s->mem, s->Wconv, s->Wloc, s->v, s->in_lens,
-                        s->mask_value, s->align + (long long)t * Ti, (long long)s->To * Ti,
-                        s->XD + r0 * XD_W + H, XD_W,                       // ctx_t -> decoder_rnn input
-                        s->XA + r1 * XA_W + PD, XA_W,                      // ctx_t -> next attention_rnn input
-                        s->ASAVE ? s->ASAVE + r0 * Ti * AD : nullptr, B, Ti, s->use_tc, st));
+  PMARK("gemm_q");
+  CHK(t2v_attn2_fwd(s->qparts, P->gq.splits, P->gq.split_stride, t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr,
+                    (long long)s->To * Ti, s->CUM + r0 * Ti, s->CUM + r1 * Ti, s->pmem, s->mem, s->Wconv, s->Wloc, s->v,
+                    s->in_lens, s->mask_value, s->ebuf, s->align + (long long)t * Ti, (long long)s->To * Ti,
+                    s->XD + r0 * XD_W + H, XD_W,                           // ctx_t -> decoder_rnn input
+                    s->XA + r1 * XA_W + PD, XA_W,                          // ctx_t -> next attention_rnn input
+                    s->ASAVE ? s->ASAVE + r0 * Ti * AD : nullptr, B, Ti, s->use_tc, st));
+  PMARK("attention(2 kernels)");
   // decoder LSTM
   CHK(run_gemm(&P->gd, r0, s->parts, st));
+  PMARK("gemm_dec");
   CHK(t2v_lstm_pointwise_fwd(s->parts, P->gd.splits, P->gd.split_stride, 4 * H, nullptr, 0, s->bd1, s->bd2,
                              s->CD + r0 * H, H,
                              s->XD + r1 * XD_W + (H + ED), XD_W,           // h_dec -> next step's recurrent input
@@ -95,6 +137,7 @@ int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) 
                              s->GD ? s->GD + r0 * 4 * H : nullptr, s->CPD ? s->CPD + r0 * H : nullptr, nullptr, 0,
                              mk ? mk + 2LL * B * H : nullptr, mk ? mk + 3LL * B * H : nullptr, s->seed, SITE_DEC_H,
                              SITE_DEC_C, p_dec, dbase, nullptr, 0, B, H, s->use_tc, st));
+  PMARK("cell_dec");
   return 0;
 }
 
@@ -113,7 +156,12 @@ T2V_API int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end
   T2V_ARG_CHECK(t_begin >= 0 && t_end <= s->To && t_begin <= t_end, "step range");
   FwdPlans P;
   CHK(make_fwd_plans(s, &P));
-  for (int t = t_begin; t < t_end; ++t) CHK(fwd_step(s, &P, t, stream));
+  g_prof.begin(t_begin, t_end);
+  for (int t = t_begin; t < t_end; ++t) {
+    g_prof.step_begin(t - g_prof.t_first, stream);
+    CHK(fwd_step(s, &P, t, stream));
+  }
+  g_prof.end("decoder forward step", stream);
   return 0;
 }
 
@@ -129,7 +177,9 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
   CHK(setup_gemm(&gxd, tc, d->DGD, 4 * H, rows, 0, d->WdT, 4 * H, B, XD_W, 4 * H, 8));
   CHK(setup_gemm(&gxa, tc, d->DGA, 4 * H, rows, 0, d->WaT, 4 * H, B, XA_W, 4 * H, 8));
   CHK(setup_gemm(&ghq, tc, d->DQ, AD, rows, 0, d->WqT, AD, B, H, AD, 1));
+  g_prof.begin(t_lo, t_hi);
   for (int t = t_hi - 1; t >= t_lo; --t) {
+    g_prof.step_begin(t - g_prof.t_first, st);
     const long long r0 = (long long)t * B, r1 = (long long)(t + 1) * B;
     const bool has_next = (t + 1 < To);
     float* dxd = d->DXD + (long long)(t & 1) * B * XD_W;
@@ -141,25 +191,34 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
                                d->dCd, s->GD + r0 * 4 * H, s->CPD + r0 * H, s->CD + r0 * H, H, d->DGD + r0 * 4 * H, 4 * H,
                                mk ? mk + 2LL * B * H : nullptr, mk ? mk + 3LL * B * H : nullptr, s->seed, SITE_DEC_H,
                                SITE_DEC_C, p_dec, dbase, nullptr, 0, B, H, s->use_tc, st));
+    PMARK("cell_dec_bwd");
     CHK(run_gemm(&gxd, r0, s->parts, st));
+    PMARK("gemm_dXD");
     CHK(t2v_sum_parts(s->parts, gxd.splits, gxd.split_stride, dxd, (long long)B * XD_W, st));
+    PMARK("sum_parts");
     // attention backward
-    CHK(t2v_attn_step_bwd(dxd + H, XD_W, d->DHC + r0 * (H + ED) + H, H + ED,
-                          has_next ? d->DXA + r1 * XA_W + PD : nullptr, XA_W,
-                          has_next ? d->dwprev + (long long)((t + 1) & 1) * B * Ti : nullptr,
-                          d->dwprev + (long long)(t & 1) * B * Ti, d->gcum, s->align + (long long)t * Ti,
-                          (long long)To * Ti, t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr, (long long)To * Ti,
-                          s->CUM + r0 * Ti, s->ASAVE + r0 * Ti * AD, s->mem, s->Wconv, s->Wloc, s->v, s->in_lens, d->dmem,
-                          d->dpmem, d->DQ + r0 * AD, d->dv_part, d->dwloc_part, d->dwconv_part, B, Ti, s->use_tc, st));
+    CHK(t2v_attn2_bwd(dxd + H, XD_W, d->DHC + r0 * (H + ED) + H, H + ED, has_next ? d->DXA + r1 * XA_W + PD : nullptr, XA_W,
+                      d->DCTX + r0 * ED, has_next ? d->dwprev + (long long)((t + 1) & 1) * B * Ti : nullptr,
+                      d->dwprev + (long long)(t & 1) * B * Ti, d->gcum + (long long)((t + 1) & 1) * B * Ti,
+                      d->gcum + (long long)(t & 1) * B * Ti, d->dw_part, s->align + (long long)t * Ti, (long long)To * Ti,
+                      t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr, (long long)To * Ti, s->CUM + r0 * Ti,
+                      s->ASAVE + r0 * Ti * AD, s->mem, s->Wconv, s->Wloc, s->v, s->in_lens, d->dpmem, d->DQ + r0 * AD,
+                      d->dv_part, d->dwloc_part, d->dwconv_part, B, Ti, st));
+    PMARK("attention_bwd(2)");
     CHK(run_gemm(&ghq, r0, d->dHq, st));
+    PMARK("gemm_dHq");
     // attention LSTM cell backward
     CHK(t2v_lstm_pointwise_bwd(dxd, XD_W, has_next ? d->DXA + r1 * XA_W + (PD + ED) : nullptr, XA_W, d->dHq, H, d->dCa,
                                s->GA + r0 * 4 * H, s->CPA + r0 * H, s->CA + r0 * H, H, d->DGA + r0 * 4 * H, 4 * H, mk,
                                mk ? mk + (long long)B * H : nullptr, s->seed, SITE_ATT_H, SITE_ATT_C, p_att, dbase,
                                nullptr, 0, B, H, s->use_tc, st));
+    PMARK("cell_att_bwd");
     CHK(run_gemm(&gxa, r0, s->parts, st));
+    PMARK("gemm_dXA");
     CHK(t2v_sum_parts(s->parts, gxa.splits, gxa.split_stride, d->DXA + r0 * XA_W, (long long)B * XA_W, st));
+    PMARK("sum_parts2");
   }
+  g_prof.end("decoder backward step", st);
   return 0;
 }
 

@@ -291,6 +291,16 @@ __global__ void adam_clip_kernel(float* __restrict__ p, float* __restrict__ g, f
     p[i] -= step * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
   }
 }
+// standard normal samples (Box-Muller over the counter-based uniforms): the VAE eps of modules.py:19
+__global__ void randn_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned int site) {
+  const uint64_t sd = t2v_resolve_seed(seed);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float u1 = fmaxf(t2v_uniform(sd, site, 2 * (uint64_t)i), 5.9604645e-8f);
+    const float u2 = t2v_uniform(sd, site, 2 * (uint64_t)i + 1);
+    out[i] = sqrtf(-2.f * logf(u1)) * cosf(6.2831853071795864f * u2);
+  }
+}
+// dst[off_i : off_i + n_i] = src_i  for a table of segments (gradient packing into one flat buffer)
 __global__ void round_tf32_kernel(float* __restrict__ x, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = t2v_tf32(x[i]);
 }
@@ -393,6 +403,10 @@ T2V_API int t2v_adam_clip_step(float* p, float* g, float* m, float* v, long long
   T2V_ARG_CHECK(step >= 1, "step counts from 1");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adam_clip_kernel<<<1184, 256, 0, st>>>(p, g, m, v, n, sumsq, gscale, max_norm, lr, beta1, beta2, eps, wd, bc1, bc2, norm_out);
+  LAUNCH_END();
+}
+T2V_API int t2v_randn(float* out, long long n, unsigned long long seed, unsigned int site, cudaStream_t st) {
+  randn_kernel<<<t2v_ceil_div(n, 256) < 1184 ? t2v_ceil_div(n, 256) : 1184, 256, 0, st>>>(out, n, seed, site);
   LAUNCH_END();
 }
 T2V_API int t2v_round_tf32(float* x, long long n, cudaStream_t st) {

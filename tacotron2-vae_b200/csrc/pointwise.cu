@@ -304,7 +304,7 @@ __global__ void relu_drop_bwd_kernel(const float* __restrict__ x, const float* _
 }
 __global__ void materialize_mask_kernel(float* __restrict__ out, long long n, T2VDrop drop, unsigned long long idx_base) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (t2v_uniform(drop.seed, drop.site, idx_base + (uint64_t)i) >= drop.p) ? 1.f : 0.f;
+  if (i < n) out[i] = (t2v_uniform(t2v_resolve_seed(drop.seed), drop.site, idx_base + (uint64_t)i) >= drop.p) ? 1.f : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------ LSTM / GRU cells

@@ -61,9 +61,15 @@ struct T2VDrop {
   uint32_t site;
   float p;             // drop probability; p<=0 => identity
 };
+// A seed argument is either a value or, with bit 63 set, a device pointer to the value: CUDA-graph replays bake kernel
+// arguments, so the per-iteration seed has to live in device memory.
+__device__ __forceinline__ uint64_t t2v_resolve_seed(uint64_t seed) {
+  return (seed >> 63) ? *reinterpret_cast<const uint64_t*>(seed & 0x7FFFFFFFFFFFFFFFULL) : seed;
+}
 __device__ __forceinline__ float t2v_keep_scale(const T2VDrop& d, uint64_t logical_idx) {
   if (d.p <= 0.f) return 1.f;
-  float keep = d.mask ? d.mask[logical_idx] : (t2v_uniform(d.seed, d.site, logical_idx) >= d.p ? 1.f : 0.f);
+  float keep = d.mask ? d.mask[logical_idx]
+                      : (t2v_uniform(t2v_resolve_seed(d.seed), d.site, logical_idx) >= d.p ? 1.f : 0.f);
   return keep * (1.f / (1.f - d.p));
 }
 

@@ -243,7 +243,8 @@ class Tacotron2(nn.Module):
         self._seed = int(getattr(hparams, "seed", 1234))
         self._step = 0
         self._rand = None                                 # explicit dropout masks / eps for parity tests
-        self.last_context = None
+        # CUDA-graph replay of the train step per input shape (T2V_GRAPHS=0 to run every launch eagerly)
+        self._graph_cache = {} if __import__("os").environ.get("T2V_GRAPHS", "1") != "0" else None
 
     # ---- engine plumbing ----
     _DEAD = ("speaker_embedding.", "emotion_embedding.", "vae_gst.ref_encoder.convs.0.weight", "vae_gst.ref_encoder.convs.0.bias")
@@ -291,6 +292,7 @@ class Tacotron2(nn.Module):
         cfg.seed = self._next_seed()
         cfg.mask_padding = bool(self.mask_padding)
         cfg.mask_value = float(self.decoder.attention_layer.score_mask_value)
+        cfg.graph_cache = self._graph_cache
         for k, v in named:
             if v.dtype != torch.float32 or not v.is_contiguous() or not v.is_cuda:
                 raise RuntimeError("parameter %s must be a contiguous fp32 CUDA tensor" % k)

@@ -14,7 +14,8 @@ HEADER = os.path.join(os.path.dirname(PKG), "include", "t2v_b200.h")
 
 _P = ctypes.c_void_p
 _CT = {"int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "long long": ctypes.c_longlong,
-       "unsigned long long": ctypes.c_ulonglong, "unsigned int": ctypes.c_uint, "cudaStream_t": _P}
+       "unsigned long long": ctypes.c_ulonglong, "unsigned int": ctypes.c_uint, "cudaStream_t": _P,
+       "unsigned long long n": ctypes.c_ulonglong}
 
 
 class T2VDecoderSeq(ctypes.Structure):
@@ -23,13 +24,13 @@ class T2VDecoderSeq(ctypes.Structure):
                  ("seed", ctypes.c_ulonglong), ("drop_masks", _P), ("mask_value", ctypes.c_float), ("in_lens", _P)] +
                 [(n, _P) for n in ("Wa", "ba1", "ba2", "Wd", "bd1", "bd2", "Wq", "Wconv", "Wloc", "v", "mem", "pmem",
                                    "XA", "XD", "CA", "CD", "CUM", "align", "GA", "GD", "CPA", "CPD", "ASAVE", "parts",
-                                   "qparts")])
+                                   "qparts", "ebuf")])
 
 
 class T2VDecoderBwd(ctypes.Structure):
     _fields_ = [("f", T2VDecoderSeq)] + [(n, _P) for n in (
-        "WaT", "WdT", "WqT", "DHC", "DGA", "DGD", "DXA", "DXD", "dCa", "dCd", "dwprev", "gcum", "dmem", "dpmem", "DQ",
-        "dHq", "dv_part", "dwloc_part", "dwconv_part")]
+        "WaT", "WdT", "WqT", "DHC", "DGA", "DGD", "DXA", "DXD", "dCa", "dCd", "dwprev", "gcum", "dpmem", "DCTX", "dw_part",
+        "DQ", "dHq", "dv_part", "dwloc_part", "dwconv_part")]
 
 
 class T2VDecoderInfer(ctypes.Structure):
@@ -121,3 +122,7 @@ def launch_count():
 
 def reset_launch_count():
     lib().t2v_reset_launch_count()
+
+
+def add_launch_count(n):
+    lib().t2v_add_launch_count(int(n))

@@ -29,12 +29,13 @@ def _trace(label):
     if not _TRACE:
         return
     import time
+    host = time.perf_counter()
     torch.cuda.synchronize()
     now = time.perf_counter()
     if _t_last[0] is not None and label:
-        print("[t2v] %-28s %9.3f ms" % (label, (now - _t_last[0]) * 1e3), flush=True)
+        print("[t2v] %-28s %9.3f ms  (host issue %8.3f ms)" % (label, (now - _t_last[0]) * 1e3, (host - _t_last[0]) * 1e3), flush=True)
     _t_last[0] = now
-SITE_ENC, SITE_PRENET, SITE_POST = 0, 3, 20          # dropout RNG site ids (decoder uses 10..13 in decoder.cu)
+SITE_ENC, SITE_PRENET, SITE_POST, SITE_EPS = 0, 3, 20, 30          # dropout RNG site ids (decoder uses 10..13 in decoder.cu)
 _ctypes = _lib.ctypes
 
 
@@ -363,18 +364,18 @@ def refenc_forward(ops, P, mel, training, dev):
         Ct = 4 if i == 0 else Ci
         Co = filters[i]
         rows = N * Ho * Wo
+        # late layers normalise over very few samples (BN2d over N*H'*W' positions): keep them exact
+        exact = rows < 100000 or not ops.tc
+        rl = 0 if exact else 1
         col = _empty(rows, 9 * Ct, device=dev)
-        L("t2v_im2col_3x3s2", x, col, N, Hc, Wc, Ci, 1 if i == 0 else 0, ops.R)
+        L("t2v_im2col_3x3s2", x, col, N, Hc, Wc, Ci, 1 if i == 0 else 0, rl)
         wname = _REF + ("convs.0.conv" if i == 0 else "convs.%d" % i)
         Wk = _empty(Co, 9 * Ct, device=dev)
-        L("t2v_conv1d_pack", P[wname + ".weight"], Wk, Co, Ct, 9, 0, ops.R)
+        L("t2v_conv1d_pack", P[wname + ".weight"], Wk, Co, Ct, 9, 0, rl)
         Y = _empty(rows, Co, device=dev)
-        # late layers normalise over very few samples (BN2d over N*H'*W' positions): keep them exact
-        exact = rows < 100000
         ops.linear(col, 9 * Ct, Wk, 9 * Ct, Y, Co, rows, Co, 9 * Ct, bias=P[wname + ".bias"], force_exact=exact)
         Xn = _empty(rows, Co, device=dev)
-        mi = _bn_forward(ops, Y, Xn, rows, Co, 1, 0, 1, rows, P, _REF + "bns.%d" % i, training, 1, None, 0, 0, 0.0, 1, dev,
-                         rnd=ops.R if i == 5 else 0)
+        mi = _bn_forward(ops, Y, Xn, rows, Co, 1, 0, 1, rows, P, _REF + "bns.%d" % i, training, 1, None, 0, 0, 0.0, 1, dev)
         layers.append(dict(col=col, Wk=Wk, Y=_Saved(Y, mi), rows=rows, Ct=Ct, Co=Co, H=Hc, W=Wc, Ci=Ci, wname=wname, exact=exact))
         x, Hc, Wc, Ci = Xn, Ho, Wo, Co
     Tq, Wq, Cq = Hc, Wc, Ci                       # GRU sequence length, remaining mel bins, channels
@@ -382,7 +383,7 @@ def refenc_forward(ops, P, mel, training, dev):
     Hh = P[_REF + "gru.weight_hh_l0"].shape[1]
     # reference feature order is c*W'+w (modules.py:73-76); ours is w*C+c -> permute the input weight columns
     Wih = _empty(3 * Hh, Fin, device=dev)
-    L("t2v_conv1d_pack", P[_REF + "gru.weight_ih_l0"], Wih, 3 * Hh, Cq, Wq, 0, ops.R)
+    L("t2v_conv1d_pack", P[_REF + "gru.weight_ih_l0"], Wih, 3 * Hh, Cq, Wq, 0, 0)
     GI = _empty(N * Tq, 3 * Hh, device=dev)
     ops.linear(x, Fin, Wih, Fin, GI, 3 * Hh, N * Tq, 3 * Hh, Fin, force_exact=True)
     HS = _zeros(Tq + 1, N, Hh, device=dev)
@@ -407,7 +408,7 @@ def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
     gWhh = _zeros(3 * Hh, Hh, device=dev)
     bh_acc = _zeros(3 * Hh, device=dev, dtype=torch.float64)
     for t in range(Tq - 1, -1, -1):
-        L("t2v_gru_pointwise_bwd", dh, SV[t], HS[t], _p(DGI, t * 3 * Hh), Tq * 3 * Hh, dgh, dhp, N, Hh, ops.R)
+        L("t2v_gru_pointwise_bwd", dh, SV[t], HS[t], _p(DGI, t * 3 * Hh), Tq * 3 * Hh, dgh, dhp, N, Hh, 0)
         ops.gemm(dgh, 3 * Hh, 1, Whh, 1, Hh, dhp, Hh, N, Hh, 3 * Hh, 1.0, 1.0)          # dh_prev += dgh @ W_hh
         ops.gemm(dgh, 1, 3 * Hh, HS[t], 1, Hh, gWhh, Hh, 3 * Hh, Hh, N, 1.0, 1.0)        # dW_hh += dgh^T h_prev
         L("t2v_col_stats", dgh, N, 3 * Hh, 1, 0, 1, 2, bh_acc, None)
@@ -429,7 +430,7 @@ def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
         rows, Co, Ct = ly["rows"], ly["Co"], ly["Ct"]
         dY = _empty(rows, Co, device=dev)
         _bn_backward(dX, ly["Y"], dY, rows, Co, 1, 0, 1, rows, P, _REF + "bns.%d" % i, training, 1, None, 0, 0, 0.0, 1, dev, grads,
-                     rnd=ops.R)
+                     rnd=0 if ly["exact"] else 1)
         grads[ly["wname"] + ".bias"] = _colsum(dY, rows, Co, 1, 0, 1, dev)
         dWk = _zeros(Co, 9 * Ct, device=dev)
         ops.linear_dw(dY, Co, ly["col"], 9 * Ct, dWk, 9 * Ct, rows, Co, 9 * Ct, device=dev, force_exact=ly["exact"])
@@ -529,7 +530,7 @@ def _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_v
     S.Wloc = P[_A + "location_layer.location_dense.linear_layer.weight"].data_ptr()
     S.v = P[_A + "v.linear_layer.weight"].data_ptr()
     S.mem, S.pmem = mem.data_ptr(), pmem.data_ptr()
-    for k in ("XA", "XD", "CA", "CD", "CUM", "align", "GA", "GD", "CPA", "CPD", "ASAVE", "parts", "qparts"):
+    for k in ("XA", "XD", "CA", "CD", "CUM", "align", "GA", "GD", "CPA", "CPD", "ASAVE", "parts", "qparts", "ebuf"):
         setattr(S, k, _lib.ptr(buf.get(k)))
 
 
@@ -537,7 +538,8 @@ def alloc_decoder_buffers(B, Ti, To, dev, save=True):
     buf = dict(XA=_zeros((To + 1) * B, 1792, device=dev), XD=_zeros((To + 1) * B, 2560, device=dev),
                CA=_zeros((To + 1) * B, 1024, device=dev), CD=_zeros((To + 1) * B, 1024, device=dev),
                CUM=_zeros((To + 1) * B, Ti, device=dev), align=_zeros(B, To, Ti, device=dev),
-               parts=_empty(8 * B * 4096, device=dev), qparts=_empty(8 * B * 128, device=dev))
+               parts=_empty(8 * B * 4096, device=dev), qparts=_empty(8 * B * 128, device=dev),
+               ebuf=_empty(B, Ti, device=dev))
     if save:
         buf.update(GA=_empty(To * B, 4096, device=dev), GD=_empty(To * B, 4096, device=dev),
                    CPA=_empty(To * B, 1024, device=dev), CPD=_empty(To * B, 1024, device=dev),
@@ -608,14 +610,15 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
     L("t2v_transpose", W["Wd"], 2560, WdT, 4096, 4096, 2560, 0)
     L("t2v_transpose", Wq, 1024, WqT, 128, 128, 1024, 0)
     _trace("  bwd proj")
+    nck = int(_lib.lib().t2v_attn2_chunks(Ti))
     D = _lib.T2VDecoderBwd()
     _ctypes.memmove(_ctypes.addressof(D.f), _ctypes.addressof(ctx["S"]), _ctypes.sizeof(_lib.T2VDecoderSeq))
     t = dict(WaT=WaT, WdT=WdT, WqT=WqT, DHC=DHC, DGA=_empty(n, 4096, device=dev), DGD=_empty(n, 4096, device=dev),
              DXA=_empty(n, 1792, device=dev), DXD=_zeros(2 * B, 2560, device=dev), dCa=_zeros(B, 1024, device=dev),
-             dCd=_zeros(B, 1024, device=dev), dwprev=_zeros(2 * B, Ti, device=dev), gcum=_zeros(B, Ti, device=dev),
-             dmem=_zeros(B * Ti, 512, device=dev), dpmem=_zeros(B * Ti, 128, device=dev), DQ=_empty(n, 128, device=dev),
-             dHq=_empty(B, 1024, device=dev), dv_part=_zeros(B, 128, device=dev), dwloc_part=_zeros(B, 128 * 32, device=dev),
-             dwconv_part=_zeros(B, 32 * 2 * 31, device=dev))
+             dCd=_zeros(B, 1024, device=dev), dwprev=_zeros(2 * B, Ti, device=dev), gcum=_zeros(2 * B, Ti, device=dev),
+             dpmem=_zeros(B * Ti, 128, device=dev), DCTX=_empty(n, 512, device=dev), dw_part=_empty(4 * B, Ti, device=dev),
+             DQ=_zeros(n, 128, device=dev), dHq=_empty(B, 1024, device=dev), dv_part=_zeros(B * nck, 128, device=dev),
+             dwloc_part=_zeros(B * nck, 128 * 32, device=dev), dwconv_part=_zeros(B * nck, 32 * 2 * 31, device=dev))
     for k, v in t.items():
         setattr(D, k, v.data_ptr())
     L("t2v_decoder_bwd_steps", D, To, 0)
@@ -640,7 +643,7 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
                              (_A + "location_layer.location_dense.linear_layer.weight", t["dwloc_part"], 128 * 32),
                              (_A + "location_layer.location_conv.conv.weight", t["dwconv_part"], 32 * 2 * 31)):
         g = _empty(cols, device=dev)
-        L("t2v_sum_rows_per_batch", part, g, 1, B, cols, 0.0)
+        L("t2v_sum_rows_per_batch", part, g, 1, B * nck, cols, 0.0)
         grads[name] = g.view_as(P[name])
     _trace("  bwd decoder dW")
     # prenet backward (model.py:91-102)
@@ -663,8 +666,11 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
         L("t2v_round_tf32", t["dpmem"], t["dpmem"].numel())
     ops.linear_dw(t["dpmem"], 128, ctx["memory"], 512, gWm, 512, B * Ti, 128, 512, device=dev)
     grads[_A + "memory_layer.linear_layer.weight"] = gWm
-    ops.linear_dx(t["dpmem"], 128, Wm, 512, t["dmem"], 512, B * Ti, 128, 512, accumulate=True)
-    return t["dmem"].view(B, Ti, 512)
+    # d(memory)[b,ti,:] = sum_t w_t[b,ti] * dctx_t[b,:]  (one batched GEMM over the saved alignments)  + dpmem @ W_m
+    dmem = _empty(B * Ti, 512, device=dev)
+    L("t2v_gemm_f32", buf["align"], 1, Ti, t["DCTX"], 1, B * 512, dmem, 512, Ti, 512, To, 1.0, 0.0, None, B, To * Ti, 512, Ti * 512)
+    ops.linear_dx(t["dpmem"], 128, Wm, 512, dmem, 512, B * Ti, 128, 512, accumulate=True)
+    return dmem.view(B, Ti, 512)
 
 
 # ======================================================================================================= postnet + outputs
@@ -692,10 +698,7 @@ def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=No
     eps = g("eps")
     if training and eps is None:
         eps = torch.empty(B, P["vae_gst.fc1.weight"].shape[0], device=dev, dtype=F32)
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(seed + 977)
-        eps.normal_(generator=gen)
-    _trace("fwd encoder")
+        L("t2v_randn", eps, eps.numel(), seed, SITE_EPS)
     style, mulv, z, c.vae = vae_forward(ops, P, mel_tgt, training, eps, dev)
     _trace("fwd vae/ref-encoder")
     memory = _empty(B, Ti, 512, device=dev)

@@ -3,8 +3,73 @@ backward pass of t2v.engine, so the reference's train.py (loss.backward(), param
 Adam.step) runs unchanged on top of the CUDA engine."""
 import torch
 
-from . import engine
+from . import _lib, engine
 from ._lib import call as L
+
+
+class GraphedStep(object):
+    """One (shape, mode) instance of the train step captured as two CUDA graphs (forward, backward).
+
+    The engine's forward/backward are fixed launch sequences for a given shape (lengths, seeds and masks live in device
+    memory), so capturing them removes the per-launch host cost (~10 us x ~16k launches per step on the B200 hosts) and
+    pins every intermediate at a fixed address.  Inputs are copied into static tensors before a replay; the dropout /
+    eps seed is a device scalar the kernels dereference (seed argument with bit 63 set, see include/t2v_b200.h)."""
+
+    def __init__(self, cfg, P, text, in_len, mel, out_len):
+        dev = text.device
+        self.names = list(cfg.names)
+        self.s_in = [text.clone(), in_len.clone(), mel.clone(), out_len.clone()]
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        seed_arg = (1 << 63) | self.seed_dev.data_ptr()
+        kw = dict(training=cfg.training, rand=None, seed=seed_arg, mask_padding=cfg.mask_padding, mask_value=cfg.mask_value)
+        snap = {k: v.clone() for k, v in cfg.buffers.items()}        # the warm-up below must not advance BN statistics
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                                # eager warm-up: lazy inits (smem attributes, TMA entry point)
+            outs, c = engine.forward_train(cfg.ops, P, *self.s_in, **kw)
+            engine.backward_train(cfg.ops, P, c, *[torch.zeros_like(outs[i]) for i in (0, 1, 2, 4, 5)])
+            del outs, c
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.g_fwd = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.g_fwd, capture_error_mode="thread_local"):
+            self.outs, self.c = engine.forward_train(cfg.ops, P, *self.s_in, **kw)
+        self.n_fwd = _lib.launch_count() - n0
+        self.s_dout = [torch.zeros_like(self.outs[i]) for i in (0, 1, 2, 4, 5)]
+        self.g_bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool(), capture_error_mode="thread_local"):
+            grads = engine.backward_train(cfg.ops, P, self.c, *self.s_dout)
+            self.live = [n for n in self.names if n in grads]
+            self.sizes = [grads[n].numel() for n in self.live]
+            self.shapes = [grads[n].shape for n in self.live]
+            self.flat = torch.cat([grads[n].reshape(-1) for n in self.live])
+            del grads
+        self.n_bwd = _lib.launch_count() - n0 - self.n_fwd
+        for k, v in cfg.buffers.items():
+            v.copy_(snap[k])
+        torch.cuda.synchronize()
+
+    def forward(self, text, in_len, mel, out_len, seed):
+        for s, t in zip(self.s_in, (text, in_len, mel, out_len)):
+            s.copy_(t, non_blocking=True)
+        self.seed_dev.fill_(int(seed) & 0x7FFFFFFFFFFFFFFF)
+        self.g_fwd.replay()
+        _lib.add_launch_count(self.n_fwd)
+        return [o.clone() for o in self.outs]
+
+    def backward(self, douts):
+        for s, t in zip(self.s_dout, douts):
+            s.copy_(t, non_blocking=True)
+        self.g_bwd.replay()
+        _lib.add_launch_count(self.n_bwd)
+        flat = self.flat.clone()
+        out, off = {}, 0
+        for n, sz, shp in zip(self.live, self.sizes, self.shapes):
+            out[n] = flat[off:off + sz].view(shp)
+            off += sz
+        return out
 
 
 class Tacotron2Function(torch.autograd.Function):
@@ -15,6 +80,21 @@ class Tacotron2Function(torch.autograd.Function):
     def forward(ctx, cfg, text, in_len, mel_tgt, out_len, *params):
         P = dict(zip(cfg.names, params))
         P.update(cfg.buffers)
+        ctx.gs = None
+        if cfg.graph_cache is not None and cfg.rand is None:
+            key = (tuple(text.shape), tuple(mel_tgt.shape), cfg.training, cfg.ops.precision, cfg.mask_padding, cfg.mask_value,
+                   params[0].data_ptr(), params[-1].data_ptr())
+            gs = cfg.graph_cache.get(key)
+            if gs is None:
+                if len(cfg.graph_cache) >= 2:                        # keep at most two shapes resident (GBs of workspace each)
+                    cfg.graph_cache.pop(next(iter(cfg.graph_cache)))
+                gs = cfg.graph_cache[key] = GraphedStep(cfg, P, text, in_len, mel_tgt, out_len)
+            outs = gs.forward(text, in_len, mel_tgt, out_len, cfg.seed)
+            ctx.gs = gs
+            ctx.cfg, ctx.c, ctx.P = cfg, None, None
+            ctx.mark_non_differentiable(outs[3], outs[6])
+            ctx.set_materialize_grads(True)
+            return tuple(outs)
         outs, c = engine.forward_train(cfg.ops, P, text, in_len, mel_tgt, out_len, training=cfg.training, rand=cfg.rand,
                                        seed=cfg.seed, mask_padding=cfg.mask_padding, mask_value=cfg.mask_value)
         ctx.cfg, ctx.c, ctx.P = cfg, c, P
@@ -25,8 +105,11 @@ class Tacotron2Function(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dmel, dpost, dgate, dalign, dmu, dlogvar, dz):
         cfg = ctx.cfg
-        grads = engine.backward_train(cfg.ops, ctx.P, ctx.c, dmel.contiguous(), dpost.contiguous(), dgate.contiguous(),
-                                      dmu.contiguous(), dlogvar.contiguous())
+        if ctx.gs is not None:
+            grads = ctx.gs.backward((dmel, dpost, dgate, dmu, dlogvar))
+        else:
+            grads = engine.backward_train(cfg.ops, ctx.P, ctx.c, dmel.contiguous(), dpost.contiguous(), dgate.contiguous(),
+                                          dmu.contiguous(), dlogvar.contiguous())
         ctx.c = None
         out = [None] * 5
         for n in cfg.names:

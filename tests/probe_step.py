@@ -12,7 +12,7 @@ m = M.Tacotron2(hp).cuda().train(); m.precision = prec
 crit = Tacotron2Loss_VAE(hp)
 batch = port.synthetic_batch(B,Ti,To,seed=0)
 x,y = m.parse_batch(batch)
-for it in range(2):
+for it in range(int(os.environ.get('PROBE_ITERS','2'))):
     t0=time.perf_counter()
     out = m(x); loss,_,_,_ = crit(out,y,0); loss.backward(); torch.cuda.synchronize()
     print("iter",it,"total ms",(time.perf_counter()-t0)*1e3, "loss", loss.item(), flush=True)

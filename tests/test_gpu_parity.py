@@ -81,7 +81,8 @@ def test_train_step_matches_golden(golden_dir, precision, tag, B, Ti, To):
             continue
         assert g is not None, k
         d = abs(float(g.norm()) - gn)
-        assert d <= gtol * gn + 1e-6 * total, (k, float(g.norm()), gn)
+        # (a conv bias in front of a training-mode BN has an exactly-zero true gradient: both sides are rounding noise)
+        assert d <= gtol * gn + (1e-6 if precision == "fp32" else 1e-4) * total, (k, float(g.norm()), gn)
         worst = max(worst, d / (gn + 1e-6 * total))
     for k in G.files:
         if k.startswith("grad::"):
@@ -119,8 +120,9 @@ def test_rng_dropout_replays_in_oracle():
             dec[t, j] = mask((B, 1024), 10 + j, 0.1, base=t * B * 1024)
     r.dec = dec
     r.post = [mask((B, 512, To), 20 + i, 0.5) for i in range(4)] + [mask((B, 80, To), 24, 0.5)]
-    gen = torch.Generator(device=dev); gen.manual_seed(seed + 977)
-    r.eps = torch.empty(B, 32, device=dev).normal_(generator=gen).cpu()
+    eps = torch.empty(B, 32, device=dev)
+    L("t2v_randn", eps, eps.numel(), seed, 30)
+    r.eps = eps.cpu()
     P = port.init_params(1234)
     with torch.no_grad():
         ref = port.tacotron2_forward(P, batch[0], batch[1], batch[2], batch[4], True, r)

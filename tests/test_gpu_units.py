@@ -201,3 +201,59 @@ def test_loss_and_adam_match_torch(L):
             assert abs(float(norm) - float(tn)) < 1e-4 * float(tn)
         pt.grad = gr.clone(); gd.copy_(g(gr))
     assert torch.allclose(pd.cpu(), pt.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_attention_v2_matches_v1(L):
+    """The SM-parallel attention kernels (attention2.cu) against the one-CTA-per-utterance reference kernels
+    (attention.cu, themselves checked against the oracle above): forward and the full backward incl. the scattered
+    adjoint conv and the per-slot weight-gradient partials."""
+    from t2v import _lib
+    torch.manual_seed(8)
+    dev = "cuda"
+    B, Ti = 5, 77
+    nck = int(_lib.lib().t2v_attn2_chunks(Ti))
+    r = lambda *s: torch.randn(*s, device=dev)
+    q = r(B, 128); wprev = torch.softmax(r(B, Ti), 1); cum = torch.rand(B, Ti, device=dev)
+    pmem = r(B, Ti, 128); mem = r(B, Ti, 512)
+    wconv = r(32, 2, 31) * 0.2; wloc = r(128, 32) * 0.2; v = r(128) * 0.3
+    lens = torch.tensor([77, 70, 40, 33, 9], device=dev)
+    out = {}
+    for ver in (1, 2):
+        w = torch.zeros(B, Ti, device=dev); cumo = torch.zeros(B, Ti, device=dev)
+        c1 = torch.zeros(B, 512, device=dev); c2 = torch.zeros(B, 512, device=dev); a = torch.zeros(B, Ti, 128, device=dev)
+        if ver == 1:
+            L("t2v_attn_step_fwd", q, 1, 0, wprev, Ti, cum, cumo, pmem, mem, wconv, wloc, v, lens, -float("inf"), w, Ti, c1, 512,
+              c2, 512, a, B, Ti, 0)
+        else:
+            e = torch.empty(B, Ti, device=dev)
+            L("t2v_attn2_fwd", q, 1, 0, wprev, Ti, cum, cumo, pmem, mem, wconv, wloc, v, lens, -float("inf"), e, w, Ti, c1, 512,
+              c2, 512, a, B, Ti, 0)
+        out[ver] = (w, cumo, c1, c2, a)
+    for x, y in zip(out[1], out[2]):
+        assert torch.allclose(x, y, atol=2e-6, rtol=1e-5)
+    w, _, _, _, a_save = out[1]
+    # backward
+    d1, d2, d3 = r(B, 512), r(B, 512), r(B, 512)
+    dw_in = r(B, Ti) * 0.1; gc = r(B, Ti) * 0.1
+    # v1
+    dmem1 = torch.zeros(B, Ti, 512, device=dev); dpm1 = torch.zeros(B, Ti, 128, device=dev); dq1 = torch.zeros(B, 128, device=dev)
+    dv1 = torch.zeros(B, 128, device=dev); dwl1 = torch.zeros(B, 128 * 32, device=dev); dwc1 = torch.zeros(B, 32 * 62, device=dev)
+    dwo1 = torch.zeros(B, Ti, device=dev); gc1 = gc.clone()
+    L("t2v_attn_step_bwd", d1, 512, d2, 512, d3, 512, dw_in, dwo1, gc1, w, Ti, wprev, Ti, cum, a_save, mem, wconv, wloc, v, lens,
+      dmem1, dpm1, dq1, dv1, dwl1, dwc1, B, Ti, 0)
+    # v2
+    dctx = torch.empty(B, 512, device=dev); dwp = torch.empty(4, B, Ti, device=dev)
+    dpm2 = torch.zeros(B, Ti, 128, device=dev); dq2 = torch.zeros(B, 128, device=dev)
+    dv2 = torch.zeros(B * nck, 128, device=dev); dwl2 = torch.zeros(B * nck, 128 * 32, device=dev)
+    dwc2 = torch.zeros(B * nck, 32 * 62, device=dev)
+    dwo2 = torch.full((B, Ti), 7.0, device=dev); gcn = torch.full((B, Ti), -3.0, device=dev)
+    L("t2v_attn2_bwd", d1, 512, d2, 512, d3, 512, dctx, dw_in, dwo2, gc, gcn, dwp, w, Ti, wprev, Ti, cum, a_save, mem, wconv,
+      wloc, v, lens, dpm2, dq2, dv2, dwl2, dwc2, B, Ti)
+    tol = dict(atol=2e-5, rtol=1e-4)
+    assert torch.allclose(dctx, d1 + d2 + d3, **tol)
+    assert torch.allclose(dmem1, w.unsqueeze(2) * dctx.unsqueeze(1), **tol)          # what the batched GEMM will produce
+    assert torch.allclose(dpm1, dpm2, **tol) and torch.allclose(dq1, dq2, **tol)
+    assert torch.allclose(dwo1, dwo2, **tol) and torch.allclose(gc1, gcn, **tol)
+    assert torch.allclose(dv1.sum(0), dv2.sum(0), **tol)
+    assert torch.allclose(dwl1.sum(0), dwl2.sum(0), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(dwc1.sum(0), dwc2.sum(0), atol=1e-4, rtol=1e-4)
