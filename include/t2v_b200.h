@@ -121,6 +121,15 @@ int t2v_lstm_pointwise_bwd(const float* dh1, long long dh1_rs, const float* dh2,
                            const float* mask_c, unsigned long long seed, unsigned int site_h, unsigned int site_c,
                            float p, unsigned long long drop_base, const long long* lens, int t, int B, int H,
                            int rnd, cudaStream_t stream);
+/* encoder BiLSTM (model.py:171-190): one fused launch per time step for both directions (recurrent matvec + cell) */
+int t2v_bilstm_step_fwd(const float* gx0, const float* gx1, long long gx_bs, const float* whh0, const float* whh1,
+                        const float* bhh0, const float* bhh1, const float* hprev0, const float* hprev1, float* hnext0,
+                        float* hnext1, float* c0, float* c1, float* seq0, float* seq1, long long seq_bs, float* gs0, float* gs1,
+                        float* cs0, float* cs1, const long long* lens, int t0, int t1, int B, int H, cudaStream_t stream);
+int t2v_bilstm_step_bwd(const float* dgn0, const float* dgn1, long long dg_bs, const float* whhT0, const float* whhT1,
+                        const float* dout0, const float* dout1, long long dout_bs, float* dc0, float* dc1, const float* gs0,
+                        const float* gs1, const float* cs0, const float* cs1, const float* cp0, const float* cp1, float* dgo0,
+                        float* dgo1, const long long* lens, int t0, int t1, int B, int H, cudaStream_t stream);
 int t2v_gru_pointwise_fwd(const float* gi, long long gi_rs, const float* gh, const float* b_ih, const float* b_hh, const float* h_prev,
                           float* h_out, float* save, int B, int H, cudaStream_t stream);
 int t2v_gru_pointwise_bwd(const float* dh, const float* save, const float* h_prev, float* dgi, long long dgi_rs, float* dgh,

@@ -81,29 +81,36 @@ __global__ void __launch_bounds__(128) attn2_energy_kernel(E2Args p) {
   __shared__ float red[4][TC];
   const int b = blockIdx.y, t0 = blockIdx.x * TC, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Ti = p.Ti;
-  conv_stage(p.w_prev, p.wprev_rs, p.cum_in, p.w_conv, b, t0, Ti, win, wcT, f);
-  // thread d: W_loc row in registers
+  // thread d: W_loc row, query and the chunk's processed-memory values in registers -- every global load of the kernel
+  // is in flight before the first use
   const int d = tid;
+  const int nt = min(TC, Ti - t0);
   float wl[NF];
 #pragma unroll
   for (int c = 0; c < NF; c += 4) {
     const float4 t = *reinterpret_cast<const float4*>(p.w_loc + d * NF + c);
     wl[c] = t.x; wl[c + 1] = t.y; wl[c + 2] = t.z; wl[c + 3] = t.w;
   }
+  float pmv[TC];
+#pragma unroll
+  for (int tt = 0; tt < TC; ++tt) pmv[tt] = (tt < nt) ? p.pmem[((long long)b * Ti + t0 + tt) * AD + d] : 0.f;
   float q = 0.f;
   for (int s = 0; s < p.n_qparts; ++s) q += p.qparts[s * p.qpart_stride + (long long)b * AD + d];
   const float vd = p.v[d];
-  const int nt = min(TC, Ti - t0);
-  for (int tt = 0; tt < nt; ++tt) {
-    const long long row = (long long)b * Ti + t0 + tt;
-    float s = q + p.pmem[row * AD + d];
-    const float* fr = f + tt * (NF + 1);
+  conv_stage(p.w_prev, p.wprev_rs, p.cum_in, p.w_conv, b, t0, Ti, win, wcT, f);
 #pragma unroll
-    for (int c = 0; c < NF; ++c) s = fmaf(fr[c], wl[c], s);
-    const float a = tanhf(s);
-    if (p.a_save) p.a_save[row * AD + d] = a;
-    const float part = warp_sum(vd * a);
-    if (lane == 0) red[warp][tt] = part;
+  for (int tt = 0; tt < TC; ++tt) {
+    if (tt < nt) {
+      const long long row = (long long)b * Ti + t0 + tt;
+      float s = q + pmv[tt];
+      const float* fr = f + tt * (NF + 1);
+#pragma unroll
+      for (int c = 0; c < NF; ++c) s = fmaf(fr[c], wl[c], s);
+      const float a = tanhf(s);
+      if (p.a_save) p.a_save[row * AD + d] = a;
+      const float part = warp_sum(vd * a);
+      if (lane == 0) red[warp][tt] = part;
+    }
   }
   __syncthreads();
   if (tid < nt) {
@@ -155,13 +162,20 @@ __global__ void __launch_bounds__(128) attn2_context_kernel(C2Args p) {
   // warp handles ti = warp, warp+4, ...; lane handles 4 channels
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* mbase = p.mem + (long long)b * Ti * ED + ch * 128 + lane * 4;
-#pragma unroll 8
-  for (int ti = warp; ti < Ti; ti += 4) {
-    const float wi = w[ti];
-    if (wi != 0.f) {
-      const float4 mv = *reinterpret_cast<const float4*>(mbase + (long long)ti * ED);
-      acc.x = fmaf(wi, mv.x, acc.x); acc.y = fmaf(wi, mv.y, acc.y);
-      acc.z = fmaf(wi, mv.z, acc.z); acc.w = fmaf(wi, mv.w, acc.w);
+  constexpr int NB = 16;                       // memory rows in flight per lane
+  for (int base = warp; base < Ti; base += 4 * NB) {
+    float4 mv[NB];
+    float wi[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int ti = base + 4 * j;
+      wi[j] = (ti < Ti) ? w[ti] : 0.f;
+      mv[j] = (wi[j] != 0.f) ? *reinterpret_cast<const float4*>(mbase + (long long)ti * ED) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      acc.x = fmaf(wi[j], mv[j].x, acc.x); acc.y = fmaf(wi[j], mv[j].y, acc.y);
+      acc.z = fmaf(wi[j], mv[j].z, acc.z); acc.w = fmaf(wi[j], mv[j].w, acc.w);
     }
   }
   *reinterpret_cast<float4*>(part + warp * 128 + lane * 4) = acc;
@@ -204,15 +218,21 @@ __global__ void __launch_bounds__(128) attn2_bwd_ctx_kernel(B1Args p) {
   const long long len = p.lens ? p.lens[b] : Ti;
   const float* mbase = p.mem + (long long)b * Ti * ED + ch * 128 + lane * 4;
   float* out = p.dw_part + ((long long)ch * p.B + b) * Ti;
-#pragma unroll 4
-  for (int ti = warp; ti < Ti; ti += 4) {
-    float acc = 0.f;
-    if (ti < len) {
-      const float4 mv = *reinterpret_cast<const float4*>(mbase + (long long)ti * ED);
-      acc = dv.x * mv.x + dv.y * mv.y + dv.z * mv.z + dv.w * mv.w;
+  constexpr int NB = 16;
+  for (int base = warp; base < Ti; base += 4 * NB) {
+    float4 mv[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int ti = base + 4 * j;
+      mv[j] = (ti < len) ? *reinterpret_cast<const float4*>(mbase + (long long)ti * ED) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) out[ti] = acc;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int ti = base + 4 * j;
+      float acc = dv.x * mv[j].x + dv.y * mv[j].y + dv.z * mv[j].z + dv.w * mv[j].w;
+      acc = warp_sum(acc);
+      if (lane == 0 && ti < Ti) out[ti] = acc;
+    }
   }
 }
 
@@ -250,6 +270,9 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
   const int b = blockIdx.y, chunk = blockIdx.x, t0 = chunk * TC, tid = threadIdx.x;
   const int nchunk = gridDim.x;
   const int nt = min(TC, Ti - t0);
+  float av[TC];                              // saved tanh activations of this chunk (thread = attention dim)
+#pragma unroll
+  for (int tt = 0; tt < TC; ++tt) av[tt] = (tt < nt) ? p.a_save[((long long)b * Ti + t0 + tt) * AD + tid] : 0.f;
   // (1) dw over the whole row, s = <w, dw>, de for this chunk
   float part = 0.f;
   for (int i = tid; i < Ti; i += 128) {
@@ -270,18 +293,23 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
   // (3) thread d: tanh/v backward over the chunk; dWloc row d in registers
   const int d = tid;
   const float vd = p.v[d];
-  float dq_acc = 0.f, dv_acc = 0.f;
+  const long long slot = (long long)b * nchunk + chunk;
+  float* wl_part = p.dwloc_part + slot * (AD * NF) + d * NF;
   float gwl[NF];
 #pragma unroll
-  for (int c = 0; c < NF; ++c) gwl[c] = 0.f;
+  for (int c = 0; c < NF; c += 4) {           // start from the running partial: loads issued before the compute
+    const float4 t = *reinterpret_cast<const float4*>(wl_part + c);
+    gwl[c] = t.x; gwl[c + 1] = t.y; gwl[c + 2] = t.z; gwl[c + 3] = t.w;
+  }
+  float dq_acc = 0.f, dv_acc = p.dv_part[slot * AD + d];
+#pragma unroll
   for (int tt = 0; tt < TC; ++tt) {
     float dp = 0.f;
     if (tt < nt) {
       const float g = de[tt];
-      const long long row = (long long)b * Ti + t0 + tt;
-      const float a = p.a_save[row * AD + d];
+      const float a = av[tt];
       dp = g * vd * (1.f - a * a);
-      if (g != 0.f) p.dpmem[row * AD + d] += dp;
+      if (g != 0.f) atomicAdd(p.dpmem + ((long long)b * Ti + t0 + tt) * AD + d, dp);   // sole writer: compiles to RED, no round trip
       dq_acc += dp;
       dv_acc = fmaf(g, a, dv_acc);
       const float* fr = f + tt * (NF + 1);
@@ -290,18 +318,10 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
     }
     dpT[d * DPS + tt] = dp;
   }
-  {
-    const long long slot = (long long)b * nchunk + chunk;
-    float* o = p.dwloc_part + slot * (AD * NF) + d * NF;
 #pragma unroll
-    for (int c = 0; c < NF; c += 4) {
-      float4 t = *reinterpret_cast<float4*>(o + c);
-      t.x += gwl[c]; t.y += gwl[c + 1]; t.z += gwl[c + 2]; t.w += gwl[c + 3];
-      *reinterpret_cast<float4*>(o + c) = t;
-    }
-    p.dv_part[slot * AD + d] += dv_acc;
-    atomicAdd(p.dq + (long long)b * AD + d, dq_acc);
-  }
+  for (int c = 0; c < NF; c += 4) *reinterpret_cast<float4*>(wl_part + c) = make_float4(gwl[c], gwl[c + 1], gwl[c + 2], gwl[c + 3]);
+  p.dv_part[slot * AD + d] = dv_acc;
+  atomicAdd(p.dq + (long long)b * AD + d, dq_acc);
   __syncthreads();
   // (4) df[ti][c] = sum_d dpre[ti][d] * Wloc[d][c]; thread (c, group of 8 ti)
   {
@@ -322,7 +342,6 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
   __syncthreads();
   // (5) dWconv[c][ch][k] += sum_ti df[ti][c] * win[ch][ti+k]
   {
-    const long long slot = (long long)b * nchunk + chunk;
     for (int i = tid; i < NF * 2 * KS; i += 128) {
       const int k = i % KS, ch = (i / KS) % 2, c = i / (2 * KS);
       float a = 0.f;

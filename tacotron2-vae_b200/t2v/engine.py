@@ -290,16 +290,17 @@ def encoder_forward(ops, P, text, in_len, training, masks, seed, dev, packed=Tru
         ops.linear(X3, 512, ops.wr(P["encoder.lstm.weight_ih_l0" + sfx]), 512, gx, 4 * Hh, R, 4 * Hh, 512,
                    bias=P["encoder.lstm.bias_ih_l0" + sfx])
         GX.append(gx)
-    hst = _zeros(2, B, Hh, device=dev)
+    hbuf = _zeros(2, 2, B, Hh, device=dev)             # [ping-pong][direction]
     cst = _zeros(2, B, Hh, device=dev)
-    rec = _empty(2, B, 4 * Hh, device=dev)
+    Whh = [P["encoder.lstm.weight_hh_l0"], P["encoder.lstm.weight_hh_l0_reverse"]]
+    bhh = [P["encoder.lstm.bias_hh_l0"], P["encoder.lstm.bias_hh_l0_reverse"]]
     for s in range(Ti):
-        for d, sfx in enumerate(("", "_reverse")):
-            t = s if d == 0 else Ti - 1 - s
-            ops.gemm(hst[d], Hh, 1, P["encoder.lstm.weight_hh_l0" + sfx], Hh, 1, rec[d], 4 * Hh, B, 4 * Hh, Hh)
-            L("t2v_lstm_pointwise_fwd", rec[d], 1, 0, 4 * Hh, _p(GX[d], (2 + t) * 4 * Hh), Tp * 4 * Hh, None,
-              P["encoder.lstm.bias_hh_l0" + sfx], cst[d], Hh, hst[d], Hh, None, 0, cst[d], Hh, GS[d, t], CS[d, t + 1],
-              _p(HoutP, (2 + t) * 512 + d * Hh), Tp * 512, None, None, 0, 0, 0, 0.0, 0, lens, t, B, Hh, 0)
+        t0, t1 = s, Ti - 1 - s
+        a, b = s & 1, (s + 1) & 1
+        L("t2v_bilstm_step_fwd", _p(GX[0], (2 + t0) * 4 * Hh), _p(GX[1], (2 + t1) * 4 * Hh), Tp * 4 * Hh, Whh[0], Whh[1],
+          bhh[0], bhh[1], hbuf[a, 0], hbuf[a, 1], hbuf[b, 0], hbuf[b, 1], cst[0], cst[1],
+          _p(HoutP, (2 + t0) * 512), _p(HoutP, (2 + t1) * 512 + Hh), Tp * 512, GS[0, t0], GS[1, t1], CS[0, t0 + 1], CS[1, t1 + 1],
+          lens, t0, t1, B, Hh)
     ctx = dict(B=B, Ti=Ti, text=text, in_len=lens, conv=conv_saved, X3=X3, GS=GS, CS=CS, HoutP=HoutP)
     return HoutP, ctx
 
@@ -312,24 +313,27 @@ def encoder_backward(ops, P, dmem, ctx, training, seed, dev, grads):
     lens = ctx["in_len"]
     HoutP, GS, CS, X3 = ctx["HoutP"], ctx["GS"], ctx["CS"], ctx["X3"]
     dX3 = _zeros(R, 512, device=dev)
+    DGs = [_zeros(R, 4 * Hh, device=dev), _zeros(R, 4 * Hh, device=dev)]
+    WT = []
+    for sfx in ("", "_reverse"):
+        wt = _empty(Hh, 4 * Hh, device=dev)
+        L("t2v_transpose", P["encoder.lstm.weight_hh_l0" + sfx], Hh, wt, 4 * Hh, 4 * Hh, Hh, 0)
+        WT.append(wt)
+    dcb = _zeros(2, B, Hh, device=dev)
+    for s in range(Ti):
+        t0, t1 = Ti - 1 - s, s                    # each direction walks its own forward order backwards
+        L("t2v_bilstm_step_bwd", _p(DGs[0], (3 + t0) * 4 * Hh) if s > 0 else None, _p(DGs[1], (1 + t1) * 4 * Hh) if s > 0 else None,
+          Tp * 4 * Hh, WT[0], WT[1], _p(dmem, t0 * 512), _p(dmem, t1 * 512 + Hh), Ti * 512, dcb[0], dcb[1], GS[0, t0], GS[1, t1],
+          CS[0, t0 + 1], CS[1, t1 + 1], CS[0, t0], CS[1, t1 + 2], _p(DGs[0], (2 + t0) * 4 * Hh), _p(DGs[1], (2 + t1) * 4 * Hh),
+          lens, t0, t1, B, Hh)
     for d, sfx in enumerate(("", "_reverse")):
-        Whh = P["encoder.lstm.weight_hh_l0" + sfx]
-        DG = _zeros(R, 4 * Hh, device=dev)
-        dh = _zeros(B, Hh, device=dev)
-        dc = _zeros(B, Hh, device=dev)
-        order = range(Ti - 1, -1, -1) if d == 0 else range(Ti)
-        for t in order:
-            cprev = CS[d, t] if d == 0 else CS[d, t + 2]          # cell after the previous step of this direction
-            L("t2v_lstm_pointwise_bwd", _p(dmem, t * 512 + d * Hh), Ti * 512, dh, Hh, None, 0, dc, GS[d, t], CS[d, t + 1],
-              cprev, Hh, _p(DG, (2 + t) * 4 * Hh), Tp * 4 * Hh, None, None, 0, 0, 0, 0.0, 0, lens, t, B, Hh, 0)
-            # dh_prev = dgates_t @ W_hh
-            ops.gemm(_p(DG, (2 + t) * 4 * Hh), Tp * 4 * Hh, 1, Whh, 1, Hh, dh, Hh, B, Hh, 4 * Hh)
+        DG = DGs[d]
         # batched weight grads; h_prev of row r is HoutP[r -/+ 1] (zero pad rows make the boundaries right)
-        gWhh = _empty(4 * Hh, Hh, device=dev)
+        gWhh = _zeros(4 * Hh, Hh, device=dev)
         if d == 0:
-            ops.gemm(_p(DG, 4 * Hh), 1, 4 * Hh, HoutP, 1, 512, gWhh, Hh, 4 * Hh, Hh, R - 1)
+            ops.linear_dw(_p(DG, 4 * Hh), 4 * Hh, HoutP, 512, gWhh, Hh, R - 1, 4 * Hh, Hh, device=dev)
         else:
-            ops.gemm(DG, 1, 4 * Hh, _p(HoutP, 512 + Hh), 1, 512, gWhh, Hh, 4 * Hh, Hh, R - 1)
+            ops.linear_dw(DG, 4 * Hh, _p(HoutP, 512 + Hh), 512, gWhh, Hh, R - 1, 4 * Hh, Hh, device=dev)
         grads["encoder.lstm.weight_hh_l0" + sfx] = gWhh
         gWih = _zeros(4 * Hh, 512, device=dev)
         ops.linear_dw(DG, 4 * Hh, X3, 512, gWih, 512, R, 4 * Hh, 512, device=dev)

@@ -33,7 +33,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 agg = collections.defaultdict(lambda: [0, 0.0])
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
-        name = e.name.split("(")[0].replace("(anonymous namespace)::", "")
+        name = e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0]
         agg[name][0] += 1; agg[name][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
 tot = sum(v[1] for v in agg.values())
 lines = ["| kernel | launches/step | total us/step | avg us | share |", "|---|---:|---:|---:|---:|"]
