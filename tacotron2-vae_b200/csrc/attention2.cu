@@ -14,6 +14,8 @@
 // Weight-gradient partials (v, W_loc, W_conv) are accumulated per CTA slot across the time loop (no atomics) and
 // reduced once after it.
 #include "t2v_common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -29,7 +31,7 @@ struct E2Args {
   const float* w_prev; long long wprev_rs;     // nullable
   const float* cum_in;                          // [B,Ti]
   const float* pmem;                            // [B,Ti,AD]
-  const float* w_conv; const float* w_loc; const float* v;
+  const float* w_conv; const float* w_loc; const float* v;   // w_conv: transposed [2*KS][NF]
   const long long* lens; float mask_value;
   float* e_out;                                 // [B,Ti]
   float* a_save;                                // [B,Ti,AD] nullable
@@ -38,7 +40,7 @@ struct E2Args {
 
 // f[ti][c] for ti in the CTA's chunk: shared by forward and backward (recompute)
 __device__ __forceinline__ void conv_stage(const float* __restrict__ w_prev, long long wprev_rs, const float* __restrict__ cum_in,
-                                           const float* __restrict__ w_conv, int b, int t0, int Ti, float* win /*[2][WIN]*/,
+                                           const float* __restrict__ w_convT, int b, int t0, int Ti, float* win /*[2][WIN]*/,
                                            float* wcT /*[2*KS][NF]*/, float* f /*[TC][NF+1]*/) {
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * WIN; i += 128) {
@@ -48,9 +50,13 @@ __device__ __forceinline__ void conv_stage(const float* __restrict__ w_prev, lon
     if (s >= 0 && s < Ti) v = (ch == 0) ? (w_prev ? w_prev[b * wprev_rs + s] : 0.f) : cum_in[(long long)b * Ti + s];
     win[i] = v;
   }
-  for (int i = tid; i < NF * 2 * KS; i += 128) {          // src [c][ch][k] -> dst [ch*KS+k][c]
-    const int k = i % KS, ch = (i / KS) % 2, c = i / (2 * KS);
-    wcT[(ch * KS + k) * NF + c] = w_conv[i];
+  {   // conv weights are pre-transposed by the host ([ch*KS+k][c]): coalesced loads, conflict-free stores
+    constexpr int NL = (NF * 2 * KS + 127) / 128;
+    float tmp[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) { const int i = tid + 128 * j; tmp[j] = (i < NF * 2 * KS) ? w_convT[i] : 0.f; }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) { const int i = tid + 128 * j; if (i < NF * 2 * KS) wcT[i] = tmp[j]; }
   }
   __syncthreads();
   const int c = tid & 31, g = tid >> 5;
@@ -104,9 +110,14 @@ __global__ void __launch_bounds__(128) attn2_energy_kernel(E2Args p) {
       const long long row = (long long)b * Ti + t0 + tt;
       float s = q + pmv[tt];
       const float* fr = f + tt * (NF + 1);
+      float s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < NF; ++c) s = fmaf(fr[c], wl[c], s);
-      const float a = tanhf(s);
+      for (int c = 0; c < NF; c += 4) {
+        s = fmaf(fr[c], wl[c], s); s1 = fmaf(fr[c + 1], wl[c + 1], s1);
+        s2 = fmaf(fr[c + 2], wl[c + 2], s2); s3 = fmaf(fr[c + 3], wl[c + 3], s3);
+      }
+      s = (s + s1) + (s2 + s3);
+      const float a = t2v_tanh(s);
       if (p.a_save) p.a_save[row * AD + d] = a;
       const float part = warp_sum(vd * a);
       if (lane == 0) red[warp][tt] = part;
@@ -184,6 +195,140 @@ __global__ void __launch_bounds__(128) attn2_context_kernel(C2Args p) {
   const int col = ch * 128 + tid;
   if (p.ctx_out1) p.ctx_out1[b * p.ctx1_rs + col] = c;
   if (p.ctx_out2) p.ctx_out2[b * p.ctx2_rs + col] = c;
+}
+
+// ---- fused forward: one thread-block cluster per utterance (CS CTAs).  CTA r computes the energies of text chunk r
+// into its shared memory; after a cluster barrier every CTA gathers all chunks through distributed shared memory,
+// does the softmax and reduces the context for its 512/CS channel slice.  One launch per decoder step.
+struct F2Args {
+  E2Args e;
+  const float* cum_in; float* cum_out; const float* mem;
+  float* w_out; long long wout_rs;
+  float* ctx_out1; long long ctx1_rs; float* ctx_out2; long long ctx2_rs;
+  int rnd, tcx;              // tcx = text positions per CTA (<= TC)
+};
+__global__ void __launch_bounds__(128) attn2_fused_kernel(F2Args p) {
+  __shared__ float win[2 * WIN];
+  __shared__ float wcT[2 * KS * NF];
+  __shared__ float f[TC * (NF + 1)];
+  __shared__ float red[4][TC];
+  __shared__ float e_loc[TC];
+  __shared__ __align__(16) float wfull[8 * TC];
+  __shared__ __align__(16) float part[4 * 128];
+  __shared__ float red2[32];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, Ti = p.e.Ti;
+  const int t0 = rank * p.tcx;
+  const int nt = max(0, min(p.tcx, Ti - t0));
+  {
+    const E2Args& q = p.e;
+    const int d = tid;
+    float wl[NF];
+#pragma unroll
+    for (int c = 0; c < NF; c += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(q.w_loc + d * NF + c);
+      wl[c] = t.x; wl[c + 1] = t.y; wl[c + 2] = t.z; wl[c + 3] = t.w;
+    }
+    float pmv[TC];
+#pragma unroll
+    for (int tt = 0; tt < TC; ++tt) pmv[tt] = (tt < nt) ? q.pmem[((long long)b * Ti + t0 + tt) * AD + d] : 0.f;
+    float qv = 0.f;
+    for (int s = 0; s < q.n_qparts; ++s) qv += q.qparts[s * q.qpart_stride + (long long)b * AD + d];
+    const float vd = q.v[d];
+    conv_stage(q.w_prev, q.wprev_rs, q.cum_in, q.w_conv, b, t0, Ti, win, wcT, f);
+#pragma unroll
+    for (int tt = 0; tt < TC; ++tt) {
+      if (tt < nt) {
+        const long long row = (long long)b * Ti + t0 + tt;
+        float s = qv + pmv[tt];
+        const float* fr = f + tt * (NF + 1);
+        float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < NF; c += 4) {
+          s = fmaf(fr[c], wl[c], s); s1 = fmaf(fr[c + 1], wl[c + 1], s1);
+          s2 = fmaf(fr[c + 2], wl[c + 2], s2); s3 = fmaf(fr[c + 3], wl[c + 3], s3);
+        }
+        s = (s + s1) + (s2 + s3);
+        const float a = t2v_tanh(s);
+        if (q.a_save) q.a_save[row * AD + d] = a;
+        const float pr = warp_sum(vd * a);
+        if (lane == 0) red[warp][tt] = pr;
+      }
+    }
+    __syncthreads();
+    if (tid < TC) {
+      float e = -INFINITY;
+      if (tid < nt) {
+        e = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+        const long long len = q.lens ? q.lens[b] : Ti;
+        if (t0 + tid >= len) e = q.mask_value;
+      }
+      e_loc[tid] = e;
+    }
+  }
+  cluster.sync();
+  // gather the energies of every chunk (distributed shared memory) and softmax
+  for (int i = tid; i < CS * TC; i += 128) {
+    const int r = i / TC, j = i % TC;
+    const float* remote = cluster.map_shared_rank(e_loc, r);
+    wfull[i] = (j < p.tcx) ? remote[j] : -INFINITY;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int i = tid; i < CS * TC; i += 128) m = fmaxf(m, wfull[i]);
+  m = block_max(m, red2);
+  float ssum = 0.f;
+  for (int i = tid; i < CS * TC; i += 128) {
+    const float x = expf(wfull[i] - m);       // padding slots hold -inf -> 0
+    wfull[i] = x;
+    ssum += x;
+  }
+  ssum = block_sum(ssum, red2);
+  const float inv = 1.f / ssum;
+  __syncthreads();
+  for (int i = tid; i < CS * TC; i += 128) {
+    const int r = i / TC, j = i % TC, ti = r * p.tcx + j;
+    const float x = wfull[i] * inv;
+    wfull[i] = x;
+    if (r == rank && j < nt) {               // each CTA publishes its own chunk
+      p.w_out[b * p.wout_rs + ti] = x;
+      p.cum_out[(long long)b * Ti + ti] = p.cum_in[(long long)b * Ti + ti] + x;
+    }
+  }
+  __syncthreads();
+  cluster.sync();                            // nobody may exit while its e_loc can still be read remotely
+  // context for channels [rank*cpc, rank*cpc + cpc), cpc = 512/CS: warp -> text positions, lane -> 4 channels
+  const int cpc = ED / CS;                   // 128 (CS=4) or 64 (CS=8)
+  const int lanes_used = cpc / 4;            // 32 or 16
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < lanes_used) {
+    const float* mbase = p.mem + (long long)b * Ti * ED + rank * cpc + lane * 4;
+    constexpr int NB = 16;
+    for (int base = warp; base < Ti; base += 4 * NB) {
+      float4 mv[NB];
+      float wi[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int ti = base + 4 * j;
+        wi[j] = (ti < Ti) ? wfull[(ti / p.tcx) * TC + (ti % p.tcx)] : 0.f;
+        mv[j] = (wi[j] != 0.f) ? *reinterpret_cast<const float4*>(mbase + (long long)ti * ED) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        acc.x = fmaf(wi[j], mv[j].x, acc.x); acc.y = fmaf(wi[j], mv[j].y, acc.y);
+        acc.z = fmaf(wi[j], mv[j].z, acc.z); acc.w = fmaf(wi[j], mv[j].w, acc.w);
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(part + warp * 128 + lane * 4) = acc;
+  __syncthreads();
+  if (tid < cpc) {
+    const float c = t2v_rnd(part[tid] + part[128 + tid] + part[256 + tid] + part[384 + tid], p.rnd);
+    const int col = rank * cpc + tid;
+    if (p.ctx_out1) p.ctx_out1[b * p.ctx1_rs + col] = c;
+    if (p.ctx_out2) p.ctx_out2[b * p.ctx2_rs + col] = c;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -288,7 +433,13 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
   if (tid < TC) de[tid] = (tid < nt) ? p.w[b * p.w_rs + t0 + tid] * (dwv[t0 + tid] - s) : 0.f;
   // (2) recompute the location features of this chunk
   conv_stage(p.w_prev, p.wprev_rs, p.cum_in, p.w_conv, b, t0, Ti, win, wcT, f);
-  for (int i = tid; i < AD * NF; i += 128) wlT[(i / NF) * (NF + 1) + (i % NF)] = p.w_loc[i];
+  {
+    float tmp[AD * NF / 128];
+#pragma unroll
+    for (int j = 0; j < AD * NF / 128; ++j) tmp[j] = p.w_loc[tid + 128 * j];
+#pragma unroll
+    for (int j = 0; j < AD * NF / 128; ++j) { const int i = tid + 128 * j; wlT[(i / NF) * (NF + 1) + (i % NF)] = tmp[j]; }
+  }
   for (int i = tid; i < 2 * WIN; i += 128) scat[i] = 0.f;
   // (3) thread d: tanh/v backward over the chunk; dWloc row d in registers
   const int d = tid;
@@ -340,28 +491,42 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
     for (int j = 0; j < TPB; ++j) df[(g * TPB + j) * (NF + 1) + c] = acc[j];
   }
   __syncthreads();
-  // (5) dWconv[c][ch][k] += sum_ti df[ti][c] * win[ch][ti+k]
+  // (5) dWconv[ch][k][c] += sum_ti df[ti][c] * win[ch][ti+k]   (partials kept in the transposed [ch*KS+k][c] layout)
   {
-    for (int i = tid; i < NF * 2 * KS; i += 128) {
-      const int k = i % KS, ch = (i / KS) % 2, c = i / (2 * KS);
+    constexpr int NL = (NF * 2 * KS + 127) / 128;
+    float* part = p.dwconv_part + slot * (NF * 2 * KS);
+    float old[NL], acc[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) { const int i = tid + 128 * j; old[j] = (i < NF * 2 * KS) ? part[i] : 0.f; }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int i = tid + 128 * j;
       float a = 0.f;
-      const float* x = win + ch * WIN + k;
+      if (i < NF * 2 * KS) {
+        const int c = i % NF, chk = i / NF;                 // chk = ch*KS + k
+        const float* x = win + (chk / KS) * WIN + (chk % KS);
 #pragma unroll 8
-      for (int tt = 0; tt < TC; ++tt) a = fmaf(df[tt * (NF + 1) + c], x[tt], a);
-      p.dwconv_part[slot * (NF * 2 * KS) + i] += a;
+        for (int tt = 0; tt < TC; ++tt) a = fmaf(df[tt * (NF + 1) + c], x[tt], a);
+      }
+      acc[j] = a;
     }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) { const int i = tid + 128 * j; if (i < NF * 2 * KS) part[i] = old[j] + acc[j]; }
   }
   // (6) adjoint conv, scattered: contribution of this chunk's df to dwcat[ch][t0-HALO+j], j in [0,WIN)
   for (int i = tid; i < 2 * WIN; i += 128) {
     const int ch = i / WIN, j = i % WIN;
     float a = 0.f;
-    // s = t0 - HALO + j ; ti = s - k + HALO  =>  tt = j - k, 0 <= tt < TC
-    const int k_lo = max(0, j - (TC - 1)), k_hi = min(KS - 1, j);
-    for (int k = k_lo; k <= k_hi; ++k) {
-      const float* dfr = df + (j - k) * (NF + 1);
-      const float* wk = wcT + (ch * KS + k) * NF;
+    // s = t0 - HALO + j ; ti = s - k + HALO  =>  tt = j - k, 0 <= tt < TC   (k uniform across the warp: broadcast reads)
+#pragma unroll 1
+    for (int k = 0; k < KS; ++k) {
+      const int tt = j - k;
+      if (tt >= 0 && tt < TC) {
+        const float* dfr = df + tt * (NF + 1);
+        const float* wk = wcT + (ch * KS + k) * NF;
 #pragma unroll 8
-      for (int c = 0; c < NF; ++c) a = fmaf(dfr[c], wk[c], a);
+        for (int c = 0; c < NF; ++c) a = fmaf(dfr[c], wk[c], a);
+      }
     }
     const int sidx = t0 - HALO + j;
     if (sidx >= 0 && sidx < Ti && a != 0.f) {
@@ -393,6 +558,26 @@ T2V_API int t2v_attn2_fwd(const float* qparts, int n_qparts, long long qpart_str
   e.qparts = qparts; e.n_qparts = n_qparts; e.qpart_stride = qpart_stride; e.w_prev = w_prev; e.wprev_rs = wprev_rs;
   e.cum_in = cum_in; e.pmem = pmem; e.w_conv = w_conv; e.w_loc = w_loc; e.v = v; e.lens = lens; e.mask_value = mask_value;
   e.e_out = e_buf; e.a_save = a_save; e.B = B; e.Ti = Ti;
+  if (Ti <= 8 * TC) {          // one cluster of 4 or 8 CTAs per utterance
+    const int CS = (Ti <= 4 * TC) ? 4 : 8;
+    F2Args fa;
+    fa.e = e; fa.cum_in = cum_in; fa.cum_out = cum_out; fa.mem = mem; fa.w_out = w_out; fa.wout_rs = wout_rs;
+    fa.ctx_out1 = ctx_out1; fa.ctx1_rs = ctx1_rs; fa.ctx_out2 = ctx_out2; fa.ctx2_rs = ctx2_rs; fa.rnd = rnd;
+    fa.tcx = (Ti + CS - 1) / CS;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(CS, B, 1);
+    cfg.blockDim = dim3(128, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn2_fused_kernel, fa));
+    T2V_COUNT_LAUNCH();
+    return 0;
+  }
   dim3 g1((Ti + TC - 1) / TC, B);
   attn2_energy_kernel<<<g1, 128, 0, st>>>(e);
   T2V_COUNT_LAUNCH();

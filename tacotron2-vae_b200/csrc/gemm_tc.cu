@@ -10,6 +10,7 @@
 //   * split-K over blockIdx.z: partial tiles are either stored to D + z*split_stride or atomically added.
 #include "t2v_common.cuh"
 #include "gemm_tc.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -109,11 +110,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 
 constexpr int kBM = 128;
 
-template <int BN, int ESIZE, int STAGES>
+template <int BN, int ESIZE, int STAGES, int BM = 128>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
   constexpr int BK = 128 / ESIZE;           // elements per 128-byte swizzle row
-  constexpr int A_BYTES = kBM * 128;
+  constexpr int A_BYTES = BM * 128;
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -124,7 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_holder = (uint32_t*)(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int it0 = blockIdx.z * p.iters_per_split;
   const int n_it = p.iters_per_split;
 
@@ -167,7 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // instruction descriptor: D=f32, A/B format, K-major both, N>>3, M>>4
       constexpr uint32_t fmt = (ESIZE == 4) ? 2u : 1u;   // TF32 : BF16
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                 ((uint32_t)(kBM >> 4) << 24);
+                                 ((uint32_t)(BM >> 4) << 24);
       for (int it = 0; it < n_it; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -190,14 +191,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
+    // accumulator row held by this thread: M=128 -> TMEM lane == row; M=64 -> rows 16q..16q+15 sit in lanes 32q..32q+15
+    const int row = (BM == 128) ? (m0 + q * 32 + lane) : (m0 + q * 16 + lane);
+    const bool lane_has_row = (BM == 128) || (lane < 16);
     float* drow = p.D + (long long)blockIdx.z * p.split_stride + (long long)row * p.ldd;
     const bool vec_ok = ((p.ldd & 3) == 0) && ((((uintptr_t)p.D) & 15) == 0) && ((p.split_stride & 3) == 0);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (row < p.M) {
+      if (row < p.M && lane_has_row) {
         const int col0 = n0 + c0;
         if (!p.epi_atomic && vec_ok && col0 + 32 <= p.N) {
 #pragma unroll
@@ -238,17 +241,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int ESIZE>
 constexpr int stages_for() { return (BN == 256) ? 4 : (BN == 128 ? 6 : 8); }
 
-template <int BN, int ESIZE>
+template <int BN, int ESIZE, int BM = 128>
 int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcParams& p, int splits, cudaStream_t st) {
-  constexpr int STAGES = stages_for<BN, ESIZE>();
-  constexpr int smem = STAGES * (kBM * 128 + BN * 128) + 1024 + 256;
+  constexpr int STAGES = (BM == 64) ? 8 : stages_for<BN, ESIZE>();
+  constexpr int smem = STAGES * (BM * 128 + BN * 128) + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    T2V_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, ESIZE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, ESIZE, STAGES, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  dim3 grid(t2v_ceil_div(p.M, kBM), t2v_ceil_div(p.N, BN), splits);
-  gemm_tc_kernel<BN, ESIZE, STAGES><<<grid, 192, smem, st>>>(tmA, tmB, p);
+  dim3 grid(t2v_ceil_div(p.M, BM), t2v_ceil_div(p.N, BN), splits);
+  gemm_tc_kernel<BN, ESIZE, STAGES, BM><<<grid, 192, smem, st>>>(tmA, tmB, p);
   T2V_COUNT_LAUNCH();
   T2V_LAUNCH_CHECK();
   return 0;
@@ -294,7 +297,10 @@ int t2v_gemm_tc_plan(T2VGemmTcPlan* plan, const void* A, long long lda, long lon
   T2V_ARG_CHECK(splits == 1 || epi_atomic || split_stride > 0, "split_stride required for partial stores");
   int BN = bn_hint;
   if (BN != 64 && BN != 128 && BN != 256) BN = (N <= 64) ? 64 : 128;
-  int r = encode_2d(&plan->tmA, A, esize, a_inner, a_rows, lda, kBM);
+  static const bool allow_m64 = !(getenv("T2V_GEMM_M64") && getenv("T2V_GEMM_M64")[0] == '0');
+  const int BM = (M <= 64 && BN == 128 && esize == 4 && allow_m64) ? 64 : 128;
+  plan->BM = BM;
+  int r = encode_2d(&plan->tmA, A, esize, a_inner, a_rows, lda, BM);
   if (r) return r;
   r = encode_2d(&plan->tmB, B, esize, b_inner, b_rows, ldb, BN);
   if (r) return r;
@@ -312,6 +318,7 @@ int t2v_gemm_tc_run(const T2VGemmTcPlan* plan, int a_row0, int b_row0, float* D,
   p.a_row0 = a_row0; p.b_row0 = b_row0; p.D = D; p.bias = bias;
   const int BN = plan->BN, splits = plan->splits;
   if (plan->esize == 4) {
+    if (BN == 128 && plan->BM == 64) return launch_gemm_tc<128, 4, 64>(plan->tmA, plan->tmB, p, splits, stream);
     if (BN == 64) return launch_gemm_tc<64, 4>(plan->tmA, plan->tmB, p, splits, stream);
     if (BN == 128) return launch_gemm_tc<128, 4>(plan->tmA, plan->tmB, p, splits, stream);
     return launch_gemm_tc<256, 4>(plan->tmA, plan->tmB, p, splits, stream);

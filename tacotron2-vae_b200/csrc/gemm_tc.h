@@ -21,7 +21,7 @@ struct GemmTcParams {
 struct T2VGemmTcPlan {
   CUtensorMap tmA, tmB;
   GemmTcParams p;
-  int BN, esize, splits;
+  int BN, esize, splits, BM;
 };
 int t2v_gemm_tc_plan(T2VGemmTcPlan* plan, const void* A, long long lda, long long a_rows, long long a_inner, const void* B,
                      long long ldb, long long b_rows, long long b_inner, long long ldd, int M, int N, int k_sub, int taps,

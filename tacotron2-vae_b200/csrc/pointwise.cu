@@ -349,10 +349,10 @@ __global__ void lstm_pointwise_fwd_kernel(LstmFwdArgs a) {
     if (a.b2) v += a.b2[col];
     g4[g] = v;
   }
-  const float ig = t2v_sigmoid(g4[0]), fg = t2v_sigmoid(g4[1]), gg = tanhf(g4[2]), og = t2v_sigmoid(g4[3]);
+  const float ig = t2v_sigmoid_fast(g4[0]), fg = t2v_sigmoid_fast(g4[1]), gg = t2v_tanh(g4[2]), og = t2v_sigmoid_fast(g4[3]);
   const float cp = a.c_prev[b * a.cprev_rs + j];
   const float c2 = fg * cp + ig * gg;
-  const float h2 = og * tanhf(c2);
+  const float h2 = og * t2v_tanh(c2);
   const uint64_t idx = a.drop_base + (uint64_t)b * a.H + j;
   const float hd = t2v_rnd(h2 * t2v_keep_scale(a.drop_h, idx), a.rnd);
   const float cd = c2 * t2v_keep_scale(a.drop_c, idx);
@@ -399,7 +399,7 @@ __global__ void lstm_pointwise_bwd_kernel(LstmBwdArgs a) {
   const float* gs = a.gates_save + (long long)b * 4 * a.H + j;
   const float ig = gs[0], fg = gs[a.H], gg = gs[2 * a.H], og = gs[3 * a.H];
   const float c2 = a.cpre_save[(long long)b * a.H + j];
-  const float tc = tanhf(c2);
+  const float tc = t2v_tanh(c2);
   float dc = a.dc[(long long)b * a.H + j] * t2v_keep_scale(a.drop_c, idx) + dh * og * (1.f - tc * tc);
   const float cp = a.c_prev[b * a.cprev_rs + j];
   dg[0] = t2v_rnd(dc * gg * ig * (1.f - ig), a.rnd);

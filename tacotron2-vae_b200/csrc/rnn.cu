@@ -11,7 +11,7 @@ namespace {
 
 constexpr int UPC = 4;          // hidden units (= warps) per CTA
 constexpr int MT = 64;          // batch rows per tile
-constexpr int MS = MT + 1;      // smem row stride of the transposed tiles (conflict-free staging and reads)
+constexpr int MS = MT + 1;      // (unused) transposed-tile stride
 
 struct BiFwdArgs {
   const float* gx[2]; long long gx_bs;     // per dir: pointer to row (b=0, t) of the pre-gates; batch stride
@@ -30,8 +30,9 @@ __global__ void __launch_bounds__(UPC * 32) bilstm_step_fwd_kernel(BiFwdArgs p) 
   extern __shared__ __align__(16) float smf[];
   const int H = p.H, dir = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * UPC, u = u0 + warp;
-  float* hT = smf;                       // [H][MT]   h_prev transposed
-  float* ws = hT + H * MS;               // [H][UPC][4] recurrent weights of this CTA's units, k-major
+  const int HS = H + 1;                  // padded row stride: lane-varying rows hit distinct banks
+  float* hT = smf;                       // [MT][H+1] h_prev tile, row major
+  float* ws = hT + ((MT * HS + 3) & ~3); // [H][UPC][4] recurrent weights of this CTA's units, k-major
   const float* W = p.w_hh[dir];
   for (int i = threadIdx.x; i < H * UPC * 4; i += UPC * 32) {
     const int k = i % H, g = (i / H) % 4, uu = i / (4 * H);
@@ -40,9 +41,27 @@ __global__ void __launch_bounds__(UPC * 32) bilstm_step_fwd_kernel(BiFwdArgs p) 
   const int t = p.t[dir];
   for (int m0 = 0; m0 < p.B; m0 += MT) {
     __syncthreads();
-    for (int i = threadIdx.x; i < H * MT; i += UPC * 32) {
-      const int k = i % H, m = i / H;
-      hT[k * MS + m] = (m0 + m < p.B) ? p.h_prev[dir][(long long)(m0 + m) * H + k] : 0.f;
+    {   // stage the h_prev tile: float4 global loads, 8 in flight per thread
+      const int nv = MT * H / 4;
+      for (int i0 = threadIdx.x; i0 < nv; i0 += UPC * 32 * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = i0 + j * UPC * 32;
+          const int m = (i * 4) / H, k = (i * 4) % H;
+          v[j] = (i < nv && m0 + m < p.B) ? *reinterpret_cast<const float4*>(p.h_prev[dir] + (long long)(m0 + m) * H + k)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = i0 + j * UPC * 32;
+          if (i < nv) {
+            const int m = (i * 4) / H, k = (i * 4) % H;
+            float* d = hT + m * HS + k;
+            d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+          }
+        }
+      }
     }
     __syncthreads();
     float acc[2][4];
@@ -52,7 +71,7 @@ __global__ void __launch_bounds__(UPC * 32) bilstm_step_fwd_kernel(BiFwdArgs p) 
       for (int g = 0; g < 4; ++g) acc[r][g] = 0.f;
 #pragma unroll 4
     for (int k = 0; k < H; ++k) {
-      const float a0 = hT[k * MS + lane], a1 = hT[k * MS + 32 + lane];
+      const float a0 = hT[lane * HS + k], a1 = hT[(32 + lane) * HS + k];
       const float4 w = *reinterpret_cast<const float4*>(ws + (k * UPC + warp) * 4);
       acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]);
       acc[0][2] = fmaf(a0, w.z, acc[0][2]); acc[0][3] = fmaf(a0, w.w, acc[0][3]);
@@ -107,17 +126,36 @@ __global__ void __launch_bounds__(UPC * 32) bilstm_step_bwd_kernel(BiBwdArgs p) 
   const int H = p.H, K = 4 * H, dir = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * UPC, u = u0 + warp;
   constexpr int KC = 256;
-  float* dT = smb;                       // [KC][MT] dgates chunk transposed
-  float* ws = dT + KC * MS;              // [KC][UPC]
+  constexpr int DS = KC + 1;
+  float* dT = smb;                       // [MT][KC+1] dgates chunk, row major
+  float* ws = dT + MT * DS;              // [KC][UPC]
   const int t = p.t[dir];
   for (int m0 = 0; m0 < p.B; m0 += MT) {
     float acc[2] = {0.f, 0.f};
     if (p.dg_next[dir]) {
       for (int k0 = 0; k0 < K; k0 += KC) {
         __syncthreads();
-        for (int i = threadIdx.x; i < KC * MT; i += UPC * 32) {
-          const int k = i % KC, m = i / KC;
-          dT[k * MS + m] = (m0 + m < p.B) ? p.dg_next[dir][(m0 + m) * p.dg_bs + k0 + k] : 0.f;
+        {
+          const int nv = MT * KC / 4;
+          for (int i0 = threadIdx.x; i0 < nv; i0 += UPC * 32 * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int i = i0 + j * UPC * 32;
+              const int m = (i * 4) / KC, k = (i * 4) % KC;
+              v[j] = (i < nv && m0 + m < p.B) ? *reinterpret_cast<const float4*>(p.dg_next[dir] + (m0 + m) * p.dg_bs + k0 + k)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int i = i0 + j * UPC * 32;
+              if (i < nv) {
+                const int m = (i * 4) / KC, k = (i * 4) % KC;
+                float* d = dT + m * DS + k;
+                d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+              }
+            }
+          }
         }
         for (int i = threadIdx.x; i < KC * UPC; i += UPC * 32) {
           const int k = i % KC, uu = i / KC;
@@ -127,8 +165,8 @@ __global__ void __launch_bounds__(UPC * 32) bilstm_step_bwd_kernel(BiBwdArgs p) 
 #pragma unroll 8
         for (int k = 0; k < KC; ++k) {
           const float w = ws[k * UPC + warp];
-          acc[0] = fmaf(dT[k * MS + lane], w, acc[0]);
-          acc[1] = fmaf(dT[k * MS + 32 + lane], w, acc[1]);
+          acc[0] = fmaf(dT[lane * DS + k], w, acc[0]);
+          acc[1] = fmaf(dT[(32 + lane) * DS + k], w, acc[1]);
         }
       }
     }
@@ -164,13 +202,13 @@ T2V_API int t2v_bilstm_step_fwd(const float* gx0, const float* gx1, long long gx
                                 float* hnext1, float* c0, float* c1, float* seq0, float* seq1, long long seq_bs, float* gs0,
                                 float* gs1, float* cs0, float* cs1, const long long* lens, int t0, int t1, int B, int H,
                                 cudaStream_t st) {
-  T2V_ARG_CHECK(B > 0 && H % UPC == 0 && H <= 512 && (H * MS) % 4 == 0, "shape");
+  T2V_ARG_CHECK(B > 0 && H % UPC == 0 && H <= 512 && H % 4 == 0, "shape");
   BiFwdArgs a;
   a.gx[0] = gx0; a.gx[1] = gx1; a.gx_bs = gx_bs; a.w_hh[0] = whh0; a.w_hh[1] = whh1; a.b_hh[0] = bhh0; a.b_hh[1] = bhh1;
   a.h_prev[0] = hprev0; a.h_prev[1] = hprev1; a.h_next[0] = hnext0; a.h_next[1] = hnext1; a.c_state[0] = c0; a.c_state[1] = c1;
   a.seq_out[0] = seq0; a.seq_out[1] = seq1; a.seq_bs = seq_bs; a.gates_save[0] = gs0; a.gates_save[1] = gs1;
   a.c_save[0] = cs0; a.c_save[1] = cs1; a.lens = lens; a.t[0] = t0; a.t[1] = t1; a.B = B; a.H = H;
-  const size_t smem = sizeof(float) * (size_t)(H * MS + H * UPC * 4);
+  const size_t smem = sizeof(float) * (size_t)(((MT * (H + 1) + 3) & ~3) + H * UPC * 4);
   static size_t cur = 48 * 1024;
   if (smem > cur) {
     T2V_CUDA_CHECK(cudaFuncSetAttribute(bilstm_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -193,7 +231,7 @@ T2V_API int t2v_bilstm_step_bwd(const float* dgn0, const float* dgn1, long long 
   a.dout[1] = dout1; a.dout_bs = dout_bs; a.dc[0] = dc0; a.dc[1] = dc1; a.gates_save[0] = gs0; a.gates_save[1] = gs1;
   a.c_save[0] = cs0; a.c_save[1] = cs1; a.c_prev[0] = cp0; a.c_prev[1] = cp1; a.dg_out[0] = dgo0; a.dg_out[1] = dgo1;
   a.lens = lens; a.t[0] = t0; a.t[1] = t1; a.B = B; a.H = H;
-  const size_t smem = sizeof(float) * (size_t)(256 * MS + 256 * UPC);
+  const size_t smem = sizeof(float) * (size_t)(MT * 257 + 256 * UPC);
   static bool set = false;
   if (!set) {
     T2V_CUDA_CHECK(cudaFuncSetAttribute(bilstm_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

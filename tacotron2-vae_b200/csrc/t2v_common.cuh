@@ -83,6 +83,13 @@ __device__ __forceinline__ float t2v_tf32(float x) {
 __device__ __forceinline__ float t2v_rnd(float x, int flag) { return flag ? t2v_tf32(x) : x; }
 
 __device__ __forceinline__ float t2v_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+// tanh through one MUFU exp + one fast divide: absolute error ~1e-7 (fp32 rounding level), ~4x fewer instructions than
+// tanhf; used inside the latency-critical decoder-step kernels.
+__device__ __forceinline__ float t2v_tanh(float x) {
+  const float e = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+__device__ __forceinline__ float t2v_sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -434,16 +434,16 @@ def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
         rows, Co, Ct = ly["rows"], ly["Co"], ly["Ct"]
         dY = _empty(rows, Co, device=dev)
         _bn_backward(dX, ly["Y"], dY, rows, Co, 1, 0, 1, rows, P, _REF + "bns.%d" % i, training, 1, None, 0, 0, 0.0, 1, dev, grads,
-                     rnd=0 if ly["exact"] else 1)
+                     rnd=ops.R)
         grads[ly["wname"] + ".bias"] = _colsum(dY, rows, Co, 1, 0, 1, dev)
         dWk = _zeros(Co, 9 * Ct, device=dev)
-        ops.linear_dw(dY, Co, ly["col"], 9 * Ct, dWk, 9 * Ct, rows, Co, 9 * Ct, device=dev, force_exact=ly["exact"])
+        ops.linear_dw(dY, Co, ly["col"], 9 * Ct, dWk, 9 * Ct, rows, Co, 9 * Ct, device=dev)
         gW = torch.empty_like(P[ly["wname"] + ".weight"])
         L("t2v_conv1d_unpack_grad", dWk, gW, Co, Ct, 9, 0.0)
         grads[ly["wname"] + ".weight"] = gW
         if i > 0:
             dcol = _empty(rows, 9 * Ct, device=dev)
-            ops.linear_dx(dY, Co, ly["Wk"], 9 * Ct, dcol, 9 * Ct, rows, Co, 9 * Ct, force_exact=ly["exact"])
+            ops.linear_dx(dY, Co, ly["Wk"], 9 * Ct, dcol, 9 * Ct, rows, Co, 9 * Ct)
             dX = _empty(N * ly["H"] * ly["W"], ly["Ci"], device=dev)
             L("t2v_col2im_3x3s2", dcol, dX, N, ly["H"], ly["W"], ly["Ci"])
 
@@ -501,6 +501,13 @@ _D = "decoder."
 _A = "decoder.attention_layer."
 
 
+def conv_weight_T(P, dev):
+    """location conv weight [32,2,31] -> [2*31, 32] (what attention2.cu stages into shared memory)"""
+    wt = _empty(62, 32, device=dev)
+    L("t2v_transpose", P[_A + "location_layer.location_conv.conv.weight"], 62, wt, 32, 32, 62, 0)
+    return wt
+
+
 def pack_decoder_weights(P, dev, R=0):
     Wa = _empty(4096, 1792, device=dev)
     L("t2v_copy2d", P[_D + "attention_rnn.weight_ih"], 768, 1, Wa, 1792, 4096, 768, 0.0, R)
@@ -530,7 +537,7 @@ def _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_v
     S.ba1, S.ba2 = P[_D + "attention_rnn.bias_ih"].data_ptr(), P[_D + "attention_rnn.bias_hh"].data_ptr()
     S.bd1, S.bd2 = P[_D + "decoder_rnn.bias_ih"].data_ptr(), P[_D + "decoder_rnn.bias_hh"].data_ptr()
     S.Wq = W["Wq"].data_ptr()
-    S.Wconv = P[_A + "location_layer.location_conv.conv.weight"].data_ptr()
+    S.Wconv = W["WconvT"].data_ptr()          # [2*31, 32]: taps-major transpose of the location conv weight
     S.Wloc = P[_A + "location_layer.location_dense.linear_layer.weight"].data_ptr()
     S.v = P[_A + "v.linear_layer.weight"].data_ptr()
     S.mem, S.pmem = mem.data_ptr(), pmem.data_ptr()
@@ -559,6 +566,7 @@ def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, dro
     W = {}
     W["Wa"], W["Wd"], W["Wpg"], W["bpg"] = pack_decoder_weights(P, dev, ops.R)
     W["Wq"] = ops.wr(P[_A + "query_layer.linear_layer.weight"])
+    W["WconvT"] = conv_weight_T(P, dev)
     pmem = _empty(B * Ti, 128, device=dev)
     ops.linear(memory, 512, ops.wr(P[_A + "memory_layer.linear_layer.weight"]), 512, pmem, 128, B * Ti, 128, 512)
     buf = alloc_decoder_buffers(B, Ti, To, dev, save=True)
@@ -648,6 +656,10 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
                              (_A + "location_layer.location_conv.conv.weight", t["dwconv_part"], 32 * 2 * 31)):
         g = _empty(cols, device=dev)
         L("t2v_sum_rows_per_batch", part, g, 1, B * nck, cols, 0.0)
+        if name.endswith("location_conv.conv.weight"):          # partials are kept in the [2*31, 32] layout
+            gt = _empty(cols, device=dev)
+            L("t2v_transpose", g, 32, gt, 62, 62, 32, 0)
+            g = gt
         grads[name] = g.view_as(P[name])
     _trace("  bwd decoder dW")
     # prenet backward (model.py:91-102)

@@ -126,6 +126,7 @@ class DecoderSession(object):
         self.W = {}
         self.W["Wa"], self.W["Wd"], self.W["Wpg"], self.W["bpg"] = engine.pack_decoder_weights(P, dev, ops.R)
         self.W["Wq"] = ops.wr(P["decoder.attention_layer.query_layer.linear_layer.weight"])
+        self.W["WconvT"] = engine.conv_weight_T(P, dev)
         self.memory = memory
         self.pmem = torch.empty(self.B * self.Ti, 128, device=dev)
         ops.linear(memory, 512, ops.wr(P["decoder.attention_layer.memory_layer.linear_layer.weight"]), 512, self.pmem, 128,

@@ -203,20 +203,22 @@ def test_loss_and_adam_match_torch(L):
     assert torch.allclose(pd.cpu(), pt.detach(), rtol=1e-5, atol=1e-6)
 
 
-def test_attention_v2_matches_v1(L):
+@pytest.mark.parametrize("Ti", [77, 120, 200, 300])
+def test_attention_v2_matches_v1(L, Ti):
     """The SM-parallel attention kernels (attention2.cu) against the one-CTA-per-utterance reference kernels
     (attention.cu, themselves checked against the oracle above): forward and the full backward incl. the scattered
     adjoint conv and the per-slot weight-gradient partials."""
     from t2v import _lib
     torch.manual_seed(8)
     dev = "cuda"
-    B, Ti = 5, 77
+    B = 5
     nck = int(_lib.lib().t2v_attn2_chunks(Ti))
     r = lambda *s: torch.randn(*s, device=dev)
     q = r(B, 128); wprev = torch.softmax(r(B, Ti), 1); cum = torch.rand(B, Ti, device=dev)
     pmem = r(B, Ti, 128); mem = r(B, Ti, 512)
     wconv = r(32, 2, 31) * 0.2; wloc = r(128, 32) * 0.2; v = r(128) * 0.3
-    lens = torch.tensor([77, 70, 40, 33, 9], device=dev)
+    lens = torch.tensor([Ti, Ti - 7, Ti // 2, 33, 9], device=dev)
+    wconvT = wconv.reshape(32, 62).t().contiguous()
     out = {}
     for ver in (1, 2):
         w = torch.zeros(B, Ti, device=dev); cumo = torch.zeros(B, Ti, device=dev)
@@ -226,7 +228,7 @@ def test_attention_v2_matches_v1(L):
               c2, 512, a, B, Ti, 0)
         else:
             e = torch.empty(B, Ti, device=dev)
-            L("t2v_attn2_fwd", q, 1, 0, wprev, Ti, cum, cumo, pmem, mem, wconv, wloc, v, lens, -float("inf"), e, w, Ti, c1, 512,
+            L("t2v_attn2_fwd", q, 1, 0, wprev, Ti, cum, cumo, pmem, mem, wconvT, wloc, v, lens, -float("inf"), e, w, Ti, c1, 512,
               c2, 512, a, B, Ti, 0)
         out[ver] = (w, cumo, c1, c2, a)
     for x, y in zip(out[1], out[2]):
@@ -247,7 +249,7 @@ def test_attention_v2_matches_v1(L):
     dv2 = torch.zeros(B * nck, 128, device=dev); dwl2 = torch.zeros(B * nck, 128 * 32, device=dev)
     dwc2 = torch.zeros(B * nck, 32 * 62, device=dev)
     dwo2 = torch.full((B, Ti), 7.0, device=dev); gcn = torch.full((B, Ti), -3.0, device=dev)
-    L("t2v_attn2_bwd", d1, 512, d2, 512, d3, 512, dctx, dw_in, dwo2, gc, gcn, dwp, w, Ti, wprev, Ti, cum, a_save, mem, wconv,
+    L("t2v_attn2_bwd", d1, 512, d2, 512, d3, 512, dctx, dw_in, dwo2, gc, gcn, dwp, w, Ti, wprev, Ti, cum, a_save, mem, wconvT,
       wloc, v, lens, dpm2, dq2, dv2, dwl2, dwc2, B, Ti)
     tol = dict(atol=2e-5, rtol=1e-4)
     assert torch.allclose(dctx, d1 + d2 + d3, **tol)
@@ -256,4 +258,18 @@ def test_attention_v2_matches_v1(L):
     assert torch.allclose(dwo1, dwo2, **tol) and torch.allclose(gc1, gcn, **tol)
     assert torch.allclose(dv1.sum(0), dv2.sum(0), **tol)
     assert torch.allclose(dwl1.sum(0), dwl2.sum(0), atol=1e-4, rtol=1e-4)
-    assert torch.allclose(dwc1.sum(0), dwc2.sum(0), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(dwc1.sum(0).view(32, 62), dwc2.sum(0).view(62, 32).t(), atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("M", [64, 37, 16])
+def test_gemm_tc_m64_tile(L, M):
+    """Small-M GEMMs (the decoder-step shapes: M = batch <= 64) run on the UMMA M=64 tile."""
+    torch.manual_seed(9)
+    dev = "cuda"
+    N, K = 4096, 1792
+    A = torch.randn(M + 70, K, device=dev)[:M]          # rows beyond M exist in memory (like the next time step's rows)
+    Bw = torch.randn(N, K, device=dev)
+    parts = torch.full((4, M, N), float("nan"), device=dev)
+    L("t2v_gemm_tc", A, K, M + 70, K, Bw, K, N, K, parts, N, None, M, N, K, 1, 0, 0, 0, 0, 4, 4, M * N, 0, 1.0, 128)
+    ref = (A.double() @ Bw.double().t()).float()
+    assert _rel(parts.sum(0), ref) < 2e-3
