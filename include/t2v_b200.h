@@ -130,6 +130,13 @@ int t2v_bilstm_step_bwd(const float* dgn0, const float* dgn1, long long dg_bs, c
                         const float* dout0, const float* dout1, long long dout_bs, float* dc0, float* dc1, const float* gs0,
                         const float* gs1, const float* cs0, const float* cs1, const float* cp0, const float* cp1, float* dgo0,
                         float* dgo1, const long long* lens, int t0, int t1, int B, int H, cudaStream_t stream);
+/* same, with dh1 given as `dh1_parts` split-K partial buffers (stride dh1_pstride) that are summed on the fly */
+int t2v_lstm_pointwise_bwd_parts(const float* dh1, long long dh1_rs, int dh1_parts, long long dh1_pstride, const float* dh2,
+                                 long long dh2_rs, const float* dh3, long long dh3_rs, float* dc, const float* gates_save,
+                                 const float* cpre_save, const float* c_prev, long long cprev_rs, float* dgates, long long dg_rs,
+                                 const float* mask_h, const float* mask_c, unsigned long long seed, unsigned int site_h,
+                                 unsigned int site_c, float p, unsigned long long drop_base, const long long* lens, int t,
+                                 int B, int H, int rnd, cudaStream_t stream);
 int t2v_gru_pointwise_fwd(const float* gi, long long gi_rs, const float* gh, const float* b_ih, const float* b_hh, const float* h_prev,
                           float* h_out, float* save, int B, int H, cudaStream_t stream);
 int t2v_gru_pointwise_bwd(const float* dh, const float* save, const float* h_prev, float* dgi, long long dgi_rs, float* dgh,

@@ -1,6 +1,7 @@
 // Library-wide state of the t2v_b200 C-ABI: last-error string, launch counter, version.
 #include "t2v_common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 static thread_local char g_err[1024] = "";
 unsigned long long g_t2v_launches = 0;
@@ -10,6 +11,11 @@ void t2v_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool t2v_pdl_enabled() {
+  static const bool on = !(getenv("T2V_PDL") && getenv("T2V_PDL")[0] == '0');
+  return on;
 }
 
 T2V_API const char* t2v_last_error(void) { return g_err; }

@@ -15,15 +15,20 @@
 // reduced once after it.
 #include "t2v_common.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int NF = 32, KS = 31, AD = 128, ED = 512, HALO = 15;
-constexpr int TC = 32;                 // text positions per CTA
+#ifndef T2V_ATTN_TC
+#define T2V_ATTN_TC 32
+#endif
+constexpr int TC = T2V_ATTN_TC;        // text positions per CTA (16 was tried: twice the CTAs but the per-CTA weight staging dominates -> slower)
 constexpr int WIN = TC + 2 * HALO;     // 62
 constexpr int NCH = 4;                 // channel chunks of 128 for the context kernels
-constexpr int TPB = 8;                 // text positions per thread in the conv stage (TC / 4 thread groups)
+constexpr int TPB = TC / 4;             // text positions per thread in the conv stage (4 thread groups)
+static_assert(TPB == 4 || TPB == 8, "TC must be 16 or 32");
 constexpr int DPS = TC + 4;            // row stride of the transposed dpre tile (bank spread, keeps float4 alignment)
 
 struct E2Args {
@@ -81,6 +86,7 @@ __device__ __forceinline__ void conv_stage(const float* __restrict__ w_prev, lon
 }
 
 __global__ void __launch_bounds__(128) attn2_energy_kernel(E2Args p) {
+  t2v_pdl_trigger();
   __shared__ float win[2 * WIN];
   __shared__ float wcT[2 * KS * NF];
   __shared__ float f[TC * (NF + 1)];
@@ -97,12 +103,13 @@ __global__ void __launch_bounds__(128) attn2_energy_kernel(E2Args p) {
     const float4 t = *reinterpret_cast<const float4*>(p.w_loc + d * NF + c);
     wl[c] = t.x; wl[c + 1] = t.y; wl[c + 2] = t.z; wl[c + 3] = t.w;
   }
+  const float vd = p.v[d];
+  t2v_pdl_wait();                                   // everything above is weights only
   float pmv[TC];
 #pragma unroll
   for (int tt = 0; tt < TC; ++tt) pmv[tt] = (tt < nt) ? p.pmem[((long long)b * Ti + t0 + tt) * AD + d] : 0.f;
   float q = 0.f;
   for (int s = 0; s < p.n_qparts; ++s) q += p.qparts[s * p.qpart_stride + (long long)b * AD + d];
-  const float vd = p.v[d];
   conv_stage(p.w_prev, p.wprev_rs, p.cum_in, p.w_conv, b, t0, Ti, win, wcT, f);
 #pragma unroll
   for (int tt = 0; tt < TC; ++tt) {
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(128) attn2_energy_kernel(E2Args p) {
       }
       s = (s + s1) + (s2 + s3);
       const float a = t2v_tanh(s);
-      if (p.a_save) p.a_save[row * AD + d] = a;
+      if (p.a_save) __stcs(p.a_save + row * AD + d, a);
       const float part = warp_sum(vd * a);
       if (lane == 0) red[warp][tt] = part;
     }
@@ -140,6 +147,8 @@ struct C2Args {
   int B, Ti, rnd;
 };
 __global__ void __launch_bounds__(128) attn2_context_kernel(C2Args p) {
+  t2v_pdl_trigger();
+  t2v_pdl_wait();
   extern __shared__ __align__(16) float sm2[];
   float* w = sm2;                 // [Ti]
   float* part = w + ((p.Ti + 3) & ~3);   // [4][128] (16-byte aligned)
@@ -216,6 +225,7 @@ __global__ void __launch_bounds__(128) attn2_fused_kernel(F2Args p) {
   __shared__ __align__(16) float wfull[8 * TC];
   __shared__ __align__(16) float part[4 * 128];
   __shared__ float red2[32];
+  t2v_pdl_trigger();
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, Ti = p.e.Ti;
@@ -230,12 +240,13 @@ __global__ void __launch_bounds__(128) attn2_fused_kernel(F2Args p) {
       const float4 t = *reinterpret_cast<const float4*>(q.w_loc + d * NF + c);
       wl[c] = t.x; wl[c + 1] = t.y; wl[c + 2] = t.z; wl[c + 3] = t.w;
     }
+    const float vd = q.v[d];
+    t2v_pdl_wait();                                 // everything above is weights only
     float pmv[TC];
 #pragma unroll
     for (int tt = 0; tt < TC; ++tt) pmv[tt] = (tt < nt) ? q.pmem[((long long)b * Ti + t0 + tt) * AD + d] : 0.f;
     float qv = 0.f;
     for (int s = 0; s < q.n_qparts; ++s) qv += q.qparts[s * q.qpart_stride + (long long)b * AD + d];
-    const float vd = q.v[d];
     conv_stage(q.w_prev, q.wprev_rs, q.cum_in, q.w_conv, b, t0, Ti, win, wcT, f);
 #pragma unroll
     for (int tt = 0; tt < TC; ++tt) {
@@ -251,7 +262,7 @@ __global__ void __launch_bounds__(128) attn2_fused_kernel(F2Args p) {
         }
         s = (s + s1) + (s2 + s3);
         const float a = t2v_tanh(s);
-        if (q.a_save) q.a_save[row * AD + d] = a;
+        if (q.a_save) __stcs(q.a_save + row * AD + d, a);
         const float pr = warp_sum(vd * a);
         if (lane == 0) red[warp][tt] = pr;
       }
@@ -343,6 +354,8 @@ struct B1Args {
   int B, Ti;
 };
 __global__ void __launch_bounds__(128) attn2_bwd_ctx_kernel(B1Args p) {
+  t2v_pdl_trigger();
+  t2v_pdl_wait();
   __shared__ __align__(16) float dsh[128];
   const int b = blockIdx.y, ch = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, Ti = p.Ti;
   const int col = ch * 128 + tid;
@@ -400,6 +413,8 @@ struct B2Args {
   int B, Ti;
 };
 __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
+  t2v_pdl_trigger();
+  t2v_pdl_wait();
   extern __shared__ __align__(16) float sm3[];
   const int Ti = p.Ti;
   float* dwv = sm3;                         // [Ti] dw then scratch
@@ -417,7 +432,7 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
   const int nt = min(TC, Ti - t0);
   float av[TC];                              // saved tanh activations of this chunk (thread = attention dim)
 #pragma unroll
-  for (int tt = 0; tt < TC; ++tt) av[tt] = (tt < nt) ? p.a_save[((long long)b * Ti + t0 + tt) * AD + tid] : 0.f;
+  for (int tt = 0; tt < TC; ++tt) av[tt] = (tt < nt) ? __ldcs(p.a_save + ((long long)b * Ti + t0 + tt) * AD + tid) : 0.f;
   // (1) dw over the whole row, s = <w, dw>, de for this chunk
   float part = 0.f;
   for (int i = tid; i < Ti; i += 128) {
@@ -483,9 +498,12 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
     for (int dd = 0; dd < AD; ++dd) {
       const float w = wlT[dd * (NF + 1) + c];
       const float4 x0 = *reinterpret_cast<const float4*>(dpT + dd * DPS + g * TPB);
-      const float4 x1 = *reinterpret_cast<const float4*>(dpT + dd * DPS + g * TPB + 4);
       acc[0] = fmaf(w, x0.x, acc[0]); acc[1] = fmaf(w, x0.y, acc[1]); acc[2] = fmaf(w, x0.z, acc[2]); acc[3] = fmaf(w, x0.w, acc[3]);
-      acc[4] = fmaf(w, x1.x, acc[4]); acc[5] = fmaf(w, x1.y, acc[5]); acc[6] = fmaf(w, x1.z, acc[6]); acc[7] = fmaf(w, x1.w, acc[7]);
+      if (TPB == 8) {
+        const float4 x1 = *reinterpret_cast<const float4*>(dpT + dd * DPS + g * TPB + 4);
+        acc[TPB - 4] = fmaf(w, x1.x, acc[TPB - 4]); acc[TPB - 3] = fmaf(w, x1.y, acc[TPB - 3]);
+        acc[TPB - 2] = fmaf(w, x1.z, acc[TPB - 2]); acc[TPB - 1] = fmaf(w, x1.w, acc[TPB - 1]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < TPB; ++j) df[(g * TPB + j) * (NF + 1) + c] = acc[j];
@@ -558,37 +576,29 @@ T2V_API int t2v_attn2_fwd(const float* qparts, int n_qparts, long long qpart_str
   e.qparts = qparts; e.n_qparts = n_qparts; e.qpart_stride = qpart_stride; e.w_prev = w_prev; e.wprev_rs = wprev_rs;
   e.cum_in = cum_in; e.pmem = pmem; e.w_conv = w_conv; e.w_loc = w_loc; e.v = v; e.lens = lens; e.mask_value = mask_value;
   e.e_out = e_buf; e.a_save = a_save; e.B = B; e.Ti = Ti;
-  if (Ti <= 8 * TC) {          // one cluster of 4 or 8 CTAs per utterance
+  // the single-launch cluster variant measured slower than the two-kernel path on the C3 shape (28 vs 17 us): opt-in
+  static const bool use_cluster = getenv("T2V_ATTN_CLUSTER") && getenv("T2V_ATTN_CLUSTER")[0] == '1';
+  if (Ti <= 8 * TC && use_cluster) {          // one cluster of 4 or 8 CTAs per utterance
     const int CS = (Ti <= 4 * TC) ? 4 : 8;
     F2Args fa;
     fa.e = e; fa.cum_in = cum_in; fa.cum_out = cum_out; fa.mem = mem; fa.w_out = w_out; fa.wout_rs = wout_rs;
     fa.ctx_out1 = ctx_out1; fa.ctx1_rs = ctx1_rs; fa.ctx_out2 = ctx_out2; fa.ctx2_rs = ctx2_rs; fa.rnd = rnd;
     fa.tcx = (Ti + CS - 1) / CS;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(CS, B, 1);
-    cfg.blockDim = dim3(128, 1, 1);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn2_fused_kernel, fa));
+    T2V_CUDA_CHECK(t2v_launch(attn2_fused_kernel, dim3(CS, B, 1), dim3(128), 0, st, true, CS, fa));
     T2V_COUNT_LAUNCH();
     return 0;
   }
   dim3 g1((Ti + TC - 1) / TC, B);
-  attn2_energy_kernel<<<g1, 128, 0, st>>>(e);
+  T2V_CUDA_CHECK(t2v_launch(attn2_energy_kernel, g1, dim3(128), 0, st, true, 1, e));
   T2V_COUNT_LAUNCH();
-  T2V_LAUNCH_CHECK();
   C2Args c;
   c.e = e_buf; c.cum_in = cum_in; c.cum_out = cum_out; c.mem = mem; c.w_out = w_out; c.wout_rs = wout_rs;
   c.ctx_out1 = ctx_out1; c.ctx1_rs = ctx1_rs; c.ctx_out2 = ctx_out2; c.ctx2_rs = ctx2_rs; c.B = B; c.Ti = Ti; c.rnd = rnd;
   dim3 g2(NCH, B);
   const size_t smem = sizeof(float) * (size_t)(((Ti + 3) & ~3) + 4 * 128 + 32);
-  attn2_context_kernel<<<g2, 128, smem, st>>>(c);
-  LAUNCH_END();
+  T2V_CUDA_CHECK(t2v_launch(attn2_context_kernel, g2, dim3(128), smem, st, true, 1, c));
+  T2V_COUNT_LAUNCH();
+  return 0;
 }
 
 T2V_API int t2v_attn2_bwd(const float* dctx1, long long dctx1_rs, const float* dctx2, long long dctx2_rs, const float* dctx3,
@@ -602,9 +612,8 @@ T2V_API int t2v_attn2_bwd(const float* dctx1, long long dctx1_rs, const float* d
   a.dctx1 = dctx1; a.dctx1_rs = dctx1_rs; a.dctx2 = dctx2; a.dctx2_rs = dctx2_rs; a.dctx3 = dctx3; a.dctx3_rs = dctx3_rs;
   a.dctx_out = dctx_out; a.mem = mem; a.lens = lens; a.dw_part = dw_part; a.dw_next_zero = dw_out; a.gcum_prev = gcum_prev;
   a.gcum_next = gcum_next; a.B = B; a.Ti = Ti;
-  attn2_bwd_ctx_kernel<<<dim3(NCH, B), 128, 0, st>>>(a);
+  T2V_CUDA_CHECK(t2v_launch(attn2_bwd_ctx_kernel, dim3(NCH, B), dim3(128), 0, st, true, 1, a));
   T2V_COUNT_LAUNCH();
-  T2V_LAUNCH_CHECK();
   B2Args e;
   e.dw_part = dw_part; e.dw_in = dw_in; e.gcum_prev = gcum_prev; e.gcum_next = gcum_next; e.dw_out = dw_out; e.w = w;
   e.w_rs = w_rs; e.w_prev = w_prev; e.wprev_rs = wprev_rs; e.cum_in = cum_in; e.a_save = a_save; e.w_conv = w_conv;
@@ -616,6 +625,7 @@ T2V_API int t2v_attn2_bwd(const float* dctx1, long long dctx1_rs, const float* d
     T2V_CUDA_CHECK(cudaFuncSetAttribute(attn2_bwd_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cur = smem;
   }
-  attn2_bwd_energy_kernel<<<dim3((Ti + TC - 1) / TC, B), 128, smem, st>>>(e);
-  LAUNCH_END();
+  T2V_CUDA_CHECK(t2v_launch(attn2_bwd_energy_kernel, dim3((Ti + TC - 1) / TC, B), dim3(128), smem, st, true, 1, e));
+  T2V_COUNT_LAUNCH();
+  return 0;
 }

@@ -37,8 +37,13 @@ int setup_gemm(StepGemm* g, bool tc, const float* A, long long lda, long long a_
     while (splits > 1 && total % splits) --splits;
     g->splits = splits;
     // inner extents are the true K so that TMA zero-fills the tail chunk on both operands
-    return t2v_gemm_tc_plan(&g->plan, A, lda, a_rows, (long long)a_k0 + K, W, ldw, N, K, ldd, M, N, K, 1, 0, 0, a_k0, 0, 4,
-                            splits, g->split_stride, 0, 1.f, 128);
+    int r = t2v_gemm_tc_plan(&g->plan, A, lda, a_rows, (long long)a_k0 + K, W, ldw, N, K, ldd, M, N, K, 1, 0, 0, a_k0, 0, 4,
+                             splits, g->split_stride, 0, 1.f, 128);
+    static const bool hint = !(getenv("T2V_L2_HINT") && getenv("T2V_L2_HINT")[0] == '0');
+    g->plan.p.b_evict_last = hint ? 1 : 0;     // step weights are re-read 800 times: keep them in L2
+    g->plan.p.b_independent = 1;               // weights: prefetch before the dependency wait
+    g->plan.p.pdl = 1;
+    return r;
   }
   g->splits = 1;
   return 0;

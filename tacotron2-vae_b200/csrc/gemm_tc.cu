@@ -62,6 +62,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// same with an L2 eviction-priority hint (weights that are re-read every decoder step: evict-last)
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -128,6 +136,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int it0 = blockIdx.z * p.iters_per_split;
   const int n_it = p.iters_per_split;
+  t2v_pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -150,17 +159,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < n_it; ++it) {
+      auto load_b = [&](int it) {
         const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
         const int g = it0 + it;
         const int tap = g / p.chunks_per_tap;
         const int chunk = g - tap * p.chunks_per_tap;
         uint8_t* sa = smem + s * STAGE_BYTES;
-        tma_load_2d(sa, &tmA, p.a_k0 + chunk * BK, p.a_row0 + m0 + tap * p.a_tap_rowshift, &full[s]);
-        tma_load_2d(sa + A_BYTES, &tmB, p.b_k0 + tap * p.b_tap_stride + chunk * BK, p.b_row0 + n0, &full[s]);
+        if (p.b_evict_last)
+          tma_load_2d_hint(sa + A_BYTES, &tmB, p.b_k0 + tap * p.b_tap_stride + chunk * BK, p.b_row0 + n0, &full[s],
+                           0x14F0000000000000ull);           // L2 evict_last
+        else
+          tma_load_2d(sa + A_BYTES, &tmB, p.b_k0 + tap * p.b_tap_stride + chunk * BK, p.b_row0 + n0, &full[s]);
+      };
+      auto load_a = [&](int it) {
+        const int s = it % STAGES;
+        const int g = it0 + it;
+        const int tap = g / p.chunks_per_tap;
+        const int chunk = g - tap * p.chunks_per_tap;
+        tma_load_2d(smem + s * STAGE_BYTES, &tmA, p.a_k0 + chunk * BK, p.a_row0 + m0 + tap * p.a_tap_rowshift, &full[s]);
+      };
+      // the B operand (weights) never depends on the previous kernel: with PDL its first ring-full of tiles streams in
+      // while the prerequisite grid is still finishing; the A operand (activations) is loaded after the dependency wait
+      const int pre = p.b_independent ? min(n_it, STAGES) : 0;
+      for (int it = 0; it < pre; ++it) {
+        mbar_expect_tx(&full[it % STAGES], STAGE_BYTES);
+        load_b(it);
+      }
+      t2v_pdl_wait();
+      for (int it = 0; it < pre; ++it) load_a(it);
+      for (int it = pre; it < n_it; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        load_a(it);
+        load_b(it);
       }
     }
   } else if (warp == 1) {
@@ -188,6 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // epilogue warps 2..5: warp w may touch TMEM lanes 32*(w%4) .. +31
+    t2v_pdl_wait();
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int q = warp & 3;
@@ -251,9 +285,8 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcP
     attr_set = true;
   }
   dim3 grid(t2v_ceil_div(p.M, BM), t2v_ceil_div(p.N, BN), splits);
-  gemm_tc_kernel<BN, ESIZE, STAGES, BM><<<grid, 192, smem, st>>>(tmA, tmB, p);
+  T2V_CUDA_CHECK(t2v_launch(gemm_tc_kernel<BN, ESIZE, STAGES, BM>, grid, dim3(192), (size_t)smem, st, p.pdl != 0, 1, tmA, tmB, p));
   T2V_COUNT_LAUNCH();
-  T2V_LAUNCH_CHECK();
   return 0;
 }
 
@@ -308,7 +341,7 @@ int t2v_gemm_tc_plan(T2VGemmTcPlan* plan, const void* A, long long lda, long lon
   p.D = nullptr; p.ldd = ldd; p.split_stride = split_stride; p.bias = nullptr; p.M = M; p.N = N;
   p.iters_per_split = total / splits; p.chunks_per_tap = cpt; p.a_tap_rowshift = a_tap_rowshift;
   p.b_tap_stride = b_tap_stride; p.epi_atomic = epi_atomic; p.alpha = alpha;
-  p.a_row0 = 0; p.b_row0 = 0; p.a_k0 = a_k0; p.b_k0 = b_k0;
+  p.a_row0 = 0; p.b_row0 = 0; p.a_k0 = a_k0; p.b_k0 = b_k0; p.b_evict_last = 0; p.b_independent = 0; p.pdl = 0;
   plan->BN = BN; plan->esize = esize; plan->splits = splits;
   return 0;
 }

@@ -17,6 +17,9 @@ struct GemmTcParams {
   int epi_atomic;
   float alpha;
   int a_row0, b_row0, a_k0, b_k0;
+  int b_independent;     // B does not depend on the preceding kernel: prefetch it before the PDL dependency wait
+  int pdl;               // launch with programmatic stream serialization
+  int b_evict_last;      // load the B operand (weights re-read every time step) with the L2 evict_last policy
 };
 struct T2VGemmTcPlan {
   CUtensorMap tmA, tmB;

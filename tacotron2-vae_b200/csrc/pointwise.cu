@@ -277,6 +277,8 @@ __global__ void sum_rows_per_batch_kernel(const float* __restrict__ x, float* __
 // sums `n_parts` partial buffers (stride part_stride) into dst (+ optional second/third plain sources)
 __global__ void sum_parts_kernel(const float* __restrict__ parts, int n_parts, long long part_stride,
                                  float* __restrict__ dst, long long n) {
+  t2v_pdl_trigger();
+  t2v_pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float a = 0.f;
@@ -325,6 +327,8 @@ struct LstmFwdArgs {
   int rnd;                                // round h to tf32 on store (it is a tensor-core GEMM operand)
 };
 __global__ void lstm_pointwise_fwd_kernel(LstmFwdArgs a) {
+  t2v_pdl_trigger();
+  t2v_pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.B * a.H) return;
   const int b = i / a.H, j = i % a.H;
@@ -362,13 +366,14 @@ __global__ void lstm_pointwise_fwd_kernel(LstmFwdArgs a) {
   if (a.seq_out) a.seq_out[b * a.seq_rs + j] = hd;
   if (a.gates_save) {
     float* gs = a.gates_save + (long long)b * 4 * a.H + j;
-    gs[0] = ig; gs[a.H] = fg; gs[2 * a.H] = gg; gs[3 * a.H] = og;
+    __stcs(gs, ig); __stcs(gs + a.H, fg); __stcs(gs + 2 * a.H, gg); __stcs(gs + 3 * a.H, og);
   }
-  if (a.cpre_save) a.cpre_save[(long long)b * a.H + j] = c2;
+  if (a.cpre_save) __stcs(a.cpre_save + (long long)b * a.H + j, c2);
 }
 
 struct LstmBwdArgs {
   const float* dh1; long long dh1_rs;     // grads wrt post-dropout h (up to 3 sources, nullable)
+  int dh1_parts; long long dh1_pstride;   // dh1 may be a sum of split-K partial buffers
   const float* dh2; long long dh2_rs;
   const float* dh3; long long dh3_rs;
   float* dc;                              // [B,H] in: grad wrt post-dropout c ; out: grad wrt c_prev (in place)
@@ -381,6 +386,8 @@ struct LstmBwdArgs {
   int rnd;
 };
 __global__ void lstm_pointwise_bwd_kernel(LstmBwdArgs a) {
+  t2v_pdl_trigger();
+  t2v_pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.B * a.H) return;
   const int b = i / a.H, j = i % a.H;
@@ -391,7 +398,9 @@ __global__ void lstm_pointwise_bwd_kernel(LstmBwdArgs a) {
     return;      // dc (state gradient) passes through unchanged
   }
   float dh = 0.f;
-  if (a.dh1) dh += a.dh1[b * a.dh1_rs + j];
+  if (a.dh1) {
+    for (int pp = 0; pp < a.dh1_parts; ++pp) dh += a.dh1[pp * a.dh1_pstride + b * a.dh1_rs + j];
+  }
   if (a.dh2) dh += a.dh2[b * a.dh2_rs + j];
   if (a.dh3) dh += a.dh3[b * a.dh3_rs + j];
   const uint64_t idx = a.drop_base + (uint64_t)b * a.H + j;
@@ -590,8 +599,9 @@ T2V_API int t2v_sum_rows_per_batch(const float* x, float* out, int B, int rows_p
   LAUNCH_END();
 }
 T2V_API int t2v_sum_parts(const float* parts, int n_parts, long long part_stride, float* dst, long long n, cudaStream_t st) {
-  sum_parts_kernel<<<grid1d(n, 256), 256, 0, st>>>(parts, n_parts, part_stride, dst, n);
-  LAUNCH_END();
+  T2V_CUDA_CHECK(t2v_launch(sum_parts_kernel, dim3(grid1d(n, 256)), dim3(256), 0, st, true, 1, parts, n_parts, part_stride, dst, n));
+  T2V_COUNT_LAUNCH();
+  return 0;
 }
 T2V_API int t2v_relu_drop_fwd(const float* x, float* out, long long o_rs, long long rows, int C, const float* mask,
                               unsigned long long seed, unsigned int site, float p, unsigned long long idx_base,
@@ -628,8 +638,27 @@ T2V_API int t2v_lstm_pointwise_fwd(const float* parts, int n_parts, long long pa
   a.gates_save = gates_save; a.cpre_save = cpre_save; a.seq_out = seq_out; a.seq_rs = seq_rs;
   a.drop_h = mk_drop(mask_h, seed, site_h, p); a.drop_c = mk_drop(mask_c, seed, site_c, p); a.drop_base = drop_base;
   a.lens = lens; a.t = t; a.B = B; a.H = H;
-  lstm_pointwise_fwd_kernel<<<grid1d((long long)B * H, 256), 256, 0, st>>>(a);
-  LAUNCH_END();
+  T2V_CUDA_CHECK(t2v_launch(lstm_pointwise_fwd_kernel, dim3(grid1d((long long)B * H, 256)), dim3(256), 0, st, true, 1, a));
+  T2V_COUNT_LAUNCH();
+  return 0;
+}
+T2V_API int t2v_lstm_pointwise_bwd_parts(const float* dh1, long long dh1_rs, int dh1_parts, long long dh1_pstride,
+                                         const float* dh2, long long dh2_rs, const float* dh3, long long dh3_rs, float* dc,
+                                         const float* gates_save, const float* cpre_save, const float* c_prev,
+                                         long long cprev_rs, float* dgates, long long dg_rs, const float* mask_h,
+                                         const float* mask_c, unsigned long long seed, unsigned int site_h,
+                                         unsigned int site_c, float p, unsigned long long drop_base, const long long* lens,
+                                         int t, int B, int H, int rnd, cudaStream_t st) {
+  LstmBwdArgs a;
+  a.rnd = rnd;
+  a.dh1 = dh1; a.dh1_rs = dh1_rs; a.dh1_parts = dh1_parts; a.dh1_pstride = dh1_pstride; a.dh2 = dh2; a.dh2_rs = dh2_rs;
+  a.dh3 = dh3; a.dh3_rs = dh3_rs; a.dc = dc;
+  a.gates_save = gates_save; a.cpre_save = cpre_save; a.c_prev = c_prev; a.cprev_rs = cprev_rs; a.dgates = dgates;
+  a.dg_rs = dg_rs; a.drop_h = mk_drop(mask_h, seed, site_h, p); a.drop_c = mk_drop(mask_c, seed, site_c, p);
+  a.drop_base = drop_base; a.lens = lens; a.t = t; a.B = B; a.H = H;
+  T2V_CUDA_CHECK(t2v_launch(lstm_pointwise_bwd_kernel, dim3(grid1d((long long)B * H, 256)), dim3(256), 0, st, true, 1, a));
+  T2V_COUNT_LAUNCH();
+  return 0;
 }
 T2V_API int t2v_lstm_pointwise_bwd(const float* dh1, long long dh1_rs, const float* dh2, long long dh2_rs,
                                    const float* dh3, long long dh3_rs, float* dc, const float* gates_save,
@@ -639,12 +668,13 @@ T2V_API int t2v_lstm_pointwise_bwd(const float* dh1, long long dh1_rs, const flo
                                    const long long* lens, int t, int B, int H, int rnd, cudaStream_t st) {
   LstmBwdArgs a;
   a.rnd = rnd;
-  a.dh1 = dh1; a.dh1_rs = dh1_rs; a.dh2 = dh2; a.dh2_rs = dh2_rs; a.dh3 = dh3; a.dh3_rs = dh3_rs; a.dc = dc;
+  a.dh1 = dh1; a.dh1_rs = dh1_rs; a.dh1_parts = 1; a.dh1_pstride = 0; a.dh2 = dh2; a.dh2_rs = dh2_rs; a.dh3 = dh3; a.dh3_rs = dh3_rs; a.dc = dc;
   a.gates_save = gates_save; a.cpre_save = cpre_save; a.c_prev = c_prev; a.cprev_rs = cprev_rs; a.dgates = dgates;
   a.dg_rs = dg_rs; a.drop_h = mk_drop(mask_h, seed, site_h, p); a.drop_c = mk_drop(mask_c, seed, site_c, p);
   a.drop_base = drop_base; a.lens = lens; a.t = t; a.B = B; a.H = H;
-  lstm_pointwise_bwd_kernel<<<grid1d((long long)B * H, 256), 256, 0, st>>>(a);
-  LAUNCH_END();
+  T2V_CUDA_CHECK(t2v_launch(lstm_pointwise_bwd_kernel, dim3(grid1d((long long)B * H, 256)), dim3(256), 0, st, true, 1, a));
+  T2V_COUNT_LAUNCH();
+  return 0;
 }
 T2V_API int t2v_gru_pointwise_fwd(const float* gi, long long gi_rs, const float* gh, const float* b_ih, const float* b_hh,
                                   const float* h_prev, float* h_out, float* save, int B, int H, cudaStream_t st) {

@@ -9,7 +9,7 @@
 
 namespace {
 
-constexpr int UPC = 4;          // hidden units (= warps) per CTA
+constexpr int UPC = 8;          // hidden units (= warps) per CTA
 constexpr int MT = 64;          // batch rows per tile
 constexpr int MS = MT + 1;      // (unused) transposed-tile stride
 
@@ -43,17 +43,17 @@ __global__ void __launch_bounds__(UPC * 32) bilstm_step_fwd_kernel(BiFwdArgs p) 
     __syncthreads();
     {   // stage the h_prev tile: float4 global loads, 8 in flight per thread
       const int nv = MT * H / 4;
-      for (int i0 = threadIdx.x; i0 < nv; i0 += UPC * 32 * 8) {
-        float4 v[8];
+      for (int i0 = threadIdx.x; i0 < nv; i0 += UPC * 32 * 16) {
+        float4 v[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const int i = i0 + j * UPC * 32;
           const int m = (i * 4) / H, k = (i * 4) % H;
           v[j] = (i < nv && m0 + m < p.B) ? *reinterpret_cast<const float4*>(p.h_prev[dir] + (long long)(m0 + m) * H + k)
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const int i = i0 + j * UPC * 32;
           if (i < nv) {
             const int m = (i * 4) / H, k = (i * 4) % H;
@@ -137,17 +137,17 @@ __global__ void __launch_bounds__(UPC * 32) bilstm_step_bwd_kernel(BiBwdArgs p) 
         __syncthreads();
         {
           const int nv = MT * KC / 4;
-          for (int i0 = threadIdx.x; i0 < nv; i0 += UPC * 32 * 8) {
-            float4 v[8];
+          for (int i0 = threadIdx.x; i0 < nv; i0 += UPC * 32 * 16) {
+            float4 v[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 16; ++j) {
               const int i = i0 + j * UPC * 32;
               const int m = (i * 4) / KC, k = (i * 4) % KC;
               v[j] = (i < nv && m0 + m < p.B) ? *reinterpret_cast<const float4*>(p.dg_next[dir] + (m0 + m) * p.dg_bs + k0 + k)
                                               : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 16; ++j) {
               const int i = i0 + j * UPC * 32;
               if (i < nv) {
                 const int m = (i * 4) / KC, k = (i * 4) % KC;

@@ -38,6 +38,35 @@ void t2v_set_error(const char* fmt, ...);
 extern unsigned long long g_t2v_launches;
 #define T2V_COUNT_LAUNCH() (++g_t2v_launches)
 
+// Programmatic dependent launch (PDL): kernels of the decoder time loop are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so that a kernel's launch + prologue (barrier init, TMEM allocation,
+// weight staging -- nothing that depends on the previous kernel) overlaps the previous kernel's tail.  t2v_pdl_wait()
+// blocks until every prerequisite grid has completed and flushed; it is a no-op for ordinary launches.
+__device__ __forceinline__ void t2v_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void t2v_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool t2v_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t t2v_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              int cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl && t2v_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static inline int t2v_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- counter-based dropout RNG: keep(seed, site, idx) is a pure function, so forward, backward and
