@@ -249,6 +249,7 @@ def main():
     # roofline of the dominant kernel group: one teacher-forced decoder step (GEMM_a, cell, q-GEMM, fused attention,
     # GEMM_d, cell), timed with CUDA events over a fresh forward's time loop
     roof = decoder_step_roofline(m, hp, B, Ti, To, dev, a.precision)
+    infer_step = inference_decoder_step(m, dev, a.precision) if rank == 0 else None
 
     _progress("roofline done")
     cpu = None
@@ -270,9 +271,45 @@ def main():
                        "l2": "per-step working set (>3 GB of saved activations) exceeds the 126 MB L2"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary()}))
+            "gpu_launches": launches, "roofline": roof, "decoder_step_inference": infer_step, "cpu_baseline": cpu,
+            "clocks": sampler.summary()}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def inference_decoder_step(m, dev, precision, B=16, Ti=120, n=1000):
+    """Config 5: batch-16 free-running autoregressive decode for `n` steps (prenet -> decode -> mel/gate projection ->
+    feedback, per-row stop bookkeeping on the device), replayed as one CUDA graph.  Returns mean us per decoder step."""
+    from t2v import engine, infer
+    with torch.no_grad():
+        ops = engine.Ops(precision)
+        P = m._state()
+        mem = torch.randn(B, Ti, 512, device=dev)
+
+        def run():
+            sess = infer.DecoderSession(ops, P, mem, None, n, training=False, seed=7)
+            sess.run_free(n, 0.5, seed=7)
+            return sess
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            keep = run()
+        times = []
+        for _ in range(4):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        mel, gate, align = keep.outputs(n)
+        ok = bool(torch.isfinite(mel).all())
+    return {"value": min(times[1:]) * 1e3 / n, "unit": "us/step", "batch": B, "text_len": Ti, "steps": n, "finite": ok,
+            "what": "free-running Decoder.inference step incl. prenet, attention, both LSTM cells, mel/gate projection"}
 
 
 def decoder_step_roofline(m, hp, B, Ti, To, dev, precision):
@@ -312,7 +349,8 @@ def decoder_step_roofline(m, hp, B, Ti, To, dev, precision):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (us * 1e-6) / 1e9
     return {"kernel": "decoder step = gemm_tc<128,4,8,64> x3 (attention_rnn gates, query, decoder_rnn gates) + "
-                      "lstm_pointwise_fwd x2 + attn2_fused (6 launches, CUDA-graph replay of Decoder.decode for all To steps)",
+                      "lstm_pointwise_fwd x2 + attn2_energy + attn2_context (7 launches, CUDA-graph replay of Decoder.decode "
+                      "for all To steps)",
             "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "us_per_step": us, "algorithmic_bytes_per_step": alg_bytes,
