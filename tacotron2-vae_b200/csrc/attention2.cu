@@ -342,6 +342,172 @@ __global__ void __launch_bounds__(128) attn2_fused_kernel(F2Args p) {
   }
 }
 
+// ---- fused forward, one CTA per utterance (the north-star "attention energy + softmax + context reduction in one
+// kernel"): 512 threads = 4 groups of 128; group g runs the chunk pipeline above on text chunk g (g+4, ... for long
+// texts) concurrently, the energies meet in shared memory, all 16 warps do the softmax and the context reduction
+// (warp -> text positions, lane -> 16 channels as 4 float4, 16 rows in flight per warp).
+struct R3Args {
+  E2Args e;
+  const float* cum_in; float* cum_out; const float* mem;
+  float* w_out; long long wout_rs;
+  float* ctx_out1; long long ctx1_rs; float* ctx_out2; long long ctx2_rs;
+  int rnd;
+};
+__global__ void __launch_bounds__(512) attn3_row_kernel(R3Args p) {
+  extern __shared__ __align__(16) float sm4[];
+  t2v_pdl_trigger();
+  const E2Args& q = p.e;
+  const int Ti = q.Ti, Tia = (Ti + 3) & ~3;
+  float* wcT = sm4;                              // [2*KS][NF]
+  float* winA = wcT + 2 * KS * NF;               // [4][2*WIN]
+  float* fA = winA + 4 * 2 * WIN;                // [4][TC*(NF+1)]
+  float* redA = fA + 4 * TC * (NF + 1);          // [4][4][TC]
+  float* ew = redA + 4 * 4 * TC;                 // [Tia] energies -> weights
+  float* part = ew + Tia;                        // [16][512]
+  float* red2 = part + 16 * 512;                 // [32]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = tid >> 7, gt = tid & 127, gwarp = warp & 3;
+  float* win = winA + grp * 2 * WIN;
+  float* f = fA + grp * TC * (NF + 1);
+  float* red = redA + grp * 4 * TC;
+  // ---- weights (independent of the previous kernel)
+  const int d = gt;
+  float wl[NF];
+#pragma unroll
+  for (int c = 0; c < NF; c += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(q.w_loc + d * NF + c);
+    wl[c] = t.x; wl[c + 1] = t.y; wl[c + 2] = t.z; wl[c + 3] = t.w;
+  }
+  const float vd = q.v[d];
+  {
+    constexpr int NL = (NF * 2 * KS + 511) / 512;
+    float tmp[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) { const int i = tid + 512 * j; tmp[j] = (i < NF * 2 * KS) ? q.w_conv[i] : 0.f; }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) { const int i = tid + 512 * j; if (i < NF * 2 * KS) wcT[i] = tmp[j]; }
+  }
+  t2v_pdl_wait();
+  float qv = 0.f;
+  for (int s = 0; s < q.n_qparts; ++s) qv += q.qparts[s * q.qpart_stride + (long long)b * AD + d];
+  const long long len = q.lens ? q.lens[b] : Ti;
+  const int nchunk = (Ti + TC - 1) / TC;
+  for (int pass = 0; pass * 4 < nchunk; ++pass) {
+    const int t0 = (pass * 4 + grp) * TC;
+    const int nt = max(0, min(TC, Ti - t0));
+    float pmv[TC];
+#pragma unroll
+    for (int tt = 0; tt < TC; ++tt) pmv[tt] = (tt < nt) ? q.pmem[((long long)b * Ti + t0 + tt) * AD + d] : 0.f;
+    for (int i = gt; i < 2 * WIN; i += 128) {
+      const int ch = i / WIN, j = i % WIN;
+      const int sidx = t0 - HALO + j;
+      float v = 0.f;
+      if (sidx >= 0 && sidx < Ti) v = (ch == 0) ? (q.w_prev ? q.w_prev[b * q.wprev_rs + sidx] : 0.f) : q.cum_in[(long long)b * Ti + sidx];
+      win[i] = v;
+    }
+    __syncthreads();
+    {
+      const int c = gt & 31, g = gt >> 5;
+      float acc[TPB];
+#pragma unroll
+      for (int j = 0; j < TPB; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        float xr[TPB + KS - 1];
+#pragma unroll
+        for (int j = 0; j < TPB + KS - 1; ++j) xr[j] = win[ch * WIN + g * TPB + j];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const float w = wcT[(ch * KS + k) * NF + c];
+#pragma unroll
+          for (int j = 0; j < TPB; ++j) acc[j] = fmaf(w, xr[j + k], acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < TPB; ++j) f[(g * TPB + j) * (NF + 1) + c] = acc[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tt = 0; tt < TC; ++tt) {
+      if (tt < nt) {
+        const long long row = (long long)b * Ti + t0 + tt;
+        float s = qv + pmv[tt], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        const float* fr = f + tt * (NF + 1);
+#pragma unroll
+        for (int c = 0; c < NF; c += 4) {
+          s = fmaf(fr[c], wl[c], s); s1 = fmaf(fr[c + 1], wl[c + 1], s1);
+          s2 = fmaf(fr[c + 2], wl[c + 2], s2); s3 = fmaf(fr[c + 3], wl[c + 3], s3);
+        }
+        s = (s + s1) + (s2 + s3);
+        const float a = t2v_tanh(s);
+        if (q.a_save) __stcs(q.a_save + row * AD + d, a);
+        const float pr = warp_sum(vd * a);
+        if (lane == 0) red[gwarp * TC + tt] = pr;
+      }
+    }
+    __syncthreads();
+    if (gt < nt) {
+      const float e = red[gt] + red[TC + gt] + red[2 * TC + gt] + red[3 * TC + gt];
+      ew[t0 + gt] = (t0 + gt < len) ? e : q.mask_value;
+    }
+  }
+  __syncthreads();
+  // ---- softmax over the text positions
+  float m = -INFINITY;
+  for (int i = tid; i < Ti; i += 512) m = fmaxf(m, ew[i]);
+  m = block_max(m, red2);
+  float ssum = 0.f;
+  for (int i = tid; i < Ti; i += 512) {
+    const float x = expf(ew[i] - m);
+    ew[i] = x;
+    ssum += x;
+  }
+  ssum = block_sum(ssum, red2);
+  const float inv = 1.f / ssum;
+  __syncthreads();
+  for (int i = tid; i < Ti; i += 512) {
+    const float x = ew[i] * inv;
+    ew[i] = x;
+    p.w_out[b * p.wout_rs + i] = x;
+    p.cum_out[(long long)b * Ti + i] = p.cum_in[(long long)b * Ti + i] + x;
+  }
+  __syncthreads();
+  // ---- context: warp -> ti = warp, warp+16, ... ; lane -> channels lane*4 + 128*j
+  float4 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* mbase = p.mem + (long long)b * Ti * ED + lane * 4;
+  for (int base = warp; base < Ti; base += 16 * 4) {
+    float4 mv[4][4];
+    float wi[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ti = base + 16 * r;
+      wi[r] = (ti < Ti) ? ew[ti] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        mv[r][j] = (wi[r] != 0.f) ? *reinterpret_cast<const float4*>(mbase + (long long)ti * ED + 128 * j)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j].x = fmaf(wi[r], mv[r][j].x, acc[j].x); acc[j].y = fmaf(wi[r], mv[r][j].y, acc[j].y);
+        acc[j].z = fmaf(wi[r], mv[r][j].z, acc[j].z); acc[j].w = fmaf(wi[r], mv[r][j].w, acc[j].w);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(part + warp * 512 + 128 * j + lane * 4) = acc[j];
+  __syncthreads();
+  float c = 0.f;
+#pragma unroll
+  for (int w = 0; w < 16; ++w) c += part[w * 512 + tid];
+  c = t2v_rnd(c, p.rnd);
+  if (p.ctx_out1) p.ctx_out1[b * p.ctx1_rs + tid] = c;
+  if (p.ctx_out2) p.ctx_out2[b * p.ctx2_rs + tid] = c;
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 struct B1Args {
   const float* dctx1; long long dctx1_rs; const float* dctx2; long long dctx2_rs; const float* dctx3; long long dctx3_rs;
@@ -576,8 +742,26 @@ T2V_API int t2v_attn2_fwd(const float* qparts, int n_qparts, long long qpart_str
   e.qparts = qparts; e.n_qparts = n_qparts; e.qpart_stride = qpart_stride; e.w_prev = w_prev; e.wprev_rs = wprev_rs;
   e.cum_in = cum_in; e.pmem = pmem; e.w_conv = w_conv; e.w_loc = w_loc; e.v = v; e.lens = lens; e.mask_value = mask_value;
   e.e_out = e_buf; e.a_save = a_save; e.B = B; e.Ti = Ti;
-  // the single-launch cluster variant measured slower than the two-kernel path on the C3 shape (28 vs 17 us): opt-in
-  static const bool use_cluster = getenv("T2V_ATTN_CLUSTER") && getenv("T2V_ATTN_CLUSTER")[0] == '1';
+  // modes: "row" (default) one CTA per utterance, everything in one launch; "split" energy + context kernels;
+  // "cluster" one 4/8-CTA cluster per utterance (measured slower than "split" on the C3 shape: 28 vs 17 us)
+  static const char* mode_env = getenv("T2V_ATTN_MODE");
+  static const int mode = (mode_env && mode_env[0] == 's') ? 1 : ((mode_env && mode_env[0] == 'c') ? 2 : 0);
+  const bool use_cluster = (mode == 2);
+  if (mode == 0) {
+    R3Args ra;
+    ra.e = e; ra.cum_in = cum_in; ra.cum_out = cum_out; ra.mem = mem; ra.w_out = w_out; ra.wout_rs = wout_rs;
+    ra.ctx_out1 = ctx_out1; ra.ctx1_rs = ctx1_rs; ra.ctx_out2 = ctx_out2; ra.ctx2_rs = ctx2_rs; ra.rnd = rnd;
+    const size_t smem = sizeof(float) * (size_t)(2 * KS * NF + 4 * 2 * WIN + 4 * TC * (NF + 1) + 4 * 4 * TC + ((Ti + 3) & ~3) +
+                                                 16 * 512 + 32);
+    static size_t cur = 48 * 1024;
+    if (smem > cur) {
+      T2V_CUDA_CHECK(cudaFuncSetAttribute(attn3_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cur = smem;
+    }
+    T2V_CUDA_CHECK(t2v_launch(attn3_row_kernel, dim3(B), dim3(512), smem, st, true, 1, ra));
+    T2V_COUNT_LAUNCH();
+    return 0;
+  }
   if (Ti <= 8 * TC && use_cluster) {          // one cluster of 4 or 8 CTAs per utterance
     const int CS = (Ti <= 4 * TC) ? 4 : 8;
     F2Args fa;

@@ -219,9 +219,11 @@ def test_graph_replay_equals_eager_and_dp_shards_add_up():
         outs[mode] = ([o.detach().clone() for o in out[:7]], {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
     for a, b in zip(outs["graph"][0], outs["eager"][0]):
         assert torch.equal(a, b)
+    total = float(torch.sqrt(sum(v.norm() ** 2 for v in outs["eager"][1].values())))
     for k, g in outs["graph"][1].items():
         ref = outs["eager"][1][k]
-        assert float((g - ref).norm()) <= 1e-3 * float(ref.norm()) + 1e-7, k      # atomics (embedding scatter, split-K, dq) add in any order
+        # atomics (embedding scatter, split-K, dq) add in any order; conv biases in front of a BN are pure rounding noise
+        assert float((g - ref).norm()) <= 1e-3 * float(ref.norm()) + 1e-5 * total, k
     mel, post, gate, align = outs["graph"][0][:4]
     for b in range(B):
         L_ = int(batch[4][b])
