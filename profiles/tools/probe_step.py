@@ -1,5 +1,5 @@
 import sys, time, os
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tacotron2-vae_b200')
+R=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tacotron2-vae_b200'))
 import torch
 import model as M
 from hparams import create_hparams

@@ -1,8 +1,8 @@
 """Scratch profiler: per-kernel device time of full-size train steps via torch.profiler (CUPTI activity records; real
 warm-cache durations, unlike ncu's serialised cold-cache replays).  usage: profile_step.py B Ti To precision [out.md]"""
 import os, sys, collections
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tacotron2-vae_b200"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tacotron2-vae_b200"))
 import torch
 from torch.profiler import profile, ProfilerActivity
 import model as M

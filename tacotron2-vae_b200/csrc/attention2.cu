@@ -689,8 +689,13 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
       if (i < NF * 2 * KS) {
         const int c = i % NF, chk = i / NF;                 // chk = ch*KS + k
         const float* x = win + (chk / KS) * WIN + (chk % KS);
-#pragma unroll 8
-        for (int tt = 0; tt < TC; ++tt) a = fmaf(df[tt * (NF + 1) + c], x[tt], a);
+        float b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll
+        for (int tt = 0; tt < TC; tt += 4) {
+          a = fmaf(df[tt * (NF + 1) + c], x[tt], a); b1 = fmaf(df[(tt + 1) * (NF + 1) + c], x[tt + 1], b1);
+          b2 = fmaf(df[(tt + 2) * (NF + 1) + c], x[tt + 2], b2); b3 = fmaf(df[(tt + 3) * (NF + 1) + c], x[tt + 3], b3);
+        }
+        a = (a + b1) + (b2 + b3);
       }
       acc[j] = a;
     }
@@ -700,18 +705,23 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
   // (6) adjoint conv, scattered: contribution of this chunk's df to dwcat[ch][t0-HALO+j], j in [0,WIN)
   for (int i = tid; i < 2 * WIN; i += 128) {
     const int ch = i / WIN, j = i % WIN;
-    float a = 0.f;
-    // s = t0 - HALO + j ; ti = s - k + HALO  =>  tt = j - k, 0 <= tt < TC   (k uniform across the warp: broadcast reads)
+    // s = t0 - HALO + j ; ti = s - k + HALO  =>  tt = j - k, 0 <= tt < TC   (k uniform across the warp: broadcast reads);
+    // four independent accumulators break the 992-long dependent FMA chain
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 1
     for (int k = 0; k < KS; ++k) {
       const int tt = j - k;
       if (tt >= 0 && tt < TC) {
         const float* dfr = df + tt * (NF + 1);
         const float* wk = wcT + (ch * KS + k) * NF;
-#pragma unroll 8
-        for (int c = 0; c < NF; ++c) a = fmaf(dfr[c], wk[c], a);
+#pragma unroll
+        for (int c = 0; c < NF; c += 4) {
+          a0 = fmaf(dfr[c], wk[c], a0); a1 = fmaf(dfr[c + 1], wk[c + 1], a1);
+          a2 = fmaf(dfr[c + 2], wk[c + 2], a2); a3 = fmaf(dfr[c + 3], wk[c + 3], a3);
+        }
       }
     }
+    const float a = (a0 + a1) + (a2 + a3);
     const int sidx = t0 - HALO + j;
     if (sidx >= 0 && sidx < Ti && a != 0.f) {
       if (ch == 0) atomicAdd(p.dw_out + (long long)b * Ti + sidx, a);

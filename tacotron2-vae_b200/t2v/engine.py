@@ -20,6 +20,7 @@ from . import _lib
 from ._lib import call as L
 
 F32 = torch.float32
+_BN256 = __import__("os").environ.get("T2V_BN256", "1") != "0"
 _TRACE = bool(int(__import__("os").environ.get("T2V_TRACE", "0")))
 _t_last = [None]
 
@@ -65,6 +66,11 @@ class Ops(object):
         self.tc = precision == "tf32"
         self.R = 1 if self.tc else 0       # producers round tensor-core operands to the tf32 grid on store
 
+    @staticmethod
+    def bn(M, N):
+        """N-tile of the tcgen05 GEMM: 256 for the large GEMMs (halves the activation-tile re-reads per FLOP)"""
+        return 256 if (N >= 512 and N % 256 == 0 and M >= 4096 and _BN256) else 128
+
     def wr(self, W):
         """weights consumed directly by a tensor-core GEMM: tf32-rounded copy (tcgen05 truncates otherwise)"""
         if not self.tc:
@@ -90,7 +96,7 @@ class Ops(object):
     def linear(self, x, lda, W, ldw, out, ldd, M, N, K, bias=None, accumulate=False, a_rows=None, force_exact=False):
         if self.tc and not force_exact and self._tc_ok((x, lda), (W, ldw)) and M >= 1:
             L("t2v_gemm_tc", x, lda, a_rows or M, K, W, ldw, N, K, out, ldd, bias, M, N, K, 1, 0, 0, 0, 0, 4, 1, 0,
-              1 if accumulate else 0, 1.0, 128)
+              1 if accumulate else 0, 1.0, self.bn(M, N))
         else:
             self.gemm(x, lda, 1, W, ldw, 1, out, ldd, M, N, K, 1.0, 1.0 if accumulate else 0.0, bias)
 
@@ -203,7 +209,7 @@ def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, se
         Y = _zeros(R, Co, device=dev)
         if ops.tc:
             L("t2v_gemm_tc", X, Ci, R, Ci, Wk, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co, P[pre + ".0.conv.bias"], M, Co, Ci, 5, 1,
-              Ci, 0, 0, 4, 1, 0, 0, 1.0, 128)
+              Ci, 0, 0, 4, 1, 0, 0, 1.0, ops.bn(M, Co))
         else:
             ops.gemm(X, Ci, 1, Wk, 5 * Ci, 1, _p(Y, 2 * Co), Co, M, Co, 5 * Ci, 1.0, 0.0, P[pre + ".0.conv.bias"])
         Xn = _empty(R, Co, device=dev)
@@ -252,7 +258,7 @@ def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0
             dX = _zeros(R, Ci, device=dev)
             if ops.tc:
                 L("t2v_gemm_tc", dY, Co, R, Co, Wd, 5 * Co, Ci, 5 * Co, _p(dX, 2 * Ci), Ci, None, M, Ci, Co, 5, 1, Co, 0, 0, 4,
-                  1, 0, 0, 1.0, 128)
+                  1, 0, 0, 1.0, ops.bn(M, Ci))
             else:
                 ops.gemm(dY, Co, 1, Wd, 5 * Co, 1, _p(dX, 2 * Ci), Ci, M, Ci, 5 * Co, 1.0, 0.0, None)
             dOut = dX
