@@ -196,7 +196,7 @@ typedef struct T2VDecoderSeq {
   float *align;                  /* [B,To,Ti] */
   float *GA, *GD, *CPA, *CPD;    /* saved gates [To,B,4096] / pre-dropout cells [To,B,1024]; NULL at inference */
   float *ASAVE;                  /* [To,B,Ti,128] tanh activations; NULL at inference */
-  float *parts, *qparts;         /* split-K workspaces: >= 8*B*4096 and 8*B*128 floats */
+  float *parts, *qparts;         /* split-K workspaces: >= 16*B*4096 (two halves, one per chain) and 8*B*128 floats */
   float *ebuf;                   /* [B,Ti] attention energies scratch */
 } T2VDecoderSeq;
 int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);
@@ -207,7 +207,7 @@ typedef struct T2VDecoderBwd {
   const float *DHC;              /* [To,B,1536] grad wrt [h_dec_t | ctx_t] from linear_projection/gate_layer */
   float *DGA, *DGD;              /* out: pre-activation gate grads [To,B,4096] */
   float *DXA;                    /* out: grad wrt XA rows [To,B,1792] */
-  float *DXD;                    /* ring [2,B,2560] */
+  float *DXD;                    /* [To,B,2560] grad wrt the XD rows (the decoder_rnn chain runs ahead of the attention chain) */
   float *dCa, *dCd;              /* [B,1024] running cell-state grads (zero-initialised by caller) */
   float *dwprev;                 /* ring [2,B,Ti] */
   float *gcum;                   /* ring [2,B,Ti] zero-initialised */

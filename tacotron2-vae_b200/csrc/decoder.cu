@@ -94,6 +94,37 @@ static StepProfiler g_prof;
 
 struct FwdPlans { StepGemm ga, gq, gd; };
 
+// The attention chain (attention_rnn gates -> cell -> query -> attention) is the only true recurrence of the decoder:
+// the decoder_rnn chain (gates -> cell) of step t consumes h_att_t / ctx_t but feeds nothing back into the attention
+// chain under teacher forcing (its output only reaches the deferred mel/gate projection), so it runs on a second
+// stream, one step behind, overlapped with the attention chain of step t+1.  Events order the hand-offs; the same code
+// is captured into the train-step CUDA graph as two parallel branches.
+struct TwoChains {
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int init() {
+    if (s2) return 0;
+    T2V_CUDA_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) T2V_CUDA_CHECK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    return 0;
+  }
+  int fork(cudaStream_t st) {      // s2 joins after everything already enqueued on st
+    T2V_CUDA_CHECK(cudaEventRecord(ev[2], st));
+    T2V_CUDA_CHECK(cudaStreamWaitEvent(s2, ev[2], 0));
+    return 0;
+  }
+  int join(cudaStream_t st) {
+    T2V_CUDA_CHECK(cudaEventRecord(ev[3], s2));
+    T2V_CUDA_CHECK(cudaStreamWaitEvent(st, ev[3], 0));
+    return 0;
+  }
+};
+static TwoChains g_chains;
+static bool two_chains_enabled() {
+  static const bool on = !(getenv("T2V_TWO_CHAINS") && getenv("T2V_TWO_CHAINS")[0] == '0');
+  return on;
+}
+
 int make_fwd_plans(const T2VDecoderSeq* s, FwdPlans* P) {
   const bool tc = s->use_tc != 0;
   const long long rows = (long long)(s->To + 1) * s->B;
@@ -103,17 +134,16 @@ int make_fwd_plans(const T2VDecoderSeq* s, FwdPlans* P) {
   return 0;
 }
 
-// one decoder step t (everything of Decoder.decode except the deferred projection)
-int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) {
+// attention chain of step t: attention_rnn gates + cell, query projection, fused attention (Decoder.decode, model.py:357-374)
+int fwd_step_att(const T2VDecoderSeq* s, const FwdPlans* P, int t, float* parts, cudaStream_t st) {
   const int B = s->B, Ti = s->Ti;
   const long long r0 = (long long)t * B, r1 = (long long)(t + 1) * B;
-  const float p_att = s->training ? s->p_att : 0.f, p_dec = s->training ? s->p_dec : 0.f;
+  const float p_att = s->training ? s->p_att : 0.f;
   const float* mk = s->drop_masks ? s->drop_masks + (long long)t * 4 * B * H : nullptr;
   const unsigned long long dbase = s->drop_masks ? 0ull : (unsigned long long)t * B * H;
-  // attention LSTM
-  CHK(run_gemm(&P->ga, r0, s->parts, st));
+  CHK(run_gemm(&P->ga, r0, parts, st));
   PMARK("gemm_att");
-  CHK(t2v_lstm_pointwise_fwd(s->parts, P->ga.splits, P->ga.split_stride, 4 * H, nullptr, 0, s->ba1, s->ba2,
+  CHK(t2v_lstm_pointwise_fwd(parts, P->ga.splits, P->ga.split_stride, 4 * H, nullptr, 0, s->ba1, s->ba2,
                              s->CA + r0 * H, H,
                              s->XA + r1 * XA_W + (PD + ED), XA_W,          // h_att -> next step's recurrent input
                              s->XD + r0 * XD_W, XD_W,                      // h_att -> decoder_rnn input / query
@@ -122,7 +152,6 @@ int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) 
                              mk, mk ? mk + (long long)B * H : nullptr, s->seed, SITE_ATT_H, SITE_ATT_C, p_att, dbase,
                              nullptr, 0, B, H, s->use_tc, st));
   PMARK("cell_att");
-  // query projection + fused attention
   CHK(run_gemm(&P->gq, r0, s->qparts, st));
   PMARK("gemm_q");
   CHK(t2v_attn2_fwd(s->qparts, P->gq.splits, P->gq.split_stride, t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr,
@@ -131,11 +160,19 @@ int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) 
                     s->XD + r0 * XD_W + H, XD_W,                           // ctx_t -> decoder_rnn input
                     s->XA + r1 * XA_W + PD, XA_W,                          // ctx_t -> next attention_rnn input
                     s->ASAVE ? s->ASAVE + r0 * Ti * AD : nullptr, B, Ti, s->use_tc, st));
-  PMARK("attention(2 kernels)");
-  // decoder LSTM
-  CHK(run_gemm(&P->gd, r0, s->parts, st));
+  PMARK("attention");
+  return 0;
+}
+// decoder_rnn chain of step t (model.py:375-381)
+int fwd_step_dec(const T2VDecoderSeq* s, const FwdPlans* P, int t, float* parts, cudaStream_t st) {
+  const int B = s->B;
+  const long long r0 = (long long)t * B, r1 = (long long)(t + 1) * B;
+  const float p_dec = s->training ? s->p_dec : 0.f;
+  const float* mk = s->drop_masks ? s->drop_masks + (long long)t * 4 * B * H : nullptr;
+  const unsigned long long dbase = s->drop_masks ? 0ull : (unsigned long long)t * B * H;
+  CHK(run_gemm(&P->gd, r0, parts, st));
   PMARK("gemm_dec");
-  CHK(t2v_lstm_pointwise_fwd(s->parts, P->gd.splits, P->gd.split_stride, 4 * H, nullptr, 0, s->bd1, s->bd2,
+  CHK(t2v_lstm_pointwise_fwd(parts, P->gd.splits, P->gd.split_stride, 4 * H, nullptr, 0, s->bd1, s->bd2,
                              s->CD + r0 * H, H,
                              s->XD + r1 * XD_W + (H + ED), XD_W,           // h_dec -> next step's recurrent input
                              nullptr, 0, s->CD + r1 * H, H,
@@ -143,6 +180,12 @@ int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) 
                              mk ? mk + 2LL * B * H : nullptr, mk ? mk + 3LL * B * H : nullptr, s->seed, SITE_DEC_H,
                              SITE_DEC_C, p_dec, dbase, nullptr, 0, B, H, s->use_tc, st));
   PMARK("cell_dec");
+  return 0;
+}
+// one full decoder step on one stream (free-running inference: the next prenet input depends on h_dec, no overlap)
+int fwd_step(const T2VDecoderSeq* s, const FwdPlans* P, int t, cudaStream_t st) {
+  CHK(fwd_step_att(s, P, t, s->parts, st));
+  CHK(fwd_step_dec(s, P, t, s->parts, st));
   return 0;
 }
 
@@ -162,11 +205,25 @@ T2V_API int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end
   FwdPlans P;
   CHK(make_fwd_plans(s, &P));
   g_prof.begin(t_begin, t_end);
-  for (int t = t_begin; t < t_end; ++t) {
-    g_prof.step_begin(t - g_prof.t_first, stream);
-    CHK(fwd_step(s, &P, t, stream));
+  const bool two = two_chains_enabled() && !g_prof.on && (t_end - t_begin) > 1;
+  if (!two) {
+    for (int t = t_begin; t < t_end; ++t) {
+      g_prof.step_begin(t - g_prof.t_first, stream);
+      CHK(fwd_step(s, &P, t, stream));
+    }
+    g_prof.end("decoder forward step", stream);
+    return 0;
   }
-  g_prof.end("decoder forward step", stream);
+  CHK(g_chains.init());
+  CHK(g_chains.fork(stream));
+  float* parts_dec = s->parts + 8LL * s->B * 4 * H;          // second half of the split-K workspace
+  for (int t = t_begin; t < t_end; ++t) {
+    CHK(fwd_step_att(s, &P, t, s->parts, stream));
+    T2V_CUDA_CHECK(cudaEventRecord(g_chains.ev[t & 1], stream));
+    T2V_CUDA_CHECK(cudaStreamWaitEvent(g_chains.s2, g_chains.ev[t & 1], 0));
+    CHK(fwd_step_dec(s, &P, t, parts_dec, g_chains.s2));
+  }
+  CHK(g_chains.join(stream));
   return 0;
 }
 
@@ -183,25 +240,38 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
   CHK(setup_gemm(&gxa, tc, d->DGA, 4 * H, rows, 0, d->WaT, 4 * H, B, XA_W, 4 * H, 8));
   CHK(setup_gemm(&ghq, tc, d->DQ, AD, rows, 0, d->WqT, AD, B, H, AD, 1));
   g_prof.begin(t_lo, t_hi);
+  const bool two = two_chains_enabled() && !g_prof.on && (t_hi - t_lo) > 1;
+  cudaStream_t sd = st;                                       // stream of the decoder_rnn chain
+  float* parts_dec = s->parts;
+  if (two) {
+    CHK(g_chains.init());
+    CHK(g_chains.fork(st));
+    sd = g_chains.s2;
+    parts_dec = s->parts + 8LL * B * 4 * H;
+  }
   for (int t = t_hi - 1; t >= t_lo; --t) {
     g_prof.step_begin(t - g_prof.t_first, st);
     const long long r0 = (long long)t * B, r1 = (long long)(t + 1) * B;
     const bool has_next = (t + 1 < To);
-    float* dxd = d->DXD + (long long)(t & 1) * B * XD_W;
-    const float* dxd_next = d->DXD + (long long)((t + 1) & 1) * B * XD_W;
+    float* dxd = d->DXD + r0 * XD_W;                          // full sequence [To,B,2560]: the decoder_rnn chain may run ahead
+    const float* dxd_next = d->DXD + r1 * XD_W;
     const float* mk = s->drop_masks ? s->drop_masks + (long long)t * 4 * B * H : nullptr;
     const unsigned long long dbase = s->drop_masks ? 0ull : (unsigned long long)t * B * H;
-    // decoder LSTM cell backward
+    // ---- decoder_rnn chain: depends only on DHC[t] and on its own previous step (h_dec part of dXD[t+1])
     CHK(t2v_lstm_pointwise_bwd(d->DHC + r0 * (H + ED), H + ED, has_next ? dxd_next + (H + ED) : nullptr, XD_W, nullptr, 0,
                                d->dCd, s->GD + r0 * 4 * H, s->CPD + r0 * H, s->CD + r0 * H, H, d->DGD + r0 * 4 * H, 4 * H,
                                mk ? mk + 2LL * B * H : nullptr, mk ? mk + 3LL * B * H : nullptr, s->seed, SITE_DEC_H,
-                               SITE_DEC_C, p_dec, dbase, nullptr, 0, B, H, s->use_tc, st));
+                               SITE_DEC_C, p_dec, dbase, nullptr, 0, B, H, s->use_tc, sd));
     PMARK("cell_dec_bwd");
-    CHK(run_gemm(&gxd, r0, s->parts, st));
+    CHK(run_gemm(&gxd, r0, parts_dec, sd));
     PMARK("gemm_dXD");
-    CHK(t2v_sum_parts(s->parts, gxd.splits, gxd.split_stride, dxd, (long long)B * XD_W, st));
+    CHK(t2v_sum_parts(parts_dec, gxd.splits, gxd.split_stride, dxd, (long long)B * XD_W, sd));
     PMARK("sum_parts");
-    // attention backward
+    if (two) {
+      T2V_CUDA_CHECK(cudaEventRecord(g_chains.ev[t & 1], sd));
+      T2V_CUDA_CHECK(cudaStreamWaitEvent(st, g_chains.ev[t & 1], 0));
+    }
+    // ---- attention chain: attention backward, query backward, attention_rnn cell + gates backward
     CHK(t2v_attn2_bwd(dxd + H, XD_W, d->DHC + r0 * (H + ED) + H, H + ED, has_next ? d->DXA + r1 * XA_W + PD : nullptr, XA_W,
                       d->DCTX + r0 * ED, has_next ? d->dwprev + (long long)((t + 1) & 1) * B * Ti : nullptr,
                       d->dwprev + (long long)(t & 1) * B * Ti, d->gcum + (long long)((t + 1) & 1) * B * Ti,
@@ -212,7 +282,6 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
     PMARK("attention_bwd(2)");
     CHK(run_gemm(&ghq, r0, d->dHq, st));
     PMARK("gemm_dHq");
-    // attention LSTM cell backward
     CHK(t2v_lstm_pointwise_bwd(dxd, XD_W, has_next ? d->DXA + r1 * XA_W + (PD + ED) : nullptr, XA_W, d->dHq, H, d->dCa,
                                s->GA + r0 * 4 * H, s->CPA + r0 * H, s->CA + r0 * H, H, d->DGA + r0 * 4 * H, 4 * H, mk,
                                mk ? mk + (long long)B * H : nullptr, s->seed, SITE_ATT_H, SITE_ATT_C, p_att, dbase,
@@ -223,6 +292,7 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
     CHK(t2v_sum_parts(s->parts, gxa.splits, gxa.split_stride, d->DXA + r0 * XA_W, (long long)B * XA_W, st));
     PMARK("sum_parts2");
   }
+  if (two) CHK(g_chains.join(st));
   g_prof.end("decoder backward step", st);
   return 0;
 }
