@@ -63,7 +63,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         s = sorted(self.samples)
@@ -349,8 +349,8 @@ def decoder_step_roofline(m, hp, B, Ti, To, dev, precision):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (us * 1e-6) / 1e9
     return {"kernel": "decoder step = gemm_tc<128,4,8,64> x3 (attention_rnn gates, query, decoder_rnn gates) + "
-                      "lstm_pointwise_fwd x2 + attn2_energy + attn2_context (7 launches, CUDA-graph replay of Decoder.decode "
-                      "for all To steps)",
+                      "lstm_pointwise_fwd x2 + attn3_row (fused energy/softmax/context): 6 launches per step in two concurrent "
+                      "chains, CUDA-graph replay of Decoder.decode for all To steps",
             "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "us_per_step": us, "algorithmic_bytes_per_step": alg_bytes,

@@ -580,7 +580,6 @@ struct B2Args {
 };
 __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
   t2v_pdl_trigger();
-  t2v_pdl_wait();
   extern __shared__ __align__(16) float sm3[];
   const int Ti = p.Ti;
   float* dwv = sm3;                         // [Ti] dw then scratch
@@ -596,9 +595,22 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
   const int b = blockIdx.y, chunk = blockIdx.x, t0 = chunk * TC, tid = threadIdx.x;
   const int nchunk = gridDim.x;
   const int nt = min(TC, Ti - t0);
+  // ---- everything below depends only on tensors saved by the FORWARD pass (alignments, cumulative weights, tanh
+  // activations) and on weights, none of which the preceding backward kernels write: it runs before the PDL wait and
+  // overlaps their tails
   float av[TC];                              // saved tanh activations of this chunk (thread = attention dim)
 #pragma unroll
   for (int tt = 0; tt < TC; ++tt) av[tt] = (tt < nt) ? __ldcs(p.a_save + ((long long)b * Ti + t0 + tt) * AD + tid) : 0.f;
+  conv_stage(p.w_prev, p.wprev_rs, p.cum_in, p.w_conv, b, t0, Ti, win, wcT, f);      // recompute the location features
+  {
+    float tmp[AD * NF / 128];
+#pragma unroll
+    for (int j = 0; j < AD * NF / 128; ++j) tmp[j] = p.w_loc[tid + 128 * j];
+#pragma unroll
+    for (int j = 0; j < AD * NF / 128; ++j) { const int i = tid + 128 * j; wlT[(i / NF) * (NF + 1) + (i % NF)] = tmp[j]; }
+  }
+  for (int i = tid; i < 2 * WIN; i += 128) scat[i] = 0.f;
+  t2v_pdl_wait();
   // (1) dw over the whole row, s = <w, dw>, de for this chunk
   float part = 0.f;
   for (int i = tid; i < Ti; i += 128) {
@@ -612,16 +624,7 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
   const float s = block_sum(part, red);
   __syncthreads();
   if (tid < TC) de[tid] = (tid < nt) ? p.w[b * p.w_rs + t0 + tid] * (dwv[t0 + tid] - s) : 0.f;
-  // (2) recompute the location features of this chunk
-  conv_stage(p.w_prev, p.wprev_rs, p.cum_in, p.w_conv, b, t0, Ti, win, wcT, f);
-  {
-    float tmp[AD * NF / 128];
-#pragma unroll
-    for (int j = 0; j < AD * NF / 128; ++j) tmp[j] = p.w_loc[tid + 128 * j];
-#pragma unroll
-    for (int j = 0; j < AD * NF / 128; ++j) { const int i = tid + 128 * j; wlT[(i / NF) * (NF + 1) + (i % NF)] = tmp[j]; }
-  }
-  for (int i = tid; i < 2 * WIN; i += 128) scat[i] = 0.f;
+  __syncthreads();
   // (3) thread d: tanh/v backward over the chunk; dWloc row d in registers
   const int d = tid;
   const float vd = p.v[d];
