@@ -169,12 +169,26 @@ int t2v_attn2_fwd(const float* qparts, int n_qparts, long long qpart_stride, con
                   const float* w_loc, const float* v, const long long* lens, float mask_value, float* e_buf, float* w_out,
                   long long wout_rs, float* ctx_out1, long long ctx1_rs, float* ctx_out2, long long ctx2_rs, float* a_save,
                   int B, int Ti, int rnd, cudaStream_t stream);
+/* backward of the step in three launches: _ctx (context reduction backward) and _dq (softmax / tanh backward -> dq,
+ * d processed-memory, dv; also initialises dw_out = 0 and gcum_next = gcum_prev) are on the recurrence of the backward time
+ * loop; _loc (location dense / conv backward, adjoint conv scattered into dw_out / gcum_next, dW_loc / dW_conv partials)
+ * only has to finish before the NEXT step's _dq, so a caller may run it on a side stream.  de_buf [B,Ti] carries the
+ * energies gradient from _dq to _loc.  t2v_attn2_bwd = the three in stream order. */
+int t2v_attn2_bwd_ctx(const float* dctx1, long long dctx1_rs, const float* dctx2, long long dctx2_rs, const float* dctx3,
+                      long long dctx3_rs, float* dctx_out, float* dw_part, const float* mem, const long long* lens, int B,
+                      int Ti, cudaStream_t stream);
+int t2v_attn2_bwd_dq(const float* dw_in, float* dw_out, const float* gcum_prev, float* gcum_next, const float* dw_part,
+                     float* de_buf, const float* w, long long w_rs, const float* a_save, const float* v, float* dpmem,
+                     float* dq, float* dv_part, int B, int Ti, cudaStream_t stream);
+int t2v_attn2_bwd_loc(float* dw_out, float* gcum_next, const float* de_buf, const float* w_prev, long long wprev_rs,
+                      const float* cum_in, const float* a_save, const float* w_conv, const float* w_loc, const float* v,
+                      float* dwloc_part, float* dwconv_part, int B, int Ti, cudaStream_t stream);
 int t2v_attn2_bwd(const float* dctx1, long long dctx1_rs, const float* dctx2, long long dctx2_rs, const float* dctx3,
                   long long dctx3_rs, float* dctx_out, const float* dw_in, float* dw_out, const float* gcum_prev,
-                  float* gcum_next, float* dw_part, const float* w, long long w_rs, const float* w_prev, long long wprev_rs,
-                  const float* cum_in, const float* a_save, const float* mem, const float* w_conv, const float* w_loc,
-                  const float* v, const long long* lens, float* dpmem, float* dq, float* dv_part, float* dwloc_part,
-                  float* dwconv_part, int B, int Ti, cudaStream_t stream);
+                  float* gcum_next, float* dw_part, float* de_buf, const float* w, long long w_rs, const float* w_prev,
+                  long long wprev_rs, const float* cum_in, const float* a_save, const float* mem, const float* w_conv,
+                  const float* w_loc, const float* v, const long long* lens, float* dpmem, float* dq, float* dv_part,
+                  float* dwloc_part, float* dwconv_part, int B, int Ti, cudaStream_t stream);
 
 /* ---- the decoder time loop: Decoder.decode / Decoder.forward / Decoder.inference (model.py:346-464) ------------- */
 typedef struct T2VDecoderSeq {
@@ -196,7 +210,7 @@ typedef struct T2VDecoderSeq {
   float *align;                  /* [B,To,Ti] */
   float *GA, *GD, *CPA, *CPD;    /* saved gates [To,B,4096] / pre-dropout cells [To,B,1024]; NULL at inference */
   float *ASAVE;                  /* [To,B,Ti,128] tanh activations; NULL at inference */
-  float *parts, *qparts;         /* split-K workspaces: >= 16*B*4096 (two halves, one per chain) and 8*B*128 floats */
+  float *parts, *qparts;         /* split-K workspaces: >= 32*B*4096 (two halves of 16 parts, one per chain) and 8*B*128 floats */
   float *ebuf;                   /* [B,Ti] attention energies scratch */
 } T2VDecoderSeq;
 int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);
@@ -213,7 +227,7 @@ typedef struct T2VDecoderBwd {
   float *gcum;                   /* ring [2,B,Ti] zero-initialised */
   float *dpmem;                  /* [B,Ti,128] accumulator (zero-initialised) */
   float *DCTX;                   /* out [To,B,512] total grad wrt ctx_t (d(memory) is one batched GEMM after the loop) */
-  float *dw_part;                /* scratch [4,B,Ti] */
+  float *dw_part;                /* scratch [5,B,Ti]: 4 context partials + the energies gradient (de_buf) */
   float *DQ;                     /* out [To,B,128], zero-initialised (accumulated with atomics) */
   float *dHq;                    /* scratch [B,1024] */
   float *dv_part, *dwloc_part, *dwconv_part;   /* [B*nchunk,128], [B*nchunk,128*32], [B*nchunk,32*2*31] accumulators (zero-init), nchunk = t2v_attn2_chunks(Ti) */

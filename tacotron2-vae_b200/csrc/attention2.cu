@@ -8,9 +8,10 @@
 //                                   reduction over Ti with all row loads in flight, cumulative-weights update
 //   backward  attn2_bwd_ctx_kernel  grid (channel-chunk, b): dctx_t = sum of its three sources (stored for the batched
 //                                   d(memory) GEMM after the loop) and the partial <dctx, memory[ti]> products
-//             attn2_bwd_energy_kernel grid (text-chunk, b): softmax backward, tanh/v backward, d(processed memory) +=,
-//                                   dq, location dense/conv backward incl. the adjoint conv scattered into the
-//                                   next step's "previous weights"/"cumulative weights" gradient buffers.
+//             attn2_bwd_dq_kernel   grid (text-chunk, b): softmax backward, tanh/v backward, d(processed memory) +=, dq
+//             attn2_bwd_loc_kernel  grid (text-chunk, b): location dense/conv backward incl. the adjoint conv scattered
+//                                   into the next step's "previous weights"/"cumulative weights" gradient buffers
+//                                   (off the recurrence: runs on a side stream in the decoder loop).
 // Weight-gradient partials (v, W_loc, W_conv) are accumulated per CTA slot across the time loop (no atomics) and
 // reduced once after it.
 #include "t2v_common.cuh"
@@ -515,8 +516,6 @@ struct B1Args {
   const float* mem;          // [B,Ti,ED]
   const long long* lens;
   float* dw_part;            // [NCH][B][Ti] partial <dctx, mem[ti]>
-  float* dw_next_zero;       // [B,Ti] buffer to clear for this step's scatter target (nullable)
-  const float* gcum_prev; float* gcum_next;   // gcum_next = gcum_prev (copied here; the energy kernel adds into it)
   int B, Ti;
 };
 __global__ void __launch_bounds__(128) attn2_bwd_ctx_kernel(B1Args p) {
@@ -531,12 +530,6 @@ __global__ void __launch_bounds__(128) attn2_bwd_ctx_kernel(B1Args p) {
   if (p.dctx3) d += p.dctx3[b * p.dctx3_rs + col];
   dsh[tid] = d;
   p.dctx_out[(long long)b * ED + col] = d;
-  if (ch == 0) {
-    for (int i = tid; i < Ti; i += 128) {
-      if (p.dw_next_zero) p.dw_next_zero[(long long)b * Ti + i] = 0.f;
-      p.gcum_next[(long long)b * Ti + i] = p.gcum_prev[(long long)b * Ti + i];
-    }
-  }
   __syncthreads();
   const float4 dv = *reinterpret_cast<const float4*>(dsh + lane * 4);
   const long long len = p.lens ? p.lens[b] : Ti;
@@ -564,8 +557,9 @@ struct B2Args {
   const float* dw_part;      // [NCH][B][Ti]
   const float* dw_in;        // [B,Ti] nullable
   const float* gcum_prev;    // [B,Ti]
-  float* gcum_next;          // [B,Ti] (+= this step's cumulative-channel gradient)
-  float* dw_out;             // [B,Ti] (+= this step's previous-weights-channel gradient; pre-zeroed)
+  float* gcum_next;          // [B,Ti] (= gcum_prev + this step's cumulative-channel gradient)
+  float* dw_out;             // [B,Ti] (this step's previous-weights-channel gradient)
+  float* de_buf;             // [B,Ti] softmax-backward energies gradient, handed from the dq kernel to the loc kernel
   const float* w; long long w_rs;
   const float* w_prev; long long wprev_rs;
   const float* cum_in;
@@ -578,27 +572,88 @@ struct B2Args {
   float* dwconv_part;        // [B*nchunk,NF*2*KS] +=
   int B, Ti;
 };
-__global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
+
+// The energy backward is two kernels because only part of it sits on the recurrence of the backward time loop:
+//   attn2_bwd_dq_kernel   softmax backward, tanh / v backward -> dq (feeds the attention_rnn cell backward of the SAME
+//                         step: critical path), d(processed memory), dv.  Also initialises this step's scatter targets.
+//   attn2_bwd_loc_kernel  location dense / conv backward: dW_loc, dW_conv and the adjoint conv scattered into the
+//                         "previous weights" / "cumulative weights" gradients that only the NEXT step's dq kernel reads;
+//                         the decoder loop runs it on a side stream under the rest of the step.
+__global__ void __launch_bounds__(128) attn2_bwd_dq_kernel(B2Args p) {
   t2v_pdl_trigger();
   extern __shared__ __align__(16) float sm3[];
   const int Ti = p.Ti;
-  float* dwv = sm3;                         // [Ti] dw then scratch
-  float* win = dwv + ((Ti + 3) & ~3);       // [2][WIN]
-  float* wcT = win + 2 * WIN;               // [2*KS][NF]
-  float* f = wcT + 2 * KS * NF;             // [TC][NF+1]
-  float* dpT = f + TC * (NF + 1);           // [AD][DPS] (dpre transposed: [d][ti], row stride DPS)
-  float* wlT = dpT + AD * DPS;               // [AD][NF+1]... W_loc [d][c] padded
-  float* df = wlT + AD * (NF + 1);          // [TC][NF+1]
-  float* de = df + TC * (NF + 1);           // [TC]
-  float* scat = de + TC;                    // [2][WIN]
-  float* red = scat + 2 * WIN;              // [32]
+  float* dwv = sm3;                         // [Ti]
+  float* de = dwv + ((Ti + 3) & ~3);        // [TC]
+  float* red = de + TC;                     // [32]
   const int b = blockIdx.y, chunk = blockIdx.x, t0 = chunk * TC, tid = threadIdx.x;
   const int nchunk = gridDim.x;
   const int nt = min(TC, Ti - t0);
-  // ---- everything below depends only on tensors saved by the FORWARD pass (alignments, cumulative weights, tanh
-  // activations) and on weights, none of which the preceding backward kernels write: it runs before the PDL wait and
-  // overlaps their tails
-  float av[TC];                              // saved tanh activations of this chunk (thread = attention dim)
+  // saved tanh activations of this chunk (thread = attention dim): forward data, loaded before the dependency wait
+  float av[TC];
+#pragma unroll
+  for (int tt = 0; tt < TC; ++tt) av[tt] = (tt < nt) ? __ldcs(p.a_save + ((long long)b * Ti + t0 + tt) * AD + tid) : 0.f;
+  const int d = tid;
+  const float vd = p.v[d];
+  const long long slot = (long long)b * nchunk + chunk;
+  t2v_pdl_wait();
+  // (1) dw over the whole row, s = <w, dw>, de for this chunk
+  float part = 0.f;
+  for (int i = tid; i < Ti; i += 128) {
+    const float gc = p.gcum_prev[(long long)b * Ti + i];
+    float dw = gc;
+    if (p.dw_in) dw += p.dw_in[(long long)b * Ti + i];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) dw += p.dw_part[((long long)c * p.B + b) * Ti + i];
+    dwv[i] = dw;
+    part = fmaf(p.w[b * p.w_rs + i], dw, part);
+    if (chunk == 0) {                        // scatter targets of this step's loc kernel
+      p.gcum_next[(long long)b * Ti + i] = gc;
+      p.dw_out[(long long)b * Ti + i] = 0.f;
+    }
+  }
+  const float s = block_sum(part, red);
+  __syncthreads();
+  if (tid < TC) {
+    const float g = (tid < nt) ? p.w[b * p.w_rs + t0 + tid] * (dwv[t0 + tid] - s) : 0.f;
+    de[tid] = g;
+    if (tid < nt) p.de_buf[(long long)b * Ti + t0 + tid] = g;
+  }
+  __syncthreads();
+  // (2) thread d: tanh/v backward over the chunk
+  float dq_acc = 0.f, dv_acc = p.dv_part[slot * AD + d];
+#pragma unroll
+  for (int tt = 0; tt < TC; ++tt) {
+    if (tt < nt) {
+      const float g = de[tt];
+      const float a = av[tt];
+      const float dp = g * vd * (1.f - a * a);
+      if (g != 0.f) atomicAdd(p.dpmem + ((long long)b * Ti + t0 + tt) * AD + d, dp);   // sole writer: compiles to RED, no round trip
+      dq_acc += dp;
+      dv_acc = fmaf(g, a, dv_acc);
+    }
+  }
+  p.dv_part[slot * AD + d] = dv_acc;
+  atomicAdd(p.dq + (long long)b * AD + d, dq_acc);
+}
+
+__global__ void __launch_bounds__(128) attn2_bwd_loc_kernel(B2Args p) {
+  t2v_pdl_trigger();
+  extern __shared__ __align__(16) float sm3[];
+  const int Ti = p.Ti;
+  float* win = sm3;                         // [2][WIN]
+  float* wcT = win + 2 * WIN;               // [2*KS][NF]
+  float* f = wcT + 2 * KS * NF;             // [TC][NF+1]
+  float* dpT = f + TC * (NF + 1);           // [AD][DPS] (dpre transposed: [d][ti], row stride DPS)
+  float* wlT = dpT + AD * DPS;              // [AD][NF+1]... W_loc [d][c] padded
+  float* df = wlT + AD * (NF + 1);          // [TC][NF+1]
+  float* de = df + TC * (NF + 1);           // [TC]
+  const int b = blockIdx.y, chunk = blockIdx.x, t0 = chunk * TC, tid = threadIdx.x;
+  const int nchunk = gridDim.x;
+  const int nt = min(TC, Ti - t0);
+  // ---- everything up to the wait depends only on tensors saved by the FORWARD pass (alignments, cumulative weights,
+  // tanh activations) and on weights
+  float av[TC];
 #pragma unroll
   for (int tt = 0; tt < TC; ++tt) av[tt] = (tt < nt) ? __ldcs(p.a_save + ((long long)b * Ti + t0 + tt) * AD + tid) : 0.f;
   conv_stage(p.w_prev, p.wprev_rs, p.cum_in, p.w_conv, b, t0, Ti, win, wcT, f);      // recompute the location features
@@ -609,44 +664,26 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
 #pragma unroll
     for (int j = 0; j < AD * NF / 128; ++j) { const int i = tid + 128 * j; wlT[(i / NF) * (NF + 1) + (i % NF)] = tmp[j]; }
   }
-  for (int i = tid; i < 2 * WIN; i += 128) scat[i] = 0.f;
-  t2v_pdl_wait();
-  // (1) dw over the whole row, s = <w, dw>, de for this chunk
-  float part = 0.f;
-  for (int i = tid; i < Ti; i += 128) {
-    float dw = p.gcum_prev[(long long)b * Ti + i];
-    if (p.dw_in) dw += p.dw_in[(long long)b * Ti + i];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) dw += p.dw_part[((long long)c * p.B + b) * Ti + i];
-    dwv[i] = dw;
-    part = fmaf(p.w[b * p.w_rs + i], dw, part);
-  }
-  const float s = block_sum(part, red);
-  __syncthreads();
-  if (tid < TC) de[tid] = (tid < nt) ? p.w[b * p.w_rs + t0 + tid] * (dwv[t0 + tid] - s) : 0.f;
-  __syncthreads();
-  // (3) thread d: tanh/v backward over the chunk; dWloc row d in registers
   const int d = tid;
   const float vd = p.v[d];
   const long long slot = (long long)b * nchunk + chunk;
   float* wl_part = p.dwloc_part + slot * (AD * NF) + d * NF;
   float gwl[NF];
 #pragma unroll
-  for (int c = 0; c < NF; c += 4) {           // start from the running partial: loads issued before the compute
+  for (int c = 0; c < NF; c += 4) {           // start from the running partial (only this kernel's earlier steps wrote it)
     const float4 t = *reinterpret_cast<const float4*>(wl_part + c);
     gwl[c] = t.x; gwl[c + 1] = t.y; gwl[c + 2] = t.z; gwl[c + 3] = t.w;
   }
-  float dq_acc = 0.f, dv_acc = p.dv_part[slot * AD + d];
+  t2v_pdl_wait();
+  if (tid < TC) de[tid] = (tid < nt) ? p.de_buf[(long long)b * Ti + t0 + tid] : 0.f;
+  __syncthreads();
+  // (3) dpre (recomputed from de and the saved activations), dWloc row d in registers
 #pragma unroll
   for (int tt = 0; tt < TC; ++tt) {
     float dp = 0.f;
     if (tt < nt) {
-      const float g = de[tt];
       const float a = av[tt];
-      dp = g * vd * (1.f - a * a);
-      if (g != 0.f) atomicAdd(p.dpmem + ((long long)b * Ti + t0 + tt) * AD + d, dp);   // sole writer: compiles to RED, no round trip
-      dq_acc += dp;
-      dv_acc = fmaf(g, a, dv_acc);
+      dp = de[tt] * vd * (1.f - a * a);
       const float* fr = f + tt * (NF + 1);
 #pragma unroll
       for (int c = 0; c < NF; ++c) gwl[c] = fmaf(dp, fr[c], gwl[c]);
@@ -655,8 +692,6 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
   }
 #pragma unroll
   for (int c = 0; c < NF; c += 4) *reinterpret_cast<float4*>(wl_part + c) = make_float4(gwl[c], gwl[c + 1], gwl[c + 2], gwl[c + 3]);
-  p.dv_part[slot * AD + d] = dv_acc;
-  atomicAdd(p.dq + (long long)b * AD + d, dq_acc);
   __syncthreads();
   // (4) df[ti][c] = sum_d dpre[ti][d] * Wloc[d][c]; thread (c, group of 8 ti)
   {
@@ -733,9 +768,9 @@ __global__ void __launch_bounds__(128) attn2_bwd_energy_kernel(B2Args p) {
   }
 }
 
-size_t bwd_energy_smem(int Ti) {
-  return sizeof(float) * (size_t)(((Ti + 3) & ~3) + 2 * WIN + 2 * KS * NF + TC * (NF + 1) + AD * DPS + AD * (NF + 1) + TC * (NF + 1) + TC +
-                                  2 * WIN + 32);
+size_t bwd_dq_smem(int Ti) { return sizeof(float) * (size_t)(((Ti + 3) & ~3) + TC + 32); }
+size_t bwd_loc_smem() {
+  return sizeof(float) * (size_t)(2 * WIN + 2 * KS * NF + TC * (NF + 1) + AD * DPS + AD * (NF + 1) + TC * (NF + 1) + TC);
 }
 
 }  // namespace
@@ -798,31 +833,75 @@ T2V_API int t2v_attn2_fwd(const float* qparts, int n_qparts, long long qpart_str
   return 0;
 }
 
-T2V_API int t2v_attn2_bwd(const float* dctx1, long long dctx1_rs, const float* dctx2, long long dctx2_rs, const float* dctx3,
-                          long long dctx3_rs, float* dctx_out, const float* dw_in, float* dw_out, const float* gcum_prev,
-                          float* gcum_next, float* dw_part, const float* w, long long w_rs, const float* w_prev,
-                          long long wprev_rs, const float* cum_in, const float* a_save, const float* mem, const float* w_conv,
-                          const float* w_loc, const float* v, const long long* lens, float* dpmem, float* dq, float* dv_part,
-                          float* dwloc_part, float* dwconv_part, int B, int Ti, cudaStream_t st) {
+// backward, three launches.  _ctx and _dq belong to the recurrence of the time loop; _loc only has to finish before the
+// NEXT step's _dq (it produces that step's dw_in / gcum_prev), so the decoder loop puts it on a side stream.
+T2V_API int t2v_attn2_bwd_ctx(const float* dctx1, long long dctx1_rs, const float* dctx2, long long dctx2_rs,
+                              const float* dctx3, long long dctx3_rs, float* dctx_out, float* dw_part, const float* mem,
+                              const long long* lens, int B, int Ti, cudaStream_t st) {
   T2V_ARG_CHECK(B > 0 && Ti > 0 && Ti <= 8192, "shape");
   B1Args a;
   a.dctx1 = dctx1; a.dctx1_rs = dctx1_rs; a.dctx2 = dctx2; a.dctx2_rs = dctx2_rs; a.dctx3 = dctx3; a.dctx3_rs = dctx3_rs;
-  a.dctx_out = dctx_out; a.mem = mem; a.lens = lens; a.dw_part = dw_part; a.dw_next_zero = dw_out; a.gcum_prev = gcum_prev;
-  a.gcum_next = gcum_next; a.B = B; a.Ti = Ti;
+  a.dctx_out = dctx_out; a.mem = mem; a.lens = lens; a.dw_part = dw_part; a.B = B; a.Ti = Ti;
   T2V_CUDA_CHECK(t2v_launch(attn2_bwd_ctx_kernel, dim3(NCH, B), dim3(128), 0, st, true, 1, a));
-  T2V_COUNT_LAUNCH();
+  LAUNCH_END();
+}
+
+static B2Args make_b2(const float* dw_in, float* dw_out, const float* gcum_prev, float* gcum_next, const float* dw_part,
+                      float* de_buf, const float* w, long long w_rs, const float* w_prev, long long wprev_rs,
+                      const float* cum_in, const float* a_save, const float* w_conv, const float* w_loc, const float* v,
+                      float* dpmem, float* dq, float* dv_part, float* dwloc_part, float* dwconv_part, int B, int Ti) {
   B2Args e;
-  e.dw_part = dw_part; e.dw_in = dw_in; e.gcum_prev = gcum_prev; e.gcum_next = gcum_next; e.dw_out = dw_out; e.w = w;
-  e.w_rs = w_rs; e.w_prev = w_prev; e.wprev_rs = wprev_rs; e.cum_in = cum_in; e.a_save = a_save; e.w_conv = w_conv;
-  e.w_loc = w_loc; e.v = v; e.dpmem = dpmem; e.dq = dq; e.dv_part = dv_part; e.dwloc_part = dwloc_part;
+  e.dw_part = dw_part; e.dw_in = dw_in; e.gcum_prev = gcum_prev; e.gcum_next = gcum_next; e.dw_out = dw_out;
+  e.de_buf = de_buf; e.w = w; e.w_rs = w_rs; e.w_prev = w_prev; e.wprev_rs = wprev_rs; e.cum_in = cum_in; e.a_save = a_save;
+  e.w_conv = w_conv; e.w_loc = w_loc; e.v = v; e.dpmem = dpmem; e.dq = dq; e.dv_part = dv_part; e.dwloc_part = dwloc_part;
   e.dwconv_part = dwconv_part; e.B = B; e.Ti = Ti;
-  const size_t smem = bwd_energy_smem(Ti);
+  return e;
+}
+
+T2V_API int t2v_attn2_bwd_dq(const float* dw_in, float* dw_out, const float* gcum_prev, float* gcum_next,
+                             const float* dw_part, float* de_buf, const float* w, long long w_rs, const float* a_save,
+                             const float* v, float* dpmem, float* dq, float* dv_part, int B, int Ti, cudaStream_t st) {
+  T2V_ARG_CHECK(B > 0 && Ti > 0 && Ti <= 8192, "shape");
+  T2V_ARG_CHECK(dw_out && gcum_next && de_buf, "scatter targets");
+  B2Args e = make_b2(dw_in, dw_out, gcum_prev, gcum_next, dw_part, de_buf, w, w_rs, nullptr, 0, nullptr, a_save, nullptr,
+                     nullptr, v, dpmem, dq, dv_part, nullptr, nullptr, B, Ti);
+  const size_t smem = bwd_dq_smem(Ti);
   static size_t cur = 48 * 1024;
   if (smem > cur) {
-    T2V_CUDA_CHECK(cudaFuncSetAttribute(attn2_bwd_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(attn2_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cur = smem;
   }
-  T2V_CUDA_CHECK(t2v_launch(attn2_bwd_energy_kernel, dim3((Ti + TC - 1) / TC, B), dim3(128), smem, st, true, 1, e));
-  T2V_COUNT_LAUNCH();
-  return 0;
+  T2V_CUDA_CHECK(t2v_launch(attn2_bwd_dq_kernel, dim3((Ti + TC - 1) / TC, B), dim3(128), smem, st, true, 1, e));
+  LAUNCH_END();
+}
+
+T2V_API int t2v_attn2_bwd_loc(float* dw_out, float* gcum_next, const float* de_buf, const float* w_prev, long long wprev_rs,
+                              const float* cum_in, const float* a_save, const float* w_conv, const float* w_loc,
+                              const float* v, float* dwloc_part, float* dwconv_part, int B, int Ti, cudaStream_t st) {
+  T2V_ARG_CHECK(B > 0 && Ti > 0 && Ti <= 8192, "shape");
+  B2Args e = make_b2(nullptr, dw_out, nullptr, gcum_next, nullptr, const_cast<float*>(de_buf), nullptr, 0, w_prev, wprev_rs,
+                     cum_in, a_save, w_conv, w_loc, v, nullptr, nullptr, nullptr, dwloc_part, dwconv_part, B, Ti);
+  const size_t smem = bwd_loc_smem();
+  static size_t cur = 48 * 1024;
+  if (smem > cur) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(attn2_bwd_loc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
+  T2V_CUDA_CHECK(t2v_launch(attn2_bwd_loc_kernel, dim3((Ti + TC - 1) / TC, B), dim3(128), smem, st, true, 1, e));
+  LAUNCH_END();
+}
+
+// the three launches in stream order (what the unit tests and a single-stream caller use)
+T2V_API int t2v_attn2_bwd(const float* dctx1, long long dctx1_rs, const float* dctx2, long long dctx2_rs, const float* dctx3,
+                          long long dctx3_rs, float* dctx_out, const float* dw_in, float* dw_out, const float* gcum_prev,
+                          float* gcum_next, float* dw_part, float* de_buf, const float* w, long long w_rs,
+                          const float* w_prev, long long wprev_rs, const float* cum_in, const float* a_save, const float* mem,
+                          const float* w_conv, const float* w_loc, const float* v, const long long* lens, float* dpmem,
+                          float* dq, float* dv_part, float* dwloc_part, float* dwconv_part, int B, int Ti, cudaStream_t st) {
+  int r = t2v_attn2_bwd_ctx(dctx1, dctx1_rs, dctx2, dctx2_rs, dctx3, dctx3_rs, dctx_out, dw_part, mem, lens, B, Ti, st);
+  if (r) return r;
+  r = t2v_attn2_bwd_dq(dw_in, dw_out, gcum_prev, gcum_next, dw_part, de_buf, w, w_rs, a_save, v, dpmem, dq, dv_part, B, Ti, st);
+  if (r) return r;
+  return t2v_attn2_bwd_loc(dw_out, gcum_next, de_buf, w_prev, wprev_rs, cum_in, a_save, w_conv, w_loc, v, dwloc_part,
+                           dwconv_part, B, Ti, st);
 }

@@ -55,6 +55,18 @@ int run_gemm(const StepGemm* g, long long a_row0, float* D, cudaStream_t st) {
 }
 #define CHK(expr) do { int r__ = (expr); if (r__) return r__; } while (0)
 
+// split-K factors of the four big step GEMMs (att fwd, dec fwd, dec bwd, att bwd); T2V_SPLITS="a,b,c,d" overrides for tuning
+int step_splits(int which) {
+  static int v[4] = {4, 4, 16, 16};
+  static bool init = false;
+  if (!init) {
+    init = true;
+    if (const char* e = getenv("T2V_SPLITS")) sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
+    for (int& x : v) x = x < 1 ? 1 : (x > 16 ? 16 : x);
+  }
+  return v[which];
+}
+
 // T2V_STEP_PROFILE=1: CUDA events after every launch of a few mid-sequence steps; averages printed to stderr.
 struct StepProfiler {
   static constexpr int MAXE = 16, NSTEPS = 16;
@@ -100,12 +112,13 @@ struct FwdPlans { StepGemm ga, gq, gd; };
 // stream, one step behind, overlapped with the attention chain of step t+1.  Events order the hand-offs; the same code
 // is captured into the train-step CUDA graph as two parallel branches.
 struct TwoChains {
-  cudaStream_t s2 = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t s2 = nullptr, s3 = nullptr;      // s3: side stream of the backward loop (location backward of the attention)
+  cudaEvent_t ev[9] = {};
   int init() {
     if (s2) return 0;
     T2V_CUDA_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) T2V_CUDA_CHECK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    T2V_CUDA_CHECK(cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking));
+    for (int i = 0; i < 9; ++i) T2V_CUDA_CHECK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
     return 0;
   }
   int fork(cudaStream_t st) {      // s2 joins after everything already enqueued on st
@@ -128,9 +141,9 @@ static bool two_chains_enabled() {
 int make_fwd_plans(const T2VDecoderSeq* s, FwdPlans* P) {
   const bool tc = s->use_tc != 0;
   const long long rows = (long long)(s->To + 1) * s->B;
-  CHK(setup_gemm(&P->ga, tc, s->XA, XA_W, rows, 0, s->Wa, XA_W, s->B, 4 * H, XA_W, 4));
+  CHK(setup_gemm(&P->ga, tc, s->XA, XA_W, rows, 0, s->Wa, XA_W, s->B, 4 * H, XA_W, step_splits(0)));
   CHK(setup_gemm(&P->gq, tc, s->XD, XD_W, rows, 0, s->Wq, H, s->B, AD, H, 8));
-  CHK(setup_gemm(&P->gd, tc, s->XD, XD_W, rows, 0, s->Wd, XD_W, s->B, 4 * H, XD_W, 4));
+  CHK(setup_gemm(&P->gd, tc, s->XD, XD_W, rows, 0, s->Wd, XD_W, s->B, 4 * H, XD_W, step_splits(1)));
   return 0;
 }
 
@@ -216,7 +229,7 @@ T2V_API int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end
   }
   CHK(g_chains.init());
   CHK(g_chains.fork(stream));
-  float* parts_dec = s->parts + 8LL * s->B * 4 * H;          // second half of the split-K workspace
+  float* parts_dec = s->parts + 16LL * s->B * 4 * H;         // second half of the split-K workspace
   for (int t = t_begin; t < t_end; ++t) {
     CHK(fwd_step_att(s, &P, t, s->parts, stream));
     T2V_CUDA_CHECK(cudaEventRecord(g_chains.ev[t & 1], stream));
@@ -236,19 +249,23 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
   const float p_att = s->training ? s->p_att : 0.f, p_dec = s->training ? s->p_dec : 0.f;
   StepGemm gxd, gxa, ghq;
   const long long rows = (long long)To * B;
-  CHK(setup_gemm(&gxd, tc, d->DGD, 4 * H, rows, 0, d->WdT, 4 * H, B, XD_W, 4 * H, 8));
-  CHK(setup_gemm(&gxa, tc, d->DGA, 4 * H, rows, 0, d->WaT, 4 * H, B, XA_W, 4 * H, 8));
+  CHK(setup_gemm(&gxd, tc, d->DGD, 4 * H, rows, 0, d->WdT, 4 * H, B, XD_W, 4 * H, step_splits(2)));
+  CHK(setup_gemm(&gxa, tc, d->DGA, 4 * H, rows, 0, d->WaT, 4 * H, B, XA_W, 4 * H, step_splits(3)));
   CHK(setup_gemm(&ghq, tc, d->DQ, AD, rows, 0, d->WqT, AD, B, H, AD, 1));
   g_prof.begin(t_lo, t_hi);
   const bool two = two_chains_enabled() && !g_prof.on && (t_hi - t_lo) > 1;
   cudaStream_t sd = st;                                       // stream of the decoder_rnn chain
   float* parts_dec = s->parts;
+  cudaStream_t sl = st;                                       // stream of the attention location backward
   if (two) {
     CHK(g_chains.init());
     CHK(g_chains.fork(st));
     sd = g_chains.s2;
-    parts_dec = s->parts + 8LL * B * 4 * H;
+    sl = g_chains.s3;
+    T2V_CUDA_CHECK(cudaStreamWaitEvent(sl, g_chains.ev[2], 0));     // the fork event
+    parts_dec = s->parts + 16LL * B * 4 * H;
   }
+  float* de_buf = d->dw_part + 4LL * B * Ti;
   for (int t = t_hi - 1; t >= t_lo; --t) {
     g_prof.step_begin(t - g_prof.t_first, st);
     const long long r0 = (long long)t * B, r1 = (long long)(t + 1) * B;
@@ -272,14 +289,27 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
       T2V_CUDA_CHECK(cudaStreamWaitEvent(st, g_chains.ev[t & 1], 0));
     }
     // ---- attention chain: attention backward, query backward, attention_rnn cell + gates backward
-    CHK(t2v_attn2_bwd(dxd + H, XD_W, d->DHC + r0 * (H + ED) + H, H + ED, has_next ? d->DXA + r1 * XA_W + PD : nullptr, XA_W,
-                      d->DCTX + r0 * ED, has_next ? d->dwprev + (long long)((t + 1) & 1) * B * Ti : nullptr,
-                      d->dwprev + (long long)(t & 1) * B * Ti, d->gcum + (long long)((t + 1) & 1) * B * Ti,
-                      d->gcum + (long long)(t & 1) * B * Ti, d->dw_part, s->align + (long long)t * Ti, (long long)To * Ti,
-                      t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr, (long long)To * Ti, s->CUM + r0 * Ti,
-                      s->ASAVE + r0 * Ti * AD, s->mem, s->Wconv, s->Wloc, s->v, s->in_lens, d->dpmem, d->DQ + r0 * AD,
-                      d->dv_part, d->dwloc_part, d->dwconv_part, B, Ti, st));
-    PMARK("attention_bwd(2)");
+    float* dw_out = d->dwprev + (long long)(t & 1) * B * Ti;
+    float* gcum_next = d->gcum + (long long)(t & 1) * B * Ti;
+    const float* a_save = s->ASAVE + r0 * Ti * AD;
+    CHK(t2v_attn2_bwd_ctx(dxd + H, XD_W, d->DHC + r0 * (H + ED) + H, H + ED, has_next ? d->DXA + r1 * XA_W + PD : nullptr,
+                          XA_W, d->DCTX + r0 * ED, d->dw_part, s->mem, s->in_lens, B, Ti, st));
+    PMARK("attention_bwd_ctx");
+    // the previous step's location backward produced this step's dw_in / gcum_prev (and read de_buf)
+    if (two && t + 1 < t_hi) T2V_CUDA_CHECK(cudaStreamWaitEvent(st, g_chains.ev[5 + ((t + 1) & 1)], 0));
+    CHK(t2v_attn2_bwd_dq(has_next ? d->dwprev + (long long)((t + 1) & 1) * B * Ti : nullptr, dw_out,
+                         d->gcum + (long long)((t + 1) & 1) * B * Ti, gcum_next, d->dw_part, de_buf,
+                         s->align + (long long)t * Ti, (long long)To * Ti, a_save, s->v, d->dpmem, d->DQ + r0 * AD, d->dv_part,
+                         B, Ti, st));
+    PMARK("attention_bwd_dq");
+    if (two) {
+      T2V_CUDA_CHECK(cudaEventRecord(g_chains.ev[7 + (t & 1)], st));
+      T2V_CUDA_CHECK(cudaStreamWaitEvent(sl, g_chains.ev[7 + (t & 1)], 0));
+    }
+    CHK(t2v_attn2_bwd_loc(dw_out, gcum_next, de_buf, t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr, (long long)To * Ti,
+                          s->CUM + r0 * Ti, a_save, s->Wconv, s->Wloc, s->v, d->dwloc_part, d->dwconv_part, B, Ti, sl));
+    if (two) T2V_CUDA_CHECK(cudaEventRecord(g_chains.ev[5 + (t & 1)], sl));
+    PMARK("attention_bwd_loc");
     CHK(run_gemm(&ghq, r0, d->dHq, st));
     PMARK("gemm_dHq");
     CHK(t2v_lstm_pointwise_bwd(dxd, XD_W, has_next ? d->DXA + r1 * XA_W + (PD + ED) : nullptr, XA_W, d->dHq, H, d->dCa,
@@ -292,7 +322,11 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
     CHK(t2v_sum_parts(s->parts, gxa.splits, gxa.split_stride, d->DXA + r0 * XA_W, (long long)B * XA_W, st));
     PMARK("sum_parts2");
   }
-  if (two) CHK(g_chains.join(st));
+  if (two) {
+    CHK(g_chains.join(st));
+    T2V_CUDA_CHECK(cudaEventRecord(g_chains.ev[4], sl));
+    T2V_CUDA_CHECK(cudaStreamWaitEvent(st, g_chains.ev[4], 0));
+  }
   g_prof.end("decoder backward step", st);
   return 0;
 }

@@ -202,6 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t fmt = (ESIZE == 4) ? 2u : 1u;   // TF32 : BF16
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(BM >> 4) << 24);
+      t2v_pdl_wait();                  // block in hardware (not in the mbarrier spin) while the prerequisite grid runs
       for (int it = 0; it < n_it; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -275,9 +276,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int ESIZE>
 constexpr int stages_for() { return (BN == 256) ? 4 : (BN == 128 ? 6 : 8); }
 
-template <int BN, int ESIZE, int BM = 128>
+template <int BN, int ESIZE, int BM = 128, int STG = 0>
 int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcParams& p, int splits, cudaStream_t st) {
-  constexpr int STAGES = (BM == 64) ? 8 : stages_for<BN, ESIZE>();
+  constexpr int STAGES = (STG > 0) ? STG : ((BM == 64) ? 8 : stages_for<BN, ESIZE>());
   constexpr int smem = STAGES * (BM * 128 + BN * 128) + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
@@ -351,7 +352,12 @@ int t2v_gemm_tc_run(const T2VGemmTcPlan* plan, int a_row0, int b_row0, float* D,
   p.a_row0 = a_row0; p.b_row0 = b_row0; p.D = D; p.bias = bias;
   const int BN = plan->BN, splits = plan->splits;
   if (plan->esize == 4) {
-    if (BN == 128 && plan->BM == 64) return launch_gemm_tc<128, 4, 64>(plan->tmA, plan->tmB, p, splits, stream);
+    if (BN == 128 && plan->BM == 64) {
+      // 4 stages = 96 KB of shared memory: two CTAs fit on an SM, so the step GEMMs of the two decoder chains co-reside
+      static const bool deep = getenv("T2V_M64_STAGES") && getenv("T2V_M64_STAGES")[0] == '8';
+      return deep ? launch_gemm_tc<128, 4, 64, 8>(plan->tmA, plan->tmB, p, splits, stream)
+                  : launch_gemm_tc<128, 4, 64, 4>(plan->tmA, plan->tmB, p, splits, stream);
+    }
     if (BN == 64) return launch_gemm_tc<64, 4>(plan->tmA, plan->tmB, p, splits, stream);
     if (BN == 128) return launch_gemm_tc<128, 4>(plan->tmA, plan->tmB, p, splits, stream);
     return launch_gemm_tc<256, 4>(plan->tmA, plan->tmB, p, splits, stream);

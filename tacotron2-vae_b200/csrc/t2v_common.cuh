@@ -42,8 +42,23 @@ extern unsigned long long g_t2v_launches;
 // cudaLaunchAttributeProgrammaticStreamSerialization so that a kernel's launch + prologue (barrier init, TMEM allocation,
 // weight staging -- nothing that depends on the previous kernel) overlaps the previous kernel's tail.  t2v_pdl_wait()
 // blocks until every prerequisite grid has completed and flushed; it is a no-op for ordinary launches.
-__device__ __forceinline__ void t2v_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void t2v_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// T2V_PDL_LATE=1: a kernel releases its dependent only after its own wait returned, so at most ONE kernel of the chain
+// is pre-launched (with the trigger at the top, the whole chain cascades onto the SMs and the waiting CTAs take shared
+// memory / warp slots from the kernel that is actually running).
+#ifndef T2V_PDL_LATE
+#define T2V_PDL_LATE 1
+#endif
+__device__ __forceinline__ void t2v_pdl_trigger() {
+#if !T2V_PDL_LATE
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void t2v_pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#if T2V_PDL_LATE
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 bool t2v_pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t t2v_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,

@@ -29,6 +29,7 @@ def build(force=False, verbose=False):
         objs.append(obj)
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                "-Xcompiler", "-fPIC,-fvisibility=hidden", "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd[1:1] = os.environ.get("T2V_NVCC_FLAGS", "").split()     # tuning builds (-DT2V_...=...)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

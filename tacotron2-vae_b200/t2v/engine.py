@@ -555,7 +555,7 @@ def alloc_decoder_buffers(B, Ti, To, dev, save=True):
     buf = dict(XA=_zeros((To + 1) * B, 1792, device=dev), XD=_zeros((To + 1) * B, 2560, device=dev),
                CA=_zeros((To + 1) * B, 1024, device=dev), CD=_zeros((To + 1) * B, 1024, device=dev),
                CUM=_zeros((To + 1) * B, Ti, device=dev), align=_zeros(B, To, Ti, device=dev),
-               parts=_empty(16 * B * 4096, device=dev), qparts=_empty(8 * B * 128, device=dev),
+               parts=_empty(32 * B * 4096, device=dev), qparts=_empty(8 * B * 128, device=dev),
                ebuf=_empty(B, Ti, device=dev))
     if save:
         buf.update(GA=_empty(To * B, 4096, device=dev), GD=_empty(To * B, 4096, device=dev),
@@ -634,7 +634,7 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
     t = dict(WaT=WaT, WdT=WdT, WqT=WqT, DHC=DHC, DGA=_empty(n, 4096, device=dev), DGD=_empty(n, 4096, device=dev),
              DXA=_empty(n, 1792, device=dev), DXD=_empty(n, 2560, device=dev), dCa=_zeros(B, 1024, device=dev),
              dCd=_zeros(B, 1024, device=dev), dwprev=_zeros(2 * B, Ti, device=dev), gcum=_zeros(2 * B, Ti, device=dev),
-             dpmem=_zeros(B * Ti, 128, device=dev), DCTX=_empty(n, 512, device=dev), dw_part=_empty(4 * B, Ti, device=dev),
+             dpmem=_zeros(B * Ti, 128, device=dev), DCTX=_empty(n, 512, device=dev), dw_part=_empty(5 * B, Ti, device=dev),
              DQ=_zeros(n, 128, device=dev), dHq=_empty(B, 1024, device=dev), dv_part=_zeros(B * nck, 128, device=dev),
              dwloc_part=_zeros(B * nck, 128 * 32, device=dev), dwconv_part=_zeros(B * nck, 32 * 2 * 31, device=dev))
     for k, v in t.items():

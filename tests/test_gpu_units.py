@@ -249,7 +249,8 @@ def test_attention_v2_matches_v1(L, Ti):
     dv2 = torch.zeros(B * nck, 128, device=dev); dwl2 = torch.zeros(B * nck, 128 * 32, device=dev)
     dwc2 = torch.zeros(B * nck, 32 * 62, device=dev)
     dwo2 = torch.full((B, Ti), 7.0, device=dev); gcn = torch.full((B, Ti), -3.0, device=dev)
-    L("t2v_attn2_bwd", d1, 512, d2, 512, d3, 512, dctx, dw_in, dwo2, gc, gcn, dwp, w, Ti, wprev, Ti, cum, a_save, mem, wconvT,
+    de = torch.empty(B, Ti, device=dev)
+    L("t2v_attn2_bwd", d1, 512, d2, 512, d3, 512, dctx, dw_in, dwo2, gc, gcn, dwp, de, w, Ti, wprev, Ti, cum, a_save, mem, wconvT,
       wloc, v, lens, dpm2, dq2, dv2, dwl2, dwc2, B, Ti)
     tol = dict(atol=2e-5, rtol=1e-4)
     assert torch.allclose(dctx, d1 + d2 + d3, **tol)
