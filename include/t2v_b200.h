@@ -169,6 +169,15 @@ int t2v_attn2_fwd(const float* qparts, int n_qparts, long long qpart_stride, con
                   const float* w_loc, const float* v, const long long* lens, float mask_value, float* e_buf, float* w_out,
                   long long wout_rs, float* ctx_out1, long long ctx1_rs, float* ctx_out2, long long ctx2_rs, float* a_save,
                   int B, int Ti, int rnd, cudaStream_t stream);
+/* forward of the step in two launches: _loc computes pre[b,ti,:] = processed_memory + W_loc conv([w_prev; w_cum]) for a step
+ * from the PREVIOUS step's alignments only (no query), so a caller may run it on a side stream under the attention_rnn
+ * GEMM / cell / query GEMM; _row = tanh(q + pre).v -> mask -> softmax -> context, cumulative weights, saved activations. */
+int t2v_attn3_loc_fwd(const float* w_prev, long long wprev_rs, const float* cum_in, const float* pmem, const float* w_conv,
+                      const float* w_loc, float* pre, int B, int Ti, cudaStream_t stream);
+int t2v_attn3_row_fwd(const float* qparts, int n_qparts, long long qpart_stride, const float* pre, const float* cum_in,
+                      float* cum_out, const float* mem, const float* v, const long long* lens, float mask_value,
+                      float* w_out, long long wout_rs, float* ctx_out1, long long ctx1_rs, float* ctx_out2,
+                      long long ctx2_rs, float* a_save, int B, int Ti, int rnd, cudaStream_t stream);
 /* backward of the step in three launches: _ctx (context reduction backward) and _dq (softmax / tanh backward -> dq,
  * d processed-memory, dv; also initialises dw_out = 0 and gcum_next = gcum_prev) are on the recurrence of the backward time
  * loop; _loc (location dense / conv backward, adjoint conv scattered into dw_out / gcum_next, dW_loc / dW_conv partials)
@@ -211,7 +220,7 @@ typedef struct T2VDecoderSeq {
   float *GA, *GD, *CPA, *CPD;    /* saved gates [To,B,4096] / pre-dropout cells [To,B,1024]; NULL at inference */
   float *ASAVE;                  /* [To,B,Ti,128] tanh activations; NULL at inference */
   float *parts, *qparts;         /* split-K workspaces: >= 32*B*4096 (two halves of 16 parts, one per chain) and 8*B*128 floats */
-  float *ebuf;                   /* [B,Ti] attention energies scratch */
+  float *ebuf;                   /* [B,Ti,129] scratch: [B,Ti] energies, then [B,Ti,128] location term + processed memory */
 } T2VDecoderSeq;
 int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);
 

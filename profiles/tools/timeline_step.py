@@ -39,5 +39,5 @@ def dump(marker, title, count=26):
         print("  stream %-4s %9.2f  +%6.2f  %s" % (e["args"].get("stream"), e["ts"] - t0, e["dur"], short(e["name"])))
     steps = [ev[idx[k + 1]]["ts"] - ev[idx[k]]["ts"] for k in range(To // 4, 3 * To // 4)]
     print("  marker-to-marker period: mean %.2f us" % (sum(steps) / len(steps)))
-dump("attn3_row_kernel", "forward loop", int(os.environ.get("TL_COUNT", 26)))
+dump("attn3_rowq_kernel", "forward loop", int(os.environ.get("TL_COUNT", 26)))
 dump("attn2_bwd_dq_kernel", "backward loop", int(os.environ.get("TL_COUNT", 30)))

@@ -509,6 +509,163 @@ __global__ void __launch_bounds__(512) attn3_row_kernel(R3Args p) {
   if (p.ctx_out2) p.ctx_out2[b * p.ctx2_rs + tid] = c;
 }
 
+// ---- forward split along the recurrence: the location term of step t+1 depends on the alignments of step t but NOT on
+// the query of step t+1, so it is computed off the critical path (side stream, under the attention_rnn GEMM / cell / query
+// GEMM of step t+1) by attn3_loc_kernel as  pre[b,ti,:] = processed_memory[b,ti,:] + W_loc conv([w_prev; w_cum])[ti] ;
+// attn3_rowq_kernel, one CTA per utterance, then only does  tanh(q + pre) . v -> mask -> softmax -> context.
+struct L3Args {
+  const float* w_prev; long long wprev_rs;     // nullable (first step)
+  const float* cum_in; const float* pmem; const float* w_conv; const float* w_loc;
+  float* pre;                                   // [B,Ti,AD]
+  int B, Ti;
+};
+__global__ void __launch_bounds__(128) attn3_loc_kernel(L3Args p) {
+  t2v_pdl_trigger();
+  __shared__ float win[2 * WIN];
+  __shared__ float wcT[2 * KS * NF];
+  __shared__ float f[TC * (NF + 1)];
+  const int b = blockIdx.y, t0 = blockIdx.x * TC, tid = threadIdx.x;
+  const int Ti = p.Ti, d = tid, nt = min(TC, Ti - t0);
+  float wl[NF];
+#pragma unroll
+  for (int c = 0; c < NF; c += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p.w_loc + d * NF + c);
+    wl[c] = t.x; wl[c + 1] = t.y; wl[c + 2] = t.z; wl[c + 3] = t.w;
+  }
+  float pmv[TC];
+#pragma unroll
+  for (int tt = 0; tt < TC; ++tt) pmv[tt] = (tt < nt) ? p.pmem[((long long)b * Ti + t0 + tt) * AD + d] : 0.f;
+  t2v_pdl_wait();
+  conv_stage(p.w_prev, p.wprev_rs, p.cum_in, p.w_conv, b, t0, Ti, win, wcT, f);
+#pragma unroll
+  for (int tt = 0; tt < TC; ++tt) {
+    if (tt < nt) {
+      float s = pmv[tt], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const float* fr = f + tt * (NF + 1);
+#pragma unroll
+      for (int c = 0; c < NF; c += 4) {
+        s = fmaf(fr[c], wl[c], s); s1 = fmaf(fr[c + 1], wl[c + 1], s1);
+        s2 = fmaf(fr[c + 2], wl[c + 2], s2); s3 = fmaf(fr[c + 3], wl[c + 3], s3);
+      }
+      p.pre[((long long)b * Ti + t0 + tt) * AD + d] = (s + s1) + (s2 + s3);
+    }
+  }
+}
+
+struct Q3Args {
+  const float* qparts; int n_qparts; long long qpart_stride;
+  const float* pre;                             // [B,Ti,AD]
+  const float* v; const long long* lens; float mask_value;
+  const float* cum_in; float* cum_out; const float* mem;
+  float* w_out; long long wout_rs;
+  float* ctx_out1; long long ctx1_rs; float* ctx_out2; long long ctx2_rs;
+  float* a_save;                                // [B,Ti,AD] nullable
+  int B, Ti, rnd;
+};
+__global__ void __launch_bounds__(512) attn3_rowq_kernel(Q3Args p) {
+  extern __shared__ __align__(16) float sm5[];
+  t2v_pdl_trigger();
+  const int Ti = p.Ti, Tia = (Ti + 3) & ~3;
+  float* redA = sm5;                             // [4 groups][4 warps][TC]
+  float* ew = redA + 4 * 4 * TC;                 // [Tia] energies -> weights
+  float* part = ew + Tia;                        // [16][512]
+  float* red2 = part + 16 * 512;                 // [32]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = tid >> 7, d = tid & 127, gwarp = warp & 3;
+  float* red = redA + grp * 4 * TC;
+  const float vd = p.v[d];
+  const long long len = p.lens ? p.lens[b] : Ti;
+  t2v_pdl_wait();
+  float qv = 0.f;
+  for (int s = 0; s < p.n_qparts; ++s) qv += p.qparts[s * p.qpart_stride + (long long)b * AD + d];
+  const int nchunk = (Ti + TC - 1) / TC;
+  for (int pass = 0; pass * 4 < nchunk; ++pass) {
+    const int t0 = (pass * 4 + grp) * TC;
+    const int nt = max(0, min(TC, Ti - t0));
+    float x[TC];
+#pragma unroll
+    for (int tt = 0; tt < TC; ++tt) x[tt] = (tt < nt) ? __ldcs(p.pre + ((long long)b * Ti + t0 + tt) * AD + d) : 0.f;
+#pragma unroll
+    for (int tt = 0; tt < TC; ++tt) {
+      const float a = t2v_tanh(qv + x[tt]);
+      if (tt < nt && p.a_save) __stcs(p.a_save + ((long long)b * Ti + t0 + tt) * AD + d, a);
+      x[tt] = (tt < nt) ? vd * a : 0.f;
+    }
+    // transposing warp reduction: 31 shuffles leave the sum over the warp's 32 attention dims of position tt in lane tt
+#pragma unroll
+    for (int sft = TC / 2; sft >= 1; sft >>= 1) {
+      const bool up = (lane & sft) != 0;
+#pragma unroll
+      for (int i = 0; i < sft; ++i) {
+        const float send = up ? x[i] : x[i + sft];
+        const float keep = up ? x[i + sft] : x[i];
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+      }
+    }
+    red[gwarp * TC + lane] = x[0];
+    __syncthreads();
+    if (d < nt) {
+      const float e = red[d] + red[TC + d] + red[2 * TC + d] + red[3 * TC + d];
+      ew[t0 + d] = (t0 + d < len) ? e : p.mask_value;
+    }
+    __syncthreads();
+  }
+  // ---- softmax over the text positions
+  float m = -INFINITY;
+  for (int i = tid; i < Ti; i += 512) m = fmaxf(m, ew[i]);
+  m = block_max(m, red2);
+  float ssum = 0.f;
+  for (int i = tid; i < Ti; i += 512) {
+    const float xx = expf(ew[i] - m);
+    ew[i] = xx;
+    ssum += xx;
+  }
+  ssum = block_sum(ssum, red2);
+  const float inv = 1.f / ssum;
+  __syncthreads();
+  for (int i = tid; i < Ti; i += 512) {
+    const float xx = ew[i] * inv;
+    ew[i] = xx;
+    p.w_out[b * p.wout_rs + i] = xx;
+    p.cum_out[(long long)b * Ti + i] = p.cum_in[(long long)b * Ti + i] + xx;
+  }
+  __syncthreads();
+  // ---- context: warp -> ti = warp, warp+16, ... ; lane -> channels lane*4 + 128*j
+  float4 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* mbase = p.mem + (long long)b * Ti * ED + lane * 4;
+  for (int base = warp; base < Ti; base += 16 * 4) {
+    float4 mv[4][4];
+    float wi[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ti = base + 16 * r;
+      wi[r] = (ti < Ti) ? ew[ti] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        mv[r][j] = (wi[r] != 0.f) ? *reinterpret_cast<const float4*>(mbase + (long long)ti * ED + 128 * j)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j].x = fmaf(wi[r], mv[r][j].x, acc[j].x); acc[j].y = fmaf(wi[r], mv[r][j].y, acc[j].y);
+        acc[j].z = fmaf(wi[r], mv[r][j].z, acc[j].z); acc[j].w = fmaf(wi[r], mv[r][j].w, acc[j].w);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(part + warp * 512 + 128 * j + lane * 4) = acc[j];
+  __syncthreads();
+  float c = 0.f;
+#pragma unroll
+  for (int w = 0; w < 16; ++w) c += part[w * 512 + tid];
+  c = t2v_rnd(c, p.rnd);
+  if (p.ctx_out1) p.ctx_out1[b * p.ctx1_rs + tid] = c;
+  if (p.ctx_out2) p.ctx_out2[b * p.ctx2_rs + tid] = c;
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 struct B1Args {
   const float* dctx1; long long dctx1_rs; const float* dctx2; long long dctx2_rs; const float* dctx3; long long dctx3_rs;
@@ -778,6 +935,37 @@ size_t bwd_loc_smem() {
 #define LAUNCH_END() do { T2V_COUNT_LAUNCH(); T2V_LAUNCH_CHECK(); return 0; } while (0)
 
 T2V_API int t2v_attn2_chunks(int Ti) { return (Ti + TC - 1) / TC; }
+
+// forward in two launches (see attn3_loc_kernel): _loc for step t+1 may run on a side stream as soon as step t's
+// alignments exist; _row is the part on the recurrence
+T2V_API int t2v_attn3_loc_fwd(const float* w_prev, long long wprev_rs, const float* cum_in, const float* pmem,
+                              const float* w_conv, const float* w_loc, float* pre, int B, int Ti, cudaStream_t st) {
+  T2V_ARG_CHECK(B > 0 && Ti > 0 && Ti <= 8192, "shape");
+  L3Args a;
+  a.w_prev = w_prev; a.wprev_rs = wprev_rs; a.cum_in = cum_in; a.pmem = pmem; a.w_conv = w_conv; a.w_loc = w_loc; a.pre = pre;
+  a.B = B; a.Ti = Ti;
+  T2V_CUDA_CHECK(t2v_launch(attn3_loc_kernel, dim3((Ti + TC - 1) / TC, B), dim3(128), 0, st, true, 1, a));
+  LAUNCH_END();
+}
+T2V_API int t2v_attn3_row_fwd(const float* qparts, int n_qparts, long long qpart_stride, const float* pre, const float* cum_in,
+                              float* cum_out, const float* mem, const float* v, const long long* lens, float mask_value,
+                              float* w_out, long long wout_rs, float* ctx_out1, long long ctx1_rs, float* ctx_out2,
+                              long long ctx2_rs, float* a_save, int B, int Ti, int rnd, cudaStream_t st) {
+  T2V_ARG_CHECK(B > 0 && Ti > 0 && Ti <= 8192, "shape");
+  Q3Args a;
+  a.qparts = qparts; a.n_qparts = n_qparts; a.qpart_stride = qpart_stride; a.pre = pre; a.v = v; a.lens = lens;
+  a.mask_value = mask_value; a.cum_in = cum_in; a.cum_out = cum_out; a.mem = mem; a.w_out = w_out; a.wout_rs = wout_rs;
+  a.ctx_out1 = ctx_out1; a.ctx1_rs = ctx1_rs; a.ctx_out2 = ctx_out2; a.ctx2_rs = ctx2_rs; a.a_save = a_save; a.B = B;
+  a.Ti = Ti; a.rnd = rnd;
+  const size_t smem = sizeof(float) * (size_t)(4 * 4 * TC + ((Ti + 3) & ~3) + 16 * 512 + 32);
+  static size_t cur = 48 * 1024;
+  if (smem > cur) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(attn3_rowq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
+  T2V_CUDA_CHECK(t2v_launch(attn3_rowq_kernel, dim3(B), dim3(512), smem, st, true, 1, a));
+  LAUNCH_END();
+}
 
 // forward: energies (e_buf [B,Ti] scratch) then softmax + context
 T2V_API int t2v_attn2_fwd(const float* qparts, int n_qparts, long long qpart_stride, const float* w_prev, long long wprev_rs,

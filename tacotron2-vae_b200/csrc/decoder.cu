@@ -148,8 +148,20 @@ int make_fwd_plans(const T2VDecoderSeq* s, FwdPlans* P) {
 }
 
 // attention chain of step t: attention_rnn gates + cell, query projection, fused attention (Decoder.decode, model.py:357-374)
-int fwd_step_att(const T2VDecoderSeq* s, const FwdPlans* P, int t, float* parts, cudaStream_t st) {
+// location term of step t's attention (needs only step t-1's alignments): off the recurrence
+int fwd_step_loc(const T2VDecoderSeq* s, int t, cudaStream_t st) {
   const int B = s->B, Ti = s->Ti;
+  return t2v_attn3_loc_fwd(t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr, (long long)s->To * Ti,
+                           s->CUM + (long long)t * B * Ti, s->pmem, s->Wconv, s->Wloc, s->ebuf + (long long)B * Ti, B, Ti, st);
+}
+static bool attn_legacy_mode() {
+  static const bool on = getenv("T2V_ATTN_MODE") != nullptr;     // "row"/"split"/"cluster": the single-stream kernels
+  return on;
+}
+// loc_done: event to wait for before the attention (the side stream's location kernel), or nullptr = run it in order
+int fwd_step_att(const T2VDecoderSeq* s, const FwdPlans* P, int t, float* parts, cudaStream_t st, cudaEvent_t loc_done = nullptr) {
+  const int B = s->B, Ti = s->Ti;
+  if (!attn_legacy_mode() && !loc_done) CHK(fwd_step_loc(s, t, st));
   const long long r0 = (long long)t * B, r1 = (long long)(t + 1) * B;
   const float p_att = s->training ? s->p_att : 0.f;
   const float* mk = s->drop_masks ? s->drop_masks + (long long)t * 4 * B * H : nullptr;
@@ -167,12 +179,21 @@ int fwd_step_att(const T2VDecoderSeq* s, const FwdPlans* P, int t, float* parts,
   PMARK("cell_att");
   CHK(run_gemm(&P->gq, r0, s->qparts, st));
   PMARK("gemm_q");
-  CHK(t2v_attn2_fwd(s->qparts, P->gq.splits, P->gq.split_stride, t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr,
-                    (long long)s->To * Ti, s->CUM + r0 * Ti, s->CUM + r1 * Ti, s->pmem, s->mem, s->Wconv, s->Wloc, s->v,
-                    s->in_lens, s->mask_value, s->ebuf, s->align + (long long)t * Ti, (long long)s->To * Ti,
-                    s->XD + r0 * XD_W + H, XD_W,                           // ctx_t -> decoder_rnn input
-                    s->XA + r1 * XA_W + PD, XA_W,                          // ctx_t -> next attention_rnn input
-                    s->ASAVE ? s->ASAVE + r0 * Ti * AD : nullptr, B, Ti, s->use_tc, st));
+  if (attn_legacy_mode()) {
+    CHK(t2v_attn2_fwd(s->qparts, P->gq.splits, P->gq.split_stride, t > 0 ? s->align + (long long)(t - 1) * Ti : nullptr,
+                      (long long)s->To * Ti, s->CUM + r0 * Ti, s->CUM + r1 * Ti, s->pmem, s->mem, s->Wconv, s->Wloc, s->v,
+                      s->in_lens, s->mask_value, s->ebuf, s->align + (long long)t * Ti, (long long)s->To * Ti,
+                      s->XD + r0 * XD_W + H, XD_W, s->XA + r1 * XA_W + PD, XA_W,
+                      s->ASAVE ? s->ASAVE + r0 * Ti * AD : nullptr, B, Ti, s->use_tc, st));
+  } else {
+    if (loc_done) T2V_CUDA_CHECK(cudaStreamWaitEvent(st, loc_done, 0));
+    CHK(t2v_attn3_row_fwd(s->qparts, P->gq.splits, P->gq.split_stride, s->ebuf + (long long)B * Ti, s->CUM + r0 * Ti,
+                          s->CUM + r1 * Ti, s->mem, s->v, s->in_lens, s->mask_value, s->align + (long long)t * Ti,
+                          (long long)s->To * Ti,
+                          s->XD + r0 * XD_W + H, XD_W,                       // ctx_t -> decoder_rnn input
+                          s->XA + r1 * XA_W + PD, XA_W,                      // ctx_t -> next attention_rnn input
+                          s->ASAVE ? s->ASAVE + r0 * Ti * AD : nullptr, B, Ti, s->use_tc, st));
+  }
   PMARK("attention");
   return 0;
 }
@@ -230,13 +251,29 @@ T2V_API int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end
   CHK(g_chains.init());
   CHK(g_chains.fork(stream));
   float* parts_dec = s->parts + 16LL * s->B * 4 * H;         // second half of the split-K workspace
+  const bool side = !attn_legacy_mode();
+  cudaStream_t sl = g_chains.s3;
+  if (side) {                                                 // location term of the first step
+    T2V_CUDA_CHECK(cudaStreamWaitEvent(sl, g_chains.ev[2], 0));
+    CHK(fwd_step_loc(s, t_begin, sl));
+    T2V_CUDA_CHECK(cudaEventRecord(g_chains.ev[5 + (t_begin & 1)], sl));
+  }
   for (int t = t_begin; t < t_end; ++t) {
-    CHK(fwd_step_att(s, &P, t, s->parts, stream));
+    CHK(fwd_step_att(s, &P, t, s->parts, stream, side ? g_chains.ev[5 + (t & 1)] : nullptr));
     T2V_CUDA_CHECK(cudaEventRecord(g_chains.ev[t & 1], stream));
     T2V_CUDA_CHECK(cudaStreamWaitEvent(g_chains.s2, g_chains.ev[t & 1], 0));
     CHK(fwd_step_dec(s, &P, t, parts_dec, g_chains.s2));
+    if (side && t + 1 < t_end) {                              // next step's location term, under its GEMM / cell / query
+      T2V_CUDA_CHECK(cudaStreamWaitEvent(sl, g_chains.ev[t & 1], 0));
+      CHK(fwd_step_loc(s, t + 1, sl));
+      T2V_CUDA_CHECK(cudaEventRecord(g_chains.ev[5 + ((t + 1) & 1)], sl));
+    }
   }
   CHK(g_chains.join(stream));
+  if (side) {
+    T2V_CUDA_CHECK(cudaEventRecord(g_chains.ev[4], sl));
+    T2V_CUDA_CHECK(cudaStreamWaitEvent(stream, g_chains.ev[4], 0));
+  }
   return 0;
 }
 

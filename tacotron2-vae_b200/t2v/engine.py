@@ -556,7 +556,7 @@ def alloc_decoder_buffers(B, Ti, To, dev, save=True):
                CA=_zeros((To + 1) * B, 1024, device=dev), CD=_zeros((To + 1) * B, 1024, device=dev),
                CUM=_zeros((To + 1) * B, Ti, device=dev), align=_zeros(B, To, Ti, device=dev),
                parts=_empty(32 * B * 4096, device=dev), qparts=_empty(8 * B * 128, device=dev),
-               ebuf=_empty(B, Ti, device=dev))
+               ebuf=_empty(B * Ti, 129, device=dev))
     if save:
         buf.update(GA=_empty(To * B, 4096, device=dev), GD=_empty(To * B, 4096, device=dev),
                    CPA=_empty(To * B, 1024, device=dev), CPD=_empty(To * B, 1024, device=dev),

@@ -220,19 +220,24 @@ def test_attention_v2_matches_v1(L, Ti):
     lens = torch.tensor([Ti, Ti - 7, Ti // 2, 33, 9], device=dev)
     wconvT = wconv.reshape(32, 62).t().contiguous()
     out = {}
-    for ver in (1, 2):
+    for ver in (1, 2, 3):
         w = torch.zeros(B, Ti, device=dev); cumo = torch.zeros(B, Ti, device=dev)
         c1 = torch.zeros(B, 512, device=dev); c2 = torch.zeros(B, 512, device=dev); a = torch.zeros(B, Ti, 128, device=dev)
         if ver == 1:
             L("t2v_attn_step_fwd", q, 1, 0, wprev, Ti, cum, cumo, pmem, mem, wconv, wloc, v, lens, -float("inf"), w, Ti, c1, 512,
               c2, 512, a, B, Ti, 0)
-        else:
+        elif ver == 2:
             e = torch.empty(B, Ti, device=dev)
             L("t2v_attn2_fwd", q, 1, 0, wprev, Ti, cum, cumo, pmem, mem, wconvT, wloc, v, lens, -float("inf"), e, w, Ti, c1, 512,
               c2, 512, a, B, Ti, 0)
+        else:       # location term precomputed off the recurrence + the query-dependent row kernel
+            pre = torch.empty(B, Ti, 128, device=dev)
+            L("t2v_attn3_loc_fwd", wprev, Ti, cum, pmem, wconvT, wloc, pre, B, Ti)
+            L("t2v_attn3_row_fwd", q, 1, 0, pre, cum, cumo, mem, v, lens, -float("inf"), w, Ti, c1, 512, c2, 512, a, B, Ti, 0)
         out[ver] = (w, cumo, c1, c2, a)
-    for x, y in zip(out[1], out[2]):
-        assert torch.allclose(x, y, atol=2e-6, rtol=1e-5)
+    for ver in (2, 3):
+        for x, y in zip(out[1], out[ver]):
+            assert torch.allclose(x, y, atol=2e-6, rtol=1e-5)
     w, _, _, _, a_save = out[1]
     # backward
     d1, d2, d3 = r(B, 512), r(B, 512), r(B, 512)
