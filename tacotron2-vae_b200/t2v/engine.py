@@ -40,6 +40,45 @@ SITE_ENC, SITE_PRENET, SITE_POST, SITE_EPS = 0, 3, 20, 30          # dropout RNG
 _ctypes = _lib.ctypes
 
 
+_SIDE = {}
+_OVERLAP = __import__("os").environ.get("T2V_OVERLAP", "1") != "0"
+
+
+class _Branch(object):
+    """`with _Branch(i):` runs the block on side stream i, ordered after everything already enqueued on the current stream
+    (a parallel branch of the train-step CUDA graph when captured); `.join()` makes the current stream wait for it.
+    Tensors created inside belong to the side stream's allocator pool; every later use of a side stream starts with a
+    new fork, so block reuse stays stream-ordered.  T2V_OVERLAP=0 runs everything in order on one stream."""
+
+    def __init__(self, idx):
+        self.main = torch.cuda.current_stream()
+        if _OVERLAP:
+            key = (self.main.device_index, idx)
+            if key not in _SIDE:
+                _SIDE[key] = torch.cuda.Stream(device=self.main.device)
+            self.side = _SIDE[key]
+        else:
+            self.side = None
+        self._ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(self.main)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+            self._ctx = None
+        return False
+
+    def join(self):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+
+
 def _p(t, off_elems=0):
     """raw device pointer (int) of tensor `t` advanced by off_elems fp32 elements"""
     return t.data_ptr() + 4 * off_elems
@@ -604,7 +643,7 @@ def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, dro
 
 
 def decoder_backward(ops, P, dO, ctx, dev, grads):
-    """dO [To*B,84] grad wrt the mel|gate rows.  Returns dmemory [B,Ti,512]."""
+    """dO [To*B,84] grad wrt the mel|gate rows.  Returns (dmemory [B,Ti,512], the weight-gradient branch to join)."""
     B, Ti, To, W, buf = ctx["B"], ctx["Ti"], ctx["To"], ctx["W"], ctx["buf"]
     n = To * B
     XA, XD = buf["XA"], buf["XD"]
@@ -641,58 +680,63 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
         setattr(D, k, v.data_ptr())
     L("t2v_decoder_bwd_steps", D, To, 0)
     _trace("  bwd decoder loop")
-    # batched weight gradients over all steps
-    gWa = _zeros(4096, 1792, device=dev)
-    ops.linear_dw(t["DGA"], 4096, XA, 1792, gWa, 1792, n, 4096, 1792, device=dev)
-    gWd = _zeros(4096, 2560, device=dev)
-    ops.linear_dw(t["DGD"], 4096, XD, 2560, gWd, 2560, n, 4096, 2560, device=dev)
-    grads[_D + "attention_rnn.weight_ih"] = gWa[:, :768].contiguous()
-    grads[_D + "attention_rnn.weight_hh"] = gWa[:, 768:].contiguous()
-    grads[_D + "decoder_rnn.weight_ih"] = gWd[:, :1536].contiguous()
-    grads[_D + "decoder_rnn.weight_hh"] = gWd[:, 1536:].contiguous()
-    gba = _colsum(t["DGA"], n, 4096, 1, 0, 1, dev)
-    gbd = _colsum(t["DGD"], n, 4096, 1, 0, 1, dev)
-    grads[_D + "attention_rnn.bias_ih"], grads[_D + "attention_rnn.bias_hh"] = gba, gba.clone()
-    grads[_D + "decoder_rnn.bias_ih"], grads[_D + "decoder_rnn.bias_hh"] = gbd, gbd.clone()
-    gWq = _zeros(128, 1024, device=dev)
-    ops.linear_dw(t["DQ"], 128, XD, 2560, gWq, 1024, n, 128, 1024, device=dev)
-    grads[_A + "query_layer.linear_layer.weight"] = gWq
-    for name, part, cols in ((_A + "v.linear_layer.weight", t["dv_part"], 128),
-                             (_A + "location_layer.location_dense.linear_layer.weight", t["dwloc_part"], 128 * 32),
-                             (_A + "location_layer.location_conv.conv.weight", t["dwconv_part"], 32 * 2 * 31)):
-        g = _empty(cols, device=dev)
-        L("t2v_sum_rows_per_batch", part, g, 1, B * nck, cols, 0.0)
-        if name.endswith("location_conv.conv.weight"):          # partials are kept in the [2*31, 32] layout
-            gt = _empty(cols, device=dev)
-            L("t2v_transpose", g, 32, gt, 62, 62, 32, 0)
-            g = gt
-        grads[name] = g.view_as(P[name])
-    _trace("  bwd decoder dW")
-    # prenet backward (model.py:91-102)
-    dP2pre = _empty(n, 256, device=dev)
-    L("t2v_relu_drop_bwd", ctx["P2pre"], t["DXA"], 1792, dP2pre, n, 256, ctx["m1"], ctx["seed"], SITE_PRENET + 1, 0.5, 0, ops.R)
-    g2 = _zeros(256, 256, device=dev)
-    ops.linear_dw(dP2pre, 256, ctx["P1"], 256, g2, 256, n, 256, 256, device=dev)
-    grads[_D + "prenet.layers.1.linear_layer.weight"] = g2
-    dP1 = _empty(n, 256, device=dev)
-    ops.linear_dx(dP2pre, 256, P[_D + "prenet.layers.1.linear_layer.weight"], 256, dP1, 256, n, 256, 256)
-    dP1pre = _empty(n, 256, device=dev)
-    L("t2v_relu_drop_bwd", ctx["P1pre"], dP1, 256, dP1pre, n, 256, ctx["m0"], ctx["seed"], SITE_PRENET, 0.5, 0, ops.R)
-    g1 = _zeros(256, 80, device=dev)
-    ops.linear_dw(dP1pre, 256, ctx["Fr"], 80, g1, 80, n, 256, 80, device=dev)
-    grads[_D + "prenet.layers.0.linear_layer.weight"] = g1
-    # memory_layer backward; dmemory = dmem(ctx path) + dpmem @ W_m
-    Wm = P[_A + "memory_layer.linear_layer.weight"]
-    gWm = _zeros(128, 512, device=dev)
     if ops.tc:
         L("t2v_round_tf32", t["dpmem"], t["dpmem"].numel())
-    ops.linear_dw(t["dpmem"], 128, ctx["memory"], 512, gWm, 512, B * Ti, 128, 512, device=dev)
-    grads[_A + "memory_layer.linear_layer.weight"] = gWm
+    # every weight gradient of the decoder is off the path to d(memory): a side branch, joined by the caller after the
+    # encoder backward
+    br = _Branch(0)
+    br.keep = (t, D)                                     # the branch reads these after this function returns
+    with br:
+        # batched weight gradients over all steps
+        gWa = _zeros(4096, 1792, device=dev)
+        ops.linear_dw(t["DGA"], 4096, XA, 1792, gWa, 1792, n, 4096, 1792, device=dev)
+        gWd = _zeros(4096, 2560, device=dev)
+        ops.linear_dw(t["DGD"], 4096, XD, 2560, gWd, 2560, n, 4096, 2560, device=dev)
+        grads[_D + "attention_rnn.weight_ih"] = gWa[:, :768].contiguous()
+        grads[_D + "attention_rnn.weight_hh"] = gWa[:, 768:].contiguous()
+        grads[_D + "decoder_rnn.weight_ih"] = gWd[:, :1536].contiguous()
+        grads[_D + "decoder_rnn.weight_hh"] = gWd[:, 1536:].contiguous()
+        gba = _colsum(t["DGA"], n, 4096, 1, 0, 1, dev)
+        gbd = _colsum(t["DGD"], n, 4096, 1, 0, 1, dev)
+        grads[_D + "attention_rnn.bias_ih"], grads[_D + "attention_rnn.bias_hh"] = gba, gba.clone()
+        grads[_D + "decoder_rnn.bias_ih"], grads[_D + "decoder_rnn.bias_hh"] = gbd, gbd.clone()
+        gWq = _zeros(128, 1024, device=dev)
+        ops.linear_dw(t["DQ"], 128, XD, 2560, gWq, 1024, n, 128, 1024, device=dev)
+        grads[_A + "query_layer.linear_layer.weight"] = gWq
+        for name, part, cols in ((_A + "v.linear_layer.weight", t["dv_part"], 128),
+                                 (_A + "location_layer.location_dense.linear_layer.weight", t["dwloc_part"], 128 * 32),
+                                 (_A + "location_layer.location_conv.conv.weight", t["dwconv_part"], 32 * 2 * 31)):
+            g = _empty(cols, device=dev)
+            L("t2v_sum_rows_per_batch", part, g, 1, B * nck, cols, 0.0)
+            if name.endswith("location_conv.conv.weight"):          # partials are kept in the [2*31, 32] layout
+                gt = _empty(cols, device=dev)
+                L("t2v_transpose", g, 32, gt, 62, 62, 32, 0)
+                g = gt
+            grads[name] = g.view_as(P[name])
+        _trace("  bwd decoder dW")
+        # prenet backward (model.py:91-102)
+        dP2pre = _empty(n, 256, device=dev)
+        L("t2v_relu_drop_bwd", ctx["P2pre"], t["DXA"], 1792, dP2pre, n, 256, ctx["m1"], ctx["seed"], SITE_PRENET + 1, 0.5, 0, ops.R)
+        g2 = _zeros(256, 256, device=dev)
+        ops.linear_dw(dP2pre, 256, ctx["P1"], 256, g2, 256, n, 256, 256, device=dev)
+        grads[_D + "prenet.layers.1.linear_layer.weight"] = g2
+        dP1 = _empty(n, 256, device=dev)
+        ops.linear_dx(dP2pre, 256, P[_D + "prenet.layers.1.linear_layer.weight"], 256, dP1, 256, n, 256, 256)
+        dP1pre = _empty(n, 256, device=dev)
+        L("t2v_relu_drop_bwd", ctx["P1pre"], dP1, 256, dP1pre, n, 256, ctx["m0"], ctx["seed"], SITE_PRENET, 0.5, 0, ops.R)
+        g1 = _zeros(256, 80, device=dev)
+        ops.linear_dw(dP1pre, 256, ctx["Fr"], 80, g1, 80, n, 256, 80, device=dev)
+        grads[_D + "prenet.layers.0.linear_layer.weight"] = g1
+        Wm = P[_A + "memory_layer.linear_layer.weight"]
+        gWm = _zeros(128, 512, device=dev)
+        ops.linear_dw(t["dpmem"], 128, ctx["memory"], 512, gWm, 512, B * Ti, 128, 512, device=dev)
+        grads[_A + "memory_layer.linear_layer.weight"] = gWm
     # d(memory)[b,ti,:] = sum_t w_t[b,ti] * dctx_t[b,:]  (one batched GEMM over the saved alignments)  + dpmem @ W_m
+    Wm = P[_A + "memory_layer.linear_layer.weight"]
     dmem = _empty(B * Ti, 512, device=dev)
     L("t2v_gemm_f32", buf["align"], 1, Ti, t["DCTX"], 1, B * 512, dmem, 512, Ti, 512, To, 1.0, 0.0, None, B, To * Ti, 512, Ti * 512)
     ops.linear_dx(t["dpmem"], 128, Wm, 512, dmem, 512, B * Ti, 128, 512, accumulate=True)
-    return dmem.view(B, Ti, 512)
+    return dmem.view(B, Ti, 512), br
 
 
 # ======================================================================================================= postnet + outputs
@@ -716,13 +760,17 @@ def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=No
     c.B, c.Ti, c.To, c.training, c.seed, c.rand = B, Ti, To, training, seed, rand
     g = (lambda name: None) if rand is None else (lambda name: getattr(rand, name))
     _trace("")
+    # the reference encoder / VAE head only needs the mel: it runs beside the text encoder (both are chains of small kernels)
+    br = _Branch(0)
+    with br:
+        eps = g("eps")
+        if training and eps is None:
+            eps = torch.empty(B, P["vae_gst.fc1.weight"].shape[0], device=dev, dtype=F32)
+            L("t2v_randn", eps, eps.numel(), seed, SITE_EPS)
+        style, mulv, z, c.vae = vae_forward(ops, P, mel_tgt, training, eps, dev)
     HoutP, c.enc = encoder_forward(ops, P, text, in_len, training, g("enc"), seed, dev, packed=True)
-    eps = g("eps")
-    if training and eps is None:
-        eps = torch.empty(B, P["vae_gst.fc1.weight"].shape[0], device=dev, dtype=F32)
-        L("t2v_randn", eps, eps.numel(), seed, SITE_EPS)
-    style, mulv, z, c.vae = vae_forward(ops, P, mel_tgt, training, eps, dev)
-    _trace("fwd vae/ref-encoder")
+    br.join()
+    _trace("fwd encoder + vae/ref-encoder")
     memory = _empty(B, Ti, 512, device=dev)
     L("t2v_unpad_add", HoutP, style, memory, B, Ti, 512, ops.R)                  # model.py:536-537
     O, align, c.dec = decoder_forward(ops, P, memory, mel_tgt, in_len, training, g("prenet"), g("dec"), seed, mask_value, dev)
@@ -767,12 +815,17 @@ def backward_train(ops, P, c, dmel, dpost, dgate, dmu, dlogvar):
     L("t2v_bct_to_padded", dpost, dres, B, 80, To, 1.0)
     dO = _empty(To * B, 84, device=dev)
     L("t2v_padded_to_rows_tb", dX0, dres, dgate, dO, 84, B, 80, To, ops.R)
-    dmem = decoder_backward(ops, P, dO, c.dec, dev, grads)
+    dmem, br_dw = decoder_backward(ops, P, dO, c.dec, dev, grads)
     _trace("bwd decoder")
     dstyle = _empty(B, 512, device=dev)
     L("t2v_sum_rows_per_batch", dmem, dstyle, B, Ti, 512, 0.0)
-    vae_backward(ops, P, dstyle, dmu, dlogvar, c.vae, dev, grads)
-    _trace("bwd vae/ref-encoder")
+    # three independent tails: decoder weight gradients (branch started in decoder_backward), VAE / reference encoder,
+    # text encoder
+    br_vae = _Branch(1)
+    with br_vae:
+        vae_backward(ops, P, dstyle, dmu, dlogvar, c.vae, dev, grads)
     encoder_backward(ops, P, dmem, c.enc, c.training, c.seed, dev, grads)
-    _trace("bwd encoder")
+    br_vae.join()
+    br_dw.join()
+    _trace("bwd encoder + vae/ref-encoder + decoder dW")
     return grads
