@@ -11,6 +11,8 @@
 #include "gemm_tc.h"
 #include "../../include/t2v_b200.h"
 
+int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);   // decoder_persist.cu
+
 namespace {
 
 constexpr int H = 1024, XA_W = 1792, XD_W = 2560, AD = 128, ED = 512, PD = 256;
@@ -236,6 +238,11 @@ __global__ void stop_flags_kernel(const float* __restrict__ O, long long ld, int
 T2V_API int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream) {
   T2V_ARG_CHECK(s && s->B > 0 && s->Ti > 0 && s->To > 0, "shape");
   T2V_ARG_CHECK(t_begin >= 0 && t_end <= s->To && t_begin <= t_end, "step range");
+  if (!getenv("T2V_STEP_PROFILE")) {
+    // the whole loop as one persistent kernel (decoder_persist.cu) when the problem fits it; 1 = not applicable
+    const int r = t2v_decoder_fwd_persist(s, t_begin, t_end, stream);
+    if (r != 1) return r;
+  }
   FwdPlans P;
   CHK(make_fwd_plans(s, &P));
   g_prof.begin(t_begin, t_end);

@@ -1,0 +1,752 @@
+// Persistent teacher-forced decoder loop (reference Decoder.forward / Decoder.decode, model.py:346-426) as ONE kernel:
+// 128 CTAs (32 clusters of 4, one CTA per SM) stay resident for all To steps; nothing is launched per step.
+//
+//   * weights never depend on the recurrence, so a producer thread per CTA streams this CTA's slice of
+//     [W_attention_rnn | W_decoder_rnn] (fp32 storage, tf32 math) through a TMA ring continuously, running ahead of the
+//     recurrence by the ring depth; the activation operand follows through a second ring as soon as the device-wide
+//     counters say that h_att / ctx / h_dec of the step exist.
+//   * GEMM decomposition: cluster c owns hidden units [32c, 32c+32) (the 128 gate rows i,f,g,o of those units = the UMMA
+//     M dimension, weights are the A operand), the batch (<= 64) is the UMMA N dimension, and the 4 CTAs of the cluster
+//     split K.  The four partial accumulators (TMEM) are exchanged through distributed shared memory (each CTA ends up
+//     with 16 batch rows x 32 units x 4 gates), summed, and the LSTM cell (+ dropout on h and c, model.py:361-364) runs on
+//     them directly: gates never touch global memory except as the saved activations of the backward pass.
+//   * the query projection is folded into the cell epilogue (per-cluster partial sums over its 32 units, summed by the
+//     consumer), the location term of the attention (conv 2->32 k31 + dense 32->128 + processed memory) is computed
+//     while the GEMM of the same step runs, and energies / softmax / context follow as soon as h_att is complete:
+//     two CTAs per utterance, energies exchanged through DSMEM, context columns split between them.
+//   * the decoder_rnn GEMM of step t-1 is interleaved behind the attention_rnn GEMM of step t on the same tensor pipe
+//     (it feeds nothing back under teacher forcing), so it overlaps the attention phase.
+//   * synchronisation: three monotonic device-wide counters (h_att, ctx, h_dec complete for step t) with release /
+//     acquire semantics; mbarriers inside the CTA / cluster.  Every wait is bounded (trap instead of hanging the GPU).
+#include "t2v_common.cuh"
+#include <stdlib.h>
+#include <type_traits>
+#include "gemm_tc.h"
+#include "../../include/t2v_b200.h"
+
+namespace {
+
+constexpr int H = 1024, XA_W = 1792, XD_W = 2560, AD = 128, ED = 512, PD = 256;
+constexpr int NF = 32, KS = 31, HALO = 15;
+constexpr unsigned SITE_ATT_H = 10, SITE_ATT_C = 11, SITE_DEC_H = 12, SITE_DEC_C = 13;
+constexpr int CL = 4, NCLUSTER = 32, NCTA = CL * NCLUSTER;
+constexpr int NTHREADS = 512;
+constexpr int NW = 4, NA = 4;                  // ring depths (weights 16 KB / stage, activations 8 KB / stage)
+constexpr int W_STAGE = 128 * 128, A_STAGE = 64 * 128;
+constexpr int ATT_CHUNKS = 14, DEC_CHUNKS = 20; // 32-wide K chunks per CTA: (64 + 128 + 256) / 32 and (256 + 128 + 256) / 32
+constexpr int SLOT = 4 * 16 * 32;              // floats of one exchange slot: [gate][batch row of the owner][unit]
+constexpr int TH_MAX = 64;                     // text positions per CTA (two CTAs per utterance) -> Ti <= 128
+constexpr int PADW = 160;                      // alignment / cumulative-alignment rows with a 15-wide zero halo
+constexpr int BAR_EPI = 1, BAR_ATT = 2;
+
+// ---- shared memory carve-up (bytes from the 1024-aligned base)
+constexpr int OFF_WRING = 0;
+constexpr int OFF_ARING = OFF_WRING + NW * W_STAGE;
+constexpr int OFF_RECV = OFF_ARING + NA * A_STAGE;                  // [2 gemms][4 sources][SLOT]
+constexpr int OFF_S = OFF_RECV + 2 * 4 * SLOT * 4;                  // [TH_MAX][128] location term + processed memory
+constexpr int OFF_F = OFF_S + TH_MAX * AD * 4;                      // [TH_MAX][33] conv output; aliased: ctx partials [4][256]
+constexpr int OFF_WCT = OFF_F + TH_MAX * 33 * 4;                    // [62][32]
+constexpr int OFF_HQ = OFF_WCT + 2 * KS * NF * 4;                   // [16][32] h_att of this CTA's rows (query partials)
+constexpr int OFF_WPAD = OFF_HQ + 16 * 32 * 4;
+constexpr int OFF_CPAD = OFF_WPAD + PADW * 4;
+constexpr int OFF_E = OFF_CPAD + PADW * 4;                          // [128] energies
+constexpr int OFF_Q = OFF_E + 128 * 4;                              // [2][128]
+constexpr int OFF_BARS = OFF_Q + 256 * 4;
+constexpr int N_BARS = 2 * NW + 2 * NA + 7;
+constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded spins: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU box
+constexpr long long WAIT_LIMIT = 4000000000LL;     // ~2 s of SM clocks
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) { if (clock64() - t0 > WAIT_LIMIT) __trap(); }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) { if (clock64() - t0 > WAIT_LIMIT) __trap(); }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 B apart (SBO); LBO unused (=1)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version for sm_100
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// device-wide monotonic counter: wait until *p >= target (bounded: ~2 s of SM clocks)
+__device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target) {
+  if (ld_acquire_u32(p) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_u32(p) < target) {
+    if (clock64() - t0 > WAIT_LIMIT) __trap();
+  }
+}
+// all prior global writes of the CTA's participating threads (ordered before this thread by a CTA barrier) become
+// visible device-wide before the increment
+__device__ __forceinline__ void signal_counter(unsigned* p) {
+  __threadfence();
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+struct PersistParams {
+  T2VDecoderSeq s;
+  int t_begin, t_end;
+  unsigned* counters;      // [0] h_att complete, [32] ctx complete, [64] h_dec complete (one 128-byte line each)
+  float* qpart;            // [2][NCLUSTER][B][128] per-cluster partial query projections
+};
+
+// K offset (columns of the weight matrix = columns of the activation row) of chunk j of this CTA's K slice.
+//   attention_rnn row XA[t] = [prenet_t (256) | ctx_{t-1} (512) | h_att_{t-1} (1024)]: prenet chunks first (known long
+//   before), then h_att (complete one attention phase earlier), then ctx (the last thing to become ready).
+__device__ __forceinline__ int att_kofs(int j, int rank) {
+  if (j < 2) return 64 * rank + 32 * j;
+  if (j < 10) return PD + ED + 256 * rank + 32 * (j - 2);
+  return PD + 128 * rank + 32 * (j - 10);
+}
+//   decoder_rnn row XD[t] = [h_att_t (1024) | ctx_t (512) | h_dec_{t-1} (1024)]
+__device__ __forceinline__ int dec_kofs(int j, int rank) {
+  if (j < 8) return 256 * rank + 32 * j;
+  if (j < 12) return H + 128 * rank + 32 * (j - 8);
+  return H + ED + 256 * rank + 32 * (j - 12);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_constant__ CUtensorMap tmWd,
+                       const __grid_constant__ CUtensorMap tmXA, const __grid_constant__ CUtensorMap tmXD,
+                       const PersistParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wring = smem + OFF_WRING;
+  uint8_t* aring = smem + OFF_ARING;
+  float* recv = (float*)(smem + OFF_RECV);
+  float* S = (float*)(smem + OFF_S);
+  float* fbuf = (float*)(smem + OFF_F);
+  float* wcT = (float*)(smem + OFF_WCT);
+  float* hq = (float*)(smem + OFF_HQ);
+  float* wpad = (float*)(smem + OFF_WPAD);
+  float* cpad = (float*)(smem + OFF_CPAD);
+  float* e_s = (float*)(smem + OFF_E);
+  float* q_s = (float*)(smem + OFF_Q);
+  uint64_t* bars = (uint64_t*)(smem + OFF_BARS);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = w_full + NW;
+  uint64_t* a_full = w_empty + NW;
+  uint64_t* a_empty = a_full + NA;
+  uint64_t* acc_full = a_empty + NA;      // [2]
+  uint64_t* acc_free = acc_full + 2;      // [2]
+  uint64_t* recv_full = acc_free + 2;     // [2]
+  uint64_t* e_full = recv_full + 2;       // [1]
+  uint32_t* tmem_holder = (uint32_t*)(smem + OFF_TMEM);
+
+  const T2VDecoderSeq& s = p.s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cid = blockIdx.x / CL;
+  const int B = s.B, Ti = s.Ti, To = s.To;
+  const int tb = p.t_begin, te = p.t_end;
+  unsigned* cnt_h = p.counters;
+  unsigned* cnt_c = p.counters + 32;
+  unsigned* cnt_d = p.counters + 64;
+
+  if (tid == 0) {
+    for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_free[i], 128);
+      mbar_init(&recv_full[i], 4 * 128);
+    }
+    mbar_init(e_full, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                 "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  cluster_sync_all();            // every CTA's barriers exist before any remote arrive / store
+
+  if (warp == 0) {
+    // =========================================================================== weight producer
+    if (lane == 0) {
+      uint32_t iw = 0;
+      auto load_w = [&](const CUtensorMap* tm, int kofs) {
+        const int st = iw % NW;
+        const uint32_t ph = (iw / NW) & 1u;
+        mbar_wait(&w_empty[st], ph ^ 1u);
+        mbar_expect_tx(&w_full[st], W_STAGE);
+        uint8_t* dst = wring + st * W_STAGE;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)     // gate rows i,f,g,o of this cluster's 32 hidden units -> 128 consecutive tile rows
+          tma_load_2d_hint(dst + g * 4096, tm, kofs, g * H + 32 * cid, &w_full[st], 0x14F0000000000000ull);
+        ++iw;
+      };
+      for (int t = tb; t <= te; ++t) {
+        if (t < te) for (int j = 0; j < ATT_CHUNKS; ++j) load_w(&tmWa, att_kofs(j, rank));
+        if (t > tb) for (int j = 0; j < DEC_CHUNKS; ++j) load_w(&tmWd, dec_kofs(j, rank));
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================================== activation producer
+    if (lane == 0) {
+      uint32_t ia = 0;
+      unsigned seen_h = 0, seen_c = 0, seen_d = 0;
+      auto need = [&](const unsigned* cnt, unsigned& seen, unsigned target) {
+        if (seen >= target) return;
+        wait_counter(cnt, target);
+        seen = target;
+        fence_proxy_async();          // the rows were written with generic-proxy stores, TMA reads them through the async proxy
+      };
+      auto load_a = [&](const CUtensorMap* tm, int kofs, int row0) {
+        const int st = ia % NA;
+        const uint32_t ph = (ia / NA) & 1u;
+        mbar_wait(&a_empty[st], ph ^ 1u);
+        mbar_expect_tx(&a_full[st], A_STAGE);
+        tma_load_2d(aring + st * A_STAGE, tm, kofs, row0, &a_full[st]);
+        ++ia;
+      };
+      for (int t = tb; t <= te; ++t) {
+        const unsigned n = (unsigned)(t - tb);
+        if (t < te) {
+          for (int j = 0; j < ATT_CHUNKS; ++j) {
+            if (j >= 10) need(cnt_c, seen_c, NCTA * n);
+            else if (j >= 2) need(cnt_h, seen_h, NCTA * n);
+            load_a(&tmXA, att_kofs(j, rank), t * B);
+          }
+        }
+        if (t > tb) {
+          for (int j = 0; j < DEC_CHUNKS; ++j) {
+            if (j < 8) need(cnt_h, seen_h, NCTA * n);
+            else if (j < 12) need(cnt_c, seen_c, NCTA * n);
+            else need(cnt_d, seen_d, NCTA * (n - 1));
+            load_a(&tmXD, dec_kofs(j, rank), (t - 1) * B);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // =========================================================================== MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, K-major both, N=64 (batch), M=128 (gate rows)
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t ic = 0;
+      auto gemm = [&](int which, int nch, unsigned idx) {
+        mbar_wait(&acc_free[which], (idx & 1u) ^ 1u);      // the epilogue has drained the previous accumulator
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + (uint32_t)(which * 64);
+        for (int j = 0; j < nch; ++j) {
+          const int sw = ic % NW, sa = ic % NA;
+          const uint32_t phw = (ic / NW) & 1u, pha = (ic / NA) & 1u;
+          mbar_wait(&w_full[sw], phw);
+          mbar_wait(&a_full[sa], pha);
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(wring + sw * W_STAGE));
+          const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(aring + sa * A_STAGE));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&w_empty[sw]);
+          tc_commit(&a_empty[sa]);
+          ++ic;
+        }
+        tc_commit(&acc_full[which]);
+      };
+      for (int t = tb; t <= te; ++t) {
+        const unsigned n = (unsigned)(t - tb);
+        if (t < te) gemm(0, ATT_CHUNKS, n);
+        if (t > tb) gemm(1, DEC_CHUNKS, n - 1);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =========================================================================== epilogue: exchange + LSTM cells
+    const int etid = tid - 128;
+    const int q = warp & 3;                 // TMEM lane quarter = gate index of the rows this thread drains
+    const int u = lane;                     // hidden unit within the cluster's 32
+    const int jg = 32 * cid + u;            // global hidden unit
+    const int blq = etid >> 5;              // cell phase: this thread owns batch rows bl = blq + 4*j (j<4) of unit u
+    const int rnd = s.use_tc;
+    uint32_t recv_remote[4], full_remote[2][4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      recv_remote[d] = mapa(smem_u32(recv), (uint32_t)d);
+      full_remote[0][d] = mapa(smem_u32(&recv_full[0]), (uint32_t)d);
+      full_remote[1][d] = mapa(smem_u32(&recv_full[1]), (uint32_t)d);
+    }
+    float wq[32];                           // query_layer weight [a = etid][this cluster's 32 units]
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(s.Wq + (long long)etid * H + 32 * cid + i);
+      wq[i] = w4.x; wq[i + 1] = w4.y; wq[i + 2] = w4.z; wq[i + 3] = w4.w;
+    }
+    float bias_a[4], bias_d[4], c_att[4], c_dec[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      bias_a[g] = s.ba1[g * H + jg] + s.ba2[g * H + jg];
+      bias_d[g] = s.bd1[g * H + jg] + s.bd2[g * H + jg];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = 16 * rank + blq + 4 * j;
+      c_att[j] = (b < B) ? s.CA[((long long)tb * B + b) * H + jg] : 0.f;
+      c_dec[j] = (b < B) ? s.CD[((long long)tb * B + b) * H + jg] : 0.f;
+    }
+    const uint64_t seed = (s.training && !s.drop_masks) ? t2v_resolve_seed(s.seed) : 0ull;
+    const float p_att = s.training ? s.p_att : 0.f, p_dec = s.training ? s.p_dec : 0.f;
+
+    auto epilogue = [&](auto which_c, const int ts, const unsigned idx) {
+      constexpr int which = decltype(which_c)::value;      // compile-time: keeps the per-GEMM register arrays in registers
+      mbar_wait(&acc_full[which], idx & 1u);
+      tc_fence_after();
+      // ---- drain TMEM: this thread holds D[gate q, unit u][batch 0..63]; batch rows 16d..16d+15 go to cluster rank d
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(which * 64 + half * 32), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int d = half * 2 + (i >> 4);
+          const uint32_t off = (uint32_t)((((which * 4 + rank) * 4 + q) * 16 + (i & 15)) * 32 + u) * 4u;
+          st_cluster_f32(recv_remote[d] + off, __uint_as_float(v[i]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_free[which]);
+#pragma unroll
+      for (int d = 0; d < 4; ++d) mbar_arrive_cluster(full_remote[which][d]);
+      mbar_wait_cluster(&recv_full[which], idx & 1u);
+      // ---- LSTM cell (model.py:357-364 / 375-381) on (unit u, batch rows blq + 4j)
+      const float* bias = which ? bias_d : bias_a;
+      float* cst = which ? c_dec : c_att;
+      const float pdrop = which ? p_dec : p_att;
+      const float kscale = 1.f / (1.f - pdrop);
+      const long long r0 = (long long)ts * B, r1 = (long long)(ts + 1) * B;
+      const float* mk = s.drop_masks ? s.drop_masks + (long long)ts * 4 * B * H + (which ? 2LL * B * H : 0) : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int bl = blq + 4 * j;
+        const int b = 16 * rank + bl;
+        float g4[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float* rp = recv + (which * 4 * 4 + g) * 16 * 32 + bl * 32 + u;
+          g4[g] = ((rp[0] + rp[SLOT]) + (rp[2 * SLOT] + rp[3 * SLOT])) + bias[g];
+        }
+        const float ig = t2v_sigmoid_fast(g4[0]), fg = t2v_sigmoid_fast(g4[1]), gg = t2v_tanh(g4[2]), og = t2v_sigmoid_fast(g4[3]);
+        const float c2 = fg * cst[j] + ig * gg;
+        const float h2 = og * t2v_tanh(c2);
+        float kh = 1.f, kc = 1.f;
+        if (pdrop > 0.f && b < B) {
+          const uint64_t li = (uint64_t)b * H + jg;
+          if (mk) { kh = mk[li] * kscale; kc = mk[(long long)B * H + li] * kscale; }
+          else {
+            const uint64_t di = (uint64_t)ts * B * H + li;
+            kh = (t2v_uniform(seed, which ? SITE_DEC_H : SITE_ATT_H, di) >= pdrop ? 1.f : 0.f) * kscale;
+            kc = (t2v_uniform(seed, which ? SITE_DEC_C : SITE_ATT_C, di) >= pdrop ? 1.f : 0.f) * kscale;
+          }
+        }
+        const float hd = t2v_rnd(h2 * kh, rnd);
+        const float cd = c2 * kc;
+        cst[j] = cd;
+        if (which == 0) hq[bl * 32 + u] = hd;
+        if (b < B) {
+          if (which == 0) {
+            s.XA[(r1 + b) * XA_W + (PD + ED) + jg] = hd;       // h_att -> next step's recurrent input
+            s.XD[(r0 + b) * XD_W + jg] = hd;                   // h_att -> decoder_rnn input / deferred dW operand
+            s.CA[(r1 + b) * H + jg] = cd;
+            if (s.GA) {
+              float* gs = s.GA + (r0 + b) * 4 * H + jg;
+              __stcs(gs, ig); __stcs(gs + H, fg); __stcs(gs + 2 * H, gg); __stcs(gs + 3 * H, og);
+            }
+            if (s.CPA) __stcs(s.CPA + (r0 + b) * H + jg, c2);
+          } else {
+            s.XD[(r1 + b) * XD_W + (H + ED) + jg] = hd;        // h_dec -> next step's recurrent input
+            s.CD[(r1 + b) * H + jg] = cd;
+            if (s.GD) {
+              float* gs = s.GD + (r0 + b) * 4 * H + jg;
+              __stcs(gs, ig); __stcs(gs + H, fg); __stcs(gs + 2 * H, gg); __stcs(gs + 3 * H, og);
+            }
+            if (s.CPD) __stcs(s.CPD + (r0 + b) * H + jg, c2);
+          }
+        }
+      }
+      if (which == 0) {
+        // ---- partial query projection over this cluster's 32 units for this CTA's 16 batch rows: thread = attention dim a
+        named_bar(BAR_EPI, 128);
+        float* qp = p.qpart + ((long long)((ts & 1) * NCLUSTER + cid) * B) * AD + etid;
+#pragma unroll 4
+        for (int bl = 0; bl < 16; ++bl) {
+          const float4* hp = reinterpret_cast<const float4*>(hq + bl * 32);
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 h4 = hp[i];
+            a0 = fmaf(wq[4 * i], h4.x, a0); a1 = fmaf(wq[4 * i + 1], h4.y, a1);
+            a2 = fmaf(wq[4 * i + 2], h4.z, a2); a3 = fmaf(wq[4 * i + 3], h4.w, a3);
+          }
+          const int b = 16 * rank + bl;
+          if (b < B) qp[(long long)b * AD] = (a0 + a1) + (a2 + a3);
+        }
+      }
+      named_bar(BAR_EPI, 128);
+      if (etid == 0) signal_counter(which ? cnt_d : cnt_h);
+    };
+    for (int t = tb; t <= te; ++t) {
+      const unsigned n = (unsigned)(t - tb);
+      if (t < te) epilogue(std::integral_constant<int, 0>{}, t, n);
+      if (t > tb) epilogue(std::integral_constant<int, 1>{}, t - 1, n - 1);
+    }
+  } else if (warp >= 8) {
+    // =========================================================================== attention (two CTAs per utterance)
+    const int atid = tid - 256, aw = warp - 8;
+    const int b = 2 * cid + (rank >> 1), hh = rank & 1;
+    const bool active = b < B;
+    const int Th = (Ti + 1) >> 1;
+    const int i0 = hh * Th;
+    const int nrow = hh ? (Ti - Th) : Th;
+    const int rnd = s.use_tc;
+    int len = Ti;
+    if (active && s.in_lens) { const long long l = s.in_lens[b]; len = l < Ti ? (int)l : Ti; }
+    const int a = atid & 127;
+    float wl[NF];                            // location_dense weight row of attention dim a
+#pragma unroll
+    for (int c = 0; c < NF; c += 4) {
+      const float4 t4 = *reinterpret_cast<const float4*>(s.Wloc + a * NF + c);
+      wl[c] = t4.x; wl[c + 1] = t4.y; wl[c + 2] = t4.z; wl[c + 3] = t4.w;
+    }
+    float vreg[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) vreg[k] = s.v[lane + 32 * k];
+    for (int i = atid; i < 2 * KS * NF; i += 256) wcT[i] = s.Wconv[i];
+    for (int i = atid; i < PADW; i += 256) {
+      const int ti = i - HALO;
+      float w0 = 0.f, c0 = 0.f;
+      if (active && ti >= 0 && ti < Ti) {
+        if (tb > 0) w0 = s.align[((long long)b * To + (tb - 1)) * Ti + ti];
+        c0 = s.CUM[((long long)tb * B + b) * Ti + ti];
+      }
+      wpad[i] = w0; cpad[i] = c0;
+    }
+    const uint32_t partner_e = mapa(smem_u32(e_s), (uint32_t)(rank ^ 1));
+    const uint32_t partner_full = mapa(smem_u32(e_full), (uint32_t)(rank ^ 1));
+    named_bar(BAR_ATT, 256);
+
+    for (int t = tb; t < te; ++t) {
+      const unsigned n = (unsigned)(t - tb);
+      if (active) {
+        // ---- location conv (2 -> 32, k = 31, zero padding) on this CTA's rows: thread = (filter c, 8 consecutive rows)
+        {
+          const int c = atid & 31, r0 = (atid >> 5) * 8;
+          if (r0 < nrow) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              const float* src = (ch ? cpad : wpad) + i0 + r0;
+              float xr[8 + KS - 1];
+#pragma unroll
+              for (int j = 0; j < 8 + KS - 1; ++j) xr[j] = src[j];
+#pragma unroll
+              for (int k = 0; k < KS; ++k) {
+                const float w = wcT[(ch * KS + k) * NF + c];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, xr[j + k], acc[j]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fbuf[(r0 + j) * 33 + c] = acc[j];
+          }
+        }
+        named_bar(BAR_ATT, 256);
+        // ---- location dense + processed memory: thread = (attention dim a, 32 rows)
+        {
+          const int rbeg = (atid >> 7) * 32;
+          const float* pm = s.pmem + ((long long)b * Ti + i0) * AD + a;
+#pragma unroll 4
+          for (int rr = rbeg; rr < rbeg + 32; ++rr) {
+            if (rr < nrow) {
+              float s0 = __ldg(pm + (long long)rr * AD), s1 = 0.f, s2 = 0.f, s3 = 0.f;
+              const float* fr = fbuf + rr * 33;
+#pragma unroll
+              for (int c = 0; c < NF; c += 4) {
+                s0 = fmaf(fr[c], wl[c], s0); s1 = fmaf(fr[c + 1], wl[c + 1], s1);
+                s2 = fmaf(fr[c + 2], wl[c + 2], s2); s3 = fmaf(fr[c + 3], wl[c + 3], s3);
+              }
+              S[rr * AD + a] = (s0 + s1) + (s2 + s3);
+            }
+          }
+        }
+        named_bar(BAR_ATT, 256);
+      }
+      // ---- h_att_t (and every cluster's partial query) complete device-wide
+      if (atid == 0) wait_counter(cnt_h, NCTA * (n + 1));
+      named_bar(BAR_ATT, 256);
+      if (active) {
+        // ---- query = sum of the 32 per-cluster partials
+        {
+          const int half = atid >> 7;
+          const float* qp = p.qpart + ((long long)((t & 1) * NCLUSTER + half * 16) * B + b) * AD + a;
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; k += 2) {
+            acc0 += __ldcg(qp + (long long)k * B * AD);
+            acc1 += __ldcg(qp + (long long)(k + 1) * B * AD);
+          }
+          q_s[half * 128 + a] = acc0 + acc1;
+        }
+        named_bar(BAR_ATT, 256);
+        float qv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) qv[k] = q_s[lane + 32 * k] + q_s[128 + lane + 32 * k];
+        // ---- energies of this CTA's rows (warp per row), mirrored into the partner CTA
+        float* asave = s.ASAVE ? s.ASAVE + (((long long)t * B + b) * Ti + i0) * AD : nullptr;
+        for (int rr = aw; rr < nrow; rr += 8) {
+          float x = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float av = t2v_tanh(qv[k] + S[rr * AD + lane + 32 * k]);
+            if (asave) __stcs(asave + (long long)rr * AD + lane + 32 * k, av);
+            x = fmaf(vreg[k], av, x);
+          }
+          x = warp_sum(x);
+          if (lane == 0) {
+            const float e = (i0 + rr < len) ? x : s.mask_value;
+            e_s[i0 + rr] = e;
+            st_cluster_f32(partner_e + (uint32_t)(i0 + rr) * 4u, e);
+          }
+        }
+        if (lane == 0) mbar_arrive_cluster(partner_full);
+        mbar_wait_cluster(e_full, n & 1u);
+        named_bar(BAR_ATT, 256);
+        // ---- softmax over all Ti positions (one warp; Ti <= 128), cumulative weights
+        if (aw == 0) {
+          float ev[4], m = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = lane + 32 * k;
+            ev[k] = (i < Ti) ? e_s[i] : -INFINITY;
+            m = fmaxf(m, ev[k]);
+          }
+          m = warp_max(m);
+          float ssum = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = lane + 32 * k;
+            ev[k] = (i < Ti) ? expf(ev[k] - m) : 0.f;
+            ssum += ev[k];
+          }
+          ssum = warp_sum(ssum);
+          const float inv = 1.f / ssum;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = lane + 32 * k;
+            if (i < Ti) {
+              const float w = ev[k] * inv;
+              const float cn = cpad[HALO + i] + w;
+              wpad[HALO + i] = w;
+              cpad[HALO + i] = cn;
+              if (hh == 0) {
+                s.align[((long long)b * To + t) * Ti + i] = w;
+                s.CUM[((long long)(t + 1) * B + b) * Ti + i] = cn;
+              }
+            }
+          }
+        }
+        named_bar(BAR_ATT, 256);
+        // ---- context columns [256 hh, 256 hh + 256): thread = (4 columns, every 4th text position)
+        {
+          const int cg = atid & 63, rg = atid >> 6;
+          const float* mb = s.mem + (long long)b * Ti * ED + 256 * hh + 4 * cg;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int base = rg; base < Ti; base += 32) {
+            float4 mv[8];
+            float wi[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const int ti = base + 4 * r;
+              wi[r] = (ti < Ti) ? wpad[HALO + ti] : 0.f;
+              mv[r] = (wi[r] != 0.f) ? __ldg(reinterpret_cast<const float4*>(mb + (long long)ti * ED))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              acc.x = fmaf(wi[r], mv[r].x, acc.x); acc.y = fmaf(wi[r], mv[r].y, acc.y);
+              acc.z = fmaf(wi[r], mv[r].z, acc.z); acc.w = fmaf(wi[r], mv[r].w, acc.w);
+            }
+          }
+          *reinterpret_cast<float4*>(fbuf + rg * 256 + 4 * cg) = acc;
+        }
+        named_bar(BAR_ATT, 256);
+        {
+          const float c = t2v_rnd((fbuf[atid] + fbuf[256 + atid]) + (fbuf[512 + atid] + fbuf[768 + atid]), rnd);
+          const int col = 256 * hh + atid;
+          s.XD[((long long)t * B + b) * XD_W + H + col] = c;              // ctx_t -> decoder_rnn input
+          s.XA[((long long)(t + 1) * B + b) * XA_W + PD + col] = c;      // ctx_t -> next attention_rnn input
+        }
+      }
+      named_bar(BAR_ATT, 256);
+      if (atid == 0) signal_counter(cnt_c);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();            // no CTA of the cluster exits while a peer may still address its shared memory
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+bool persist_enabled() {      // read per call: the tests flip T2V_PERSIST to compare against the per-step launches
+  const char* e = getenv("T2V_PERSIST");
+  return !(e && e[0] == '0');
+}
+
+}  // namespace
+
+int t2v_encode_tmap_2d(CUtensorMap* map, const void* base, int esize, long long inner, long long rows,
+                       long long row_stride_elems, int box_rows);
+
+// Returns 0 when the loop was enqueued, 1 when the persistent kernel does not apply to this problem (the caller then
+// uses the per-step launches), anything else = error.
+int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream) {
+  if (!persist_enabled()) return 1;
+  if (!s->use_tc || s->B > 64 || s->Ti > 2 * TH_MAX || s->Ti < 1 || t_end - t_begin < 2) return 1;
+  if (!s->parts || !s->ebuf) return 1;
+  static int max_clusters = -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(NCTA); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, dec_persist_fwd_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    max_clusters = n;
+  }
+  if (max_clusters < NCLUSTER) return 1;       // all 128 CTAs must be co-resident (they wait on each other)
+
+  PersistParams p;
+  p.s = *s;
+  p.t_begin = t_begin; p.t_end = t_end;
+  p.counters = reinterpret_cast<unsigned*>(s->ebuf);
+  p.qpart = s->parts;
+  CUtensorMap tmWa, tmWd, tmXA, tmXD;
+  const long long rows = (long long)(s->To + 1) * s->B;
+  int r;
+  if ((r = t2v_encode_tmap_2d(&tmWa, s->Wa, 4, XA_W, 4 * H, XA_W, 32))) return r;
+  if ((r = t2v_encode_tmap_2d(&tmWd, s->Wd, 4, XD_W, 4 * H, XD_W, 32))) return r;
+  if ((r = t2v_encode_tmap_2d(&tmXA, s->XA, 4, XA_W, rows, XA_W, 64))) return r;
+  if ((r = t2v_encode_tmap_2d(&tmXD, s->XD, 4, XD_W, rows, XD_W, 64))) return r;
+  T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 96 * sizeof(unsigned), stream));
+  T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel, tmWa, tmWd, tmXA, tmXD, p));
+  T2V_COUNT_LAUNCH();
+  return 0;
+}

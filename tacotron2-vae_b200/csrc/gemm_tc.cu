@@ -312,6 +312,11 @@ int encode_2d(CUtensorMap* map, const void* base, int esize, long long inner, lo
 
 }  // namespace
 
+int t2v_encode_tmap_2d(CUtensorMap* map, const void* base, int esize, long long inner, long long rows,
+                       long long row_stride_elems, int box_rows) {
+  return encode_2d(map, base, esize, inner, rows, row_stride_elems, box_rows);
+}
+
 // D[M,N] = alpha * sum_{tap,k} A[a_row0 + m + tap*a_tap_rowshift, a_k0 + k] * B[b_row0 + n, b_k0 + tap*b_tap_stride + k] (+ bias[n])
 //   A: `a_rows` x `a_inner` elements, row stride lda; B: `b_rows` rows of `b_inner` elements, row stride ldb.
 //   esize 4 => fp32 storage / tf32 math, esize 2 => bf16.  splits>1: partial sums go to D + z*split_stride

@@ -279,3 +279,40 @@ def test_gemm_tc_m64_tile(L, M):
     L("t2v_gemm_tc", A, K, M + 70, K, Bw, K, N, K, parts, N, None, M, N, K, 1, 0, 0, 0, 0, 4, 4, M * N, 0, 1.0, 128)
     ref = (A.double() @ Bw.double().t()).float()
     assert _rel(parts.sum(0), ref) < 2e-3
+
+
+@pytest.mark.parametrize("B,Ti,To,training", [(5, 23, 12, True), (64, 120, 24, True), (16, 128, 9, False), (1, 7, 5, True)])
+def test_persistent_decoder_loop_matches_per_step_launches(L, B, Ti, To, training):
+    """decoder_persist.cu (one resident kernel for the whole teacher-forced loop) against the per-step launch sequence of
+    decoder.cu on the same inputs / same counter RNG: mel+gate rows, alignments and every saved activation.  Both paths
+    round the same operands to tf32 and accumulate in fp32; only the split-K summation order differs: tolerance 2e-4 of
+    the buffer's max, and one tf32 ulp (2^-10) for XA / XD, whose h / ctx columns are stored rounded to the tf32 grid."""
+    import os
+    from oracle import port
+    from t2v import engine
+    dev = torch.device("cuda")
+    P = {k: v.to(dev) for k, v in port.init_params(1234).items()}
+    ops = engine.Ops("tf32")
+    g = torch.Generator().manual_seed(B * 1000 + Ti)
+    memory = (torch.randn(B, Ti, 512, generator=g) * 0.5).to(dev)
+    mel = (torch.randn(B, 80, To, generator=g) * 2 - 5).to(dev)
+    in_len = torch.randint(max(1, Ti // 2), Ti + 1, (B,), generator=g).sort(descending=True)[0]
+    in_len[0] = Ti
+    in_len = in_len.to(dev)
+    outs = {}
+    for mode in ("0", "1"):
+        os.environ["T2V_PERSIST"] = mode
+        try:
+            O, align, ctx = engine.decoder_forward(ops, P, memory, mel, in_len, training, None, None, 77, -float("inf"), dev)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("T2V_PERSIST", None)
+        buf = ctx["buf"]
+        outs[mode] = dict(O=O.clone(), align=align.clone(), **{k: buf[k].clone() for k in
+                          ("XA", "XD", "CA", "CD", "CUM", "GA", "GD", "CPA", "CPD", "ASAVE")})
+    for k in outs["0"]:
+        a, b = outs["1"][k], outs["0"][k]
+        assert torch.isfinite(a).all(), k
+        err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+        print("persistent vs per-step %-6s max-rel %.3e" % (k, err))
+        assert err <= (1.5e-3 if k in ("XA", "XD") else 2e-4), (k, err)
