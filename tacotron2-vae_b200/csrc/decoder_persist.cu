@@ -44,15 +44,16 @@ constexpr int OFF_WRING = 0;
 constexpr int OFF_ARING = OFF_WRING + NW * W_STAGE;
 constexpr int OFF_RECV = OFF_ARING + NA * A_STAGE;                  // [2 gemms][4 sources][SLOT]
 constexpr int OFF_S = OFF_RECV + 2 * 4 * SLOT * 4;                  // [TH_MAX][128] location term + processed memory
-constexpr int OFF_F = OFF_S + TH_MAX * AD * 4;                      // [TH_MAX][33] conv output; aliased: ctx partials [4][256]
-constexpr int OFF_WCT = OFF_F + TH_MAX * 33 * 4;                    // [62][32]
+constexpr int FS = 36;                                              // row stride of the conv output (16-byte aligned rows)
+constexpr int OFF_F = OFF_S + TH_MAX * AD * 4;                      // [TH_MAX][FS] conv output; aliased: ctx partials [4][256]
+constexpr int OFF_WCT = OFF_F + TH_MAX * FS * 4;                    // [62][32]
 constexpr int OFF_HQ = OFF_WCT + 2 * KS * NF * 4;                   // [16][32] h_att of this CTA's rows (query partials)
 constexpr int OFF_WPAD = OFF_HQ + 16 * 32 * 4;
 constexpr int OFF_CPAD = OFF_WPAD + PADW * 4;
 constexpr int OFF_E = OFF_CPAD + PADW * 4;                          // [128] energies
 constexpr int OFF_Q = OFF_E + 128 * 4;                              // [2][128]
 constexpr int OFF_BARS = OFF_Q + 256 * 4;
-constexpr int N_BARS = 2 * NW + 2 * NA + 7;
+constexpr int N_BARS = 2 * NW + 2 * NA + 8;
 constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
 
@@ -66,9 +67,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -157,8 +155,20 @@ __device__ __forceinline__ uint32_t mapa(uint32_t cta_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+// DSMEM stores that carry their own completion: the bytes are counted on an mbarrier of the destination CTA, so neither a
+// remote arrive nor a release fence (which would also wait for this thread's outstanding global stores) is needed
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t cluster_bar, float a, float b, float c, float d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void st_async_f32(uint32_t cluster_addr, uint32_t cluster_bar, float a) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
+               ::"r"(cluster_addr), "f"(a), "r"(cluster_bar) : "memory");
+}
+// 1-D bulk copy global -> this CTA's shared memory, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -189,7 +199,9 @@ struct PersistParams {
   int t_begin, t_end;
   unsigned* counters;      // [0] h_att complete, [32] ctx complete, [64] h_dec complete (one 128-byte line each)
   float* qpart;            // [2][NCLUSTER][B][128] per-cluster partial query projections
+  long long* trace;        // T2V_PERSIST_TRACE: [2 CTAs][TRACE_STEPS][32] clock64 stamps, else nullptr
 };
+constexpr int TRACE_T0 = 100, TRACE_STEPS = 4, TRACE_CTA_B = 77;
 
 // K offset (columns of the weight matrix = columns of the activation row) of chunk j of this CTA's K slice.
 //   attention_rnn row XA[t] = [prenet_t (256) | ctx_{t-1} (512) | h_att_{t-1} (1024)]: prenet chunks first (known long
@@ -232,6 +244,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   uint64_t* acc_free = acc_full + 2;      // [2]
   uint64_t* recv_full = acc_free + 2;     // [2]
   uint64_t* e_full = recv_full + 2;       // [1]
+  uint64_t* s_full = e_full + 1;          // [1] processed-memory tile landed in S
   uint32_t* tmem_holder = (uint32_t*)(smem + OFF_TMEM);
 
   const T2VDecoderSeq& s = p.s;
@@ -243,6 +256,12 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   unsigned* cnt_h = p.counters;
   unsigned* cnt_c = p.counters + 32;
   unsigned* cnt_d = p.counters + 64;
+  // debug time stamps of a few mid-sequence steps (two CTAs); compiled in, one predictable branch per event when off
+  const int trace_slot = (blockIdx.x == 0) ? 0 : ((blockIdx.x == TRACE_CTA_B) ? 1 : -1);
+  auto TR = [&](unsigned n, int ev) {
+    if (p.trace && trace_slot >= 0 && n >= (unsigned)TRACE_T0 && n < (unsigned)(TRACE_T0 + TRACE_STEPS))
+      p.trace[((long long)trace_slot * TRACE_STEPS + (n - TRACE_T0)) * 32 + ev] = clock64();
+  };
 
   if (tid == 0) {
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
@@ -250,9 +269,10 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_free[i], 128);
-      mbar_init(&recv_full[i], 4 * 128);
+      mbar_init(&recv_full[i], 1);          // one expect_tx arrive per phase; the data arrives as st.async bytes
     }
-    mbar_init(e_full, 8);
+    mbar_init(e_full, 1);
+    mbar_init(s_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -282,8 +302,9 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         ++iw;
       };
       for (int t = tb; t <= te; ++t) {
-        if (t < te) for (int j = 0; j < ATT_CHUNKS; ++j) load_w(&tmWa, att_kofs(j, rank));
+        if (t < te) for (int j = 0; j < ATT_CHUNKS; ++j) { load_w(&tmWa, att_kofs(j, rank)); if (j == 0) TR(t - tb, 24); }
         if (t > tb) for (int j = 0; j < DEC_CHUNKS; ++j) load_w(&tmWd, dec_kofs(j, rank));
+        TR(t - tb, 25);
       }
     }
   } else if (warp == 1) {
@@ -311,8 +332,11 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           for (int j = 0; j < ATT_CHUNKS; ++j) {
             if (j >= 10) need(cnt_c, seen_c, NCTA * n);
             else if (j >= 2) need(cnt_h, seen_h, NCTA * n);
+            if (j == 2) TR(n, 0);
+            if (j == 10) TR(n, 1);
             load_a(&tmXA, att_kofs(j, rank), t * B);
           }
+          TR(n, 2);
         }
         if (t > tb) {
           for (int j = 0; j < DEC_CHUNKS; ++j) {
@@ -321,6 +345,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
             else need(cnt_d, seen_d, NCTA * (n - 1));
             load_a(&tmXD, dec_kofs(j, rank), (t - 1) * B);
           }
+          TR(n, 3);
         }
       }
     }
@@ -340,6 +365,8 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           mbar_wait(&w_full[sw], phw);
           mbar_wait(&a_full[sa], pha);
           tc_fence_after();
+          if (which == 0 && j == 0) TR(idx, 4);
+          if (which == 0 && j == 10) TR(idx, 5);
           const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(wring + sw * W_STAGE));
           const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(aring + sa * A_STAGE));
 #pragma unroll
@@ -350,6 +377,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           ++ic;
         }
         tc_commit(&acc_full[which]);
+        TR(which ? idx + 1 : idx, which ? 7 : 6);
       };
       for (int t = tb; t <= te; ++t) {
         const unsigned n = (unsigned)(t - tb);
@@ -397,23 +425,48 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       constexpr int which = decltype(which_c)::value;      // compile-time: keeps the per-GEMM register arrays in registers
       mbar_wait(&acc_full[which], idx & 1u);
       tc_fence_after();
-      // ---- drain TMEM: this thread holds D[gate q, unit u][batch 0..63]; batch rows 16d..16d+15 go to cluster rank d
+      const unsigned tn = which ? idx + 1 : idx;       // trace row = the step during which this epilogue runs
+      if (etid == 0) {
+        mbar_expect_tx(&recv_full[which], 4 * SLOT * 4);   // four 8 KB slots (own included) land as st.async bytes
+        TR(tn, which ? 14 : 8);
+      }
+      // ---- drain TMEM: this thread holds D[gate q, unit u][batch 0..63]; batch rows 16d..16d+15 go to cluster rank d.
+      // A 4x4 transpose inside every lane quad turns "one unit, 4 batch rows" into "one batch row, 4 units", so the
+      // exchange is 16-byte DSMEM stores that cover whole 128-byte rows of the [gate][batch row][unit] slot.
+      {
+        const int r4 = lane & 3, m4 = lane >> 2;
+        const uint32_t slot_off = (uint32_t)(((which * 4 + rank) * 4 + q) * 16 * 32 + 4 * m4) * 4u;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(which * 64 + half * 32), v);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(which * 64 + half * 32), v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int d = half * 2 + (i >> 4);
-          const uint32_t off = (uint32_t)((((which * 4 + rank) * 4 + q) * 16 + (i & 15)) * 32 + u) * 4u;
-          st_cluster_f32(recv_remote[d] + off, __uint_as_float(v[i]));
+          for (int k = 0; k < 8; ++k) {
+            float a0 = __uint_as_float(v[4 * k]), a1 = __uint_as_float(v[4 * k + 1]);
+            float a2 = __uint_as_float(v[4 * k + 2]), a3 = __uint_as_float(v[4 * k + 3]);
+            {
+              const bool odd = (r4 & 1) != 0;
+              const float y0 = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
+              const float y1 = __shfl_xor_sync(0xffffffffu, odd ? a2 : a3, 1);
+              if (odd) { a0 = y0; a2 = y1; } else { a1 = y0; a3 = y1; }
+            }
+            {
+              const bool hi = (r4 & 2) != 0;
+              const float y0 = __shfl_xor_sync(0xffffffffu, hi ? a0 : a2, 2);
+              const float y1 = __shfl_xor_sync(0xffffffffu, hi ? a1 : a3, 2);
+              if (hi) { a0 = y0; a1 = y1; } else { a2 = y0; a3 = y1; }
+            }
+            // now a_j = D[gate q, unit 4*m4 + j][batch half*32 + 4k + r4]
+            const int d = half * 2 + (k >> 2);             // destination rank (compile-time), batch row 4*(k&3) + r4 of its 16
+            st_async_v4(recv_remote[d] + slot_off + (uint32_t)((4 * (k & 3) + r4) * 32) * 4u, full_remote[which][d], a0, a1, a2, a3);
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(&acc_free[which]);
-#pragma unroll
-      for (int d = 0; d < 4; ++d) mbar_arrive_cluster(full_remote[which][d]);
+      if (etid == 0 && which == 0) TR(tn, 9);
       mbar_wait_cluster(&recv_full[which], idx & 1u);
+      if (etid == 0 && which == 0) TR(tn, 10);
       // ---- LSTM cell (model.py:357-364 / 375-381) on (unit u, batch rows blq + 4j)
       const float* bias = which ? bias_d : bias_a;
       float* cst = which ? c_dec : c_att;
@@ -421,6 +474,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       const float kscale = 1.f / (1.f - pdrop);
       const long long r0 = (long long)ts * B, r1 = (long long)(ts + 1) * B;
       const float* mk = s.drop_masks ? s.drop_masks + (long long)ts * 4 * B * H + (which ? 2LL * B * H : 0) : nullptr;
+      float sv_i[4], sv_f[4], sv_g[4], sv_o[4], sv_c2[4];     // saved activations: written after the signal
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int bl = blq + 4 * j;
@@ -445,30 +499,19 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           }
         }
         const float hd = t2v_rnd(h2 * kh, rnd);
-        const float cd = c2 * kc;
-        cst[j] = cd;
+        cst[j] = c2 * kc;
+        sv_i[j] = ig; sv_f[j] = fg; sv_g[j] = gg; sv_o[j] = og; sv_c2[j] = c2;
         if (which == 0) hq[bl * 32 + u] = hd;
-        if (b < B) {
+        if (b < B) {       // only what other CTAs wait for goes out before the signal
           if (which == 0) {
             s.XA[(r1 + b) * XA_W + (PD + ED) + jg] = hd;       // h_att -> next step's recurrent input
             s.XD[(r0 + b) * XD_W + jg] = hd;                   // h_att -> decoder_rnn input / deferred dW operand
-            s.CA[(r1 + b) * H + jg] = cd;
-            if (s.GA) {
-              float* gs = s.GA + (r0 + b) * 4 * H + jg;
-              __stcs(gs, ig); __stcs(gs + H, fg); __stcs(gs + 2 * H, gg); __stcs(gs + 3 * H, og);
-            }
-            if (s.CPA) __stcs(s.CPA + (r0 + b) * H + jg, c2);
           } else {
             s.XD[(r1 + b) * XD_W + (H + ED) + jg] = hd;        // h_dec -> next step's recurrent input
-            s.CD[(r1 + b) * H + jg] = cd;
-            if (s.GD) {
-              float* gs = s.GD + (r0 + b) * 4 * H + jg;
-              __stcs(gs, ig); __stcs(gs + H, fg); __stcs(gs + 2 * H, gg); __stcs(gs + 3 * H, og);
-            }
-            if (s.CPD) __stcs(s.CPD + (r0 + b) * H + jg, c2);
           }
         }
       }
+      if (etid == 0 && which == 0) TR(tn, 11);
       if (which == 0) {
         // ---- partial query projection over this cluster's 32 units for this CTA's 16 batch rows: thread = attention dim a
         named_bar(BAR_EPI, 128);
@@ -488,7 +531,27 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
       }
       named_bar(BAR_EPI, 128);
+      if (etid == 0 && which == 0) TR(tn, 12);
       if (etid == 0) signal_counter(which ? cnt_d : cnt_h);
+      if (etid == 0) TR(tn, which ? 15 : 13);
+      // ---- saved activations of the backward pass + the cell state sequence (nobody inside this kernel reads them)
+      {
+        float* Gs = which ? s.GD : s.GA;
+        float* CPs = which ? s.CPD : s.CPA;
+        float* Cs = which ? s.CD : s.CA;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int b = 16 * rank + blq + 4 * j;
+          if (b < B) {
+            Cs[(r1 + b) * H + jg] = cst[j];
+            if (Gs) {
+              float* gs = Gs + (r0 + b) * 4 * H + jg;
+              __stcs(gs, sv_i[j]); __stcs(gs + H, sv_f[j]); __stcs(gs + 2 * H, sv_g[j]); __stcs(gs + 3 * H, sv_o[j]);
+            }
+            if (CPs) __stcs(CPs + (r0 + b) * H + jg, sv_c2[j]);
+          }
+        }
+      }
     };
     for (int t = tb; t <= te; ++t) {
       const unsigned n = (unsigned)(t - tb);
@@ -507,12 +570,6 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     int len = Ti;
     if (active && s.in_lens) { const long long l = s.in_lens[b]; len = l < Ti ? (int)l : Ti; }
     const int a = atid & 127;
-    float wl[NF];                            // location_dense weight row of attention dim a
-#pragma unroll
-    for (int c = 0; c < NF; c += 4) {
-      const float4 t4 = *reinterpret_cast<const float4*>(s.Wloc + a * NF + c);
-      wl[c] = t4.x; wl[c + 1] = t4.y; wl[c + 2] = t4.z; wl[c + 3] = t4.w;
-    }
     float vreg[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) vreg[k] = s.v[lane + 32 * k];
@@ -530,9 +587,24 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     const uint32_t partner_full = mapa(smem_u32(e_full), (uint32_t)(rank ^ 1));
     named_bar(BAR_ATT, 256);
 
+    float qv[4] = {0.f, 0.f, 0.f, 0.f};
     for (int t = tb; t < te; ++t) {
       const unsigned n = (unsigned)(t - tb);
       if (active) {
+        // the partner's energies of this step arrive as st.async bytes on e_full
+        if (atid == 0) mbar_expect_tx(e_full, (uint32_t)(hh ? Th : Ti - Th) * 4u);
+        // ---- processed-memory rows of this CTA -> S (bulk copy, lands while the conv runs); every reader of the previous
+        // step's S passed the barrier at the end of that step
+        if (atid == 0 && nrow > 0) {
+          mbar_expect_tx(s_full, (uint32_t)nrow * AD * 4u);
+          bulk_load_1d(S, s.pmem + ((long long)b * Ti + i0) * AD, (uint32_t)nrow * AD * 4u, s_full);
+        }
+        float wl[NF];                        // location_dense weight row of attention dim a (re-read per step: the
+#pragma unroll                               // registers are needed by the context phase)
+        for (int c = 0; c < NF; c += 4) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(s.Wloc + a * NF + c));
+          wl[c] = t4.x; wl[c + 1] = t4.y; wl[c + 2] = t4.z; wl[c + 3] = t4.w;
+        }
         // ---- location conv (2 -> 32, k = 31, zero padding) on this CTA's rows: thread = (filter c, 8 consecutive rows)
         {
           const int c = atid & 31, r0 = (atid >> 5) * 8;
@@ -554,23 +626,24 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
               }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) fbuf[(r0 + j) * 33 + c] = acc[j];
+            for (int j = 0; j < 8; ++j) fbuf[(r0 + j) * FS + c] = acc[j];
           }
         }
         named_bar(BAR_ATT, 256);
-        // ---- location dense + processed memory: thread = (attention dim a, 32 rows)
+        // ---- S += location dense: thread = (attention dim a, 32 rows)
+        if (nrow > 0) mbar_wait(s_full, n & 1u);
         {
           const int rbeg = (atid >> 7) * 32;
-          const float* pm = s.pmem + ((long long)b * Ti + i0) * AD + a;
 #pragma unroll 4
           for (int rr = rbeg; rr < rbeg + 32; ++rr) {
             if (rr < nrow) {
-              float s0 = __ldg(pm + (long long)rr * AD), s1 = 0.f, s2 = 0.f, s3 = 0.f;
-              const float* fr = fbuf + rr * 33;
+              float s0 = S[rr * AD + a], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+              const float4* fr = reinterpret_cast<const float4*>(fbuf + rr * FS);     // broadcast 16-byte loads
 #pragma unroll
               for (int c = 0; c < NF; c += 4) {
-                s0 = fmaf(fr[c], wl[c], s0); s1 = fmaf(fr[c + 1], wl[c + 1], s1);
-                s2 = fmaf(fr[c + 2], wl[c + 2], s2); s3 = fmaf(fr[c + 3], wl[c + 3], s3);
+                const float4 f4 = fr[c >> 2];
+                s0 = fmaf(f4.x, wl[c], s0); s1 = fmaf(f4.y, wl[c + 1], s1);
+                s2 = fmaf(f4.z, wl[c + 2], s2); s3 = fmaf(f4.w, wl[c + 3], s3);
               }
               S[rr * AD + a] = (s0 + s1) + (s2 + s3);
             }
@@ -579,7 +652,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         named_bar(BAR_ATT, 256);
       }
       // ---- h_att_t (and every cluster's partial query) complete device-wide
-      if (atid == 0) wait_counter(cnt_h, NCTA * (n + 1));
+      if (atid == 0) { TR(n, 16); wait_counter(cnt_h, NCTA * (n + 1)); TR(n, 17); }
       named_bar(BAR_ATT, 256);
       if (active) {
         // ---- query = sum of the 32 per-cluster partials
@@ -595,29 +668,50 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           q_s[half * 128 + a] = acc0 + acc1;
         }
         named_bar(BAR_ATT, 256);
-        float qv[4];
+        if (atid == 0) TR(n, 18);
 #pragma unroll
         for (int k = 0; k < 4; ++k) qv[k] = q_s[lane + 32 * k] + q_s[128 + lane + 32 * k];
-        // ---- energies of this CTA's rows (warp per row), mirrored into the partner CTA
-        float* asave = s.ASAVE ? s.ASAVE + (((long long)t * B + b) * Ti + i0) * AD : nullptr;
-        for (int rr = aw; rr < nrow; rr += 8) {
-          float x = 0.f;
+        // ---- energies of this CTA's rows: warp aw owns rows aw + 8k (k < 8), all in flight at once; a transposing
+        // reduction (9 shuffles) leaves row aw + 8*(lane & 7) in every lane, lanes 0..7 mirror them into the partner CTA
+        {
+          float x[8];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float av = t2v_tanh(qv[k] + S[rr * AD + lane + 32 * k]);
-            if (asave) __stcs(asave + (long long)rr * AD + lane + 32 * k, av);
-            x = fmaf(vreg[k], av, x);
+          for (int k = 0; k < 8; ++k) {
+            const int rr = aw + 8 * k;
+            float acc = 0.f;
+            if (rr < nrow) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const float av = t2v_tanh(qv[kk] + S[rr * AD + lane + 32 * kk]);
+                acc = fmaf(vreg[kk], av, acc);
+              }
+            }
+            x[k] = acc;
           }
-          x = warp_sum(x);
-          if (lane == 0) {
-            const float e = (i0 + rr < len) ? x : s.mask_value;
+#pragma unroll
+          for (int sft = 4; sft >= 1; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
+#pragma unroll
+            for (int i = 0; i < sft; ++i) {
+              const float send = up ? x[i] : x[i + sft];
+              const float keep = up ? x[i + sft] : x[i];
+              x[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+            }
+          }
+          float e = x[0];
+          e += __shfl_xor_sync(0xffffffffu, e, 8);
+          e += __shfl_xor_sync(0xffffffffu, e, 16);
+          const int rr = aw + 8 * (lane & 7);
+          if (lane < 8 && rr < nrow) {
+            e = (i0 + rr < len) ? e : s.mask_value;
             e_s[i0 + rr] = e;
-            st_cluster_f32(partner_e + (uint32_t)(i0 + rr) * 4u, e);
+            st_async_f32(partner_e + (uint32_t)(i0 + rr) * 4u, partner_full, e);
           }
         }
-        if (lane == 0) mbar_arrive_cluster(partner_full);
+        if (atid == 0) TR(n, 19);
         mbar_wait_cluster(e_full, n & 1u);
         named_bar(BAR_ATT, 256);
+        if (atid == 0) TR(n, 20);
         // ---- softmax over all Ti positions (one warp; Ti <= 128), cumulative weights
         if (aw == 0) {
           float ev[4], m = -INFINITY;
@@ -653,23 +747,24 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           }
         }
         named_bar(BAR_ATT, 256);
-        // ---- context columns [256 hh, 256 hh + 256): thread = (4 columns, every 4th text position)
+        if (atid == 0) TR(n, 21);
+        // ---- context columns [256 hh, 256 hh + 256): thread = (4 columns, every 4th text position), 16 rows in flight
         {
           const int cg = atid & 63, rg = atid >> 6;
           const float* mb = s.mem + (long long)b * Ti * ED + 256 * hh + 4 * cg;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int base = rg; base < Ti; base += 32) {
-            float4 mv[8];
-            float wi[8];
+          for (int base = rg; base < Ti; base += 64) {
+            float4 mv[16];
+            float wi[16];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
+            for (int r = 0; r < 16; ++r) {
               const int ti = base + 4 * r;
               wi[r] = (ti < Ti) ? wpad[HALO + ti] : 0.f;
               mv[r] = (wi[r] != 0.f) ? __ldg(reinterpret_cast<const float4*>(mb + (long long)ti * ED))
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
+            for (int r = 0; r < 16; ++r) {
               acc.x = fmaf(wi[r], mv[r].x, acc.x); acc.y = fmaf(wi[r], mv[r].y, acc.y);
               acc.z = fmaf(wi[r], mv[r].z, acc.z); acc.w = fmaf(wi[r], mv[r].w, acc.w);
             }
@@ -677,6 +772,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           *reinterpret_cast<float4*>(fbuf + rg * 256 + 4 * cg) = acc;
         }
         named_bar(BAR_ATT, 256);
+        if (atid == 0) TR(n, 22);
         {
           const float c = t2v_rnd((fbuf[atid] + fbuf[256 + atid]) + (fbuf[512 + atid] + fbuf[768 + atid]), rnd);
           const int col = 256 * hh + atid;
@@ -685,7 +781,18 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
       }
       named_bar(BAR_ATT, 256);
-      if (atid == 0) signal_counter(cnt_c);
+      if (atid == 0) { signal_counter(cnt_c); TR(n, 23); }
+      // ---- saved tanh activations of the backward pass, recomputed off the critical path (S and the query are still here;
+      // storing them inside the energy loop would put 30 KB of global stores in front of the exchange)
+      if (active && s.ASAVE) {
+        float* asave = s.ASAVE + (((long long)t * B + b) * Ti + i0) * AD;
+        for (int rr = aw; rr < nrow; rr += 8) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            __stcs(asave + (long long)rr * AD + lane + 32 * kk, t2v_tanh(qv[kk] + S[rr * AD + lane + 32 * kk]));
+        }
+        named_bar(BAR_ATT, 256);           // S is overwritten by the next step's bulk copy
+      }
     }
   }
   tc_fence_before();
@@ -738,6 +845,13 @@ int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cuda
   p.t_begin = t_begin; p.t_end = t_end;
   p.counters = reinterpret_cast<unsigned*>(s->ebuf);
   p.qpart = s->parts;
+  p.trace = nullptr;
+  const bool trace = getenv("T2V_PERSIST_TRACE") != nullptr && (t_end - t_begin) >= TRACE_T0 + TRACE_STEPS + 2;
+  const size_t trace_bytes = 2 * TRACE_STEPS * 32 * sizeof(long long);
+  if (trace) {
+    T2V_CUDA_CHECK(cudaMalloc(&p.trace, trace_bytes));
+    T2V_CUDA_CHECK(cudaMemsetAsync(p.trace, 0, trace_bytes, stream));
+  }
   CUtensorMap tmWa, tmWd, tmXA, tmXD;
   const long long rows = (long long)(s->To + 1) * s->B;
   int r;
@@ -748,5 +862,26 @@ int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cuda
   T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 96 * sizeof(unsigned), stream));
   T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel, tmWa, tmWd, tmXA, tmXD, p));
   T2V_COUNT_LAUNCH();
+  if (trace) {      // debugging aid: not usable under stream capture
+    static const char* names[26] = {"A:h ready", "A:ctx ready", "A:att loads issued", "A:dec loads issued", "M:att first chunk",
+                                    "M:att ctx chunk", "M:att committed", "M:dec committed", "E:att acc full", "E:att pushed",
+                                    "E:att recv full", "E:att cell done", "E:att q partial done", "E:h signalled", "E:dec acc full",
+                                    "E:dec signalled", "T:loc done, wait h", "T:h seen", "T:query summed", "T:energies done",
+                                    "T:energies exchanged", "T:softmax done", "T:context partials", "T:ctx signalled",
+                                    "W:att first load", "W:step loads issued"};
+    long long h[2 * TRACE_STEPS * 32];
+    T2V_CUDA_CHECK(cudaStreamSynchronize(stream));
+    T2V_CUDA_CHECK(cudaMemcpy(h, p.trace, trace_bytes, cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    for (int c = 0; c < 2; ++c) {
+      const long long base = h[(c * TRACE_STEPS) * 32 + 1];     // "ctx ready" of the first traced step
+      fprintf(stderr, "[t2v persist trace] CTA %d: SM clocks relative to 'A:ctx ready' of step %d\n", c ? TRACE_CTA_B : 0, TRACE_T0);
+      for (int ev = 0; ev < 26; ++ev) {
+        fprintf(stderr, "  %-24s", names[ev]);
+        for (int n = 0; n < TRACE_STEPS; ++n) fprintf(stderr, " %8lld", h[(c * TRACE_STEPS + n) * 32 + ev] ? h[(c * TRACE_STEPS + n) * 32 + ev] - base : -1);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   return 0;
 }
