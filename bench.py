@@ -348,11 +348,20 @@ def decoder_step_roofline(m, hp, B, Ti, To, dev, precision):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (us * 1e-6) / 1e9
-    return {"kernel": "decoder step = gemm_tc<128,4,8,64> x3 (attention_rnn gates, query, decoder_rnn gates) + "
-                      "lstm_pointwise_fwd x2 + attn3_row (fused energy/softmax/context): 6 launches per step in two concurrent "
-                      "chains, CUDA-graph replay of Decoder.decode for all To steps",
+    persist = os.environ.get("T2V_PERSIST", "1") != "0" and precision == "tf32" and B <= 64 and Ti <= 128
+    kernel = ("dec_persist_fwd_kernel: ONE persistent launch for all To steps of Decoder.decode (128 CTAs = 32 clusters x 4; "
+              "TMA weight streaming, tcgen05 tf32 split-K over the cluster + DSMEM exchange, LSTM cells / query partials "
+              "in the epilogue, attention by CTA pairs); per-step time = kernel time / To") if persist else (
+              "decoder step = gemm_tc<128,4,8,64> x3 (attention_rnn gates, query, decoder_rnn gates) + lstm_pointwise_fwd x2 + "
+              "attn3_row (fused energy/softmax/context): 6 launches per step in two concurrent chains, CUDA-graph replay")
+    traffic = None
+    try:      # measured DRAM bytes per step of the same kernel (ncu, profiles/r01_ncu_persist_dram.json)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_persist_dram.json")))["dram_bytes_per_step"] if persist else None
+    except Exception:  # noqa: BLE001
+        pass
+    return {"kernel": kernel,
             "bound": "hbm",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "us_per_step": us, "algorithmic_bytes_per_step": alg_bytes,
             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}
 

@@ -22,6 +22,7 @@ for it in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); L("t2v_decoder_fwd_steps", S, 0, To); e1.record(); torch.cuda.synchronize()
     print("loop %d: %.2f us/step" % (it, e0.elapsed_time(e1) * 1e3 / To), flush=True)
-os.environ["T2V_PERSIST_TRACE"] = "1"
-L("t2v_decoder_fwd_steps", S, 0, To)
-torch.cuda.synchronize()
+if not os.environ.get("NOTRACE"):
+    os.environ["T2V_PERSIST_TRACE"] = "1"
+    L("t2v_decoder_fwd_steps", S, 0, To)
+    torch.cuda.synchronize()

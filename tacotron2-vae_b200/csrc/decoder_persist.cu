@@ -192,6 +192,18 @@ __device__ __forceinline__ void signal_counter(unsigned* p) {
   __threadfence();
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
+__device__ __forceinline__ uint64_t l2_policy(int kind) {      // 1: evict_last, 2: evict_first
+  uint64_t pol;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg_v4_hint(const float* ptr, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr), "l"(pol));
+  return r;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 struct PersistParams {
@@ -199,6 +211,7 @@ struct PersistParams {
   int t_begin, t_end;
   unsigned* counters;      // [0] h_att complete, [32] ctx complete, [64] h_dec complete (one 128-byte line each)
   float* qpart;            // [2][NCLUSTER][B][128] per-cluster partial query projections
+  int wa_hint, wd_hint, mem_hint;   // L2 eviction priority of the weight streams / the encoder memory: 0 normal, 1 evict_last, 2 evict_first
   long long* trace;        // T2V_PERSIST_TRACE: [2 CTAs][TRACE_STEPS][32] clock64 stamps, else nullptr
 };
 constexpr int TRACE_T0 = 100, TRACE_STEPS = 4, TRACE_CTA_B = 77;
@@ -290,20 +303,23 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     // =========================================================================== weight producer
     if (lane == 0) {
       uint32_t iw = 0;
-      auto load_w = [&](const CUtensorMap* tm, int kofs) {
+      const uint64_t pol_a = l2_policy(p.wa_hint), pol_d = l2_policy(p.wd_hint);
+      auto load_w = [&](const CUtensorMap* tm, int kofs, int hint, uint64_t pol) {
         const int st = iw % NW;
         const uint32_t ph = (iw / NW) & 1u;
         mbar_wait(&w_empty[st], ph ^ 1u);
         mbar_expect_tx(&w_full[st], W_STAGE);
         uint8_t* dst = wring + st * W_STAGE;
 #pragma unroll
-        for (int g = 0; g < 4; ++g)     // gate rows i,f,g,o of this cluster's 32 hidden units -> 128 consecutive tile rows
-          tma_load_2d_hint(dst + g * 4096, tm, kofs, g * H + 32 * cid, &w_full[st], 0x14F0000000000000ull);
+        for (int g = 0; g < 4; ++g) {   // gate rows i,f,g,o of this cluster's 32 hidden units -> 128 consecutive tile rows
+          if (hint) tma_load_2d_hint(dst + g * 4096, tm, kofs, g * H + 32 * cid, &w_full[st], pol);
+          else tma_load_2d(dst + g * 4096, tm, kofs, g * H + 32 * cid, &w_full[st]);
+        }
         ++iw;
       };
       for (int t = tb; t <= te; ++t) {
-        if (t < te) for (int j = 0; j < ATT_CHUNKS; ++j) { load_w(&tmWa, att_kofs(j, rank)); if (j == 0) TR(t - tb, 24); }
-        if (t > tb) for (int j = 0; j < DEC_CHUNKS; ++j) load_w(&tmWd, dec_kofs(j, rank));
+        if (t < te) for (int j = 0; j < ATT_CHUNKS; ++j) { load_w(&tmWa, att_kofs(j, rank), p.wa_hint, pol_a); if (j == 0) TR(t - tb, 24); }
+        if (t > tb) for (int j = 0; j < DEC_CHUNKS; ++j) load_w(&tmWd, dec_kofs(j, rank), p.wd_hint, pol_d);
         TR(t - tb, 25);
       }
     }
@@ -586,6 +602,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     const uint32_t partner_e = mapa(smem_u32(e_s), (uint32_t)(rank ^ 1));
     const uint32_t partner_full = mapa(smem_u32(e_full), (uint32_t)(rank ^ 1));
     named_bar(BAR_ATT, 256);
+    const uint64_t pol_m = l2_policy(p.mem_hint);
 
     float qv[4] = {0.f, 0.f, 0.f, 0.f};
     for (int t = tb; t < te; ++t) {
@@ -760,8 +777,9 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
             for (int r = 0; r < 16; ++r) {
               const int ti = base + 4 * r;
               wi[r] = (ti < Ti) ? wpad[HALO + ti] : 0.f;
-              mv[r] = (wi[r] != 0.f) ? __ldg(reinterpret_cast<const float4*>(mb + (long long)ti * ED))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+              mv[r] = (wi[r] == 0.f) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                     : (p.mem_hint ? ldg_v4_hint(mb + (long long)ti * ED, pol_m)
+                                                   : __ldg(reinterpret_cast<const float4*>(mb + (long long)ti * ED)));
             }
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
@@ -846,6 +864,10 @@ int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cuda
   p.counters = reinterpret_cast<unsigned*>(s->ebuf);
   p.qpart = s->parts;
   p.trace = nullptr;
+  auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+  p.wa_hint = env_int("T2V_PERSIST_WA_HINT", 1);
+  p.wd_hint = env_int("T2V_PERSIST_WD_HINT", 2);     // decoder_rnn weights stream from HBM: do not let them evict W_a / memory
+  p.mem_hint = env_int("T2V_PERSIST_MEM_HINT", 1);
   const bool trace = getenv("T2V_PERSIST_TRACE") != nullptr && (t_end - t_begin) >= TRACE_T0 + TRACE_STEPS + 2;
   const size_t trace_bytes = 2 * TRACE_STEPS * 32 * sizeof(long long);
   if (trace) {
