@@ -12,6 +12,7 @@
 #include "../../include/t2v_b200.h"
 
 int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);   // decoder_persist.cu
+int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStream_t stream);         // decoder_persist_bwd.cu
 
 namespace {
 
@@ -288,6 +289,10 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
   const T2VDecoderSeq* s = &d->f;
   T2V_ARG_CHECK(s->B > 0 && s->Ti > 0 && s->To > 0, "shape");
   T2V_ARG_CHECK(t_lo >= 0 && t_hi <= s->To && t_lo <= t_hi, "step range");
+  if (!getenv("T2V_STEP_PROFILE")) {
+    const int r = t2v_decoder_bwd_persist(d, t_hi, t_lo, st);      // the whole reverse loop as one persistent kernel; 1 = n/a
+    if (r != 1) return r;
+  }
   const bool tc = s->use_tc != 0;
   const int B = s->B, Ti = s->Ti, To = s->To;
   const float p_att = s->training ? s->p_att : 0.f, p_dec = s->training ? s->p_dec : 0.f;

@@ -1,0 +1,799 @@
+// Persistent backward of the teacher-forced decoder loop (the reverse-time recurrence of Decoder.decode, model.py:346-389)
+// as ONE kernel: 128 CTAs (32 clusters of 4) stay resident for all To steps, like decoder_persist.cu for the forward.
+//
+// Per step t (descending) the loop has two chains:
+//   decoder_rnn chain  (one step ahead, feeds nothing back into the attention chain of earlier steps except dXD[t]):
+//       D1  cell backward   dh_dec = DHC[t][:1024] + dXD[t+1][1536:]  -> DGD[t]                       (epilogue warps)
+//       D2  dXD[t] = DGD[t] W_d   (tcgen05, split-K over the cluster, DSMEM exchange)               (MMA + epilogue warps)
+//   attention chain (the critical recurrence):
+//       A1  attention backward per utterance (two CTAs, rows split): dctx -> dw -> softmax backward -> dpre -> dq,
+//           then (off the critical path) dW_loc, dW_conv, dv accumulated in registers for the whole sequence and the
+//           adjoint location conv that carries the gradient to the previous step's alignments     (attention warps)
+//       A2  dHq = dq W_q, attention_rnn cell backward -> DGA[t]                                     (epilogue warps)
+//       A3  DXA[t] = DGA[t] W_a                                                                      (MMA + epilogue warps)
+//   GEMM decomposition: cluster c owns output columns [56c, 56c+56) of DXA (UMMA M=64) and [80c, 80c+80) of dXD (M=128),
+//   the batch is N, the 4 CTAs split K = 4096 gate rows; W^T tiles stream through a TMA ring that runs ahead of the
+//   recurrence, the gate gradients follow as soon as the device-wide counters say they are complete.
+// Five monotonic device-wide counters order the phases (release / acquire); every wait is bounded.
+#include "t2v_common.cuh"
+#include <stdlib.h>
+#include <type_traits>
+#include "persist_common.cuh"
+#include "gemm_tc.h"
+#include "../../include/t2v_b200.h"
+
+namespace {
+
+constexpr int H = 1024, XA_W = 1792, XD_W = 2560, AD = 128, ED = 512, PD = 256;
+constexpr int NF = 32, KS = 31, HALO = 15;
+constexpr unsigned SITE_ATT_H = 10, SITE_ATT_C = 11, SITE_DEC_H = 12, SITE_DEC_C = 13;
+constexpr int CL = 4, NCLUSTER = 32, NCTA = CL * NCLUSTER, NTHREADS = 512;
+constexpr int XA_CPC = XA_W / NCLUSTER, XD_CPC = XD_W / NCLUSTER;   // 56 / 80 output columns per cluster
+constexpr int WU = 8192, NWU = 6;              // weight ring: 8 KB units; a DXA chunk takes 1 unit, a dXD chunk 2 (even-aligned)
+constexpr int NA = 5, A_STAGE = 64 * 128;      // gate-gradient ring (64 batch rows x 32 floats)
+constexpr int KCH = 32;                        // 32-wide K chunks per CTA and GEMM (K slice = 4096 / 4)
+constexpr int RA_P = 64, RD_P = 80;            // column pitch of the exchange slots [src][batch row 16][cols]
+constexpr int TH_MAX = 64, PADW = 160, FS = 36;
+constexpr int BAR_EPI = 1, BAR_ATT = 2;
+
+constexpr int OFF_WRING = 0;
+constexpr int OFF_ARING = OFF_WRING + NWU * WU;
+constexpr int OFF_RECVA = OFF_ARING + NA * A_STAGE;
+constexpr int OFF_RECVD = OFF_RECVA + 4 * 16 * RA_P * 4;
+constexpr int OFF_ABUF = OFF_RECVD + 4 * 16 * RD_P * 4;            // [TH_MAX][128] saved tanh -> dpre (in place)
+constexpr int OFF_F = OFF_ABUF + TH_MAX * AD * 4;                   // [TH_MAX][FS] conv output f -> df (in place)
+constexpr int OFF_WCT = OFF_F + TH_MAX * FS * 4;                    // [62][32]
+constexpr int OFF_WLOC = OFF_WCT + 2 * KS * NF * 4;                 // [128][32]
+constexpr int OFF_WQ = OFF_WLOC + AD * NF * 4;                      // [128][32] query weight columns of this cluster's units
+constexpr int OFF_DQ = OFF_WQ + AD * 32 * 4;                        // [16][128]
+constexpr int OFF_DCTX = OFF_DQ + 16 * AD * 4;                      // [512]
+constexpr int OFF_SMALL = OFF_DCTX + ED * 4;
+// small arrays (floats): wpad[160] cpad[160] wt[64] dwv[64] de[64] Ps[64] Gs[64] adj[2][64] halo[2][2][64] spart[2][2] q_s[2][128]
+constexpr int SM_WPAD = 0, SM_CPAD = 160, SM_WT = 320, SM_DWV = 384, SM_DE = 448, SM_P = 512, SM_G = 576, SM_ADJ = 640,
+              SM_HALO = 768, SM_SPART = 1024, SM_QS = 1028, SM_TOTAL = 1284;
+constexpr int OFF_BARS = OFF_SMALL + ((SM_TOTAL * 4 + 15) / 16) * 16;
+constexpr int N_BARS = 2 * NWU + 2 * NA + 9;
+constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+
+struct BwdParams {
+  T2VDecoderBwd d;
+  unsigned* counters;      // [0] DGD[t] complete, [32] dXD[t], [64] dq[t], [96] DGA[t], [128] DXA[t]
+  int wa_hint, wd_hint;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_constant__ CUtensorMap tmWd64,
+                       const __grid_constant__ CUtensorMap tmWd16, const __grid_constant__ CUtensorMap tmGA,
+                       const __grid_constant__ CUtensorMap tmGD, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wring = smem + OFF_WRING;
+  uint8_t* aring = smem + OFF_ARING;
+  float* recv_a = (float*)(smem + OFF_RECVA);
+  float* recv_d = (float*)(smem + OFF_RECVD);
+  float* Abuf = (float*)(smem + OFF_ABUF);
+  float* f_s = (float*)(smem + OFF_F);
+  float* wcT = (float*)(smem + OFF_WCT);
+  float* WlocS = (float*)(smem + OFF_WLOC);
+  float* WqS = (float*)(smem + OFF_WQ);
+  float* dq_s = (float*)(smem + OFF_DQ);
+  float* dctx_s = (float*)(smem + OFF_DCTX);
+  float* small = (float*)(smem + OFF_SMALL);
+  uint64_t* bars = (uint64_t*)(smem + OFF_BARS);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = w_full + NWU;
+  uint64_t* a_full = w_empty + NWU;
+  uint64_t* a_empty = a_full + NA;
+  uint64_t* acc_full = a_empty + NA;      // [2]: 0 = DXA GEMM, 1 = dXD GEMM
+  uint64_t* acc_free = acc_full + 2;      // [2]
+  uint64_t* recv_full = acc_free + 2;     // [2]
+  uint64_t* at_full = recv_full + 2;      // saved tanh tile landed
+  uint64_t* x_full = at_full + 1;         // partner's softmax-backward partial sum landed
+  uint64_t* h_full = x_full + 1;          // partner's adjoint-conv halo landed
+  uint32_t* tmem_holder = (uint32_t*)(smem + OFF_TMEM);
+
+  const T2VDecoderBwd& d = p.d;
+  const T2VDecoderSeq& s = d.f;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cid = blockIdx.x / CL;
+  const int B = s.B, Ti = s.Ti, To = s.To;
+  unsigned* cnt_gd = p.counters;
+  unsigned* cnt_xd = p.counters + 32;
+  unsigned* cnt_q = p.counters + 64;
+  unsigned* cnt_ga = p.counters + 96;
+  unsigned* cnt_xa = p.counters + 128;
+
+  if (tid == 0) {
+    for (int i = 0; i < NWU; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_free[i], 128);
+      mbar_init(&recv_full[i], 1);
+    }
+    mbar_init(at_full, 1);
+    mbar_init(x_full, 1);
+    mbar_init(h_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                 "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  cluster_sync_all();
+
+  // iteration `it` = -1 .. To-1: attention-chain step t = To-1-it (it >= 0), decoder_rnn-chain step td = t-1 (td >= 0)
+  if (warp == 0) {
+    // =========================================================================== weight producer
+    if (lane == 0) {
+      uint32_t us = 0;
+      const uint64_t pol_a = l2_policy(p.wa_hint), pol_d = l2_policy(p.wd_hint);
+      auto load_unit = [&](const CUtensorMap* tm, int kofs, int row, uint32_t bytes, int hint, uint64_t pol) {
+        const int u = us % NWU;
+        const uint32_t ph = (us / NWU) & 1u;
+        mbar_wait(&w_empty[u], ph ^ 1u);
+        mbar_expect_tx(&w_full[u], bytes);
+        if (hint) tma_load_2d_hint(wring + u * WU, tm, kofs, row, &w_full[u], pol);
+        else tma_load_2d(wring + u * WU, tm, kofs, row, &w_full[u]);
+        ++us;
+      };
+      for (int it = -1; it < To; ++it) {
+        const int td = To - 2 - it;
+        if (td >= 0) {
+          for (int j = 0; j < KCH; ++j) {       // 80 rows of W_d^T: 64 + 16 into two consecutive units
+            load_unit(&tmWd64, 1024 * rank + 32 * j, XD_CPC * cid, 64 * 128, p.wd_hint, pol_d);
+            load_unit(&tmWd16, 1024 * rank + 32 * j, XD_CPC * cid + 64, 16 * 128, p.wd_hint, pol_d);
+          }
+        }
+        if (it >= 0)
+          for (int j = 0; j < KCH; ++j) load_unit(&tmWa, 1024 * rank + 32 * j, XA_CPC * cid, XA_CPC * 128, p.wa_hint, pol_a);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================================== gate-gradient producer
+    if (lane == 0) {
+      uint32_t ia = 0;
+      unsigned seen_gd = 0, seen_ga = 0;
+      auto need = [&](const unsigned* cnt, unsigned& seen, unsigned target) {
+        if (seen >= target) return;
+        wait_counter(cnt, target);
+        seen = target;
+        fence_proxy_async();
+      };
+      auto load_a = [&](const CUtensorMap* tm, int kofs, int row0) {
+        const int st = ia % NA;
+        const uint32_t ph = (ia / NA) & 1u;
+        mbar_wait(&a_empty[st], ph ^ 1u);
+        mbar_expect_tx(&a_full[st], A_STAGE);
+        tma_load_2d(aring + st * A_STAGE, tm, kofs, row0, &a_full[st]);
+        ++ia;
+      };
+      for (int it = -1; it < To; ++it) {
+        const int t = To - 1 - it, td = t - 1;
+        if (td >= 0) {
+          need(cnt_gd, seen_gd, NCTA * (unsigned)(it + 2));
+          for (int j = 0; j < KCH; ++j) load_a(&tmGD, 1024 * rank + 32 * j, td * B);
+        }
+        if (it >= 0) {
+          need(cnt_ga, seen_ga, NCTA * (unsigned)(it + 1));
+          for (int j = 0; j < KCH; ++j) load_a(&tmGA, 1024 * rank + 32 * j, t * B);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // =========================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+      constexpr uint32_t idesc128 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t us = 0, ia = 0;
+      for (int it = -1; it < To; ++it) {
+        const int td = To - 2 - it;
+        if (td >= 0) {                           // dXD[td] = DGD[td] W_d : M = 128 (80 live rows), accumulator columns 64..127
+          mbar_wait(&acc_free[1], ((unsigned)(it + 1) & 1u) ^ 1u);
+          tc_fence_after();
+          for (int j = 0; j < KCH; ++j) {
+            const int u = us % NWU, sa = ia % NA;
+            const uint32_t phw = (us / NWU) & 1u, pha = (ia / NA) & 1u;
+            mbar_wait(&w_full[u], phw);
+            mbar_wait(&w_full[u + 1], phw);
+            mbar_wait(&a_full[sa], pha);
+            tc_fence_after();
+            const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(wring + u * WU));
+            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(aring + sa * A_STAGE));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_tf32(tmem_base + 64u, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc128, (j > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&w_empty[u]);
+            tc_commit(&w_empty[u + 1]);
+            tc_commit(&a_empty[sa]);
+            us += 2; ++ia;
+          }
+          tc_commit(&acc_full[1]);
+        }
+        if (it >= 0) {                           // DXA[t] = DGA[t] W_a : M = 64 (56 live rows), accumulator columns 0..63
+          mbar_wait(&acc_free[0], ((unsigned)it & 1u) ^ 1u);
+          tc_fence_after();
+          for (int j = 0; j < KCH; ++j) {
+            const int u = us % NWU, sa = ia % NA;
+            const uint32_t phw = (us / NWU) & 1u, pha = (ia / NA) & 1u;
+            mbar_wait(&w_full[u], phw);
+            mbar_wait(&a_full[sa], pha);
+            tc_fence_after();
+            const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(wring + u * WU));
+            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(aring + sa * A_STAGE));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc64, (j > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&w_empty[u]);
+            tc_commit(&a_empty[sa]);
+            ++us; ++ia;
+          }
+          tc_commit(&acc_full[0]);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =========================================================================== cells + GEMM epilogues
+    const int etid = tid - 128;
+    const int q = warp & 3;
+    const int u = lane, jg = 32 * cid + u, blq = etid >> 5;
+    const int rnd = s.use_tc;
+    uint32_t recv_remote[2][4], full_remote[2][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      recv_remote[0][r] = mapa(smem_u32(recv_a), (uint32_t)r);
+      recv_remote[1][r] = mapa(smem_u32(recv_d), (uint32_t)r);
+      full_remote[0][r] = mapa(smem_u32(&recv_full[0]), (uint32_t)r);
+      full_remote[1][r] = mapa(smem_u32(&recv_full[1]), (uint32_t)r);
+    }
+    for (int i = etid; i < AD * 32; i += 128) WqS[i] = s.Wq[(long long)(i >> 5) * H + 32 * cid + (i & 31)];
+    float dca[4], dcd[4];                    // running cell-state gradients of this thread's (unit, batch row) pairs
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = 16 * rank + blq + 4 * j;
+      dca[j] = (b < B) ? d.dCa[(long long)b * H + jg] : 0.f;
+      dcd[j] = (b < B) ? d.dCd[(long long)b * H + jg] : 0.f;
+    }
+    const uint64_t seed = (s.training && !s.drop_masks) ? t2v_resolve_seed(s.seed) : 0ull;
+    const float p_att = s.training ? s.p_att : 0.f, p_dec = s.training ? s.p_dec : 0.f;
+    unsigned seen_xd = 0, seen_xa = 0, seen_q = 0;
+    named_bar(BAR_EPI, 128);
+
+    // ---- LSTM cell backward (the math of lstm_pointwise_bwd_kernel) for step ts; which: 0 attention_rnn, 1 decoder_rnn
+    auto cell_bwd = [&](auto which_c, const int ts, const unsigned n_xd, const unsigned n_xa, const unsigned n_q) {
+      constexpr int which = decltype(which_c)::value;
+      const long long r0 = (long long)ts * B, r1 = (long long)(ts + 1) * B;
+      const bool has_next = ts + 1 < To;
+      const float* Gs = which ? s.GD : s.GA;
+      const float* CPs = which ? s.CPD : s.CPA;
+      const float* Cs = which ? s.CD : s.CA;
+      float* DG = which ? d.DGD : d.DGA;
+      float* dcs = which ? dcd : dca;
+      const float pdrop = which ? p_dec : p_att;
+      const float kscale = 1.f / (1.f - pdrop);
+      const float* mk = s.drop_masks ? s.drop_masks + (long long)ts * 4 * B * H + (which ? 2LL * B * H : 0) : nullptr;
+      // saved forward activations: independent of the recurrence, in flight while the counters are polled
+      float sg[4][4], sc2[4], scp[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int b = 16 * rank + blq + 4 * j;
+        if (b < B) {
+          const float* gs = Gs + (r0 + b) * 4 * H + jg;
+          sg[j][0] = __ldcs(gs); sg[j][1] = __ldcs(gs + H); sg[j][2] = __ldcs(gs + 2 * H); sg[j][3] = __ldcs(gs + 3 * H);
+          sc2[j] = __ldcs(CPs + (r0 + b) * H + jg);
+          scp[j] = __ldcs(Cs + (r0 + b) * H + jg);
+        } else {
+          sg[j][0] = sg[j][1] = sg[j][2] = sg[j][3] = 0.f; sc2[j] = 0.f; scp[j] = 0.f;
+        }
+      }
+      if (etid == 0) {
+        if (seen_xd < n_xd) { wait_counter(cnt_xd, n_xd); seen_xd = n_xd; }
+        if (seen_xa < n_xa) { wait_counter(cnt_xa, n_xa); seen_xa = n_xa; }
+        if (seen_q < n_q) { wait_counter(cnt_q, n_q); seen_q = n_q; }
+      }
+      named_bar(BAR_EPI, 128);
+      float dh[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int b = 16 * rank + blq + 4 * j;
+        float v = 0.f;
+        if (b < B) {
+          if (which == 0) {
+            v = __ldcg(d.DXD + (r0 + b) * XD_W + jg);
+            if (has_next) v += __ldcg(d.DXA + (r1 + b) * XA_W + (PD + ED) + jg);
+          } else {
+            v = __ldcg(d.DHC + (r0 + b) * (H + ED) + jg);
+            if (has_next) v += __ldcg(d.DXD + (r1 + b) * XD_W + (H + ED) + jg);
+          }
+        }
+        dh[j] = v;
+      }
+      if (which == 0) {
+        // ---- dHq = dq W_q for this CTA's 16 batch rows x 32 units (dq of the whole batch is complete: cnt_q)
+        for (int i = etid; i < 16 * AD; i += 128) {
+          const int b = 16 * rank + (i >> 7);
+          dq_s[i] = (b < B) ? __ldcg(d.DQ + (r0 + b) * AD + (i & 127)) : 0.f;
+        }
+        named_bar(BAR_EPI, 128);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int a0 = 0; a0 < AD; a0 += 4) {
+          const float w0 = WqS[a0 * 32 + u], w1 = WqS[(a0 + 1) * 32 + u], w2 = WqS[(a0 + 2) * 32 + u], w3 = WqS[(a0 + 3) * 32 + u];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 q4 = *reinterpret_cast<const float4*>(dq_s + (blq + 4 * j) * AD + a0);
+            acc[j] = fmaf(q4.x, w0, acc[j]); acc[j] = fmaf(q4.y, w1, acc[j]);
+            acc[j] = fmaf(q4.z, w2, acc[j]); acc[j] = fmaf(q4.w, w3, acc[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dh[j] += acc[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int b = 16 * rank + blq + 4 * j;
+        float kh = 1.f, kc = 1.f;
+        if (pdrop > 0.f && b < B) {
+          const uint64_t li = (uint64_t)b * H + jg;
+          if (mk) { kh = mk[li] * kscale; kc = mk[(long long)B * H + li] * kscale; }
+          else {
+            const uint64_t di = (uint64_t)ts * B * H + li;
+            kh = (t2v_uniform(seed, which ? SITE_DEC_H : SITE_ATT_H, di) >= pdrop ? 1.f : 0.f) * kscale;
+            kc = (t2v_uniform(seed, which ? SITE_DEC_C : SITE_ATT_C, di) >= pdrop ? 1.f : 0.f) * kscale;
+          }
+        }
+        const float ig = sg[j][0], fg = sg[j][1], gg = sg[j][2], og = sg[j][3];
+        const float dhh = dh[j] * kh;
+        const float tc = t2v_tanh(sc2[j]);
+        const float dc = dcs[j] * kc + dhh * og * (1.f - tc * tc);
+        dcs[j] = dc * fg;
+        if (b < B) {
+          float* dg = DG + (r0 + b) * 4 * H + jg;
+          dg[0] = t2v_rnd(dc * gg * ig * (1.f - ig), rnd);
+          dg[H] = t2v_rnd(dc * scp[j] * fg * (1.f - fg), rnd);
+          dg[2 * H] = t2v_rnd(dc * ig * (1.f - gg * gg), rnd);
+          dg[3 * H] = t2v_rnd(dhh * tc * og * (1.f - og), rnd);
+        }
+      }
+      named_bar(BAR_EPI, 128);
+      if (etid == 0) signal_counter(which ? cnt_gd : cnt_ga);
+    };
+
+    // ---- GEMM epilogue: drain TMEM, exchange the split-K partials (16 batch rows per rank), sum, write dX rows
+    auto gemm_epi = [&](auto which_c, const int ts, const unsigned idx) {
+      constexpr int which = decltype(which_c)::value;
+      constexpr int CP = which ? RD_P : RA_P;                  // slot column pitch
+      constexpr int NC = which ? XD_CPC : XA_CPC;              // live columns
+      if (etid == 0) mbar_expect_tx(&recv_full[which], 4u * 16u * NC * 4u);
+      mbar_wait(&acc_full[which], idx & 1u);
+      tc_fence_after();
+      {
+        const int r4 = lane & 3, m4 = lane >> 2;
+        // accumulator row (= output column) held by this lane: M=64 keeps rows 16q..16q+15 in lanes 0..15 of quarter q
+        const int col0 = which ? (32 * q + 4 * m4) : (16 * q + 4 * m4);
+        const bool live = which ? (col0 < NC) : (lane < 16 && col0 < NC);
+        const uint32_t slot_off = (uint32_t)((rank * 16) * CP + col0) * 4u;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(which * 64 + half * 32), v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float a0 = __uint_as_float(v[4 * k]), a1 = __uint_as_float(v[4 * k + 1]);
+            float a2 = __uint_as_float(v[4 * k + 2]), a3 = __uint_as_float(v[4 * k + 3]);
+            {
+              const bool odd = (r4 & 1) != 0;
+              const float y0 = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
+              const float y1 = __shfl_xor_sync(0xffffffffu, odd ? a2 : a3, 1);
+              if (odd) { a0 = y0; a2 = y1; } else { a1 = y0; a3 = y1; }
+            }
+            {
+              const bool hi = (r4 & 2) != 0;
+              const float y0 = __shfl_xor_sync(0xffffffffu, hi ? a0 : a2, 2);
+              const float y1 = __shfl_xor_sync(0xffffffffu, hi ? a1 : a3, 2);
+              if (hi) { a0 = y0; a1 = y1; } else { a2 = y0; a3 = y1; }
+            }
+            // a_j = D[column col0 + j][batch half*32 + 4k + r4]
+            const int dst = half * 2 + (k >> 2);
+            if (live)
+              st_async_v4(recv_remote[which][dst] + slot_off + (uint32_t)((4 * (k & 3) + r4) * CP) * 4u, full_remote[which][dst],
+                          a0, a1, a2, a3);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_free[which]);
+      mbar_wait_cluster(&recv_full[which], idx & 1u);
+      {
+        const float* rv = which ? recv_d : recv_a;
+        float* out = which ? d.DXD : d.DXA;
+        const int ld = which ? XD_W : XA_W;
+        constexpr int NC4 = NC / 4;
+        for (int task = etid; task < 16 * NC4; task += 128) {
+          const int bl = task / NC4, c4 = task - bl * NC4;
+          const int b = 16 * rank + bl;
+          const float* rp = rv + bl * CP + 4 * c4;
+          const float4 x0 = *reinterpret_cast<const float4*>(rp);
+          const float4 x1 = *reinterpret_cast<const float4*>(rp + 16 * CP);
+          const float4 x2 = *reinterpret_cast<const float4*>(rp + 2 * 16 * CP);
+          const float4 x3 = *reinterpret_cast<const float4*>(rp + 3 * 16 * CP);
+          float4 o;
+          o.x = (x0.x + x1.x) + (x2.x + x3.x); o.y = (x0.y + x1.y) + (x2.y + x3.y);
+          o.z = (x0.z + x1.z) + (x2.z + x3.z); o.w = (x0.w + x1.w) + (x2.w + x3.w);
+          if (b < B) *reinterpret_cast<float4*>(out + ((long long)ts * B + b) * ld + NC * cid + 4 * c4) = o;
+        }
+      }
+      named_bar(BAR_EPI, 128);
+      if (etid == 0) signal_counter(which ? cnt_xd : cnt_xa);
+    };
+
+    for (int it = -1; it < To; ++it) {
+      const int t = To - 1 - it, td = t - 1;
+      // D1(td): needs dXD[td+1] (the dXD epilogue of the previous iteration)
+      if (td >= 0) cell_bwd(std::integral_constant<int, 1>{}, td, NCTA * (unsigned)(it + 1), 0u, 0u);
+      // A2(t): needs dXD[t], DXA[t+1] and dq[t]
+      if (it >= 0) cell_bwd(std::integral_constant<int, 0>{}, t, NCTA * (unsigned)(it + 1), NCTA * (unsigned)it, NCTA * (unsigned)(it + 1));
+      if (td >= 0) gemm_epi(std::integral_constant<int, 1>{}, td, (unsigned)(it + 1));
+      if (it >= 0) gemm_epi(std::integral_constant<int, 0>{}, t, (unsigned)it);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = 16 * rank + blq + 4 * j;
+      if (b < B) { d.dCa[(long long)b * H + jg] = dca[j]; d.dCd[(long long)b * H + jg] = dcd[j]; }
+    }
+  } else if (warp >= 8) {
+    // =========================================================================== attention backward (two CTAs per utterance)
+    const int atid = tid - 256, aw = warp - 8;
+    const int b = 2 * cid + (rank >> 1), hh = rank & 1;
+    const bool active = b < B;
+    const int Th = (Ti + 1) >> 1;
+    const int i0 = hh * Th;
+    const int nrow = hh ? (Ti - Th) : Th;
+    // partner (rows of the other half) sends its adjoint-conv outputs that fall into my rows: if I own [0,Th) these are
+    // s in [Th-15, Th) clipped at 0 -> my local rows [Th-cnt, Th), cnt = min(15, Th); if I own [Th,Ti): s in [Th, Th+15)
+    // clipped at Ti -> my local rows [0, cnt), cnt = min(15, Ti-Th)
+    const int halo_cnt = hh ? min(HALO, Ti - Th) : min(HALO, Th);
+    int len = Ti;
+    if (active && s.in_lens) { const long long l = s.in_lens[b]; len = l < Ti ? (int)l : Ti; }
+    const int a = atid & 127;
+    float* wpad = small + SM_WPAD; float* cpad = small + SM_CPAD; float* wt_s = small + SM_WT; float* dwv_s = small + SM_DWV;
+    float* de_s = small + SM_DE; float* P_s = small + SM_P; float* G_s = small + SM_G; float* adj_s = small + SM_ADJ;
+    float* halo_s = small + SM_HALO; float* spart = small + SM_SPART; float* q_s = small + SM_QS;
+    const float va = s.v[a];
+    for (int i = atid; i < 2 * KS * NF; i += 256) wcT[i] = s.Wconv[i];
+    for (int i = atid; i < AD * NF; i += 256) WlocS[i] = s.Wloc[i];
+    for (int i = atid; i < SM_TOTAL; i += 256) small[i] = 0.f;
+    const uint32_t partner_spart = mapa(smem_u32(spart), (uint32_t)(rank ^ 1));
+    const uint32_t partner_x = mapa(smem_u32(x_full), (uint32_t)(rank ^ 1));
+    const uint32_t partner_halo = mapa(smem_u32(halo_s), (uint32_t)(rank ^ 1));
+    const uint32_t partner_h = mapa(smem_u32(h_full), (uint32_t)(rank ^ 1));
+    const uint64_t pol_m = l2_policy(1);
+    float gwl[16];                           // dW_loc[a][16*(atid>>7) .. +16) over this CTA's rows, all steps
+#pragma unroll
+    for (int c = 0; c < 16; ++c) gwl[c] = 0.f;
+    float wcacc[8];                          // dW_conv entries atid + 256 m, all steps
+#pragma unroll
+    for (int m = 0; m < 8; ++m) wcacc[m] = 0.f;
+    float dv_acc = 0.f;                      // dv[a] over rows of row group (atid>>7), all steps
+    unsigned seen_xd = 0, seen_xa = 0;
+    named_bar(BAR_ATT, 256);
+
+    for (int it = 0; it < To; ++it) {
+      const int t = To - 1 - it;
+      const bool has_next = t + 1 < To;
+      const int par = it & 1;
+      if (active) {
+        // ---- forward data of this step (independent of the recurrence): alignments, cumulative weights, saved tanh tile
+        if (atid == 0) {
+          mbar_expect_tx(x_full, 4u);
+          mbar_expect_tx(h_full, (uint32_t)halo_cnt * 2u * 4u);
+          if (nrow > 0) {
+            mbar_expect_tx(at_full, (uint32_t)nrow * AD * 4u);
+            bulk_load_1d(Abuf, s.ASAVE + (((long long)t * B + b) * Ti + i0) * AD, (uint32_t)nrow * AD * 4u, at_full);
+          }
+        }
+        for (int i = atid; i < Ti; i += 256) {
+          wpad[HALO + i] = (t > 0) ? __ldg(s.align + ((long long)b * To + (t - 1)) * Ti + i) : 0.f;
+          cpad[HALO + i] = __ldg(s.CUM + ((long long)t * B + b) * Ti + i);
+        }
+        if (atid < nrow) wt_s[atid] = __ldg(s.align + ((long long)b * To + t) * Ti + i0 + atid);
+        named_bar(BAR_ATT, 256);
+        // ---- location conv recomputed on this CTA's rows (needed by dW_loc / dW_conv below)
+        {
+          const int c = atid & 31, r0 = (atid >> 5) * 8;
+          if (r0 < nrow) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              const float* src = (ch ? cpad : wpad) + i0 + r0;
+              float xr[8 + KS - 1];
+#pragma unroll
+              for (int j = 0; j < 8 + KS - 1; ++j) xr[j] = src[j];
+#pragma unroll
+              for (int k = 0; k < KS; ++k) {
+                const float w = wcT[(ch * KS + k) * NF + c];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, xr[j + k], acc[j]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f_s[(r0 + j) * FS + c] = acc[j];
+          }
+        }
+      }
+      // ---- dXD[t] and DXA[t+1] complete device-wide
+      if (atid == 0) {
+        const unsigned n_xd = NCTA * (unsigned)(it + 1), n_xa = NCTA * (unsigned)it;
+        if (seen_xd < n_xd) { wait_counter(cnt_xd, n_xd); seen_xd = n_xd; }
+        if (seen_xa < n_xa) { wait_counter(cnt_xa, n_xa); seen_xa = n_xa; }
+      }
+      named_bar(BAR_ATT, 256);
+      if (active) {
+        // ---- total gradient wrt ctx_t (three consumers of ctx_t, model.py:357,375,383)
+        for (int col = atid; col < ED; col += 256) {
+          float v = __ldcg(d.DXD + ((long long)t * B + b) * XD_W + H + col) + __ldcg(d.DHC + ((long long)t * B + b) * (H + ED) + H + col);
+          if (has_next) v += __ldcg(d.DXA + ((long long)(t + 1) * B + b) * XA_W + PD + col);
+          dctx_s[col] = v;
+          if (hh == 0) d.DCTX[((long long)t * B + b) * ED + col] = v;
+        }
+        named_bar(BAR_ATT, 256);
+        // ---- dw_i = <dctx, memory_i> + (gradient wrt w_t from step t+1's location conv) + (gradient wrt cum_{t+1})
+        {
+          float4 dc4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dc4[j] = *reinterpret_cast<const float4*>(dctx_s + lane * 4 + 128 * j);
+          const float* mb = s.mem + ((long long)b * Ti + i0) * ED + lane * 4;
+          for (int rb = 0; rb < nrow; rb += 32) {
+            float4 mv[4][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = rb + aw + 8 * k;
+              const bool ld = rr < nrow && (i0 + rr) < len;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                mv[k][j] = ld ? ldg_v4_hint(mb + (long long)rr * ED + 128 * j, pol_m) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = rb + aw + 8 * k;
+              float acc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                acc += dc4[j].x * mv[k][j].x + dc4[j].y * mv[k][j].y + dc4[j].z * mv[k][j].z + dc4[j].w * mv[k][j].w;
+              acc = warp_sum(acc);
+              if (lane == 0 && rr < nrow) dwv_s[rr] = acc + G_s[rr] + P_s[rr];
+            }
+          }
+        }
+        named_bar(BAR_ATT, 256);
+        // ---- softmax backward: s = sum_i w_i dw_i over both halves, de_i = w_i (dw_i - s)
+        if (aw == 0) {
+          float part = 0.f;
+          for (int rr = lane; rr < nrow; rr += 32) part = fmaf(wt_s[rr], dwv_s[rr], part);
+          part = warp_sum(part);
+          if (lane == 0) {
+            spart[par * 2 + hh] = part;
+            st_async_f32(partner_spart + (uint32_t)(par * 2 + hh) * 4u, partner_x, part);
+          }
+        }
+        mbar_wait_cluster(x_full, (unsigned)it & 1u);
+        named_bar(BAR_ATT, 256);
+        {
+          const float ssum = spart[par * 2] + spart[par * 2 + 1];
+          if (atid < nrow) de_s[atid] = wt_s[atid] * (dwv_s[atid] - ssum);
+        }
+        if (nrow > 0) mbar_wait(at_full, (unsigned)it & 1u);
+        named_bar(BAR_ATT, 256);
+        // ---- tanh / v backward on this CTA's rows: dpre (kept in place of the saved tanh), dq, dv, d(processed memory)
+        {
+          const int rbeg = (atid >> 7) * 32;
+          float dq_acc = 0.f;
+          float* dpm = d.dpmem + ((long long)b * Ti + i0) * AD + a;
+#pragma unroll 4
+          for (int rr = rbeg; rr < rbeg + 32; ++rr) {
+            if (rr < nrow) {
+              const float g = de_s[rr];
+              const float av = Abuf[rr * AD + a];
+              const float dp = g * va * (1.f - av * av);
+              Abuf[rr * AD + a] = dp;
+              if (g != 0.f) atomicAdd(dpm + (long long)rr * AD, dp);     // sole writer of the address: RED
+              dq_acc += dp;
+              dv_acc = fmaf(g, av, dv_acc);
+            }
+          }
+          q_s[(atid >> 7) * 128 + a] = dq_acc;
+        }
+        named_bar(BAR_ATT, 256);
+        if (atid < AD) atomicAdd(d.DQ + ((long long)t * B + b) * AD + atid, q_s[atid] + q_s[128 + atid]);
+      }
+      named_bar(BAR_ATT, 256);
+      if (atid == 0) signal_counter(cnt_q);
+      // ================= off the critical path: weight gradients of the location layer, adjoint conv for step t-1
+      if (active) {
+        // ---- dW_loc[a][c] += sum_rows dpre[row][a] f[row][c]   (thread: a, 16 of the 32 filters, all rows)
+        {
+          const int cb = (atid >> 7) * 16;
+          for (int rr = 0; rr < nrow; ++rr) {
+            const float dp = Abuf[rr * AD + a];
+            const float4* fr = reinterpret_cast<const float4*>(f_s + rr * FS + cb);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 f4 = fr[c4];
+              gwl[4 * c4] = fmaf(dp, f4.x, gwl[4 * c4]); gwl[4 * c4 + 1] = fmaf(dp, f4.y, gwl[4 * c4 + 1]);
+              gwl[4 * c4 + 2] = fmaf(dp, f4.z, gwl[4 * c4 + 2]); gwl[4 * c4 + 3] = fmaf(dp, f4.w, gwl[4 * c4 + 3]);
+            }
+          }
+        }
+        // ---- df[row][c] = sum_a dpre[row][a] W_loc[a][c]   (thread: filter c, 8 rows)
+        float dfr[8];
+        {
+          const int c = atid & 31, r0 = (atid >> 5) * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dfr[j] = 0.f;
+          if (r0 < nrow) {
+#pragma unroll 2
+            for (int a0 = 0; a0 < AD; a0 += 4) {
+              const float w0 = WlocS[a0 * NF + c], w1 = WlocS[(a0 + 1) * NF + c], w2 = WlocS[(a0 + 2) * NF + c], w3 = WlocS[(a0 + 3) * NF + c];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 d4 = *reinterpret_cast<const float4*>(Abuf + (r0 + j) * AD + a0);
+                dfr[j] = fmaf(d4.x, w0, dfr[j]); dfr[j] = fmaf(d4.y, w1, dfr[j]);
+                dfr[j] = fmaf(d4.z, w2, dfr[j]); dfr[j] = fmaf(d4.w, w3, dfr[j]);
+              }
+            }
+          }
+        }
+        named_bar(BAR_ATT, 256);             // every reader of f is done: f_s becomes df
+        {
+          const int c = atid & 31, r0 = (atid >> 5) * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f_s[(r0 + j) * FS + c] = (r0 + j < nrow) ? dfr[j] : 0.f;
+        }
+        named_bar(BAR_ATT, 256);
+        // ---- dW_conv[(ch,k)][c] += sum_rows df[row][c] x_ch[row + k - 15]
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const int e = atid + 256 * m;
+          if (e < 2 * KS * NF) {
+            const int c = e & 31, chk = e >> 5;
+            const float* x = ((chk >= KS) ? cpad : wpad) + i0 + (chk >= KS ? chk - KS : chk);
+            float a0 = 0.f, a1 = 0.f;
+            int rr = 0;
+            for (; rr + 1 < nrow; rr += 2) {
+              a0 = fmaf(f_s[rr * FS + c], x[rr], a0);
+              a1 = fmaf(f_s[(rr + 1) * FS + c], x[rr + 1], a1);
+            }
+            if (rr < nrow) a0 = fmaf(f_s[rr * FS + c], x[rr], a0);
+            wcacc[m] += a0 + a1;
+          }
+        }
+        // ---- adjoint conv: dx[ch][s] = sum_{k,c} df[s-k+15][c] W_conv[c][ch][k], s in [i0-15, i0+nrow+15);
+        // own rows stay here, the rows of the other half go to the partner CTA
+        if (t > 0) {
+          const int span = nrow + 2 * HALO;
+          if (atid < 2 * span) {
+            const int ch = atid / span, j = atid - ch * span;
+            const int sidx = i0 - HALO + j;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int k = 0; k < KS; ++k) {
+              const int tt = j - k;
+              if (tt >= 0 && tt < nrow) {
+                const float4* dfp = reinterpret_cast<const float4*>(f_s + tt * FS);
+                const float4* wk = reinterpret_cast<const float4*>(wcT + (ch * KS + k) * NF);
+#pragma unroll
+                for (int c4 = 0; c4 < NF / 4; ++c4) {
+                  const float4 x4 = dfp[c4], w4 = wk[c4];
+                  a0 = fmaf(x4.x, w4.x, a0); a1 = fmaf(x4.y, w4.y, a1); a2 = fmaf(x4.z, w4.z, a2); a3 = fmaf(x4.w, w4.w, a3);
+                }
+              }
+            }
+            const float av = (a0 + a1) + (a2 + a3);
+            if (sidx >= 0 && sidx < Ti) {
+              if (sidx >= i0 && sidx < i0 + nrow) adj_s[ch * 64 + (sidx - i0)] = av;
+              else st_async_f32(partner_halo + (uint32_t)((par * 2 + ch) * 64 + (hh ? sidx : sidx - Th)) * 4u, partner_h, av);
+            }
+          }
+          mbar_wait_cluster(h_full, (unsigned)it & 1u);
+          named_bar(BAR_ATT, 256);
+          if (atid < nrow) {
+            // rows that received a halo contribution from the partner: the last `halo_cnt` rows of the first half /
+            // the first `halo_cnt` rows of the second half
+            const bool got = hh ? (atid < halo_cnt) : (atid >= nrow - halo_cnt);
+            const float h0 = got ? halo_s[(par * 2 + 0) * 64 + atid] : 0.f;
+            const float h1 = got ? halo_s[(par * 2 + 1) * 64 + atid] : 0.f;
+            P_s[atid] = adj_s[atid] + h0;
+            G_s[atid] += adj_s[64 + atid] + h1;
+          }
+        }
+      }
+      named_bar(BAR_ATT, 256);
+    }
+    // ---- sequence-long accumulators -> the partial buffers the engine reduces over (slot 0 of the utterance)
+    if (active) {
+      const int nck = (Ti + 31) / 32;
+      const long long slot = (long long)b * nck;
+      atomicAdd(d.dv_part + slot * AD + a, dv_acc);
+      float* wl = d.dwloc_part + slot * (AD * NF) + a * NF + (atid >> 7) * 16;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) atomicAdd(wl + c, gwl[c]);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int e = atid + 256 * m;
+        if (e < 2 * KS * NF) atomicAdd(d.dwconv_part + slot * (2 * KS * NF) + e, wcacc[m]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+bool persist_bwd_enabled() {
+  const char* e = getenv("T2V_PERSIST_BWD");
+  return !(e && e[0] == '0');
+}
+
+}  // namespace
+
+int t2v_encode_tmap_2d(CUtensorMap* map, const void* base, int esize, long long inner, long long rows,
+                       long long row_stride_elems, int box_rows);
+
+// Returns 0 when the loop was enqueued, 1 when the persistent kernel does not apply (the caller uses the per-step launches).
+int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStream_t stream) {
+  const T2VDecoderSeq* s = &d->f;
+  if (!persist_bwd_enabled()) return 1;
+  if (!s->use_tc || s->B > 64 || s->Ti > 2 * TH_MAX || s->Ti < 1 || t_hi != s->To || t_lo != 0 || s->To < 2) return 1;
+  if (!s->GA || !s->GD || !s->CPA || !s->CPD || !s->ASAVE || !d->dHq) return 1;
+  static int max_clusters = -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(dec_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(NCTA); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, dec_persist_bwd_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    max_clusters = n;
+  }
+  if (max_clusters < NCLUSTER) return 1;
+
+  BwdParams p;
+  p.d = *d;
+  p.counters = reinterpret_cast<unsigned*>(d->dHq);          // scratch [B,1024] floats, unused by this path otherwise
+  auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+  p.wa_hint = env_int("T2V_PERSIST_BWD_WA_HINT", 1);
+  p.wd_hint = env_int("T2V_PERSIST_BWD_WD_HINT", 2);
+  CUtensorMap tmWa, tmWd64, tmWd16, tmGA, tmGD;
+  const long long rows = (long long)s->To * s->B;
+  int r;
+  if ((r = t2v_encode_tmap_2d(&tmWa, d->WaT, 4, 4 * H, XA_W, 4 * H, XA_CPC))) return r;
+  if ((r = t2v_encode_tmap_2d(&tmWd64, d->WdT, 4, 4 * H, XD_W, 4 * H, 64))) return r;
+  if ((r = t2v_encode_tmap_2d(&tmWd16, d->WdT, 4, 4 * H, XD_W, 4 * H, 16))) return r;
+  if ((r = t2v_encode_tmap_2d(&tmGA, d->DGA, 4, 4 * H, rows, 4 * H, 64))) return r;
+  if ((r = t2v_encode_tmap_2d(&tmGD, d->DGD, 4, 4 * H, rows, 4 * H, 64))) return r;
+  T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 160 * sizeof(unsigned), stream));
+  T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel, tmWa, tmWd64, tmWd16, tmGA, tmGD, p));
+  T2V_COUNT_LAUNCH();
+  return 0;
+}

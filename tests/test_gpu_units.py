@@ -316,3 +316,45 @@ def test_persistent_decoder_loop_matches_per_step_launches(L, B, Ti, To, trainin
         err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
         print("persistent vs per-step %-6s max-rel %.3e" % (k, err))
         assert err <= (1.5e-3 if k in ("XA", "XD") else 2e-4), (k, err)
+
+
+@pytest.mark.parametrize("B,Ti,To", [(5, 23, 12), (64, 120, 20), (3, 128, 7), (1, 1, 4)])
+def test_persistent_decoder_backward_matches_per_step_launches(L, B, Ti, To):
+    """decoder_persist_bwd.cu (one resident kernel for the reverse-time loop) against the per-step launch sequence on the same
+    saved forward state: d(memory), every decoder weight gradient, the dX sequences and the gate gradients.
+    Different split-K order / fp32 dHq instead of a tf32 GEMM: tolerance 2e-3 of each tensor's max (measured ~1e-4)."""
+    import os
+    from oracle import port
+    from t2v import engine
+    dev = torch.device("cuda")
+    P = {k: v.to(dev) for k, v in port.init_params(1234).items()}
+    ops = engine.Ops("tf32")
+    g = torch.Generator().manual_seed(B * 1000 + Ti)
+    memory = (torch.randn(B, Ti, 512, generator=g) * 0.5).to(dev)
+    mel = (torch.randn(B, 80, To, generator=g) * 2 - 5).to(dev)
+    in_len = torch.randint(max(1, Ti // 2), Ti + 1, (B,), generator=g).sort(descending=True)[0]
+    in_len[0] = Ti
+    in_len = in_len.to(dev)
+    dO = (torch.randn(To * B, 84, generator=g) * 0.1).to(dev)
+    dO[:, 81:] = 0
+    outs = {}
+    for mode in ("0", "1"):
+        os.environ["T2V_PERSIST_BWD"] = mode
+        try:
+            O, align, ctx = engine.decoder_forward(ops, P, memory, mel, in_len, True, None, None, 77, -float("inf"), dev)
+            grads = {}
+            dmem, br = engine.decoder_backward(ops, P, dO, ctx, dev, grads)
+            br.join()
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("T2V_PERSIST_BWD", None)
+        t, _ = br.keep
+        res = dict(dmem=dmem.clone(), **{k: t[k].clone() for k in ("DXA", "DXD", "DGA", "DGD", "DCTX", "DQ", "dpmem", "dCa", "dCd")})
+        res.update({"grad:" + k: v.clone() for k, v in grads.items()})
+        outs[mode] = res
+    for k in outs["0"]:
+        a, b = outs["1"][k], outs["0"][k]
+        assert torch.isfinite(a).all(), k
+        err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+        print("persistent bwd vs per-step %-60s max-rel %.3e" % (k, err))
+        assert err <= 2e-3, (k, err)
