@@ -221,8 +221,13 @@ typedef struct T2VDecoderSeq {
   float *ASAVE;                  /* [To,B,Ti,128] tanh activations; NULL at inference */
   float *parts, *qparts;         /* split-K workspaces: >= 32*B*4096 (two halves of 16 parts, one per chain) and 8*B*128 floats */
   float *ebuf;                   /* [B,Ti,129] scratch: [B,Ti] energies, then [B,Ti,128] location term + processed memory */
+  const float *WaP, *WdP;        /* optional (NULL = unused): Wa / Wd re-tiled by t2v_pack_step_tiles (modes 0 / 1) for the persistent
+                                    loop kernel: every TMA box is one contiguous 16 KB block instead of 128 strided 128-byte rows */
 } T2VDecoderSeq;
 int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);
+/* re-tile a decoder-step weight matrix into the order the persistent loop kernels stream it (same number of floats):
+   mode 0: Wa [4096,1792] -> WaP ; 1: Wd [4096,2560] -> WdP ; 2: WaT [1792,4096] -> WaTP ; 3: WdT [2560,4096] -> WdTP */
+int t2v_pack_step_tiles(const float* W, int mode, float* out, cudaStream_t stream);
 
 typedef struct T2VDecoderBwd {
   T2VDecoderSeq f;               /* the forward description (same buffers) */
@@ -240,6 +245,7 @@ typedef struct T2VDecoderBwd {
   float *DQ;                     /* out [To,B,128], zero-initialised (accumulated with atomics) */
   float *dHq;                    /* scratch [B,1024] */
   float *dv_part, *dwloc_part, *dwconv_part;   /* [B*nchunk,128], [B*nchunk,128*32], [B*nchunk,32*2*31] accumulators (zero-init), nchunk = t2v_attn2_chunks(Ti) */
+  const float *WaTP, *WdTP;      /* optional (NULL = unused): WaT / WdT re-tiled by t2v_pack_step_tiles (modes 2 / 3) */
 } T2VDecoderBwd;
 int t2v_decoder_bwd_steps(const T2VDecoderBwd* s, int t_hi, int t_lo, cudaStream_t stream);  /* t = t_hi-1 .. t_lo */
 

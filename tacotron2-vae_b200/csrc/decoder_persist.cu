@@ -32,7 +32,8 @@ constexpr int NF = 32, KS = 31, HALO = 15;
 constexpr unsigned SITE_ATT_H = 10, SITE_ATT_C = 11, SITE_DEC_H = 12, SITE_DEC_C = 13;
 constexpr int CL = 4, NCLUSTER = 32, NCTA = CL * NCLUSTER;
 constexpr int NTHREADS = 512;
-constexpr int NW = 4, NA = 4;                  // ring depths (weights 16 KB / stage, activations 8 KB / stage)
+constexpr int NS = 4;                          // ring depth: a stage = one K chunk of weights (16 KB) + activations (8 KB)
+constexpr int NW = NS, NA = NS;
 constexpr int W_STAGE = 128 * 128, A_STAGE = 64 * 128;
 constexpr int ATT_CHUNKS = 14, DEC_CHUNKS = 20; // 32-wide K chunks per CTA: (64 + 128 + 256) / 32 and (256 + 128 + 256) / 32
 constexpr int SLOT = 4 * 16 * 32;              // floats of one exchange slot: [gate][batch row of the owner][unit]
@@ -54,7 +55,7 @@ constexpr int OFF_CPAD = OFF_WPAD + PADW * 4;
 constexpr int OFF_E = OFF_CPAD + PADW * 4;                          // [128] energies
 constexpr int OFF_Q = OFF_E + 128 * 4;                              // [2][128]
 constexpr int OFF_BARS = OFF_Q + 256 * 4;
-constexpr int N_BARS = 2 * NW + 2 * NA + 8;
+constexpr int N_BARS = 2 * NS + 8;
 constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
 
@@ -63,6 +64,7 @@ struct PersistParams {
   int t_begin, t_end;
   unsigned* counters;      // [0] h_att complete, [32] ctx complete, [64] h_dec complete (one 128-byte line each)
   float* qpart;            // [2][NCLUSTER][B][128] per-cluster partial query projections
+  int packed;              // tmWa / tmWd describe the re-tiled copies (one contiguous 16 KB box per chunk)
   int wa_hint, wd_hint, mem_hint;   // L2 eviction priority of the weight streams / the encoder memory: 0 normal, 1 evict_last, 2 evict_first
   long long* trace;        // T2V_PERSIST_TRACE: [2 CTAs][TRACE_STEPS][32] clock64 stamps, else nullptr
 };
@@ -101,11 +103,9 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   float* e_s = (float*)(smem + OFF_E);
   float* q_s = (float*)(smem + OFF_Q);
   uint64_t* bars = (uint64_t*)(smem + OFF_BARS);
-  uint64_t* w_full = bars;
-  uint64_t* w_empty = w_full + NW;
-  uint64_t* a_full = w_empty + NW;
-  uint64_t* a_empty = a_full + NA;
-  uint64_t* acc_full = a_empty + NA;      // [2]
+  uint64_t* full = bars;                  // [NS] both producers arrive (count 2) with their byte counts: ONE wait per chunk
+  uint64_t* empty = full + NS;            // [NS] freed by the MMA commit; both producers wait on it
+  uint64_t* acc_full = empty + NS;        // [2]
   uint64_t* acc_free = acc_full + 2;      // [2]
   uint64_t* recv_full = acc_free + 2;     // [2]
   uint64_t* e_full = recv_full + 2;       // [1]
@@ -129,8 +129,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   };
 
   if (tid == 0) {
-    for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_free[i], 128);
@@ -156,22 +155,28 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     if (lane == 0) {
       uint32_t iw = 0;
       const uint64_t pol_a = l2_policy(p.wa_hint), pol_d = l2_policy(p.wd_hint);
-      auto load_w = [&](const CUtensorMap* tm, int kofs, int hint, uint64_t pol) {
-        const int st = iw % NW;
-        const uint32_t ph = (iw / NW) & 1u;
-        mbar_wait(&w_empty[st], ph ^ 1u);
-        mbar_expect_tx(&w_full[st], W_STAGE);
+      auto load_w = [&](const CUtensorMap* tm, int kofs, int tile, int hint, uint64_t pol) {
+        const int st = iw % NS;
+        const uint32_t ph = (iw / NS) & 1u;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_expect_tx(&full[st], W_STAGE);
         uint8_t* dst = wring + st * W_STAGE;
+        if (p.packed) {                 // tile-contiguous copy: the whole [4 gates x 32 units][32] tile is one box
+          if (hint) tma_load_2d_hint(dst, tm, 0, tile * 128, &full[st], pol);
+          else tma_load_2d(dst, tm, 0, tile * 128, &full[st]);
+          ++iw;
+          return;
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {   // gate rows i,f,g,o of this cluster's 32 hidden units -> 128 consecutive tile rows
-          if (hint) tma_load_2d_hint(dst + g * 4096, tm, kofs, g * H + 32 * cid, &w_full[st], pol);
-          else tma_load_2d(dst + g * 4096, tm, kofs, g * H + 32 * cid, &w_full[st]);
+          if (hint) tma_load_2d_hint(dst + g * 4096, tm, kofs, g * H + 32 * cid, &full[st], pol);
+          else tma_load_2d(dst + g * 4096, tm, kofs, g * H + 32 * cid, &full[st]);
         }
         ++iw;
       };
       for (int t = tb; t <= te; ++t) {
-        if (t < te) for (int j = 0; j < ATT_CHUNKS; ++j) { load_w(&tmWa, att_kofs(j, rank), p.wa_hint, pol_a); if (j == 0) TR(t - tb, 24); }
-        if (t > tb) for (int j = 0; j < DEC_CHUNKS; ++j) load_w(&tmWd, dec_kofs(j, rank), p.wd_hint, pol_d);
+        if (t < te) for (int j = 0; j < ATT_CHUNKS; ++j) { load_w(&tmWa, att_kofs(j, rank), (cid * CL + rank) * ATT_CHUNKS + j, p.wa_hint, pol_a); if (j == 0) TR(t - tb, 24); }
+        if (t > tb) for (int j = 0; j < DEC_CHUNKS; ++j) load_w(&tmWd, dec_kofs(j, rank), (cid * CL + rank) * DEC_CHUNKS + j, p.wd_hint, pol_d);
         TR(t - tb, 25);
       }
     }
@@ -187,11 +192,11 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         fence_proxy_async();          // the rows were written with generic-proxy stores, TMA reads them through the async proxy
       };
       auto load_a = [&](const CUtensorMap* tm, int kofs, int row0) {
-        const int st = ia % NA;
-        const uint32_t ph = (ia / NA) & 1u;
-        mbar_wait(&a_empty[st], ph ^ 1u);
-        mbar_expect_tx(&a_full[st], A_STAGE);
-        tma_load_2d(aring + st * A_STAGE, tm, kofs, row0, &a_full[st]);
+        const int st = ia % NS;
+        const uint32_t ph = (ia / NS) & 1u;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_expect_tx(&full[st], A_STAGE);
+        tma_load_2d(aring + st * A_STAGE, tm, kofs, row0, &full[st]);
         ++ia;
       };
       for (int t = tb; t <= te; ++t) {
@@ -218,34 +223,44 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       }
     }
   } else if (warp == 2) {
-    // =========================================================================== MMA issuer
-    if (lane == 0) {
+    // =========================================================================== MMA issuer (whole warp in the loop, one
+    // elected lane issues: keeps every tcgen05 operand in uniform registers)
+    {
       // instruction descriptor: D=f32, A=B=tf32, K-major both, N=64 (batch), M=128 (gate rows)
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      uint32_t ic = 0;
+      // running ring position; the descriptors of stage s are the stage-0 descriptors + s * (stage bytes >> 4)
+      int st = 0;
+      uint32_t ph = 0;
+      const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(wring));
+      const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(aring));
+      bool ready = false;                    // phase test of the current stage, started while the previous chunk was issued
       auto gemm = [&](int which, int nch, unsigned idx) {
         mbar_wait(&acc_free[which], (idx & 1u) ^ 1u);      // the epilogue has drained the previous accumulator
         tc_fence_after();
         const uint32_t dcol = tmem_base + (uint32_t)(which * 64);
         for (int j = 0; j < nch; ++j) {
-          const int sw = ic % NW, sa = ic % NA;
-          const uint32_t phw = (ic / NW) & 1u, pha = (ic / NA) & 1u;
-          mbar_wait(&w_full[sw], phw);
-          mbar_wait(&a_full[sa], pha);
+          if (!ready) mbar_wait(&full[st], ph);
           tc_fence_after();
-          if (which == 0 && j == 0) TR(idx, 4);
-          if (which == 0 && j == 10) TR(idx, 5);
-          const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(wring + sw * W_STAGE));
-          const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(aring + sa * A_STAGE));
+          const int sn = (st + 1 == NS) ? 0 : st + 1;
+          const uint32_t pn = (st + 1 == NS) ? (ph ^ 1u) : ph;
+          ready = mbar_test_wait(&full[sn], pn);           // overlaps the issue below
+          if (elect_one()) {
+            if (which == 0 && j == 0) TR(idx, 4);
+            if (which == 0 && j == 10) TR(idx, 5);
+            const uint64_t adesc = adesc0 + (uint64_t)(st * (W_STAGE >> 4));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(st * (A_STAGE >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&w_empty[sw]);
-          tc_commit(&a_empty[sa]);
-          ++ic;
+            for (int k = 0; k < 4; ++k)
+              tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&empty[st]);
+            if (j == nch - 1) {
+              tc_commit(&acc_full[which]);
+              TR(which ? idx + 1 : idx, which ? 7 : 6);
+            }
+          }
+          __syncwarp();
+          st = sn; ph = pn;
         }
-        tc_commit(&acc_full[which]);
-        TR(which ? idx + 1 : idx, which ? 7 : 6);
       };
       for (int t = tb; t <= te; ++t) {
         const unsigned n = (unsigned)(t - tb);
@@ -674,6 +689,31 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   }
 }
 
+// out tile order: mode 0/1 (forward): [cluster][rank][chunk][gate*32 + unit][32 k] ; mode 2/3 (backward, from the transposed
+// weights): [cluster][rank][chunk][output column of the cluster][32 gate rows]
+__global__ void pack_step_tiles_kernel(const float* __restrict__ W, int mode, float* __restrict__ out, long long n4) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= n4) return;
+  const int kk = (int)(i4 & 7) * 4;
+  long long row = i4 >> 3;                       // tile * rows_per_tile + m
+  long long src;
+  if (mode < 2) {
+    const int nch = mode ? DEC_CHUNKS : ATT_CHUNKS, ld = mode ? XD_W : XA_W;
+    const int m = (int)(row & 127);
+    const long long tile = row >> 7;
+    const int j = (int)(tile % nch), cr = (int)(tile / nch), rank = cr & 3, c = cr >> 2;
+    const int kofs = mode ? dec_kofs(j, rank) : att_kofs(j, rank);
+    src = (long long)((m >> 5) * H + 32 * c + (m & 31)) * ld + kofs + kk;
+  } else {
+    const int rows = (mode == 3) ? XD_W / NCLUSTER : XA_W / NCLUSTER;
+    const int m = (int)(row % rows);
+    const long long tile = row / rows;
+    const int j = (int)(tile & 31), cr = (int)(tile >> 5), rank = cr & 3, c = cr >> 2;
+    src = (long long)(rows * c + m) * (4 * H) + 1024 * rank + 32 * j + kk;
+  }
+  *reinterpret_cast<float4*>(out + i4 * 4) = *reinterpret_cast<const float4*>(W + src);
+}
+
 bool persist_enabled() {      // read per call: the tests flip T2V_PERSIST to compare against the per-step launches
   const char* e = getenv("T2V_PERSIST");
   return !(e && e[0] == '0');
@@ -729,8 +769,14 @@ int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cuda
   CUtensorMap tmWa, tmWd, tmXA, tmXD;
   const long long rows = (long long)(s->To + 1) * s->B;
   int r;
-  if ((r = t2v_encode_tmap_2d(&tmWa, s->Wa, 4, XA_W, 4 * H, XA_W, 32))) return r;
-  if ((r = t2v_encode_tmap_2d(&tmWd, s->Wd, 4, XD_W, 4 * H, XD_W, 32))) return r;
+  p.packed = (s->WaP && s->WdP && env_int("T2V_PERSIST_PACKED", 1)) ? 1 : 0;
+  if (p.packed) {
+    if ((r = t2v_encode_tmap_2d(&tmWa, s->WaP, 4, 32, (long long)NCTA * ATT_CHUNKS * 128, 32, 128))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmWd, s->WdP, 4, 32, (long long)NCTA * DEC_CHUNKS * 128, 32, 128))) return r;
+  } else {
+    if ((r = t2v_encode_tmap_2d(&tmWa, s->Wa, 4, XA_W, 4 * H, XA_W, 32))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmWd, s->Wd, 4, XD_W, 4 * H, XD_W, 32))) return r;
+  }
   if ((r = t2v_encode_tmap_2d(&tmXA, s->XA, 4, XA_W, rows, XA_W, 64))) return r;
   if ((r = t2v_encode_tmap_2d(&tmXD, s->XD, 4, XD_W, rows, XD_W, 64))) return r;
   T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 96 * sizeof(unsigned), stream));
@@ -757,5 +803,14 @@ int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cuda
       }
     }
   }
+  return 0;
+}
+
+T2V_API int t2v_pack_step_tiles(const float* W, int mode, float* out, cudaStream_t stream) {
+  T2V_ARG_CHECK(W && out && mode >= 0 && mode <= 3, "mode 0..3");
+  const long long n4 = (long long)4 * H * ((mode == 0 || mode == 2) ? XA_W : XD_W) / 4;
+  pack_step_tiles_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(W, mode, out, n4);
+  T2V_COUNT_LAUNCH();
+  T2V_LAUNCH_CHECK();
   return 0;
 }

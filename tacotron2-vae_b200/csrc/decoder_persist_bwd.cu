@@ -29,16 +29,15 @@ constexpr int NF = 32, KS = 31, HALO = 15;
 constexpr unsigned SITE_ATT_H = 10, SITE_ATT_C = 11, SITE_DEC_H = 12, SITE_DEC_C = 13;
 constexpr int CL = 4, NCLUSTER = 32, NCTA = CL * NCLUSTER, NTHREADS = 512;
 constexpr int XA_CPC = XA_W / NCLUSTER, XD_CPC = XD_W / NCLUSTER;   // 56 / 80 output columns per cluster
-constexpr int WU = 8192, NWU = 6;              // weight ring: 8 KB units; a DXA chunk takes 1 unit, a dXD chunk 2 (even-aligned)
-constexpr int NA = 5, A_STAGE = 64 * 128;      // gate-gradient ring (64 batch rows x 32 floats)
+constexpr int NS = 5;                          // ring depth: a stage = one K chunk: W^T tile (<= 80 rows, 10 KB) + gate gradients (8 KB)
+constexpr int W_PART = 80 * 128, A_STAGE = 64 * 128, STAGE = W_PART + A_STAGE;
 constexpr int KCH = 32;                        // 32-wide K chunks per CTA and GEMM (K slice = 4096 / 4)
 constexpr int RA_P = 64, RD_P = 80;            // column pitch of the exchange slots [src][batch row 16][cols]
 constexpr int TH_MAX = 64, PADW = 160, FS = 36;
 constexpr int BAR_EPI = 1, BAR_ATT = 2;
 
-constexpr int OFF_WRING = 0;
-constexpr int OFF_ARING = OFF_WRING + NWU * WU;
-constexpr int OFF_RECVA = OFF_ARING + NA * A_STAGE;
+constexpr int OFF_RING = 0;
+constexpr int OFF_RECVA = OFF_RING + NS * STAGE;
 constexpr int OFF_RECVD = OFF_RECVA + 4 * 16 * RA_P * 4;
 constexpr int OFF_ABUF = OFF_RECVD + 4 * 16 * RD_P * 4;            // [TH_MAX][128] saved tanh -> dpre (in place)
 constexpr int OFF_F = OFF_ABUF + TH_MAX * AD * 4;                   // [TH_MAX][FS] conv output f -> df (in place)
@@ -52,7 +51,7 @@ constexpr int OFF_SMALL = OFF_DCTX + ED * 4;
 constexpr int SM_WPAD = 0, SM_CPAD = 160, SM_WT = 320, SM_DWV = 384, SM_DE = 448, SM_P = 512, SM_G = 576, SM_ADJ = 640,
               SM_HALO = 768, SM_SPART = 1024, SM_QS = 1028, SM_TOTAL = 1284;
 constexpr int OFF_BARS = OFF_SMALL + ((SM_TOTAL * 4 + 15) / 16) * 16;
-constexpr int N_BARS = 2 * NWU + 2 * NA + 9;
+constexpr int N_BARS = 2 * NS + 10;
 constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -60,8 +59,13 @@ static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 struct BwdParams {
   T2VDecoderBwd d;
   unsigned* counters;      // [0] DGD[t] complete, [32] dXD[t], [64] dq[t], [96] DGA[t], [128] DXA[t]
+  int dbg_skip;            // timing experiments only (results are garbage): 1 = no weight loads, 2 = no gate-gradient loads
+  int rotate;              // rotate the chunk order per cluster
+  int packed;              // the weight tensor maps describe the re-tiled copies (contiguous boxes)
   int wa_hint, wd_hint;
+  long long* trace;        // T2V_PERSIST_TRACE: [2 CTAs][TRACE_STEPS][32] clock64 stamps, else nullptr
 };
+constexpr int TRACE_I0 = 100, TRACE_STEPS = 4, TRACE_CTA_B = 77;
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_constant__ CUtensorMap tmWd64,
@@ -69,8 +73,9 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
                        const __grid_constant__ CUtensorMap tmGD, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* wring = smem + OFF_WRING;
-  uint8_t* aring = smem + OFF_ARING;
+  uint8_t* ring = smem + OFF_RING;        // stage s: [W^T tile 10 KB | gate gradients 8 KB]; the M=128 descriptor of the dXD
+                                          // GEMM reads 48 rows past the 80 loaded ones (into the gradient part): those
+                                          // accumulator rows are never drained
   float* recv_a = (float*)(smem + OFF_RECVA);
   float* recv_d = (float*)(smem + OFF_RECVD);
   float* Abuf = (float*)(smem + OFF_ABUF);
@@ -82,16 +87,15 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   float* dctx_s = (float*)(smem + OFF_DCTX);
   float* small = (float*)(smem + OFF_SMALL);
   uint64_t* bars = (uint64_t*)(smem + OFF_BARS);
-  uint64_t* w_full = bars;
-  uint64_t* w_empty = w_full + NWU;
-  uint64_t* a_full = w_empty + NWU;
-  uint64_t* a_empty = a_full + NA;
-  uint64_t* acc_full = a_empty + NA;      // [2]: 0 = DXA GEMM, 1 = dXD GEMM
+  uint64_t* full = bars;                  // [NS] both producers arrive (count 2) with their byte counts: ONE wait per chunk
+  uint64_t* empty = full + NS;            // [NS]
+  uint64_t* acc_full = empty + NS;        // [2]: 0 = DXA GEMM, 1 = dXD GEMM
   uint64_t* acc_free = acc_full + 2;      // [2]
   uint64_t* recv_full = acc_free + 2;     // [2]
   uint64_t* at_full = recv_full + 2;      // saved tanh tile landed
   uint64_t* x_full = at_full + 1;         // partner's softmax-backward partial sum landed
   uint64_t* h_full = x_full + 1;          // partner's adjoint-conv halo landed
+  uint64_t* dq_full = h_full + 1;         // dq rows of this CTA's batch rows staged
   uint32_t* tmem_holder = (uint32_t*)(smem + OFF_TMEM);
 
   const T2VDecoderBwd& d = p.d;
@@ -105,10 +109,17 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   unsigned* cnt_q = p.counters + 64;
   unsigned* cnt_ga = p.counters + 96;
   unsigned* cnt_xa = p.counters + 128;
+  // the 32 clusters walk the K chunks in rotated order: at any moment the CTAs that share a K slice (same rank) read 32
+  // DIFFERENT gate-gradient tiles instead of all hitting the same 64 L2 lines
+  const int rot = p.rotate ? cid : 0;
+  const int trace_slot = (blockIdx.x == 0) ? 0 : ((blockIdx.x == TRACE_CTA_B) ? 1 : -1);
+  auto TR = [&](int it, int ev) {
+    if (p.trace && trace_slot >= 0 && it >= TRACE_I0 && it < TRACE_I0 + TRACE_STEPS)
+      p.trace[((long long)trace_slot * TRACE_STEPS + (it - TRACE_I0)) * 32 + ev] = clock64();
+  };
 
   if (tid == 0) {
-    for (int i = 0; i < NWU; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_free[i], 128);
@@ -117,6 +128,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     mbar_init(at_full, 1);
     mbar_init(x_full, 1);
     mbar_init(h_full, 1);
+    mbar_init(dq_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -134,27 +146,39 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   if (warp == 0) {
     // =========================================================================== weight producer
     if (lane == 0) {
-      uint32_t us = 0;
+      uint32_t iw = 0;
       const uint64_t pol_a = l2_policy(p.wa_hint), pol_d = l2_policy(p.wd_hint);
-      auto load_unit = [&](const CUtensorMap* tm, int kofs, int row, uint32_t bytes, int hint, uint64_t pol) {
-        const int u = us % NWU;
-        const uint32_t ph = (us / NWU) & 1u;
-        mbar_wait(&w_empty[u], ph ^ 1u);
-        mbar_expect_tx(&w_full[u], bytes);
-        if (hint) tma_load_2d_hint(wring + u * WU, tm, kofs, row, &w_full[u], pol);
-        else tma_load_2d(wring + u * WU, tm, kofs, row, &w_full[u]);
-        ++us;
+      auto tma_w = [&](void* dst, const CUtensorMap* tm, int kofs, int row, uint64_t* bar, int hint, uint64_t pol) {
+        if (hint) tma_load_2d_hint(dst, tm, kofs, row, bar, pol);
+        else tma_load_2d(dst, tm, kofs, row, bar);
       };
       for (int it = -1; it < To; ++it) {
         const int td = To - 2 - it;
         if (td >= 0) {
-          for (int j = 0; j < KCH; ++j) {       // 80 rows of W_d^T: 64 + 16 into two consecutive units
-            load_unit(&tmWd64, 1024 * rank + 32 * j, XD_CPC * cid, 64 * 128, p.wd_hint, pol_d);
-            load_unit(&tmWd16, 1024 * rank + 32 * j, XD_CPC * cid + 64, 16 * 128, p.wd_hint, pol_d);
+          for (int jj = 0; jj < KCH; ++jj, ++iw) {    // 80 rows of W_d^T (two boxes: 64 + 16 rows)
+            const int j = (jj + rot) & (KCH - 1);
+            const int st = iw % NS;
+            mbar_wait(&empty[st], ((iw / NS) & 1u) ^ 1u);
+            const int k0 = p.packed ? 0 : 1024 * rank + 32 * j;
+            const int r0 = p.packed ? ((cid * CL + rank) * KCH + j) * XD_CPC : XD_CPC * cid;
+            if (p.dbg_skip & 1) { mbar_arrive(&full[st]); continue; }
+            mbar_expect_tx(&full[st], XD_CPC * 128);
+            tma_w(ring + st * STAGE, &tmWd64, k0, r0, &full[st], p.wd_hint, pol_d);
+            tma_w(ring + st * STAGE + 64 * 128, &tmWd16, k0, r0 + 64, &full[st], p.wd_hint, pol_d);
           }
         }
-        if (it >= 0)
-          for (int j = 0; j < KCH; ++j) load_unit(&tmWa, 1024 * rank + 32 * j, XA_CPC * cid, XA_CPC * 128, p.wa_hint, pol_a);
+        if (it >= 0) {
+          for (int jj = 0; jj < KCH; ++jj, ++iw) {
+            const int j = (jj + rot) & (KCH - 1);
+            const int st = iw % NS;
+            mbar_wait(&empty[st], ((iw / NS) & 1u) ^ 1u);
+            const int k0 = p.packed ? 0 : 1024 * rank + 32 * j;
+            const int r0 = p.packed ? ((cid * CL + rank) * KCH + j) * XA_CPC : XA_CPC * cid;
+            if (p.dbg_skip & 1) { mbar_arrive(&full[st]); continue; }
+            mbar_expect_tx(&full[st], XA_CPC * 128);
+            tma_w(ring + st * STAGE, &tmWa, k0, r0, &full[st], p.wa_hint, pol_a);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -169,75 +193,76 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         fence_proxy_async();
       };
       auto load_a = [&](const CUtensorMap* tm, int kofs, int row0) {
-        const int st = ia % NA;
-        const uint32_t ph = (ia / NA) & 1u;
-        mbar_wait(&a_empty[st], ph ^ 1u);
-        mbar_expect_tx(&a_full[st], A_STAGE);
-        tma_load_2d(aring + st * A_STAGE, tm, kofs, row0, &a_full[st]);
+        const int st = ia % NS;
+        const uint32_t ph = (ia / NS) & 1u;
+        mbar_wait(&empty[st], ph ^ 1u);
+        if (p.dbg_skip & 2) { mbar_arrive(&full[st]); ++ia; return; }
+        mbar_expect_tx(&full[st], A_STAGE);
+        tma_load_2d(ring + st * STAGE + W_PART, tm, kofs, row0, &full[st]);
         ++ia;
       };
       for (int it = -1; it < To; ++it) {
         const int t = To - 1 - it, td = t - 1;
         if (td >= 0) {
           need(cnt_gd, seen_gd, NCTA * (unsigned)(it + 2));
-          for (int j = 0; j < KCH; ++j) load_a(&tmGD, 1024 * rank + 32 * j, td * B);
+          for (int j = 0; j < KCH; ++j) load_a(&tmGD, 1024 * rank + 32 * ((j + rot) & (KCH - 1)), td * B);
         }
         if (it >= 0) {
           need(cnt_ga, seen_ga, NCTA * (unsigned)(it + 1));
-          for (int j = 0; j < KCH; ++j) load_a(&tmGA, 1024 * rank + 32 * j, t * B);
+          for (int j = 0; j < KCH; ++j) load_a(&tmGA, 1024 * rank + 32 * ((j + rot) & (KCH - 1)), t * B);
         }
       }
     }
   } else if (warp == 2) {
-    // =========================================================================== MMA issuer
-    if (lane == 0) {
+    // =========================================================================== MMA issuer (whole warp in the loop, one
+    // elected lane issues)
+    {
       constexpr uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
       constexpr uint32_t idesc128 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      uint32_t us = 0, ia = 0;
+      int st = 0;
+      uint32_t ph = 0;
+      const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(ring));
+      const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(ring + W_PART));
+      bool ready = false;                    // phase test of the current stage, started while the previous chunk was issued
+      // which 1: dXD[td] = DGD[td] W_d, M = 128 (80 live rows), accumulator columns 64..127
+      // which 0: DXA[t]  = DGA[t]  W_a, M = 64 (56 live rows), accumulator columns 0..63
+      auto gemm = [&](const int which, const unsigned idx, const int it) {
+        mbar_wait(&acc_free[which], (idx & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + (uint32_t)(which * 64);
+        const uint32_t idesc = which ? idesc128 : idesc64;
+        for (int j = 0; j < KCH; ++j) {
+          if (!ready) mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const int sn = (st + 1 == NS) ? 0 : st + 1;
+          const uint32_t pn = (st + 1 == NS) ? (ph ^ 1u) : ph;
+          ready = mbar_test_wait(&full[sn], pn);           // overlaps the issue below
+          if (elect_one()) {
+            if (j == 0) TR(it, which ? 27 : 29);
+            const uint64_t adesc = adesc0 + (uint64_t)(st * (STAGE >> 4));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(st * (STAGE >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+            if (p.dbg_skip & 4) {        // timing experiment: twice the tensor work per chunk
+#pragma unroll
+              for (int k = 0; k < 4; ++k) tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+            }
+            if (p.dbg_skip & 8) mbar_arrive(&empty[st]);     // timing experiment: free the stage at issue, not at MMA completion
+            else tc_commit(&empty[st]);
+            if (j == KCH - 1) {
+              tc_commit(&acc_full[which]);
+              TR(it, which ? 28 : 30);
+            }
+          }
+          __syncwarp();
+          st = sn; ph = pn;
+        }
+      };
       for (int it = -1; it < To; ++it) {
         const int td = To - 2 - it;
-        if (td >= 0) {                           // dXD[td] = DGD[td] W_d : M = 128 (80 live rows), accumulator columns 64..127
-          mbar_wait(&acc_free[1], ((unsigned)(it + 1) & 1u) ^ 1u);
-          tc_fence_after();
-          for (int j = 0; j < KCH; ++j) {
-            const int u = us % NWU, sa = ia % NA;
-            const uint32_t phw = (us / NWU) & 1u, pha = (ia / NA) & 1u;
-            mbar_wait(&w_full[u], phw);
-            mbar_wait(&w_full[u + 1], phw);
-            mbar_wait(&a_full[sa], pha);
-            tc_fence_after();
-            const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(wring + u * WU));
-            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(aring + sa * A_STAGE));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_tf32(tmem_base + 64u, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc128, (j > 0 || k > 0) ? 1u : 0u);
-            tc_commit(&w_empty[u]);
-            tc_commit(&w_empty[u + 1]);
-            tc_commit(&a_empty[sa]);
-            us += 2; ++ia;
-          }
-          tc_commit(&acc_full[1]);
-        }
-        if (it >= 0) {                           // DXA[t] = DGA[t] W_a : M = 64 (56 live rows), accumulator columns 0..63
-          mbar_wait(&acc_free[0], ((unsigned)it & 1u) ^ 1u);
-          tc_fence_after();
-          for (int j = 0; j < KCH; ++j) {
-            const int u = us % NWU, sa = ia % NA;
-            const uint32_t phw = (us / NWU) & 1u, pha = (ia / NA) & 1u;
-            mbar_wait(&w_full[u], phw);
-            mbar_wait(&a_full[sa], pha);
-            tc_fence_after();
-            const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(wring + u * WU));
-            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(aring + sa * A_STAGE));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc64, (j > 0 || k > 0) ? 1u : 0u);
-            tc_commit(&w_empty[u]);
-            tc_commit(&a_empty[sa]);
-            ++us; ++ia;
-          }
-          tc_commit(&acc_full[0]);
-        }
+        if (td >= 0) gemm(1, (unsigned)(it + 1), it);
+        if (it >= 0) gemm(0, (unsigned)it, it);
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -265,6 +290,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     const uint64_t seed = (s.training && !s.drop_masks) ? t2v_resolve_seed(s.seed) : 0ull;
     const float p_att = s.training ? s.p_att : 0.f, p_dec = s.training ? s.p_dec : 0.f;
     unsigned seen_xd = 0, seen_xa = 0, seen_q = 0;
+    int cur_it = -1;
     named_bar(BAR_EPI, 128);
 
     // ---- LSTM cell backward (the math of lstm_pointwise_bwd_kernel) for step ts; which: 0 attention_rnn, 1 decoder_rnn
@@ -295,9 +321,19 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
       }
       if (etid == 0) {
+        TR(cur_it, which ? 0 : 15);
         if (seen_xd < n_xd) { wait_counter(cnt_xd, n_xd); seen_xd = n_xd; }
         if (seen_xa < n_xa) { wait_counter(cnt_xa, n_xa); seen_xa = n_xa; }
         if (seen_q < n_q) { wait_counter(cnt_q, n_q); seen_q = n_q; }
+        TR(cur_it, which ? 1 : 3);
+        if (which == 0) {        // dq of this CTA's 16 batch rows: one contiguous bulk copy (the rows were written with atomics)
+          const int nb = min(16, B - 16 * rank);
+          if (nb > 0) {
+            fence_proxy_async();
+            mbar_expect_tx(dq_full, (uint32_t)nb * AD * 4u);
+            bulk_load_1d(dq_s, d.DQ + (r0 + 16 * rank) * AD, (uint32_t)nb * AD * 4u, dq_full);
+          }
+        }
       }
       named_bar(BAR_EPI, 128);
       float dh[4];
@@ -318,11 +354,8 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       }
       if (which == 0) {
         // ---- dHq = dq W_q for this CTA's 16 batch rows x 32 units (dq of the whole batch is complete: cnt_q)
-        for (int i = etid; i < 16 * AD; i += 128) {
-          const int b = 16 * rank + (i >> 7);
-          dq_s[i] = (b < B) ? __ldcg(d.DQ + (r0 + b) * AD + (i & 127)) : 0.f;
-        }
-        named_bar(BAR_EPI, 128);
+        if (16 * rank < B) mbar_wait(dq_full, (unsigned)cur_it & 1u);
+        if (etid == 0) TR(cur_it, 4);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
         for (int a0 = 0; a0 < AD; a0 += 4) {
@@ -336,6 +369,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) dh[j] += acc[j];
+        if (etid == 0) TR(cur_it, 5);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -364,7 +398,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
       }
       named_bar(BAR_EPI, 128);
-      if (etid == 0) signal_counter(which ? cnt_gd : cnt_ga);
+      if (etid == 0) { signal_counter(which ? cnt_gd : cnt_ga); TR(cur_it, which ? 2 : 6); }
     };
 
     // ---- GEMM epilogue: drain TMEM, exchange the split-K partials (16 batch rows per rank), sum, write dX rows
@@ -375,6 +409,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       if (etid == 0) mbar_expect_tx(&recv_full[which], 4u * 16u * NC * 4u);
       mbar_wait(&acc_full[which], idx & 1u);
       tc_fence_after();
+      if (etid == 0) TR(cur_it, which ? 7 : 11);
       {
         const int r4 = lane & 3, m4 = lane >> 2;
         // accumulator row (= output column) held by this lane: M=64 keeps rows 16q..16q+15 in lanes 0..15 of quarter q
@@ -411,7 +446,9 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       }
       tc_fence_before();
       mbar_arrive(&acc_free[which]);
+      if (etid == 0) TR(cur_it, which ? 8 : 12);
       mbar_wait_cluster(&recv_full[which], idx & 1u);
+      if (etid == 0) TR(cur_it, which ? 9 : 13);
       {
         const float* rv = which ? recv_d : recv_a;
         float* out = which ? d.DXD : d.DXA;
@@ -432,11 +469,12 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
       }
       named_bar(BAR_EPI, 128);
-      if (etid == 0) signal_counter(which ? cnt_xd : cnt_xa);
+      if (etid == 0) { signal_counter(which ? cnt_xd : cnt_xa); TR(cur_it, which ? 10 : 14); }
     };
 
     for (int it = -1; it < To; ++it) {
       const int t = To - 1 - it, td = t - 1;
+      cur_it = it;
       // D1(td): needs dXD[td+1] (the dXD epilogue of the previous iteration)
       if (td >= 0) cell_bwd(std::integral_constant<int, 1>{}, td, NCTA * (unsigned)(it + 1), 0u, 0u);
       // A2(t): needs dXD[t], DXA[t+1] and dq[t]
@@ -479,10 +517,13 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     float gwl[16];                           // dW_loc[a][16*(atid>>7) .. +16) over this CTA's rows, all steps
 #pragma unroll
     for (int c = 0; c < 16; ++c) gwl[c] = 0.f;
-    float wcacc[8];                          // dW_conv entries atid + 256 m, all steps
+    float wcacc[8];                          // dW_conv[(channel atid>>7, taps 8*((atid>>5)&3) .. +8)][filter atid&31], all steps
 #pragma unroll
     for (int m = 0; m < 8; ++m) wcacc[m] = 0.f;
     float dv_acc = 0.f;                      // dv[a] over rows of row group (atid>>7), all steps
+    float dpm_acc[32];                       // d(processed memory)[row group rows][a], all steps (was 1 M atomics per step)
+#pragma unroll
+    for (int k = 0; k < 32; ++k) dpm_acc[k] = 0.f;
     unsigned seen_xd = 0, seen_xa = 0;
     named_bar(BAR_ATT, 256);
 
@@ -534,8 +575,10 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       // ---- dXD[t] and DXA[t+1] complete device-wide
       if (atid == 0) {
         const unsigned n_xd = NCTA * (unsigned)(it + 1), n_xa = NCTA * (unsigned)it;
+        TR(it, 16);
         if (seen_xd < n_xd) { wait_counter(cnt_xd, n_xd); seen_xd = n_xd; }
         if (seen_xa < n_xa) { wait_counter(cnt_xa, n_xa); seen_xa = n_xa; }
+        TR(it, 17);
       }
       named_bar(BAR_ATT, 256);
       if (active) {
@@ -547,16 +590,17 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           if (hh == 0) d.DCTX[((long long)t * B + b) * ED + col] = v;
         }
         named_bar(BAR_ATT, 256);
+        if (atid == 0) TR(it, 18);
         // ---- dw_i = <dctx, memory_i> + (gradient wrt w_t from step t+1's location conv) + (gradient wrt cum_{t+1})
         {
           float4 dc4[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) dc4[j] = *reinterpret_cast<const float4*>(dctx_s + lane * 4 + 128 * j);
           const float* mb = s.mem + ((long long)b * Ti + i0) * ED + lane * 4;
-          for (int rb = 0; rb < nrow; rb += 32) {
-            float4 mv[4][4];
+          for (int rb = 0; rb < nrow; rb += 16) {
+            float4 mv[2][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 2; ++k) {
               const int rr = rb + aw + 8 * k;
               const bool ld = rr < nrow && (i0 + rr) < len;
 #pragma unroll
@@ -564,7 +608,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
                 mv[k][j] = ld ? ldg_v4_hint(mb + (long long)rr * ED + 128 * j, pol_m) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 2; ++k) {
               const int rr = rb + aw + 8 * k;
               float acc = 0.f;
 #pragma unroll
@@ -576,6 +620,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           }
         }
         named_bar(BAR_ATT, 256);
+        if (atid == 0) TR(it, 19);
         // ---- softmax backward: s = sum_i w_i dw_i over both halves, de_i = w_i (dw_i - s)
         if (aw == 0) {
           float part = 0.f;
@@ -588,25 +633,27 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
         mbar_wait_cluster(x_full, (unsigned)it & 1u);
         named_bar(BAR_ATT, 256);
+        if (atid == 0) TR(it, 20);
         {
           const float ssum = spart[par * 2] + spart[par * 2 + 1];
           if (atid < nrow) de_s[atid] = wt_s[atid] * (dwv_s[atid] - ssum);
         }
         if (nrow > 0) mbar_wait(at_full, (unsigned)it & 1u);
         named_bar(BAR_ATT, 256);
+        if (atid == 0) TR(it, 21);
         // ---- tanh / v backward on this CTA's rows: dpre (kept in place of the saved tanh), dq, dv, d(processed memory)
         {
           const int rbeg = (atid >> 7) * 32;
           float dq_acc = 0.f;
-          float* dpm = d.dpmem + ((long long)b * Ti + i0) * AD + a;
-#pragma unroll 4
-          for (int rr = rbeg; rr < rbeg + 32; ++rr) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const int rr = rbeg + k;
             if (rr < nrow) {
               const float g = de_s[rr];
               const float av = Abuf[rr * AD + a];
               const float dp = g * va * (1.f - av * av);
               Abuf[rr * AD + a] = dp;
-              if (g != 0.f) atomicAdd(dpm + (long long)rr * AD, dp);     // sole writer of the address: RED
+              dpm_acc[k] += dp;
               dq_acc += dp;
               dv_acc = fmaf(g, av, dv_acc);
             }
@@ -614,10 +661,11 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           q_s[(atid >> 7) * 128 + a] = dq_acc;
         }
         named_bar(BAR_ATT, 256);
+        if (atid == 0) TR(it, 22);
         if (atid < AD) atomicAdd(d.DQ + ((long long)t * B + b) * AD + atid, q_s[atid] + q_s[128 + atid]);
       }
       named_bar(BAR_ATT, 256);
-      if (atid == 0) signal_counter(cnt_q);
+      if (atid == 0) { signal_counter(cnt_q); TR(it, 23); }
       // ================= off the critical path: weight gradients of the location layer, adjoint conv for step t-1
       if (active) {
         // ---- dW_loc[a][c] += sum_rows dpre[row][a] f[row][c]   (thread: a, 16 of the 32 filters, all rows)
@@ -654,29 +702,32 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           }
         }
         named_bar(BAR_ATT, 256);             // every reader of f is done: f_s becomes df
+        if (atid == 0) TR(it, 24);
         {
           const int c = atid & 31, r0 = (atid >> 5) * 8;
 #pragma unroll
           for (int j = 0; j < 8; ++j) f_s[(r0 + j) * FS + c] = (r0 + j < nrow) ? dfr[j] : 0.f;
         }
         named_bar(BAR_ATT, 256);
-        // ---- dW_conv[(ch,k)][c] += sum_rows df[row][c] x_ch[row + k - 15]
+        // ---- dW_conv[(ch,k)][c] += sum_rows df[row][c] x_ch[row + k - 15]: thread = (filter c, channel, 8 consecutive taps),
+        // the taps share one sliding window of x (3 shared-memory loads per row instead of 16)
+        {
+          const int c = atid & 31, g = atid >> 5;
+          const int kk0 = 8 * (g & 3);
+          const float* x = ((g >> 2) ? cpad : wpad) + i0 + kk0;
+          for (int rr0 = 0; rr0 < nrow; rr0 += 8) {
+            float xw[16];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          const int e = atid + 256 * m;
-          if (e < 2 * KS * NF) {
-            const int c = e & 31, chk = e >> 5;
-            const float* x = ((chk >= KS) ? cpad : wpad) + i0 + (chk >= KS ? chk - KS : chk);
-            float a0 = 0.f, a1 = 0.f;
-            int rr = 0;
-            for (; rr + 1 < nrow; rr += 2) {
-              a0 = fmaf(f_s[rr * FS + c], x[rr], a0);
-              a1 = fmaf(f_s[(rr + 1) * FS + c], x[rr + 1], a1);
+            for (int i = 0; i < 16; ++i) xw[i] = x[rr0 + i];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const float dfv = f_s[(rr0 + r) * FS + c];          // rows >= nrow hold zeros
+#pragma unroll
+              for (int e = 0; e < 8; ++e) wcacc[e] = fmaf(dfv, xw[r + e], wcacc[e]);
             }
-            if (rr < nrow) a0 = fmaf(f_s[rr * FS + c], x[rr], a0);
-            wcacc[m] += a0 + a1;
           }
         }
+        if (atid == 0) TR(it, 25);
         // ---- adjoint conv: dx[ch][s] = sum_{k,c} df[s-k+15][c] W_conv[c][ch][k], s in [i0-15, i0+nrow+15);
         // own rows stay here, the rows of the other half go to the partner CTA
         if (t > 0) {
@@ -717,19 +768,27 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
       }
       named_bar(BAR_ATT, 256);
+      if (atid == 0) TR(it, 26);
     }
     // ---- sequence-long accumulators -> the partial buffers the engine reduces over (slot 0 of the utterance)
     if (active) {
       const int nck = (Ti + 31) / 32;
       const long long slot = (long long)b * nck;
       atomicAdd(d.dv_part + slot * AD + a, dv_acc);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {         // single writer per element; the caller zero-initialised the buffer
+        const int rr = (atid >> 7) * 32 + k;
+        if (rr < nrow) d.dpmem[((long long)b * Ti + i0 + rr) * AD + a] = dpm_acc[k];
+      }
       float* wl = d.dwloc_part + slot * (AD * NF) + a * NF + (atid >> 7) * 16;
 #pragma unroll
       for (int c = 0; c < 16; ++c) atomicAdd(wl + c, gwl[c]);
+      {
+        const int c = atid & 31, g = atid >> 5;
+        const int kk0 = 8 * (g & 3);
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int e = atid + 256 * m;
-        if (e < 2 * KS * NF) atomicAdd(d.dwconv_part + slot * (2 * KS * NF) + e, wcacc[m]);
+        for (int e = 0; e < 8; ++e)
+          if (kk0 + e < KS) atomicAdd(d.dwconv_part + slot * (2 * KS * NF) + ((g >> 2) * KS + kk0 + e) * NF + c, wcacc[e]);
       }
     }
   }
@@ -782,18 +841,55 @@ int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStre
   p.d = *d;
   p.counters = reinterpret_cast<unsigned*>(d->dHq);          // scratch [B,1024] floats, unused by this path otherwise
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+  p.rotate = env_int("T2V_PERSIST_ROTATE", 1);
+  p.dbg_skip = env_int("T2V_PERSIST_DBG_SKIP", 0);
   p.wa_hint = env_int("T2V_PERSIST_BWD_WA_HINT", 1);
   p.wd_hint = env_int("T2V_PERSIST_BWD_WD_HINT", 2);
+  p.trace = nullptr;
+  const bool trace = getenv("T2V_PERSIST_TRACE") != nullptr && s->To >= TRACE_I0 + TRACE_STEPS + 2;
+  const size_t trace_bytes = 2 * TRACE_STEPS * 32 * sizeof(long long);
+  if (trace) {
+    T2V_CUDA_CHECK(cudaMalloc(&p.trace, trace_bytes));
+    T2V_CUDA_CHECK(cudaMemsetAsync(p.trace, 0, trace_bytes, stream));
+  }
   CUtensorMap tmWa, tmWd64, tmWd16, tmGA, tmGD;
   const long long rows = (long long)s->To * s->B;
   int r;
-  if ((r = t2v_encode_tmap_2d(&tmWa, d->WaT, 4, 4 * H, XA_W, 4 * H, XA_CPC))) return r;
-  if ((r = t2v_encode_tmap_2d(&tmWd64, d->WdT, 4, 4 * H, XD_W, 4 * H, 64))) return r;
-  if ((r = t2v_encode_tmap_2d(&tmWd16, d->WdT, 4, 4 * H, XD_W, 4 * H, 16))) return r;
+  p.packed = (d->WaTP && d->WdTP && env_int("T2V_PERSIST_PACKED", 1)) ? 1 : 0;
+  if (p.packed) {
+    if ((r = t2v_encode_tmap_2d(&tmWa, d->WaTP, 4, 32, (long long)NCTA * KCH * XA_CPC, 32, XA_CPC))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmWd64, d->WdTP, 4, 32, (long long)NCTA * KCH * XD_CPC, 32, 64))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmWd16, d->WdTP, 4, 32, (long long)NCTA * KCH * XD_CPC, 32, 16))) return r;
+  } else {
+    if ((r = t2v_encode_tmap_2d(&tmWa, d->WaT, 4, 4 * H, XA_W, 4 * H, XA_CPC))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmWd64, d->WdT, 4, 4 * H, XD_W, 4 * H, 64))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmWd16, d->WdT, 4, 4 * H, XD_W, 4 * H, 16))) return r;
+  }
   if ((r = t2v_encode_tmap_2d(&tmGA, d->DGA, 4, 4 * H, rows, 4 * H, 64))) return r;
   if ((r = t2v_encode_tmap_2d(&tmGD, d->DGD, 4, 4 * H, rows, 4 * H, 64))) return r;
   T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 160 * sizeof(unsigned), stream));
   T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel, tmWa, tmWd64, tmWd16, tmGA, tmGD, p));
   T2V_COUNT_LAUNCH();
+  if (trace) {      // debugging aid: not usable under stream capture
+    static const char* names[31] = {"E:D1 start", "E:D1 inputs seen", "E:D1 DGD signalled", "E:A2 dq seen", "E:A2 dq staged",
+                                    "E:A2 dHq done", "E:A2 DGA signalled", "E:D2 acc full", "E:D2 pushed", "E:D2 recv full",
+                                    "E:D2 dXD signalled", "E:A3 acc full", "E:A3 pushed", "E:A3 recv full", "E:A3 DXA signalled",
+                                    "E:A2 start", "T:pre done, wait", "T:inputs seen", "T:dctx done", "T:dw done", "T:s exchanged",
+                                    "T:de + tanh tile", "T:dpre done", "T:dq signalled", "T:dWloc + df done", "T:dWconv done",
+                                    "T:adjoint + halo done", "M:D2 first chunk", "M:D2 committed", "M:A3 first chunk", "M:A3 committed"};
+    long long h[2 * TRACE_STEPS * 32];
+    T2V_CUDA_CHECK(cudaStreamSynchronize(stream));
+    T2V_CUDA_CHECK(cudaMemcpy(h, p.trace, trace_bytes, cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    for (int c = 0; c < 2; ++c) {
+      const long long base = h[(c * TRACE_STEPS) * 32 + 17];     // "inputs seen" of the first traced iteration
+      fprintf(stderr, "[t2v persist bwd trace] CTA %d: SM clocks relative to 'T:inputs seen' of iteration %d\n", c ? TRACE_CTA_B : 0, TRACE_I0);
+      for (int ev = 0; ev < 31; ++ev) {
+        fprintf(stderr, "  %-24s", names[ev]);
+        for (int n = 0; n < TRACE_STEPS; ++n) fprintf(stderr, " %8lld", h[(c * TRACE_STEPS + n) * 32 + ev] ? h[(c * TRACE_STEPS + n) * 32 + ev] - base : -1);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   return 0;
 }

@@ -34,6 +34,16 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// non-blocking phase test (the MMA loop polls the NEXT stage with it while it issues the current one)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // bounded spins: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU box
 constexpr long long WAIT_LIMIT = 4000000000LL;     // ~2 s of SM clocks
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -56,6 +66,13 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+// one lane of a converged warp (the compiler knows the predicate is warp-uniform-exclusive: tcgen05 issue without the
+// per-lane "waterfall" loop it emits around instructions with possibly divergent uniform operands)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -24,13 +24,13 @@ class T2VDecoderSeq(ctypes.Structure):
                  ("seed", ctypes.c_ulonglong), ("drop_masks", _P), ("mask_value", ctypes.c_float), ("in_lens", _P)] +
                 [(n, _P) for n in ("Wa", "ba1", "ba2", "Wd", "bd1", "bd2", "Wq", "Wconv", "Wloc", "v", "mem", "pmem",
                                    "XA", "XD", "CA", "CD", "CUM", "align", "GA", "GD", "CPA", "CPD", "ASAVE", "parts",
-                                   "qparts", "ebuf")])
+                                   "qparts", "ebuf", "WaP", "WdP")])
 
 
 class T2VDecoderBwd(ctypes.Structure):
     _fields_ = [("f", T2VDecoderSeq)] + [(n, _P) for n in (
         "WaT", "WdT", "WqT", "DHC", "DGA", "DGD", "DXA", "DXD", "dCa", "dCd", "dwprev", "gcum", "dpmem", "DCTX", "dw_part",
-        "DQ", "dHq", "dv_part", "dwloc_part", "dwconv_part")]
+        "DQ", "dHq", "dv_part", "dwloc_part", "dwconv_part", "WaTP", "WdTP")]
 
 
 class T2VDecoderInfer(ctypes.Structure):

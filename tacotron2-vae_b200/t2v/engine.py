@@ -581,6 +581,7 @@ def _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_v
     S.Wa, S.Wd = W["Wa"].data_ptr(), W["Wd"].data_ptr()
     S.ba1, S.ba2 = P[_D + "attention_rnn.bias_ih"].data_ptr(), P[_D + "attention_rnn.bias_hh"].data_ptr()
     S.bd1, S.bd2 = P[_D + "decoder_rnn.bias_ih"].data_ptr(), P[_D + "decoder_rnn.bias_hh"].data_ptr()
+    S.WaP, S.WdP = _lib.ptr(W.get("WaP")), _lib.ptr(W.get("WdP"))
     S.Wq = W["Wq"].data_ptr()
     S.Wconv = W["WconvT"].data_ptr()          # [2*31, 32]: taps-major transpose of the location conv weight
     S.Wloc = P[_A + "location_layer.location_dense.linear_layer.weight"].data_ptr()
@@ -612,6 +613,10 @@ def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, dro
     W["Wa"], W["Wd"], W["Wpg"], W["bpg"] = pack_decoder_weights(P, dev, ops.R)
     W["Wq"] = ops.wr(P[_A + "query_layer.linear_layer.weight"])
     W["WconvT"] = conv_weight_T(P, dev)
+    if ops.tc:      # tile-contiguous copies for the persistent loop kernel (decoder_persist.cu)
+        W["WaP"], W["WdP"] = _empty(4096, 1792, device=dev), _empty(4096, 2560, device=dev)
+        L("t2v_pack_step_tiles", W["Wa"], 0, W["WaP"])
+        L("t2v_pack_step_tiles", W["Wd"], 1, W["WdP"])
     pmem = _empty(B * Ti, 128, device=dev)
     ops.linear(memory, 512, ops.wr(P[_A + "memory_layer.linear_layer.weight"]), 512, pmem, 128, B * Ti, 128, 512)
     buf = alloc_decoder_buffers(B, Ti, To, dev, save=True)
@@ -666,6 +671,11 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
     L("t2v_transpose", W["Wa"], 1792, WaT, 4096, 4096, 1792, 0)
     L("t2v_transpose", W["Wd"], 2560, WdT, 4096, 4096, 2560, 0)
     L("t2v_transpose", Wq, 1024, WqT, 128, 128, 1024, 0)
+    WaTP = WdTP = None
+    if ops.tc:      # tile-contiguous copies for the persistent reverse loop (decoder_persist_bwd.cu)
+        WaTP, WdTP = _empty(1792, 4096, device=dev), _empty(2560, 4096, device=dev)
+        L("t2v_pack_step_tiles", WaT, 2, WaTP)
+        L("t2v_pack_step_tiles", WdT, 3, WdTP)
     _trace("  bwd proj")
     nck = int(_lib.lib().t2v_attn2_chunks(Ti))
     D = _lib.T2VDecoderBwd()
@@ -678,6 +688,8 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
              dwloc_part=_zeros(B * nck, 128 * 32, device=dev), dwconv_part=_zeros(B * nck, 32 * 2 * 31, device=dev))
     for k, v in t.items():
         setattr(D, k, v.data_ptr())
+    D.WaTP, D.WdTP = _lib.ptr(WaTP), _lib.ptr(WdTP)
+    t["_packed"] = (WaTP, WdTP)
     L("t2v_decoder_bwd_steps", D, To, 0)
     _trace("  bwd decoder loop")
     if ops.tc:
