@@ -250,6 +250,7 @@ def main():
     # GEMM_d, cell), timed with CUDA events over a fresh forward's time loop
     roof = decoder_step_roofline(m, hp, B, Ti, To, dev, a.precision)
     infer_step = inference_decoder_step(m, dev, a.precision) if rank == 0 else None
+    bwd_step = decoder_step_backward(m, B, Ti, To, dev, a.precision) if rank == 0 else None
 
     _progress("roofline done")
     cpu = None
@@ -271,10 +272,55 @@ def main():
                        "l2": "per-step working set (>3 GB of saved activations) exceeds the 126 MB L2"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": launches, "roofline": roof, "decoder_step_inference": infer_step, "cpu_baseline": cpu,
+            "gpu_launches": launches, "roofline": roof, "decoder_step_inference": infer_step, "decoder_step_backward": bwd_step, "cpu_baseline": cpu,
             "clocks": sampler.summary()}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def decoder_step_backward(m, B, Ti, To, dev, precision):
+    """Times the reverse-time decoder loop alone (t2v_decoder_bwd_steps over To steps: dec_persist_bwd_kernel when it applies)
+    with CUDA events around the launch inside engine.decoder_backward.  Algorithmic bytes per step: the same fp32 weights as the
+    forward step (72.4 MB, read once) + saved activations of the step + gate-gradient rows written."""
+    from t2v import engine
+    import t2v.engine as E
+    with torch.no_grad():
+        ops = engine.Ops(precision)
+        P = m._state()
+        mem = torch.randn(B, Ti, 512, device=dev)
+        mel = torch.randn(B, 80, To, device=dev)
+        in_len = torch.full((B,), Ti, device=dev, dtype=torch.long)
+        dO = torch.randn(To * B, 84, device=dev) * 0.1
+        _, _, ctx = engine.decoder_forward(ops, P, mem, mel, in_len, True, None, None, 1, -float("inf"), dev)
+        times = []
+        orig = E.L
+
+        def timed_L(name, *args):
+            if name != "t2v_decoder_bwd_steps":
+                return orig(name, *args)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            r = orig(name, *args)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e3 / To)
+            return r
+        E.L = timed_L
+        try:
+            for _ in range(3):
+                _, br = engine.decoder_backward(ops, P, dO, ctx, dev, {})
+                br.join()
+                torch.cuda.synchronize()
+        finally:
+            E.L = orig
+    us = min(times[1:])
+    s4 = 4
+    alg = 18103953 * s4 + (B * Ti * 640 + B * Ti * 128 + B * (4096 * 4 + 1024 * 4 + 1792 + 2560 + 1536)) * s4
+    return {"value": us, "unit": "us/step", "batch": B, "text_len": Ti, "steps": To, "algorithmic_bytes_per_step": alg,
+            "achieved_gbs": alg / (us * 1e-6) / 1e9,
+            "what": "reverse-time Decoder.decode step (both LSTM cell backwards, attention backward incl. location-layer weight "
+                    "gradients, dX GEMMs): dec_persist_bwd_kernel time / To"}
 
 
 def inference_decoder_step(m, dev, precision, B=16, Ti=120, n=1000):
