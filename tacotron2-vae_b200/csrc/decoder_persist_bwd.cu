@@ -215,8 +215,8 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       }
     }
   } else if (warp == 2 || warp == 3) {
-    // =========================================================================== MMA issuer(s).  Default: warp 2 issues every
-    // chunk (deterministic accumulation order).  T2V_PERSIST_TWO_ISSUERS=1: warps 2 and 3 issue the even / odd K chunks;
+    // =========================================================================== MMA issuer(s).  Default (T2V_PERSIST_TWO_ISSUERS=1):
+    // warps 2 and 3 issue the even / odd K chunks (=0: warp 2 issues every chunk, deterministic accumulation order);
     // accumulation into the same TMEM columns commutes, only the chunk that initialises the accumulator (j = 0, warp 2) has
     // to be issued first (named barrier) and the accumulator-complete barrier counts one commit per issuer.  Measured: the
     // small-N tf32 MMAs (128x64x8: ~100-140 cycles each) bound the GEMM phases either way (17.6 k vs 19 k cycles per dXD GEMM).
@@ -855,9 +855,9 @@ int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStre
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
   p.rotate = env_int("T2V_PERSIST_ROTATE", 1);
   p.dbg_skip = env_int("T2V_PERSIST_DBG_SKIP", 0);
-  // two issuers are ~2 % faster on the reverse loop but make the fp32 accumulation order (and so the last bits of every
-  // gradient) vary from run to run; the default keeps the loop deterministic
-  p.two_issuers = env_int("T2V_PERSIST_TWO_ISSUERS", 0);
+  // two issuers: 33.8 vs 36-37 us per step with this loop; the fp32 accumulation order of the dX GEMMs (and so the last bits of the
+  // gradients) then varies from run to run, like the atomics of the embedding / dq / split-K paths already do.  =0: one issuer.
+  p.two_issuers = env_int("T2V_PERSIST_TWO_ISSUERS", 1);
   p.wa_hint = env_int("T2V_PERSIST_BWD_WA_HINT", 1);
   p.wd_hint = env_int("T2V_PERSIST_BWD_WD_HINT", 2);
   p.trace = nullptr;
