@@ -369,7 +369,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         if (16 * rank < B) mbar_wait(dq_full, (unsigned)cur_it & 1u);
         if (etid == 0) TR(cur_it, 4);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
+#pragma unroll 8
         for (int a0 = 0; a0 < AD; a0 += 4) {
           const float w0 = WqS[a0 * 32 + u], w1 = WqS[(a0 + 1) * 32 + u], w2 = WqS[(a0 + 2) * 32 + u], w3 = WqS[(a0 + 3) * 32 + u];
 #pragma unroll
