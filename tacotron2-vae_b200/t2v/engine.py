@@ -42,6 +42,7 @@ _ctypes = _lib.ctypes
 
 _SIDE = {}
 _OVERLAP = __import__("os").environ.get("T2V_OVERLAP", "1") != "0"
+_POST_DW_BRANCH = __import__("os").environ.get("T2V_POST_DW_BRANCH", "1") != "0"
 
 
 class _Branch(object):
@@ -51,6 +52,7 @@ class _Branch(object):
     new fork, so block reuse stays stream-ordered.  T2V_OVERLAP=0 runs everything in order on one stream."""
 
     def __init__(self, idx):
+        self.keep = None
         self.main = torch.cuda.current_stream()
         if _OVERLAP:
             key = (self.main.device_index, idx)
@@ -262,10 +264,25 @@ def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, se
     return X, saved
 
 
-def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0, dev, grads, need_dx):
+class _NoBranch(object):
+    keep = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0, dev, grads, need_dx, dw_branch=None):
+    """dw_branch: a _Branch on which the weight gradients (transposes + row-reduction GEMMs: off the dX chain) are enqueued;
+    the caller joins it.  Tensors the branch reads are kept alive in dw_branch.keep until then."""
     Tp = T + 4
     R = B * Tp
     M = R - 4
+    br = dw_branch if dw_branch is not None else _NoBranch()
+    if dw_branch is not None and dw_branch.keep is None:
+        dw_branch.keep = []
     for i in range(len(saved) - 1, -1, -1):
         s = saved[i]
         Ci, Co = s["Ci"], s["Co"]
@@ -274,23 +291,26 @@ def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0
         _bn_backward(dOut, s["Y"], dY, R, Co, Tp, 2, 2 + T, B * T, P, pre + ".1", training, s["act"], s["mask"], seed,
                      site0 + i, s["p"], T, dev, grads, rnd=ops.R)
         grads[pre + ".0.conv.bias"] = _colsum(dY, R, Co, Tp, 2, 2 + T, dev)
-        # weight gradient in tap-major form: dWk[co, tap*Ci+ci] = sum_r dY[r+2, co] * X[r+tap, ci]
-        dWk = _zeros(Co, 5 * Ci, device=dev)
-        if ops.tc:
-            # K-major operands for the row reduction: dyT[co, r] = dY[r+2, co]; xT[ci, r] = X[r+tap, ci].  The tap shift is
-            # applied while transposing because TMA needs 16-byte aligned inner coordinates.
-            Mp = _ceil4(M)
-            dyT = _zeros(Co, Mp, device=dev)
-            L("t2v_transpose", _p(dY, 2 * Co), Co, dyT, Mp, M, Co, 1)
-            xT = _zeros(Ci, Mp, device=dev)
-            for tap in range(5):
-                L("t2v_transpose", _p(s["X"], tap * Ci), Ci, xT, Mp, M, Ci, 1)
-                Ops._tc_reduce_rows(dyT, Mp, Co, 0, xT, Mp, Ci, 0, _p(dWk, tap * Ci), 5 * Ci, M, True)
-        else:
-            ops.gemm(_p(dY, 2 * Co), 1, Co, s["X"], 1, Ci, dWk, 5 * Ci, Co, 5 * Ci, M, 1.0, 0.0, None)
-        gW = _empty(Co, Ci, 5, device=dev)
-        L("t2v_conv1d_unpack_grad", dWk, gW, Co, Ci, 5, 0.0)
-        grads[pre + ".0.conv.weight"] = gW
+        if dw_branch is not None:
+            dw_branch.keep.append(dY)
+        with br:
+            # weight gradient in tap-major form: dWk[co, tap*Ci+ci] = sum_r dY[r+2, co] * X[r+tap, ci]
+            dWk = _zeros(Co, 5 * Ci, device=dev)
+            if ops.tc:
+                # K-major operands for the row reduction: dyT[co, r] = dY[r+2, co]; xT[ci, r] = X[r+tap, ci].  The tap shift
+                # is applied while transposing because TMA needs 16-byte aligned inner coordinates.
+                Mp = _ceil4(M)
+                dyT = _zeros(Co, Mp, device=dev)
+                L("t2v_transpose", _p(dY, 2 * Co), Co, dyT, Mp, M, Co, 1)
+                xT = _zeros(Ci, Mp, device=dev)
+                for tap in range(5):
+                    L("t2v_transpose", _p(s["X"], tap * Ci), Ci, xT, Mp, M, Ci, 1)
+                    Ops._tc_reduce_rows(dyT, Mp, Co, 0, xT, Mp, Ci, 0, _p(dWk, tap * Ci), 5 * Ci, M, True)
+            else:
+                ops.gemm(_p(dY, 2 * Co), 1, Co, s["X"], 1, Ci, dWk, 5 * Ci, Co, 5 * Ci, M, 1.0, 0.0, None)
+            gW = _empty(Co, Ci, 5, device=dev)
+            L("t2v_conv1d_unpack_grad", dWk, gW, Co, Ci, 5, 0.0)
+            grads[pre + ".0.conv.weight"] = gW
         if i > 0 or need_dx:
             Wd = _empty(Ci, 5 * Co, device=dev)
             L("t2v_conv1d_pack", s["W"], Wd, Co, Ci, 5, 1, ops.R)
@@ -819,8 +839,11 @@ def backward_train(ops, P, c, dmel, dpost, dgate, dmu, dlogvar):
     _trace("")
     dY5 = _zeros(R, 80, device=dev)
     L("t2v_bct_to_padded", dpost, dY5, B, 80, To, 0.0)
+    # the Postnet weight gradients are off the path to the decoder: a side branch that runs beside the dX chain and then on
+    # the ~20 SMs the persistent decoder-backward kernel leaves free
+    br_post = _Branch(2) if _POST_DW_BRANCH else None
     dX0 = conv_stack_backward(ops, P, "postnet.convolutions", dY5, c.post, B, To, c.training, c.seed, SITE_POST, dev, grads,
-                              need_dx=True)
+                              need_dx=True, dw_branch=br_post)
     _trace("bwd postnet")
     dres = _zeros(R, 80, device=dev)                      # dmel + dpost (residual, model.py:543)
     L("t2v_bct_to_padded", dmel, dres, B, 80, To, 0.0)
@@ -839,5 +862,7 @@ def backward_train(ops, P, c, dmel, dpost, dgate, dmu, dlogvar):
     encoder_backward(ops, P, dmem, c.enc, c.training, c.seed, dev, grads)
     br_vae.join()
     br_dw.join()
+    if br_post is not None:
+        br_post.join()
     _trace("bwd encoder + vae/ref-encoder + decoder dW")
     return grads
