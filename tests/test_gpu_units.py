@@ -358,3 +358,46 @@ def test_persistent_decoder_backward_matches_per_step_launches(L, B, Ti, To):
         err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
         print("persistent bwd vs per-step %-60s max-rel %.3e" % (k, err))
         assert err <= 2e-3, (k, err)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_pack_step_tiles_is_a_pure_permutation(L, mode):
+    """t2v_pack_step_tiles re-tiles a decoder-step weight matrix into the order the persistent loop kernels stream it:
+    bit-exact gather, checked against the index arithmetic documented in decoder_persist.cu (forward: [cluster][rank][chunk]
+    [gate*32+unit][32 k], K offsets in the order prenet / h_att / ctx resp. h_att / ctx / h_dec; backward: [cluster][rank]
+    [chunk][output column][32 gate rows])."""
+    dev = torch.device("cuda")
+    K = 1792 if mode in (0, 2) else 2560
+    g = torch.Generator().manual_seed(mode)
+    if mode < 2:
+        W = torch.randn(4096, K, generator=g).to(dev)
+        nch = 14 if mode == 0 else 20
+
+        def kofs(j, r):
+            if mode == 0:
+                return 64 * r + 32 * j if j < 2 else (768 + 256 * r + 32 * (j - 2) if j < 10 else 256 + 128 * r + 32 * (j - 10))
+            return 256 * r + 32 * j if j < 8 else (1024 + 128 * r + 32 * (j - 8) if j < 12 else 1536 + 256 * r + 32 * (j - 12))
+        ref = torch.empty(32, 4, nch, 128, 32, device=dev)
+        rows = torch.arange(128, device=dev)
+        for c in (0, 5, 31):
+            src_rows = (rows // 32) * 1024 + 32 * c + (rows % 32)
+            for r in range(4):
+                for j in range(nch):
+                    ref[c, r, j] = W[src_rows][:, kofs(j, r):kofs(j, r) + 32]
+        check = (0, 5, 31)
+    else:
+        W = torch.randn(K, 4096, generator=g).to(dev)
+        cpc = K // 32
+        ref = torch.empty(32, 4, 32, cpc, 32, device=dev)
+        for c in (0, 7, 31):
+            for r in range(4):
+                for j in range(32):
+                    ref[c, r, j] = W[cpc * c:cpc * (c + 1), 1024 * r + 32 * j:1024 * r + 32 * j + 32]
+        check = (0, 7, 31)
+    out = torch.empty(4096 * K, device=dev)
+    L("t2v_pack_step_tiles", W, mode, out)
+    torch.cuda.synchronize()
+    out = out.view(ref.shape)
+    for c in check:
+        assert torch.equal(out[c], ref[c]), (mode, c)
+    assert torch.equal(out.flatten().sort()[0], W.flatten().sort()[0])      # a permutation: nothing lost, nothing duplicated
