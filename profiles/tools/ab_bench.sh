@@ -1,4 +1,13 @@
-# A/B of engine-level switches on the bench line (ms per train step)
+# A/B of the Postnet-dW side branch on the bench line (ms per train step, or the failure)
 python -c "import torch; torch.zeros(1).cuda()"
-for v in 1 0; do echo "== T2V_POST_DW_BRANCH=$v"; T2V_POST_DW_BRANCH=$v timeout 300 python bench.py --no-cpu-baseline --steps 5 --warmup 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'])"; done
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -1
+for v in 1 0 1 0; do
+  echo "== T2V_POST_DW_BRANCH=$v"
+  T2V_POST_DW_BRANCH=$v timeout 200 python bench.py --no-cpu-baseline --steps 5 --warmup 3 > /tmp/ab.json 2> /tmp/ab.err
+  echo "rc=$?"; python - <<'PY'
+import json
+try:
+    d = json.load(open("/tmp/ab.json")); print("ms_per_step", d["ms_per_step"], "bwd", d["decoder_step_backward"]["value"])
+except Exception as e:
+    print("FAILED:", open("/tmp/ab.err").read()[-1500:].split("Traceback")[-1][:600])
+PY
+done

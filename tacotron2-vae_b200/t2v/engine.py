@@ -42,7 +42,11 @@ _ctypes = _lib.ctypes
 
 _SIDE = {}
 _OVERLAP = __import__("os").environ.get("T2V_OVERLAP", "1") != "0"
-_POST_DW_BRANCH = __import__("os").environ.get("T2V_POST_DW_BRANCH", "1") != "0"
+# Postnet weight gradients on a side branch beside the persistent decoder-backward kernel: 76.9 -> 75.1 ms per train step when it
+# works, but 2 of 4 bench runs died with "unspecified launch failure" (a bounded wait trapping; not reproduced with the branch off in
+# 6 runs).  Until the interaction of other resident grids with the 128 co-resident CTAs of the persistent kernels is understood, nothing
+# runs concurrently with them: OFF by default.
+_POST_DW_BRANCH = __import__("os").environ.get("T2V_POST_DW_BRANCH", "0") == "1"
 
 
 class _Branch(object):
