@@ -13,6 +13,7 @@
 
 int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);   // decoder_persist.cu
 int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStream_t stream);         // decoder_persist_bwd.cu
+int t2v_decoder_infer_persist(const T2VDecoderInfer* d, int t_begin, int t_end, cudaStream_t stream);  // decoder_persist.cu
 
 namespace {
 
@@ -386,6 +387,10 @@ T2V_API int t2v_decoder_infer_steps(const T2VDecoderInfer* d, int t_begin, int t
   const T2VDecoderSeq* s = &d->f;
   T2V_ARG_CHECK(s->B > 0 && s->Ti > 0 && s->To > 0, "shape");
   T2V_ARG_CHECK(t_begin >= 0 && t_end <= s->To && t_begin <= t_end, "step range");
+  if (!getenv("T2V_STEP_PROFILE")) {
+    const int r = t2v_decoder_infer_persist(d, t_begin, t_end, st);     // the whole free-running loop as one persistent kernel; 1 = n/a
+    if (r != 1) return r;
+  }
   const bool tc = s->use_tc != 0;
   const int B = s->B;
   FwdPlans P;

@@ -67,7 +67,16 @@ struct PersistParams {
   int packed;              // tmWa / tmWd describe the re-tiled copies (one contiguous 16 KB box per chunk)
   int wa_hint, wd_hint, mem_hint;   // L2 eviction priority of the weight streams / the encoder memory: 0 normal, 1 evict_last, 2 evict_first
   long long* trace;        // T2V_PERSIST_TRACE: [2 CTAs][TRACE_STEPS][32] clock64 stamps, else nullptr
+  // ---- free-running inference (Decoder.inference, model.py:428-464) only
+  const float *Wp1, *Wp2, *Wpg, *bpg;   // prenet [256,80], [256,256]; [linear_projection ; gate_layer] [81,1536], bias [81]
+  const float* prenet_masks;            // [n,2,B,256] or nullptr (counter RNG)
+  float* O;                             // [n,B,84] mel | gate rows
+  float* opart;                         // [2][NCLUSTER][B][84] per-cluster partial projections of h_dec
+  float* ocpart;                        // [2][B][2][84] per-CTA partial projections of ctx
+  float gate_threshold;
+  int* n_frames;                        // [B] or nullptr
 };
+constexpr unsigned SITE_PRENET0 = 3, SITE_PRENET1 = 4;
 constexpr int TRACE_T0 = 100, TRACE_STEPS = 4, TRACE_CTA_B = 77;
 
 // K offset (columns of the weight matrix = columns of the activation row) of chunk j of this CTA's K slice.
@@ -85,6 +94,13 @@ __device__ __forceinline__ int dec_kofs(int j, int rank) {
   return H + ED + 256 * rank + 32 * (j - 12);
 }
 
+// Free-running inference: the prenet of step t needs the mel frame of step t-1, so its chunks come LAST in the attention_rnn GEMM
+// (h_att_{t-1}, ctx_{t-1} are older), and the decoder_rnn GEMM of step t runs inside step t: h_dec_{t-1} first, ctx_t last.
+// The functions return the chunk index of the teacher-forcing order (tile index of the packed weights); kofs follows from it.
+__device__ __forceinline__ int att_chunk_infer(int j) { return j < 8 ? j + 2 : (j < 12 ? j + 2 : j - 12); }   // h(8) ctx(4) prenet(2)
+__device__ __forceinline__ int dec_chunk_infer(int j) { return j < 8 ? j + 12 : (j < 16 ? j - 8 : j - 8); }    // h_dec(8) h_att(8) ctx(4)
+
+template <bool INFER>
 __global__ void __launch_bounds__(NTHREADS, 1)
 dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_constant__ CUtensorMap tmWd,
                        const __grid_constant__ CUtensorMap tmXA, const __grid_constant__ CUtensorMap tmXD,
@@ -121,6 +137,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   unsigned* cnt_h = p.counters;
   unsigned* cnt_c = p.counters + 32;
   unsigned* cnt_d = p.counters + 64;
+  unsigned* cnt_p = p.counters + 96;      // inference: prenet rows of step t complete
   // debug time stamps of a few mid-sequence steps (two CTAs); compiled in, one predictable branch per event when off
   const int trace_slot = (blockIdx.x == 0) ? 0 : ((blockIdx.x == TRACE_CTA_B) ? 1 : -1);
   auto TR = [&](unsigned n, int ev) {
@@ -174,10 +191,17 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
         ++iw;
       };
-      for (int t = tb; t <= te; ++t) {
-        if (t < te) for (int j = 0; j < ATT_CHUNKS; ++j) { load_w(&tmWa, att_kofs(j, rank), (cid * CL + rank) * ATT_CHUNKS + j, p.wa_hint, pol_a); if (j == 0) TR(t - tb, 24); }
-        if (t > tb) for (int j = 0; j < DEC_CHUNKS; ++j) load_w(&tmWd, dec_kofs(j, rank), (cid * CL + rank) * DEC_CHUNKS + j, p.wd_hint, pol_d);
-        TR(t - tb, 25);
+      if (INFER) {
+        for (int t = tb; t < te; ++t) {
+          for (int j = 0; j < ATT_CHUNKS; ++j) { const int c = att_chunk_infer(j); load_w(&tmWa, att_kofs(c, rank), (cid * CL + rank) * ATT_CHUNKS + c, p.wa_hint, pol_a); }
+          for (int j = 0; j < DEC_CHUNKS; ++j) { const int c = dec_chunk_infer(j); load_w(&tmWd, dec_kofs(c, rank), (cid * CL + rank) * DEC_CHUNKS + c, p.wd_hint, pol_d); }
+        }
+      } else {
+        for (int t = tb; t <= te; ++t) {
+          if (t < te) for (int j = 0; j < ATT_CHUNKS; ++j) { load_w(&tmWa, att_kofs(j, rank), (cid * CL + rank) * ATT_CHUNKS + j, p.wa_hint, pol_a); if (j == 0) TR(t - tb, 24); }
+          if (t > tb) for (int j = 0; j < DEC_CHUNKS; ++j) load_w(&tmWd, dec_kofs(j, rank), (cid * CL + rank) * DEC_CHUNKS + j, p.wd_hint, pol_d);
+          TR(t - tb, 25);
+        }
       }
     }
   } else if (warp == 1) {
@@ -199,6 +223,24 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         tma_load_2d(aring + st * A_STAGE, tm, kofs, row0, &full[st]);
         ++ia;
       };
+      unsigned seen_p = 0;
+      if (INFER) {
+        for (int t = tb; t < te; ++t) {
+          const unsigned n = (unsigned)(t - tb);
+          for (int j = 0; j < ATT_CHUNKS; ++j) {
+            if (j < 8) need(cnt_h, seen_h, NCTA * n);
+            else if (j < 12) need(cnt_c, seen_c, NCTA * n);
+            else need(cnt_p, seen_p, NCTA * (n + 1));
+            load_a(&tmXA, att_kofs(att_chunk_infer(j), rank), t * B);
+          }
+          for (int j = 0; j < DEC_CHUNKS; ++j) {
+            if (j < 8) need(cnt_d, seen_d, NCTA * n);
+            else if (j < 16) need(cnt_h, seen_h, NCTA * (n + 1));
+            else need(cnt_c, seen_c, NCTA * (n + 1));
+            load_a(&tmXD, dec_kofs(dec_chunk_infer(j), rank), t * B);
+          }
+        }
+      } else
       for (int t = tb; t <= te; ++t) {
         const unsigned n = (unsigned)(t - tb);
         if (t < te) {
@@ -262,10 +304,17 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           st = sn; ph = pn;
         }
       };
-      for (int t = tb; t <= te; ++t) {
-        const unsigned n = (unsigned)(t - tb);
-        if (t < te) gemm(0, ATT_CHUNKS, n);
-        if (t > tb) gemm(1, DEC_CHUNKS, n - 1);
+      if (INFER) {
+        for (int t = tb; t < te; ++t) {
+          gemm(0, ATT_CHUNKS, (unsigned)(t - tb));
+          gemm(1, DEC_CHUNKS, (unsigned)(t - tb));
+        }
+      } else {
+        for (int t = tb; t <= te; ++t) {
+          const unsigned n = (unsigned)(t - tb);
+          if (t < te) gemm(0, ATT_CHUNKS, n);
+          if (t > tb) gemm(1, DEC_CHUNKS, n - 1);
+        }
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -384,7 +433,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         const float hd = t2v_rnd(h2 * kh, rnd);
         cst[j] = c2 * kc;
         sv_i[j] = ig; sv_f[j] = fg; sv_g[j] = gg; sv_o[j] = og; sv_c2[j] = c2;
-        if (which == 0) hq[bl * 32 + u] = hd;
+        if (which == 0 || INFER) hq[bl * 32 + u] = hd;
         if (b < B) {       // only what other CTAs wait for goes out before the signal
           if (which == 0) {
             s.XA[(r1 + b) * XA_W + (PD + ED) + jg] = hd;       // h_att -> next step's recurrent input
@@ -413,6 +462,33 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           if (b < B) qp[(long long)b * AD] = (a0 + a1) + (a2 + a3);
         }
       }
+      if (INFER && which == 1) {
+        // ---- inference: partial mel / gate projection of h_dec over this cluster's 32 units for this CTA's 16 batch rows
+        // (linear_projection + gate_layer, model.py:383-388): thread = output o (81 of the 128 threads)
+        named_bar(BAR_EPI, 128);
+        if (etid < 81) {
+          float wp[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.Wpg + (long long)etid * (H + ED) + 32 * cid + i));
+            wp[i] = w4.x; wp[i + 1] = w4.y; wp[i + 2] = w4.z; wp[i + 3] = w4.w;
+          }
+          float* op = p.opart + ((long long)((ts & 1) * NCLUSTER + cid) * B) * 84 + etid;
+#pragma unroll 4
+          for (int bl = 0; bl < 16; ++bl) {
+            const float4* hp = reinterpret_cast<const float4*>(hq + bl * 32);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 h4 = hp[i];
+              a0 = fmaf(wp[4 * i], h4.x, a0); a1 = fmaf(wp[4 * i + 1], h4.y, a1);
+              a2 = fmaf(wp[4 * i + 2], h4.z, a2); a3 = fmaf(wp[4 * i + 3], h4.w, a3);
+            }
+            const int b = 16 * rank + bl;
+            if (b < B) op[(long long)b * 84] = (a0 + a1) + (a2 + a3);
+          }
+        }
+      }
       named_bar(BAR_EPI, 128);
       if (etid == 0 && which == 0) TR(tn, 12);
       if (etid == 0) signal_counter(which ? cnt_d : cnt_h);
@@ -436,10 +512,17 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
       }
     };
-    for (int t = tb; t <= te; ++t) {
-      const unsigned n = (unsigned)(t - tb);
-      if (t < te) epilogue(std::integral_constant<int, 0>{}, t, n);
-      if (t > tb) epilogue(std::integral_constant<int, 1>{}, t - 1, n - 1);
+    if (INFER) {
+      for (int t = tb; t < te; ++t) {
+        epilogue(std::integral_constant<int, 0>{}, t, (unsigned)(t - tb));
+        epilogue(std::integral_constant<int, 1>{}, t, (unsigned)(t - tb));
+      }
+    } else {
+      for (int t = tb; t <= te; ++t) {
+        const unsigned n = (unsigned)(t - tb);
+        if (t < te) epilogue(std::integral_constant<int, 0>{}, t, n);
+        if (t > tb) epilogue(std::integral_constant<int, 1>{}, t - 1, n - 1);
+      }
     }
   } else if (warp >= 8) {
     // =========================================================================== attention (two CTAs per utterance)
@@ -470,6 +553,29 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     const uint32_t partner_full = mapa(smem_u32(e_full), (uint32_t)(rank ^ 1));
     named_bar(BAR_ATT, 256);
     const uint64_t pol_m = l2_policy(p.mem_hint);
+
+    // ---- inference only: mel / gate frame f = sum of the per-cluster h_dec partials + the two ctx partials + bias -> O[f],
+    // stop bookkeeping (Decoder.inference, model.py:449-459); leaves the frame in mel_s for the prenet
+    float* mel_s = fbuf;                      // [84]   (fbuf is free between the location phase and the context phase)
+    float* p1_s = fbuf + 128;                 // [256]
+    float* ctx_s = fbuf + 1024;               // [256]  (next to the four context partial rows)
+    auto frame_from_partials = [&](const int f) {
+      if (atid < 81) {
+        const int o = atid;
+        float acc = p.bpg[o];
+        const float* op = p.opart + ((long long)((f & 1) * NCLUSTER) * B + b) * 84 + o;
+#pragma unroll 8
+        for (int c = 0; c < NCLUSTER; ++c) acc += __ldcg(op + (long long)c * B * 84);
+        const float* oc = p.ocpart + ((long long)((f & 1) * B + b) * 2) * 84 + o;
+        acc += __ldcg(oc) + __ldcg(oc + 84);
+        mel_s[o] = acc;
+        if (hh == 0) {
+          p.O[((long long)f * B + b) * 84 + o] = acc;
+          if (o == 80 && p.n_frames && p.n_frames[b] < 0 && 1.f / (1.f + expf(-acc)) > p.gate_threshold) p.n_frames[b] = f + 1;
+        }
+      }
+    };
+    const uint64_t pseed = (INFER && !p.prenet_masks) ? t2v_resolve_seed(s.seed) : 0ull;
 
     float qv[4] = {0.f, 0.f, 0.f, 0.f};
     for (int t = tb; t < te; ++t) {
@@ -534,6 +640,59 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           }
         }
         named_bar(BAR_ATT, 256);
+      }
+      if (INFER) {
+        // ---- prenet of step t (model.py:91-102; dropout always on) from the mel frame of step t-1: needs every cluster's
+        // projection partial (cnt_d) and the partner CTA's ctx partial (cnt_c) of that step
+        if (atid == 0 && n > 0) { wait_counter(cnt_d, NCTA * n); wait_counter(cnt_c, NCTA * n); }
+        named_bar(BAR_ATT, 256);
+        if (active) {
+          if (n > 0) frame_from_partials(t - 1);
+          else if (t > 0 && atid < 81) mel_s[atid] = p.O[((long long)(t - 1) * B + b) * 84 + atid];
+          named_bar(BAR_ATT, 256);
+          float* xa = s.XA + ((long long)t * B + b) * XA_W;
+          if (t == 0) {                       // go frame = zeros (model.py:241-247): both prenet layers give exactly 0
+            if (atid < 128) xa[128 * hh + atid] = 0.f;
+          } else {
+            const float* pm0 = p.prenet_masks ? p.prenet_masks + ((long long)t * 2 * B + b) * PD : nullptr;
+            const float* pm1 = pm0 ? pm0 + (long long)B * PD : nullptr;
+            const uint64_t pidx = ((uint64_t)t * B + b) * PD;
+            // layer 1 (80 -> 256, both CTAs of the pair): warp per output, lanes 0..19 hold four inputs each
+            const float4 m4 = (lane < 20) ? *reinterpret_cast<const float4*>(mel_s + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int k = 0; k < 32; ++k) {
+              const int j = aw + 8 * k;
+              float acc = 0.f;
+              if (lane < 20) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.Wp1 + j * 80 + 4 * lane));
+                acc = w4.x * m4.x + w4.y * m4.y + w4.z * m4.z + w4.w * m4.w;
+              }
+              acc = warp_sum(acc);
+              if (lane == 0) {
+                const float keep = pm0 ? pm0[j] : (t2v_uniform(pseed, SITE_PRENET0, pidx + j) >= 0.5f ? 1.f : 0.f);
+                p1_s[j] = t2v_rnd(fmaxf(acc, 0.f) * keep * 2.f, rnd);
+              }
+            }
+            named_bar(BAR_ATT, 256);
+            // layer 2 (256 -> 256): this CTA's 128 outputs, warp per output, each lane 8 inputs
+            const float4 x0 = *reinterpret_cast<const float4*>(p1_s + 4 * lane);
+            const float4 x1 = *reinterpret_cast<const float4*>(p1_s + 128 + 4 * lane);
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+              const int j = 128 * hh + aw + 8 * k;
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.Wp2 + j * PD + 4 * lane));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.Wp2 + j * PD + 128 + 4 * lane));
+              float acc = (w0.x * x0.x + w0.y * x0.y + w0.z * x0.z + w0.w * x0.w) + (w1.x * x1.x + w1.y * x1.y + w1.z * x1.z + w1.w * x1.w);
+              acc = warp_sum(acc);
+              if (lane == 0) {
+                const float keep = pm1 ? pm1[j] : (t2v_uniform(pseed, SITE_PRENET1, pidx + j) >= 0.5f ? 1.f : 0.f);
+                xa[j] = t2v_rnd(fmaxf(acc, 0.f) * keep * 2.f, rnd);
+              }
+            }
+          }
+        }
+        named_bar(BAR_ATT, 256);
+        if (atid == 0) signal_counter(cnt_p);
       }
       // ---- h_att_t (and every cluster's partial query) complete device-wide
       if (atid == 0) { TR(n, 16); wait_counter(cnt_h, NCTA * (n + 1)); TR(n, 17); }
@@ -663,6 +822,22 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           const int col = 256 * hh + atid;
           s.XD[((long long)t * B + b) * XD_W + H + col] = c;              // ctx_t -> decoder_rnn input
           s.XA[((long long)(t + 1) * B + b) * XA_W + PD + col] = c;      // ctx_t -> next attention_rnn input
+          if (INFER) ctx_s[atid] = c;
+        }
+        if (INFER) {
+          // ---- partial mel / gate projection of this CTA's 256 ctx columns (the ctx half of [h_dec | ctx] W_pg^T): warp per output
+          named_bar(BAR_ATT, 256);
+          const float4 c0 = *reinterpret_cast<const float4*>(ctx_s + 4 * lane);
+          const float4 c1 = *reinterpret_cast<const float4*>(ctx_s + 128 + 4 * lane);
+          float* oc = p.ocpart + ((long long)(((t & 1) * B + b) * 2 + hh)) * 84;
+          for (int o = aw; o < 81; o += 8) {
+            const float* wr = p.Wpg + (long long)o * (H + ED) + H + 256 * hh;
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr + 4 * lane));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + 128 + 4 * lane));
+            float acc = (w0.x * c0.x + w0.y * c0.y + w0.z * c0.z + w0.w * c0.w) + (w1.x * c1.x + w1.y * c1.y + w1.z * c1.z + w1.w * c1.w);
+            acc = warp_sum(acc);
+            if (lane == 0) oc[o] = acc;
+          }
         }
       }
       named_bar(BAR_ATT, 256);
@@ -677,6 +852,27 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
             __stcs(asave + (long long)rr * AD + lane + 32 * kk, t2v_tanh(qv[kk] + S[rr * AD + lane + 32 * kk]));
         }
         named_bar(BAR_ATT, 256);           // S is overwritten by the next step's bulk copy
+      }
+    }
+  }
+  if (INFER && warp >= 8) {
+    // ---- the last frame of the range (the loop publishes frame t-1 at the start of step t)
+    const int atid = tid - 256;
+    const int b = 2 * cid + (rank >> 1), hh = rank & 1;
+    float* fb = (float*)(smem + OFF_F);
+    if (atid == 0) { wait_counter(cnt_d, NCTA * (unsigned)(te - tb)); wait_counter(cnt_c, NCTA * (unsigned)(te - tb)); }
+    named_bar(BAR_ATT, 256);
+    if (b < B && atid < 81) {
+      const int f = te - 1, o = atid;
+      float acc = p.bpg[o];
+      const float* op = p.opart + ((long long)((f & 1) * NCLUSTER) * B + b) * 84 + o;
+      for (int c = 0; c < NCLUSTER; ++c) acc += __ldcg(op + (long long)c * B * 84);
+      const float* oc = p.ocpart + ((long long)((f & 1) * B + b) * 2) * 84 + o;
+      acc += __ldcg(oc) + __ldcg(oc + 84);
+      fb[o] = acc;
+      if (hh == 0) {
+        p.O[((long long)f * B + b) * 84 + o] = acc;
+        if (o == 80 && p.n_frames && p.n_frames[b] < 0 && 1.f / (1.f + expf(-acc)) > p.gate_threshold) p.n_frames[b] = f + 1;
       }
     }
   }
@@ -725,16 +921,21 @@ int t2v_encode_tmap_2d(CUtensorMap* map, const void* base, int esize, long long 
                        long long row_stride_elems, int box_rows);
 
 // Returns 0 when the loop was enqueued, 1 when the persistent kernel does not apply to this problem (the caller then
-// uses the per-step launches), anything else = error.
-int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream) {
+// uses the per-step launches), anything else = error.  inf != nullptr: free-running inference (prenet, mel / gate projection
+// and stop bookkeeping inside the kernel).
+static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, int t_begin, int t_end, cudaStream_t stream) {
   if (!persist_enabled()) return 1;
   if (!s->use_tc || s->B > 64 || s->Ti > 2 * TH_MAX || s->Ti < 1 || t_end - t_begin < 2) return 1;
   if (!s->parts || !s->ebuf) return 1;
-  static int max_clusters = -1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    T2V_CUDA_CHECK(cudaFuncSetAttribute(dec_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+  if (inf && (!inf->Wp1 || !inf->Wp2 || !inf->Wpg || !inf->bpg || !inf->O)) return 1;
+  void (*kernel)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, PersistParams) =
+      inf ? dec_persist_fwd_kernel<true> : dec_persist_fwd_kernel<false>;
+  static int max_clusters[2] = {-1, -1};
+  static bool attr_set[2] = {false, false};
+  const int ki = inf ? 1 : 0;
+  if (!attr_set[ki]) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set[ki] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -743,24 +944,32 @@ int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cuda
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (max_clusters < 0) {
+  if (max_clusters[ki] < 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, dec_persist_fwd_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-    max_clusters = n;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    max_clusters[ki] = n;
   }
-  if (max_clusters < NCLUSTER) return 1;       // all 128 CTAs must be co-resident (they wait on each other)
+  if (max_clusters[ki] < NCLUSTER) return 1;       // all 128 CTAs must be co-resident (they wait on each other)
 
   PersistParams p;
+  memset(&p, 0, sizeof(p));
   p.s = *s;
   p.t_begin = t_begin; p.t_end = t_end;
   p.counters = reinterpret_cast<unsigned*>(s->ebuf);
   p.qpart = s->parts;
   p.trace = nullptr;
+  if (inf) {
+    p.Wp1 = inf->Wp1; p.Wp2 = inf->Wp2; p.Wpg = inf->Wpg; p.bpg = inf->bpg; p.prenet_masks = inf->prenet_masks;
+    p.O = inf->O; p.gate_threshold = inf->gate_threshold; p.n_frames = inf->n_frames;
+    p.opart = s->parts + 8192LL * s->B;
+    p.ocpart = s->parts + 16384LL * s->B;
+  }
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
   p.wa_hint = env_int("T2V_PERSIST_WA_HINT", 1);
-  p.wd_hint = env_int("T2V_PERSIST_WD_HINT", 2);     // decoder_rnn weights stream from HBM: do not let them evict W_a / memory
+  p.wd_hint = env_int("T2V_PERSIST_WD_HINT", inf ? 1 : 2);     // training: decoder_rnn weights stream from HBM, do not let them evict
+                                                               // W_a / memory; inference (no saved activations): everything fits L2
   p.mem_hint = env_int("T2V_PERSIST_MEM_HINT", 1);
-  const bool trace = getenv("T2V_PERSIST_TRACE") != nullptr && (t_end - t_begin) >= TRACE_T0 + TRACE_STEPS + 2;
+  const bool trace = !inf && getenv("T2V_PERSIST_TRACE") != nullptr && (t_end - t_begin) >= TRACE_T0 + TRACE_STEPS + 2;
   const size_t trace_bytes = 2 * TRACE_STEPS * 32 * sizeof(long long);
   if (trace) {
     T2V_CUDA_CHECK(cudaMalloc(&p.trace, trace_bytes));
@@ -779,8 +988,8 @@ int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cuda
   }
   if ((r = t2v_encode_tmap_2d(&tmXA, s->XA, 4, XA_W, rows, XA_W, 64))) return r;
   if ((r = t2v_encode_tmap_2d(&tmXD, s->XD, 4, XD_W, rows, XD_W, 64))) return r;
-  T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 96 * sizeof(unsigned), stream));
-  T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dec_persist_fwd_kernel, tmWa, tmWd, tmXA, tmXD, p));
+  T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 128 * sizeof(unsigned), stream));
+  T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmWa, tmWd, tmXA, tmXD, p));
   T2V_COUNT_LAUNCH();
   if (trace) {      // debugging aid: not usable under stream capture
     static const char* names[26] = {"A:h ready", "A:ctx ready", "A:att loads issued", "A:dec loads issued", "M:att first chunk",
@@ -804,6 +1013,13 @@ int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cuda
     }
   }
   return 0;
+}
+
+int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream) {
+  return launch_persist(s, nullptr, t_begin, t_end, stream);
+}
+int t2v_decoder_infer_persist(const T2VDecoderInfer* d, int t_begin, int t_end, cudaStream_t stream) {
+  return launch_persist(&d->f, d, t_begin, t_end, stream);
 }
 
 T2V_API int t2v_pack_step_tiles(const float* W, int mode, float* out, cudaStream_t stream) {

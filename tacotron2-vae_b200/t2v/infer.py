@@ -127,6 +127,11 @@ class DecoderSession(object):
         self.W["Wa"], self.W["Wd"], self.W["Wpg"], self.W["bpg"] = engine.pack_decoder_weights(P, dev, ops.R)
         self.W["Wq"] = ops.wr(P["decoder.attention_layer.query_layer.linear_layer.weight"])
         self.W["WconvT"] = engine.conv_weight_T(P, dev)
+        if ops.tc:      # tile-contiguous copies for the persistent loop kernel (decoder_persist.cu)
+            self.W["WaP"] = torch.empty(4096, 1792, device=dev)
+            self.W["WdP"] = torch.empty(4096, 2560, device=dev)
+            L("t2v_pack_step_tiles", self.W["Wa"], 0, self.W["WaP"])
+            L("t2v_pack_step_tiles", self.W["Wd"], 1, self.W["WdP"])
         self.memory = memory
         self.pmem = torch.empty(self.B * self.Ti, 128, device=dev)
         ops.linear(memory, 512, ops.wr(P["decoder.attention_layer.memory_layer.linear_layer.weight"]), 512, self.pmem, 128,
