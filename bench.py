@@ -355,7 +355,8 @@ def inference_decoder_step(m, dev, precision, B=16, Ti=120, n=1000):
         mel, gate, align = keep.outputs(n)
         ok = bool(torch.isfinite(mel).all())
     return {"value": min(times[1:]) * 1e3 / n, "unit": "us/step", "batch": B, "text_len": Ti, "steps": n, "finite": ok,
-            "what": "free-running Decoder.inference step incl. prenet, attention, both LSTM cells, mel/gate projection"}
+            "what": "free-running Decoder.inference step incl. prenet, attention, both LSTM cells, mel/gate projection, stop flags: "
+                         "dec_persist_fwd_kernel<INFER> time / steps (one persistent launch; per-step launches: ~88 us)"}
 
 
 def decoder_step_roofline(m, hp, B, Ti, To, dev, precision):

@@ -465,14 +465,16 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       if (INFER && which == 1) {
         // ---- inference: partial mel / gate projection of h_dec over this cluster's 32 units for this CTA's 16 batch rows
         // (linear_projection + gate_layer, model.py:383-388): thread = output o (81 of the 128 threads)
-        named_bar(BAR_EPI, 128);
+        float wp[32];
         if (etid < 81) {
-          float wp[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.Wpg + (long long)etid * (H + ED) + 32 * cid + i));
             wp[i] = w4.x; wp[i + 1] = w4.y; wp[i + 2] = w4.z; wp[i + 3] = w4.w;
           }
+        }
+        named_bar(BAR_EPI, 128);
+        if (etid < 81) {
           float* op = p.opart + ((long long)((ts & 1) * NCLUSTER + cid) * B) * 84 + etid;
 #pragma unroll 4
           for (int bl = 0; bl < 16; ++bl) {
@@ -564,10 +566,14 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         const int o = atid;
         float acc = p.bpg[o];
         const float* op = p.opart + ((long long)((f & 1) * NCLUSTER) * B + b) * 84 + o;
-#pragma unroll 8
-        for (int c = 0; c < NCLUSTER; ++c) acc += __ldcg(op + (long long)c * B * 84);
+        float pv[NCLUSTER];                   // all 32 partials in flight at once (one L2 round trip)
+#pragma unroll
+        for (int c = 0; c < NCLUSTER; ++c) pv[c] = __ldcg(op + (long long)c * B * 84);
         const float* oc = p.ocpart + ((long long)((f & 1) * B + b) * 2) * 84 + o;
-        acc += __ldcg(oc) + __ldcg(oc + 84);
+        const float oc0 = __ldcg(oc), oc1 = __ldcg(oc + 84);
+#pragma unroll
+        for (int c = 0; c < NCLUSTER; ++c) acc += pv[c];
+        acc += oc0 + oc1;
         mel_s[o] = acc;
         if (hh == 0) {
           p.O[((long long)f * B + b) * 84 + o] = acc;
@@ -659,7 +665,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
             const uint64_t pidx = ((uint64_t)t * B + b) * PD;
             // layer 1 (80 -> 256, both CTAs of the pair): warp per output, lanes 0..19 hold four inputs each
             const float4 m4 = (lane < 20) ? *reinterpret_cast<const float4*>(mel_s + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < 32; ++k) {
               const int j = aw + 8 * k;
               float acc = 0.f;
@@ -677,7 +683,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
             // layer 2 (256 -> 256): this CTA's 128 outputs, warp per output, each lane 8 inputs
             const float4 x0 = *reinterpret_cast<const float4*>(p1_s + 4 * lane);
             const float4 x1 = *reinterpret_cast<const float4*>(p1_s + 128 + 4 * lane);
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < 16; ++k) {
               const int j = 128 * hh + aw + 8 * k;
               const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.Wp2 + j * PD + 4 * lane));
