@@ -13,3 +13,12 @@ for mode in ("1", "0"):
     os.environ["T2V_PERSIST"] = mode
     r = bench.inference_decoder_step(m, torch.device("cuda"), "tf32", B=B, Ti=Ti, n=n)
     print("T2V_PERSIST=%s: %.2f us/step (B=%d, Ti=%d, %d steps, finite=%s)" % (mode, r["value"], B, Ti, n, r["finite"]), flush=True)
+if os.environ.get("TRACE"):
+    from oracle import port
+    from t2v import engine, infer
+    os.environ["T2V_PERSIST"] = "1"
+    os.environ["T2V_PERSIST_TRACE"] = "1"
+    P = m._state()
+    sess = infer.DecoderSession(engine.Ops("tf32"), P, torch.randn(B, Ti, 512, device="cuda"), None, 300, training=False, seed=7)
+    sess.run_free(300, 2.0, seed=7)
+    torch.cuda.synchronize()

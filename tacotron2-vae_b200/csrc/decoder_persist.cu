@@ -582,6 +582,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       }
     };
     const uint64_t pseed = (INFER && !p.prenet_masks) ? t2v_resolve_seed(s.seed) : 0ull;
+    const uint64_t pol_keep = l2_policy(1);
 
     float qv[4] = {0.f, 0.f, 0.f, 0.f};
     for (int t = tb; t < te; ++t) {
@@ -650,7 +651,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       if (INFER) {
         // ---- prenet of step t (model.py:91-102; dropout always on) from the mel frame of step t-1: needs every cluster's
         // projection partial (cnt_d) and the partner CTA's ctx partial (cnt_c) of that step
-        if (atid == 0 && n > 0) { wait_counter(cnt_d, NCTA * n); wait_counter(cnt_c, NCTA * n); }
+        if (atid == 0 && n > 0) { TR(n, 0); wait_counter(cnt_d, NCTA * n); wait_counter(cnt_c, NCTA * n); TR(n, 1); }
         named_bar(BAR_ATT, 256);
         if (active) {
           if (n > 0) frame_from_partials(t - 1);
@@ -670,7 +671,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
               const int j = aw + 8 * k;
               float acc = 0.f;
               if (lane < 20) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.Wp1 + j * 80 + 4 * lane));
+                const float4 w4 = ldg_v4_hint(p.Wp1 + j * 80 + 4 * lane, pol_keep);     // stays in L2 next to the weight streams
                 acc = w4.x * m4.x + w4.y * m4.y + w4.z * m4.z + w4.w * m4.w;
               }
               acc = warp_sum(acc);
@@ -686,8 +687,8 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
 #pragma unroll 8
             for (int k = 0; k < 16; ++k) {
               const int j = 128 * hh + aw + 8 * k;
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.Wp2 + j * PD + 4 * lane));
-              const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.Wp2 + j * PD + 128 + 4 * lane));
+              const float4 w0 = ldg_v4_hint(p.Wp2 + j * PD + 4 * lane, pol_keep);
+              const float4 w1 = ldg_v4_hint(p.Wp2 + j * PD + 128 + 4 * lane, pol_keep);
               float acc = (w0.x * x0.x + w0.y * x0.y + w0.z * x0.z + w0.w * x0.w) + (w1.x * x1.x + w1.y * x1.y + w1.z * x1.z + w1.w * x1.w);
               acc = warp_sum(acc);
               if (lane == 0) {
@@ -698,7 +699,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           }
         }
         named_bar(BAR_ATT, 256);
-        if (atid == 0) signal_counter(cnt_p);
+        if (atid == 0) { TR(n, 2); signal_counter(cnt_p); TR(n, 3); }
       }
       // ---- h_att_t (and every cluster's partial query) complete device-wide
       if (atid == 0) { TR(n, 16); wait_counter(cnt_h, NCTA * (n + 1)); TR(n, 17); }
@@ -836,10 +837,11 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           const float4 c0 = *reinterpret_cast<const float4*>(ctx_s + 4 * lane);
           const float4 c1 = *reinterpret_cast<const float4*>(ctx_s + 128 + 4 * lane);
           float* oc = p.ocpart + ((long long)(((t & 1) * B + b) * 2 + hh)) * 84;
+#pragma unroll 4
           for (int o = aw; o < 81; o += 8) {
             const float* wr = p.Wpg + (long long)o * (H + ED) + H + 256 * hh;
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr + 4 * lane));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + 128 + 4 * lane));
+            const float4 w0 = ldg_v4_hint(wr + 4 * lane, pol_keep);
+            const float4 w1 = ldg_v4_hint(wr + 128 + 4 * lane, pol_keep);
             float acc = (w0.x * c0.x + w0.y * c0.y + w0.z * c0.z + w0.w * c0.w) + (w1.x * c1.x + w1.y * c1.y + w1.z * c1.z + w1.w * c1.w);
             acc = warp_sum(acc);
             if (lane == 0) oc[o] = acc;
@@ -972,10 +974,10 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
   }
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
   p.wa_hint = env_int("T2V_PERSIST_WA_HINT", 1);
-  p.wd_hint = env_int("T2V_PERSIST_WD_HINT", inf ? 1 : 2);     // training: decoder_rnn weights stream from HBM, do not let them evict
-                                                               // W_a / memory; inference (no saved activations): everything fits L2
+  p.wd_hint = env_int("T2V_PERSIST_WD_HINT", 2);               // decoder_rnn weights stream from HBM: do not let them evict W_a / memory
+                                                               // (inference: 50.8 vs 51.4 us with evict_last)
   p.mem_hint = env_int("T2V_PERSIST_MEM_HINT", 1);
-  const bool trace = !inf && getenv("T2V_PERSIST_TRACE") != nullptr && (t_end - t_begin) >= TRACE_T0 + TRACE_STEPS + 2;
+  const bool trace = getenv("T2V_PERSIST_TRACE") != nullptr && (t_end - t_begin) >= TRACE_T0 + TRACE_STEPS + 2;
   const size_t trace_bytes = 2 * TRACE_STEPS * 32 * sizeof(long long);
   if (trace) {
     T2V_CUDA_CHECK(cudaMalloc(&p.trace, trace_bytes));
