@@ -122,7 +122,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], p.two_issuers ? 2 : 1);
+      mbar_init(&acc_full[i], 1);
       mbar_init(&acc_free[i], 128);
       mbar_init(&recv_full[i], 1);
     }
@@ -214,67 +214,58 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
       }
     }
-  } else if (warp == 2 || warp == 3) {
-    // =========================================================================== MMA issuer(s).  Default (T2V_PERSIST_TWO_ISSUERS=1):
-    // warps 2 and 3 issue the even / odd K chunks (=0: warp 2 issues every chunk, deterministic accumulation order);
-    // accumulation into the same TMEM columns commutes, only the chunk that initialises the accumulator (j = 0, warp 2) has
-    // to be issued first (named barrier) and the accumulator-complete barrier counts one commit per issuer.  Measured: the
-    // small-N tf32 MMAs (128x64x8: ~100-140 cycles each) bound the GEMM phases either way (17.6 k vs 19 k cycles per dXD GEMM).
+  } else if (warp == 2) {
+    // =========================================================================== MMA issuer (whole warp in the loop, one
+    // elected lane issues).  A second issuing warp (even / odd chunks into the same accumulator) was 2-8 % faster but made
+    // about one bench run in four die with "unspecified launch failure": tcgen05.mma from two threads into the same TMEM
+    // columns is not ordered by anything, so this stays a single issuer.
     {
       constexpr uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
       constexpr uint32_t idesc128 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const int mw = p.two_issuers ? (warp - 2) : 0;
-      const bool mine_all = !p.two_issuers;
-      if (p.two_issuers || warp == 2) {
-        int st = 0;
-        uint32_t ph = 0;
-        bool ready = false;
-        const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(ring));
-        const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(ring + W_PART));
-        // which 1: dXD[td] = DGD[td] W_d, M = 128 (80 live rows), accumulator columns 64..127
-        // which 0: DXA[t]  = DGA[t]  W_a, M = 64 (56 live rows), accumulator columns 0..63
-        auto gemm = [&](const int which, const unsigned idx, const int it) {
-          mbar_wait(&acc_free[which], (idx & 1u) ^ 1u);
+      int st = 0;
+      uint32_t ph = 0;
+      const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(ring));
+      const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(ring + W_PART));
+      bool ready = false;                    // phase test of the current stage, started while the previous chunk was issued
+      // which 1: dXD[td] = DGD[td] W_d, M = 128 (80 live rows), accumulator columns 64..127
+      // which 0: DXA[t]  = DGA[t]  W_a, M = 64 (56 live rows), accumulator columns 0..63
+      auto gemm = [&](const int which, const unsigned idx, const int it) {
+        mbar_wait(&acc_free[which], (idx & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + (uint32_t)(which * 64);
+        const uint32_t idesc = which ? idesc128 : idesc64;
+        for (int j = 0; j < KCH; ++j) {
+          if (!ready) mbar_wait(&full[st], ph);
           tc_fence_after();
-          const uint32_t dcol = tmem_base + (uint32_t)(which * 64);
-          const uint32_t idesc = which ? idesc128 : idesc64;
-          if (p.two_issuers && mw == 1) named_bar(3, 64);      // chunk 0 (accumulator init) has been issued by warp 2
-          for (int j = 0; j < KCH; ++j) {
-            const int sn = (st + 1 == NS) ? 0 : st + 1;
-            const uint32_t pn = (st + 1 == NS) ? (ph ^ 1u) : ph;
-            if (mine_all || (j & 1) == mw) {
-              if (!(mine_all && ready)) mbar_wait(&full[st], ph);
-              tc_fence_after();
-              if (mine_all) ready = mbar_test_wait(&full[sn], pn);     // next stage's phase test overlaps the issue below
-              if (elect_one()) {
-                if (j == 0) TR(it, which ? 27 : 29);
-                const uint64_t adesc = adesc0 + (uint64_t)(st * (STAGE >> 4));
-                const uint64_t bdesc = bdesc0 + (uint64_t)(st * (STAGE >> 4));
+          const int sn = (st + 1 == NS) ? 0 : st + 1;
+          const uint32_t pn = (st + 1 == NS) ? (ph ^ 1u) : ph;
+          ready = mbar_test_wait(&full[sn], pn);           // overlaps the issue below
+          if (elect_one()) {
+            if (j == 0) TR(it, which ? 27 : 29);
+            const uint64_t adesc = adesc0 + (uint64_t)(st * (STAGE >> 4));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(st * (STAGE >> 4));
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
-                if (p.dbg_skip & 4) {        // timing experiment: twice the tensor work per chunk
+            for (int k = 0; k < 4; ++k)
+              tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+            if (p.dbg_skip & 4) {        // timing experiment: twice the tensor work per chunk
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
-                }
-                if (p.dbg_skip & 8) mbar_arrive(&empty[st]);     // timing experiment: free the stage at issue
-                else tc_commit(&empty[st]);
-                if (j >= KCH - 2 && (mine_all ? j == KCH - 1 : true)) {   // this issuer's last chunk
-                  tc_commit(&acc_full[which]);
-                  if (j == KCH - 1) TR(it, which ? 28 : 30);
-                }
-              }
-              __syncwarp();
-              if (p.two_issuers && j == 0) named_bar(3, 64);
+              for (int k = 0; k < 4; ++k) tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
             }
-            st = sn; ph = pn;
+            if (p.dbg_skip & 8) mbar_arrive(&empty[st]);     // timing experiment: free the stage at issue, not at MMA completion
+            else tc_commit(&empty[st]);
+            if (j == KCH - 1) {
+              tc_commit(&acc_full[which]);
+              TR(it, which ? 28 : 30);
+            }
           }
-        };
-        for (int it = -1; it < To; ++it) {
-          const int td = To - 2 - it;
-          if (td >= 0) gemm(1, (unsigned)(it + 1), it);
-          if (it >= 0) gemm(0, (unsigned)it, it);
+          __syncwarp();
+          st = sn; ph = pn;
         }
+      };
+      for (int it = -1; it < To; ++it) {
+        const int td = To - 2 - it;
+        if (td >= 0) gemm(1, (unsigned)(it + 1), it);
+        if (it >= 0) gemm(0, (unsigned)it, it);
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -855,9 +846,7 @@ int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStre
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
   p.rotate = env_int("T2V_PERSIST_ROTATE", 1);
   p.dbg_skip = env_int("T2V_PERSIST_DBG_SKIP", 0);
-  // two issuers: 33.8 vs 36-37 us per step with this loop; the fp32 accumulation order of the dX GEMMs (and so the last bits of the
-  // gradients) then varies from run to run, like the atomics of the embedding / dq / split-K paths already do.  =0: one issuer.
-  p.two_issuers = env_int("T2V_PERSIST_TWO_ISSUERS", 1);
+  p.two_issuers = 0;       // removed (see the MMA issuer comment in the kernel)
   p.wa_hint = env_int("T2V_PERSIST_BWD_WA_HINT", 1);
   p.wd_hint = env_int("T2V_PERSIST_BWD_WD_HINT", 2);
   p.trace = nullptr;

@@ -222,8 +222,8 @@ def test_graph_replay_equals_eager_and_dp_shards_add_up():
     total = float(torch.sqrt(sum(v.norm() ** 2 for v in outs["eager"][1].values())))
     for k, g in outs["graph"][1].items():
         ref = outs["eager"][1][k]
-        # atomics (embedding scatter, split-K, dq) and the two MMA issuers of the persistent backward loop add in any order;
-        # conv biases in front of a BN are pure rounding noise (true gradient 0): absolute floor 3e-5 of the total gradient norm
+        # atomics (embedding scatter, split-K, dq) add in any order; conv biases in front of a BN are pure rounding noise
+        # (true gradient 0): absolute floor 3e-5 of the total gradient norm
         assert float((g - ref).norm()) <= 1e-3 * float(ref.norm()) + 3e-5 * total, k
     mel, post, gate, align = outs["graph"][0][:4]
     for b in range(B):
