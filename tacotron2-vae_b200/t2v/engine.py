@@ -42,10 +42,11 @@ _ctypes = _lib.ctypes
 
 _SIDE = {}
 _OVERLAP = __import__("os").environ.get("T2V_OVERLAP", "1") != "0"
-# Postnet weight gradients on a side branch beside the persistent decoder-backward kernel: 76.9 -> 75.1 ms per train step when it
-# works, but 2 of 4 bench runs died with "unspecified launch failure" (a bounded wait trapping; not reproduced with the branch off in
-# 6 runs).  Until the interaction of other resident grids with the 128 co-resident CTAs of the persistent kernels is understood, nothing
-# runs concurrently with them: OFF by default.
+# Postnet weight gradients on a side branch beside the persistent decoder-backward kernel: 77.3 -> 75.1 ms per train step.  History:
+# 2 of 4 bench runs died with "unspecified launch failure" while the backward kernel still had two MMA-issuing warps (which failed on
+# their own too); with the single issuer 4 of 4 runs with the branch were clean.  Still OFF by default until a longer soak run: all 128
+# CTAs of the persistent kernels must become co-resident, and foreign CTAs on the GPU while their clusters are placed are the one
+# situation that has not been exercised for long.
 _POST_DW_BRANCH = __import__("os").environ.get("T2V_POST_DW_BRANCH", "0") == "1"
 
 
