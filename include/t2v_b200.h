@@ -259,6 +259,8 @@ typedef struct T2VDecoderInfer {
   float gate_threshold;
   int *n_frames;                 /* [B] first step whose sigmoid(gate) > threshold (+1), or n if never */
 } T2VDecoderInfer;
+/* free-running decode of steps [t_begin, t_end): one persistent kernel (prenet, both cells, attention, mel / gate projection, stop
+   bookkeeping inside) when use_tc, B <= 64, Ti <= 128 and the range has >= 2 steps; otherwise the per-step launch sequence */
 int t2v_decoder_infer_steps(const T2VDecoderInfer* s, int t_begin, int t_end, cudaStream_t stream);
 
 /* ---- loss (loss_function.py:27-45) -------------------------------------------------------------------------------- */

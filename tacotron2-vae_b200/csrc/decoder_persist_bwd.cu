@@ -33,7 +33,7 @@ constexpr int NS = 5;                          // ring depth: a stage = one K ch
 constexpr int W_PART = 80 * 128, A_STAGE = 64 * 128, STAGE = W_PART + A_STAGE;
 constexpr int KCH = 32;                        // 32-wide K chunks per CTA and GEMM (K slice = 4096 / 4)
 constexpr int RA_P = 64, RD_P = 80;            // column pitch of the exchange slots [src][batch row 16][cols]
-constexpr int TH_MAX = 64, PADW = 160, FS = 36;
+constexpr int TH_MAX = 64, FS = 36;
 constexpr int BAR_EPI = 1, BAR_ATT = 2;
 
 constexpr int OFF_RING = 0;
