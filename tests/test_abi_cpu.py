@@ -81,3 +81,33 @@ def test_kl_anneal_and_mask_helpers():
                 port.kl_weight(fn, step)
     mk = get_mask_from_lengths(torch.tensor([3, 1]))
     assert mk.dtype == torch.bool and mk.tolist() == [[True, True, True], [True, False, False]]
+
+
+def test_persistent_loop_chunk_schedule_partitions_k():
+    """Host-side restatement of the K-chunk schedule of the persistent decoder kernels (decoder_persist.cu: att_kofs / dec_kofs /
+    att_chunk_infer / dec_chunk_infer; decoder_persist_bwd.cu: K slice 1024*rank + 32*j): over the 4 cluster ranks the chunks must
+    cover every column of XA (1792) / XD (2560) / the 4096 gate rows exactly once, in every order the kernels use."""
+    def att_kofs(j, r):
+        return 64 * r + 32 * j if j < 2 else (768 + 256 * r + 32 * (j - 2) if j < 10 else 256 + 128 * r + 32 * (j - 10))
+
+    def dec_kofs(j, r):
+        return 256 * r + 32 * j if j < 8 else (1024 + 128 * r + 32 * (j - 8) if j < 12 else 1536 + 256 * r + 32 * (j - 12))
+
+    def att_chunk_infer(j):
+        return j + 2 if j < 12 else j - 12
+
+    def dec_chunk_infer(j):
+        return j + 12 if j < 8 else j - 8
+
+    for kofs, nch, width in ((att_kofs, 14, 1792), (dec_kofs, 20, 2560)):
+        cols = sorted(c for r in range(4) for j in range(nch) for c in range(kofs(j, r), kofs(j, r) + 32))
+        assert cols == list(range(width))
+    assert sorted(att_chunk_infer(j) for j in range(14)) == list(range(14))
+    assert sorted(dec_chunk_infer(j) for j in range(20)) == list(range(20))
+    # inference order: h_att (cols 768..), ctx (256..767), prenet (0..255) for the attention_rnn; h_dec, h_att, ctx for the decoder_rnn
+    assert [att_kofs(att_chunk_infer(j), 0) for j in (0, 8, 12)] == [768, 256, 0]
+    assert [dec_kofs(dec_chunk_infer(j), 0) for j in (0, 8, 16)] == [1536, 0, 1024]
+    rows = sorted(k for r in range(4) for j in range(32) for k in range(1024 * r + 32 * j, 1024 * r + 32 * j + 32))
+    assert rows == list(range(4096))
+    # output-column ownership of the backward GEMMs: 32 clusters x 56 / 80 columns
+    assert 32 * 56 == 1792 and 32 * 80 == 2560 and 56 % 4 == 0 and 80 % 4 == 0
