@@ -36,7 +36,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--ti", type=int, default=120)
     ap.add_argument("--to", type=int, default=800)
-    ap.add_argument("--precision", default=os.environ.get("T2V_PRECISION", "tf32"), choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("T2V_PRECISION", "fp16"), choices=["fp16", "bf16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -265,9 +265,11 @@ def main():
         print(json.dumps({
             "metric": "padded mel-frames/s (train fwd+bwd+opt)", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if a.precision == "tf32" else "f32", "data": "synthetic",
-            "config": {"workload": "C3: Tacotron2-VAE train step, batch %d/GPU, Ti<=%d, To<=%d, fp32 storage, %s GEMMs" %
-                       (B, Ti, To, "tcgen05 tf32" if a.precision == "tf32" else "FFMA fp32"),
+            "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32"}.get(a.precision, a.precision), "data": "synthetic",
+            "config": {"workload": "C3: Tacotron2-VAE train step, batch %d/GPU, Ti<=%d, To<=%d, fp32 master weights / state, %s" %
+                       (B, Ti, To, {"fp16": "fp16 operands in the decoder loops (tcgen05 kind::f16), tf32 GEMMs elsewhere",
+                                    "bf16": "bf16 operands in the decoder loops (tcgen05 kind::f16), tf32 GEMMs elsewhere",
+                                    "tf32": "tcgen05 tf32 GEMMs", "fp32": "FFMA fp32 GEMMs"}[a.precision]),
                        "parallelism": "dp%d" % world, "global_batch": B * world,
                        "l2": "per-step working set (>3 GB of saved activations) exceeds the 126 MB L2"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
@@ -386,8 +388,10 @@ def decoder_step_roofline(m, hp, B, Ti, To, dev, precision):
             times.append(e0.elapsed_time(e1))
         times = times[1:]
     us = min(times) * 1e3 / To
-    s = 4
-    alg_bytes = 18103953 * s + (B * Ti * 640 + 4 * B * Ti + B * 8192 + B * 1361) * s     # SURVEY.md 8(d), fp32 storage
+    s = 2 if precision in ("fp16", "bf16") else 4
+    # weights 18 103 953 x s + activations x s, s = bytes per operand element (2: fp16 / bf16 -- the north star's
+    # own denominator, 47.32 MB at B=64 -- or 4: fp32 storage)
+    alg_bytes = 18103953 * s + (B * Ti * 640 + 4 * B * Ti + B * 8192 + B * 1361) * s
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -395,7 +399,7 @@ def decoder_step_roofline(m, hp, B, Ti, To, dev, precision):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (us * 1e-6) / 1e9
-    persist = os.environ.get("T2V_PERSIST", "1") != "0" and precision == "tf32" and B <= 64 and Ti <= 128
+    persist = os.environ.get("T2V_PERSIST", "1") != "0" and precision != "fp32" and B <= 64 and Ti <= 128
     kernel = ("dec_persist_fwd_kernel: ONE persistent launch for all To steps of Decoder.decode (128 CTAs = 32 clusters x 4; "
               "TMA weight streaming, tcgen05 tf32 split-K over the cluster + DSMEM exchange, LSTM cells / query partials "
               "in the epilogue, attention by CTA pairs); per-step time = kernel time / To") if persist else (

@@ -40,6 +40,13 @@ int t2v_gemm_tc(const void* A, long long lda, long long a_rows, long long a_inne
                 int taps, int a_tap_rowshift, int b_tap_stride, int a_k0, int b_k0, int esize, int splits,
                 long long split_stride, int epi_atomic, float alpha, int bn_hint, cudaStream_t stream);
 
+/* row-reduction form with MN-major operands (no transposed copies): D[n_a,n_b] (+)= alpha * sum_{r<rows} A[a_row0+r, i] * B[b_row0+r, j];
+   the weight-gradient GEMMs dW = dY^T X of every nn.Linear / Conv1d (autograd of model.py:91-148).  epi: 0 store, 1 atomicAdd,
+   2 non-atomic += (splits == 1); splits > 1 needs epi 1 (D pre-initialised). */
+int t2v_gemm_tc_rowred(const float* A, long long lda, int n_a, long long a_row0, const float* B, long long ldb, int n_b,
+                       long long b_row0, float* D, long long ldd, long long rows, int splits, long long split_stride,
+                       int epi, float alpha, cudaStream_t stream);
+
 /* ---- text embedding (model.py:474,528) -- integer gather, bit exact ------------------------------------------- */
 int t2v_embedding_fwd(const long long* ids, const float* table, float* out_padded, int B, int T, int C, int n_symbols,
                       int rnd, cudaStream_t stream);
@@ -54,7 +61,8 @@ int t2v_bn_finalize(const double* sum, const double* sumsq, double n, int C, flo
                     cudaStream_t stream);
 int t2v_bn_eval_prepare(const float* running_mean, const float* running_var, int C, float eps, float* mean,
                         float* invstd, cudaStream_t stream);
-int t2v_bn_act_fwd(const float* y, float* out, long long rows, int C, int period, int lo, int hi, const float* mean,
+/* out_lo (nullable): tf32(x - out) -- the low part of the split operand x = out + out_lo of an error-compensated tensor-core GEMM */
+int t2v_bn_act_fwd(const float* y, float* out, float* out_lo, long long rows, int C, int period, int lo, int hi, const float* mean,
                    const float* invstd, const float* gamma, const float* beta, int act, const float* drop_mask,
                    unsigned long long seed, unsigned int site, float p, int T, int rnd, cudaStream_t stream);
 int t2v_bn_act_bwd_reduce(const float* dout, const float* y, long long rows, int C, int period, int lo, int hi,
@@ -223,11 +231,23 @@ typedef struct T2VDecoderSeq {
   float *ebuf;                   /* [B,Ti,129] scratch: [B,Ti] energies, then [B,Ti,128] location term + processed memory */
   const float *WaP, *WdP;        /* optional (NULL = unused): Wa / Wd re-tiled by t2v_pack_step_tiles (modes 0 / 1) for the persistent
                                     loop kernel: every TMA box is one contiguous 16 KB block instead of 128 strided 128-byte rows */
+  float *HCLO;                   /* optional [To,B,1536]: low-order residual of [h_dec_t | ctx_t] after rounding onto the operand grid
+                                    (x = x_hi + x_lo): lets the deferred mel / gate projection run as a split (error-compensated)
+                                    tensor-core GEMM.  Written by the persistent loop kernel only; zero-initialise */
+  int op16;                      /* 0: fp32 storage / tf32 math in the persistent loops; 1: fp16, 2: bf16 operand copies (kind::f16) */
+  void *XA16, *XD16;             /* op16: 16-bit copies of XA / XD (same shapes), the tensor-core operands; zero-initialise */
+  const void *WaP16, *WdP16;     /* op16: 16-bit re-tiled weights (t2v_pack_step_tiles16 modes 0 / 1) */
 } T2VDecoderSeq;
+int t2v_sizeof_decoder_structs(int which);   /* sizeof(T2VDecoderSeq / T2VDecoderBwd / T2VDecoderInfer) for which = 0 / 1 / 2: binding check */
 int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);
 /* re-tile a decoder-step weight matrix into the order the persistent loop kernels stream it (same number of floats):
    mode 0: Wa [4096,1792] -> WaP ; 1: Wd [4096,2560] -> WdP ; 2: WaT [1792,4096] -> WaTP ; 3: WdT [2560,4096] -> WdTP */
 int t2v_pack_step_tiles(const float* W, int mode, float* out, cudaStream_t stream);
+/* 16-bit variant for op16 (fmt 1 = fp16, 2 = bf16): modes 0 / 1 only, K chunks of 64 columns */
+int t2v_pack_step_tiles16(const float* W, int mode, void* out, int fmt, cudaStream_t stream);
+/* strided fp32 -> 16-bit conversion (fmt 1 = fp16, 2 = bf16), e.g. the prenet columns of XA into XA16 */
+int t2v_cvt16_2d(const float* src, long long s_ld, void* dst, long long d_ld, long long rows, int cols, int fmt,
+                 cudaStream_t stream);
 
 typedef struct T2VDecoderBwd {
   T2VDecoderSeq f;               /* the forward description (same buffers) */

@@ -35,7 +35,10 @@ constexpr int NTHREADS = 512;
 constexpr int NS = 4;                          // ring depth: a stage = one K chunk of weights (16 KB) + activations (8 KB)
 constexpr int NW = NS, NA = NS;
 constexpr int W_STAGE = 128 * 128, A_STAGE = 64 * 128;
-constexpr int ATT_CHUNKS = 14, DEC_CHUNKS = 20; // 32-wide K chunks per CTA: (64 + 128 + 256) / 32 and (256 + 128 + 256) / 32
+// K chunks per CTA (one 128-byte swizzle row of K per chunk): fp32 storage = 32 columns -> (64 + 128 + 256) / 32 = 14 and
+// (256 + 128 + 256) / 32 = 20 chunks; 16-bit operands = 64 columns -> 7 and 10 chunks of the same 16 KB + 8 KB
+template <int OP> struct Chunks { static constexpr int ATT = OP ? 7 : 14, DEC = OP ? 10 : 20, CK = OP ? 64 : 32; };
+constexpr int ATT_CHUNKS = 14, DEC_CHUNKS = 20;
 constexpr int SLOT = 4 * 16 * 32;              // floats of one exchange slot: [gate][batch row of the owner][unit]
 constexpr int TH_MAX = 64;                     // text positions per CTA (two CTAs per utterance) -> Ti <= 128
 constexpr int PADW = 160;                      // alignment / cumulative-alignment rows with a 15-wide zero halo
@@ -82,25 +85,43 @@ constexpr int TRACE_T0 = 100, TRACE_STEPS = 4, TRACE_CTA_B = 77;
 // K offset (columns of the weight matrix = columns of the activation row) of chunk j of this CTA's K slice.
 //   attention_rnn row XA[t] = [prenet_t (256) | ctx_{t-1} (512) | h_att_{t-1} (1024)]: prenet chunks first (known long
 //   before), then h_att (complete one attention phase earlier), then ctx (the last thing to become ready).
-__device__ __forceinline__ int att_kofs(int j, int rank) {
+__host__ __device__ __forceinline__ int att_kofs(int j, int rank) {
   if (j < 2) return 64 * rank + 32 * j;
   if (j < 10) return PD + ED + 256 * rank + 32 * (j - 2);
   return PD + 128 * rank + 32 * (j - 10);
 }
+// 16-bit operands: the same K slices in 64-column chunks: prenet (1), h_att (4), ctx (2)
+__host__ __device__ __forceinline__ int att_kofs16(int j, int rank) {
+  if (j < 1) return 64 * rank;
+  if (j < 5) return PD + ED + 256 * rank + 64 * (j - 1);
+  return PD + 128 * rank + 64 * (j - 5);
+}
 //   decoder_rnn row XD[t] = [h_att_t (1024) | ctx_t (512) | h_dec_{t-1} (1024)]
-__device__ __forceinline__ int dec_kofs(int j, int rank) {
+__host__ __device__ __forceinline__ int dec_kofs(int j, int rank) {
   if (j < 8) return 256 * rank + 32 * j;
   if (j < 12) return H + 128 * rank + 32 * (j - 8);
   return H + ED + 256 * rank + 32 * (j - 12);
 }
+// 16-bit operands: h_att (4), ctx (2), h_dec (4)
+__host__ __device__ __forceinline__ int dec_kofs16(int j, int rank) {
+  if (j < 4) return 256 * rank + 64 * j;
+  if (j < 6) return H + 128 * rank + 64 * (j - 4);
+  return H + ED + 256 * rank + 64 * (j - 6);
+}
+template <int OP> __device__ __forceinline__ int att_kofs_t(int j, int rank) { return OP ? att_kofs16(j, rank) : att_kofs(j, rank); }
+template <int OP> __device__ __forceinline__ int dec_kofs_t(int j, int rank) { return OP ? dec_kofs16(j, rank) : dec_kofs(j, rank); }
 
 // Free-running inference: the prenet of step t needs the mel frame of step t-1, so its chunks come LAST in the attention_rnn GEMM
 // (h_att_{t-1}, ctx_{t-1} are older), and the decoder_rnn GEMM of step t runs inside step t: h_dec_{t-1} first, ctx_t last.
 // The functions return the chunk index of the teacher-forcing order (tile index of the packed weights); kofs follows from it.
-__device__ __forceinline__ int att_chunk_infer(int j) { return j < 8 ? j + 2 : (j < 12 ? j + 2 : j - 12); }   // h(8) ctx(4) prenet(2)
-__device__ __forceinline__ int dec_chunk_infer(int j) { return j < 8 ? j + 12 : (j < 16 ? j - 8 : j - 8); }    // h_dec(8) h_att(8) ctx(4)
+template <int OP> __device__ __forceinline__ int att_chunk_infer(int j) {      // h(8) ctx(4) prenet(2)  |  16-bit: h(4) ctx(2) prenet(1)
+  return OP ? (j < 6 ? j + 1 : 0) : (j < 12 ? j + 2 : j - 12);
+}
+template <int OP> __device__ __forceinline__ int dec_chunk_infer(int j) {      // h_dec(8) h_att(8) ctx(4)  |  16-bit: h_dec(4) h_att(4) ctx(2)
+  return OP ? (j < 4 ? j + 6 : j - 4) : (j < 8 ? j + 12 : j - 8);
+}
 
-template <bool INFER>
+template <bool INFER, int OP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_constant__ CUtensorMap tmWd,
                        const __grid_constant__ CUtensorMap tmXA, const __grid_constant__ CUtensorMap tmXD,
@@ -128,12 +149,20 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   uint64_t* s_full = e_full + 1;          // [1] processed-memory tile landed in S
   uint32_t* tmem_holder = (uint32_t*)(smem + OFF_TMEM);
 
+  constexpr int ATT_CHUNKS = Chunks<OP>::ATT, DEC_CHUNKS = Chunks<OP>::DEC;     // (shadow the fp32 counts of the file scope)
+  constexpr int JA_H = OP ? 1 : 2, JA_C = OP ? 5 : 10;          // attention_rnn GEMM: first chunk that needs h_att / ctx
+  constexpr int JD_C = OP ? 4 : 8, JD_D = OP ? 6 : 12;          // decoder_rnn GEMM: first chunk that needs ctx / h_dec
   const T2VDecoderSeq& s = p.s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_ctarank();
   const int cid = blockIdx.x / CL;
   const int B = s.B, Ti = s.Ti, To = s.To;
   const int tb = p.t_begin, te = p.t_end;
+  // rounding grid of the operand copies: tf32 for fp32 storage, the 16-bit format otherwise (ABI `rnd` codes, t2v_common.cuh)
+  const int opfmt = OP ? s.op16 : 0;
+  const int rnd_op = OP ? (s.op16 == 2 ? 3 : 2) : s.use_tc;
+  uint16_t* const xa16 = reinterpret_cast<uint16_t*>(s.XA16);
+  uint16_t* const xd16 = reinterpret_cast<uint16_t*>(s.XD16);
   unsigned* cnt_h = p.counters;
   unsigned* cnt_c = p.counters + 32;
   unsigned* cnt_d = p.counters + 64;
@@ -193,13 +222,13 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       };
       if (INFER) {
         for (int t = tb; t < te; ++t) {
-          for (int j = 0; j < ATT_CHUNKS; ++j) { const int c = att_chunk_infer(j); load_w(&tmWa, att_kofs(c, rank), (cid * CL + rank) * ATT_CHUNKS + c, p.wa_hint, pol_a); }
-          for (int j = 0; j < DEC_CHUNKS; ++j) { const int c = dec_chunk_infer(j); load_w(&tmWd, dec_kofs(c, rank), (cid * CL + rank) * DEC_CHUNKS + c, p.wd_hint, pol_d); }
+          for (int j = 0; j < ATT_CHUNKS; ++j) { const int c = att_chunk_infer<OP>(j); load_w(&tmWa, att_kofs_t<OP>(c, rank), (cid * CL + rank) * ATT_CHUNKS + c, p.wa_hint, pol_a); }
+          for (int j = 0; j < DEC_CHUNKS; ++j) { const int c = dec_chunk_infer<OP>(j); load_w(&tmWd, dec_kofs_t<OP>(c, rank), (cid * CL + rank) * DEC_CHUNKS + c, p.wd_hint, pol_d); }
         }
       } else {
         for (int t = tb; t <= te; ++t) {
-          if (t < te) for (int j = 0; j < ATT_CHUNKS; ++j) { load_w(&tmWa, att_kofs(j, rank), (cid * CL + rank) * ATT_CHUNKS + j, p.wa_hint, pol_a); if (j == 0) TR(t - tb, 24); }
-          if (t > tb) for (int j = 0; j < DEC_CHUNKS; ++j) load_w(&tmWd, dec_kofs(j, rank), (cid * CL + rank) * DEC_CHUNKS + j, p.wd_hint, pol_d);
+          if (t < te) for (int j = 0; j < ATT_CHUNKS; ++j) { load_w(&tmWa, att_kofs_t<OP>(j, rank), (cid * CL + rank) * ATT_CHUNKS + j, p.wa_hint, pol_a); if (j == 0) TR(t - tb, 24); }
+          if (t > tb) for (int j = 0; j < DEC_CHUNKS; ++j) load_w(&tmWd, dec_kofs_t<OP>(j, rank), (cid * CL + rank) * DEC_CHUNKS + j, p.wd_hint, pol_d);
           TR(t - tb, 25);
         }
       }
@@ -228,16 +257,16 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         for (int t = tb; t < te; ++t) {
           const unsigned n = (unsigned)(t - tb);
           for (int j = 0; j < ATT_CHUNKS; ++j) {
-            if (j < 8) need(cnt_h, seen_h, NCTA * n);
-            else if (j < 12) need(cnt_c, seen_c, NCTA * n);
+            if (j < JD_C) need(cnt_h, seen_h, NCTA * n);               // (h: 8 | 4 chunks, ctx: 4 | 2, prenet: 2 | 1)
+            else if (j < JD_D) need(cnt_c, seen_c, NCTA * n);
             else need(cnt_p, seen_p, NCTA * (n + 1));
-            load_a(&tmXA, att_kofs(att_chunk_infer(j), rank), t * B);
+            load_a(&tmXA, att_kofs_t<OP>(att_chunk_infer<OP>(j), rank), t * B);
           }
           for (int j = 0; j < DEC_CHUNKS; ++j) {
-            if (j < 8) need(cnt_d, seen_d, NCTA * n);
-            else if (j < 16) need(cnt_h, seen_h, NCTA * (n + 1));
+            if (j < JD_C) need(cnt_d, seen_d, NCTA * n);               // (h_dec: 8 | 4 chunks, h_att: 8 | 4, ctx: 4 | 2)
+            else if (j < 2 * JD_C) need(cnt_h, seen_h, NCTA * (n + 1));
             else need(cnt_c, seen_c, NCTA * (n + 1));
-            load_a(&tmXD, dec_kofs(dec_chunk_infer(j), rank), t * B);
+            load_a(&tmXD, dec_kofs_t<OP>(dec_chunk_infer<OP>(j), rank), t * B);
           }
         }
       } else
@@ -245,20 +274,20 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         const unsigned n = (unsigned)(t - tb);
         if (t < te) {
           for (int j = 0; j < ATT_CHUNKS; ++j) {
-            if (j >= 10) need(cnt_c, seen_c, NCTA * n);
-            else if (j >= 2) need(cnt_h, seen_h, NCTA * n);
-            if (j == 2) TR(n, 0);
-            if (j == 10) TR(n, 1);
-            load_a(&tmXA, att_kofs(j, rank), t * B);
+            if (j >= JA_C) need(cnt_c, seen_c, NCTA * n);
+            else if (j >= JA_H) need(cnt_h, seen_h, NCTA * n);
+            if (j == JA_H) TR(n, 0);
+            if (j == JA_C) TR(n, 1);
+            load_a(&tmXA, att_kofs_t<OP>(j, rank), t * B);
           }
           TR(n, 2);
         }
         if (t > tb) {
           for (int j = 0; j < DEC_CHUNKS; ++j) {
-            if (j < 8) need(cnt_h, seen_h, NCTA * n);
-            else if (j < 12) need(cnt_c, seen_c, NCTA * n);
+            if (j < JD_C) need(cnt_h, seen_h, NCTA * n);
+            else if (j < JD_D) need(cnt_c, seen_c, NCTA * n);
             else need(cnt_d, seen_d, NCTA * (n - 1));
-            load_a(&tmXD, dec_kofs(j, rank), (t - 1) * B);
+            load_a(&tmXD, dec_kofs_t<OP>(j, rank), (t - 1) * B);
           }
           TR(n, 3);
         }
@@ -269,7 +298,9 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     // elected lane issues: keeps every tcgen05 operand in uniform registers)
     {
       // instruction descriptor: D=f32, A=B=tf32, K-major both, N=64 (batch), M=128 (gate rows)
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // (16-bit operands: format 0 = fp16, 1 = bf16; one instruction consumes 32 bytes of K per row either way)
+      const uint32_t fmt = OP ? (opfmt == 2 ? 1u : 0u) : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // running ring position; the descriptors of stage s are the stage-0 descriptors + s * (stage bytes >> 4)
       int st = 0;
       uint32_t ph = 0;
@@ -288,12 +319,14 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           ready = mbar_test_wait(&full[sn], pn);           // overlaps the issue below
           if (elect_one()) {
             if (which == 0 && j == 0) TR(idx, 4);
-            if (which == 0 && j == 10) TR(idx, 5);
+            if (which == 0 && j == JA_C) TR(idx, 5);
             const uint64_t adesc = adesc0 + (uint64_t)(st * (W_STAGE >> 4));
             const uint64_t bdesc = bdesc0 + (uint64_t)(st * (A_STAGE >> 4));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              if (OP) tc_mma_f16(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+              else tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+            }
             tc_commit(&empty[st]);
             if (j == nch - 1) {
               tc_commit(&acc_full[which]);
@@ -324,7 +357,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     const int u = lane;                     // hidden unit within the cluster's 32
     const int jg = 32 * cid + u;            // global hidden unit
     const int blq = etid >> 5;              // cell phase: this thread owns batch rows bl = blq + 4*j (j<4) of unit u
-    const int rnd = s.use_tc;
+    const int rnd = rnd_op;
     uint32_t recv_remote[4], full_remote[2][4];
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
@@ -407,6 +440,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       const long long r0 = (long long)ts * B, r1 = (long long)(ts + 1) * B;
       const float* mk = s.drop_masks ? s.drop_masks + (long long)ts * 4 * B * H + (which ? 2LL * B * H : 0) : nullptr;
       float sv_i[4], sv_f[4], sv_g[4], sv_o[4], sv_c2[4];     // saved activations: written after the signal
+      float sv_lo[4] = {0.f, 0.f, 0.f, 0.f};                  // h_dec - (h_dec on the operand grid): the split projection's low part
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int bl = blq + 4 * j;
@@ -430,16 +464,25 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
             kc = (t2v_uniform(seed, which ? SITE_DEC_C : SITE_ATT_C, di) >= pdrop ? 1.f : 0.f) * kscale;
           }
         }
-        const float hd = t2v_rnd(h2 * kh, rnd);
+        const float hx = h2 * kh;               // exact h (after dropout); hd = its copy on the operand grid
+        const float hd = t2v_rnd(hx, rnd);
         cst[j] = c2 * kc;
         sv_i[j] = ig; sv_f[j] = fg; sv_g[j] = gg; sv_o[j] = og; sv_c2[j] = c2;
-        if (which == 0 || INFER) hq[bl * 32 + u] = hd;
+        // (inference: the mel / gate projection inside the kernel takes the exact h_dec, like the reference's fp32 Linear)
+        if (which == 0 || INFER) hq[bl * 32 + u] = which ? hx : hd;
         if (b < B) {       // only what other CTAs wait for goes out before the signal
           if (which == 0) {
             s.XA[(r1 + b) * XA_W + (PD + ED) + jg] = hd;       // h_att -> next step's recurrent input
             s.XD[(r0 + b) * XD_W + jg] = hd;                   // h_att -> decoder_rnn input / deferred dW operand
+            if (OP) {
+              const uint16_t h16 = t2v_enc16(hx, opfmt);
+              xa16[(r1 + b) * XA_W + (PD + ED) + jg] = h16;
+              xd16[(r0 + b) * XD_W + jg] = h16;
+            }
           } else {
             s.XD[(r1 + b) * XD_W + (H + ED) + jg] = hd;        // h_dec -> next step's recurrent input
+            if (OP) xd16[(r1 + b) * XD_W + (H + ED) + jg] = t2v_enc16(hx, opfmt);
+            sv_lo[j] = hx - hd;
           }
         }
       }
@@ -510,6 +553,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
               __stcs(gs, sv_i[j]); __stcs(gs + H, sv_f[j]); __stcs(gs + 2 * H, sv_g[j]); __stcs(gs + 3 * H, sv_o[j]);
             }
             if (CPs) __stcs(CPs + (r0 + b) * H + jg, sv_c2[j]);
+            if (which == 1 && s.HCLO) __stcs(s.HCLO + (r0 + b) * (H + ED) + jg, t2v_tf32(sv_lo[j]));
           }
         }
       }
@@ -534,7 +578,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     const int Th = (Ti + 1) >> 1;
     const int i0 = hh * Th;
     const int nrow = hh ? (Ti - Th) : Th;
-    const int rnd = s.use_tc;
+    const int rnd = rnd_op;
     int len = Ti;
     if (active && s.in_lens) { const long long l = s.in_lens[b]; len = l < Ti ? (int)l : Ti; }
     const int a = atid & 127;
@@ -659,7 +703,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           named_bar(BAR_ATT, 256);
           float* xa = s.XA + ((long long)t * B + b) * XA_W;
           if (t == 0) {                       // go frame = zeros (model.py:241-247): both prenet layers give exactly 0
-            if (atid < 128) xa[128 * hh + atid] = 0.f;
+            if (atid < 128) { xa[128 * hh + atid] = 0.f; if (OP) xa16[((long long)t * B + b) * XA_W + 128 * hh + atid] = 0; }
           } else {
             const float* pm0 = p.prenet_masks ? p.prenet_masks + ((long long)t * 2 * B + b) * PD : nullptr;
             const float* pm1 = pm0 ? pm0 + (long long)B * PD : nullptr;
@@ -677,7 +721,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
               acc = warp_sum(acc);
               if (lane == 0) {
                 const float keep = pm0 ? pm0[j] : (t2v_uniform(pseed, SITE_PRENET0, pidx + j) >= 0.5f ? 1.f : 0.f);
-                p1_s[j] = t2v_rnd(fmaxf(acc, 0.f) * keep * 2.f, rnd);
+                p1_s[j] = fmaxf(acc, 0.f) * keep * 2.f;       // (FFMA mat-vecs: the prenet stays exact fp32)
               }
             }
             named_bar(BAR_ATT, 256);
@@ -693,7 +737,9 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
               acc = warp_sum(acc);
               if (lane == 0) {
                 const float keep = pm1 ? pm1[j] : (t2v_uniform(pseed, SITE_PRENET1, pidx + j) >= 0.5f ? 1.f : 0.f);
-                xa[j] = t2v_rnd(fmaxf(acc, 0.f) * keep * 2.f, rnd);
+                const float pv = fmaxf(acc, 0.f) * keep * 2.f;
+                xa[j] = t2v_rnd(pv, rnd);
+                if (OP) xa16[((long long)t * B + b) * XA_W + j] = t2v_enc16(pv, opfmt);
               }
             }
           }
@@ -825,11 +871,18 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         named_bar(BAR_ATT, 256);
         if (atid == 0) TR(n, 22);
         {
-          const float c = t2v_rnd((fbuf[atid] + fbuf[256 + atid]) + (fbuf[512 + atid] + fbuf[768 + atid]), rnd);
+          const float cx = (fbuf[atid] + fbuf[256 + atid]) + (fbuf[512 + atid] + fbuf[768 + atid]);
+          const float c = t2v_rnd(cx, rnd);
           const int col = 256 * hh + atid;
           s.XD[((long long)t * B + b) * XD_W + H + col] = c;              // ctx_t -> decoder_rnn input
           s.XA[((long long)(t + 1) * B + b) * XA_W + PD + col] = c;      // ctx_t -> next attention_rnn input
-          if (INFER) ctx_s[atid] = c;
+          if (OP) {
+            const uint16_t c16 = t2v_enc16(cx, opfmt);
+            xd16[((long long)t * B + b) * XD_W + H + col] = c16;
+            xa16[((long long)(t + 1) * B + b) * XA_W + PD + col] = c16;
+          }
+          if (s.HCLO) __stcs(s.HCLO + ((long long)t * B + b) * (H + ED) + H + col, t2v_tf32(cx - c));
+          if (INFER) ctx_s[atid] = cx;                                    // exact ctx for the in-kernel projection
         }
         if (INFER) {
           // ---- partial mel / gate projection of this CTA's 256 ctx columns (the ctx half of [h_dec | ctx] W_pg^T): warp per output
@@ -918,6 +971,32 @@ __global__ void pack_step_tiles_kernel(const float* __restrict__ W, int mode, fl
   *reinterpret_cast<float4*>(out + i4 * 4) = *reinterpret_cast<const float4*>(W + src);
 }
 
+// 16-bit tiles (modes 0 / 1): [cluster][rank][chunk][gate*32 + unit][64 k] as fp16 / bf16, one contiguous 16 KB TMA box per chunk
+__global__ void pack_step_tiles16_kernel(const float* __restrict__ W, int mode, uint16_t* __restrict__ out, int fmt, long long n4) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= n4) return;
+  const int kk = (int)(i4 & 15) * 4;
+  const long long row = i4 >> 4;                 // tile * 128 + m
+  const int nch = mode ? Chunks<1>::DEC : Chunks<1>::ATT, ld = mode ? XD_W : XA_W;
+  const int m = (int)(row & 127);
+  const long long tile = row >> 7;
+  const int j = (int)(tile % nch), cr = (int)(tile / nch), rank = cr & 3, c = cr >> 2;
+  const int kofs = mode ? dec_kofs16(j, rank) : att_kofs16(j, rank);
+  const float4 v = *reinterpret_cast<const float4*>(W + (long long)((m >> 5) * H + 32 * c + (m & 31)) * ld + kofs + kk);
+  uint2 o;
+  o.x = (uint32_t)t2v_enc16(v.x, fmt) | ((uint32_t)t2v_enc16(v.y, fmt) << 16);
+  o.y = (uint32_t)t2v_enc16(v.z, fmt) | ((uint32_t)t2v_enc16(v.w, fmt) << 16);
+  *reinterpret_cast<uint2*>(out + i4 * 4) = o;
+}
+__global__ void cvt16_2d_kernel(const float* __restrict__ src, long long s_ld, uint16_t* __restrict__ dst, long long d_ld,
+                                long long rows, int cols, int fmt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  const int c = (int)(i % cols);
+  dst[r * d_ld + c] = t2v_enc16(src[r * s_ld + c], fmt);
+}
+
 bool persist_enabled() {      // read per call: the tests flip T2V_PERSIST to compare against the per-step launches
   const char* e = getenv("T2V_PERSIST");
   return !(e && e[0] == '0');
@@ -936,11 +1015,17 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
   if (!s->use_tc || s->B > 64 || s->Ti > 2 * TH_MAX || s->Ti < 1 || t_end - t_begin < 2) return 1;
   if (!s->parts || !s->ebuf) return 1;
   if (inf && (!inf->Wp1 || !inf->Wp2 || !inf->Wpg || !inf->bpg || !inf->O)) return 1;
+  const int op = s->op16 ? 1 : 0;
+  if (op && (!s->XA16 || !s->XD16 || !s->WaP16 || !s->WdP16 || s->op16 > 2)) {
+    t2v_set_error("op16 needs XA16 / XD16 / WaP16 / WdP16");
+    return -1;
+  }
   void (*kernel)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, PersistParams) =
-      inf ? dec_persist_fwd_kernel<true> : dec_persist_fwd_kernel<false>;
-  static int max_clusters[2] = {-1, -1};
-  static bool attr_set[2] = {false, false};
-  const int ki = inf ? 1 : 0;
+      inf ? (op ? dec_persist_fwd_kernel<true, 1> : dec_persist_fwd_kernel<true, 0>)
+          : (op ? dec_persist_fwd_kernel<false, 1> : dec_persist_fwd_kernel<false, 0>);
+  static int max_clusters[4] = {-1, -1, -1, -1};
+  static bool attr_set[4] = {false, false, false, false};
+  const int ki = (inf ? 1 : 0) + 2 * op;
   if (!attr_set[ki]) {
     T2V_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set[ki] = true;
@@ -987,15 +1072,24 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
   const long long rows = (long long)(s->To + 1) * s->B;
   int r;
   p.packed = (s->WaP && s->WdP && env_int("T2V_PERSIST_PACKED", 1)) ? 1 : 0;
-  if (p.packed) {
+  if (op) {
+    p.packed = 1;
+    if ((r = t2v_encode_tmap_2d(&tmWa, s->WaP16, 2, 64, (long long)NCTA * Chunks<1>::ATT * 128, 64, 128))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmWd, s->WdP16, 2, 64, (long long)NCTA * Chunks<1>::DEC * 128, 64, 128))) return r;
+  } else if (p.packed) {
     if ((r = t2v_encode_tmap_2d(&tmWa, s->WaP, 4, 32, (long long)NCTA * ATT_CHUNKS * 128, 32, 128))) return r;
     if ((r = t2v_encode_tmap_2d(&tmWd, s->WdP, 4, 32, (long long)NCTA * DEC_CHUNKS * 128, 32, 128))) return r;
   } else {
     if ((r = t2v_encode_tmap_2d(&tmWa, s->Wa, 4, XA_W, 4 * H, XA_W, 32))) return r;
     if ((r = t2v_encode_tmap_2d(&tmWd, s->Wd, 4, XD_W, 4 * H, XD_W, 32))) return r;
   }
-  if ((r = t2v_encode_tmap_2d(&tmXA, s->XA, 4, XA_W, rows, XA_W, 64))) return r;
-  if ((r = t2v_encode_tmap_2d(&tmXD, s->XD, 4, XD_W, rows, XD_W, 64))) return r;
+  if (op) {
+    if ((r = t2v_encode_tmap_2d(&tmXA, s->XA16, 2, XA_W, rows, XA_W, 64))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmXD, s->XD16, 2, XD_W, rows, XD_W, 64))) return r;
+  } else {
+    if ((r = t2v_encode_tmap_2d(&tmXA, s->XA, 4, XA_W, rows, XA_W, 64))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmXD, s->XD, 4, XD_W, rows, XD_W, 64))) return r;
+  }
   T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 128 * sizeof(unsigned), stream));
   T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmWa, tmWd, tmXA, tmXD, p));
   T2V_COUNT_LAUNCH();
@@ -1028,6 +1122,27 @@ int t2v_decoder_fwd_persist(const T2VDecoderSeq* s, int t_begin, int t_end, cuda
 }
 int t2v_decoder_infer_persist(const T2VDecoderInfer* d, int t_begin, int t_end, cudaStream_t stream) {
   return launch_persist(&d->f, d, t_begin, t_end, stream);
+}
+
+T2V_API int t2v_pack_step_tiles16(const float* W, int mode, void* out, int fmt, cudaStream_t stream) {
+  T2V_ARG_CHECK(W && out && (mode == 0 || mode == 1) && (fmt == 1 || fmt == 2), "mode 0..1, fmt 1 (fp16) / 2 (bf16)");
+  const long long n4 = (long long)4 * H * (mode == 0 ? XA_W : XD_W) / 4;
+  pack_step_tiles16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(W, mode, reinterpret_cast<uint16_t*>(out), fmt, n4);
+  T2V_COUNT_LAUNCH();
+  T2V_LAUNCH_CHECK();
+  return 0;
+}
+T2V_API int t2v_cvt16_2d(const float* src, long long s_ld, void* dst, long long d_ld, long long rows, int cols, int fmt,
+                         cudaStream_t stream) {
+  T2V_ARG_CHECK(src && dst && rows > 0 && cols > 0 && (fmt == 1 || fmt == 2), "fmt 1 (fp16) / 2 (bf16)");
+  const long long n = rows * cols;
+  cvt16_2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, s_ld, reinterpret_cast<uint16_t*>(dst), d_ld, rows, cols, fmt);
+  T2V_COUNT_LAUNCH();
+  T2V_LAUNCH_CHECK();
+  return 0;
+}
+T2V_API int t2v_sizeof_decoder_structs(int which) {
+  return which == 0 ? (int)sizeof(T2VDecoderSeq) : (which == 1 ? (int)sizeof(T2VDecoderBwd) : (int)sizeof(T2VDecoderInfer));
 }
 
 T2V_API int t2v_pack_step_tiles(const float* W, int mode, float* out, cudaStream_t stream) {

@@ -237,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       if (row < p.M && lane_has_row) {
         const int col0 = n0 + c0;
-        if (!p.epi_atomic && vec_ok && col0 + 32 <= p.N) {
+        if (p.epi_atomic != 1 && vec_ok && col0 + 32 <= p.N) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o;
@@ -249,6 +249,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               o.x += p.bias[col0 + j + 0]; o.y += p.bias[col0 + j + 1];
               o.z += p.bias[col0 + j + 2]; o.w += p.bias[col0 + j + 3];
             }
+            if (p.epi_atomic == 2) {          // D += tile (single writer per element: splits == 1)
+              const float4 old = *reinterpret_cast<const float4*>(drow + col0 + j);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
             *reinterpret_cast<float4*>(drow + col0 + j) = o;
           }
         } else {
@@ -258,9 +262,130 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (col < p.N) {
               float o = __uint_as_float(v[j]) * p.alpha;
               if (p.bias && blockIdx.z == 0) o += p.bias[col];
-              if (p.epi_atomic) atomicAdd(drow + col, o);
+              if (p.epi_atomic == 1) atomicAdd(drow + col, o);
+              else if (p.epi_atomic == 2) drow[col] += o;
               else drow[col] = o;
             }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-reduction GEMM with MN-major operands:  D[i, j] (+)= alpha * sum_r A[a_row0 + r, m0 + i] * B[b_row0 + r, n0 + j].
+// Both operands are read in their natural row-major layout (rows = the reduction index), so the weight-gradient GEMMs
+// dW = dY^T X (reference: autograd of nn.Linear / Conv1d, model.py:91-148) need no transposed copies.  A TMA box is
+// {32 floats of MN (128 B), BKR reduction rows} and lands as BKR swizzled 128-byte rows = the canonical UMMA MN-major
+// SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with LBO = one box and SBO = 1024 B; one tf32
+// MMA consumes 8 reduction rows (one 1024-byte swizzle atom per MN group), so the K advance is +1024 B.
+constexpr int BKR = 32;                      // reduction rows per stage
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((BKR * 128) >> 4) << 16;   // LBO: next group of 32 MN elements = next box
+  d |= (uint64_t)(1024 >> 4) << 32;          // SBO: next group of 8 reduction rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+  constexpr int BM = 128;
+  constexpr int A_BYTES = BM * BKR * 4;
+  constexpr int B_BYTES = BN * BKR * 4;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int BOX = 32 * BKR * 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_holder = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int it0 = blockIdx.z * p.iters_per_split;
+  const int n_it = min(p.iters_per_split, p.chunks_per_tap - it0);   // chunks_per_tap = total 32-row iterations; the last split may be short
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                 "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // boxes that start beyond the MN extent of an operand are skipped by TMA (fully out of bounds -> zero fill)
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        const int r = (it0 + it) * BKR;
+        uint8_t* sa = smem + s * STAGE_BYTES;
+#pragma unroll
+        for (int g = 0; g < BM / 32; ++g) tma_load_2d(sa + g * BOX, &tmA, m0 + 32 * g, p.a_row0 + r, &full[s]);
+#pragma unroll
+        for (int g = 0; g < BN / 32; ++g) tma_load_2d(sa + A_BYTES + g * BOX, &tmB, n0 + 32 * g, p.b_row0 + r, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D=f32, A=B=tf32, both MN-major (bits 15 / 16)
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_mnmajor_sw128_desc(sa);
+        const uint64_t bdesc = make_mnmajor_sw128_desc(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKR / 8; ++k)      // 8 reduction rows (1024 B of every MN group) per instruction
+          tc_mma<true>(tmem_base, adesc + (uint64_t)(64 * k), bdesc + (uint64_t)(64 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&empty[s]);
+      }
+      tc_commit(tmem_full);
+    }
+  } else if (n_it > 0) {
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    float* drow = p.D + (long long)blockIdx.z * p.split_stride + (long long)row * p.ldd;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (row < p.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          if (col < p.N) {
+            const float o = __uint_as_float(v[j]) * p.alpha;
+            if (p.epi_atomic == 1) atomicAdd(drow + col, o);
+            else if (p.epi_atomic == 2) drow[col] += o;
+            else drow[col] = o;
           }
         }
       }
@@ -383,4 +508,64 @@ T2V_API int t2v_gemm_tc(const void* A, long long lda, long long a_rows, long lon
                            b_tap_stride, a_k0, b_k0, esize, splits, split_stride, epi_atomic, alpha, bn_hint);
   if (r) return r;
   return t2v_gemm_tc_run(&plan, 0, 0, D, bias, stream);
+}
+
+namespace {
+int encode_mn(CUtensorMap* map, const void* base, long long cols, long long rows, long long ld) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) { t2v_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -2; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld * 4)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)BKR};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    t2v_set_error("cuTensorMapEncodeTiled (MN-major) failed with CUresult %d (cols=%lld rows=%lld ld=%lld)", (int)r, cols, rows, ld);
+    return -3;
+  }
+  return 0;
+}
+template <int BN, int STAGES>
+int launch_gemm_tc_mn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcParams& p, int splits, cudaStream_t st) {
+  constexpr int smem = STAGES * (128 + BN) * BKR * 4 + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_mn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(t2v_ceil_div(p.M, 128), t2v_ceil_div(p.N, BN), splits);
+  gemm_tc_mn_kernel<BN, STAGES><<<grid, 192, smem, st>>>(tmA, tmB, p);
+  T2V_COUNT_LAUNCH();
+  T2V_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace
+
+// D[n_a, n_b] (+)= alpha * sum_{r < rows} A[a_row0 + r, i] * B[b_row0 + r, j]   (fp32 storage, tf32 math; operands must already be on
+// the tf32 grid).  A: [>= a_row0 + rows, n_a] row-major with row stride lda, B likewise.  epi: 0 store (splits == 1 or split_stride),
+// 1 atomicAdd into a pre-initialised D, 2 non-atomic D += (splits == 1).  The reduction is cut into `splits` equal ranges of 32-row
+// iterations (splits must divide ceil(rows / 32)); rows past the end are zero-filled by TMA.
+T2V_API int t2v_gemm_tc_rowred(const float* A, long long lda, int n_a, long long a_row0, const float* B, long long ldb, int n_b,
+                               long long b_row0, float* D, long long ldd, long long rows, int splits, long long split_stride,
+                               int epi, float alpha, cudaStream_t stream) {
+  T2V_ARG_CHECK(A && B && D && n_a > 0 && n_b > 0 && rows > 0 && splits >= 1, "shape");
+  T2V_ARG_CHECK((((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "operand base must be 16-byte aligned");
+  T2V_ARG_CHECK((lda * 4) % 16 == 0 && (ldb * 4) % 16 == 0, "row strides must be multiples of 16 bytes");
+  const int iters = t2v_ceil_div(rows, BKR);
+  T2V_ARG_CHECK(splits <= iters, "more splits than 32-row iterations");
+  T2V_ARG_CHECK(splits == 1 || epi == 1, "split-K partial tiles are accumulated with atomics (epi 1)");
+  CUtensorMap tmA, tmB;
+  int r = encode_mn(&tmA, A, n_a, a_row0 + rows, lda);       // row extent = end of the reduction range: the tail is zero-filled
+  if (r) return r;
+  r = encode_mn(&tmB, B, n_b, b_row0 + rows, ldb);
+  if (r) return r;
+  GemmTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.D = D; p.ldd = ldd; p.split_stride = split_stride; p.M = n_a; p.N = n_b; p.iters_per_split = t2v_ceil_div(iters, splits); p.chunks_per_tap = iters;
+  p.epi_atomic = epi; p.alpha = alpha; p.a_row0 = (int)a_row0; p.b_row0 = (int)b_row0;
+  if (n_b > 128 && n_b % 256 == 0) return launch_gemm_tc_mn<256, 4>(tmA, tmB, p, splits, stream);
+  if (n_b > 64) return launch_gemm_tc_mn<128, 6>(tmA, tmB, p, splits, stream);
+  return launch_gemm_tc_mn<64, 8>(tmA, tmB, p, splits, stream);
 }

@@ -137,25 +137,30 @@ __global__ void bn_eval_prepare_kernel(const float* __restrict__ running_mean, c
 }
 
 // out = dropout(act(gamma*(y-mean)*invstd+beta)) on valid rows, 0 on pad rows
-__global__ void bn_act_fwd_kernel(const float* __restrict__ y, float* __restrict__ out, long long rows, int C,
-                                  RowSpace rs, BnCtx ctx, int rnd) {
+// out_lo (optional): the residual x - round(x) on the tf32 grid, for the split (error-compensated) tensor-core GEMMs
+__global__ void bn_act_fwd_kernel(const float* __restrict__ y, float* __restrict__ out, float* __restrict__ out_lo, long long rows,
+                                  int C, RowSpace rs, BnCtx ctx, int rnd) {
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index
   const long long total4 = rows * C / 4;
   if (i4 >= total4) return;
   const long long r = (i4 * 4) / C;
   const int c = (int)((i4 * 4) % C);
-  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f), ol = o;
   if (rs.valid(r)) {
     const float4 v = reinterpret_cast<const float4*>(y)[i4];
-    float in[4] = {v.x, v.y, v.z, v.w}, res[4];
+    float in[4] = {v.x, v.y, v.z, v.w}, res[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float pre = ctx.gamma[c + j] * ((in[j] - ctx.mean[c + j]) * ctx.invstd[c + j]) + ctx.beta[c + j];
-      res[j] = t2v_rnd(act_fwd(pre, ctx.act) * t2v_keep_scale(ctx.drop, drop_index(rs, r, c + j, C, ctx.T)), rnd);
+      const float x = act_fwd(pre, ctx.act) * t2v_keep_scale(ctx.drop, drop_index(rs, r, c + j, C, ctx.T));
+      res[j] = t2v_rnd(x, rnd);
+      lo[j] = t2v_tf32(x - res[j]);
     }
     o = make_float4(res[0], res[1], res[2], res[3]);
+    ol = make_float4(lo[0], lo[1], lo[2], lo[3]);
   }
   reinterpret_cast<float4*>(out)[i4] = o;
+  if (out_lo) reinterpret_cast<float4*>(out_lo)[i4] = ol;
 }
 
 // training-mode BN backward (given dgamma/dbeta sums): dy = gamma*invstd*(g - dbeta/n - xhat*dgamma/n); 0 on pad rows
@@ -530,13 +535,13 @@ T2V_API int t2v_bn_eval_prepare(const float* running_mean, const float* running_
   bn_eval_prepare_kernel<<<t2v_ceil_div(C, 128), 128, 0, st>>>(running_mean, running_var, C, eps, mean, invstd);
   LAUNCH_END();
 }
-T2V_API int t2v_bn_act_fwd(const float* y, float* out, long long rows, int C, int period, int lo, int hi,
+T2V_API int t2v_bn_act_fwd(const float* y, float* out, float* out_lo, long long rows, int C, int period, int lo, int hi,
                            const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
                            const float* drop_mask, unsigned long long seed, unsigned int site, float p, int T,
                            int rnd, cudaStream_t st) {
   T2V_ARG_CHECK(C % 4 == 0, "C must be a multiple of 4");
   BnCtx ctx = mk_ctx(y, mean, invstd, gamma, beta, act, mk_drop(drop_mask, seed, site, p), T);
-  bn_act_fwd_kernel<<<grid1d(rows * C / 4, 256), 256, 0, st>>>(y, out, rows, C, mk_rs(period, lo, hi), ctx, rnd);
+  bn_act_fwd_kernel<<<grid1d(rows * C / 4, 256), 256, 0, st>>>(y, out, out_lo, rows, C, mk_rs(period, lo, hi), ctx, rnd);
   LAUNCH_END();
 }
 // pass 1 of BN backward: dbeta_sum / dgamma_sum (double[C], pre-zeroed)

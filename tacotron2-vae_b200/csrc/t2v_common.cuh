@@ -124,7 +124,35 @@ __device__ __forceinline__ float t2v_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ float t2v_rnd(float x, int flag) { return flag ? t2v_tf32(x) : x; }
+// 16-bit operand formats of the tensor-core path (kind::f16): the fp32 copy of an operand is rounded onto the same grid as
+// its 16-bit copy, so a tf32 GEMM over the fp32 copy and an f16 GEMM over the 16-bit copy see the same numbers.
+//   fp16 has the significand of tf32 (11 bits) with a narrower exponent (|x| <= 65504; below 6.1e-5 the spacing is 6e-8):
+//   used for forward activations and weights.  bf16 = 8-bit significand, fp32 exponent.
+__device__ __forceinline__ uint16_t t2v_f16_bits(float x) {
+  uint16_t h;
+  asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return h;
+}
+__device__ __forceinline__ uint16_t t2v_bf16_bits(float x) {
+  uint16_t h;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return h;
+}
+__device__ __forceinline__ float t2v_f16_to_f32(uint16_t h) {
+  float f;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+  return f;
+}
+__device__ __forceinline__ float t2v_bf16_to_f32(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
+// operand rounding flag of the ABI (`rnd`): 0 none, 1 tf32 grid, 2 fp16 grid, 3 bf16 grid
+__device__ __forceinline__ float t2v_rnd(float x, int flag) {
+  if (flag == 0) return x;
+  if (flag == 1) return t2v_tf32(x);
+  if (flag == 2) return t2v_f16_to_f32(t2v_f16_bits(x));
+  return t2v_bf16_to_f32(t2v_bf16_bits(x));
+}
+// 16-bit encoding of an operand for fmt 1 (fp16) / 2 (bf16)
+__device__ __forceinline__ uint16_t t2v_enc16(float x, int fmt) { return fmt == 2 ? t2v_bf16_bits(x) : t2v_f16_bits(x); }
 
 __device__ __forceinline__ float t2v_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 // tanh through one MUFU exp + one fast divide: absolute error ~1e-7 (fp32 rounding level), ~4x fewer instructions than

@@ -107,15 +107,29 @@ class Ops(object):
     """GEMM front-end that picks the kernel for the precision mode."""
 
     def __init__(self, precision="fp32"):
-        assert precision in ("fp32", "tf32")
+        assert precision in ("fp32", "tf32", "fp16", "bf16")
         self.precision = precision
-        self.tc = precision == "tf32"
+        self.tc = precision != "fp32"
         self.R = 1 if self.tc else 0       # producers round tensor-core operands to the tf32 grid on store
+        # the persistent decoder loops stream 16-bit operand copies in the fp16 / bf16 modes (kind::f16 MMAs): fp16 keeps the
+        # 11-bit significand of tf32 at half the bytes; everything outside the two loops runs as in the tf32 mode
+        self.op16 = {"fp16": 1, "bf16": 2}.get(precision, 0)
+        self.RX = (self.op16 + 1) if self.op16 else self.R     # rounding grid of the decoder-loop activations (ABI `rnd` code)
+        # split (error-compensated) tensor-core GEMMs x = x_hi + x_lo for the two places where tf32 rounding dominates the
+        # error of the outputs: the deferred mel / gate projection and the Postnet forward (DESIGN.md "Precision modes")
+        self.split = self.tc and __import__("os").environ.get("T2V_SPLIT", "1") != "0"
 
     @staticmethod
     def bn(M, N):
         """N-tile of the tcgen05 GEMM: 256 for the large GEMMs (halves the activation-tile re-reads per FLOP)"""
         return 256 if (N >= 512 and N % 256 == 0 and M >= 4096 and _BN256) else 128
+
+    def lo(self, W, Whi):
+        """low part of a split weight: tf32(W - W_hi)"""
+        Wl = W.detach().clone()
+        L("t2v_axpby", Whi, -1.0, Wl, 1.0, Wl.numel())
+        L("t2v_round_tf32", Wl, Wl.numel())
+        return Wl
 
     def wr(self, W):
         """weights consumed directly by a tensor-core GEMM: tf32-rounded copy (tcgen05 truncates otherwise)"""
@@ -142,7 +156,7 @@ class Ops(object):
     def linear(self, x, lda, W, ldw, out, ldd, M, N, K, bias=None, accumulate=False, a_rows=None, force_exact=False):
         if self.tc and not force_exact and self._tc_ok((x, lda), (W, ldw)) and M >= 1:
             L("t2v_gemm_tc", x, lda, a_rows or M, K, W, ldw, N, K, out, ldd, bias, M, N, K, 1, 0, 0, 0, 0, 4, 1, 0,
-              1 if accumulate else 0, 1.0, self.bn(M, N))
+              2 if accumulate else 0, 1.0, self.bn(M, N))
         else:
             self.gemm(x, lda, 1, W, ldw, 1, out, ldd, M, N, K, 1.0, 1.0 if accumulate else 0.0, bias)
 
@@ -154,21 +168,25 @@ class Ops(object):
             WT = _zeros(K, Np, device=W.device)
             L("t2v_transpose", W, ldw, WT, Np, N, K, 1)
             L("t2v_gemm_tc", dy, ldy, M, N, WT, Np, K, N, dx, lddx, None, M, K, N, 1, 0, 0, 0, 0, 4, 1, 0,
-              1 if accumulate else 0, 1.0, 128)
+              2 if accumulate else 0, 1.0, 128)
         else:
             self.gemm(dy, ldy, 1, W, 1, ldw, dx, lddx, M, K, N, 1.0, 1.0 if accumulate else 0.0, None)
 
     # dW[N,K] = dy[M,N]^T @ x[M,K]   (reduction over the M rows); dW must be zero-initialised unless accumulate
     def linear_dw(self, dy, ldy, x, ldx, dW, lddw, M, N, K, accumulate=False, device=None, force_exact=False):
-        if self.tc and not force_exact and M >= 256 and device is not None:
-            Mp = _ceil4(M)
-            dyT = _empty(N, Mp, device=device)
-            xT = _empty(K, Mp, device=device)
-            L("t2v_transpose", dy, ldy, dyT, Mp, M, N, 1)
-            L("t2v_transpose", x, ldx, xT, Mp, M, K, 1)
-            self._tc_reduce_rows(dyT, Mp, N, 0, xT, Mp, K, 0, dW, lddw, M, accumulate)
+        if self.tc and not force_exact and M >= 256 and self._tc_ok((dy, ldy), (x, ldx)):
+            self.rowred(dy, ldy, N, 0, x, ldx, K, 0, dW, lddw, M)
         else:
             self.gemm(dy, 1, ldy, x, 1, ldx, dW, lddw, N, K, M, 1.0, 1.0 if accumulate else 0.0, None)
+
+    @staticmethod
+    def rowred(A, lda, n_a, a_row0, Bm, ldb, n_b, b_row0, D, ldd, rows):
+        """D[n_a, n_b] += sum_r A[a_row0+r, :]^T B[b_row0+r, :] on the MN-major tcgen05 kernel (no transposed copies);
+        split over the reduction so that ~2 CTAs per SM exist.  D must be zero-initialised (or hold the running sum)."""
+        iters = (rows + 31) // 32
+        tiles = ((n_a + 127) // 128) * ((n_b + 255) // 256 if (n_b > 128 and n_b % 256 == 0) else (n_b + 127) // 128)
+        splits = max(1, min(iters, int(round(296.0 / tiles))))
+        L("t2v_gemm_tc_rowred", A, lda, n_a, a_row0, Bm, ldb, n_b, b_row0, D, ldd, rows, splits, 0, 1, 1.0)
 
     @staticmethod
     def _tc_reduce_rows(AT, lda, n_a, a_k0, BT, ldb, n_b, b_k0, D, ldd, Mred, accumulate, a_inner=None, b_inner=None):
@@ -189,7 +207,7 @@ class Ops(object):
 
 # ======================================================================================================= helpers
 def _bn_forward(ops, Y, Xout, rows, C, period, lo, hi, n_valid, P, pre, training, act, mask, seed, site, p, T, dev,
-                update_running=True, rnd=0):
+                update_running=True, rnd=0, out_lo=None):
     """BatchNorm (batch stats in training, running stats in eval) + activation + dropout.  Returns (mean, invstd)."""
     mean = _empty(C, device=dev)
     invstd = _empty(C, device=dev)
@@ -201,7 +219,7 @@ def _bn_forward(ops, Y, Xout, rows, C, period, lo, hi, n_valid, P, pre, training
           P[pre + ".num_batches_tracked"] if update_running else None)
     else:
         L("t2v_bn_eval_prepare", P[pre + ".running_mean"], P[pre + ".running_var"], C, 1e-5, mean, invstd)
-    L("t2v_bn_act_fwd", Y, Xout, rows, C, period, lo, hi, mean, invstd, P[pre + ".weight"], P[pre + ".bias"], act,
+    L("t2v_bn_act_fwd", Y, Xout, out_lo, rows, C, period, lo, hi, mean, invstd, P[pre + ".weight"], P[pre + ".bias"], act,
       mask, seed, site, p, T, rnd)
     return mean, invstd
 
@@ -239,13 +257,16 @@ class _Saved(object):
 
 
 # ======================================================================================================= conv1d stacks
-def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, seed, site0, dev, round_last=True):
+def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, seed, site0, dev, round_last=True, Xlo=None):
     """k=5/p=2 Conv1d + BatchNorm1d + act + dropout(.5) layers over padded channels-last rows (Encoder
-    model.py:159-177, Postnet model.py:105-148).  X: [B*(T+4), chans[0]].  Returns (out, saved)."""
+    model.py:159-177, Postnet model.py:105-148).  X: [B*(T+4), chans[0]].  Returns (out, saved).
+    Xlo: the low part of the split input (x = X + Xlo, both on the tf32 grid) -> every layer runs as the three-term split
+    x_hi W_hi + x_lo W_hi + x_hi W_lo on the tensor cores (fp32-level accuracy at 3x the tf32 GEMM time)."""
     Tp = T + 4
     R = B * Tp
     M = R - 4
     saved = []
+    split = Xlo is not None and ops.tc
     for i in range(len(chans) - 1):
         Ci, Co = chans[i], chans[i + 1]
         pre = "%s.%d" % (prefix, i)
@@ -254,18 +275,28 @@ def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, se
         L("t2v_conv1d_pack", W, Wk, Co, Ci, 5, 0, ops.R)
         Y = _zeros(R, Co, device=dev)
         if ops.tc:
+            bn = ops.bn(M, Co)
             L("t2v_gemm_tc", X, Ci, R, Ci, Wk, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co, P[pre + ".0.conv.bias"], M, Co, Ci, 5, 1,
-              Ci, 0, 0, 4, 1, 0, 0, 1.0, ops.bn(M, Co))
+              Ci, 0, 0, 4, 1, 0, 0, 1.0, bn)
+            if split:
+                Wf = _empty(Co, 5 * Ci, device=dev)
+                L("t2v_conv1d_pack", W, Wf, Co, Ci, 5, 0, 0)
+                Wl = ops.lo(Wf, Wk)
+                L("t2v_gemm_tc", Xlo, Ci, R, Ci, Wk, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co, None, M, Co, Ci, 5, 1,
+                  Ci, 0, 0, 4, 1, 0, 2, 1.0, bn)
+                L("t2v_gemm_tc", X, Ci, R, Ci, Wl, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co, None, M, Co, Ci, 5, 1,
+                  Ci, 0, 0, 4, 1, 0, 2, 1.0, bn)
         else:
             ops.gemm(X, Ci, 1, Wk, 5 * Ci, 1, _p(Y, 2 * Co), Co, M, Co, 5 * Ci, 1.0, 0.0, P[pre + ".0.conv.bias"])
         Xn = _empty(R, Co, device=dev)
         p = 0.5 if training else 0.0
         mask = None if masks is None else masks[i]
         last = i == len(chans) - 2
+        Xnlo = _empty(R, Co, device=dev) if (split and not last) else None
         mi = _bn_forward(ops, Y, Xn, R, Co, Tp, 2, 2 + T, B * T, P, pre + ".1", training, acts[i], mask, seed, site0 + i, p, T, dev,
-                         rnd=ops.R if (round_last or not last) else 0)
+                         rnd=ops.R if (round_last or not last) else 0, out_lo=Xnlo)
         saved.append(dict(X=X, Y=_Saved(Y, mi), mask=mask, p=p, Ci=Ci, Co=Co, act=acts[i], W=W))
-        X = Xn
+        X, Xlo = Xn, Xnlo
     return X, saved
 
 
@@ -302,15 +333,9 @@ def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0
             # weight gradient in tap-major form: dWk[co, tap*Ci+ci] = sum_r dY[r+2, co] * X[r+tap, ci]
             dWk = _zeros(Co, 5 * Ci, device=dev)
             if ops.tc:
-                # K-major operands for the row reduction: dyT[co, r] = dY[r+2, co]; xT[ci, r] = X[r+tap, ci].  The tap shift
-                # is applied while transposing because TMA needs 16-byte aligned inner coordinates.
-                Mp = _ceil4(M)
-                dyT = _zeros(Co, Mp, device=dev)
-                L("t2v_transpose", _p(dY, 2 * Co), Co, dyT, Mp, M, Co, 1)
-                xT = _zeros(Ci, Mp, device=dev)
+                # one row-reduction GEMM per tap: the tap is a row offset of the X operand (MN-major operands, no transposes)
                 for tap in range(5):
-                    L("t2v_transpose", _p(s["X"], tap * Ci), Ci, xT, Mp, M, Ci, 1)
-                    Ops._tc_reduce_rows(dyT, Mp, Co, 0, xT, Mp, Ci, 0, _p(dWk, tap * Ci), 5 * Ci, M, True)
+                    Ops.rowred(dY, Co, Co, 2, s["X"], Ci, Ci, tap, _p(dWk, tap * Ci), 5 * Ci, M)
             else:
                 ops.gemm(_p(dY, 2 * Co), 1, Co, s["X"], 1, Ci, dWk, 5 * Ci, Co, 5 * Ci, M, 1.0, 0.0, None)
             gW = _empty(Co, Ci, 5, device=dev)
@@ -396,8 +421,13 @@ def encoder_backward(ops, P, dmem, ctx, training, seed, dev, grads):
           Tp * 4 * Hh, WT[0], WT[1], _p(dmem, t0 * 512), _p(dmem, t1 * 512 + Hh), Ti * 512, dcb[0], dcb[1], GS[0, t0], GS[1, t1],
           CS[0, t0 + 1], CS[1, t1 + 1], CS[0, t0], CS[1, t1 + 2], _p(DGs[0], (2 + t0) * 4 * Hh), _p(DGs[1], (2 + t1) * 4 * Hh),
           lens, t0, t1, B, Hh)
+    if ops.tc:      # operands of the tensor-core weight-gradient GEMMs go onto the tf32 grid (tcgen05 would truncate)
+        L("t2v_round_tf32", HoutP, HoutP.numel())
     for d, sfx in enumerate(("", "_reverse")):
         DG = DGs[d]
+        gb = _colsum(DG, R, 4 * Hh, 1, 0, 1, dev)
+        if ops.tc:
+            L("t2v_round_tf32", DG, DG.numel())
         # batched weight grads; h_prev of row r is HoutP[r -/+ 1] (zero pad rows make the boundaries right)
         gWhh = _zeros(4 * Hh, Hh, device=dev)
         if d == 0:
@@ -407,9 +437,6 @@ def encoder_backward(ops, P, dmem, ctx, training, seed, dev, grads):
         grads["encoder.lstm.weight_hh_l0" + sfx] = gWhh
         gWih = _zeros(4 * Hh, 512, device=dev)
         ops.linear_dw(DG, 4 * Hh, X3, 512, gWih, 512, R, 4 * Hh, 512, device=dev)
-        gb = _colsum(DG, R, 4 * Hh, 1, 0, 1, dev)
-        if ops.tc:
-            L("t2v_round_tf32", DG, DG.numel())
         grads["encoder.lstm.weight_ih_l0" + sfx] = gWih
         grads["encoder.lstm.bias_ih_l0" + sfx] = gb
         grads["encoder.lstm.bias_hh_l0" + sfx] = gb.clone()
@@ -594,6 +621,17 @@ def pack_decoder_weights(P, dev, R=0):
     return Wa, Wd, Wpg, bpg
 
 
+def pack_projection_lo(ops, P, W, dev):
+    """W_lo = tf32(W - W_hi) of [linear_projection ; gate_layer] for the split projection"""
+    if not (ops.tc and ops.split):
+        return
+    Wf = _empty(81, 1536, device=dev)
+    L("t2v_copy2d", P[_D + "linear_projection.linear_layer.weight"], 1536, 1, Wf, 1536, 80, 1536, 0.0, 0)
+    L("t2v_copy2d", P[_D + "gate_layer.linear_layer.weight"], 1536, 1, _p(Wf, 80 * 1536), 1536, 1, 1536, 0.0, 0)
+    W["Wpg_x"] = Wf                         # exact copy (the in-kernel projection of the free-running loop uses it)
+    W["Wpg_lo"] = ops.lo(Wf, W["Wpg"])
+
+
 def _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_value, in_len, mem, pmem, buf):
     S.B, S.Ti, S.To = B, Ti, To
     S.use_tc = 1 if ops.tc else 0
@@ -612,11 +650,14 @@ def _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_v
     S.Wloc = P[_A + "location_layer.location_dense.linear_layer.weight"].data_ptr()
     S.v = P[_A + "v.linear_layer.weight"].data_ptr()
     S.mem, S.pmem = mem.data_ptr(), pmem.data_ptr()
-    for k in ("XA", "XD", "CA", "CD", "CUM", "align", "GA", "GD", "CPA", "CPD", "ASAVE", "parts", "qparts", "ebuf"):
+    for k in ("XA", "XD", "CA", "CD", "CUM", "align", "GA", "GD", "CPA", "CPD", "ASAVE", "parts", "qparts", "ebuf", "HCLO",
+              "XA16", "XD16"):
         setattr(S, k, _lib.ptr(buf.get(k)))
+    S.op16 = ops.op16 if buf.get("XA16") is not None else 0
+    S.WaP16, S.WdP16 = _lib.ptr(W.get("WaP16")), _lib.ptr(W.get("WdP16"))
 
 
-def alloc_decoder_buffers(B, Ti, To, dev, save=True):
+def alloc_decoder_buffers(B, Ti, To, dev, save=True, op16=0, split=False):
     buf = dict(XA=_zeros((To + 1) * B, 1792, device=dev), XD=_zeros((To + 1) * B, 2560, device=dev),
                CA=_zeros((To + 1) * B, 1024, device=dev), CD=_zeros((To + 1) * B, 1024, device=dev),
                CUM=_zeros((To + 1) * B, Ti, device=dev), align=_zeros(B, To, Ti, device=dev),
@@ -626,7 +667,41 @@ def alloc_decoder_buffers(B, Ti, To, dev, save=True):
         buf.update(GA=_empty(To * B, 4096, device=dev), GD=_empty(To * B, 4096, device=dev),
                    CPA=_empty(To * B, 1024, device=dev), CPD=_empty(To * B, 1024, device=dev),
                    ASAVE=_empty(To * B * Ti, 128, device=dev))
+    if op16:        # 16-bit operand copies of XA / XD for the persistent loop (zero rows = the initial h / ctx / go frame)
+        buf.update(XA16=torch.zeros((To + 1) * B, 1792, device=dev, dtype=torch.int16),
+                   XD16=torch.zeros((To + 1) * B, 2560, device=dev, dtype=torch.int16))
+    if split:       # low parts of [h_dec_t | ctx_t] for the split mel / gate projection
+        buf["HCLO"] = _zeros(To * B, 1536, device=dev)
     return buf
+
+
+def pack_step_weights(ops, W, dev):
+    """tile-contiguous copies of Wa / Wd for the persistent loop kernels (decoder_persist.cu): fp32 tiles (tf32 math) and, in the
+    fp16 / bf16 modes, 16-bit tiles made from the same (already rounded) fp32 matrices"""
+    if not ops.tc:
+        return
+    W["WaP"], W["WdP"] = _empty(4096, 1792, device=dev), _empty(4096, 2560, device=dev)
+    L("t2v_pack_step_tiles", W["Wa"], 0, W["WaP"])
+    L("t2v_pack_step_tiles", W["Wd"], 1, W["WdP"])
+    if ops.op16:
+        W["WaP16"] = torch.empty(4096, 1792, device=dev, dtype=torch.int16)
+        W["WdP16"] = torch.empty(4096, 2560, device=dev, dtype=torch.int16)
+        L("t2v_pack_step_tiles16", W["Wa"], 0, W["WaP16"], ops.op16)
+        L("t2v_pack_step_tiles16", W["Wd"], 1, W["WdP16"], ops.op16)
+
+
+def project_mel_gate(ops, W, XD, HCLO, O, B, To):
+    """deferred linear_projection + gate_layer of [h_dec_t | ctx_t] for all steps (model.py:383-388) -> O [To*B, 84].
+    h_dec_t sits in XD row t+1 (cols 1536..), ctx_t in XD row t (cols 1024..1535), both on the operand grid; with the low
+    parts (HCLO, W_lo) the product is the three-term split x_hi W_hi + x_lo W_hi + x_hi W_lo: the mel frames are sums with
+    heavy cancellation, and plain tf32 rounding of this one GEMM was 90 % of the mel error of the whole decoder."""
+    n = To * B
+    ops.linear(_p(XD, B * 2560 + 1536), 2560, W["Wpg"], 1536, O, 84, n, 81, 1024, bias=W["bpg"], a_rows=n)
+    ops.linear(_p(XD, 1024), 2560, _p(W["Wpg"], 1024), 1536, O, 84, n, 81, 512, accumulate=True, a_rows=n)
+    if HCLO is not None and ops.tc and W.get("Wpg_lo") is not None:
+        ops.linear(HCLO, 1536, W["Wpg"], 1536, O, 84, n, 81, 1536, accumulate=True)
+        ops.linear(_p(XD, B * 2560 + 1536), 2560, W["Wpg_lo"], 1536, O, 84, n, 81, 1024, accumulate=True, a_rows=n)
+        ops.linear(_p(XD, 1024), 2560, _p(W["Wpg_lo"], 1024), 1536, O, 84, n, 81, 512, accumulate=True, a_rows=n)
 
 
 def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, drop_masks, seed, mask_value, dev):
@@ -638,13 +713,11 @@ def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, dro
     W["Wa"], W["Wd"], W["Wpg"], W["bpg"] = pack_decoder_weights(P, dev, ops.R)
     W["Wq"] = ops.wr(P[_A + "query_layer.linear_layer.weight"])
     W["WconvT"] = conv_weight_T(P, dev)
-    if ops.tc:      # tile-contiguous copies for the persistent loop kernel (decoder_persist.cu)
-        W["WaP"], W["WdP"] = _empty(4096, 1792, device=dev), _empty(4096, 2560, device=dev)
-        L("t2v_pack_step_tiles", W["Wa"], 0, W["WaP"])
-        L("t2v_pack_step_tiles", W["Wd"], 1, W["WdP"])
+    pack_step_weights(ops, W, dev)
+    pack_projection_lo(ops, P, W, dev)
     pmem = _empty(B * Ti, 128, device=dev)
     ops.linear(memory, 512, ops.wr(P[_A + "memory_layer.linear_layer.weight"]), 512, pmem, 128, B * Ti, 128, 512)
-    buf = alloc_decoder_buffers(B, Ti, To, dev, save=True)
+    buf = alloc_decoder_buffers(B, Ti, To, dev, save=True, op16=ops.op16, split=ops.split)
     # prenet over the go frame + all teacher frames (model.py:406-409); dropout always on (model.py:101)
     Fr = _empty((To + 1) * B, 80, device=dev)
     L("t2v_bct_to_rows_tb_shift", mel_tgt, Fr, B, 80, To, ops.R)
@@ -657,7 +730,9 @@ def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, dro
     L("t2v_relu_drop_fwd", P1pre, P1, 256, n, 256, m0, seed, SITE_PRENET, 0.5, 0, ops.R)
     P2pre = _empty(n, 256, device=dev)
     ops.linear(P1, 256, ops.wr(P[_D + "prenet.layers.1.linear_layer.weight"]), 256, P2pre, 256, n, 256, 256)
-    L("t2v_relu_drop_fwd", P2pre, buf["XA"], 1792, n, 256, m1, seed, SITE_PRENET + 1, 0.5, 0, ops.R)
+    L("t2v_relu_drop_fwd", P2pre, buf["XA"], 1792, n, 256, m1, seed, SITE_PRENET + 1, 0.5, 0, ops.RX)
+    if ops.op16:
+        L("t2v_cvt16_2d", buf["XA"], 1792, buf["XA16"], 1792, n, 256, ops.op16)
     S = _lib.T2VDecoderSeq()
     _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_value, in_len, memory, pmem, buf)
     _trace("  fwd prenet+pack")
@@ -665,8 +740,7 @@ def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, dro
     _trace("  fwd decoder loop")
     # deferred mel/gate projection of [h_dec_t | ctx_t] for all steps (model.py:383-388)
     O = _zeros(To * B, 84, device=dev)
-    ops.linear(_p(buf["XD"], B * 2560 + 1536), 2560, W["Wpg"], 1536, O, 84, To * B, 81, 1024, bias=W["bpg"], a_rows=To * B)
-    ops.linear(_p(buf["XD"], 1024), 2560, _p(W["Wpg"], 1024), 1536, O, 84, To * B, 81, 512, accumulate=True, a_rows=To * B)
+    project_mel_gate(ops, W, buf["XD"], buf.get("HCLO"), O, B, To)
     ctx = dict(B=B, Ti=Ti, To=To, W=W, pmem=pmem, memory=memory, buf=buf, S=S, Fr=Fr, P1pre=P1pre, P1=P1, P2pre=P2pre,
                m0=m0, m1=m1, seed=seed, O=O)
     return O, buf["align"], ctx
@@ -777,9 +851,14 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
 
 
 # ======================================================================================================= postnet + outputs
-def postnet_forward(ops, P, X0p, B, To, training, masks, seed, dev):
+def postnet_forward(ops, P, X0p, B, To, training, masks, seed, dev, X0lo=None):
     return conv_stack_forward(ops, P, "postnet.convolutions", X0p, B, To, [80, 512, 512, 512, 512, 80], [2, 2, 2, 2, 0],
-                              training, masks, seed, SITE_POST, dev, round_last=False)
+                              training, masks, seed, SITE_POST, dev, round_last=False, Xlo=X0lo)
+
+
+def split_lo(ops, x, x_hi):
+    """tf32(x - x_hi): the low part of a split tensor-core operand"""
+    return ops.lo(x, x_hi)
 
 
 class TrainContext(object):
@@ -815,10 +894,13 @@ def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=No
     X0p = _zeros(B * (To + 4), 80, device=dev)
     L("t2v_rows_tb_to_padded", O, 84, X0p, B, 80, To, 0)
     X0r = X0p                                             # Postnet conv-0 operand (tf32-rounded copy in the tensor-core mode)
+    X0lo = None
     if ops.tc:
         X0r = _zeros(B * (To + 4), 80, device=dev)
         L("t2v_rows_tb_to_padded", O, 84, X0r, B, 80, To, 1)
-    Y5, c.post = postnet_forward(ops, P, X0r, B, To, training, g("post"), seed, dev)
+        if ops.split:
+            X0lo = split_lo(ops, X0p, X0r)
+    Y5, c.post = postnet_forward(ops, P, X0r, B, To, training, g("post"), seed, dev, X0lo=X0lo)
     _trace("fwd postnet")
     lens = out_len if mask_padding else None
     mel = _empty(B, 80, To, device=dev)

@@ -10,7 +10,7 @@ from ._lib import call as L
 
 
 def default_precision():
-    return os.environ.get("T2V_PRECISION", "tf32")
+    return os.environ.get("T2V_PRECISION", "fp16")
 
 
 def _need_cuda(t, what):
@@ -127,16 +127,13 @@ class DecoderSession(object):
         self.W["Wa"], self.W["Wd"], self.W["Wpg"], self.W["bpg"] = engine.pack_decoder_weights(P, dev, ops.R)
         self.W["Wq"] = ops.wr(P["decoder.attention_layer.query_layer.linear_layer.weight"])
         self.W["WconvT"] = engine.conv_weight_T(P, dev)
-        if ops.tc:      # tile-contiguous copies for the persistent loop kernel (decoder_persist.cu)
-            self.W["WaP"] = torch.empty(4096, 1792, device=dev)
-            self.W["WdP"] = torch.empty(4096, 2560, device=dev)
-            L("t2v_pack_step_tiles", self.W["Wa"], 0, self.W["WaP"])
-            L("t2v_pack_step_tiles", self.W["Wd"], 1, self.W["WdP"])
+        engine.pack_step_weights(ops, self.W, dev)       # tile-contiguous copies for the persistent loop kernel
+        engine.pack_projection_lo(ops, P, self.W, dev)
         self.memory = memory
         self.pmem = torch.empty(self.B * self.Ti, 128, device=dev)
         ops.linear(memory, 512, ops.wr(P["decoder.attention_layer.memory_layer.linear_layer.weight"]), 512, self.pmem, 128,
                    self.B * self.Ti, 128, 512)
-        self.buf = engine.alloc_decoder_buffers(self.B, self.Ti, self.To, dev, save=False)
+        self.buf = engine.alloc_decoder_buffers(self.B, self.Ti, self.To, dev, save=False, op16=ops.op16)
         self.O = torch.zeros(self.To * self.B, 84, device=dev)
         self.S = _lib.T2VDecoderSeq()
         self.in_len = None if in_len is None else in_len.long().contiguous()
@@ -149,8 +146,12 @@ class DecoderSession(object):
             raise RuntimeError("decoder session exhausted (%d steps)" % self.To)
         B, t = self.B, self.t
         x = prenet_out.contiguous().float()
-        L("t2v_copy2d", x, 256, 1, engine._p(self.buf["XA"], t * B * 1792), 1792, B, 256, 0.0, self.ops.R)
+        L("t2v_copy2d", x, 256, 1, engine._p(self.buf["XA"], t * B * 1792), 1792, B, 256, 0.0, self.ops.RX)
         L("t2v_decoder_fwd_steps", self.S, t, t + 1)
+        if self.ops.op16:      # single steps run the per-step launches (fp32 rows): keep the 16-bit operand copies in step
+            for k, w in (("XA", 1792), ("XD", 2560)):
+                L("t2v_cvt16_2d", engine._p(self.buf[k], t * B * w), w, self.buf[k + "16"].data_ptr() + 2 * t * B * w, w,
+                  2 * B, w, self.ops.op16)
         o = engine._p(self.O, t * B * 84)
         XD = self.buf["XD"]
         self.ops.linear(engine._p(XD, (t + 1) * B * 2560 + 1536), 2560, self.W["Wpg"], 1536, o, 84, B, 81, 1024,
@@ -169,10 +170,11 @@ class DecoderSession(object):
         D.f.seed = seed
         P1 = torch.empty(2 * B, 256, device=self.dev)
         nfr = torch.full((B,), -1, device=self.dev, dtype=torch.int32)
-        Wp1 = self.ops.wr(P["decoder.prenet.layers.0.linear_layer.weight"])
-        Wp2 = self.ops.wr(P["decoder.prenet.layers.1.linear_layer.weight"])
+        # the prenet and the mel / gate projection inside the persistent kernel are FFMA mat-vecs: exact fp32 weights
+        Wp1 = P["decoder.prenet.layers.0.linear_layer.weight"]
+        Wp2 = P["decoder.prenet.layers.1.linear_layer.weight"]
         D.Wp1, D.Wp2 = Wp1.data_ptr(), Wp2.data_ptr()
-        D.Wpg, D.bpg = self.W["Wpg"].data_ptr(), self.W["bpg"].data_ptr()
+        D.Wpg, D.bpg = self.W.get("Wpg_x", self.W["Wpg"]).data_ptr(), self.W["bpg"].data_ptr()
         D.prenet_masks = _lib.ptr(prenet_masks)
         D.O, D.P1 = self.O.data_ptr(), P1.data_ptr()
         D.gate_threshold = gate_threshold

@@ -18,7 +18,8 @@ def test_library_exports_every_declared_symbol():
     loaded = _lib.load_library(lib_path)
     assert loaded.t2v_version() >= 100
     # struct layouts agree between the header and the ctypes mirror
-    assert ctypes.sizeof(_lib.T2VDecoderSeq) == 48 + 8 * 25 + (8 if ctypes.sizeof(ctypes.c_void_p) == 8 else 0) or True
+    for which, st in enumerate((_lib.T2VDecoderSeq, _lib.T2VDecoderBwd, _lib.T2VDecoderInfer)):
+        assert ctypes.sizeof(st) == loaded.t2v_sizeof_decoder_structs(which), st.__name__
 
 
 def test_argument_errors_are_reported_without_a_gpu():

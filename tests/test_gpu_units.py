@@ -104,7 +104,7 @@ def test_bn_act_dropout_matches_torch(L):
     rm = torch.zeros(C, device=dev); rv = torch.ones(C, device=dev); nbt = torch.zeros((), device=dev, dtype=torch.long)
     L("t2v_bn_finalize", sums[0], sums[1], float(B * T), C, 1e-5, 0.1, mean, invstd, rm, rv, nbt)
     out = torch.empty_like(Y)
-    L("t2v_bn_act_fwd", Y, out, B * Tp, C, Tp, 2, 2 + T, mean, invstd, gamma, beta, 2, mask, 0, 0, 0.5, T, 0)
+    L("t2v_bn_act_fwd", Y, out, None, B * Tp, C, Tp, 2, 2 + T, mean, invstd, gamma, beta, 2, mask, 0, 0, 0.5, T, 0)
     o = torch.empty(B, C, T, device=dev)
     L("t2v_padded_to_bct", out, None, o, B, C, T, None, 0.0)
     xr = x.cpu().double().requires_grad_(True)
@@ -437,3 +437,95 @@ def test_persistent_free_running_decode_matches_per_step_launches(L, B, Ti, n):
         assert err <= 5e-3, (k, err)
     assert torch.allclose(outs["1"]["align"].sum(-1), torch.ones(B, n, device=dev), atol=1e-5)
     assert torch.equal(outs["1"]["nfr"], outs["0"]["nfr"])
+
+
+@pytest.mark.parametrize("rows,n_a,n_b,a0,b0,splits", [(1000, 128, 128, 0, 0, 1), (4099, 512, 512, 2, 3, 7), (51200, 81, 1024, 0, 64, 37),
+                                                       (300, 84, 80, 0, 0, 2), (777, 256, 56, 1, 0, 3)])
+def test_gemm_tc_rowred_mn_major(L, rows, n_a, n_b, a0, b0, splits):
+    """t2v_gemm_tc_rowred: D = A[a0:a0+rows]^T B[b0:b0+rows] straight from the row-major operands (MN-major UMMA descriptors, no
+    transposed copies), split over the reduction with atomics.  Operands are pre-rounded to tf32, so only the fp32 summation
+    order differs from the fp64 reference: tolerance 1e-4 of the result's max."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(rows + n_a)
+    lda, ldb = n_a + 4, n_b + 8
+    A = torch.randn(rows + a0 + 5, lda, generator=g).to(dev)
+    Bm = torch.randn(rows + b0 + 5, ldb, generator=g).to(dev)
+    L("t2v_round_tf32", A, A.numel())
+    L("t2v_round_tf32", Bm, Bm.numel())
+    D = torch.zeros(n_a, n_b, device=dev)
+    L("t2v_gemm_tc_rowred", A, lda, n_a, a0, Bm, ldb, n_b, b0, D, n_b, rows, splits, 0, 1, 1.0)
+    torch.cuda.synchronize()
+    ref = (A[a0:a0 + rows, :n_a].double().t() @ Bm[b0:b0 + rows, :n_b].double()).float()
+    err = float((D - ref).abs().max() / ref.abs().max())
+    print("rowred rows=%d %dx%d splits=%d max-rel %.2e" % (rows, n_a, n_b, splits, err))
+    assert err < 1e-4, err
+    if splits == 1:      # non-atomic accumulate: D += the same product
+        L("t2v_gemm_tc_rowred", A, lda, n_a, a0, Bm, ldb, n_b, b0, D, n_b, rows, 1, 0, 2, 1.0)
+        torch.cuda.synchronize()
+        assert float((D - 2 * ref).abs().max() / ref.abs().max()) < 2e-4
+
+
+@pytest.mark.parametrize("mode,fmt", [(0, 1), (1, 1), (0, 2), (1, 2)])
+def test_pack_step_tiles16(L, mode, fmt):
+    """16-bit re-tiling of the decoder-step weights for the fp16 / bf16 persistent loop: [cluster][rank][chunk][gate*32+unit][64 k],
+    values = round-to-nearest conversions of the fp32 matrix."""
+    dev = torch.device("cuda")
+    K = 1792 if mode == 0 else 2560
+    g = torch.Generator().manual_seed(mode)
+    W = (torch.randn(4096, K, generator=g) * 0.05).to(dev)
+    nch = 7 if mode == 0 else 10
+
+    def kofs(j, r):
+        if mode == 0:
+            return 64 * r if j < 1 else (768 + 256 * r + 64 * (j - 1) if j < 5 else 256 + 128 * r + 64 * (j - 5))
+        return 256 * r + 64 * j if j < 4 else (1024 + 128 * r + 64 * (j - 4) if j < 6 else 1536 + 256 * r + 64 * (j - 6))
+    out = torch.empty(4096 * K, device=dev, dtype=torch.int16)
+    L("t2v_pack_step_tiles16", W, mode, out, fmt)
+    torch.cuda.synchronize()
+    dt = torch.float16 if fmt == 1 else torch.bfloat16
+    got = out.view(dt).view(32, 4, nch, 128, 64)
+    rows = torch.arange(128, device=dev)
+    for c in (0, 9, 31):
+        src_rows = (rows // 32) * 1024 + 32 * c + (rows % 32)
+        for r in range(4):
+            for j in range(nch):
+                ref = W[src_rows][:, kofs(j, r):kofs(j, r) + 64].to(dt)
+                assert torch.equal(got[c, r, j], ref), (mode, fmt, c, r, j)
+
+
+@pytest.mark.parametrize("B,Ti,To,training", [(5, 23, 12, True), (64, 120, 24, True), (16, 128, 9, False)])
+def test_persistent_loop_16bit_operands_match_tf32_loop(L, B, Ti, To, training):
+    """The fp16-operand instantiation of the persistent forward loop (kind::f16 MMAs over 16-bit copies of the weights and of
+    XA / XD) against the tf32 instantiation on the same inputs and the same counter RNG.  fp16 and tf32 share the 11-bit
+    significand, so the operand values are identical wherever |x| >= 6.1e-5 and the outputs agree to accumulation-order noise
+    (tolerance 5e-4 of each buffer's max; 1.5e-3 = one ulp for XA / XD themselves); bf16 is held to 2e-2."""
+    from oracle import port
+    from t2v import engine
+    dev = torch.device("cuda")
+    P = {k: v.to(dev) for k, v in port.init_params(1234).items()}
+    g = torch.Generator().manual_seed(B * 1000 + Ti)
+    memory = (torch.randn(B, Ti, 512, generator=g) * 0.5).to(dev)
+    mel = (torch.randn(B, 80, To, generator=g) * 2 - 5).to(dev)
+    in_len = torch.randint(max(1, Ti // 2), Ti + 1, (B,), generator=g).sort(descending=True)[0]
+    in_len[0] = Ti
+    in_len = in_len.to(dev)
+    outs = {}
+    for prec in ("tf32", "fp16", "bf16"):
+        ops = engine.Ops(prec)
+        O, align, ctx = engine.decoder_forward(ops, P, memory, mel, in_len, training, None, None, 77, -float("inf"), dev)
+        torch.cuda.synchronize()
+        buf = ctx["buf"]
+        outs[prec] = dict(O=O.clone(), align=align.clone(), **{k: buf[k].clone() for k in ("XA", "XD", "CA", "CD", "GA", "GD", "HCLO")})
+        if prec != "tf32":      # the 16-bit copies are the fp32 rows on the 16-bit grid
+            dt = torch.float16 if prec == "fp16" else torch.bfloat16
+            for k in ("XA", "XD"):
+                assert torch.equal(buf[k + "16"].view(dt)[:To * B].float(), buf[k][:To * B]), k
+    for prec, tol in (("fp16", 5e-4), ("bf16", 2e-2)):
+        for k in outs["tf32"]:
+            a, b = outs[prec][k], outs["tf32"][k]
+            assert torch.isfinite(a).all(), k
+            if k == "HCLO":
+                continue
+            err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+            print("%s vs tf32 loop %-6s max-rel %.3e" % (prec, k, err))
+            assert err <= (max(tol, 1.5e-3) if k in ("XA", "XD") else tol), (prec, k, err)
