@@ -1,5 +1,5 @@
 """Scratch: in-kernel time stamps (SM clocks) of a few mid-sequence steps of the persistent decoder loop
-(T2V_PERSIST_TRACE, decoder_persist.cu) + event-timed us/step of the loop alone.  usage: trace_persist.py [B Ti To]"""
+(T2V_PERSIST_TRACE, decoder_persist.cu) + event-timed us/step of the loop alone.  usage: trace_persist.py [fp16|bf16|tf32] [B Ti To]"""
 import os, sys
 R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tacotron2-vae_b200"))
@@ -8,10 +8,12 @@ from oracle import port
 from t2v import engine
 from t2v._lib import call as L
 
-B, Ti, To = (int(x) for x in sys.argv[1:4]) if len(sys.argv) > 3 else (64, 120, 400)
+PREC = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].isdigit() else "fp16"
+_a = [x for x in sys.argv[1:] if x.isdigit()]
+B, Ti, To = (int(x) for x in _a[:3]) if len(_a) >= 3 else (64, 120, 400)
 dev = torch.device("cuda")
 P = {k: v.to(dev) for k, v in port.init_params(1234).items()}
-ops = engine.Ops("tf32")
+ops = engine.Ops(PREC)
 mem = torch.randn(B, Ti, 512, device=dev) * 0.5
 mel = torch.randn(B, 80, To, device=dev) * 2 - 5
 in_len = torch.full((B,), Ti, device=dev, dtype=torch.long)

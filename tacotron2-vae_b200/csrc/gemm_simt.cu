@@ -7,8 +7,10 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8;   // 256 threads, 8x8 outputs each
-
+constexpr int BK = 16;
+// 256 threads; tile BM x BN with TM x TN outputs per thread: 128x128 (8x8) for wide outputs, 128x64 (8x4) and 256x32 (8x4) for the
+// narrow ones (reference-encoder convolutions with 32 / 64 filters, VAE head): no FMAs wasted on columns that do not exist
+template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, long long a_rs, long long a_cs, const float* __restrict__ B,
                  long long b_rs, long long b_cs, float* __restrict__ C, long long c_rs, int M, int N, int K,
@@ -21,7 +23,9 @@ gemm_simt_kernel(const float* __restrict__ A, long long a_rs, long long a_cs, co
   C += (long long)blockIdx.z * c_bs;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;   // thread computes rows ty*8.., cols tx*8..
+  constexpr int NTX = BN / TN;
+  static_assert((BM / TM) * NTX == 256, "tile shape");
+  const int tx = tid % NTX, ty = tid / NTX;   // thread computes rows ty*TM.., cols tx*TN..
   float acc[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
@@ -91,10 +95,18 @@ T2V_API int t2v_gemm_f32(const float* A, long long a_rs, long long a_cs, const f
                          int batch, long long a_bs, long long b_bs, long long c_bs, cudaStream_t stream) {
   T2V_ARG_CHECK(A && B && C, "null operand");
   T2V_ARG_CHECK(M > 0 && N > 0 && K > 0 && batch >= 1 && batch <= 65535, "shape");
+  const int BM = (N <= 32) ? 256 : 128, BN = (N <= 32) ? 32 : (N <= 64 ? 64 : 128);
   dim3 grid(t2v_ceil_div(N, BN), t2v_ceil_div(M, BM), batch);
   T2V_ARG_CHECK(grid.y <= 65535, "M too large for this launch geometry");
-  gemm_simt_kernel<<<grid, 256, 0, stream>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, c_rs, M, N, K, alpha, beta, bias, a_bs,
-                                             b_bs, c_bs);
+  if (BN == 32)
+    gemm_simt_kernel<256, 32, 8, 4><<<grid, 256, 0, stream>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, c_rs, M, N, K, alpha, beta, bias,
+                                                             a_bs, b_bs, c_bs);
+  else if (BN == 64)
+    gemm_simt_kernel<128, 64, 8, 4><<<grid, 256, 0, stream>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, c_rs, M, N, K, alpha, beta, bias,
+                                                             a_bs, b_bs, c_bs);
+  else
+    gemm_simt_kernel<128, 128, 8, 8><<<grid, 256, 0, stream>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, c_rs, M, N, K, alpha, beta, bias,
+                                                              a_bs, b_bs, c_bs);
   T2V_COUNT_LAUNCH();
   T2V_LAUNCH_CHECK();
   return 0;

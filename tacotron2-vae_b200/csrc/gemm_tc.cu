@@ -282,17 +282,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Row-reduction GEMM with MN-major operands:  D[i, j] (+)= alpha * sum_r A[a_row0 + r, m0 + i] * B[b_row0 + r, n0 + j].
 // Both operands are read in their natural row-major layout (rows = the reduction index), so the weight-gradient GEMMs
 // dW = dY^T X (reference: autograd of nn.Linear / Conv1d, model.py:91-148) need no transposed copies.  A TMA box is
-// {32 floats of MN (128 B), BKR reduction rows} and lands as BKR swizzled 128-byte rows = the canonical UMMA MN-major
-// SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with LBO = one box and SBO = 1024 B; one tf32
-// MMA consumes 8 reduction rows (one 1024-byte swizzle atom per MN group), so the K advance is +1024 B.
+// {32 floats of MN (128 B), BKR reduction rows} and lands as BKR 128-byte rows.  For 4-byte (tf32) MN-major operands the tensor core
+// accepts exactly one shared-memory layout: 128-byte swizzle with a 32-BYTE atom (UMMA layout type 1, "SWIZZLE_128B_BASE32B";
+// TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units, i.e. 4 reduction
+// rows x 128 B per 512-byte swizzle atom, LBO = next group of 32 MN elements (= one TMA box), SBO = next group of 4 rows = 512 B.
+// One tf32 MMA consumes 8 reduction rows (two atoms), so the K advance is +1024 B.  The plain SWIZZLE_128B layout with the MN-major
+// bits set is silently computed as zeros by the hardware (profiles/r02_mn_major_probe.txt, tools/mn_probe.cu).
 constexpr int BKR = 32;                      // reduction rows per stage
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((BKR * 128) >> 4) << 16;   // LBO: next group of 32 MN elements = next box
-  d |= (uint64_t)(1024 >> 4) << 32;          // SBO: next group of 8 reduction rows
+  d |= (uint64_t)(512 >> 4) << 32;           // SBO: next group of 4 reduction rows
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  d |= (uint64_t)1 << 61;                    // SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -519,7 +522,7 @@ int encode_mn(CUtensorMap* map, const void* base, long long cols, long long rows
   cuuint32_t box[2] = {32u, (cuuint32_t)BKR};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     t2v_set_error("cuTensorMapEncodeTiled (MN-major) failed with CUresult %d (cols=%lld rows=%lld ld=%lld)", (int)r, cols, rows, ld);

@@ -32,9 +32,14 @@ def apply_gradient_allreduce(module):
     def hook(*unused):
         Variable._execution_engine.queue_callback(allreduce_params)
 
-    for p in module.parameters():
-        if p.requires_grad:
-            p.register_hook(hook)
+    if hasattr(module, "_t2v_post_backward") or type(module).__name__ == "Tacotron2":
+        # the B200 engine writes the gradients into the flat buffer itself and queues this callback from its backward
+        # (no per-parameter autograd hooks: autograd never sees per-parameter gradients on that path)
+        module._t2v_post_backward = list(getattr(module, "_t2v_post_backward", ())) + [allreduce_params]
+    else:
+        for p in module.parameters():
+            if p.requires_grad:
+                p.register_hook(hook)
 
     def set_needs_reduction(self, inp, out):
         self.needs_reduction = True

@@ -36,7 +36,8 @@ class Tacotron2Logger(SummaryWriter):
         for tag, value in model.named_parameters():
             self.add_histogram(tag.replace(".", "/"), value.detach().float().cpu().numpy(), iteration)
         try:
-            from plotting_utils import plot_alignment_to_numpy, plot_gate_outputs_to_numpy, plot_spectrogram_to_numpy
+            from plotting_utils import (plot_alignment_to_numpy, plot_gate_outputs_to_numpy, plot_scatter,
+                                        plot_spectrogram_to_numpy)
         except Exception:   # noqa: BLE001
             return
         mel_targets, gate_targets = y
@@ -46,3 +47,4 @@ class Tacotron2Logger(SummaryWriter):
         self.add_image("mel_predicted", plot_spectrogram_to_numpy(mel_outputs[idx].detach().cpu().numpy()), iteration)
         self.add_image("gate", plot_gate_outputs_to_numpy(gate_targets[idx].detach().cpu().numpy(),
                                                           torch.sigmoid(gate_outputs[idx]).detach().cpu().numpy()), iteration)
+        self.add_image("latent_dim", plot_scatter(mus, emotions), iteration)

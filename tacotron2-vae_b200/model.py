@@ -220,9 +220,35 @@ class _FunctionConfig(object):
     pass
 
 
+# dimensions the sm_100a kernels are specialised for (tile shapes, shared-memory carve-ups, register arrays): the reference's
+# defaults (hparams.py:52-104).  Anything else would make the kernels index out of bounds, so it is refused up front.
+_KERNEL_DIMS = dict(
+    n_mel_channels=80, symbols_embedding_dim=512, encoder_kernel_size=5, encoder_n_convolutions=3, encoder_embedding_dim=512,
+    E=512, ref_enc_filters=[32, 32, 64, 64, 128, 128], ref_enc_size=[3, 3], ref_enc_strides=[2, 2], ref_enc_pad=[1, 1],
+    ref_enc_gru_size=256, n_frames_per_step=1, decoder_rnn_dim=1024, prenet_dim=256, attention_rnn_dim=1024, attention_dim=128,
+    attention_location_n_filters=32, attention_location_kernel_size=31, postnet_embedding_dim=512, postnet_kernel_size=5,
+    postnet_n_convolutions=5)
+
+
+def check_hparams(hparams):
+    """raise a clear error for architectures the kernels are not built for (instead of corrupting memory)"""
+    bad = []
+    for k, want in _KERNEL_DIMS.items():
+        got = getattr(hparams, k)
+        got = list(got) if isinstance(got, (list, tuple)) else got
+        if got != want:
+            bad.append("%s=%r (kernels are built for %r)" % (k, got, want))
+    for k in ("p_attention_dropout", "p_decoder_dropout"):
+        if not 0.0 <= float(getattr(hparams, k)) < 1.0:
+            bad.append("%s=%r (must be in [0, 1))" % (k, getattr(hparams, k)))
+    if bad:
+        raise ValueError("hparams not supported by the t2v_b200 kernels: " + "; ".join(bad))
+
+
 class Tacotron2(nn.Module):
     def __init__(self, hparams):
         super().__init__()
+        check_hparams(hparams)
         self.mask_padding = hparams.mask_padding
         self.fp16_run = hparams.fp16_run
         self.n_mel_channels = hparams.n_mel_channels
@@ -239,7 +265,8 @@ class Tacotron2(nn.Module):
         ref = weakref.ref(self)
         for m in (self.transcript_embedding, self.encoder, self.decoder, self.decoder.prenet, self.postnet, self.vae_gst):
             object.__setattr__(m, "_root", ref)
-        self.precision = _infer.default_precision()      # "tf32" (tcgen05) or "fp32" (exact FFMA)
+        # "fp16" (default: fp16 operands in the decoder loops, tf32 elsewhere), "bf16", "tf32" (all tcgen05) or "fp32" (exact FFMA)
+        self.precision = _infer.default_precision()
         self._seed = int(getattr(hparams, "seed", 1234))
         self._step = 0
         self._rand = None                                 # explicit dropout masks / eps for parity tests
@@ -250,7 +277,10 @@ class Tacotron2(nn.Module):
     _DEAD = ("speaker_embedding.", "emotion_embedding.", "vae_gst.ref_encoder.convs.0.weight", "vae_gst.ref_encoder.convs.0.bias")
 
     def _ops(self):
-        return _engine.Ops(self.precision)
+        ops = _engine.Ops(self.precision)
+        ops.p_att = float(self.decoder.p_attention_dropout)
+        ops.p_dec = float(self.decoder.p_decoder_dropout)
+        return ops
 
     def _state(self):
         return _infer.state_tensors(self)
@@ -292,7 +322,20 @@ class Tacotron2(nn.Module):
         cfg.seed = self._next_seed()
         cfg.mask_padding = bool(self.mask_padding)
         cfg.mask_value = float(self.decoder.attention_layer.score_mask_value)
+        cfg.ops.p_att = float(self.decoder.p_attention_dropout)
+        cfg.ops.p_dec = float(self.decoder.p_decoder_dropout)
         cfg.graph_cache = self._graph_cache
+        # persistent flat gradient buffer (created on first use): the backward graph writes into it, `.grad`s are views of it
+        cfg.flat = None
+        if self.training and torch.is_grad_enabled():
+            if getattr(self, "_t2v_flat_grads", None) is None:
+                from t2v import optim as _optim
+                self._t2v_flat_grads = _optim.FlatGrads(self)
+            cfg.flat = self._t2v_flat_grads
+        cfg.need_grad = torch.is_grad_enabled() and any(v.requires_grad for _, v in named)
+        cfg.post_backward = list(getattr(self, "_t2v_post_backward", ()))
+        # user hooks on parameters only fire when autograd itself delivers the gradient: keep the autograd path for them
+        cfg.param_hooks = any(getattr(v, "_backward_hooks", None) for _, v in named)
         for k, v in named:
             if v.dtype != torch.float32 or not v.is_contiguous() or not v.is_cuda:
                 raise RuntimeError("parameter %s must be a contiguous fp32 CUDA tensor" % k)

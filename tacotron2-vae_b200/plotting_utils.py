@@ -37,3 +37,15 @@ def plot_gate_outputs_to_numpy(gate_targets, gate_outputs):
     ax.set_xlabel("Frames (Green target, Red predicted)")
     ax.set_ylabel("Gate State")
     return _to_numpy(fig)
+
+
+def plot_scatter(mus, y):
+    """first two latent means of the batch, one colour per emotion class (reference plotting_utils.py:63-83 -> "latent_dim")"""
+    colors, labels = ("r", "b", "g", "y"), ("neu", "sad", "ang", "hap")
+    mus = mus.detach().cpu().numpy()
+    cls = np.argmax(y.detach().cpu().numpy(), 1)
+    fig, ax = plt.subplots(figsize=(12, 12))
+    for i, (c, label) in enumerate(zip(colors, labels)):
+        ax.scatter(mus[cls == i, 0], mus[cls == i, 1], c=c, label=label, alpha=0.5)
+    ax.legend(loc="upper left")
+    return _to_numpy(fig)

@@ -7,6 +7,10 @@ from . import _lib, engine
 from ._lib import call as L
 
 
+_GRAPH_AFTER = int(__import__("os").environ.get("T2V_GRAPH_AFTER", "2"))     # capture a shape on its n-th sighting
+_GRAPH_MAX = int(__import__("os").environ.get("T2V_GRAPH_MAX", "3"))         # graphs kept resident (LRU)
+
+
 class GraphedStep(object):
     """One (shape, mode) instance of the train step captured as two CUDA graphs (forward, backward).
 
@@ -26,9 +30,11 @@ class GraphedStep(object):
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
+        self.with_backward = bool(getattr(cfg, "need_grad", True))
         with torch.cuda.stream(side):                                # eager warm-up: lazy inits (smem attributes, TMA entry point)
             outs, c = engine.forward_train(cfg.ops, P, *self.s_in, **kw)
-            engine.backward_train(cfg.ops, P, c, *[torch.zeros_like(outs[i]) for i in (0, 1, 2, 4, 5)])
+            if self.with_backward:
+                engine.backward_train(cfg.ops, P, c, *[torch.zeros_like(outs[i]) for i in (0, 1, 2, 4, 5)])
             del outs, c
         cur.wait_stream(side)
         torch.cuda.synchronize()
@@ -37,6 +43,13 @@ class GraphedStep(object):
         with torch.cuda.graph(self.g_fwd, capture_error_mode="thread_local"):
             self.outs, self.c = engine.forward_train(cfg.ops, P, *self.s_in, **kw)
         self.n_fwd = _lib.launch_count() - n0
+        self.direct = False
+        if not self.with_backward:           # eval / no_grad forward (validate(), train.py:122-147): nothing to differentiate
+            self.c = None
+            for k, v in cfg.buffers.items():
+                v.copy_(snap[k])
+            torch.cuda.synchronize()
+            return
         self.s_dout = [torch.zeros_like(self.outs[i]) for i in (0, 1, 2, 4, 5)]
         self.g_bwd = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool(), capture_error_mode="thread_local"):
@@ -44,7 +57,17 @@ class GraphedStep(object):
             self.live = [n for n in self.names if n in grads]
             self.sizes = [grads[n].numel() for n in self.live]
             self.shapes = [grads[n].shape for n in self.live]
-            self.flat = torch.cat([grads[n].reshape(-1) for n in self.live])
+            # the gradients land in ONE flat buffer inside the graph.  When the model owns a persistent flat gradient buffer with
+            # the same layout (t2v.optim.FlatGrads: every `.grad` is a view of it, the all-reduce and the fused clip+Adam step
+            # run on it) the graph writes straight into that buffer: no clone, no per-parameter copies afterwards.
+            fg = getattr(cfg, "flat", None)
+            self.direct = fg is not None and [k for k, _ in fg.named] == self.live and fg.numel == sum(self.sizes)
+            self.fg = fg if self.direct else None
+            if self.direct:
+                self.flat = fg.buffer
+                torch.cat([grads[n].reshape(-1) for n in self.live], out=self.flat)
+            else:
+                self.flat = torch.cat([grads[n].reshape(-1) for n in self.live])
             del grads
         self.n_bwd = _lib.launch_count() - n0 - self.n_fwd
         for k, v in cfg.buffers.items():
@@ -58,6 +81,23 @@ class GraphedStep(object):
         self.g_fwd.replay()
         _lib.add_launch_count(self.n_fwd)
         return [o.clone() for o in self.outs]
+
+    def backward_direct(self, douts):
+        """replay the backward graph into the model's flat gradient buffer and make every `.grad` the view of its slice
+        (accumulating onto gradients that are already there, like autograd would)"""
+        for s, t in zip(self.s_dout, douts):
+            s.copy_(t, non_blocking=True)
+        fg = self.fg
+        prev = None
+        if any(p.grad is not None for _, p in fg.named):
+            fg.adopt_grads()                     # whatever the caller accumulated so far now sits in the flat buffer
+            prev = fg.buffer.clone()
+        self.g_bwd.replay()
+        _lib.add_launch_count(self.n_bwd)
+        if prev is not None:
+            fg.buffer.add_(prev)
+        for (_, p), v in zip(fg.named, fg.views):
+            p.grad = v
 
     def backward(self, douts):
         for s, t in zip(self.s_dout, douts):
@@ -81,14 +121,29 @@ class Tacotron2Function(torch.autograd.Function):
         P = dict(zip(cfg.names, params))
         P.update(cfg.buffers)
         ctx.gs = None
+        gs = None
         if cfg.graph_cache is not None and cfg.rand is None:
-            key = (tuple(text.shape), tuple(mel_tgt.shape), cfg.training, cfg.ops.precision, cfg.mask_padding, cfg.mask_value,
-                   params[0].data_ptr(), params[-1].data_ptr())
+            # A graph is tied to one exact (B, Ti, To): TextMelCollate pads every batch to its own maxima (data_utils.py:82-137) and
+            # padding further would change the results (BN statistics and the MSE denominators include padded positions, quirk
+            # Q4), so shapes are never bucketed.  A shape is captured only once it REPEATS (fixed-shape training / the bench /
+            # bucketed samplers); first sightings run the eager launch sequence, so variable-length data costs nothing extra.
+            need_grad = bool(getattr(cfg, "need_grad", True))
+            key = (tuple(text.shape), tuple(mel_tgt.shape), cfg.training, need_grad, cfg.ops.precision, cfg.mask_padding,
+                   cfg.mask_value, cfg.ops.p_att, cfg.ops.p_dec, params[0].data_ptr(), params[-1].data_ptr())
             gs = cfg.graph_cache.get(key)
             if gs is None:
-                if len(cfg.graph_cache) >= 2:                        # keep at most two shapes resident (GBs of workspace each)
-                    cfg.graph_cache.pop(next(iter(cfg.graph_cache)))
-                gs = cfg.graph_cache[key] = GraphedStep(cfg, P, text, in_len, mel_tgt, out_len)
+                seen = cfg.graph_cache.setdefault("_seen", {})
+                seen[key] = seen.get(key, 0) + 1
+                if len(seen) > 64:
+                    seen.pop(next(iter(seen)))
+                if seen[key] >= _GRAPH_AFTER:
+                    live = [k for k in cfg.graph_cache if k != "_seen"]
+                    if len(live) >= _GRAPH_MAX:                      # bounded: every entry pins GBs of workspace
+                        cfg.graph_cache.pop(live[0])
+                    gs = cfg.graph_cache[key] = GraphedStep(cfg, P, text, in_len, mel_tgt, out_len)
+            else:
+                cfg.graph_cache[key] = cfg.graph_cache.pop(key)      # LRU order
+        if gs is not None:
             outs = gs.forward(text, in_len, mel_tgt, out_len, cfg.seed)
             ctx.gs = gs
             ctx.cfg, ctx.c, ctx.P = cfg, None, None
@@ -105,6 +160,14 @@ class Tacotron2Function(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dmel, dpost, dgate, dalign, dmu, dlogvar, dz):
         cfg = ctx.cfg
+        # module-level "after backward" callbacks (distributed.apply_gradient_allreduce): run when the whole backward is done
+        for cb in getattr(cfg, "post_backward", ()):
+            torch.autograd.Variable._execution_engine.queue_callback(cb)
+        if ctx.gs is not None and ctx.gs.direct and not cfg.param_hooks:
+            # fast path: gradients go straight into the flat buffer the optimizer / all-reduce work on; autograd sees no
+            # parameter gradients (None), so the module-level callbacks stand in for per-parameter hooks
+            ctx.gs.backward_direct((dmel, dpost, dgate, dmu, dlogvar))
+            return tuple([None] * (5 + len(cfg.names)))
         if ctx.gs is not None:
             grads = ctx.gs.backward((dmel, dpost, dgate, dmu, dlogvar))
         else:
@@ -130,7 +193,11 @@ class VaeLossFunction(torch.autograd.Function):
           args[5].numel(), float(kl_weight), acc, out)
         ctx.save_for_backward(*args)
         ctx.kl_weight = float(kl_weight)
-        return out[0], out[1], out[2]
+        total, recon, kl = out[0], out[1], out[2]
+        # the reference only ever backpropagates the total (train.py:215-222); recon / kl are reporting values.  Marking them
+        # non-differentiable makes a backward through them fail loudly instead of silently returning zero gradients.
+        ctx.mark_non_differentiable(recon, kl)
+        return total, recon, kl
 
     @staticmethod
     def backward(ctx, g_total, g_recon, g_kl):

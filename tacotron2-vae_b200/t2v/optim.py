@@ -56,16 +56,66 @@ class FusedAdamClip(object):
         self.norm = torch.zeros(1, device=dev)
         self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.step_count = 0
+        self._init_groups(module)
 
-    def zero_grad(self):
-        self.flat.buffer.zero_()
+    def zero_grad(self, set_to_none=True):
+        """like nn.Module.zero_grad(set_to_none=True): the next backward writes the flat buffer instead of accumulating"""
+        for _, p in self.flat.named:
+            p.grad = None
+        if not set_to_none:
+            self.flat.buffer.zero_()
+
+    # ---- torch.optim.Optimizer-compatible surface (train.py:92-119, 171-172, 226-229: param_groups lr updates, checkpoints)
+    @property
+    def param_groups(self):
+        return self._groups
+
+    def _init_groups(self, module):
+        allp = list(module.parameters())
+        self._groups = [dict(params=allp, lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.wd,
+                             amsgrad=False, maximize=False)]
+        pos = {id(p): i for i, p in enumerate(allp)}
+        self._index = [pos[id(p)] for _, p in self.flat.named]      # position of each flat slice in module.parameters()
+
+    def state_dict(self):
+        """torch.optim.Adam layout: state[i] = {step, exp_avg, exp_avg_sq} for every parameter that has been stepped
+        (the reference's dead parameters, quirk Q6, have no entry -- exactly like torch, which skips grad=None)"""
+        state = {}
+        if self.step_count > 0:
+            off = 0
+            for i, (_, p) in zip(self._index, self.flat.named):
+                n = p.numel()
+                state[i] = dict(step=torch.tensor(float(self.step_count)), exp_avg=self.m[off:off + n].view_as(p).clone(),
+                                exp_avg_sq=self.v[off:off + n].view_as(p).clone())
+                off += n
+        g = dict(self._groups[0])
+        g["params"] = list(range(len(self._groups[0]["params"])))
+        return dict(state=state, param_groups=[g])
+
+    def load_state_dict(self, sd):
+        g = sd["param_groups"][0]
+        self._groups[0].update({k: v for k, v in g.items() if k != "params"})
+        self.m.zero_()
+        self.v.zero_()
+        steps = []
+        off = 0
+        for i, (_, p) in zip(self._index, self.flat.named):
+            n = p.numel()
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is not None:
+                self.m[off:off + n].view_as(p).copy_(st["exp_avg"])
+                self.v[off:off + n].view_as(p).copy_(st["exp_avg_sq"])
+                steps.append(int(float(st["step"])))
+            off += n
+        self.step_count = max(steps) if steps else 0
 
     def step(self, grad_scale=1.0):
         """returns the (device) total gradient norm before clipping, like clip_grad_norm_"""
         self.flat.adopt_grads()
         self.step_count += 1
+        g = self._groups[0]
         L("t2v_grad_sumsq", self.flat.buffer, self.flat.numel, float(grad_scale), self.sumsq)
         L("t2v_adam_clip_step", self.params, self.flat.buffer, self.m, self.v, self.flat.numel, self.sumsq, float(grad_scale),
-          float(self.max_norm), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
-          self.step_count, self.norm)
+          float(self.max_norm), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+          float(g["weight_decay"]), self.step_count, self.norm)
         return self.norm
