@@ -40,6 +40,15 @@ int t2v_gemm_tc(const void* A, long long lda, long long a_rows, long long a_inne
                 int taps, int a_tap_rowshift, int b_tap_stride, int a_k0, int b_k0, int esize, int splits,
                 long long split_stride, int epi_atomic, float alpha, int bn_hint, cudaStream_t stream);
 
+/* split (error-compensated) product for fp32 operands given as hi + lo parts on the tf32 grid (x = hi + lo):
+   D = alpha * (A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T) (+ bias) through one accumulator -- fp32-level accuracy from tf32 tensor-core
+   products at 3x the K loop.  Used where tf32 rounding dominated the error of the outputs: the deferred mel / gate projection
+   (model.py:383-388) and the Postnet forward (model.py:105-148). */
+int t2v_gemm_tc_split3(const float* A_hi, const float* A_lo, long long lda, long long a_rows, long long a_inner, const float* B_hi,
+                       const float* B_lo, long long ldb, long long b_rows, long long b_inner, float* D, long long ldd,
+                       const float* bias, int M, int N, int k_sub, int taps, int a_tap_rowshift, int b_tap_stride, int a_k0,
+                       int b_k0, float alpha, int bn_hint, cudaStream_t stream);
+
 /* row-reduction form with MN-major operands (no transposed copies): D[n_a,n_b] (+)= alpha * sum_{r<rows} A[a_row0+r, i] * B[b_row0+r, j];
    the weight-gradient GEMMs dW = dY^T X of every nn.Linear / Conv1d (autograd of model.py:91-148).  epi: 0 store, 1 atomicAdd,
    2 non-atomic += (splits == 1); splits > 1 needs epi 1 (D pre-initialised). */
@@ -138,6 +147,15 @@ int t2v_bilstm_step_bwd(const float* dgn0, const float* dgn1, long long dg_bs, c
                         const float* dout0, const float* dout1, long long dout_bs, float* dc0, float* dc1, const float* gs0,
                         const float* gs1, const float* cs0, const float* cs1, const float* cp0, const float* cp1, float* dgo0,
                         float* dgo1, const long long* lens, int t0, int t1, int B, int H, cudaStream_t stream);
+/* whole-sequence persistent versions (ONE launch for all Ti steps of both directions, B <= 64): gx0 / gx1 [B*(Ti+4), 4H] hoisted input
+   projections on the padded rows, seq [B*(Ti+4), 2H] output rows, gates [2,Ti,B,4H], cells [2,Ti+2,B,H] (zero-initialised), hbuf scratch
+   [2,2,B,H], counters 64 x u32 (zeroed by the call); backward: dout [B,Ti,2H] -> dg0 / dg1 [B*(Ti+4), 4H] */
+int t2v_bilstm_seq_fwd(const float* gx0, const float* gx1, const float* whh0, const float* whh1, const float* bhh0,
+                       const float* bhh1, float* seq, float* gates, float* cells, float* hbuf, unsigned int* counters,
+                       const long long* lens, int B, int H, int Ti, cudaStream_t stream);
+int t2v_bilstm_seq_bwd(const float* whhT0, const float* whhT1, const float* dout, const float* gates, const float* cells,
+                       float* dg0, float* dg1, unsigned int* counters, const long long* lens, int B, int H, int Ti,
+                       cudaStream_t stream);
 /* same, with dh1 given as `dh1_parts` split-K partial buffers (stride dh1_pstride) that are summed on the fly */
 int t2v_lstm_pointwise_bwd_parts(const float* dh1, long long dh1_rs, int dh1_parts, long long dh1_pstride, const float* dh2,
                                  long long dh2_rs, const float* dh3, long long dh3_rs, float* dc, const float* gates_save,
@@ -231,15 +249,16 @@ typedef struct T2VDecoderSeq {
   float *ebuf;                   /* [B,Ti,129] scratch: [B,Ti] energies, then [B,Ti,128] location term + processed memory */
   const float *WaP, *WdP;        /* optional (NULL = unused): Wa / Wd re-tiled by t2v_pack_step_tiles (modes 0 / 1) for the persistent
                                     loop kernel: every TMA box is one contiguous 16 KB block instead of 128 strided 128-byte rows */
-  float *HCLO;                   /* optional [To,B,1536]: low-order residual of [h_dec_t | ctx_t] after rounding onto the operand grid
-                                    (x = x_hi + x_lo): lets the deferred mel / gate projection run as a split (error-compensated)
-                                    tensor-core GEMM.  Written by the persistent loop kernel only; zero-initialise */
+  float *HCHI, *HCLO;            /* optional [To,B,1536] each: [h_dec_t | ctx_t] on the operand grid (hi) and the low-order residual
+                                    (x = x_hi + x_lo, both on the tf32 grid): the operands of the deferred mel / gate projection as ONE
+                                    split (error-compensated) tensor-core GEMM.  Written by the persistent loop kernel only */
   int op16;                      /* 0: fp32 storage / tf32 math in the persistent loops; 1: fp16, 2: bf16 operand copies (kind::f16) */
   void *XA16, *XD16;             /* op16: 16-bit copies of XA / XD (same shapes), the tensor-core operands; zero-initialise */
   const void *WaP16, *WdP16;     /* op16: 16-bit re-tiled weights (t2v_pack_step_tiles16 modes 0 / 1) */
 } T2VDecoderSeq;
 int t2v_sizeof_decoder_structs(int which);   /* sizeof(T2VDecoderSeq / T2VDecoderBwd / T2VDecoderInfer) for which = 0 / 1 / 2: binding check */
 int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);
+int t2v_decoder_last_path(void);   /* 1: the last t2v_decoder_fwd_steps of this thread enqueued the persistent kernel (HCHI / HCLO valid) */
 /* re-tile a decoder-step weight matrix into the order the persistent loop kernels stream it (same number of floats):
    mode 0: Wa [4096,1792] -> WaP ; 1: Wd [4096,2560] -> WdP ; 2: WaT [1792,4096] -> WaTP ; 3: WdT [2560,4096] -> WdTP */
 int t2v_pack_step_tiles(const float* W, int mode, float* out, cudaStream_t stream);

@@ -35,6 +35,10 @@ for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
         name = e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0]
         agg[name][0] += 1; agg[name][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+if os.environ.get("T2V_PROFILE_LIST"):      # per-launch durations (us) of the kernels whose name contains the given substring
+    pat = os.environ["T2V_PROFILE_LIST"]
+    evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and pat in e.name), key=lambda e: e.time_range.start)
+    print("per-launch us of *%s*: %s" % (pat, " ".join("%.0f" % (e.device_time if hasattr(e, "device_time") else e.cuda_time) for e in evs[:len(evs) // N])))
 tot = sum(v[1] for v in agg.values())
 lines = ["| kernel | launches/step | total us/step | avg us | share |", "|---|---:|---:|---:|---:|"]
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:

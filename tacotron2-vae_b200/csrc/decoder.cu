@@ -237,12 +237,19 @@ __global__ void stop_flags_kernel(const float* __restrict__ O, long long ld, int
 
 }  // namespace
 
+// 1 when the last t2v_decoder_fwd_steps call of this thread enqueued the persistent loop kernel (which also emits HCHI / HCLO),
+// 0 when it issued the per-step launches
+static thread_local int g_last_path = 0;
+T2V_API int t2v_decoder_last_path(void) { return g_last_path; }
+
 T2V_API int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream) {
   T2V_ARG_CHECK(s && s->B > 0 && s->Ti > 0 && s->To > 0, "shape");
   T2V_ARG_CHECK(t_begin >= 0 && t_end <= s->To && t_begin <= t_end, "step range");
+  g_last_path = 0;
   if (!getenv("T2V_STEP_PROFILE")) {
     // the whole loop as one persistent kernel (decoder_persist.cu) when the problem fits it; 1 = not applicable
     const int r = t2v_decoder_fwd_persist(s, t_begin, t_end, stream);
+    if (r == 0) g_last_path = 1;
     if (r != 1) return r;
   }
   FwdPlans P;

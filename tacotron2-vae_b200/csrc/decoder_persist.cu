@@ -58,9 +58,34 @@ constexpr int OFF_CPAD = OFF_WPAD + PADW * 4;
 constexpr int OFF_E = OFF_CPAD + PADW * 4;                          // [128] energies
 constexpr int OFF_Q = OFF_E + 128 * 4;                              // [2][128]
 constexpr int OFF_BARS = OFF_Q + 256 * 4;
-constexpr int N_BARS = 2 * NS + 8;
+constexpr int N_BARS = 2 * NS + 9;
 constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+// 16-bit operands of the in-kernel query projection (op16 only): query_layer columns of this cluster's 32 units [128 a][32 u] and
+// this CTA's h_att rows [16 b][32 u], K-major rows of 64 bytes in the SWIZZLE_64B layout (written by ordinary threads)
+constexpr int OFF_WQ16 = (OFF_TMEM + 16 + 1023) / 1024 * 1024;
+constexpr int OFF_HQ16 = OFF_WQ16 + 128 * 64;
+constexpr int SMEM_BYTES = OFF_HQ16 + 16 * 64 + 1024;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+// element index of (row r, k) in a [rows][32] 16-bit tile stored K-major with the 64-byte swizzle: the 16-byte chunk c = k / 8 of
+// row r sits at chunk c ^ ((r >> 1) & 3)   (verified by profiles/tools/sw64_probe.cu)
+__device__ __forceinline__ int swz64(int r, int k) { return r * 32 + ((((k >> 3) ^ (r >> 1)) & 3) << 3) + (k & 7); }
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;          // SBO: 8 rows of 64 bytes
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                   // SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 struct PersistParams {
   T2VDecoderSeq s;
@@ -147,6 +172,9 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   uint64_t* recv_full = acc_free + 2;     // [2]
   uint64_t* e_full = recv_full + 2;       // [1]
   uint64_t* s_full = e_full + 1;          // [1] processed-memory tile landed in S
+  uint64_t* q_full = s_full + 1;          // [1] op16: the query-projection MMA of this step has retired
+  uint16_t* wq16 = (uint16_t*)(smem + OFF_WQ16);
+  uint16_t* hq16 = (uint16_t*)(smem + OFF_HQ16);
   uint32_t* tmem_holder = (uint32_t*)(smem + OFF_TMEM);
 
   constexpr int ATT_CHUNKS = Chunks<OP>::ATT, DEC_CHUNKS = Chunks<OP>::DEC;     // (shadow the fp32 counts of the file scope)
@@ -183,11 +211,12 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     }
     mbar_init(e_full, 1);
     mbar_init(s_full, 1);
+    mbar_init(q_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
-                 "r"(128u) : "memory");
+                 "r"(OP ? 256u : 128u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -371,6 +400,12 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       const float4 w4 = *reinterpret_cast<const float4*>(s.Wq + (long long)etid * H + 32 * cid + i);
       wq[i] = w4.x; wq[i + 1] = w4.y; wq[i + 2] = w4.z; wq[i + 3] = w4.w;
     }
+    if (OP) {      // op16: the same weights as the A operand of the per-step query MMA (M = 128 attention dims, K = 32 units)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) wq16[swz64(etid, i)] = t2v_enc16(wq[i], opfmt);
+      fence_proxy_async();
+      named_bar(BAR_EPI, 128);
+    }
     float bias_a[4], bias_d[4], c_att[4], c_dec[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -388,6 +423,26 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
 
     auto epilogue = [&](auto which_c, const int ts, const unsigned idx) {
       constexpr int which = decltype(which_c)::value;      // compile-time: keeps the per-GEMM register arrays in registers
+      // dropout keep scales of this thread's four (unit, batch row) pairs: independent of the recurrence, computed while the
+      // accumulator is still being produced
+      const float pdrop = which ? p_dec : p_att;
+      const float kscale = 1.f / (1.f - pdrop);
+      const float* mk = s.drop_masks ? s.drop_masks + (long long)ts * 4 * B * H + (which ? 2LL * B * H : 0) : nullptr;
+      float kh4[4], kc4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int b = 16 * rank + blq + 4 * j;
+        kh4[j] = 1.f; kc4[j] = 1.f;
+        if (pdrop > 0.f && b < B) {
+          const uint64_t li = (uint64_t)b * H + jg;
+          if (mk) { kh4[j] = mk[li] * kscale; kc4[j] = mk[(long long)B * H + li] * kscale; }
+          else {
+            const uint64_t di = (uint64_t)ts * B * H + li;
+            kh4[j] = (t2v_uniform(seed, which ? SITE_DEC_H : SITE_ATT_H, di) >= pdrop ? 1.f : 0.f) * kscale;
+            kc4[j] = (t2v_uniform(seed, which ? SITE_DEC_C : SITE_ATT_C, di) >= pdrop ? 1.f : 0.f) * kscale;
+          }
+        }
+      }
       mbar_wait(&acc_full[which], idx & 1u);
       tc_fence_after();
       const unsigned tn = which ? idx + 1 : idx;       // trace row = the step during which this epilogue runs
@@ -435,12 +490,10 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       // ---- LSTM cell (model.py:357-364 / 375-381) on (unit u, batch rows blq + 4j)
       const float* bias = which ? bias_d : bias_a;
       float* cst = which ? c_dec : c_att;
-      const float pdrop = which ? p_dec : p_att;
-      const float kscale = 1.f / (1.f - pdrop);
       const long long r0 = (long long)ts * B, r1 = (long long)(ts + 1) * B;
-      const float* mk = s.drop_masks ? s.drop_masks + (long long)ts * 4 * B * H + (which ? 2LL * B * H : 0) : nullptr;
       float sv_i[4], sv_f[4], sv_g[4], sv_o[4], sv_c2[4];     // saved activations: written after the signal
       float sv_lo[4] = {0.f, 0.f, 0.f, 0.f};                  // h_dec - (h_dec on the operand grid): the split projection's low part
+      float sv_hi[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int bl = blq + 4 * j;
@@ -454,22 +507,14 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         const float ig = t2v_sigmoid_fast(g4[0]), fg = t2v_sigmoid_fast(g4[1]), gg = t2v_tanh(g4[2]), og = t2v_sigmoid_fast(g4[3]);
         const float c2 = fg * cst[j] + ig * gg;
         const float h2 = og * t2v_tanh(c2);
-        float kh = 1.f, kc = 1.f;
-        if (pdrop > 0.f && b < B) {
-          const uint64_t li = (uint64_t)b * H + jg;
-          if (mk) { kh = mk[li] * kscale; kc = mk[(long long)B * H + li] * kscale; }
-          else {
-            const uint64_t di = (uint64_t)ts * B * H + li;
-            kh = (t2v_uniform(seed, which ? SITE_DEC_H : SITE_ATT_H, di) >= pdrop ? 1.f : 0.f) * kscale;
-            kc = (t2v_uniform(seed, which ? SITE_DEC_C : SITE_ATT_C, di) >= pdrop ? 1.f : 0.f) * kscale;
-          }
-        }
+        const float kh = kh4[j], kc = kc4[j];
         const float hx = h2 * kh;               // exact h (after dropout); hd = its copy on the operand grid
         const float hd = t2v_rnd(hx, rnd);
         cst[j] = c2 * kc;
         sv_i[j] = ig; sv_f[j] = fg; sv_g[j] = gg; sv_o[j] = og; sv_c2[j] = c2;
         // (inference: the mel / gate projection inside the kernel takes the exact h_dec, like the reference's fp32 Linear)
         if (which == 0 || INFER) hq[bl * 32 + u] = which ? hx : hd;
+        if (OP && which == 0) hq16[swz64(bl, u)] = t2v_enc16(hx, opfmt);
         if (b < B) {       // only what other CTAs wait for goes out before the signal
           if (which == 0) {
             s.XA[(r1 + b) * XA_W + (PD + ED) + jg] = hd;       // h_att -> next step's recurrent input
@@ -483,11 +528,39 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
             s.XD[(r1 + b) * XD_W + (H + ED) + jg] = hd;        // h_dec -> next step's recurrent input
             if (OP) xd16[(r1 + b) * XD_W + (H + ED) + jg] = t2v_enc16(hx, opfmt);
             sv_lo[j] = hx - hd;
+            sv_hi[j] = hd;
           }
         }
       }
       if (etid == 0 && which == 0) TR(tn, 11);
-      if (which == 0) {
+      if (OP && which == 0) {
+        // ---- partial query projection over this cluster's 32 units for this CTA's 16 batch rows on the tensor core:
+        // D[128 a, 16 b] = Wq16[a][u] * hq16[b][u]  (two K=16 instructions) into TMEM columns 128..143; thread = attention dim a
+        fence_proxy_async();                  // the h rows were written with ordinary stores, the MMA reads them through the async proxy
+        tc_fence_before();
+        named_bar(BAR_EPI, 128);
+        tc_fence_after();
+        if (warp == 4 && elect_one()) {
+          const uint32_t fq = (opfmt == 2) ? 1u : 0u;
+          const uint32_t idq = (1u << 4) | (fq << 7) | (fq << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+          const uint64_t ad = make_kmajor_sw64_desc(smem_u32(wq16)), bd = make_kmajor_sw64_desc(smem_u32(hq16));
+          tc_mma_f16(tmem_base + 128u, ad, bd, idq, 0u);
+          tc_mma_f16(tmem_base + 128u, ad + 2, bd + 2, idq, 1u);
+          tc_commit(q_full);
+        }
+        __syncwarp();
+        mbar_wait(q_full, idx & 1u);
+        tc_fence_after();
+        uint32_t qv[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + 128u, qv);
+        float* qp = p.qpart + ((long long)((ts & 1) * NCLUSTER + cid) * B) * AD + etid;
+#pragma unroll
+        for (int bl = 0; bl < 16; ++bl) {
+          const int b = 16 * rank + bl;
+          if (b < B) qp[(long long)b * AD] = __uint_as_float(qv[bl]);
+        }
+        tc_fence_before();
+      } else if (which == 0) {
         // ---- partial query projection over this cluster's 32 units for this CTA's 16 batch rows: thread = attention dim a
         named_bar(BAR_EPI, 128);
         float* qp = p.qpart + ((long long)((ts & 1) * NCLUSTER + cid) * B) * AD + etid;
@@ -553,7 +626,10 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
               __stcs(gs, sv_i[j]); __stcs(gs + H, sv_f[j]); __stcs(gs + 2 * H, sv_g[j]); __stcs(gs + 3 * H, sv_o[j]);
             }
             if (CPs) __stcs(CPs + (r0 + b) * H + jg, sv_c2[j]);
-            if (which == 1 && s.HCLO) __stcs(s.HCLO + (r0 + b) * (H + ED) + jg, t2v_tf32(sv_lo[j]));
+            if (which == 1 && s.HCLO) {
+              __stcs(s.HCHI + (r0 + b) * (H + ED) + jg, sv_hi[j]);
+              __stcs(s.HCLO + (r0 + b) * (H + ED) + jg, t2v_tf32(sv_lo[j]));
+            }
           }
         }
       }
@@ -881,7 +957,10 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
             xd16[((long long)t * B + b) * XD_W + H + col] = c16;
             xa16[((long long)(t + 1) * B + b) * XA_W + PD + col] = c16;
           }
-          if (s.HCLO) __stcs(s.HCLO + ((long long)t * B + b) * (H + ED) + H + col, t2v_tf32(cx - c));
+          if (s.HCLO) {
+            __stcs(s.HCHI + ((long long)t * B + b) * (H + ED) + H + col, c);
+            __stcs(s.HCLO + ((long long)t * B + b) * (H + ED) + H + col, t2v_tf32(cx - c));
+          }
           if (INFER) ctx_s[atid] = cx;                                    // exact ctx for the in-kernel projection
         }
         if (INFER) {
@@ -942,7 +1021,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   __syncwarp();
   cluster_sync_all();            // no CTA of the cluster exits while a peer may still address its shared memory
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(OP ? 256u : 128u) : "memory");
   }
 }
 
@@ -1014,6 +1093,7 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
   if (!persist_enabled()) return 1;
   if (!s->use_tc || s->B > 64 || s->Ti > 2 * TH_MAX || s->Ti < 1 || t_end - t_begin < 2) return 1;
   if (!s->parts || !s->ebuf) return 1;
+  if ((s->HCHI != nullptr) != (s->HCLO != nullptr)) { t2v_set_error("HCHI and HCLO come as a pair"); return -1; }
   if (inf && (!inf->Wp1 || !inf->Wp2 || !inf->Wpg || !inf->bpg || !inf->O)) return 1;
   const int op = s->op16 ? 1 : 0;
   if (op && (!s->XA16 || !s->XD16 || !s->WaP16 || !s->WdP16 || s->op16 > 2)) {

@@ -120,7 +120,8 @@ constexpr int kBM = 128;
 
 template <int BN, int ESIZE, int STAGES, int BM = 128>
 __global__ void __launch_bounds__(192, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmTcParams p) {
   constexpr int BK = 128 / ESIZE;           // elements per 128-byte swizzle row
   constexpr int A_BYTES = BM * 128;
   constexpr int B_BYTES = BN * 128;
@@ -159,24 +160,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
+      // split product: iteration g belongs to term g / iters_per_term (0: A,B  1: A2,B  2: A,B2)
       auto load_b = [&](int it) {
         const int s = it % STAGES;
-        const int g = it0 + it;
+        int g = it0 + it;
+        const int term = p.iters_per_term > 0 ? g / p.iters_per_term : 0;
+        g -= term * p.iters_per_term;
         const int tap = g / p.chunks_per_tap;
         const int chunk = g - tap * p.chunks_per_tap;
         uint8_t* sa = smem + s * STAGE_BYTES;
+        const CUtensorMap* mb = (term == 2) ? &tmB2 : &tmB;
         if (p.b_evict_last)
-          tma_load_2d_hint(sa + A_BYTES, &tmB, p.b_k0 + tap * p.b_tap_stride + chunk * BK, p.b_row0 + n0, &full[s],
+          tma_load_2d_hint(sa + A_BYTES, mb, p.b_k0 + tap * p.b_tap_stride + chunk * BK, p.b_row0 + n0, &full[s],
                            0x14F0000000000000ull);           // L2 evict_last
         else
-          tma_load_2d(sa + A_BYTES, &tmB, p.b_k0 + tap * p.b_tap_stride + chunk * BK, p.b_row0 + n0, &full[s]);
+          tma_load_2d(sa + A_BYTES, mb, p.b_k0 + tap * p.b_tap_stride + chunk * BK, p.b_row0 + n0, &full[s]);
       };
       auto load_a = [&](int it) {
         const int s = it % STAGES;
-        const int g = it0 + it;
+        int g = it0 + it;
+        const int term = p.iters_per_term > 0 ? g / p.iters_per_term : 0;
+        g -= term * p.iters_per_term;
         const int tap = g / p.chunks_per_tap;
         const int chunk = g - tap * p.chunks_per_tap;
-        tma_load_2d(smem + s * STAGE_BYTES, &tmA, p.a_k0 + chunk * BK, p.a_row0 + m0 + tap * p.a_tap_rowshift, &full[s]);
+        const CUtensorMap* ma = (term == 1) ? &tmA2 : &tmA;
+        tma_load_2d(smem + s * STAGE_BYTES, ma, p.a_k0 + chunk * BK, p.a_row0 + m0 + tap * p.a_tap_rowshift, &full[s]);
       };
       // the B operand (weights) never depends on the previous kernel: with PDL its first ring-full of tiles streams in
       // while the prerequisite grid is still finishing; the A operand (activations) is loaded after the dependency wait
@@ -405,7 +413,11 @@ template <int BN, int ESIZE>
 constexpr int stages_for() { return (BN == 256) ? 4 : (BN == 128 ? 6 : 8); }
 
 template <int BN, int ESIZE, int BM = 128, int STG = 0>
-int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcParams& p, int splits, cudaStream_t st) {
+int launch_gemm_tc(const T2VGemmTcPlan* plan, const GemmTcParams& p, int splits, cudaStream_t st) {
+  const CUtensorMap& tmA = plan->tmA;
+  const CUtensorMap& tmB = plan->tmB;
+  const CUtensorMap& tmA2 = p.iters_per_term > 0 ? plan->tmA2 : plan->tmA;
+  const CUtensorMap& tmB2 = p.iters_per_term > 0 ? plan->tmB2 : plan->tmB;
   constexpr int STAGES = (STG > 0) ? STG : ((BM == 64) ? 8 : stages_for<BN, ESIZE>());
   constexpr int smem = STAGES * (BM * 128 + BN * 128) + 1024 + 256;
   static bool attr_set = false;
@@ -414,7 +426,8 @@ int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcP
     attr_set = true;
   }
   dim3 grid(t2v_ceil_div(p.M, BM), t2v_ceil_div(p.N, BN), splits);
-  T2V_CUDA_CHECK(t2v_launch(gemm_tc_kernel<BN, ESIZE, STAGES, BM>, grid, dim3(192), (size_t)smem, st, p.pdl != 0, 1, tmA, tmB, p));
+  T2V_CUDA_CHECK(t2v_launch(gemm_tc_kernel<BN, ESIZE, STAGES, BM>, grid, dim3(192), (size_t)smem, st, p.pdl != 0, 1, tmA, tmB, tmA2,
+                            tmB2, p));
   T2V_COUNT_LAUNCH();
   return 0;
 }
@@ -476,6 +489,7 @@ int t2v_gemm_tc_plan(T2VGemmTcPlan* plan, const void* A, long long lda, long lon
   p.iters_per_split = total / splits; p.chunks_per_tap = cpt; p.a_tap_rowshift = a_tap_rowshift;
   p.b_tap_stride = b_tap_stride; p.epi_atomic = epi_atomic; p.alpha = alpha;
   p.a_row0 = 0; p.b_row0 = 0; p.a_k0 = a_k0; p.b_k0 = b_k0; p.b_evict_last = 0; p.b_independent = 0; p.pdl = 0;
+  p.iters_per_term = 0;
   plan->BN = BN; plan->esize = esize; plan->splits = splits;
   return 0;
 }
@@ -488,16 +502,16 @@ int t2v_gemm_tc_run(const T2VGemmTcPlan* plan, int a_row0, int b_row0, float* D,
     if (BN == 128 && plan->BM == 64) {
       // 4 stages = 96 KB of shared memory: two CTAs fit on an SM, so the step GEMMs of the two decoder chains co-reside
       static const bool deep = getenv("T2V_M64_STAGES") && getenv("T2V_M64_STAGES")[0] == '8';
-      return deep ? launch_gemm_tc<128, 4, 64, 8>(plan->tmA, plan->tmB, p, splits, stream)
-                  : launch_gemm_tc<128, 4, 64, 4>(plan->tmA, plan->tmB, p, splits, stream);
+      return deep ? launch_gemm_tc<128, 4, 64, 8>(plan, p, splits, stream)
+                  : launch_gemm_tc<128, 4, 64, 4>(plan, p, splits, stream);
     }
-    if (BN == 64) return launch_gemm_tc<64, 4>(plan->tmA, plan->tmB, p, splits, stream);
-    if (BN == 128) return launch_gemm_tc<128, 4>(plan->tmA, plan->tmB, p, splits, stream);
-    return launch_gemm_tc<256, 4>(plan->tmA, plan->tmB, p, splits, stream);
+    if (BN == 64) return launch_gemm_tc<64, 4>(plan, p, splits, stream);
+    if (BN == 128) return launch_gemm_tc<128, 4>(plan, p, splits, stream);
+    return launch_gemm_tc<256, 4>(plan, p, splits, stream);
   } else {
-    if (BN == 64) return launch_gemm_tc<64, 2>(plan->tmA, plan->tmB, p, splits, stream);
-    if (BN == 128) return launch_gemm_tc<128, 2>(plan->tmA, plan->tmB, p, splits, stream);
-    return launch_gemm_tc<256, 2>(plan->tmA, plan->tmB, p, splits, stream);
+    if (BN == 64) return launch_gemm_tc<64, 2>(plan, p, splits, stream);
+    if (BN == 128) return launch_gemm_tc<128, 2>(plan, p, splits, stream);
+    return launch_gemm_tc<256, 2>(plan, p, splits, stream);
   }
 }
 
@@ -510,6 +524,29 @@ T2V_API int t2v_gemm_tc(const void* A, long long lda, long long a_rows, long lon
   int r = t2v_gemm_tc_plan(&plan, A, lda, a_rows, a_inner, B, ldb, b_rows, b_inner, ldd, M, N, k_sub, taps, a_tap_rowshift,
                            b_tap_stride, a_k0, b_k0, esize, splits, split_stride, epi_atomic, alpha, bn_hint);
   if (r) return r;
+  return t2v_gemm_tc_run(&plan, 0, 0, D, bias, stream);
+}
+
+// Split (error-compensated) form of t2v_gemm_tc for fp32 operands given as hi + lo parts on the tf32 grid:
+//   D = alpha * (A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T) (+ bias)   -- the three terms run through ONE accumulator (3x the K
+// loop, no read-modify-write of D), which recovers fp32-level accuracy from tf32 tensor-core products.  Same addressing as
+// t2v_gemm_tc (taps included); A_lo has the layout of A_hi, B_lo the layout of B_hi.
+T2V_API int t2v_gemm_tc_split3(const float* A_hi, const float* A_lo, long long lda, long long a_rows, long long a_inner,
+                               const float* B_hi, const float* B_lo, long long ldb, long long b_rows, long long b_inner, float* D,
+                               long long ldd, const float* bias, int M, int N, int k_sub, int taps, int a_tap_rowshift,
+                               int b_tap_stride, int a_k0, int b_k0, float alpha, int bn_hint, cudaStream_t stream) {
+  T2V_ARG_CHECK(A_hi && A_lo && B_hi && B_lo && D, "null operand");
+  T2V_ARG_CHECK((((uintptr_t)A_lo) & 15) == 0 && (((uintptr_t)B_lo) & 15) == 0, "operand base must be 16-byte aligned");
+  T2VGemmTcPlan plan;
+  int r = t2v_gemm_tc_plan(&plan, A_hi, lda, a_rows, a_inner, B_hi, ldb, b_rows, b_inner, ldd, M, N, k_sub, taps, a_tap_rowshift,
+                           b_tap_stride, a_k0, b_k0, 4, 1, 0, 0, alpha, bn_hint);
+  if (r) return r;
+  r = encode_2d(&plan.tmA2, A_lo, 4, a_inner, a_rows, lda, plan.BM);
+  if (r) return r;
+  r = encode_2d(&plan.tmB2, B_lo, 4, b_inner, b_rows, ldb, plan.BN);
+  if (r) return r;
+  plan.p.iters_per_term = plan.p.iters_per_split;
+  plan.p.iters_per_split *= 3;
   return t2v_gemm_tc_run(&plan, 0, 0, D, bias, stream);
 }
 

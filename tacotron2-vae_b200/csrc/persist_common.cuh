@@ -161,8 +161,13 @@ __device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target)
 }
 // all prior global writes of the CTA's participating threads (ordered before this thread by a CTA barrier) become
 // visible device-wide before the increment
+// (red.release is itself a release operation -- cumulative over everything that happens-before it, including the other threads'
+//  stores ordered by the CTA barrier -- so no separate __threadfence(), which would be a second, sequentially-consistent fence on
+//  the critical chain of every step; -DT2V_SIGNAL_FENCE restores it)
 __device__ __forceinline__ void signal_counter(unsigned* p) {
+#ifdef T2V_SIGNAL_FENCE
   __threadfence();
+#endif
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ uint64_t l2_policy(int kind) {      // 1: evict_last, 2: evict_first

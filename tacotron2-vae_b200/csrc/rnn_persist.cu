@@ -1,0 +1,311 @@
+// Encoder BiLSTM (reference model.py:171-190: nn.LSTM, bidirectional, packed by input_lengths) as ONE persistent kernel per pass:
+// 64 CTAs (32 per direction, 8 hidden units each, warp = unit) stay resident for all Ti steps.  The recurrent weights of a CTA's
+// units are staged into shared memory once (the per-step launches of rnn.cu re-staged them 120 times), the cell / cell-gradient
+// state lives in registers, and the only per-step exchange is the new h (forward) or the new gate gradients (backward) through
+// L2, ordered by one monotonic device-wide counter per direction (red.release / ld.acquire, bounded waits).
+// Same arithmetic as bilstm_step_fwd / bilstm_step_bwd (exact fp32 FFMA): the two paths are compared bit for bit in the tests.
+#include "t2v_common.cuh"
+#include <stdlib.h>
+
+namespace {
+
+constexpr int UPC = 8;          // hidden units (= warps) per CTA
+constexpr int MT = 64;          // batch rows (lane -> rows lane, lane + 32)
+constexpr long long WAIT_LIMIT = 4000000000LL;
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target) {
+  if (ld_acquire_u32(p) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_u32(p) < target) {
+    if (clock64() - t0 > WAIT_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void signal_counter(unsigned* p) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+
+struct SeqFwd {
+  const float* gx[2];            // [B*Tp, 4H] hoisted input projections (padded rows: row b*Tp + 2 + t)
+  const float* w_hh[2];          // [4H, H]
+  const float* b_hh[2];          // [4H]
+  float* seq;                    // [B*Tp, 2H] layer output (direction d writes columns d*H ..)
+  float* gates;                  // [2, Ti, B, 4H] saved gate activations
+  float* cells;                  // [2, Ti + 2, B, H] saved cell states, slot t + 1 = cell after time t
+  float* hbuf;                   // [2 dirs][2][B][H] h exchange (ping-pong)
+  unsigned* counters;            // [2][32] one line per direction, zero-initialised
+  const long long* lens;         // [B] or nullptr (Encoder.inference: no packing)
+  int B, H, Ti, Tp;
+};
+
+__global__ void __launch_bounds__(UPC * 32, 1) bilstm_seq_fwd_kernel(SeqFwd p) {
+  extern __shared__ __align__(16) float smf[];
+  const int H = p.H, dir = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * UPC, u = u0 + warp;
+  const int HS = H + 1;
+  const int ncta = gridDim.x;
+  float* hT = smf;                       // [MT][H+1] h_prev tile
+  float* ws = hT + ((MT * HS + 3) & ~3); // [H][UPC][4] recurrent weights of this CTA's units, k-major
+  const float* W = p.w_hh[dir];
+  for (int i = threadIdx.x; i < H * UPC * 4; i += UPC * 32) {
+    const int k = i % H, g = (i / H) % 4, uu = i / (4 * H);
+    ws[(k * UPC + uu) * 4 + g] = W[((long long)g * H + u0 + uu) * H + k];
+  }
+  const float* bh = p.b_hh[dir];
+  const float b_i = bh[u], b_f = bh[H + u], b_g = bh[2 * H + u], b_o = bh[3 * H + u];
+  unsigned* cnt = p.counters + 32 * dir;
+  float cst[2] = {0.f, 0.f};
+  long long len[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int b = r * 32 + lane;
+    len[r] = (b < p.B) ? (p.lens ? p.lens[b] : (long long)p.Ti) : 0;
+  }
+  for (int s = 0; s < p.Ti; ++s) {
+    const int t = dir ? p.Ti - 1 - s : s;
+    const float* hprev = p.hbuf + ((long long)(dir * 2 + (s & 1)) * p.B) * H;
+    float* hnext = p.hbuf + ((long long)(dir * 2 + ((s + 1) & 1)) * p.B) * H;
+    // gate pre-activations of this step: independent of the recurrence, in flight while the counter is polled
+    float gxv[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int b = r * 32 + lane;
+      if (b < p.B) {
+        const float* gx = p.gx[dir] + ((long long)b * p.Tp + 2 + t) * 4 * H;
+        gxv[r][0] = gx[u]; gxv[r][1] = gx[H + u]; gxv[r][2] = gx[2 * H + u]; gxv[r][3] = gx[3 * H + u];
+      } else {
+        gxv[r][0] = gxv[r][1] = gxv[r][2] = gxv[r][3] = 0.f;
+      }
+    }
+    if (s > 0) {
+      if (threadIdx.x == 0) wait_counter(cnt, (unsigned)(ncta * s));
+      __syncthreads();
+      const int nv = MT * H / 4;
+      for (int i0 = threadIdx.x; i0 < nv; i0 += UPC * 32 * 16) {
+        float4 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int i = i0 + j * UPC * 32;
+          const int m = (i * 4) / H, k = (i * 4) % H;
+          v[j] = (i < nv && m < p.B) ? __ldcg(reinterpret_cast<const float4*>(hprev + (long long)m * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int i = i0 + j * UPC * 32;
+          if (i < nv) {
+            const int m = (i * 4) / H, k = (i * 4) % H;
+            float* d = hT + m * HS + k;
+            d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+          }
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < MT * HS; i += UPC * 32) hT[i] = 0.f;
+    }
+    __syncthreads();
+    float acc[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[r][g] = 0.f;
+    if (s > 0) {
+#pragma unroll 4
+      for (int k = 0; k < H; ++k) {
+        const float a0 = hT[lane * HS + k], a1 = hT[(32 + lane) * HS + k];
+        const float4 w = *reinterpret_cast<const float4*>(ws + (k * UPC + warp) * 4);
+        acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]);
+        acc[0][2] = fmaf(a0, w.z, acc[0][2]); acc[0][3] = fmaf(a0, w.w, acc[0][3]);
+        acc[1][0] = fmaf(a1, w.x, acc[1][0]); acc[1][1] = fmaf(a1, w.y, acc[1][1]);
+        acc[1][2] = fmaf(a1, w.z, acc[1][2]); acc[1][3] = fmaf(a1, w.w, acc[1][3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int b = r * 32 + lane;
+      if (b >= p.B) continue;
+      float* gs = p.gates + (((long long)dir * p.Ti + t) * p.B + b) * 4 * H + u;
+      float* cs = p.cells + (((long long)dir * (p.Ti + 2) + t + 1) * p.B + b) * H + u;
+      float* so = p.seq + ((long long)b * p.Tp + 2 + t) * 2 * H + dir * H + u;
+      if (t >= len[r]) {      // dead step of a packed row: state untouched, zero output (pad_packed_sequence)
+        *so = 0.f;
+        gs[0] = 0.f; gs[H] = 0.f; gs[2 * H] = 0.f; gs[3 * H] = 0.f;
+        *cs = 0.f;
+        hnext[(long long)b * H + u] = hT[b * HS + u];
+        continue;
+      }
+      const float ig = t2v_sigmoid(acc[r][0] + gxv[r][0] + b_i);
+      const float fg = t2v_sigmoid(acc[r][1] + gxv[r][1] + b_f);
+      const float gg = tanhf(acc[r][2] + gxv[r][2] + b_g);
+      const float og = t2v_sigmoid(acc[r][3] + gxv[r][3] + b_o);
+      const float c2 = fg * cst[r] + ig * gg;
+      const float h2 = og * tanhf(c2);
+      cst[r] = c2;
+      hnext[(long long)b * H + u] = h2;
+      *so = h2;
+      gs[0] = ig; gs[H] = fg; gs[2 * H] = gg; gs[3 * H] = og;
+      *cs = c2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) signal_counter(cnt);
+  }
+}
+
+struct SeqBwd {
+  const float* w_hhT[2];         // [H, 4H] transposed recurrent weights
+  const float* dout;             // [B, Ti, 2H] gradient wrt the layer output
+  const float* gates;            // [2, Ti, B, 4H]
+  const float* cells;            // [2, Ti + 2, B, H]
+  float* dg[2];                  // [B*Tp, 4H] gate gradients per direction (padded rows: row b*Tp + 2 + t)
+  unsigned* counters;
+  const long long* lens;
+  int B, H, Ti, Tp;
+};
+
+__global__ void __launch_bounds__(UPC * 32, 1) bilstm_seq_bwd_kernel(SeqBwd p) {
+  extern __shared__ __align__(16) float smb[];
+  const int H = p.H, K = 4 * H, dir = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * UPC, u = u0 + warp;
+  const int ncta = gridDim.x;
+  constexpr int KC = 256, DS = KC + 1;
+  float* dT = smb;                       // [MT][KC+1] gate-gradient chunk of the previously processed step
+  float* ws = dT + MT * DS;              // [K][UPC] this CTA's columns of W_hh^T, staged once
+  for (int i = threadIdx.x; i < K * UPC; i += UPC * 32) {
+    const int k = i % K, uu = i / K;
+    ws[k * UPC + uu] = p.w_hhT[dir][(long long)(u0 + uu) * K + k];
+  }
+  unsigned* cnt = p.counters + 32 * dir;
+  float dcs[2] = {0.f, 0.f};
+  long long len[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int b = r * 32 + lane;
+    len[r] = (b < p.B) ? (p.lens ? p.lens[b] : (long long)p.Ti) : 0;
+  }
+  __syncthreads();
+  for (int s = 0; s < p.Ti; ++s) {
+    const int t = dir ? s : p.Ti - 1 - s;             // each direction walks its own forward order backwards
+    const int tn = dir ? t - 1 : t + 1;               // the step processed in the previous iteration
+    const int tp = dir ? t + 1 : t - 1;               // the step whose cell state entered step t (slot tp + 1)
+    // saved activations of this step: independent of the recurrence
+    float sg[2][4], sc2[2], scp[2], dov[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int b = r * 32 + lane;
+      if (b < p.B) {
+        const float* gs = p.gates + (((long long)dir * p.Ti + t) * p.B + b) * 4 * H + u;
+        sg[r][0] = gs[0]; sg[r][1] = gs[H]; sg[r][2] = gs[2 * H]; sg[r][3] = gs[3 * H];
+        sc2[r] = p.cells[(((long long)dir * (p.Ti + 2) + t + 1) * p.B + b) * H + u];
+        scp[r] = p.cells[(((long long)dir * (p.Ti + 2) + tp + 1) * p.B + b) * H + u];
+        dov[r] = p.dout[((long long)b * p.Ti + t) * 2 * H + dir * H + u];
+      } else {
+        sg[r][0] = sg[r][1] = sg[r][2] = sg[r][3] = 0.f; sc2[r] = scp[r] = dov[r] = 0.f;
+      }
+    }
+    float acc[2] = {0.f, 0.f};
+    if (s > 0) {
+      if (threadIdx.x == 0) wait_counter(cnt, (unsigned)(ncta * s));
+      const float* dgn = p.dg[dir] + ((long long)2 + tn) * K;       // row (b = 0, tn); batch stride Tp * K
+      for (int k0 = 0; k0 < K; k0 += KC) {
+        __syncthreads();
+        const int nv = MT * KC / 4;
+        for (int i0 = threadIdx.x; i0 < nv; i0 += UPC * 32 * 16) {
+          float4 v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int i = i0 + j * UPC * 32;
+            const int m = (i * 4) / KC, k = (i * 4) % KC;
+            v[j] = (i < nv && m < p.B) ? __ldcg(reinterpret_cast<const float4*>(dgn + (long long)m * p.Tp * K + k0 + k))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int i = i0 + j * UPC * 32;
+            if (i < nv) {
+              const int m = (i * 4) / KC, k = (i * 4) % KC;
+              float* d = dT + m * DS + k;
+              d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+            }
+          }
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < KC; ++k) {
+          const float w = ws[(k0 + k) * UPC + warp];
+          acc[0] = fmaf(dT[lane * DS + k], w, acc[0]);
+          acc[1] = fmaf(dT[(32 + lane) * DS + k], w, acc[1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int b = r * 32 + lane;
+      if (b >= p.B) continue;
+      float* dg = p.dg[dir] + ((long long)b * p.Tp + 2 + t) * K + u;
+      if (t >= len[r]) { dg[0] = 0.f; dg[H] = 0.f; dg[2 * H] = 0.f; dg[3 * H] = 0.f; continue; }
+      const float dh = acc[r] + dov[r];
+      const float ig = sg[r][0], fg = sg[r][1], gg = sg[r][2], og = sg[r][3];
+      const float tc = tanhf(sc2[r]);
+      const float dc = dcs[r] + dh * og * (1.f - tc * tc);
+      dg[0] = dc * gg * ig * (1.f - ig);
+      dg[H] = dc * scp[r] * fg * (1.f - fg);
+      dg[2 * H] = dc * ig * (1.f - gg * gg);
+      dg[3 * H] = dh * tc * og * (1.f - og);
+      dcs[r] = dc * fg;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) signal_counter(cnt);
+  }
+}
+
+}  // namespace
+
+// Whole-sequence forward of both directions.  gx0 / gx1: [B*Tp, 4H] input projections (+ b_ih) on the padded rows (Tp = Ti + 4, valid
+// rows 2..Ti+1); seq: [B*Tp, 2H] output rows; gates [2,Ti,B,4H], cells [2,Ti+2,B,H] (zero-initialised: slots 0 and Ti+1 stay zero);
+// hbuf: scratch [2,2,B,H]; counters: 64 unsigned, zeroed by this call.  B <= 64, H <= 512 (larger batches: the per-step launches
+// t2v_bilstm_step_fwd / _bwd).
+T2V_API int t2v_bilstm_seq_fwd(const float* gx0, const float* gx1, const float* whh0, const float* whh1, const float* bhh0,
+                               const float* bhh1, float* seq, float* gates, float* cells, float* hbuf, unsigned int* counters,
+                               const long long* lens, int B, int H, int Ti, cudaStream_t st) {
+  T2V_ARG_CHECK(gx0 && gx1 && whh0 && whh1 && seq && gates && cells && hbuf && counters && B > 0 && Ti > 0, "null / shape");
+  T2V_ARG_CHECK(B <= MT && H % UPC == 0 && H <= 512 && H % 4 == 0, "B <= 64, H <= 512");
+  SeqFwd a;
+  a.gx[0] = gx0; a.gx[1] = gx1; a.w_hh[0] = whh0; a.w_hh[1] = whh1; a.b_hh[0] = bhh0; a.b_hh[1] = bhh1; a.seq = seq;
+  a.gates = gates; a.cells = cells; a.hbuf = hbuf; a.counters = counters; a.lens = lens; a.B = B; a.H = H; a.Ti = Ti; a.Tp = Ti + 4;
+  const size_t smem = sizeof(float) * (size_t)(((MT * (H + 1) + 3) & ~3) + H * UPC * 4);
+  static size_t cur = 48 * 1024;
+  if (smem > cur) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(bilstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
+  T2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned), st));
+  bilstm_seq_fwd_kernel<<<dim3(H / UPC, 2), UPC * 32, smem, st>>>(a);
+  T2V_COUNT_LAUNCH();
+  T2V_LAUNCH_CHECK();
+  return 0;
+}
+
+// Whole-sequence backward: dout [B,Ti,2H] -> dg0 / dg1 [B*Tp, 4H] (gate gradients on the padded rows; pad rows untouched).
+T2V_API int t2v_bilstm_seq_bwd(const float* whhT0, const float* whhT1, const float* dout, const float* gates, const float* cells,
+                               float* dg0, float* dg1, unsigned int* counters, const long long* lens, int B, int H, int Ti,
+                               cudaStream_t st) {
+  T2V_ARG_CHECK(whhT0 && whhT1 && dout && gates && cells && dg0 && dg1 && counters && B > 0 && Ti > 0, "null / shape");
+  T2V_ARG_CHECK(B <= MT && H % UPC == 0 && (4 * H) % 256 == 0 && H <= 512, "B <= 64, H <= 512");
+  SeqBwd a;
+  a.w_hhT[0] = whhT0; a.w_hhT[1] = whhT1; a.dout = dout; a.gates = gates; a.cells = cells; a.dg[0] = dg0; a.dg[1] = dg1;
+  a.counters = counters; a.lens = lens; a.B = B; a.H = H; a.Ti = Ti; a.Tp = Ti + 4;
+  const size_t smem = sizeof(float) * (size_t)(MT * 257 + 4 * H * UPC);
+  static size_t cur = 48 * 1024;
+  if (smem > cur) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(bilstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
+  T2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned), st));
+  bilstm_seq_bwd_kernel<<<dim3(H / UPC, 2), UPC * 32, smem, st>>>(a);
+  T2V_COUNT_LAUNCH();
+  T2V_LAUNCH_CHECK();
+  return 0;
+}

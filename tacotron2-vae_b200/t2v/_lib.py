@@ -24,7 +24,7 @@ class T2VDecoderSeq(ctypes.Structure):
                  ("seed", ctypes.c_ulonglong), ("drop_masks", _P), ("mask_value", ctypes.c_float), ("in_lens", _P)] +
                 [(n, _P) for n in ("Wa", "ba1", "ba2", "Wd", "bd1", "bd2", "Wq", "Wconv", "Wloc", "v", "mem", "pmem",
                                    "XA", "XD", "CA", "CD", "CUM", "align", "GA", "GD", "CPA", "CPD", "ASAVE", "parts",
-                                   "qparts", "ebuf", "WaP", "WdP", "HCLO")] +
+                                   "qparts", "ebuf", "WaP", "WdP", "HCHI", "HCLO")] +
                 [("op16", ctypes.c_int)] + [(n, _P) for n in ("XA16", "XD16", "WaP16", "WdP16")])
 
 

@@ -6,7 +6,7 @@ import sys
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libt2v_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "pointwise.cu", "attention.cu", "attention2.cu", "misc.cu", "rnn.cu", "decoder.cu", "decoder_persist.cu", "decoder_persist_bwd.cu"]
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "pointwise.cu", "attention.cu", "attention2.cu", "misc.cu", "rnn.cu", "rnn_persist.cu", "decoder.cu", "decoder_persist.cu", "decoder_persist_bwd.cu"]
 
 
 def _stale():

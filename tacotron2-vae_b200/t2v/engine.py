@@ -48,6 +48,7 @@ _OVERLAP = __import__("os").environ.get("T2V_OVERLAP", "1") != "0"
 # CTAs of the persistent kernels must become co-resident, and foreign CTAs on the GPU while their clusters are placed are the one
 # situation that has not been exercised for long.
 _POST_DW_BRANCH = __import__("os").environ.get("T2V_POST_DW_BRANCH", "0") == "1"
+_BILSTM_PERSIST = __import__("os").environ.get("T2V_BILSTM_PERSIST", "1") != "0"
 
 
 class _Branch(object):
@@ -277,16 +278,15 @@ def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, se
         Y = _zeros(R, Co, device=dev)
         if ops.tc:
             bn = ops.bn(M, Co)
-            L("t2v_gemm_tc", X, Ci, R, Ci, Wk, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co, P[pre + ".0.conv.bias"], M, Co, Ci, 5, 1,
-              Ci, 0, 0, 4, 1, 0, 0, 1.0, bn)
             if split:
                 Wf = _empty(Co, 5 * Ci, device=dev)
                 L("t2v_conv1d_pack", W, Wf, Co, Ci, 5, 0, 0)
                 Wl = ops.lo(Wf, Wk)
-                L("t2v_gemm_tc", Xlo, Ci, R, Ci, Wk, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co, None, M, Co, Ci, 5, 1,
-                  Ci, 0, 0, 4, 1, 0, 2, 1.0, bn)
-                L("t2v_gemm_tc", X, Ci, R, Ci, Wl, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co, None, M, Co, Ci, 5, 1,
-                  Ci, 0, 0, 4, 1, 0, 2, 1.0, bn)
+                L("t2v_gemm_tc_split3", X, Xlo, Ci, R, Ci, Wk, Wl, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co, P[pre + ".0.conv.bias"],
+                  M, Co, Ci, 5, 1, Ci, 0, 0, 1.0, bn)
+            else:
+                L("t2v_gemm_tc", X, Ci, R, Ci, Wk, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co, P[pre + ".0.conv.bias"], M, Co, Ci, 5, 1,
+                  Ci, 0, 0, 4, 1, 0, 0, 1.0, bn)
         else:
             ops.gemm(X, Ci, 1, Wk, 5 * Ci, 1, _p(Y, 2 * Co), Co, M, Co, 5 * Ci, 1.0, 0.0, P[pre + ".0.conv.bias"])
         Xn = _empty(R, Co, device=dev)
@@ -390,7 +390,11 @@ def encoder_forward(ops, P, text, in_len, training, masks, seed, dev, packed=Tru
     cst = _zeros(2, B, Hh, device=dev)
     Whh = [P["encoder.lstm.weight_hh_l0"], P["encoder.lstm.weight_hh_l0_reverse"]]
     bhh = [P["encoder.lstm.bias_hh_l0"], P["encoder.lstm.bias_hh_l0_reverse"]]
-    for s in range(Ti):
+    persist = B <= 64 and _BILSTM_PERSIST
+    if persist:        # one resident kernel for all Ti steps of both directions (rnn_persist.cu)
+        cnt = torch.zeros(64, device=dev, dtype=torch.int32)
+        L("t2v_bilstm_seq_fwd", GX[0], GX[1], Whh[0], Whh[1], bhh[0], bhh[1], HoutP, GS, CS, hbuf, cnt, lens, B, Hh, Ti)
+    for s in range(0 if persist else Ti):
         t0, t1 = s, Ti - 1 - s
         a, b = s & 1, (s + 1) & 1
         L("t2v_bilstm_step_fwd", _p(GX[0], (2 + t0) * 4 * Hh), _p(GX[1], (2 + t1) * 4 * Hh), Tp * 4 * Hh, Whh[0], Whh[1],
@@ -416,7 +420,11 @@ def encoder_backward(ops, P, dmem, ctx, training, seed, dev, grads):
         L("t2v_transpose", P["encoder.lstm.weight_hh_l0" + sfx], Hh, wt, 4 * Hh, 4 * Hh, Hh, 0)
         WT.append(wt)
     dcb = _zeros(2, B, Hh, device=dev)
-    for s in range(Ti):
+    persist = B <= 64 and _BILSTM_PERSIST
+    if persist:
+        cnt = torch.zeros(64, device=dev, dtype=torch.int32)
+        L("t2v_bilstm_seq_bwd", WT[0], WT[1], dmem, GS, CS, DGs[0], DGs[1], cnt, lens, B, Hh, Ti)
+    for s in range(0 if persist else Ti):
         t0, t1 = Ti - 1 - s, s                    # each direction walks its own forward order backwards
         L("t2v_bilstm_step_bwd", _p(DGs[0], (3 + t0) * 4 * Hh) if s > 0 else None, _p(DGs[1], (1 + t1) * 4 * Hh) if s > 0 else None,
           Tp * 4 * Hh, WT[0], WT[1], _p(dmem, t0 * 512), _p(dmem, t1 * 512 + Hh), Ti * 512, dcb[0], dcb[1], GS[0, t0], GS[1, t1],
@@ -655,7 +663,7 @@ def _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_v
     S.Wloc = P[_A + "location_layer.location_dense.linear_layer.weight"].data_ptr()
     S.v = P[_A + "v.linear_layer.weight"].data_ptr()
     S.mem, S.pmem = mem.data_ptr(), pmem.data_ptr()
-    for k in ("XA", "XD", "CA", "CD", "CUM", "align", "GA", "GD", "CPA", "CPD", "ASAVE", "parts", "qparts", "ebuf", "HCLO",
+    for k in ("XA", "XD", "CA", "CD", "CUM", "align", "GA", "GD", "CPA", "CPD", "ASAVE", "parts", "qparts", "ebuf", "HCHI", "HCLO",
               "XA16", "XD16"):
         setattr(S, k, _lib.ptr(buf.get(k)))
     S.op16 = ops.op16 if buf.get("XA16") is not None else 0
@@ -675,8 +683,9 @@ def alloc_decoder_buffers(B, Ti, To, dev, save=True, op16=0, split=False):
     if op16:        # 16-bit operand copies of XA / XD for the persistent loop (zero rows = the initial h / ctx / go frame)
         buf.update(XA16=torch.zeros((To + 1) * B, 1792, device=dev, dtype=torch.int16),
                    XD16=torch.zeros((To + 1) * B, 2560, device=dev, dtype=torch.int16))
-    if split:       # low parts of [h_dec_t | ctx_t] for the split mel / gate projection
-        buf["HCLO"] = _zeros(To * B, 1536, device=dev)
+    if split:       # [h_dec_t | ctx_t] as hi + lo parts: the operands of the split mel / gate projection
+        buf["HCHI"] = _empty(To * B, 1536, device=dev)
+        buf["HCLO"] = _empty(To * B, 1536, device=dev)
     return buf
 
 
@@ -695,18 +704,20 @@ def pack_step_weights(ops, W, dev):
         L("t2v_pack_step_tiles16", W["Wd"], 1, W["WdP16"], ops.op16)
 
 
-def project_mel_gate(ops, W, XD, HCLO, O, B, To):
+def project_mel_gate(ops, W, buf, O, B, To, persistent):
     """deferred linear_projection + gate_layer of [h_dec_t | ctx_t] for all steps (model.py:383-388) -> O [To*B, 84].
-    h_dec_t sits in XD row t+1 (cols 1536..), ctx_t in XD row t (cols 1024..1535), both on the operand grid; with the low
-    parts (HCLO, W_lo) the product is the three-term split x_hi W_hi + x_lo W_hi + x_hi W_lo: the mel frames are sums with
-    heavy cancellation, and plain tf32 rounding of this one GEMM was 90 % of the mel error of the whole decoder."""
+    The mel frames are sums with heavy cancellation: plain tf32 rounding of this one GEMM was 90 % of the mel error of the whole
+    decoder.  When the persistent loop kernel ran it left [h_dec_t | ctx_t] as hi + lo parts (HCHI / HCLO) and the projection is
+    ONE split GEMM x_hi W_hi + x_lo W_hi + x_hi W_lo; otherwise (per-step launches) two plain GEMMs over the XD rows: h_dec_t sits in
+    XD row t+1 (cols 1536..), ctx_t in XD row t (cols 1024..1535)."""
     n = To * B
+    XD = buf["XD"]
+    if persistent and ops.tc and ops.split and buf.get("HCHI") is not None and W.get("Wpg_lo") is not None:
+        L("t2v_gemm_tc_split3", buf["HCHI"], buf["HCLO"], 1536, n, 1536, W["Wpg"], W["Wpg_lo"], 1536, 81, 1536, O, 84, W["bpg"],
+          n, 81, 1536, 1, 0, 0, 0, 0, 1.0, 128)
+        return
     ops.linear(_p(XD, B * 2560 + 1536), 2560, W["Wpg"], 1536, O, 84, n, 81, 1024, bias=W["bpg"], a_rows=n)
     ops.linear(_p(XD, 1024), 2560, _p(W["Wpg"], 1024), 1536, O, 84, n, 81, 512, accumulate=True, a_rows=n)
-    if HCLO is not None and ops.tc and W.get("Wpg_lo") is not None:
-        ops.linear(HCLO, 1536, W["Wpg"], 1536, O, 84, n, 81, 1536, accumulate=True)
-        ops.linear(_p(XD, B * 2560 + 1536), 2560, W["Wpg_lo"], 1536, O, 84, n, 81, 1024, accumulate=True, a_rows=n)
-        ops.linear(_p(XD, 1024), 2560, _p(W["Wpg_lo"], 1024), 1536, O, 84, n, 81, 512, accumulate=True, a_rows=n)
 
 
 def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, drop_masks, seed, mask_value, dev):
@@ -742,10 +753,11 @@ def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, dro
     _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_value, in_len, memory, pmem, buf)
     _trace("  fwd prenet+pack")
     L("t2v_decoder_fwd_steps", S, 0, To)
+    persistent = bool(_lib.lib().t2v_decoder_last_path())      # 1: the persistent loop kernel was enqueued (HCHI / HCLO are valid)
     _trace("  fwd decoder loop")
     # deferred mel/gate projection of [h_dec_t | ctx_t] for all steps (model.py:383-388)
     O = _zeros(To * B, 84, device=dev)
-    project_mel_gate(ops, W, buf["XD"], buf.get("HCLO"), O, B, To)
+    project_mel_gate(ops, W, buf, O, B, To, persistent)
     ctx = dict(B=B, Ti=Ti, To=To, W=W, pmem=pmem, memory=memory, buf=buf, S=S, Fr=Fr, P1pre=P1pre, P1=P1, P2pre=P2pre,
                m0=m0, m1=m1, seed=seed, O=O)
     return O, buf["align"], ctx

@@ -130,7 +130,10 @@ def test_train_step_at_bench_batch_vs_oracle(precision):
             continue
         assert g is not None, k
         gn, rn = float(g.norm()), float(gr.norm())
-        # (conv biases in front of a training-mode BN have an exactly-zero true gradient: rounding noise on both sides)
+        if k.endswith(".0.conv.bias") or (k.startswith("vae_gst.ref_encoder.convs.") and k.endswith(".bias")):
+            # a conv bias in front of a training-mode BatchNorm has an exactly-zero true gradient: both sides are rounding noise
+            assert gn <= 1e-2 * total and rn <= 1e-2 * total, (k, gn, rn, total)
+            continue
         rel = abs(gn - rn) / (rn + 1e-4 * total)
         if rel > worst[1]:
             worst = (k, rel)

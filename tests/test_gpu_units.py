@@ -531,3 +531,49 @@ def test_persistent_loop_16bit_operands_match_tf32_loop(L, B, Ti, To, training):
             err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
             print("%s vs tf32 loop %-6s max-rel %.3e" % (prec, k, err))
             assert err <= (max(tol, 1.5e-3) if k in ("XA", "XD") else tol), (prec, k, err)
+
+
+@pytest.mark.parametrize("B,Ti,packed", [(64, 120, True), (5, 17, True), (3, 9, False), (1, 1, True)])
+def test_persistent_bilstm_matches_per_step_launches(L, B, Ti, packed):
+    """rnn_persist.cu (one resident kernel for all Ti steps of both directions, forward and backward) against the per-step launches
+    of rnn.cu: same FFMA loops in the same order, so outputs, saved activations and every encoder gradient agree bit for bit
+    (gradients that go through atomics: 1e-5 of the max)."""
+    from oracle import port
+    from t2v import engine
+    dev = torch.device("cuda")
+    P = {k: v.to(dev) for k, v in port.init_params(1234).items()}
+    ops = engine.Ops("fp32")
+    g = torch.Generator().manual_seed(B * 100 + Ti)
+    text = torch.randint(1, 79, (B, Ti), generator=g).to(dev)
+    in_len = torch.randint(max(1, Ti // 2), Ti + 1, (B,), generator=g).sort(descending=True)[0]
+    in_len[0] = Ti
+    in_len = in_len.to(dev)
+    dmem = torch.randn(B, Ti, 512, generator=g).to(dev)
+    res = {}
+    for mode in (True, False):
+        engine._BILSTM_PERSIST = mode
+        try:
+            n0 = _launches()
+            HoutP, ctx = engine.encoder_forward(ops, P, text, in_len if packed else None, True, None, 5, dev, packed=packed)
+            n_fwd = _launches() - n0
+            grads = {}
+            engine.encoder_backward(ops, P, dmem.clone(), ctx, True, 5, dev, grads)
+            torch.cuda.synchronize()
+        finally:
+            engine._BILSTM_PERSIST = True
+        res[mode] = dict(HoutP=HoutP.clone(), GS=ctx["GS"].clone(), CS=ctx["CS"].clone(), n_fwd=n_fwd,
+                         **{"g:" + k: v.clone() for k, v in grads.items() if k.startswith("encoder.lstm")})
+    assert res[True]["n_fwd"] <= res[False]["n_fwd"] - (Ti - 1)          # Ti step launches became one
+    for k in res[True]:
+        if k == "n_fwd":
+            continue
+        a, b = res[True][k], res[False][k]
+        if k.startswith("g:"):
+            assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-12, k
+        else:
+            assert torch.equal(a, b), k
+
+
+def _launches():
+    from t2v import _lib
+    return _lib.launch_count()
