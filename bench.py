@@ -146,18 +146,21 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        # bounded sample of the C3 workload: same text length, batch and frame count cut so K+W steps take ~2-3 minutes
-        budget_frames = int(120.0 * 300.0 / max(1, a.steps + min(a.warmup, 1)))
-        To_s = 100
-        B_s = max(2, min(a.batch, budget_frames // To_s))
+        # bounded sample of the C3 workload: the SAME batch and text length (BatchNorm statistics and every GEMM shape depend on
+        # the batch), only the number of mel frames per utterance is cut (the decoder loop is linear in it) so that K + W steps
+        # end within a few minutes
+        B_s = a.batch
+        To_s = max(16, min(a.to, int(120000.0 / max(1, a.batch) / max(1, a.steps + min(a.warmup, 2)))))   # ~17 k frames / step at the default K=5, W=2
         threads = pick_cpu_threads(cores)
-        fps, sec = cpu_oracle_throughput(B_s, a.ti, To_s, a.steps, min(a.warmup, 1), threads)
-        sample = "B=%d,Ti=%d,To=%d (%d padded frames/step) of the B=%d,To=%d workload" % (B_s, a.ti, To_s, B_s * To_s, a.batch, a.to)
+        fps, sec = cpu_oracle_throughput(B_s, a.ti, To_s, a.steps, min(a.warmup, 2), threads)
+        sample = "B=%d,Ti=%d,To=%d (%d padded frames/step) of the B=%d,To=%d workload: frames per utterance cut, batch kept" % (
+            B_s, a.ti, To_s, B_s * To_s, a.batch, a.to)
         print(json.dumps({
             "impl": "reference", "metric": "padded mel-frames/s (train fwd+bwd+opt)", "value": fps, "unit": "frames/s",
-            "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C3: Tacotron2-VAE train step, batch %d/GPU, Ti<=%d, To<=%d" % (a.batch, a.ti, a.to),
+                       "sample": sample, "parallelism": "dp1", "global_batch": a.batch,
                        "note": "CPU oracle (oracle/port.py, restatement of the reference's PyTorch CPU path) on a bounded sample"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "host_cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -168,6 +171,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        # communicator / transport lines of the NCCL init (ring / tree / NVLS over NVSwitch) go to stderr, the JSON line stays alone
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     import model as t2v_model
     from hparams import create_hparams
@@ -255,11 +262,11 @@ def main():
     _progress("roofline done")
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
-        Bs, Tos = 8, 100
+        Bs, Tos = B, 48                                   # same batch, frames per utterance cut (see --impl reference)
         threads = pick_cpu_threads(cores)
         fps, sec = cpu_oracle_throughput(Bs, Ti, Tos, 2, 1, threads)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "host_cores": cores, "kind": "port",
-               "sample": "B=%d,Ti=%d,To=%d (%d padded frames/step, 2 steps) of the C3 workload" % (Bs, Ti, Tos, Bs * Tos)}
+               "sample": "B=%d,Ti=%d,To=%d (%d padded frames/step, 2 steps + 1 warm-up) of the C3 workload" % (Bs, Ti, Tos, Bs * Tos)}
     _progress("cpu baseline done")
     if rank == 0:
         print(json.dumps({
@@ -401,19 +408,29 @@ def decoder_step_roofline(m, hp, B, Ti, To, dev, precision):
     achieved = alg_bytes / (us * 1e-6) / 1e9
     persist = os.environ.get("T2V_PERSIST", "1") != "0" and precision != "fp32" and B <= 64 and Ti <= 128
     kernel = ("dec_persist_fwd_kernel: ONE persistent launch for all To steps of Decoder.decode (128 CTAs = 32 clusters x 4; "
-              "TMA weight streaming, tcgen05 tf32 split-K over the cluster + DSMEM exchange, LSTM cells / query partials "
-              "in the epilogue, attention by CTA pairs); per-step time = kernel time / To") if persist else (
+              "TMA weight streaming, tcgen05 %s split-K over the cluster + DSMEM exchange, LSTM cells in the epilogue, query "
+              "projection as a per-CTA UMMA, attention by CTA pairs); per-step time = kernel time / To" %
+              ("kind::f16 (%s operands)" % precision if s == 2 else "kind::tf32")) if persist else (
               "decoder step = gemm_tc<128,4,8,64> x3 (attention_rnn gates, query, decoder_rnn gates) + lstm_pointwise_fwd x2 + "
               "attn3_row (fused energy/softmax/context): 6 launches per step in two concurrent chains, CUDA-graph replay")
-    traffic = None
-    try:      # measured DRAM bytes per step of the same kernel (ncu, profiles/r01_ncu_persist_dram.json)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_persist_dram.json")))["dram_bytes_per_step"] if persist else None
+    traffic, traffic_src = None, None
+    try:      # DRAM bytes per step of the same kernel from the committed ncu --set full capture (NOT measured in this run)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_persist_dram.json")))
+        if persist and tj.get("precision") == precision:
+            traffic = tj["dram_bytes_per_step"]
+            traffic_src = "profiles/r02_ncu_persist_dram.json: ncu --set full of dec_persist_fwd_kernel, B=%d Ti=%d To=%d, %s" % (
+                tj.get("B", 0), tj.get("Ti", 0), tj.get("To", 0), tj.get("precision"))
     except Exception:  # noqa: BLE001
         pass
     return {"kernel": kernel,
             "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src,
+            "frac_on_dram_traffic": (traffic / (us * 1e-6) / 1e9 / peak) if traffic else None,
             "us_per_step": us, "algorithmic_bytes_per_step": alg_bytes,
+            "algorithmic_bytes_note": "SURVEY 8(d): 18 103 953 weights + step activations, x %d bytes per operand element (%s)" % (
+                s, "the north star's bf16 denominator" if s == 2 else "fp32 storage"),
+            "target_us_for_half_of_peak": alg_bytes / (0.5 * peak * 1e9) * 1e6,
             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}
 
 
