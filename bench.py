@@ -171,10 +171,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        # communicator / transport lines of the NCCL init (ring / tree / NVLS over NVSwitch) go to stderr, the JSON line stays alone
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("T2V_NCCL_DEBUG"):      # NCCL's own init log (communicators, rings / trees / NVLS) into a file per rank
+            os.environ.setdefault("NCCL_DEBUG", "INFO")
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH")
+            os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", "nccl_init_%h_%p.log"))
         dist.init_process_group("nccl", device_id=dev)
     import model as t2v_model
     from hparams import create_hparams
@@ -260,6 +260,22 @@ def main():
     bwd_step = decoder_step_backward(m, B, Ti, To, dev, a.precision) if rank == 0 else None
 
     _progress("roofline done")
+    comm = None
+    if world > 1:      # the gradient exchange alone: one ncclAllReduce(SUM) over the flat fp32 gradient buffer, device-timed, max over ranks
+        times = []
+        for _ in range(5):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); dist.all_reduce(flat.buffer); e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        t = torch.tensor([min(times[1:])], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nbytes = flat.numel * 4
+        comm = {"backend": "nccl", "nccl_version": ".".join(str(v) for v in torch.cuda.nccl.version()), "world_size": dist.get_world_size(),
+                "allreduce_bytes": nbytes, "allreduce_ms": float(t), "allreduce_busbw_gbs": nbytes * 2 * (world - 1) / world / (float(t) * 1e-3) / 1e9,
+                "share_of_step": float(t) / (ms / a.steps),
+                "note": "one blocking all-reduce after the backward graph; not overlapped (it is %.1f %% of the step)" % (100 * float(t) / (ms / a.steps))}
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
         Bs, Tos = B, 48                                   # same batch, frames per utterance cut (see --impl reference)
@@ -281,7 +297,7 @@ def main():
                        "l2": "per-step working set (>3 GB of saved activations) exceeds the 126 MB L2"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": launches, "roofline": roof, "decoder_step_inference": infer_step, "decoder_step_backward": bwd_step, "cpu_baseline": cpu,
+            "gpu_launches": launches, "comm": comm, "roofline": roof, "decoder_step_inference": infer_step, "decoder_step_backward": bwd_step, "cpu_baseline": cpu,
             "clocks": sampler.summary()}))
     if world > 1:
         dist.destroy_process_group()
