@@ -32,9 +32,7 @@ constexpr int NF = 32, KS = 31, HALO = 15;
 constexpr unsigned SITE_ATT_H = 10, SITE_ATT_C = 11, SITE_DEC_H = 12, SITE_DEC_C = 13;
 constexpr int CL = 4, NCLUSTER = 32, NCTA = CL * NCLUSTER;
 constexpr int NTHREADS = 512;
-constexpr int NS = 4;                          // ring depth: a stage = one K chunk of weights (16 KB) + activations (8 KB)
-constexpr int NW = NS, NA = NS;
-constexpr int W_STAGE = 128 * 128, A_STAGE = 64 * 128;
+constexpr int W_STAGE = 128 * 128, A_STAGE = 64 * 128;   // bytes of one ring stage: weights [128 gate rows][128 B of K], activations [64][128 B]
 // K chunks per CTA (one 128-byte swizzle row of K per chunk): fp32 storage = 32 columns -> (64 + 128 + 256) / 32 = 14 and
 // (256 + 128 + 256) / 32 = 20 chunks; 16-bit operands = 64 columns -> 7 and 10 chunks of the same 16 KB + 8 KB
 template <int OP> struct Chunks { static constexpr int ATT = OP ? 7 : 14, DEC = OP ? 10 : 20, CK = OP ? 64 : 32; };
@@ -43,29 +41,36 @@ constexpr int SLOT = 4 * 16 * 32;              // floats of one exchange slot: [
 constexpr int TH_MAX = 64;                     // text positions per CTA (two CTAs per utterance) -> Ti <= 128
 constexpr int PADW = 160;                      // alignment / cumulative-alignment rows with a 15-wide zero halo
 constexpr int BAR_EPI = 1, BAR_ATT = 2;
+constexpr int FS = 36;                         // row stride of the fp32 conv output (16-byte aligned rows)
 
-// ---- shared memory carve-up (bytes from the 1024-aligned base)
-constexpr int OFF_WRING = 0;
-constexpr int OFF_ARING = OFF_WRING + NW * W_STAGE;
-constexpr int OFF_RECV = OFF_ARING + NA * A_STAGE;                  // [2 gemms][4 sources][SLOT]
-constexpr int OFF_S = OFF_RECV + 2 * 4 * SLOT * 4;                  // [TH_MAX][128] location term + processed memory
-constexpr int FS = 36;                                              // row stride of the conv output (16-byte aligned rows)
-constexpr int OFF_F = OFF_S + TH_MAX * AD * 4;                      // [TH_MAX][FS] conv output; aliased: ctx partials [4][256]
-constexpr int OFF_WCT = OFF_F + TH_MAX * FS * 4;                    // [62][32]
-constexpr int OFF_HQ = OFF_WCT + 2 * KS * NF * 4;                   // [16][32] h_att of this CTA's rows (query partials)
-constexpr int OFF_WPAD = OFF_HQ + 16 * 32 * 4;
-constexpr int OFF_CPAD = OFF_WPAD + PADW * 4;
-constexpr int OFF_E = OFF_CPAD + PADW * 4;                          // [128] energies
-constexpr int OFF_Q = OFF_E + 128 * 4;                              // [2][128]
-constexpr int OFF_BARS = OFF_Q + 256 * 4;
-constexpr int N_BARS = 2 * NS + 9;
-constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
-// 16-bit operands of the in-kernel query projection (op16 only): query_layer columns of this cluster's 32 units [128 a][32 u] and
-// this CTA's h_att rows [16 b][32 u], K-major rows of 64 bytes in the SWIZZLE_64B layout (written by ordinary threads)
-constexpr int OFF_WQ16 = (OFF_TMEM + 16 + 1023) / 1024 * 1024;
-constexpr int OFF_HQ16 = OFF_WQ16 + 128 * 64;
-constexpr int SMEM_BYTES = OFF_HQ16 + 16 * 64 + 1024;
-static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+// ---- shared memory carve-up (bytes from the 1024-aligned base), per operand mode.  op16: a stage holds twice the K (64 columns), so
+// three stages buffer more of the weight stream than four did; the 24 KB pay for the 16-bit operands of the two small in-kernel UMMAs
+// (query projection, location dense) whose fp32 FFMA versions were the busiest shared-memory loops of the step.
+template <int OP> struct SM {
+  static constexpr int NS = OP ? 3 : 4;                             // ring depth: a stage = weights (16 KB) + activations (8 KB)
+  static constexpr int OFF_WRING = 0;
+  static constexpr int OFF_ARING = OFF_WRING + NS * W_STAGE;
+  static constexpr int OFF_RECV = OFF_ARING + NS * A_STAGE;         // [2 gemms][4 sources][SLOT]
+  static constexpr int OFF_S = OFF_RECV + 2 * 4 * SLOT * 4;         // [TH_MAX][128] location term + processed memory
+  static constexpr int OFF_F = OFF_S + TH_MAX * AD * 4;             // fp32: [TH_MAX][FS] conv output; aliased: ctx partials [4][256],
+  static constexpr int F_BYTES = OP ? 1280 * 4 : TH_MAX * FS * 4;   //       inference scratch (op16: only those, 1280 floats)
+  static constexpr int OFF_WCT = OFF_F + F_BYTES;                   // [62][32]
+  static constexpr int OFF_HQ = OFF_WCT + 2 * KS * NF * 4;          // [16][32] h_att of this CTA's rows (query partials)
+  static constexpr int OFF_WPAD = OFF_HQ + 16 * 32 * 4;
+  static constexpr int OFF_CPAD = OFF_WPAD + PADW * 4;
+  static constexpr int OFF_E = OFF_CPAD + PADW * 4;                 // [128] energies
+  static constexpr int OFF_Q = OFF_E + 128 * 4;                     // [2][128]
+  static constexpr int OFF_BARS = OFF_Q + 256 * 4;
+  static constexpr int N_BARS = 2 * NS + 10;
+  static constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
+  // op16 only: K-major 16-bit tiles with rows of 64 bytes in the SWIZZLE_64B layout, written by ordinary threads:
+  static constexpr int OFF_WQ16 = (OFF_TMEM + 16 + 1023) / 1024 * 1024;   // query_layer columns of this cluster's units [128 a][32 u]
+  static constexpr int OFF_HQ16 = OFF_WQ16 + 128 * 64;                    // this CTA's h_att rows [16 b][32 u]
+  static constexpr int OFF_WL16 = OFF_HQ16 + 16 * 64;                     // location_dense weight [128 a][32 c]
+  static constexpr int OFF_F16 = OFF_WL16 + 128 * 64;                     // location conv output of this CTA's rows [64 r][32 c]
+  static constexpr int SMEM_BYTES = (OP ? OFF_F16 + 64 * 64 : OFF_TMEM + 16) + 1024;
+};
+static_assert(SM<0>::SMEM_BYTES <= 232448 && SM<1>::SMEM_BYTES <= 232448, "shared memory budget");
 // element index of (row r, k) in a [rows][32] 16-bit tile stored K-major with the 64-byte swizzle: the 16-byte chunk c = k / 8 of
 // row r sits at chunk c ^ ((r >> 1) & 3)   (verified by profiles/tools/sw64_probe.cu)
 __device__ __forceinline__ int swz64(int r, int k) { return r * 32 + ((((k >> 3) ^ (r >> 1)) & 3) << 3) + (k & 7); }
@@ -153,18 +158,20 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
                        const PersistParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* wring = smem + OFF_WRING;
-  uint8_t* aring = smem + OFF_ARING;
-  float* recv = (float*)(smem + OFF_RECV);
-  float* S = (float*)(smem + OFF_S);
-  float* fbuf = (float*)(smem + OFF_F);
-  float* wcT = (float*)(smem + OFF_WCT);
-  float* hq = (float*)(smem + OFF_HQ);
-  float* wpad = (float*)(smem + OFF_WPAD);
-  float* cpad = (float*)(smem + OFF_CPAD);
-  float* e_s = (float*)(smem + OFF_E);
-  float* q_s = (float*)(smem + OFF_Q);
-  uint64_t* bars = (uint64_t*)(smem + OFF_BARS);
+  using L = SM<OP>;
+  constexpr int NS = L::NS;
+  uint8_t* wring = smem + L::OFF_WRING;
+  uint8_t* aring = smem + L::OFF_ARING;
+  float* recv = (float*)(smem + L::OFF_RECV);
+  float* S = (float*)(smem + L::OFF_S);
+  float* fbuf = (float*)(smem + L::OFF_F);
+  float* wcT = (float*)(smem + L::OFF_WCT);
+  float* hq = (float*)(smem + L::OFF_HQ);
+  float* wpad = (float*)(smem + L::OFF_WPAD);
+  float* cpad = (float*)(smem + L::OFF_CPAD);
+  float* e_s = (float*)(smem + L::OFF_E);
+  float* q_s = (float*)(smem + L::OFF_Q);
+  uint64_t* bars = (uint64_t*)(smem + L::OFF_BARS);
   uint64_t* full = bars;                  // [NS] both producers arrive (count 2) with their byte counts: ONE wait per chunk
   uint64_t* empty = full + NS;            // [NS] freed by the MMA commit; both producers wait on it
   uint64_t* acc_full = empty + NS;        // [2]
@@ -173,9 +180,12 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   uint64_t* e_full = recv_full + 2;       // [1]
   uint64_t* s_full = e_full + 1;          // [1] processed-memory tile landed in S
   uint64_t* q_full = s_full + 1;          // [1] op16: the query-projection MMA of this step has retired
-  uint16_t* wq16 = (uint16_t*)(smem + OFF_WQ16);
-  uint16_t* hq16 = (uint16_t*)(smem + OFF_HQ16);
-  uint32_t* tmem_holder = (uint32_t*)(smem + OFF_TMEM);
+  uint64_t* l_full = q_full + 1;          // [1] op16: the location-dense MMA of this step has retired
+  uint16_t* wq16 = (uint16_t*)(smem + L::OFF_WQ16);
+  uint16_t* hq16 = (uint16_t*)(smem + L::OFF_HQ16);
+  uint16_t* wl16 = (uint16_t*)(smem + L::OFF_WL16);
+  uint16_t* f16s = (uint16_t*)(smem + L::OFF_F16);
+  uint32_t* tmem_holder = (uint32_t*)(smem + L::OFF_TMEM);
 
   constexpr int ATT_CHUNKS = Chunks<OP>::ATT, DEC_CHUNKS = Chunks<OP>::DEC;     // (shadow the fp32 counts of the file scope)
   constexpr int JA_H = OP ? 1 : 2, JA_C = OP ? 5 : 10;          // attention_rnn GEMM: first chunk that needs h_att / ctx
@@ -212,6 +222,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     mbar_init(e_full, 1);
     mbar_init(s_full, 1);
     mbar_init(q_full, 1);
+    mbar_init(l_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -662,6 +673,11 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
 #pragma unroll
     for (int k = 0; k < 4; ++k) vreg[k] = s.v[lane + 32 * k];
     for (int i = atid; i < 2 * KS * NF; i += 256) wcT[i] = s.Wconv[i];
+    if (OP) {      // op16: location_dense weight as the A operand of the per-step dense MMA (M = 128 attention dims, K = 32 filters)
+      for (int i = atid; i < AD * NF; i += 256) wl16[swz64(i >> 5, i & 31)] = t2v_enc16(s.Wloc[i], opfmt);
+      for (int i = atid; i < 64 * 32; i += 256) f16s[i] = 0;
+      fence_proxy_async();
+    }
     for (int i = atid; i < PADW; i += 256) {
       const int ti = i - HALO;
       float w0 = 0.f, c0 = 0.f;
@@ -717,10 +733,12 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           bulk_load_1d(S, s.pmem + ((long long)b * Ti + i0) * AD, (uint32_t)nrow * AD * 4u, s_full);
         }
         float wl[NF];                        // location_dense weight row of attention dim a (re-read per step: the
-#pragma unroll                               // registers are needed by the context phase)
-        for (int c = 0; c < NF; c += 4) {
-          const float4 t4 = __ldg(reinterpret_cast<const float4*>(s.Wloc + a * NF + c));
-          wl[c] = t4.x; wl[c + 1] = t4.y; wl[c + 2] = t4.z; wl[c + 3] = t4.w;
+        if (!OP) {                           // registers are needed by the context phase); op16: the dense runs on the tensor core
+#pragma unroll
+          for (int c = 0; c < NF; c += 4) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(s.Wloc + a * NF + c));
+            wl[c] = t4.x; wl[c + 1] = t4.y; wl[c + 2] = t4.z; wl[c + 3] = t4.w;
+          }
         }
         // ---- location conv (2 -> 32, k = 31, zero padding) on this CTA's rows: thread = (filter c, 8 consecutive rows)
         {
@@ -742,10 +760,42 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
                 for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, xr[j + k], acc[j]);
               }
             }
+            if (OP) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) fbuf[(r0 + j) * FS + c] = acc[j];
+              for (int j = 0; j < 8; ++j) f16s[swz64(r0 + j, c)] = t2v_enc16(acc[j], opfmt);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) fbuf[(r0 + j) * FS + c] = acc[j];
+            }
           }
         }
+        if (OP) {
+          // ---- S += location dense on the tensor core: D[128 a, 64 rows] = Wloc16[a][c] * f16s[row][c] (two K=16 instructions)
+          // into TMEM columns 144..207; warp w reads attention dims 32 (w & 3) .. +31 of rows 32 (w >> 2) .. +31
+          fence_proxy_async();
+          tc_fence_before();
+          named_bar(BAR_ATT, 256);
+          tc_fence_after();
+          if (aw == 0 && elect_one()) {
+            const uint32_t fq = (opfmt == 2) ? 1u : 0u;
+            const uint32_t idl = (1u << 4) | (fq << 7) | (fq << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t ad = make_kmajor_sw64_desc(smem_u32(wl16)), bd = make_kmajor_sw64_desc(smem_u32(f16s));
+            tc_mma_f16(tmem_base + 144u, ad, bd, idl, 0u);
+            tc_mma_f16(tmem_base + 144u, ad + 2, bd + 2, idl, 1u);
+            tc_commit(l_full);
+          }
+          __syncwarp();
+          if (nrow > 0) mbar_wait(s_full, n & 1u);
+          mbar_wait(l_full, n & 1u);
+          tc_fence_after();
+          uint32_t lv[32];
+          tmem_ld32(tmem_base + ((uint32_t)((aw & 3) * 32) << 16) + 144u + (uint32_t)((aw >> 2) * 32), lv);
+          const int a2 = 32 * (aw & 3) + lane, rb = 32 * (aw >> 2);
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr)
+            if (rb + rr < nrow) S[(rb + rr) * AD + a2] += __uint_as_float(lv[rr]);
+          tc_fence_before();
+        } else {
         named_bar(BAR_ATT, 256);
         // ---- S += location dense: thread = (attention dim a, 32 rows)
         if (nrow > 0) mbar_wait(s_full, n & 1u);
@@ -765,6 +815,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
               S[rr * AD + a] = (s0 + s1) + (s2 + s3);
             }
           }
+        }
         }
         named_bar(BAR_ATT, 256);
       }
@@ -999,7 +1050,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     // ---- the last frame of the range (the loop publishes frame t-1 at the start of step t)
     const int atid = tid - 256;
     const int b = 2 * cid + (rank >> 1), hh = rank & 1;
-    float* fb = (float*)(smem + OFF_F);
+    float* fb = (float*)(smem + SM<OP>::OFF_F);
     if (atid == 0) { wait_counter(cnt_d, NCTA * (unsigned)(te - tb)); wait_counter(cnt_c, NCTA * (unsigned)(te - tb)); }
     named_bar(BAR_ATT, 256);
     if (b < B && atid < 81) {
@@ -1106,13 +1157,14 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
   static int max_clusters[4] = {-1, -1, -1, -1};
   static bool attr_set[4] = {false, false, false, false};
   const int ki = (inf ? 1 : 0) + 2 * op;
+  const int smem_bytes = op ? SM<1>::SMEM_BYTES : SM<0>::SMEM_BYTES;
   if (!attr_set[ki]) {
-    T2V_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set[ki] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(NCTA); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+  cfg.gridDim = dim3(NCTA); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
