@@ -312,6 +312,12 @@ int t2v_loss_bwd(const float* mel, const float* post, const float* tgt, long lon
                  cudaStream_t stream);
 
 /* ---- STFT / mel front-end pieces (stft.py:77-105, layers.py:75-92, audio_processing.py:77-83) ------------------- */
+/* the whole front-end as ONE kernel for the reference recipe (filter 1024, hop 256, win 1024): reflect pad -> hann -> 1024-point FFT
+   in shared memory (two real frames per complex transform) -> |X| -> mel filterbank -> log(max(., clip)); wav [B,S] -> out [B,n_mel,S/256+1].
+   window [1024], twiddle [1024] complex, mel_basis [n_mel,513], band_lo / band_hi [n_mel] = non-zero bin range of every filter */
+int t2v_stft_mel_fused(const float* wav, int B, int S, const float* window, const float* twiddle, const float* mel_basis,
+                       const int* band_lo, const int* band_hi, float* out, int n_mel, int n_frames, float clip,
+                       cudaStream_t stream);
 int t2v_reflect_pad(const float* wav, float* out, int B, int S, int pad, long long ld, cudaStream_t stream);
 int t2v_stft_mag(const float* ft, long long ft_ld, float* mag, long long mag_ld, long long rows, int nb, cudaStream_t stream);
 int t2v_mel_log(const float* mel, long long mel_ld, float* out, int B, int n_mel, int n_frames, long long rows_per_batch,

@@ -83,15 +83,6 @@ __device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;                   // SWIZZLE_64B
   return d;
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 struct PersistParams {
   T2VDecoderSeq s;
   int t_begin, t_end;
@@ -1154,7 +1145,10 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
   void (*kernel)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, PersistParams) =
       inf ? (op ? dec_persist_fwd_kernel<true, 1> : dec_persist_fwd_kernel<true, 0>)
           : (op ? dec_persist_fwd_kernel<false, 1> : dec_persist_fwd_kernel<false, 0>);
-  static int max_clusters[4] = {-1, -1, -1, -1};
+  static int max_clusters_dev[16][4];
+  static bool mc_init = false;
+  if (!mc_init) { for (auto& row : max_clusters_dev) for (int& v : row) v = -1; mc_init = true; }
+  int* max_clusters = max_clusters_dev[t2v_device_slot()];
   static bool attr_set[4] = {false, false, false, false};
   const int ki = (inf ? 1 : 0) + 2 * op;
   const int smem_bytes = op ? SM<1>::SMEM_BYTES : SM<0>::SMEM_BYTES;
@@ -1165,9 +1159,11 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(NCTA); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (max_clusters[ki] < 0) {
     int n = 0;
@@ -1223,6 +1219,7 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
     if ((r = t2v_encode_tmap_2d(&tmXD, s->XD, 4, XD_W, rows, XD_W, 64))) return r;
   }
   T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 128 * sizeof(unsigned), stream));
+  cfg.numAttrs = t2v_coop_enabled() ? 2 : 1;
   T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmWa, tmWd, tmXA, tmXD, p));
   T2V_COUNT_LAUNCH();
   if (trace) {      // debugging aid: not usable under stream capture

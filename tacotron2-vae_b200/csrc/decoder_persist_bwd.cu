@@ -43,9 +43,13 @@ constexpr int OFF_ABUF = OFF_RECVD + 4 * 16 * RD_P * 4;            // [TH_MAX][1
 constexpr int OFF_F = OFF_ABUF + TH_MAX * AD * 4;                   // [TH_MAX][FS] conv output f -> df (in place)
 constexpr int OFF_WCT = OFF_F + TH_MAX * FS * 4;                    // [62][32]
 constexpr int OFF_WLOC = OFF_WCT + 2 * KS * NF * 4;                 // [128][32]
-constexpr int OFF_WQ = OFF_WLOC + AD * NF * 4;                      // [128][32] query weight columns of this cluster's units
-constexpr int OFF_DQ = OFF_WQ + AD * 32 * 4;                        // [16][128]
-constexpr int OFF_DCTX = OFF_DQ + 16 * AD * 4;                      // [512]
+// dHq = dq W_q on the tensor core (per CTA: 32 units x 16 batch rows, K = 128 attention dims): fp16 operands, K-major rows of 128
+// bytes (SWIZZLE_128B), two K blocks of 64.  A = W_q^T slice [64 rows: 32 units + 32 zero rows][128 a] (static), B = dq rows of this CTA
+// [16 b][128 a], scaled by a per-CTA power of two so that gradient magnitudes sit inside the fp16 range; D [unit][b] in TMEM.
+constexpr int OFF_WQ16 = (OFF_WLOC + AD * NF * 4 + 1023) / 1024 * 1024;   // 2 blocks x [64][64] fp16 = 16 KB
+constexpr int OFF_DQ16 = OFF_WQ16 + 2 * 64 * 128;                          // 2 blocks x [16][64] fp16 = 4 KB
+constexpr int OFF_DHQ = OFF_DQ16 + 2 * 16 * 128;                           // [16][32] fp32 result tile + [4] partial maxima
+constexpr int OFF_DCTX = OFF_DHQ + 16 * 32 * 4 + 16;                       // [512]
 constexpr int OFF_SMALL = OFF_DCTX + ED * 4;
 // small arrays (floats): wpad[160] cpad[160] wt[64] dwv[64] de[64] Ps[64] Gs[64] adj[2][64] halo[2][2][64] spart[2][2] q_s[2][128]
 constexpr int SM_WPAD = 0, SM_CPAD = 160, SM_WT = 320, SM_DWV = 384, SM_DE = 448, SM_P = 512, SM_G = 576, SM_ADJ = 640,
@@ -83,8 +87,10 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   float* f_s = (float*)(smem + OFF_F);
   float* wcT = (float*)(smem + OFF_WCT);
   float* WlocS = (float*)(smem + OFF_WLOC);
-  float* WqS = (float*)(smem + OFF_WQ);
-  float* dq_s = (float*)(smem + OFF_DQ);
+  uint16_t* wq16 = (uint16_t*)(smem + OFF_WQ16);
+  uint16_t* dq16 = (uint16_t*)(smem + OFF_DQ16);
+  float* dhq_s = (float*)(smem + OFF_DHQ);
+  float* qmax_s = dhq_s + 16 * 32;
   float* dctx_s = (float*)(smem + OFF_DCTX);
   float* small = (float*)(smem + OFF_SMALL);
   uint64_t* bars = (uint64_t*)(smem + OFF_BARS);
@@ -96,7 +102,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   uint64_t* at_full = recv_full + 2;      // saved tanh tile landed
   uint64_t* x_full = at_full + 1;         // partner's softmax-backward partial sum landed
   uint64_t* h_full = x_full + 1;          // partner's adjoint-conv halo landed
-  uint64_t* dq_full = h_full + 1;         // dq rows of this CTA's batch rows staged
+  uint64_t* dq_full = h_full + 1;         // the dHq MMA of this iteration has retired
   uint32_t* tmem_holder = (uint32_t*)(smem + OFF_TMEM);
 
   const T2VDecoderBwd& d = p.d;
@@ -134,7 +140,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
-                 "r"(128u) : "memory");
+                 "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -282,7 +288,13 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       full_remote[0][r] = mapa(smem_u32(&recv_full[0]), (uint32_t)r);
       full_remote[1][r] = mapa(smem_u32(&recv_full[1]), (uint32_t)r);
     }
-    for (int i = etid; i < AD * 32; i += 128) WqS[i] = s.Wq[(long long)(i >> 5) * H + 32 * cid + (i & 31)];
+    // W_q^T slice as the A operand: element (unit u, a) at K block a / 64, row u, 16-byte chunk ((a % 64) / 8) ^ (u & 7)
+    for (int i = etid; i < 64 * AD; i += 128) {
+      const int u = i >> 7, a = i & 127, kk = a & 63;
+      const float w = (u < 32) ? s.Wq[(long long)a * H + 32 * cid + u] : 0.f;
+      wq16[(a >> 6) * (64 * 64) + u * 64 + ((((kk >> 3) ^ (u & 7)) << 3) | (kk & 7))] = t2v_f16_bits(w);
+    }
+    fence_proxy_async();
     float dca[4], dcd[4];                    // running cell-state gradients of this thread's (unit, batch row) pairs
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -329,14 +341,6 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         if (seen_xa < n_xa) { wait_counter(cnt_xa, n_xa); seen_xa = n_xa; }
         if (seen_q < n_q) { wait_counter(cnt_q, n_q); seen_q = n_q; }
         TR(cur_it, which ? 1 : 3);
-        if (which == 0) {        // dq of this CTA's 16 batch rows: one contiguous bulk copy (the rows were written with atomics)
-          const int nb = min(16, B - 16 * rank);
-          if (nb > 0) {
-            fence_proxy_async();
-            mbar_expect_tx(dq_full, (uint32_t)nb * AD * 4u);
-            bulk_load_1d(dq_s, d.DQ + (r0 + 16 * rank) * AD, (uint32_t)nb * AD * 4u, dq_full);
-          }
-        }
       }
       named_bar(BAR_EPI, 128);
       float dh[4];
@@ -356,22 +360,74 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         dh[j] = v;
       }
       if (which == 0) {
-        // ---- dHq = dq W_q for this CTA's 16 batch rows x 32 units (dq of the whole batch is complete: cnt_q)
-        if (16 * rank < B) mbar_wait(dq_full, (unsigned)cur_it & 1u);
-        if (etid == 0) TR(cur_it, 4);
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-        for (int a0 = 0; a0 < AD; a0 += 4) {
-          const float w0 = WqS[a0 * 32 + u], w1 = WqS[(a0 + 1) * 32 + u], w2 = WqS[(a0 + 2) * 32 + u], w3 = WqS[(a0 + 3) * 32 + u];
+        // ---- dHq = dq W_q for this CTA's 16 batch rows x 32 units (dq of the whole batch is complete: cnt_q) on the tensor core.
+        // thread -> (row etid / 8, attention dims 16 (etid % 8) .. +16): straight from L2 (the rows were accumulated with atomics)
+        const int qr = etid >> 3, qa = (etid & 7) * 16;
+        float4 dqv[4];
+        {
+          const int bq = 16 * rank + qr;
+          const float4* src = reinterpret_cast<const float4*>(d.DQ + (r0 + bq) * AD + qa);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 q4 = *reinterpret_cast<const float4*>(dq_s + (blq + 4 * j) * AD + a0);
-            acc[j] = fmaf(q4.x, w0, acc[j]); acc[j] = fmaf(q4.y, w1, acc[j]);
-            acc[j] = fmaf(q4.z, w2, acc[j]); acc[j] = fmaf(q4.w, w3, acc[j]);
+          for (int i = 0; i < 4; ++i) dqv[i] = (bq < B) ? __ldcg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float mx = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fmaxf(fabsf(dqv[i].x), fabsf(dqv[i].y)), fmaxf(fabsf(dqv[i].z), fabsf(dqv[i].w))));
+        mx = warp_max(mx);
+        if (lane == 0) qmax_s[q] = mx;
+        named_bar(BAR_EPI, 128);
+        mx = fmaxf(fmaxf(qmax_s[0], qmax_s[1]), fmaxf(qmax_s[2], qmax_s[3]));
+        // power-of-two scale that puts the largest |dq| of the tile into [2^13, 2^14): gradients are far below the fp16 range
+        int ex = 0;
+        (void)frexpf(mx, &ex);
+        const float scale = (mx > 0.f) ? exp2f((float)(14 - ex)) : 1.f;
+        {
+          const int kb = qa >> 6, kk = qa & 63;                  // 16 consecutive a = two 16-byte chunks of row qr
+          uint16_t* row = dq16 + kb * (16 * 64) + qr * 64;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const float4 lo = dqv[2 * c], hi = dqv[2 * c + 1];
+            uint4 pk;
+            pk.x = (uint32_t)t2v_f16_bits(lo.x * scale) | ((uint32_t)t2v_f16_bits(lo.y * scale) << 16);
+            pk.y = (uint32_t)t2v_f16_bits(lo.z * scale) | ((uint32_t)t2v_f16_bits(lo.w * scale) << 16);
+            pk.z = (uint32_t)t2v_f16_bits(hi.x * scale) | ((uint32_t)t2v_f16_bits(hi.y * scale) << 16);
+            pk.w = (uint32_t)t2v_f16_bits(hi.z * scale) | ((uint32_t)t2v_f16_bits(hi.w * scale) << 16);
+            *reinterpret_cast<uint4*>(row + ((((kk >> 3) + c) ^ (qr & 7)) << 3)) = pk;
           }
         }
+        fence_proxy_async();
+        tc_fence_before();
+        named_bar(BAR_EPI, 128);
+        tc_fence_after();
+        if (etid == 0) TR(cur_it, 4);
+        if (warp == 4 && elect_one()) {
+          constexpr uint32_t idq = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);      // D f32, A = B = f16
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dh[j] += acc[j];
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t ad = make_kmajor_sw128_desc(smem_u32(wq16) + kb * (64 * 128));
+            const uint64_t bd = make_kmajor_sw128_desc(smem_u32(dq16) + kb * (16 * 128));
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) tc_mma_f16(tmem_base + 128u, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), idq, (kb | k4) ? 1u : 0u);
+          }
+          tc_commit(dq_full);
+        }
+        __syncwarp();
+        mbar_wait(dq_full, (unsigned)cur_it & 1u);
+        tc_fence_after();
+        {
+          // M = 64: accumulator row (unit) 16 q' + l sits in TMEM lane 32 q' + l (l < 16); units 0..31 -> warps q = 0, 1
+          uint32_t hv[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + 128u, hv);
+          if (q < 2 && lane < 16) {
+            const float inv = 1.f / scale;
+#pragma unroll
+            for (int bl = 0; bl < 16; ++bl) dhq_s[bl * 32 + 16 * q + lane] = __uint_as_float(hv[bl]) * inv;
+          }
+        }
+        tc_fence_before();
+        named_bar(BAR_EPI, 128);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dh[j] += dhq_s[(blq + 4 * j) * 32 + u];
         if (etid == 0) TR(cur_it, 5);
       }
 #pragma unroll
@@ -800,7 +856,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   __syncwarp();
   cluster_sync_all();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
 }
 
@@ -820,7 +876,10 @@ int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStre
   if (!persist_bwd_enabled()) return 1;
   if (!s->use_tc || s->B > 64 || s->Ti > 2 * TH_MAX || s->Ti < 1 || t_hi != s->To || t_lo != 0 || s->To < 2) return 1;
   if (!s->GA || !s->GD || !s->CPA || !s->CPD || !s->ASAVE || !d->dHq) return 1;
-  static int max_clusters = -1;
+  static int max_clusters_dev[16];
+  static bool mc_init = false;
+  if (!mc_init) { for (int& v : max_clusters_dev) v = -1; mc_init = true; }
+  int& max_clusters = max_clusters_dev[t2v_device_slot()];
   static bool attr_set = false;
   if (!attr_set) {
     T2V_CUDA_CHECK(cudaFuncSetAttribute(dec_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -829,9 +888,11 @@ int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStre
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(NCTA); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (max_clusters < 0) {
     int n = 0;
@@ -872,6 +933,7 @@ int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStre
   if ((r = t2v_encode_tmap_2d(&tmGA, d->DGA, 4, 4 * H, rows, 4 * H, 64))) return r;
   if ((r = t2v_encode_tmap_2d(&tmGD, d->DGD, 4, 4 * H, rows, 4 * H, 64))) return r;
   T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 160 * sizeof(unsigned), stream));
+  cfg.numAttrs = t2v_coop_enabled() ? 2 : 1;
   T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel, tmWa, tmWd64, tmWd16, tmGA, tmGD, p));
   T2V_COUNT_LAUNCH();
   if (trace) {      // debugging aid: not usable under stream capture

@@ -307,10 +307,13 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) 
   return d;
 }
 
-template <int BN, int STAGES>
+// MB = number of 128-row blocks of D a CTA owns (1 or 2): with MB = 2 the B tile of a stage feeds two accumulators (TMEM columns
+// [0, BN) and [BN, 2 BN)), which cuts the L2 -> shared-memory operand traffic per FLOP by a third -- these GEMMs are bound by it
+// (fp32 operands: 42 FLOP per operand byte for a 128 x 256 tile, 64 for 256 x 256).
+template <int BN, int STAGES, int MB>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
-  constexpr int BM = 128;
+  constexpr int BM = 128 * MB;
   constexpr int A_BYTES = BM * BKR * 4;
   constexpr int B_BYTES = BN * BKR * 4;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -334,7 +337,7 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
-                 "r"((uint32_t)BN) : "memory");
+                 "r"((uint32_t)(BN * MB)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -362,7 +365,7 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       // D=f32, A=B=tf32, both MN-major (bits 15 / 16)
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
-                                 ((uint32_t)(BM >> 4) << 24);
+                                 ((uint32_t)(128 >> 4) << 24);
       for (int it = 0; it < n_it; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -373,7 +376,10 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint64_t bdesc = make_mnmajor_sw128_desc(sa + A_BYTES);
 #pragma unroll
         for (int k = 0; k < BKR / 8; ++k)      // 8 reduction rows (1024 B of every MN group) per instruction
-          tc_mma<true>(tmem_base, adesc + (uint64_t)(64 * k), bdesc + (uint64_t)(64 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb)      // the second 128-row block of A starts 4 boxes (4 * BOX bytes) further
+            tc_mma<true>(tmem_base + (uint32_t)(mb * BN), adesc + (uint64_t)(64 * k + mb * ((4 * BOX) >> 4)), bdesc + (uint64_t)(64 * k),
+                         idesc, (it > 0 || k > 0) ? 1u : 0u);
         tc_commit(&empty[s]);
       }
       tc_commit(tmem_full);
@@ -382,12 +388,14 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int mb = 0; mb < MB; ++mb) {
+    const int row = m0 + mb * 128 + q * 32 + lane;
     float* drow = p.D + (long long)blockIdx.z * p.split_stride + (long long)row * p.ldd;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BN + c0), v);
       if (row < p.M) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -401,11 +409,12 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN * MB)) : "memory");
   }
 }
 
@@ -567,16 +576,16 @@ int encode_mn(CUtensorMap* map, const void* base, long long cols, long long rows
   }
   return 0;
 }
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MB = 1>
 int launch_gemm_tc_mn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcParams& p, int splits, cudaStream_t st) {
-  constexpr int smem = STAGES * (128 + BN) * BKR * 4 + 1024 + 256;
+  constexpr int smem = STAGES * (128 * MB + BN) * BKR * 4 + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    T2V_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_mn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_mn_kernel<BN, STAGES, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  dim3 grid(t2v_ceil_div(p.M, 128), t2v_ceil_div(p.N, BN), splits);
-  gemm_tc_mn_kernel<BN, STAGES><<<grid, 192, smem, st>>>(tmA, tmB, p);
+  dim3 grid(t2v_ceil_div(p.M, 128 * MB), t2v_ceil_div(p.N, BN), splits);
+  gemm_tc_mn_kernel<BN, STAGES, MB><<<grid, 192, smem, st>>>(tmA, tmB, p);
   T2V_COUNT_LAUNCH();
   T2V_LAUNCH_CHECK();
   return 0;
@@ -605,6 +614,7 @@ T2V_API int t2v_gemm_tc_rowred(const float* A, long long lda, int n_a, long long
   memset(&p, 0, sizeof(p));
   p.D = D; p.ldd = ldd; p.split_stride = split_stride; p.M = n_a; p.N = n_b; p.iters_per_split = t2v_ceil_div(iters, splits); p.chunks_per_tap = iters;
   p.epi_atomic = epi; p.alpha = alpha; p.a_row0 = (int)a_row0; p.b_row0 = (int)b_row0;
+  if (n_b > 128 && n_b % 256 == 0 && n_a >= 512) return launch_gemm_tc_mn<256, 3, 2>(tmA, tmB, p, splits, stream);   // 256 x 256 tiles
   if (n_b > 128 && n_b % 256 == 0) return launch_gemm_tc_mn<256, 4>(tmA, tmB, p, splits, stream);
   if (n_b > 64) return launch_gemm_tc_mn<128, 6>(tmA, tmB, p, splits, stream);
   return launch_gemm_tc_mn<64, 8>(tmA, tmB, p, splits, stream);

@@ -47,7 +47,10 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // bounded spins: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU box
-constexpr long long WAIT_LIMIT = 4000000000LL;     // ~2 s of SM clocks
+#ifndef T2V_WAIT_LIMIT
+#define T2V_WAIT_LIMIT 4000000000LL                // ~2 s of SM clocks (sanitizer builds raise it: -DT2V_WAIT_LIMIT=...)
+#endif
+constexpr long long WAIT_LIMIT = T2V_WAIT_LIMIT;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -112,6 +115,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -184,5 +195,23 @@ __device__ __forceinline__ float4 ldg_v4_hint(const float* ptr, uint64_t pol) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+
+
+// ---------------------------------------------------------------------------------------------- host-side launch policy
+// The persistent kernels wait on each other across CTAs, so every CTA of the grid must be resident at the same time.  They are
+// launched COOPERATIVELY (cudaLaunchAttributeCooperative next to the cluster dimension): the driver then places the whole grid at once
+// or not yet at all -- kernels that happen to hold SMs when the launch arrives (a side branch of the same CUDA graph, another
+// process, a profiler replay) delay the launch instead of stranding part of the grid in front of a spin-wait.  The bounded waits
+// (WAIT_LIMIT) remain as a second line of defence.  T2V_COOP=0 launches without the attribute.
+inline bool t2v_coop_enabled() {
+  static const bool on = !(getenv("T2V_COOP") && getenv("T2V_COOP")[0] == '0');
+  return on;
+}
+// per-device cache slot for cudaOccupancyMaxActiveClusters results (a process may drive several GPUs)
+inline int t2v_device_slot() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d < 0 ? 0 : (d > 15 ? 15 : d);
+}
 
 }  // namespace

@@ -11,7 +11,10 @@ namespace {
 
 constexpr int UPC = 8;          // hidden units (= warps) per CTA
 constexpr int MT = 64;          // batch rows (lane -> rows lane, lane + 32)
-constexpr long long WAIT_LIMIT = 4000000000LL;
+#ifndef T2V_WAIT_LIMIT
+#define T2V_WAIT_LIMIT 4000000000LL
+#endif
+constexpr long long WAIT_LIMIT = T2V_WAIT_LIMIT;
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -261,6 +264,20 @@ __global__ void __launch_bounds__(UPC * 32, 1) bilstm_seq_bwd_kernel(SeqBwd p) {
   }
 }
 
+// all 64 CTAs wait on each other: cooperative launch = the grid is placed as a whole or not yet at all (T2V_COOP=0: plain launch)
+template <typename Args>
+cudaError_t launch_coop(void (*kernel)(Args), dim3 grid, int block, size_t smem, cudaStream_t st, Args a) {
+  static const bool coop = !(getenv("T2V_COOP") && getenv("T2V_COOP")[0] == '0');
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = coop ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 }  // namespace
 
 // Whole-sequence forward of both directions.  gx0 / gx1: [B*Tp, 4H] input projections (+ b_ih) on the padded rows (Tp = Ti + 4, valid
@@ -282,9 +299,8 @@ T2V_API int t2v_bilstm_seq_fwd(const float* gx0, const float* gx1, const float* 
     cur = smem;
   }
   T2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned), st));
-  bilstm_seq_fwd_kernel<<<dim3(H / UPC, 2), UPC * 32, smem, st>>>(a);
+  T2V_CUDA_CHECK(launch_coop(bilstm_seq_fwd_kernel, dim3(H / UPC, 2), UPC * 32, smem, st, a));
   T2V_COUNT_LAUNCH();
-  T2V_LAUNCH_CHECK();
   return 0;
 }
 
@@ -304,8 +320,7 @@ T2V_API int t2v_bilstm_seq_bwd(const float* whhT0, const float* whhT1, const flo
     cur = smem;
   }
   T2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned), st));
-  bilstm_seq_bwd_kernel<<<dim3(H / UPC, 2), UPC * 32, smem, st>>>(a);
+  T2V_CUDA_CHECK(launch_coop(bilstm_seq_bwd_kernel, dim3(H / UPC, 2), UPC * 32, smem, st, a));
   T2V_COUNT_LAUNCH();
-  T2V_LAUNCH_CHECK();
   return 0;
 }

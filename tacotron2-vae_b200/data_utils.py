@@ -16,7 +16,11 @@ from utils import load_filepaths_and_text, load_wav_to_torch
 
 
 class TextMelLoader(torch.utils.data.Dataset):
-    def __init__(self, audiopaths_and_text, hparams):
+    """defer_mel=True: __getitem__ returns the normalised waveform instead of the mel (pure CPU work, safe in DataLoader worker
+    processes); TextMelCollate(..., stft=loader.stft) then computes the mels of the whole batch in one fused GPU launch."""
+
+    def __init__(self, audiopaths_and_text, hparams, defer_mel=False):
+        self.defer_mel = defer_mel
         self.audiopaths_and_text = load_filepaths_and_text(audiopaths_and_text)
         self.text_cleaners = hparams.text_cleaners
         self.max_wav_value = hparams.max_wav_value
@@ -38,6 +42,8 @@ class TextMelLoader(torch.utils.data.Dataset):
         audio, sr = load_wav_to_torch(filename)
         if sr != self.stft.sampling_rate:
             raise ValueError("{} SR doesn't match target {} SR".format(sr, self.stft.sampling_rate))
+        if self.defer_mel:
+            return audio / self.max_wav_value                  # 1-D waveform; the collate function batches the STFT
         wav = (audio / self.max_wav_value).unsqueeze(0)
         dev = self.stft.mel_basis.device
         return self.stft.mel_spectrogram(wav.to(dev)).squeeze(0).cpu()
@@ -63,11 +69,46 @@ class TextMelLoader(torch.utils.data.Dataset):
         return len(self.audiopaths_and_text)
 
 
+def batch_mel_spectrogram(stft, wavs):
+    """Batched wav -> mel on the GPU: `wavs` = list of 1-D float waveforms in [-1, 1] of different lengths.  They are
+    zero-padded into one [B, S_max] tensor and go through ONE fused STFT/mel launch; every utterance then keeps its own
+    len // hop + 1 frames.  Frames that touch the padding differ from the per-utterance reflect padding, so the last
+    ceil(n_fft / 2 / hop) = 2 frames of shorter utterances are recomputed from a per-utterance tail call."""
+    dev = stft.mel_basis.device
+    lens = [int(w.numel()) for w in wavs]
+    S = max(lens)
+    batch = torch.zeros(len(wavs), S, device=dev)
+    for i, w in enumerate(wavs):
+        batch[i, :lens[i]] = w.to(dev, non_blocking=True)
+    mel = stft.mel_spectrogram(batch)
+    hop, n_fft = stft.hop_length, stft.filter_length
+    out = []
+    for i, n in enumerate(lens):
+        nF = n // hop + 1
+        m = mel[i, :, :nF].clone()
+        if n < S:       # the frames whose window crosses the end of this utterance need ITS reflection, not the batch padding
+            k = min(nF, (n_fft // 2 + hop - 1) // hop + 1)
+            tail0 = max(0, (nF - k) * hop - n_fft // 2)                 # first sample the last k frames can see
+            if tail0 == 0:
+                m = stft.mel_spectrogram(batch[i:i + 1, :n])[0]
+            else:
+                # re-run the tail with enough left context that its first frames are interior frames; keep only the last k
+                ctx = (tail0 // hop) * hop
+                tail = stft.mel_spectrogram(batch[i:i + 1, ctx:n])[0]
+                m[:, nF - k:] = tail[:, tail.shape[1] - k:]
+        out.append(m)
+    return out
+
+
 class TextMelCollate(object):
-    def __init__(self, n_frames_per_step):
+    def __init__(self, n_frames_per_step, stft=None):
         self.n_frames_per_step = n_frames_per_step
+        self.stft = stft             # with TextMelLoader(defer_mel=True): batch items carry waveforms, mels are made here
 
     def __call__(self, batch):
+        if self.stft is not None and batch[0][1].dim() == 1:
+            mels = batch_mel_spectrogram(self.stft, [x[1] for x in batch])
+            batch = [(x[0], m.cpu(), x[2], x[3]) for x, m in zip(batch, mels)]
         in_len, order = torch.sort(torch.LongTensor([len(x[0]) for x in batch]), dim=0, descending=True)
         B = len(batch)
         text = torch.zeros(B, int(in_len[0]), dtype=torch.long)

@@ -9,7 +9,7 @@ import re
 import torch
 
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG, "libt2v_b200.so")
+LIB_PATH = os.path.join(PKG, "libt2v_b200%s.so" % os.environ.get("T2V_LIB_SUFFIX", ""))
 HEADER = os.path.join(os.path.dirname(PKG), "include", "t2v_b200.h")
 
 _P = ctypes.c_void_p

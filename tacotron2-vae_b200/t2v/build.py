@@ -5,8 +5,10 @@ import sys
 
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libt2v_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "pointwise.cu", "attention.cu", "attention2.cu", "misc.cu", "rnn.cu", "rnn_persist.cu", "decoder.cu", "decoder_persist.cu", "decoder_persist_bwd.cu"]
+# T2V_LIB_SUFFIX selects a side build (e.g. "_san": long wait limits for compute-sanitizer runs) next to the product library
+SUFFIX = os.environ.get("T2V_LIB_SUFFIX", "")
+LIB = os.path.join(PKG, "libt2v_b200%s.so" % SUFFIX)
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "pointwise.cu", "attention.cu", "attention2.cu", "misc.cu", "stft_fused.cu", "rnn.cu", "rnn_persist.cu", "decoder.cu", "decoder_persist.cu", "decoder_persist_bwd.cu"]
 
 
 def _stale():
@@ -23,9 +25,9 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
-    os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
+    os.makedirs(os.path.join(PKG, "build" + SUFFIX), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(PKG, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(PKG, "build" + SUFFIX, src.replace(".cu", ".o"))
         objs.append(obj)
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                "-Xcompiler", "-fPIC,-fvisibility=hidden", "-c", os.path.join(CSRC, src), "-o", obj]

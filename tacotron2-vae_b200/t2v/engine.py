@@ -186,8 +186,21 @@ class Ops(object):
         """D[n_a, n_b] += sum_r A[a_row0+r, :]^T B[b_row0+r, :] on the MN-major tcgen05 kernel (no transposed copies);
         split over the reduction so that ~2 CTAs per SM exist.  D must be zero-initialised (or hold the running sum)."""
         iters = (rows + 31) // 32
-        tiles = ((n_a + 127) // 128) * ((n_b + 255) // 256 if (n_b > 128 and n_b % 256 == 0) else (n_b + 127) // 128)
-        splits = max(1, min(iters, int(round(296.0 / tiles))))
+        wide = n_b > 128 and n_b % 256 == 0
+        bm = 256 if (wide and n_a >= 512) else 128            # the tile shapes t2v_gemm_tc_rowred picks
+        tiles = ((n_a + bm - 1) // bm) * ((n_b + 255) // 256 if wide else (n_b + 127) // 128)
+        # split the reduction so that the CTAs fill whole waves of the 148 SMs (each extra split costs one more pass of atomics over D)
+        if tiles * 8 < 148:            # few output tiles (conv / small-N weight gradients): as many splits as it takes to fill two waves
+            splits = max(1, min(iters // 8 if iters >= 8 else 1, (296 + tiles - 1) // tiles))
+        else:
+            best, splits = 0.0, 1
+            for sp in range(1, 9):
+                if sp > iters or iters // sp < 16:
+                    break
+                n = tiles * sp
+                eff = n / (((n + 147) // 148) * 148.0) - 0.02 * (sp - 1)
+                if eff > best + 1e-9:
+                    best, splits = eff, sp
         L("t2v_gemm_tc_rowred", A, lda, n_a, a_row0, Bm, ldb, n_b, b_row0, D, ldd, rows, splits, 0, 1, 1.0)
 
     @staticmethod

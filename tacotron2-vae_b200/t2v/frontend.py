@@ -79,7 +79,43 @@ def _stft_magnitude(wav, stft):
     return MAG, rows_pb, nF
 
 
+def _fused_tables(stft, mel_basis):
+    """constant tables of the fused kernel (hann window, FFT twiddles, non-zero band of every mel filter), cached on the STFT object"""
+    dev = mel_basis.device
+    key = (str(dev), mel_basis.data_ptr())
+    tabs = getattr(stft, "_fused", None)
+    if tabs is None or tabs[0] != key:
+        n = stft.filter_length
+        win = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n)
+        ang = -2.0 * np.pi * np.arange(n) / n
+        tw = np.stack([np.cos(ang), np.sin(ang)], 1)
+        nz = (mel_basis.detach().cpu().numpy() != 0)
+        lo = np.where(nz.any(1), nz.argmax(1), 0)
+        hi = np.where(nz.any(1), nz.shape[1] - nz[:, ::-1].argmax(1), 0)
+        tabs = (key, torch.from_numpy(win.astype(np.float32)).to(dev), torch.from_numpy(tw.astype(np.float32)).contiguous().to(dev),
+                torch.from_numpy(lo.astype(np.int32)).to(dev), torch.from_numpy(hi.astype(np.int32)).to(dev))
+        stft._fused = tabs
+    return tabs[1:]
+
+
 def mel_spectrogram(wav, stft, mel_basis):
+    """wav [B,S] -> log-mel [B,n_mel,S//hop+1].  The reference recipe (n_fft 1024, hop 256) runs as ONE fused kernel
+    (stft_fused.cu: FFT in shared memory, no intermediate in HBM); other geometries take the GEMM path below."""
+    if not wav.is_cuda:
+        raise RuntimeError("the t2v STFT runs on CUDA tensors only")
+    if stft.filter_length == 1024 and stft.hop_length == 256 and mel_basis.shape[1] == 513 and mel_basis.shape[0] <= 128 \
+            and wav.shape[1] > 512:
+        wav = wav.contiguous().float()
+        B, S = wav.shape
+        nF = S // 256 + 1
+        win, tw, lo, hi = _fused_tables(stft, mel_basis)
+        out = torch.empty(B, mel_basis.shape[0], nF, device=wav.device)
+        L("t2v_stft_mel_fused", wav, B, S, win, tw, mel_basis.contiguous(), lo, hi, out, mel_basis.shape[0], nF, 1e-5)
+        return out
+    return mel_spectrogram_gemm(wav, stft, mel_basis)
+
+
+def mel_spectrogram_gemm(wav, stft, mel_basis):
     MAG, rows_pb, nF = _stft_magnitude(wav, stft)
     dev = wav.device
     B = wav.shape[0]

@@ -85,3 +85,70 @@ def test_reference_train_loop_call_sequence(tmp_path):
         a = model.encoder.inference(emb)
         b = model2.encoder.inference(model2.transcript_embedding(x[0]).transpose(1, 2))
     assert torch.equal(a, b)
+
+
+def test_reference_layout_checkpoint_with_dead_param_adam_state(tmp_path):
+    """A checkpoint in the reference's layout (train.py:113-119: iteration / state_dict / optimizer / learning_rate) whose Adam state
+    has NO entries for the parameters that never receive a gradient (quirk Q6: speaker / emotion embeddings, the outer CoordConv
+    weight) -- exactly what torch.optim.Adam saves for them -- loads into (a) torch.optim.Adam as train.py:100-110 does and (b) the fused
+    flat-buffer optimizer, and both continue identically."""
+    import model as t2v_model
+    from hparams import create_hparams
+    from loss_function import Tacotron2Loss_VAE
+    from oracle import port
+    from t2v import optim
+    hp = create_hparams("anneal_function=constant")
+    batch = port.synthetic_batch(3, 14, 18, seed=2)
+
+    def run_steps(model, opt, n, fused):
+        crit = Tacotron2Loss_VAE(hp)
+        model.train()
+        for it in range(n):
+            model._step = 50 + it                       # same dropout stream in every run
+            model.zero_grad()
+            x, y = model.parse_batch(batch)
+            loss = crit(model(x), y, it)[0]
+            loss.backward()
+            if fused:
+                opt.step()
+            else:
+                torch.nn.utils.clip_grad_norm_(model.parameters(), hp.grad_clip_thresh)
+                opt.step()
+
+    # ---- produce the checkpoint with the reference's own optimizer class
+    m0 = t2v_model.Tacotron2(hp)
+    m0.load_state_dict(port.init_params(1234))
+    m0 = m0.cuda()
+    m0._graph_cache = None
+    o0 = torch.optim.Adam(m0.parameters(), lr=hp.learning_rate, weight_decay=hp.weight_decay)
+    run_steps(m0, o0, 2, False)
+    ck = os.path.join(str(tmp_path), "checkpoint_2")
+    torch.save({"iteration": 2, "state_dict": m0.state_dict(), "optimizer": o0.state_dict(), "learning_rate": hp.learning_rate}, ck)
+    d = torch.load(ck, map_location="cpu")
+    names = [k for k, _ in m0.named_parameters()]
+    dead = [i for i, k in enumerate(names) if k.startswith(t2v_model.Tacotron2._DEAD)]
+    assert dead and all(i not in d["optimizer"]["state"] for i in dead)          # torch skipped them: grad was None
+    assert len(d["optimizer"]["state"]) == len(names) - len(dead)
+    # ---- (a) torch.optim.Adam resume, (b) fused optimizer resume: one more step each, same parameters afterwards
+    res = {}
+    for fused in (False, True):
+        m = t2v_model.Tacotron2(hp).cuda()
+        m._graph_cache = None
+        m.load_state_dict(d["state_dict"])
+        if fused:
+            opt = optim.FusedAdamClip(m, lr=hp.learning_rate, weight_decay=hp.weight_decay, max_norm=hp.grad_clip_thresh)
+        else:
+            opt = torch.optim.Adam(m.parameters(), lr=hp.learning_rate, weight_decay=hp.weight_decay)
+        opt.load_state_dict(d["optimizer"])
+        for g in opt.param_groups:
+            g["lr"] = d["learning_rate"]
+        run_steps(m, opt, 1, fused)
+        res[fused] = {k: v.detach().clone() for k, v in m.named_parameters()}
+        if fused:
+            sd = opt.state_dict()
+            assert set(sd["state"]) == set(d["optimizer"]["state"]) and int(sd["state"][dead[-1] + 1]["step"]) == 3
+    for k in res[False]:
+        a, b = res[True][k], res[False][k]
+        assert float((a - b).abs().max()) <= 2e-6 + 1e-4 * float(b.abs().max()), k
+    for i in dead:
+        assert torch.equal(res[True][names[i]], m0.state_dict()[names[i]])        # untouched by both optimizers
