@@ -259,6 +259,7 @@ def main():
     infer_step = inference_decoder_step(m, dev, a.precision) if rank == 0 else None
     bwd_step = decoder_step_backward(m, B, Ti, To, dev, a.precision) if rank == 0 else None
 
+    stft = stft_mel_roofline(dev, B, To) if rank == 0 else None
     _progress("roofline done")
     comm = None
     if world > 1:      # the gradient exchange alone: one ncclAllReduce(SUM) over the flat fp32 gradient buffer, device-timed, max over ranks
@@ -297,10 +298,39 @@ def main():
                        "l2": "per-step working set (>3 GB of saved activations) exceeds the 126 MB L2"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": launches, "comm": comm, "roofline": roof, "decoder_step_inference": infer_step, "decoder_step_backward": bwd_step, "cpu_baseline": cpu,
+            "gpu_launches": launches, "comm": comm, "roofline": roof, "decoder_step_inference": infer_step, "decoder_step_backward": bwd_step, "stft_mel": stft, "cpu_baseline": cpu,
             "clocks": sampler.summary()}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def stft_mel_roofline(dev, B, To):
+    """The mel front-end of one batch (reference TacotronSTFT.mel_spectrogram, layers.py:75-92): B waveforms of To * 256 samples ->
+    [B, 80, To + 1] log-mel, ONE fused kernel (stft_fused.cu).  Algorithmic bytes: 1024 B in + 320 B out per frame."""
+    from layers import TacotronSTFT
+    st = TacotronSTFT(1024, 256, 1024, 80, 16000, 0.0, 8000.0).to(dev)
+    wav = torch.rand(B, To * 256, device=dev) * 2 - 1
+    for _ in range(3):
+        mel = st.mel_spectrogram(wav)
+    times = []
+    for _ in range(5):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); mel = st.mel_spectrogram(wav); e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    frames = B * (To + 1)
+    ms = min(times)
+    peak = 6514.8
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:  # noqa: BLE001
+        pass
+    gbs = frames * 1344 / (ms * 1e-3) / 1e9
+    return {"kernel": "stft_mel_fused_kernel", "frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3), "bound": "hbm",
+            "algorithmic_bytes_per_frame": 1344, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+            "finite": bool(torch.isfinite(mel).all()),
+            "note": "FFT butterflies in shared memory (5 radix-4 passes with a barrier each) bound this kernel, not HBM"}
 
 
 def decoder_step_backward(m, B, Ti, To, dev, precision):

@@ -1,6 +1,7 @@
 """The call sequence of the reference's train.py (train.py:150-250: DataLoader(TextMelLoader, TextMelCollate) ->
 parse_batch -> model(x) -> criterion -> backward -> clip_grad_norm_ -> Adam.step -> validate() in eval mode ->
 save/load checkpoint) on this engine, with wav files generated on the fly (mel extraction by the t2v STFT kernels)."""
+import copy
 import os
 
 import numpy as np
@@ -139,7 +140,7 @@ def test_reference_layout_checkpoint_with_dead_param_adam_state(tmp_path):
             opt = optim.FusedAdamClip(m, lr=hp.learning_rate, weight_decay=hp.weight_decay, max_norm=hp.grad_clip_thresh)
         else:
             opt = torch.optim.Adam(m.parameters(), lr=hp.learning_rate, weight_decay=hp.weight_decay)
-        opt.load_state_dict(d["optimizer"])
+        opt.load_state_dict(copy.deepcopy(d["optimizer"]))       # (torch keeps the CPU `step` tensors and bumps them in place)
         for g in opt.param_groups:
             g["lr"] = d["learning_rate"]
         run_steps(m, opt, 1, fused)
