@@ -56,6 +56,13 @@ int t2v_gemm_tc_rowred(const float* A, long long lda, int n_a, long long a_row0,
                        long long b_row0, float* D, long long ldd, long long rows, int splits, long long split_stride,
                        int epi, float alpha, cudaStream_t stream);
 
+/* the same row reduction over 16-bit operands (fp16 / bf16 copies, kind::f16, 64 reduction rows per stage): the decoder's big weight
+   gradients dW = DG^T X from the fp16 copies the persistent loops leave behind (XA16 / XD16, DGA16 / DGD16).  alpha_dev (nullable):
+   device scalar multiplied onto alpha (the inverse gradient scale). */
+int t2v_gemm_tc_rowred16(const void* A, long long lda, int n_a, long long a_row0, const void* B, long long ldb, int n_b,
+                         long long b_row0, float* D, long long ldd, long long rows, int splits, int epi, float alpha,
+                         const float* alpha_dev, int fmt, cudaStream_t stream);
+
 /* ---- text embedding (model.py:474,528) -- integer gather, bit exact ------------------------------------------- */
 int t2v_embedding_fwd(const long long* ids, const float* table, float* out_padded, int B, int T, int C, int n_symbols,
                       int rnd, cudaStream_t stream);
@@ -262,7 +269,10 @@ int t2v_decoder_last_path(void);   /* 1: the last t2v_decoder_fwd_steps of this 
 /* re-tile a decoder-step weight matrix into the order the persistent loop kernels stream it (same number of floats):
    mode 0: Wa [4096,1792] -> WaP ; 1: Wd [4096,2560] -> WdP ; 2: WaT [1792,4096] -> WaTP ; 3: WdT [2560,4096] -> WdTP */
 int t2v_pack_step_tiles(const float* W, int mode, float* out, cudaStream_t stream);
-/* 16-bit variant for op16 (fmt 1 = fp16, 2 = bf16): modes 0 / 1 only, K chunks of 64 columns */
+/* power-of-two scale that maps max |x| to 2^target_log2: out[0] = s, out[1] = 1 / s (out[2..3] scratch); keeps fp16 copies of
+   gradients (~1e-8) inside the fp16 range without touching their significands */
+int t2v_grad_scale(const float* x, long long n, int target_log2, float* out, cudaStream_t stream);
+/* 16-bit variant for op16 (fmt 1 = fp16, 2 = bf16): K chunks of 64 columns; modes 0 / 1 forward tiles, 2 / 3 backward tiles (W^T) */
 int t2v_pack_step_tiles16(const float* W, int mode, void* out, int fmt, cudaStream_t stream);
 /* strided fp32 -> 16-bit conversion (fmt 1 = fp16, 2 = bf16), e.g. the prenet columns of XA into XA16 */
 int t2v_cvt16_2d(const float* src, long long s_ld, void* dst, long long d_ld, long long rows, int cols, int fmt,
@@ -285,8 +295,14 @@ typedef struct T2VDecoderBwd {
   float *dHq;                    /* scratch [B,1024] */
   float *dv_part, *dwloc_part, *dwconv_part;   /* [B*nchunk,128], [B*nchunk,128*32], [B*nchunk,32*2*31] accumulators (zero-init), nchunk = t2v_attn2_chunks(Ti) */
   const float *WaTP, *WdTP;      /* optional (NULL = unused): WaT / WdT re-tiled by t2v_pack_step_tiles (modes 2 / 3) */
+  int op16;                      /* 1: the two dX GEMMs of the loop run on fp16 copies (kind::f16): */
+  void *DGA16, *DGD16;           /*   out: gate gradients x dg_scale[0] as saturating fp16, [To,B,4096] each (also the operands of the
+                                      16-bit weight-gradient GEMMs after the loop) */
+  const void *WaTP16, *WdTP16;   /*   fp16 re-tiled W^T (t2v_pack_step_tiles16 modes 2 / 3) */
+  const float* dg_scale;         /*   device [2] = {s, 1/s}: power-of-two gradient scale (t2v_grad_scale) */
 } T2VDecoderBwd;
 int t2v_decoder_bwd_steps(const T2VDecoderBwd* s, int t_hi, int t_lo, cudaStream_t stream);  /* t = t_hi-1 .. t_lo */
+int t2v_decoder_last_bwd_path(void);   /* 1: the last t2v_decoder_bwd_steps of this thread enqueued the persistent kernel (DGA16 / DGD16 valid) */
 
 typedef struct T2VDecoderInfer {
   T2VDecoderSeq f;

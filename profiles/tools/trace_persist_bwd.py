@@ -10,7 +10,7 @@ from t2v import engine
 B, Ti, To = (int(x) for x in sys.argv[1:4]) if len(sys.argv) > 3 else (64, 120, 400)
 dev = torch.device("cuda")
 P = {k: v.to(dev) for k, v in port.init_params(1234).items()}
-ops = engine.Ops("tf32")
+ops = engine.Ops(sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].isdigit() else "fp16")
 mem = torch.randn(B, Ti, 512, device=dev) * 0.5
 mel = torch.randn(B, 80, To, device=dev) * 2 - 5
 in_len = torch.full((B,), Ti, device=dev, dtype=torch.long)

@@ -241,6 +241,8 @@ __global__ void stop_flags_kernel(const float* __restrict__ O, long long ld, int
 // 0 when it issued the per-step launches
 static thread_local int g_last_path = 0;
 T2V_API int t2v_decoder_last_path(void) { return g_last_path; }
+static thread_local int g_last_bwd_path = 0;
+T2V_API int t2v_decoder_last_bwd_path(void) { return g_last_bwd_path; }     // same for t2v_decoder_bwd_steps (DGA16 / DGD16 valid)
 
 T2V_API int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream) {
   T2V_ARG_CHECK(s && s->B > 0 && s->Ti > 0 && s->To > 0, "shape");
@@ -297,8 +299,10 @@ T2V_API int t2v_decoder_bwd_steps(const T2VDecoderBwd* d, int t_hi, int t_lo, cu
   const T2VDecoderSeq* s = &d->f;
   T2V_ARG_CHECK(s->B > 0 && s->Ti > 0 && s->To > 0, "shape");
   T2V_ARG_CHECK(t_lo >= 0 && t_hi <= s->To && t_lo <= t_hi, "step range");
+  g_last_bwd_path = 0;
   if (!getenv("T2V_STEP_PROFILE")) {
     const int r = t2v_decoder_bwd_persist(d, t_hi, t_lo, st);      // the whole reverse loop as one persistent kernel; 1 = n/a
+    if (r == 0) g_last_bwd_path = 1;
     if (r != 1) return r;
   }
   const bool tc = s->use_tc != 0;

@@ -1097,13 +1097,23 @@ __global__ void pack_step_tiles16_kernel(const float* __restrict__ W, int mode, 
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 >= n4) return;
   const int kk = (int)(i4 & 15) * 4;
-  const long long row = i4 >> 4;                 // tile * 128 + m
-  const int nch = mode ? Chunks<1>::DEC : Chunks<1>::ATT, ld = mode ? XD_W : XA_W;
-  const int m = (int)(row & 127);
-  const long long tile = row >> 7;
-  const int j = (int)(tile % nch), cr = (int)(tile / nch), rank = cr & 3, c = cr >> 2;
-  const int kofs = mode ? dec_kofs16(j, rank) : att_kofs16(j, rank);
-  const float4 v = *reinterpret_cast<const float4*>(W + (long long)((m >> 5) * H + 32 * c + (m & 31)) * ld + kofs + kk);
+  const long long row = i4 >> 4;                 // tile * rows_per_tile + m
+  long long src;
+  if (mode < 2) {
+    const int nch = mode ? Chunks<1>::DEC : Chunks<1>::ATT, ld = mode ? XD_W : XA_W;
+    const int m = (int)(row & 127);
+    const long long tile = row >> 7;
+    const int j = (int)(tile % nch), cr = (int)(tile / nch), rank = cr & 3, c = cr >> 2;
+    const int kofs = mode ? dec_kofs16(j, rank) : att_kofs16(j, rank);
+    src = (long long)((m >> 5) * H + 32 * c + (m & 31)) * ld + kofs + kk;
+  } else {       // backward tiles from W^T [XA_W | XD_W, 4096]: [cluster][rank][16 chunks][output column of the cluster][64 gate rows]
+    const int rows = (mode == 3) ? XD_W / NCLUSTER : XA_W / NCLUSTER;
+    const int m = (int)(row % rows);
+    const long long tile = row / rows;
+    const int j = (int)(tile & 15), cr = (int)(tile >> 4), rank = cr & 3, c = cr >> 2;
+    src = (long long)(rows * c + m) * (4 * H) + 1024 * rank + 64 * j + kk;
+  }
+  const float4 v = *reinterpret_cast<const float4*>(W + src);
   uint2 o;
   o.x = (uint32_t)t2v_enc16(v.x, fmt) | ((uint32_t)t2v_enc16(v.y, fmt) << 16);
   o.y = (uint32_t)t2v_enc16(v.z, fmt) | ((uint32_t)t2v_enc16(v.w, fmt) << 16);
@@ -1116,6 +1126,22 @@ __global__ void cvt16_2d_kernel(const float* __restrict__ src, long long s_ld, u
   const long long r = i / cols;
   const int c = (int)(i % cols);
   dst[r * d_ld + c] = t2v_enc16(src[r * s_ld + c], fmt);
+}
+
+// max |x| -> power-of-two scale (t2v_grad_scale)
+__global__ void absmax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ out_bits) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));     // non-negative floats order like their bit patterns
+}
+__global__ void scale_from_max_kernel(float* out, int target_log2) {
+  const float m = out[2];
+  int ex = 0;
+  (void)frexpf(m, &ex);                          // m in [2^(ex-1), 2^ex)
+  const float sc = (m > 0.f && isfinite(m)) ? exp2f((float)(target_log2 - ex)) : 1.f;
+  out[0] = sc;
+  out[1] = 1.f / sc;
 }
 
 bool persist_enabled() {      // read per call: the tests flip T2V_PERSIST to compare against the per-step launches
@@ -1254,9 +1280,19 @@ int t2v_decoder_infer_persist(const T2VDecoderInfer* d, int t_begin, int t_end, 
 }
 
 T2V_API int t2v_pack_step_tiles16(const float* W, int mode, void* out, int fmt, cudaStream_t stream) {
-  T2V_ARG_CHECK(W && out && (mode == 0 || mode == 1) && (fmt == 1 || fmt == 2), "mode 0..1, fmt 1 (fp16) / 2 (bf16)");
-  const long long n4 = (long long)4 * H * (mode == 0 ? XA_W : XD_W) / 4;
+  T2V_ARG_CHECK(W && out && mode >= 0 && mode <= 3 && (fmt == 1 || fmt == 2), "mode 0..3, fmt 1 (fp16) / 2 (bf16)");
+  const long long n4 = (long long)4 * H * ((mode == 0 || mode == 2) ? XA_W : XD_W) / 4;
   pack_step_tiles16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(W, mode, reinterpret_cast<uint16_t*>(out), fmt, n4);
+  T2V_COUNT_LAUNCH();
+  T2V_LAUNCH_CHECK();
+  return 0;
+}
+T2V_API int t2v_grad_scale(const float* x, long long n, int target_log2, float* out, cudaStream_t stream) {
+  T2V_ARG_CHECK(x && out && n > 0 && target_log2 >= -8 && target_log2 <= 15, "shape / target");
+  T2V_CUDA_CHECK(cudaMemsetAsync(out, 0, 4 * sizeof(float), stream));
+  absmax_kernel<<<296, 256, 0, stream>>>(x, n, reinterpret_cast<unsigned*>(out + 2));
+  T2V_COUNT_LAUNCH();
+  scale_from_max_kernel<<<1, 1, 0, stream>>>(out, target_log2);
   T2V_COUNT_LAUNCH();
   T2V_LAUNCH_CHECK();
   return 0;

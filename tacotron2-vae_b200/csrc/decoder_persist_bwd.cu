@@ -31,7 +31,12 @@ constexpr int CL = 4, NCLUSTER = 32, NCTA = CL * NCLUSTER, NTHREADS = 512;
 constexpr int XA_CPC = XA_W / NCLUSTER, XD_CPC = XD_W / NCLUSTER;   // 56 / 80 output columns per cluster
 constexpr int NS = 5;                          // ring depth: a stage = one K chunk: W^T tile (<= 80 rows, 10 KB) + gate gradients (8 KB)
 constexpr int W_PART = 80 * 128, A_STAGE = 64 * 128, STAGE = W_PART + A_STAGE;
-constexpr int KCH = 32;                        // 32-wide K chunks per CTA and GEMM (K slice = 4096 / 4)
+constexpr int KCH32 = 32;                      // fp32 storage: 32-wide K chunks per CTA and GEMM (K slice = 4096 / 4)
+// op16: the W^T tiles and the gate gradients stream as fp16 copies (kind::f16), 64 K columns per 128-byte row -> 16 chunks of the
+// same bytes.  The gate gradients are ~1e-8: they are multiplied by a power-of-two scale (device scalar, derived from max |dO| by
+// t2v_grad_scale) before the saturating fp16 conversion and the dX rows are unscaled in fp32, so the fp16 mode keeps tf32's 11-bit
+// significand on both operands and only the RANGE is managed.
+template <int OP> struct KC { static constexpr int N = OP ? 16 : 32, W = OP ? 64 : 32; };
 constexpr int RA_P = 64, RD_P = 80;            // column pitch of the exchange slots [src][batch row 16][cols]
 constexpr int TH_MAX = 64, FS = 36;
 constexpr int BAR_EPI = 1, BAR_ATT = 2;
@@ -60,6 +65,12 @@ constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
+__device__ __forceinline__ uint16_t f16_sat(float x) {      // round to nearest, clamp to +-65504 instead of producing inf
+  uint16_t h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return h;
+}
+
 struct BwdParams {
   T2VDecoderBwd d;
   unsigned* counters;      // [0] DGD[t] complete, [32] dXD[t], [64] dq[t], [96] DGA[t], [128] DXA[t]
@@ -68,10 +79,13 @@ struct BwdParams {
   int rotate;              // rotate the chunk order per cluster
   int packed;              // the weight tensor maps describe the re-tiled copies (contiguous boxes)
   int wa_hint, wd_hint;
+  const float* scale;      // op16: [2] = {s, 1 / s}
   long long* trace;        // T2V_PERSIST_TRACE: [2 CTAs][TRACE_STEPS][32] clock64 stamps, else nullptr
+  long long* gtrace;       // T2V_PERSIST_TRACE: [NCTA][8] %globaltimer stamps (ns, comparable ACROSS CTAs) of iteration TRACE_I0
 };
 constexpr int TRACE_I0 = 100, TRACE_STEPS = 4, TRACE_CTA_B = 77;
 
+template <int OP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_constant__ CUtensorMap tmWd64,
                        const __grid_constant__ CUtensorMap tmWd16, const __grid_constant__ CUtensorMap tmGA,
@@ -105,8 +119,12 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   uint64_t* dq_full = h_full + 1;         // the dHq MMA of this iteration has retired
   uint32_t* tmem_holder = (uint32_t*)(smem + OFF_TMEM);
 
+  constexpr int KCH = KC<OP>::N, CKW = KC<OP>::W;
   const T2VDecoderBwd& d = p.d;
   const T2VDecoderSeq& s = d.f;
+  const float g_scale = OP ? p.scale[0] : 1.f, g_inv = OP ? p.scale[1] : 1.f;
+  uint16_t* const dga16 = reinterpret_cast<uint16_t*>(d.DGA16);
+  uint16_t* const dgd16 = reinterpret_cast<uint16_t*>(d.DGD16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_ctarank();
   const int cid = blockIdx.x / CL;
@@ -120,6 +138,13 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   // DIFFERENT gate-gradient tiles instead of all hitting the same 64 L2 lines
   const int rot = p.rotate ? cid : 0;
   const int trace_slot = (blockIdx.x == 0) ? 0 : ((blockIdx.x == TRACE_CTA_B) ? 1 : -1);
+  auto GT = [&](int it, int ev) {
+    if (p.gtrace && it == TRACE_I0) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      p.gtrace[blockIdx.x * 8 + ev] = (long long)ns;
+    }
+  };
   auto TR = [&](int it, int ev) {
     if (p.trace && trace_slot >= 0 && it >= TRACE_I0 && it < TRACE_I0 + TRACE_STEPS)
       p.trace[((long long)trace_slot * TRACE_STEPS + (it - TRACE_I0)) * 32 + ev] = clock64();
@@ -212,11 +237,11 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         const int t = To - 1 - it, td = t - 1;
         if (td >= 0) {
           need(cnt_gd, seen_gd, NCTA * (unsigned)(it + 2));
-          for (int j = 0; j < KCH; ++j) load_a(&tmGD, 1024 * rank + 32 * ((j + rot) & (KCH - 1)), td * B);
+          for (int j = 0; j < KCH; ++j) load_a(&tmGD, 1024 * rank + CKW * ((j + rot) & (KCH - 1)), td * B);
         }
         if (it >= 0) {
           need(cnt_ga, seen_ga, NCTA * (unsigned)(it + 1));
-          for (int j = 0; j < KCH; ++j) load_a(&tmGA, 1024 * rank + 32 * ((j + rot) & (KCH - 1)), t * B);
+          for (int j = 0; j < KCH; ++j) load_a(&tmGA, 1024 * rank + CKW * ((j + rot) & (KCH - 1)), t * B);
         }
       }
     }
@@ -226,8 +251,9 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     // about one bench run in four die with "unspecified launch failure": tcgen05.mma from two threads into the same TMEM
     // columns is not ordered by anything, so this stays a single issuer.
     {
-      constexpr uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
-      constexpr uint32_t idesc128 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t fmt = OP ? 0u : 2u;       // fp16 : tf32
+      constexpr uint32_t idesc64 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+      constexpr uint32_t idesc128 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int st = 0;
       uint32_t ph = 0;
       const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(ring));
@@ -252,7 +278,8 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
             const uint64_t bdesc = bdesc0 + (uint64_t)(st * (STAGE >> 4));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+              if (OP) tc_mma_f16(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+              else tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
             if (p.dbg_skip & 4) {        // timing experiment: twice the tensor work per chunk
 #pragma unroll
               for (int k = 0; k < 4; ++k) tc_mma_tf32(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
@@ -341,6 +368,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         if (seen_xa < n_xa) { wait_counter(cnt_xa, n_xa); seen_xa = n_xa; }
         if (seen_q < n_q) { wait_counter(cnt_q, n_q); seen_q = n_q; }
         TR(cur_it, which ? 1 : 3);
+        GT(cur_it, which ? 1 : 3);
       }
       named_bar(BAR_EPI, 128);
       float dh[4];
@@ -450,14 +478,18 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         dcs[j] = dc * fg;
         if (b < B) {
           float* dg = DG + (r0 + b) * 4 * H + jg;
-          dg[0] = t2v_rnd(dc * gg * ig * (1.f - ig), rnd);
-          dg[H] = t2v_rnd(dc * scp[j] * fg * (1.f - fg), rnd);
-          dg[2 * H] = t2v_rnd(dc * ig * (1.f - gg * gg), rnd);
-          dg[3 * H] = t2v_rnd(dhh * tc * og * (1.f - og), rnd);
+          const float d0 = dc * gg * ig * (1.f - ig), d1 = dc * scp[j] * fg * (1.f - fg);
+          const float d2 = dc * ig * (1.f - gg * gg), d3 = dhh * tc * og * (1.f - og);
+          dg[0] = t2v_rnd(d0, rnd); dg[H] = t2v_rnd(d1, rnd); dg[2 * H] = t2v_rnd(d2, rnd); dg[3 * H] = t2v_rnd(d3, rnd);
+          if (OP) {
+            uint16_t* dg16 = (which ? dgd16 : dga16) + (r0 + b) * 4 * H + jg;
+            dg16[0] = f16_sat(d0 * g_scale); dg16[H] = f16_sat(d1 * g_scale);
+            dg16[2 * H] = f16_sat(d2 * g_scale); dg16[3 * H] = f16_sat(d3 * g_scale);
+          }
         }
       }
       named_bar(BAR_EPI, 128);
-      if (etid == 0) { signal_counter(which ? cnt_gd : cnt_ga); TR(cur_it, which ? 2 : 6); }
+      if (etid == 0) { GT(cur_it, which ? 5 : 6); signal_counter(which ? cnt_gd : cnt_ga); TR(cur_it, which ? 2 : 6); }
     };
 
     // ---- GEMM epilogue: drain TMEM, exchange the split-K partials (16 batch rows per rank), sum, write dX rows
@@ -524,6 +556,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           float4 o;
           o.x = (x0.x + x1.x) + (x2.x + x3.x); o.y = (x0.y + x1.y) + (x2.y + x3.y);
           o.z = (x0.z + x1.z) + (x2.z + x3.z); o.w = (x0.w + x1.w) + (x2.w + x3.w);
+          if (OP) { o.x *= g_inv; o.y *= g_inv; o.z *= g_inv; o.w *= g_inv; }
           if (b < B) *reinterpret_cast<float4*>(out + ((long long)ts * B + b) * ld + NC * cid + 4 * c4) = o;
         }
       }
@@ -638,6 +671,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         if (seen_xd < n_xd) { wait_counter(cnt_xd, n_xd); seen_xd = n_xd; }
         if (seen_xa < n_xa) { wait_counter(cnt_xa, n_xa); seen_xa = n_xa; }
         TR(it, 17);
+        GT(it, 0);
       }
       named_bar(BAR_ATT, 256);
       if (active) {
@@ -724,7 +758,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         if (atid < AD) atomicAdd(d.DQ + ((long long)t * B + b) * AD + atid, q_s[atid] + q_s[128 + atid]);
       }
       named_bar(BAR_ATT, 256);
-      if (atid == 0) { signal_counter(cnt_q); TR(it, 23); }
+      if (atid == 0) { GT(it, 2); signal_counter(cnt_q); TR(it, 23); GT(it, 4); }
       // ================= off the critical path: weight gradients of the location layer, adjoint conv for step t-1
       if (active) {
         // ---- dW_loc[a][c] += sum_rows dpre[row][a] f[row][c]   (thread: a, 16 of the 32 filters, all rows)
@@ -876,14 +910,21 @@ int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStre
   if (!persist_bwd_enabled()) return 1;
   if (!s->use_tc || s->B > 64 || s->Ti > 2 * TH_MAX || s->Ti < 1 || t_hi != s->To || t_lo != 0 || s->To < 2) return 1;
   if (!s->GA || !s->GD || !s->CPA || !s->CPD || !s->ASAVE || !d->dHq) return 1;
-  static int max_clusters_dev[16];
+  const int op = d->op16 ? 1 : 0;
+  if (op && (!d->DGA16 || !d->DGD16 || !d->WaTP16 || !d->WdTP16 || !d->dg_scale)) {
+    t2v_set_error("op16 backward needs DGA16 / DGD16 / WaTP16 / WdTP16 / dg_scale");
+    return -1;
+  }
+  void (*kernel)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, BwdParams) =
+      op ? dec_persist_bwd_kernel<1> : dec_persist_bwd_kernel<0>;
+  static int max_clusters_dev[16][2];
   static bool mc_init = false;
-  if (!mc_init) { for (int& v : max_clusters_dev) v = -1; mc_init = true; }
-  int& max_clusters = max_clusters_dev[t2v_device_slot()];
-  static bool attr_set = false;
-  if (!attr_set) {
-    T2V_CUDA_CHECK(cudaFuncSetAttribute(dec_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+  if (!mc_init) { for (auto& row : max_clusters_dev) for (int& v : row) v = -1; mc_init = true; }
+  int& max_clusters = max_clusters_dev[t2v_device_slot()][op];
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[op]) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set[op] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -896,7 +937,7 @@ int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStre
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (max_clusters < 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, dec_persist_bwd_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
     max_clusters = n;
   }
   if (max_clusters < NCLUSTER) return 1;
@@ -910,31 +951,45 @@ int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStre
   p.two_issuers = 0;       // removed (see the MMA issuer comment in the kernel)
   p.wa_hint = env_int("T2V_PERSIST_BWD_WA_HINT", 1);
   p.wd_hint = env_int("T2V_PERSIST_BWD_WD_HINT", 2);
+  p.scale = d->dg_scale;
   p.trace = nullptr;
+  p.gtrace = nullptr;
   const bool trace = getenv("T2V_PERSIST_TRACE") != nullptr && s->To >= TRACE_I0 + TRACE_STEPS + 2;
   const size_t trace_bytes = 2 * TRACE_STEPS * 32 * sizeof(long long);
   if (trace) {
     T2V_CUDA_CHECK(cudaMalloc(&p.trace, trace_bytes));
     T2V_CUDA_CHECK(cudaMemsetAsync(p.trace, 0, trace_bytes, stream));
+    T2V_CUDA_CHECK(cudaMalloc(&p.gtrace, NCTA * 8 * sizeof(long long)));
+    T2V_CUDA_CHECK(cudaMemsetAsync(p.gtrace, 0, NCTA * 8 * sizeof(long long), stream));
   }
   CUtensorMap tmWa, tmWd64, tmWd16, tmGA, tmGD;
   const long long rows = (long long)s->To * s->B;
   int r;
   p.packed = (d->WaTP && d->WdTP && env_int("T2V_PERSIST_PACKED", 1)) ? 1 : 0;
-  if (p.packed) {
-    if ((r = t2v_encode_tmap_2d(&tmWa, d->WaTP, 4, 32, (long long)NCTA * KCH * XA_CPC, 32, XA_CPC))) return r;
-    if ((r = t2v_encode_tmap_2d(&tmWd64, d->WdTP, 4, 32, (long long)NCTA * KCH * XD_CPC, 32, 64))) return r;
-    if ((r = t2v_encode_tmap_2d(&tmWd16, d->WdTP, 4, 32, (long long)NCTA * KCH * XD_CPC, 32, 16))) return r;
+  if (op) {
+    p.packed = 1;
+    if ((r = t2v_encode_tmap_2d(&tmWa, d->WaTP16, 2, 64, (long long)NCTA * KC<1>::N * XA_CPC, 64, XA_CPC))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmWd64, d->WdTP16, 2, 64, (long long)NCTA * KC<1>::N * XD_CPC, 64, 64))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmWd16, d->WdTP16, 2, 64, (long long)NCTA * KC<1>::N * XD_CPC, 64, 16))) return r;
+  } else if (p.packed) {
+    if ((r = t2v_encode_tmap_2d(&tmWa, d->WaTP, 4, 32, (long long)NCTA * KCH32 * XA_CPC, 32, XA_CPC))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmWd64, d->WdTP, 4, 32, (long long)NCTA * KCH32 * XD_CPC, 32, 64))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmWd16, d->WdTP, 4, 32, (long long)NCTA * KCH32 * XD_CPC, 32, 16))) return r;
   } else {
     if ((r = t2v_encode_tmap_2d(&tmWa, d->WaT, 4, 4 * H, XA_W, 4 * H, XA_CPC))) return r;
     if ((r = t2v_encode_tmap_2d(&tmWd64, d->WdT, 4, 4 * H, XD_W, 4 * H, 64))) return r;
     if ((r = t2v_encode_tmap_2d(&tmWd16, d->WdT, 4, 4 * H, XD_W, 4 * H, 16))) return r;
   }
-  if ((r = t2v_encode_tmap_2d(&tmGA, d->DGA, 4, 4 * H, rows, 4 * H, 64))) return r;
-  if ((r = t2v_encode_tmap_2d(&tmGD, d->DGD, 4, 4 * H, rows, 4 * H, 64))) return r;
+  if (op) {
+    if ((r = t2v_encode_tmap_2d(&tmGA, d->DGA16, 2, 4 * H, rows, 4 * H, 64))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmGD, d->DGD16, 2, 4 * H, rows, 4 * H, 64))) return r;
+  } else {
+    if ((r = t2v_encode_tmap_2d(&tmGA, d->DGA, 4, 4 * H, rows, 4 * H, 64))) return r;
+    if ((r = t2v_encode_tmap_2d(&tmGD, d->DGD, 4, 4 * H, rows, 4 * H, 64))) return r;
+  }
   T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 160 * sizeof(unsigned), stream));
   cfg.numAttrs = t2v_coop_enabled() ? 2 : 1;
-  T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dec_persist_bwd_kernel, tmWa, tmWd64, tmWd16, tmGA, tmGD, p));
+  T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmWa, tmWd64, tmWd16, tmGA, tmGD, p));
   T2V_COUNT_LAUNCH();
   if (trace) {      // debugging aid: not usable under stream capture
     static const char* names[31] = {"E:D1 start", "E:D1 inputs seen", "E:D1 DGD signalled", "E:A2 dq seen", "E:A2 dq staged",
@@ -947,6 +1002,24 @@ int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStre
     T2V_CUDA_CHECK(cudaStreamSynchronize(stream));
     T2V_CUDA_CHECK(cudaMemcpy(h, p.trace, trace_bytes, cudaMemcpyDeviceToHost));
     cudaFree(p.trace);
+    {      // cross-CTA view of one iteration (global timer, ns): who signals late, who sees the counters late
+      static long long g[NCTA * 8];
+      T2V_CUDA_CHECK(cudaMemcpy(g, p.gtrace, sizeof(g), cudaMemcpyDeviceToHost));
+      cudaFree(p.gtrace);
+      static const char* gn[8] = {"T:inputs seen", "E:D1 inputs seen", "T:dq signal begin", "E:A2 inputs (dq) seen", "T:dq signal done",
+                                  "E:D1 DGD signal begin", "E:A2 DGA signal begin", ""};
+      long long base = 0;
+      for (int c = 0; c < NCTA; ++c) if (g[c * 8 + 0] && (!base || g[c * 8 + 0] < base)) base = g[c * 8 + 0];
+      fprintf(stderr, "[t2v persist bwd gtrace] iteration %d, ns relative to the earliest 'T:inputs seen'; per event: min / median / max (CTA of max)\n", TRACE_I0);
+      for (int ev = 0; ev < 7; ++ev) {
+        long long v[NCTA]; int arg = 0;
+        for (int c = 0; c < NCTA; ++c) { v[c] = g[c * 8 + ev] - base; if (v[c] > v[arg]) arg = c; }
+        long long srt[NCTA];
+        memcpy(srt, v, sizeof(srt));
+        for (int i = 1; i < NCTA; ++i) { long long x = srt[i]; int j = i - 1; while (j >= 0 && srt[j] > x) { srt[j + 1] = srt[j]; --j; } srt[j + 1] = x; }
+        fprintf(stderr, "  %-26s %7lld %7lld %7lld  (CTA %d)   p90 %lld\n", gn[ev], srt[0], srt[NCTA / 2], srt[NCTA - 1], arg, srt[NCTA * 9 / 10]);
+      }
+    }
     for (int c = 0; c < 2; ++c) {
       const long long base = h[(c * TRACE_STEPS) * 32 + 17];     // "inputs seen" of the first traced iteration
       fprintf(stderr, "[t2v persist bwd trace] CTA %d: SM clocks relative to 'T:inputs seen' of iteration %d\n", c ? TRACE_CTA_B : 0, TRACE_I0);

@@ -418,6 +418,125 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same row reduction over 16-bit operands (fp16 / bf16, kind::f16).  For 2-byte MN-major operands the plain 128-byte swizzle
+// is the accepted layout (UMMA layout type 2, TMA SWIZZLE_128B): a box is {64 elements of MN (128 B), BKR16 reduction rows}, LBO = one box,
+// SBO = 1024 B (8 rows), one K=16 instruction = two atoms -> +2048 B per instruction (profiles/tools/mn16_probe.cu).
+constexpr int BKR16 = 64;
+__device__ __forceinline__ uint64_t make_mnmajor16_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((BKR16 * 128) >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+template <int BN, int STAGES, int MB>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_mn16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p, int fmt_bf16) {
+  constexpr int BM = 128 * MB;
+  constexpr int BOX = 64 * BKR16 * 2;                    // 8 KB
+  constexpr int A_BYTES = (BM / 64) * BOX;
+  constexpr int B_BYTES = (BN / 64) * BOX;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_holder = (uint32_t*)(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int it0 = blockIdx.z * p.iters_per_split;
+  const int n_it = min(p.iters_per_split, p.chunks_per_tap - it0);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                 "r"((uint32_t)(BN * MB)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        const int r = (it0 + it) * BKR16;
+        uint8_t* sa = smem + s * STAGE_BYTES;
+#pragma unroll
+        for (int g = 0; g < BM / 64; ++g) tma_load_2d(sa + g * BOX, &tmA, m0 + 64 * g, p.a_row0 + r, &full[s]);
+#pragma unroll
+        for (int g = 0; g < BN / 64; ++g) tma_load_2d(sa + A_BYTES + g * BOX, &tmB, n0 + 64 * g, p.b_row0 + r, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t fmt = fmt_bf16 ? 1u : 0u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_mnmajor16_desc(sa);
+        const uint64_t bdesc = make_mnmajor16_desc(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKR16 / 16; ++k)
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb)      // the second 128-row block of A starts 2 boxes further
+            tc_mma<false>(tmem_base + (uint32_t)(mb * BN), adesc + (uint64_t)(128 * k + mb * ((2 * BOX) >> 4)), bdesc + (uint64_t)(128 * k),
+                          idesc, (it > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&empty[s]);
+      }
+      tc_commit(tmem_full);
+    }
+  } else if (n_it > 0) {
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const float alpha = p.alpha * (p.alpha_dev ? *p.alpha_dev : 1.f);
+    const int q = warp & 3;
+#pragma unroll 1
+    for (int mb = 0; mb < MB; ++mb) {
+      const int row = m0 + mb * 128 + q * 32 + lane;
+      float* drow = p.D + (long long)row * p.ldd;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BN + c0), v);
+        if (row < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = n0 + c0 + j;
+            if (col < p.N) {
+              const float o = __uint_as_float(v[j]) * alpha;
+              if (p.epi_atomic == 1) atomicAdd(drow + col, o);
+              else if (p.epi_atomic == 2) drow[col] += o;
+              else drow[col] = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN * MB)) : "memory");
+  }
+}
+
 template <int BN, int ESIZE>
 constexpr int stages_for() { return (BN == 256) ? 4 : (BN == 128 ? 6 : 8); }
 
@@ -618,4 +737,57 @@ T2V_API int t2v_gemm_tc_rowred(const float* A, long long lda, int n_a, long long
   if (n_b > 128 && n_b % 256 == 0) return launch_gemm_tc_mn<256, 4>(tmA, tmB, p, splits, stream);
   if (n_b > 64) return launch_gemm_tc_mn<128, 6>(tmA, tmB, p, splits, stream);
   return launch_gemm_tc_mn<64, 8>(tmA, tmB, p, splits, stream);
+}
+
+namespace {
+int encode_mn16(CUtensorMap* map, const void* base, long long cols, long long rows, long long ld) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) { t2v_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -2; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld * 2)};
+  cuuint32_t box[2] = {64u, (cuuint32_t)BKR16};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    t2v_set_error("cuTensorMapEncodeTiled (MN-major, 16-bit) failed with CUresult %d (cols=%lld rows=%lld ld=%lld)", (int)r, cols, rows, ld);
+    return -3;
+  }
+  return 0;
+}
+}  // namespace
+
+// D[n_a, n_b] (+)= alpha * (*alpha_dev) * sum_{r < rows} A[a_row0 + r, i] * B[b_row0 + r, j] over 16-bit operands (fmt 1 fp16, 2 bf16).
+T2V_API int t2v_gemm_tc_rowred16(const void* A, long long lda, int n_a, long long a_row0, const void* B, long long ldb, int n_b,
+                                 long long b_row0, float* D, long long ldd, long long rows, int splits, int epi, float alpha,
+                                 const float* alpha_dev, int fmt, cudaStream_t stream) {
+  T2V_ARG_CHECK(A && B && D && n_a > 0 && n_b > 0 && rows > 0 && splits >= 1 && (fmt == 1 || fmt == 2), "shape / fmt");
+  T2V_ARG_CHECK((((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "operand base must be 16-byte aligned");
+  T2V_ARG_CHECK((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0, "row strides must be multiples of 16 bytes");
+  T2V_ARG_CHECK(n_b % 256 == 0 && n_a >= 256, "16-bit row reduction is built for the large weight gradients (n_b % 256 == 0)");
+  const int iters = t2v_ceil_div(rows, BKR16);
+  T2V_ARG_CHECK(splits <= iters, "more splits than 64-row iterations");
+  T2V_ARG_CHECK(splits == 1 || epi == 1, "split-K partial tiles are accumulated with atomics (epi 1)");
+  CUtensorMap tmA, tmB;
+  int r = encode_mn16(&tmA, A, n_a, a_row0 + rows, lda);
+  if (r) return r;
+  r = encode_mn16(&tmB, B, n_b, b_row0 + rows, ldb);
+  if (r) return r;
+  GemmTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.D = D; p.ldd = ldd; p.M = n_a; p.N = n_b; p.iters_per_split = t2v_ceil_div(iters, splits); p.chunks_per_tap = iters;
+  p.epi_atomic = epi; p.alpha = alpha; p.alpha_dev = alpha_dev; p.a_row0 = (int)a_row0; p.b_row0 = (int)b_row0;
+  constexpr int STAGES = 3, MB = 2, BN = 256;
+  constexpr int smem = STAGES * (128 * MB + BN) * BKR16 * 2 + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_mn16_kernel<BN, STAGES, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(t2v_ceil_div(n_a, 128 * MB), t2v_ceil_div(n_b, BN), splits);
+  gemm_tc_mn16_kernel<BN, STAGES, MB><<<grid, 192, smem, stream>>>(tmA, tmB, p, fmt == 2 ? 1 : 0);
+  T2V_COUNT_LAUNCH();
+  T2V_LAUNCH_CHECK();
+  return 0;
 }

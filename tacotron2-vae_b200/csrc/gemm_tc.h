@@ -20,6 +20,7 @@ struct GemmTcParams {
   int b_independent;     // B does not depend on the preceding kernel: prefetch it before the PDL dependency wait
   int pdl;               // launch with programmatic stream serialization
   int b_evict_last;      // load the B operand (weights re-read every time step) with the L2 evict_last policy
+  const float* alpha_dev; // nullable device scalar multiplied onto alpha (row-reduction kernels)
   int iters_per_term;    // > 0: split (error-compensated) product, the K loop walks 3 terms of iters_per_term iterations each:
                          // (A, B), (A2, B), (A, B2) -- x_hi W_hi + x_lo W_hi + x_hi W_lo in ONE accumulator
 };

@@ -49,6 +49,8 @@ _OVERLAP = __import__("os").environ.get("T2V_OVERLAP", "1") != "0"
 # situation that has not been exercised for long.
 _POST_DW_BRANCH = __import__("os").environ.get("T2V_POST_DW_BRANCH", "0") == "1"
 _BILSTM_PERSIST = __import__("os").environ.get("T2V_BILSTM_PERSIST", "1") != "0"
+_DW16 = __import__("os").environ.get("T2V_DW16", "1") != "0"          # decoder weight gradients from the fp16 copies (fp16 mode)
+_BWD16 = __import__("os").environ.get("T2V_BWD16", "1") != "0"        # fp16 operand copies in the persistent backward loop (op16 modes)
 
 
 class _Branch(object):
@@ -182,6 +184,28 @@ class Ops(object):
             self.gemm(dy, 1, ldy, x, 1, ldx, dW, lddw, N, K, M, 1.0, 1.0 if accumulate else 0.0, None)
 
     @staticmethod
+    def pick_splits(tiles, iters):
+        """split count of a row-reduction GEMM: fill whole waves of the 148 SMs (each extra split costs one more pass of atomics over D)"""
+        if tiles * 8 < 148:            # few output tiles (conv / small-N weight gradients): as many splits as it takes to fill two waves
+            return max(1, min(iters // 8 if iters >= 8 else 1, (296 + tiles - 1) // tiles))
+        best, splits = 0.0, 1
+        for sp in range(1, 9):
+            if sp > iters or iters // sp < 16:
+                break
+            n = tiles * sp
+            eff = n / (((n + 147) // 148) * 148.0) - 0.02 * (sp - 1)
+            if eff > best + 1e-9:
+                best, splits = eff, sp
+        return splits
+
+    @staticmethod
+    def rowred16(A16, lda, n_a, B16, ldb, n_b, D, ldd, rows, alpha_dev, fmt=1):
+        """D[n_a, n_b] += (*alpha_dev) * A16^T B16 over fp16 copies (kind::f16, 256 x 256 tiles); D zero-initialised"""
+        iters = (rows + 63) // 64
+        tiles = ((n_a + 255) // 256) * (n_b // 256)
+        L("t2v_gemm_tc_rowred16", A16, lda, n_a, 0, B16, ldb, n_b, 0, D, ldd, rows, Ops.pick_splits(tiles, iters), 1, 1.0, alpha_dev, fmt)
+
+    @staticmethod
     def rowred(A, lda, n_a, a_row0, Bm, ldb, n_b, b_row0, D, ldd, rows):
         """D[n_a, n_b] += sum_r A[a_row0+r, :]^T B[b_row0+r, :] on the MN-major tcgen05 kernel (no transposed copies);
         split over the reduction so that ~2 CTAs per SM exist.  D must be zero-initialised (or hold the running sum)."""
@@ -190,17 +214,7 @@ class Ops(object):
         bm = 256 if (wide and n_a >= 512) else 128            # the tile shapes t2v_gemm_tc_rowred picks
         tiles = ((n_a + bm - 1) // bm) * ((n_b + 255) // 256 if wide else (n_b + 127) // 128)
         # split the reduction so that the CTAs fill whole waves of the 148 SMs (each extra split costs one more pass of atomics over D)
-        if tiles * 8 < 148:            # few output tiles (conv / small-N weight gradients): as many splits as it takes to fill two waves
-            splits = max(1, min(iters // 8 if iters >= 8 else 1, (296 + tiles - 1) // tiles))
-        else:
-            best, splits = 0.0, 1
-            for sp in range(1, 9):
-                if sp > iters or iters // sp < 16:
-                    break
-                n = tiles * sp
-                eff = n / (((n + 147) // 148) * 148.0) - 0.02 * (sp - 1)
-                if eff > best + 1e-9:
-                    best, splits = eff, sp
+        splits = Ops.pick_splits(tiles, iters)
         L("t2v_gemm_tc_rowred", A, lda, n_a, a_row0, Bm, ldb, n_b, b_row0, D, ldd, rows, splits, 0, 1, 1.0)
 
     @staticmethod
@@ -819,7 +833,25 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
         setattr(D, k, v.data_ptr())
     D.WaTP, D.WdTP = _lib.ptr(WaTP), _lib.ptr(WdTP)
     t["_packed"] = (WaTP, WdTP)
+    D.op16 = 0
+    if ops.tc and ops.op16 and _BWD16:
+        # fp16 copies of the W^T tiles and of the gate gradients for the two dX GEMMs of the loop (kind::f16).  Gradients are
+        # ~1e-8: a power-of-two scale derived from max |dO| keeps them inside the fp16 range (saturating conversion), the dX rows
+        # are unscaled in fp32 -- same 11-bit significand as the tf32 path, half the L2 -> SM bytes that bound these GEMMs.
+        t["scale"] = _zeros(4, device=dev)
+        L("t2v_grad_scale", dO, dO.numel(), 12, t["scale"])
+        t["WaTP16"] = torch.empty(1792, 4096, device=dev, dtype=torch.int16)
+        t["WdTP16"] = torch.empty(2560, 4096, device=dev, dtype=torch.int16)
+        L("t2v_pack_step_tiles16", WaT, 2, t["WaTP16"], 1)
+        L("t2v_pack_step_tiles16", WdT, 3, t["WdTP16"], 1)
+        t["DGA16"] = torch.empty(n, 4096, device=dev, dtype=torch.int16)
+        t["DGD16"] = torch.empty(n, 4096, device=dev, dtype=torch.int16)
+        D.op16 = 1
+        D.DGA16, D.DGD16 = t["DGA16"].data_ptr(), t["DGD16"].data_ptr()
+        D.WaTP16, D.WdTP16 = t["WaTP16"].data_ptr(), t["WdTP16"].data_ptr()
+        D.dg_scale = t["scale"].data_ptr()
     L("t2v_decoder_bwd_steps", D, To, 0)
+    dw16 = bool(D.op16) and ops.op16 == 1 and bool(_lib.lib().t2v_decoder_last_bwd_path()) and buf.get("XA16") is not None and _DW16
     _trace("  bwd decoder loop")
     if ops.tc:
         L("t2v_round_tf32", t["dpmem"], t["dpmem"].numel())
@@ -830,9 +862,14 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
     with br:
         # batched weight gradients over all steps
         gWa = _zeros(4096, 1792, device=dev)
-        ops.linear_dw(t["DGA"], 4096, XA, 1792, gWa, 1792, n, 4096, 1792, device=dev)
         gWd = _zeros(4096, 2560, device=dev)
-        ops.linear_dw(t["DGD"], 4096, XD, 2560, gWd, 2560, n, 4096, 2560, device=dev)
+        if dw16:     # the two big weight gradients straight from the fp16 copies the loops left behind (gradient copy x 1 / scale)
+            inv = t["scale"].data_ptr() + 4
+            Ops.rowred16(t["DGA16"], 4096, 4096, buf["XA16"], 1792, 1792, gWa, 1792, n, inv)
+            Ops.rowred16(t["DGD16"], 4096, 4096, buf["XD16"], 2560, 2560, gWd, 2560, n, inv)
+        else:
+            ops.linear_dw(t["DGA"], 4096, XA, 1792, gWa, 1792, n, 4096, 1792, device=dev)
+            ops.linear_dw(t["DGD"], 4096, XD, 2560, gWd, 2560, n, 4096, 2560, device=dev)
         grads[_D + "attention_rnn.weight_ih"] = gWa[:, :768].contiguous()
         grads[_D + "attention_rnn.weight_hh"] = gWa[:, 768:].contiguous()
         grads[_D + "decoder_rnn.weight_ih"] = gWd[:, :1536].contiguous()

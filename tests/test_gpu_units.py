@@ -577,3 +577,69 @@ def test_persistent_bilstm_matches_per_step_launches(L, B, Ti, packed):
 def _launches():
     from t2v import _lib
     return _lib.launch_count()
+
+
+@pytest.mark.parametrize("B,Ti,To,gscale", [(5, 23, 12, 0.1), (64, 120, 20, 1e-7), (3, 128, 7, 3e-4)])
+def test_persistent_backward_fp16_operands_match_tf32_loop(L, B, Ti, To, gscale):
+    """The fp16-operand instantiation of the persistent backward loop (W^T tiles and gate gradients as fp16 copies, gradients scaled by a
+    power of two derived from max |dO|) against the tf32 instantiation on the same saved forward state, for upstream gradients of very
+    different magnitudes (1e-7 is what a C3-sized loss produces: far below the fp16 range without the scale).  fp16 and tf32 share
+    the 11-bit significand: tolerance 2e-3 of each tensor's max."""
+    from oracle import port
+    from t2v import engine
+    dev = torch.device("cuda")
+    P = {k: v.to(dev) for k, v in port.init_params(1234).items()}
+    g = torch.Generator().manual_seed(B * 1000 + Ti)
+    memory = (torch.randn(B, Ti, 512, generator=g) * 0.5).to(dev)
+    mel = (torch.randn(B, 80, To, generator=g) * 2 - 5).to(dev)
+    in_len = torch.randint(max(1, Ti // 2), Ti + 1, (B,), generator=g).sort(descending=True)[0]
+    in_len[0] = Ti
+    in_len = in_len.to(dev)
+    dO = (torch.randn(To * B, 84, generator=g) * gscale).to(dev)
+    dO[:, 81:] = 0
+    ops = engine.Ops("fp16")
+    O, align, ctx = engine.decoder_forward(ops, P, memory, mel, in_len, True, None, None, 77, -float("inf"), dev)
+    outs = {}
+    for mode in (True, False):
+        engine._BWD16 = mode
+        try:
+            grads = {}
+            dmem, br = engine.decoder_backward(ops, P, dO, ctx, dev, grads)
+            br.join()
+            torch.cuda.synchronize()
+        finally:
+            engine._BWD16 = True
+        t, D = br.keep
+        assert int(D.op16) == (1 if mode else 0)
+        res = dict(dmem=dmem.clone(), **{k: t[k].clone() for k in ("DXA", "DXD", "DGA", "DGD", "DCTX", "DQ", "dpmem")})
+        res.update({"grad:" + k: v.clone() for k, v in grads.items()})
+        if mode:
+            sc = t["scale"].cpu()
+            assert float(sc[0]) * float(sc[1]) == 1.0 and 2048.0 <= float(sc[0]) * float(dO.abs().max()) < 4096.0 + 1e-3
+            dg16 = t["DGA16"].view(torch.float16).float() * float(sc[1])
+            assert float((dg16 - t["DGA"]).abs().max()) <= 2e-3 * float(t["DGA"].abs().max())       # the copies are the same numbers
+        outs[mode] = res
+    for k in outs[False]:
+        a, b = outs[True][k], outs[False][k]
+        assert torch.isfinite(a).all(), k
+        err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+        print("bwd fp16 vs tf32 %-60s max-rel %.3e" % (k, err))
+        assert err <= 2e-3, (k, err)
+
+
+@pytest.mark.parametrize("rows,n_a,n_b,splits", [(4096, 4096, 1792, 2), (1000, 512, 256, 1), (51200, 4096, 2560, 5)])
+def test_gemm_tc_rowred16_mn_major_fp16(L, rows, n_a, n_b, splits):
+    """t2v_gemm_tc_rowred16: D = alpha_dev * A16^T B16 from row-major fp16 operands (MN-major kind::f16 UMMA, 256 x 256 tiles, 64
+    reduction rows per stage) against an fp64 reference of the same fp16 values: only the fp32 accumulation order differs."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(rows + n_a)
+    A = torch.randn(rows + 3, n_a, generator=g).to(dev).half()
+    Bm = torch.randn(rows + 3, n_b, generator=g).to(dev).half()
+    D = torch.zeros(n_a, n_b, device=dev)
+    alpha = torch.tensor([0.25], device=dev)
+    L("t2v_gemm_tc_rowred16", A.view(torch.int16), n_a, n_a, 0, Bm.view(torch.int16), n_b, n_b, 0, D, n_b, rows, splits, 1, 1.0, alpha, 1)
+    torch.cuda.synchronize()
+    ref = 0.25 * (A[:rows].double().t() @ Bm[:rows].double()).float()
+    err = float((D - ref).abs().max() / ref.abs().max())
+    print("rowred16 rows=%d %dx%d splits=%d max-rel %.2e" % (rows, n_a, n_b, splits, err))
+    assert err < 1e-4, err
