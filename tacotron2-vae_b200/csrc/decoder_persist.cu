@@ -91,6 +91,7 @@ struct PersistParams {
   int packed;              // tmWa / tmWd describe the re-tiled copies (one contiguous 16 KB box per chunk)
   int wa_hint, wd_hint, mem_hint;   // L2 eviction priority of the weight streams / the encoder memory: 0 normal, 1 evict_last, 2 evict_first
   long long* trace;        // T2V_PERSIST_TRACE: [2 CTAs][TRACE_STEPS][32] clock64 stamps, else nullptr
+  long long* gtrace;       // T2V_PERSIST_TRACE: [NCTA][8] %globaltimer stamps (ns, comparable across CTAs) of step TRACE_T0
   // ---- free-running inference (Decoder.inference, model.py:428-464) only
   const float *Wp1, *Wp2, *Wpg, *bpg;   // prenet [256,80], [256,256]; [linear_projection ; gate_layer] [81,1536], bias [81]
   const float* prenet_masks;            // [n,2,B,256] or nullptr (counter RNG)
@@ -101,6 +102,15 @@ struct PersistParams {
   int* n_frames;                        // [B] or nullptr
 };
 constexpr unsigned SITE_PRENET0 = 3, SITE_PRENET1 = 4;
+constexpr unsigned Q_SENTINEL = 0x7FC0DEADu;       // "no value yet" in the query-partial slots: a NaN payload no partial sum can produce
+__device__ __forceinline__ float ld_relaxed_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void fill_u32_kernel(unsigned* __restrict__ x, long long n, unsigned v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = v;
+}
 constexpr int TRACE_T0 = 100, TRACE_STEPS = 4, TRACE_CTA_B = 77;
 
 // K offset (columns of the weight matrix = columns of the activation row) of chunk j of this CTA's K slice.
@@ -198,6 +208,13 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   unsigned* cnt_p = p.counters + 96;      // inference: prenet rows of step t complete
   // debug time stamps of a few mid-sequence steps (two CTAs); compiled in, one predictable branch per event when off
   const int trace_slot = (blockIdx.x == 0) ? 0 : ((blockIdx.x == TRACE_CTA_B) ? 1 : -1);
+  auto GT = [&](unsigned n, int ev) {
+    if (p.gtrace && n == (unsigned)TRACE_T0) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      p.gtrace[blockIdx.x * 8 + ev] = (long long)ns;
+    }
+  };
   auto TR = [&](unsigned n, int ev) {
     if (p.trace && trace_slot >= 0 && n >= (unsigned)TRACE_T0 && n < (unsigned)(TRACE_T0 + TRACE_STEPS))
       p.trace[((long long)trace_slot * TRACE_STEPS + (n - TRACE_T0)) * 32 + ev] = clock64();
@@ -308,7 +325,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
             if (j >= JA_C) need(cnt_c, seen_c, NCTA * n);
             else if (j >= JA_H) need(cnt_h, seen_h, NCTA * n);
             if (j == JA_H) TR(n, 0);
-            if (j == JA_C) TR(n, 1);
+            if (j == JA_C) { TR(n, 1); GT(n, 2); }
             load_a(&tmXA, att_kofs_t<OP>(j, rank), t * B);
           }
           TR(n, 2);
@@ -451,6 +468,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       if (etid == 0) {
         mbar_expect_tx(&recv_full[which], 4 * SLOT * 4);   // four 8 KB slots (own included) land as st.async bytes
         TR(tn, which ? 14 : 8);
+        if (which == 0) GT(tn, 4);
       }
       // ---- drain TMEM: this thread holds D[gate q, unit u][batch 0..63]; batch rows 16d..16d+15 go to cluster rank d.
       // A 4x4 transpose inside every lane quad turns "one unit, 4 batch rows" into "one batch row, 4 units", so the
@@ -611,6 +629,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       }
       named_bar(BAR_EPI, 128);
       if (etid == 0 && which == 0) TR(tn, 12);
+      if (etid == 0 && which == 0) GT(tn, 3);
       if (etid == 0) signal_counter(which ? cnt_d : cnt_h);
       if (etid == 0) TR(tn, which ? 15 : 13);
       // ---- saved activations of the backward pass + the cell state sequence (nobody inside this kernel reads them)
@@ -865,22 +884,46 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         named_bar(BAR_ATT, 256);
         if (atid == 0) { TR(n, 2); signal_counter(cnt_p); TR(n, 3); }
       }
-      // ---- h_att_t (and every cluster's partial query) complete device-wide
-      if (atid == 0) { TR(n, 16); wait_counter(cnt_h, NCTA * (n + 1)); TR(n, 17); }
-      named_bar(BAR_ATT, 256);
+      // ---- the query of step t.  Flag-in-data: the 32 per-cluster partials of this utterance are polled directly -- every slot
+      // holds a sentinel (a NaN pattern no partial can take) until its producer's store lands -- instead of waiting for the
+      // device-wide h counter and THEN fetching them (one L2 round trip less on the critical chain, no exposure to the slowest of
+      // the 128 CTAs).  Slots are re-armed one step later by the hh == 0 CTA: by then both CTAs of the pair have consumed them
+      // (they exchanged the energies computed from this query), and the next write to the same parity comes after this CTA's
+      // ctx signal of the current step.  CTAs without an utterance keep the counter wait (it keeps their signals in step).
+      if (!active) {
+        if (atid == 0) wait_counter(cnt_h, NCTA * (n + 1));
+        named_bar(BAR_ATT, 256);
+      }
       if (active) {
-        // ---- query = sum of the 32 per-cluster partials
+        if (atid == 0) TR(n, 16);
         {
           const int half = atid >> 7;
+          if (hh == 0 && n > 0) {      // re-arm the slots of step t - 1
+            float* qo = p.qpart + ((long long)(((t - 1) & 1) * NCLUSTER + half * 16) * B + b) * AD + a;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) qo[(long long)k * B * AD] = __uint_as_float(Q_SENTINEL);
+          }
           const float* qp = p.qpart + ((long long)((t & 1) * NCLUSTER + half * 16) * B + b) * AD + a;
+          float v[16];
+          bool ok = false;
+          const long long t0 = clock64();
+          // (while nothing has arrived only ONE slot per thread is polled: 32 sectors per CTA and poll instead of 512)
+          while (__float_as_uint(ld_relaxed_f32(qp)) == Q_SENTINEL) { if (clock64() - t0 > WAIT_LIMIT) __trap(); }
+          while (!ok) {
+            ok = true;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              v[k] = ld_relaxed_f32(qp + (long long)k * B * AD);
+              ok = ok && (__float_as_uint(v[k]) != Q_SENTINEL);
+            }
+            if (!ok && clock64() - t0 > WAIT_LIMIT) __trap();
+          }
           float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-          for (int k = 0; k < 16; k += 2) {
-            acc0 += __ldcg(qp + (long long)k * B * AD);
-            acc1 += __ldcg(qp + (long long)(k + 1) * B * AD);
-          }
+          for (int k = 0; k < 16; k += 2) { acc0 += v[k]; acc1 += v[k + 1]; }
           q_s[half * 128 + a] = acc0 + acc1;
         }
+        if (atid == 0) { TR(n, 17); GT(n, 0); }
         named_bar(BAR_ATT, 256);
         if (atid == 0) TR(n, 18);
 #pragma unroll
@@ -1023,7 +1066,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
       }
       named_bar(BAR_ATT, 256);
-      if (atid == 0) { signal_counter(cnt_c); TR(n, 23); }
+      if (atid == 0) { GT(n, 1); signal_counter(cnt_c); TR(n, 23); GT(n, 5); }
       // ---- saved tanh activations of the backward pass, recomputed off the critical path (S and the query are still here;
       // storing them inside the energy loop would put 30 KB of global stores in front of the exchange)
       if (active && s.ASAVE) {
@@ -1205,6 +1248,7 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
   p.counters = reinterpret_cast<unsigned*>(s->ebuf);
   p.qpart = s->parts;
   p.trace = nullptr;
+  p.gtrace = nullptr;
   if (inf) {
     p.Wp1 = inf->Wp1; p.Wp2 = inf->Wp2; p.Wpg = inf->Wpg; p.bpg = inf->bpg; p.prenet_masks = inf->prenet_masks;
     p.O = inf->O; p.gate_threshold = inf->gate_threshold; p.n_frames = inf->n_frames;
@@ -1221,6 +1265,8 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
   if (trace) {
     T2V_CUDA_CHECK(cudaMalloc(&p.trace, trace_bytes));
     T2V_CUDA_CHECK(cudaMemsetAsync(p.trace, 0, trace_bytes, stream));
+    T2V_CUDA_CHECK(cudaMalloc(&p.gtrace, NCTA * 8 * sizeof(long long)));
+    T2V_CUDA_CHECK(cudaMemsetAsync(p.gtrace, 0, NCTA * 8 * sizeof(long long), stream));
   }
   CUtensorMap tmWa, tmWd, tmXA, tmXD;
   const long long rows = (long long)(s->To + 1) * s->B;
@@ -1245,6 +1291,7 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
     if ((r = t2v_encode_tmap_2d(&tmXD, s->XD, 4, XD_W, rows, XD_W, 64))) return r;
   }
   T2V_CUDA_CHECK(cudaMemsetAsync(p.counters, 0, 128 * sizeof(unsigned), stream));
+  fill_u32_kernel<<<64, 256, 0, stream>>>(reinterpret_cast<unsigned*>(p.qpart), 2LL * NCLUSTER * s->B * AD, Q_SENTINEL);   // arm the query slots
   cfg.numAttrs = t2v_coop_enabled() ? 2 : 1;
   T2V_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmWa, tmWd, tmXA, tmXD, p));
   T2V_COUNT_LAUNCH();
@@ -1259,6 +1306,29 @@ static int launch_persist(const T2VDecoderSeq* s, const T2VDecoderInfer* inf, in
     T2V_CUDA_CHECK(cudaStreamSynchronize(stream));
     T2V_CUDA_CHECK(cudaMemcpy(h, p.trace, trace_bytes, cudaMemcpyDeviceToHost));
     cudaFree(p.trace);
+    {      // cross-CTA view of one step (global timer, ns)
+      static long long g[NCTA * 8];
+      T2V_CUDA_CHECK(cudaMemcpy(g, p.gtrace, sizeof(g), cudaMemcpyDeviceToHost));
+      cudaFree(p.gtrace);
+      static const char* gn[6] = {"T:query partials seen", "T:ctx signal begin", "A:ctx ready (this step's GEMM)", "E:h signal begin", "E:att acc full",
+                                  "T:ctx signal done"};
+      long long base = 0;
+      for (int c = 0; c < NCTA; ++c) if (g[c * 8 + 4] && (!base || g[c * 8 + 4] < base)) base = g[c * 8 + 4];
+      fprintf(stderr, "[t2v persist gtrace] step %d, ns relative to the earliest 'E:att acc full'; per event: min / median / p90 / max (CTA of max)\n", TRACE_T0);
+      for (int ev = 0; ev < 6; ++ev) {
+        long long v[NCTA]; int arg = 0;
+        for (int c = 0; c < NCTA; ++c) { v[c] = g[c * 8 + ev] - base; if (v[c] > v[arg]) arg = c; }
+        long long srt[NCTA];
+        memcpy(srt, v, sizeof(srt));
+        for (int i = 1; i < NCTA; ++i) { long long x = srt[i]; int j = i - 1; while (j >= 0 && srt[j] > x) { srt[j + 1] = srt[j]; --j; } srt[j + 1] = x; }
+        fprintf(stderr, "  %-32s %7lld %7lld %7lld %7lld  (CTA %d)\n", gn[ev], srt[0], srt[NCTA / 2], srt[NCTA * 9 / 10], srt[NCTA - 1], arg);
+      }
+      fprintf(stderr, "  late CTAs at 'T:ctx signal begin' (> median + 500 ns):");
+      { long long v[NCTA], srt[NCTA]; for (int c = 0; c < NCTA; ++c) v[c] = g[c * 8 + 1] - base; memcpy(srt, v, sizeof(srt));
+        for (int i = 1; i < NCTA; ++i) { long long x = srt[i]; int j = i - 1; while (j >= 0 && srt[j] > x) { srt[j + 1] = srt[j]; --j; } srt[j + 1] = x; }
+        for (int c = 0; c < NCTA; ++c) if (v[c] > srt[NCTA / 2] + 500) fprintf(stderr, " %d(+%lld)", c, v[c] - srt[NCTA / 2]); }
+      fprintf(stderr, "\n");
+    }
     for (int c = 0; c < 2; ++c) {
       const long long base = h[(c * TRACE_STEPS) * 32 + 1];     // "ctx ready" of the first traced step
       fprintf(stderr, "[t2v persist trace] CTA %d: SM clocks relative to 'A:ctx ready' of step %d\n", c ? TRACE_CTA_B : 0, TRACE_T0);
