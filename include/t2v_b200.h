@@ -262,6 +262,8 @@ typedef struct T2VDecoderSeq {
   int op16;                      /* 0: fp32 storage / tf32 math in the persistent loops; 1: fp16, 2: bf16 operand copies (kind::f16) */
   void *XA16, *XD16;             /* op16: 16-bit copies of XA / XD (same shapes), the tensor-core operands; zero-initialise */
   const void *WaP16, *WdP16;     /* op16: 16-bit re-tiled weights (t2v_pack_step_tiles16 modes 0 / 1) */
+  const void *mem16;             /* op16, optional: fp16 copy of `mem` (exact for values on the tf32 grid) read by the context reduction:
+                                    half the bytes and all Ti <= 128 rows of a column group in flight at once */
 } T2VDecoderSeq;
 int t2v_sizeof_decoder_structs(int which);   /* sizeof(T2VDecoderSeq / T2VDecoderBwd / T2VDecoderInfer) for which = 0 / 1 / 2: binding check */
 int t2v_decoder_fwd_steps(const T2VDecoderSeq* s, int t_begin, int t_end, cudaStream_t stream);

@@ -53,7 +53,7 @@ template <int OP> struct SM {
   static constexpr int OFF_RECV = OFF_ARING + NS * A_STAGE;         // [2 gemms][4 sources][SLOT]
   static constexpr int OFF_S = OFF_RECV + 2 * 4 * SLOT * 4;         // [TH_MAX][128] location term + processed memory
   static constexpr int OFF_F = OFF_S + TH_MAX * AD * 4;             // fp32: [TH_MAX][FS] conv output; aliased: ctx partials [4][256],
-  static constexpr int F_BYTES = OP ? 1280 * 4 : TH_MAX * FS * 4;   //       inference scratch (op16: only those, 1280 floats)
+  static constexpr int F_BYTES = OP ? 2304 * 4 : TH_MAX * FS * 4;   //       inference scratch (op16: only those: ctx partials [8][256] + [256])
   static constexpr int OFF_WCT = OFF_F + F_BYTES;                   // [62][32]
   static constexpr int OFF_HQ = OFF_WCT + 2 * KS * NF * 4;          // [16][32] h_att of this CTA's rows (query partials)
   static constexpr int OFF_WPAD = OFF_HQ + 16 * 32 * 4;
@@ -706,7 +706,7 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     // stop bookkeeping (Decoder.inference, model.py:449-459); leaves the frame in mel_s for the prenet
     float* mel_s = fbuf;                      // [84]   (fbuf is free between the location phase and the context phase)
     float* p1_s = fbuf + 128;                 // [256]
-    float* ctx_s = fbuf + 1024;               // [256]  (next to the four context partial rows)
+    float* ctx_s = fbuf + (OP ? 2048 : 1024); // [256]  (next to the context partial rows)
     auto frame_from_partials = [&](const int f) {
       if (atid < 81) {
         const int o = atid;
@@ -1005,8 +1005,34 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
         named_bar(BAR_ATT, 256);
         if (atid == 0) TR(n, 21);
-        // ---- context columns [256 hh, 256 hh + 256): thread = (4 columns, every 4th text position), 16 rows in flight
-        {
+        // ---- context columns [256 hh, 256 hh + 256)
+        const bool ctx16 = OP && s.mem16 != nullptr;
+        if (ctx16) {
+          // fp16 copy of the encoder memory: thread = (8 columns, every 8th text position) -> all Ti <= 128 rows of the column group
+          // in flight at once (ONE L2 round trip instead of two, half the bytes)
+          const int cg = atid & 31, rg = atid >> 5;
+          const uint16_t* mb = reinterpret_cast<const uint16_t*>(s.mem16) + (long long)b * Ti * ED + 256 * hh + 8 * cg;
+          uint4 mv[16];
+          float wi[16];
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const int ti = rg + 8 * r;
+            wi[r] = (ti < Ti) ? wpad[HALO + ti] : 0.f;
+            mv[r] = (wi[r] == 0.f) ? make_uint4(0u, 0u, 0u, 0u) : ldg_u4_hint(mb + (long long)ti * ED, pol_m);
+          }
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const uint32_t w4[4] = {mv[r].x, mv[r].y, mv[r].z, mv[r].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc[2 * i] = fmaf(wi[r], t2v_f16_to_f32((uint16_t)(w4[i] & 0xFFFFu)), acc[2 * i]);
+              acc[2 * i + 1] = fmaf(wi[r], t2v_f16_to_f32((uint16_t)(w4[i] >> 16)), acc[2 * i + 1]);
+            }
+          }
+          *reinterpret_cast<float4*>(fbuf + rg * 256 + 8 * cg) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          *reinterpret_cast<float4*>(fbuf + rg * 256 + 8 * cg + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        } else {
           const int cg = atid & 63, rg = atid >> 6;
           const float* mb = s.mem + (long long)b * Ti * ED + 256 * hh + 4 * cg;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1032,7 +1058,8 @@ dec_persist_fwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         named_bar(BAR_ATT, 256);
         if (atid == 0) TR(n, 22);
         {
-          const float cx = (fbuf[atid] + fbuf[256 + atid]) + (fbuf[512 + atid] + fbuf[768 + atid]);
+          float cx = (fbuf[atid] + fbuf[256 + atid]) + (fbuf[512 + atid] + fbuf[768 + atid]);
+          if (ctx16) cx += (fbuf[1024 + atid] + fbuf[1280 + atid]) + (fbuf[1536 + atid] + fbuf[1792 + atid]);
           const float c = t2v_rnd(cx, rnd);
           const int col = 256 * hh + atid;
           s.XD[((long long)t * B + b) * XD_W + H + col] = c;              // ctx_t -> decoder_rnn input

@@ -25,7 +25,7 @@ class T2VDecoderSeq(ctypes.Structure):
                 [(n, _P) for n in ("Wa", "ba1", "ba2", "Wd", "bd1", "bd2", "Wq", "Wconv", "Wloc", "v", "mem", "pmem",
                                    "XA", "XD", "CA", "CD", "CUM", "align", "GA", "GD", "CPA", "CPD", "ASAVE", "parts",
                                    "qparts", "ebuf", "WaP", "WdP", "HCHI", "HCLO")] +
-                [("op16", ctypes.c_int)] + [(n, _P) for n in ("XA16", "XD16", "WaP16", "WdP16")])
+                [("op16", ctypes.c_int)] + [(n, _P) for n in ("XA16", "XD16", "WaP16", "WdP16", "mem16")])
 
 
 class T2VDecoderBwd(ctypes.Structure):

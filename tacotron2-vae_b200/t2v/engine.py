@@ -695,6 +695,10 @@ def _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_v
         setattr(S, k, _lib.ptr(buf.get(k)))
     S.op16 = ops.op16 if buf.get("XA16") is not None else 0
     S.WaP16, S.WdP16 = _lib.ptr(W.get("WaP16")), _lib.ptr(W.get("WdP16"))
+    if S.op16:       # fp16 copy of the encoder memory for the context reduction of the persistent loop (exact: mem is on the tf32 grid)
+        buf["mem16"] = torch.empty(B * Ti, 512, device=mem.device, dtype=torch.int16)
+        L("t2v_cvt16_2d", mem, 512, buf["mem16"], 512, B * Ti, 512, 1)
+    S.mem16 = _lib.ptr(buf.get("mem16"))
 
 
 def alloc_decoder_buffers(B, Ti, To, dev, save=True, op16=0, split=False):
