@@ -163,6 +163,13 @@ int t2v_bilstm_seq_fwd(const float* gx0, const float* gx1, const float* whh0, co
 int t2v_bilstm_seq_bwd(const float* whhT0, const float* whhT1, const float* dout, const float* gates, const float* cells,
                        float* dg0, float* dg1, unsigned int* counters, const long long* lens, int B, int H, int Ti,
                        cudaStream_t stream);
+/* reference-encoder GRU (reference modules.py:60-80, nn.GRU batch_first, h0 = 0) as one persistent launch per pass, B <= 64:
+   gi rows (b, t) at gi + b * gi_bs + t * 3H (x W_ih^T, no bias), hs [Tq+1,B,H] (slot 0 zero), save [Tq,B,4H] (r, z, n, gh_n),
+   counter 32 x u32 (zeroed by the call); backward: dh_last [B,H] -> dgi (same row layout as gi) and dgh [Tq,B,3H] */
+int t2v_gru_seq_fwd(const float* gi, long long gi_bs, const float* w_hh, const float* b_ih, const float* b_hh, float* hs,
+                    float* save, unsigned int* counter, int B, int H, int Tq, cudaStream_t stream);
+int t2v_gru_seq_bwd(const float* w_hh, const float* dh_last, const float* save, const float* hs, float* dgi, long long dgi_bs,
+                    float* dgh, unsigned int* counter, int B, int H, int Tq, cudaStream_t stream);
 /* same, with dh1 given as `dh1_parts` split-K partial buffers (stride dh1_pstride) that are summed on the fly */
 int t2v_lstm_pointwise_bwd_parts(const float* dh1, long long dh1_rs, int dh1_parts, long long dh1_pstride, const float* dh2,
                                  long long dh2_rs, const float* dh3, long long dh3_rs, float* dc, const float* gates_save,

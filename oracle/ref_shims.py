@@ -20,6 +20,7 @@ third-party packages and three runtime patches for PyTorch-1.0-isms (SURVEY.md s
     torch.cuda.LongTensor and returns uint8, which ``~`` no longer treats as logical-not)
 """
 import importlib
+import importlib.machinery
 import os
 import sys
 import types
@@ -83,21 +84,28 @@ def _pad_center(data, size, axis=-1, **kw):
     return np.pad(data, lengths, mode="constant")
 
 
+def _module(name):
+    """stub module with a __spec__ (importlib.util.find_spec raises on modules without one; torch._dynamo probes 'tensorflow')"""
+    m = types.ModuleType(name)
+    m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+    return m
+
+
 def _install_shims():
     if "tensorflow" not in sys.modules:
         sys.path.insert(0, _PKG)
         hp_mod = importlib.import_module("hparams")  # this repo's HParams stand-in
         sys.path.remove(_PKG)
         del sys.modules["hparams"]
-        tf = types.ModuleType("tensorflow")
+        tf = _module("tensorflow")
         tf.contrib = types.SimpleNamespace(training=types.SimpleNamespace(HParams=hp_mod.HParams))
         tf.logging = types.SimpleNamespace(info=lambda *a, **k: None)
         sys.modules["tensorflow"] = tf
     if "librosa" not in sys.modules:
-        lib = types.ModuleType("librosa")
-        filt = types.ModuleType("librosa.filters")
+        lib = _module("librosa")
+        filt = _module("librosa.filters")
         filt.mel = slaney_mel_filterbank
-        util = types.ModuleType("librosa.util")
+        util = _module("librosa.util")
         util.pad_center = _pad_center
         util.tiny = lambda x: np.finfo(np.asarray(x).dtype if np.issubdtype(np.asarray(x).dtype, np.floating) else np.float32).tiny
         util.normalize = lambda S, norm=np.inf, **kw: S if norm is None else S / np.max(np.abs(S))
@@ -105,7 +113,7 @@ def _install_shims():
         sys.modules.update({"librosa": lib, "librosa.filters": filt, "librosa.util": util})
     for name in ("jamo", "jamo.jamo", "unidecode", "inflect", "nltk"):
         if name not in sys.modules:
-            sys.modules[name] = types.ModuleType(name)
+            sys.modules[name] = _module(name)
     j = sys.modules["jamo"]
     if not hasattr(j, "h2j"):
         def _h2j(s):

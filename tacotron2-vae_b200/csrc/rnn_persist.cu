@@ -264,6 +264,193 @@ __global__ void __launch_bounds__(UPC * 32, 1) bilstm_seq_bwd_kernel(SeqBwd p) {
   }
 }
 
+
+// ---- reference-encoder GRU (reference modules.py:60-80: nn.GRU(128 * n_mel / 64, 256, batch_first), last hidden state) ---------
+// Same scheme, one direction: H / 8 CTAs, warp = hidden unit, lane -> batch rows lane, lane + 32; W_hh rows (r, z, n) of the CTA's
+// units stay in shared memory for all Tq steps.  Arithmetic identical to gru_pointwise_fwd / _bwd + exact fp32 GEMMs.
+struct GruFwd {
+  const float* gi; long long gi_bs;   // x W_ih^T rows: (b, t) at gi + b * gi_bs + t * 3H
+  const float* w_hh;                  // [3H, H]
+  const float* b_ih; const float* b_hh;
+  float* hs;                          // [Tq + 1, B, H], slot 0 = h0 (zero), slot t + 1 = h after step t
+  float* save;                        // [Tq, B, 4H]: r, z, n, gh_n
+  unsigned* counter;
+  int B, H, Tq;
+};
+
+__global__ void __launch_bounds__(UPC * 32, 1) gru_seq_fwd_kernel(GruFwd p) {
+  extern __shared__ __align__(16) float smg[];
+  const int H = p.H, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * UPC, u = u0 + warp, HS = H + 1, ncta = gridDim.x;
+  float* hT = smg;                       // [MT][H+1]
+  float* ws = hT + ((MT * HS + 3) & ~3); // [H][UPC][4] (r, z, n, -)
+  for (int i = threadIdx.x; i < H * UPC * 3; i += UPC * 32) {
+    const int k = i % H, g = (i / H) % 3, uu = i / (3 * H);
+    ws[(k * UPC + uu) * 4 + g] = p.w_hh[((long long)g * H + u0 + uu) * H + k];
+  }
+  const float br = p.b_ih[u], bz = p.b_ih[H + u], bn = p.b_ih[2 * H + u];
+  const float cr = p.b_hh[u], cz = p.b_hh[H + u], cn = p.b_hh[2 * H + u];
+  for (int s = 0; s < p.Tq; ++s) {
+    float giv[2][3];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int b = r * 32 + lane;
+      if (b < p.B) {
+        const float* g = p.gi + (long long)b * p.gi_bs + (long long)s * 3 * H;
+        giv[r][0] = g[u]; giv[r][1] = g[H + u]; giv[r][2] = g[2 * H + u];
+      } else {
+        giv[r][0] = giv[r][1] = giv[r][2] = 0.f;
+      }
+    }
+    const float* hprev = p.hs + (long long)s * p.B * H;
+    if (s > 0) {
+      if (threadIdx.x == 0) wait_counter(p.counter, (unsigned)(ncta * s));
+      __syncthreads();
+      const int nv = MT * H / 4;
+      for (int i0 = threadIdx.x; i0 < nv; i0 += UPC * 32 * 16) {
+        float4 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int i = i0 + j * UPC * 32;
+          const int m = (i * 4) / H, k = (i * 4) % H;
+          v[j] = (i < nv && m < p.B) ? __ldcg(reinterpret_cast<const float4*>(hprev + (long long)m * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int i = i0 + j * UPC * 32;
+          if (i < nv) {
+            const int m = (i * 4) / H, k = (i * 4) % H;
+            float* d = hT + m * HS + k;
+            d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+          }
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < MT * HS; i += UPC * 32) hT[i] = 0.f;
+    }
+    __syncthreads();
+    float acc[2][3];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 0.f;
+    if (s > 0) {
+#pragma unroll 4
+      for (int k = 0; k < H; ++k) {
+        const float a0 = hT[lane * HS + k], a1 = hT[(32 + lane) * HS + k];
+        const float4 w = *reinterpret_cast<const float4*>(ws + (k * UPC + warp) * 4);
+        acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]); acc[0][2] = fmaf(a0, w.z, acc[0][2]);
+        acc[1][0] = fmaf(a1, w.x, acc[1][0]); acc[1][1] = fmaf(a1, w.y, acc[1][1]); acc[1][2] = fmaf(a1, w.z, acc[1][2]);
+      }
+    }
+    float* hnext = p.hs + (long long)(s + 1) * p.B * H;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int b = r * 32 + lane;
+      if (b >= p.B) continue;
+      const float rg = t2v_sigmoid(giv[r][0] + br + acc[r][0] + cr);
+      const float zg = t2v_sigmoid(giv[r][1] + bz + acc[r][1] + cz);
+      const float ghn = acc[r][2] + cn;
+      const float ng = tanhf(giv[r][2] + bn + rg * ghn);
+      const float hp = hT[b * HS + u];
+      hnext[(long long)b * H + u] = (1.f - zg) * ng + zg * hp;
+      float* sv = p.save + ((long long)s * p.B + b) * 4 * H + u;
+      sv[0] = rg; sv[H] = zg; sv[2 * H] = ng; sv[3 * H] = ghn;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) signal_counter(p.counter);
+  }
+}
+
+struct GruBwd {
+  const float* w_hh;                  // [3H, H]
+  const float* dh_last;               // [B, H]
+  const float* save; const float* hs;
+  float* dgi; long long dgi_bs;       // gradient wrt x W_ih^T: row (b, t) at dgi + b * dgi_bs + t * 3H
+  float* dgh;                         // [Tq, B, 3H] gradient wrt h W_hh^T (+ b_hh), kept for the batched dW_hh / db_hh
+  unsigned* counter;
+  int B, H, Tq;
+};
+
+__global__ void __launch_bounds__(UPC * 32, 1) gru_seq_bwd_kernel(GruBwd p) {
+  extern __shared__ __align__(16) float smg[];
+  const int H = p.H, K = 3 * H, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * UPC, u = u0 + warp, ncta = gridDim.x;
+  constexpr int KC = 256, DS = KC + 1;
+  float* dT = smg;                       // [MT][KC+1]
+  float* ws = dT + MT * DS;              // [K][UPC]: W_hh[k][u]
+  for (int i = threadIdx.x; i < K * UPC; i += UPC * 32) {
+    const int uu = i % UPC, k = i / UPC;
+    ws[k * UPC + uu] = p.w_hh[(long long)k * H + u0 + uu];
+  }
+  float carry[2] = {0.f, 0.f};
+  __syncthreads();
+  for (int s = 0; s < p.Tq; ++s) {
+    const int t = p.Tq - 1 - s;
+    float sr[2], sz[2], sn[2], sg[2], hp[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int b = r * 32 + lane;
+      if (b < p.B) {
+        const float* sv = p.save + ((long long)t * p.B + b) * 4 * H + u;
+        sr[r] = sv[0]; sz[r] = sv[H]; sn[r] = sv[2 * H]; sg[r] = sv[3 * H];
+        hp[r] = p.hs[((long long)t * p.B + b) * H + u];
+      } else {
+        sr[r] = sz[r] = sn[r] = sg[r] = hp[r] = 0.f;
+      }
+    }
+    float acc[2] = {0.f, 0.f};
+    if (s > 0) {
+      if (threadIdx.x == 0) wait_counter(p.counter, (unsigned)(ncta * s));
+      const float* dgn = p.dgh + (long long)(t + 1) * p.B * K;
+      for (int k0 = 0; k0 < K; k0 += KC) {
+        __syncthreads();
+        const int nv = MT * KC / 4;
+        for (int i0 = threadIdx.x; i0 < nv; i0 += UPC * 32 * 16) {
+          float4 v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int i = i0 + j * UPC * 32;
+            const int m = (i * 4) / KC, k = (i * 4) % KC;
+            v[j] = (i < nv && m < p.B) ? __ldcg(reinterpret_cast<const float4*>(dgn + (long long)m * K + k0 + k))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int i = i0 + j * UPC * 32;
+            if (i < nv) {
+              const int m = (i * 4) / KC, k = (i * 4) % KC;
+              float* d = dT + m * DS + k;
+              d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+            }
+          }
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < KC; ++k) {
+          const float w = ws[(k0 + k) * UPC + warp];
+          acc[0] = fmaf(dT[lane * DS + k], w, acc[0]);
+          acc[1] = fmaf(dT[(32 + lane) * DS + k], w, acc[1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int b = r * 32 + lane;
+      if (b >= p.B) continue;
+      const float d = (s == 0) ? p.dh_last[(long long)b * H + u] : carry[r] + acc[r];
+      const float dn = d * (1.f - sz[r]) * (1.f - sn[r] * sn[r]);
+      const float dz = d * (hp[r] - sn[r]) * sz[r] * (1.f - sz[r]);
+      const float dr = dn * sg[r] * sr[r] * (1.f - sr[r]);
+      float* a = p.dgi + (long long)b * p.dgi_bs + (long long)t * K + u;
+      a[0] = dr; a[H] = dz; a[2 * H] = dn;
+      float* c = p.dgh + ((long long)t * p.B + b) * K + u;
+      c[0] = dr; c[H] = dz; c[2 * H] = dn * sr[r];
+      carry[r] = d * sz[r];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) signal_counter(p.counter);
+  }
+}
+
 // all 64 CTAs wait on each other: cooperative launch = the grid is placed as a whole or not yet at all (T2V_COOP=0: plain launch)
 template <typename Args>
 cudaError_t launch_coop(void (*kernel)(Args), dim3 grid, int block, size_t smem, cudaStream_t st, Args a) {
@@ -321,6 +508,48 @@ T2V_API int t2v_bilstm_seq_bwd(const float* whhT0, const float* whhT1, const flo
   }
   T2V_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64 * sizeof(unsigned), st));
   T2V_CUDA_CHECK(launch_coop(bilstm_seq_bwd_kernel, dim3(H / UPC, 2), UPC * 32, smem, st, a));
+  T2V_COUNT_LAUNCH();
+  return 0;
+}
+
+// Reference-encoder GRU, all Tq steps in one launch.  gi: rows (b, t) at gi + b * gi_bs + t * 3H (x W_ih^T without bias);
+// hs [Tq+1, B, H] with slot 0 zero (h0); save [Tq, B, 4H]; counter: 32 unsigned, zeroed by this call.  B <= 64, H <= 512.
+T2V_API int t2v_gru_seq_fwd(const float* gi, long long gi_bs, const float* w_hh, const float* b_ih, const float* b_hh, float* hs,
+                            float* save, unsigned int* counter, int B, int H, int Tq, cudaStream_t st) {
+  T2V_ARG_CHECK(gi && w_hh && b_ih && b_hh && hs && save && counter && B > 0 && Tq > 0, "null / shape");
+  T2V_ARG_CHECK(B <= MT && H % UPC == 0 && H <= 512 && H % 4 == 0, "B <= 64, H <= 512");
+  GruFwd a;
+  a.gi = gi; a.gi_bs = gi_bs; a.w_hh = w_hh; a.b_ih = b_ih; a.b_hh = b_hh; a.hs = hs; a.save = save; a.counter = counter;
+  a.B = B; a.H = H; a.Tq = Tq;
+  const size_t smem = sizeof(float) * (size_t)(((MT * (H + 1) + 3) & ~3) + H * UPC * 4);
+  static size_t cur = 48 * 1024;
+  if (smem > cur) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(gru_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
+  T2V_CUDA_CHECK(cudaMemsetAsync(counter, 0, 32 * sizeof(unsigned), st));
+  T2V_CUDA_CHECK(launch_coop(gru_seq_fwd_kernel, dim3(H / UPC), UPC * 32, smem, st, a));
+  T2V_COUNT_LAUNCH();
+  return 0;
+}
+
+// Backward through time: dh_last [B,H] -> dgi rows (b, t) at dgi + b * dgi_bs + t * 3H and dgh [Tq, B, 3H] (the caller forms
+// dW_hh = sum_t dgh[t]^T hs[t] and db_hh = colsum(dgh) as two batched reductions).
+T2V_API int t2v_gru_seq_bwd(const float* w_hh, const float* dh_last, const float* save, const float* hs, float* dgi,
+                            long long dgi_bs, float* dgh, unsigned int* counter, int B, int H, int Tq, cudaStream_t st) {
+  T2V_ARG_CHECK(w_hh && dh_last && save && hs && dgi && dgh && counter && B > 0 && Tq > 0, "null / shape");
+  T2V_ARG_CHECK(B <= MT && H % UPC == 0 && (3 * H) % 256 == 0 && H <= 512, "B <= 64, 3H % 256 == 0, H <= 512");
+  GruBwd a;
+  a.w_hh = w_hh; a.dh_last = dh_last; a.save = save; a.hs = hs; a.dgi = dgi; a.dgi_bs = dgi_bs; a.dgh = dgh; a.counter = counter;
+  a.B = B; a.H = H; a.Tq = Tq;
+  const size_t smem = sizeof(float) * (size_t)(MT * 257 + 3 * H * UPC);
+  static size_t cur = 48 * 1024;
+  if (smem > cur) {
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(gru_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
+  T2V_CUDA_CHECK(cudaMemsetAsync(counter, 0, 32 * sizeof(unsigned), st));
+  T2V_CUDA_CHECK(launch_coop(gru_seq_bwd_kernel, dim3(H / UPC), UPC * 32, smem, st, a));
   T2V_COUNT_LAUNCH();
   return 0;
 }

@@ -528,7 +528,12 @@ def refenc_forward(ops, P, mel, training, dev):
     HS = _zeros(Tq + 1, N, Hh, device=dev)
     SV = _empty(Tq, N, 4 * Hh, device=dev)
     gh = _empty(N, 3 * Hh, device=dev)
-    for t in range(Tq):
+    persist = N <= 64 and _BILSTM_PERSIST
+    if persist:        # all Tq steps in one resident kernel (rnn_persist.cu)
+        cnt = torch.zeros(32, device=dev, dtype=torch.int32)
+        L("t2v_gru_seq_fwd", GI, Tq * 3 * Hh, P[_REF + "gru.weight_hh_l0"], P[_REF + "gru.bias_ih_l0"], P[_REF + "gru.bias_hh_l0"],
+          HS, SV, cnt, N, Hh, Tq)
+    for t in range(0 if persist else Tq):
         ops.gemm(HS[t], Hh, 1, P[_REF + "gru.weight_hh_l0"], Hh, 1, gh, 3 * Hh, N, 3 * Hh, Hh)
         L("t2v_gru_pointwise_fwd", _p(GI, t * 3 * Hh), Tq * 3 * Hh, gh, P[_REF + "gru.bias_ih_l0"], P[_REF + "gru.bias_hh_l0"],
           HS[t], HS[t + 1], SV[t], N, Hh)
@@ -546,7 +551,14 @@ def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
     dhp = _empty(N, Hh, device=dev)
     gWhh = _zeros(3 * Hh, Hh, device=dev)
     bh_acc = _zeros(3 * Hh, device=dev, dtype=torch.float64)
-    for t in range(Tq - 1, -1, -1):
+    persist = N <= 64 and _BILSTM_PERSIST
+    if persist:
+        DGH = _empty(Tq, N, 3 * Hh, device=dev)
+        cnt = torch.zeros(32, device=dev, dtype=torch.int32)
+        L("t2v_gru_seq_bwd", Whh, dh_last, SV, HS, DGI, Tq * 3 * Hh, DGH, cnt, N, Hh, Tq)
+        ops.linear_dw(DGH, 3 * Hh, HS, Hh, gWhh, Hh, Tq * N, 3 * Hh, Hh, device=dev, force_exact=True)   # sum_t dgh[t]^T h[t-1]
+        L("t2v_col_stats", DGH, Tq * N, 3 * Hh, 1, 0, 1, 2, bh_acc, None)
+    for t in range(-1 if persist else Tq - 1, -1, -1):
         L("t2v_gru_pointwise_bwd", dh, SV[t], HS[t], _p(DGI, t * 3 * Hh), Tq * 3 * Hh, dgh, dhp, N, Hh, 0)
         ops.gemm(dgh, 3 * Hh, 1, Whh, 1, Hh, dhp, Hh, N, Hh, 3 * Hh, 1.0, 1.0)          # dh_prev += dgh @ W_hh
         ops.gemm(dgh, 1, 3 * Hh, HS[t], 1, Hh, gWhh, Hh, 3 * Hh, Hh, N, 1.0, 1.0)        # dW_hh += dgh^T h_prev

@@ -574,6 +574,44 @@ def test_persistent_bilstm_matches_per_step_launches(L, B, Ti, packed):
             assert torch.equal(a, b), k
 
 
+@pytest.mark.parametrize("N,To", [(64, 800), (5, 130), (1, 64)])
+def test_persistent_gru_matches_per_step_launches(L, N, To):
+    """Reference-encoder GRU (modules.py:60-80) as one resident kernel per pass (rnn_persist.cu) against the per-step GEMM + pointwise
+    launches: the forward state is bit-identical (same FFMA order); gradients differ only by summation order of the batched dW_hh."""
+    from oracle import port
+    from t2v import engine
+    dev = torch.device("cuda")
+    P = {k: v.to(dev) for k, v in port.init_params(1234).items()}
+    ops = engine.Ops("fp32")
+    g = torch.Generator().manual_seed(N * 7 + To)
+    mel = (torch.randn(N, 80, To, generator=g) * 2 - 5).to(dev)
+    dh = torch.randn(N, 256, generator=g).to(dev)
+    res = {}
+    for mode in (True, False):
+        engine._BILSTM_PERSIST = mode
+        try:
+            n0 = _launches()
+            h, ctx = engine.refenc_forward(ops, P, mel, True, dev)
+            n_fwd = _launches() - n0
+            grads = {}
+            engine.refenc_backward(ops, P, dh.clone(), ctx, True, dev, grads)
+            torch.cuda.synchronize()
+        finally:
+            engine._BILSTM_PERSIST = True
+        res[mode] = dict(h=h.clone(), HS=ctx["HS"].clone(), SV=ctx["SV"].clone(), n_fwd=n_fwd,
+                         **{"g:" + k: v.clone() for k, v in grads.items()})
+    Tq = res[True]["HS"].shape[0] - 1
+    assert res[True]["n_fwd"] <= res[False]["n_fwd"] - (2 * Tq - 1)
+    for k in res[True]:
+        if k == "n_fwd":
+            continue
+        a, b = res[True][k], res[False][k]
+        if k.startswith("g:"):
+            assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-12, k
+        else:
+            assert torch.equal(a, b), k
+
+
 def _launches():
     from t2v import _lib
     return _lib.launch_count()
