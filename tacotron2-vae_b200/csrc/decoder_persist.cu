@@ -71,18 +71,6 @@ template <int OP> struct SM {
   static constexpr int SMEM_BYTES = (OP ? OFF_F16 + 64 * 64 : OFF_TMEM + 16) + 1024;
 };
 static_assert(SM<0>::SMEM_BYTES <= 232448 && SM<1>::SMEM_BYTES <= 232448, "shared memory budget");
-// element index of (row r, k) in a [rows][32] 16-bit tile stored K-major with the 64-byte swizzle: the 16-byte chunk c = k / 8 of
-// row r sits at chunk c ^ ((r >> 1) & 3)   (verified by profiles/tools/sw64_probe.cu)
-__device__ __forceinline__ int swz64(int r, int k) { return r * 32 + ((((k >> 3) ^ (r >> 1)) & 3) << 3) + (k & 7); }
-__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;          // SBO: 8 rows of 64 bytes
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;                   // SWIZZLE_64B
-  return d;
-}
 struct PersistParams {
   T2VDecoderSeq s;
   int t_begin, t_end;

@@ -29,7 +29,10 @@ constexpr int NF = 32, KS = 31, HALO = 15;
 constexpr unsigned SITE_ATT_H = 10, SITE_ATT_C = 11, SITE_DEC_H = 12, SITE_DEC_C = 13;
 constexpr int CL = 4, NCLUSTER = 32, NCTA = CL * NCLUSTER, NTHREADS = 512;
 constexpr int XA_CPC = XA_W / NCLUSTER, XD_CPC = XD_W / NCLUSTER;   // 56 / 80 output columns per cluster
-constexpr int NS = 5;                          // ring depth: a stage = one K chunk: W^T tile (<= 80 rows, 10 KB) + gate gradients (8 KB)
+// ring depth: a stage = one K chunk: W^T tile (<= 80 rows, 10 KB) + gate gradients (8 KB)
+#ifndef T2V_BWD_NS
+#define T2V_BWD_NS 5
+#endif
 constexpr int W_PART = 80 * 128, A_STAGE = 64 * 128, STAGE = W_PART + A_STAGE;
 constexpr int KCH32 = 32;                      // fp32 storage: 32-wide K chunks per CTA and GEMM (K slice = 4096 / 4)
 // op16: the W^T tiles and the gate gradients stream as fp16 copies (kind::f16), 64 K columns per 128-byte row -> 16 chunks of the
@@ -40,30 +43,46 @@ template <int OP> struct KC { static constexpr int N = OP ? 16 : 32, W = OP ? 64
 constexpr int RA_P = 64, RD_P = 80;            // column pitch of the exchange slots [src][batch row 16][cols]
 constexpr int TH_MAX = 64, FS = 36;
 constexpr int BAR_EPI = 1, BAR_ATT = 2;
+constexpr int US_P = 33;                       // row pitch of the staged adjoint-conv products (op16)
 
-constexpr int OFF_RING = 0;
-constexpr int OFF_RECVA = OFF_RING + NS * STAGE;
-constexpr int OFF_RECVD = OFF_RECVA + 4 * 16 * RA_P * 4;
-constexpr int OFF_ABUF = OFF_RECVD + 4 * 16 * RD_P * 4;            // [TH_MAX][128] saved tanh -> dpre (in place)
-constexpr int OFF_F = OFF_ABUF + TH_MAX * AD * 4;                   // [TH_MAX][FS] conv output f -> df (in place)
-constexpr int OFF_WCT = OFF_F + TH_MAX * FS * 4;                    // [62][32]
-constexpr int OFF_WLOC = OFF_WCT + 2 * KS * NF * 4;                 // [128][32]
-// dHq = dq W_q on the tensor core (per CTA: 32 units x 16 batch rows, K = 128 attention dims): fp16 operands, K-major rows of 128
-// bytes (SWIZZLE_128B), two K blocks of 64.  A = W_q^T slice [64 rows: 32 units + 32 zero rows][128 a] (static), B = dq rows of this CTA
-// [16 b][128 a], scaled by a per-CTA power of two so that gradient magnitudes sit inside the fp16 range; D [unit][b] in TMEM.
-constexpr int OFF_WQ16 = (OFF_WLOC + AD * NF * 4 + 1023) / 1024 * 1024;   // 2 blocks x [64][64] fp16 = 16 KB
-constexpr int OFF_DQ16 = OFF_WQ16 + 2 * 64 * 128;                          // 2 blocks x [16][64] fp16 = 4 KB
-constexpr int OFF_DHQ = OFF_DQ16 + 2 * 16 * 128;                           // [16][32] fp32 result tile + [4] partial maxima
-constexpr int OFF_DCTX = OFF_DHQ + 16 * 32 * 4 + 16;                       // [512]
-constexpr int OFF_SMALL = OFF_DCTX + ED * 4;
 // small arrays (floats): wpad[160] cpad[160] wt[64] dwv[64] de[64] Ps[64] Gs[64] adj[2][64] halo[2][2][64] spart[2][2] q_s[2][128]
+// tmax[8]
 constexpr int SM_WPAD = 0, SM_CPAD = 160, SM_WT = 320, SM_DWV = 384, SM_DE = 448, SM_P = 512, SM_G = 576, SM_ADJ = 640,
-              SM_HALO = 768, SM_SPART = 1024, SM_QS = 1028, SM_TOTAL = 1284;
-constexpr int OFF_BARS = OFF_SMALL + ((SM_TOTAL * 4 + 15) / 16) * 16;
-constexpr int N_BARS = 2 * NS + 10;
-constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
-static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+              SM_HALO = 768, SM_SPART = 1024, SM_QS = 1028, SM_TMAX = 1284, SM_TOTAL = 1292;
+constexpr int N_BARS_MAX = 2 * 5 + 12;
+
+// Shared-memory map.  op16 trades one ring stage and the fp32 location-dense weights for the fp16 operands of the attention-tail
+// UMMAs (dW_loc, df, adjoint-conv products; see the attention warps).
+template <int OP> struct LY {
+  static constexpr int NS = OP ? (T2V_BWD_NS > 4 ? 4 : T2V_BWD_NS) : T2V_BWD_NS;
+  static constexpr int OFF_RING = 0;
+  static constexpr int OFF_RECVA = OFF_RING + NS * STAGE;
+  static constexpr int OFF_RECVD = OFF_RECVA + 4 * 16 * RA_P * 4;
+  static constexpr int OFF_ABUF = OFF_RECVD + 4 * 16 * RD_P * 4;            // [TH_MAX][128] saved tanh -> dpre (in place)
+  static constexpr int OFF_F = OFF_ABUF + TH_MAX * AD * 4;                   // [TH_MAX][FS] conv output f -> df (in place)
+  static constexpr int OFF_WCT = OFF_F + TH_MAX * FS * 4;                    // [62][32]
+  static constexpr int OFF_WLOC = OFF_WCT + 2 * KS * NF * 4;                 // [128][32] fp32 (FFMA path only)
+  // dHq = dq W_q on the tensor core (per CTA: 32 units x 16 batch rows, K = 128 attention dims): fp16 operands, K-major rows of 128
+  // bytes (SWIZZLE_128B), two K blocks of 64.  A = W_q^T slice [64 rows: 32 units + 32 zero rows][128 a] (static), B = dq rows of this
+  // CTA [16 b][128 a], scaled by a per-CTA power of two so that gradient magnitudes sit inside the fp16 range; D [unit][b] in TMEM.
+  static constexpr int OFF_WQ16 = (OFF_WLOC + (OP ? 0 : AD * NF * 4) + 1023) / 1024 * 1024;   // 2 blocks x [64][64] fp16 = 16 KB
+  static constexpr int OFF_DQ16 = OFF_WQ16 + 2 * 64 * 128;                   // 2 blocks x [16][64] fp16 = 4 KB
+  // op16 attention tail: dpre [64 rows][128 a] (2 SW128 blocks), f^T [32 filters][64 rows] (SW128), W_loc^T [32][128 a] (2 SW128
+  // blocks), df [64 rows][32 filters] (SW64), W_conv [64 = 2 x 32 taps][32 filters] (SW64)
+  static constexpr int OFF_DP16 = OFF_DQ16 + 2 * 16 * 128;
+  static constexpr int OFF_F16T = OFF_DP16 + (OP ? 2 * 64 * 128 : 0);
+  static constexpr int OFF_WL16T = OFF_F16T + (OP ? 32 * 128 : 0);
+  static constexpr int OFF_DF16 = OFF_WL16T + (OP ? 2 * 32 * 128 : 0);
+  static constexpr int OFF_WC16 = OFF_DF16 + (OP ? 64 * 64 : 0);
+  static constexpr int OFF_DHQ = OFF_WC16 + (OP ? 64 * 64 : 0);              // [16][32] fp32 result tile + [4] partial maxima
+  static constexpr int OFF_DCTX = OFF_DHQ + 16 * 32 * 4 + 16;                // [512]
+  static constexpr int OFF_SMALL = OFF_DCTX + ED * 4;
+  static constexpr int OFF_BARS = OFF_SMALL + ((SM_TOTAL * 4 + 15) / 16) * 16;
+  static constexpr int OFF_TMEM = OFF_BARS + N_BARS_MAX * 8;
+  static constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(2 * TH_MAX * US_P * 4 <= TH_MAX * AD * 4, "adjoint products are staged in the tanh tile");
+};
 
 __device__ __forceinline__ uint16_t f16_sat(float x) {      // round to nearest, clamp to +-65504 instead of producing inf
   uint16_t h;
@@ -92,22 +111,29 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
                        const __grid_constant__ CUtensorMap tmGD, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* ring = smem + OFF_RING;        // stage s: [W^T tile 10 KB | gate gradients 8 KB]; the M=128 descriptor of the dXD
+  using L = LY<OP>;
+  constexpr int NS = L::NS;
+  uint8_t* ring = smem + L::OFF_RING;     // stage s: [W^T tile 10 KB | gate gradients 8 KB]; the M=128 descriptor of the dXD
                                           // GEMM reads 48 rows past the 80 loaded ones (into the gradient part): those
                                           // accumulator rows are never drained
-  float* recv_a = (float*)(smem + OFF_RECVA);
-  float* recv_d = (float*)(smem + OFF_RECVD);
-  float* Abuf = (float*)(smem + OFF_ABUF);
-  float* f_s = (float*)(smem + OFF_F);
-  float* wcT = (float*)(smem + OFF_WCT);
-  float* WlocS = (float*)(smem + OFF_WLOC);
-  uint16_t* wq16 = (uint16_t*)(smem + OFF_WQ16);
-  uint16_t* dq16 = (uint16_t*)(smem + OFF_DQ16);
-  float* dhq_s = (float*)(smem + OFF_DHQ);
+  float* recv_a = (float*)(smem + L::OFF_RECVA);
+  float* recv_d = (float*)(smem + L::OFF_RECVD);
+  float* Abuf = (float*)(smem + L::OFF_ABUF);
+  float* f_s = (float*)(smem + L::OFF_F);
+  float* wcT = (float*)(smem + L::OFF_WCT);
+  float* WlocS = (float*)(smem + L::OFF_WLOC);
+  uint16_t* wq16 = (uint16_t*)(smem + L::OFF_WQ16);
+  uint16_t* dq16 = (uint16_t*)(smem + L::OFF_DQ16);
+  uint16_t* dp16 = (uint16_t*)(smem + L::OFF_DP16);
+  uint16_t* f16T = (uint16_t*)(smem + L::OFF_F16T);
+  uint16_t* wl16T = (uint16_t*)(smem + L::OFF_WL16T);
+  uint16_t* df16 = (uint16_t*)(smem + L::OFF_DF16);
+  uint16_t* wc16 = (uint16_t*)(smem + L::OFF_WC16);
+  float* dhq_s = (float*)(smem + L::OFF_DHQ);
   float* qmax_s = dhq_s + 16 * 32;
-  float* dctx_s = (float*)(smem + OFF_DCTX);
-  float* small = (float*)(smem + OFF_SMALL);
-  uint64_t* bars = (uint64_t*)(smem + OFF_BARS);
+  float* dctx_s = (float*)(smem + L::OFF_DCTX);
+  float* small = (float*)(smem + L::OFF_SMALL);
+  uint64_t* bars = (uint64_t*)(smem + L::OFF_BARS);
   uint64_t* full = bars;                  // [NS] both producers arrive (count 2) with their byte counts: ONE wait per chunk
   uint64_t* empty = full + NS;            // [NS]
   uint64_t* acc_full = empty + NS;        // [2]: 0 = DXA GEMM, 1 = dXD GEMM
@@ -117,7 +143,9 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
   uint64_t* x_full = at_full + 1;         // partner's softmax-backward partial sum landed
   uint64_t* h_full = x_full + 1;          // partner's adjoint-conv halo landed
   uint64_t* dq_full = h_full + 1;         // the dHq MMA of this iteration has retired
-  uint32_t* tmem_holder = (uint32_t*)(smem + OFF_TMEM);
+  uint64_t* t1_full = dq_full + 1;        // op16 attention tail: the dW_loc / df MMAs have retired
+  uint64_t* t2_full = t1_full + 1;        // op16 attention tail: the adjoint-conv product MMAs have retired
+  uint32_t* tmem_holder = (uint32_t*)(smem + L::OFF_TMEM);
 
   constexpr int KCH = KC<OP>::N, CKW = KC<OP>::W;
   const T2VDecoderBwd& d = p.d;
@@ -161,6 +189,8 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     mbar_init(x_full, 1);
     mbar_init(h_full, 1);
     mbar_init(dq_full, 1);
+    mbar_init(t1_full, 1);
+    mbar_init(t2_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -348,6 +378,22 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       const float pdrop = which ? p_dec : p_att;
       const float kscale = 1.f / (1.f - pdrop);
       const float* mk = s.drop_masks ? s.drop_masks + (long long)ts * 4 * B * H + (which ? 2LL * B * H : 0) : nullptr;
+      // the same lines of the NEXT iteration (step ts - 1) are pulled from HBM into L2 now: the loads below then cost an L2 hit
+      // instead of a DRAM round trip inside the epilogue warps' serial program (the slowest CTA sets the pace of every step)
+      if (ts > 0) {
+        const long long rp = (long long)(ts - 1) * B;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int b = 16 * rank + blq + 4 * j;
+          if (b < B) {
+            const float* gs = Gs + (rp + b) * 4 * H + jg;
+            prefetch_l2(gs); prefetch_l2(gs + H); prefetch_l2(gs + 2 * H); prefetch_l2(gs + 3 * H);
+            prefetch_l2(CPs + (rp + b) * H + jg);
+            prefetch_l2(Cs + (rp + b) * H + jg);
+            if (which) prefetch_l2(d.DHC + (rp + b) * (H + ED) + jg);
+          }
+        }
+      }
       // saved forward activations: independent of the recurrence, in flight while the counters are polled
       float sg[4][4], sc2[4], scp[4];
 #pragma unroll
@@ -599,7 +645,24 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
     float* halo_s = small + SM_HALO; float* spart = small + SM_SPART; float* q_s = small + SM_QS;
     const float va = s.v[a];
     for (int i = atid; i < 2 * KS * NF; i += 256) wcT[i] = s.Wconv[i];
-    for (int i = atid; i < AD * NF; i += 256) WlocS[i] = s.Wloc[i];
+    if constexpr (OP) {
+      // W_loc^T as the B operand of df = dpre W_loc: element (filter c, a) at K block a / 64, row c, chunk ((a % 64) / 8) ^ (c & 7);
+      // W_conv as the B operand of the adjoint products: row n = 32 ch + tap (tap 31 = zero row), 32 filters = 64-byte rows (SW64)
+      for (int i = atid; i < AD * NF; i += 256) {
+        const int aa = i >> 5, c = i & 31, kk = aa & 63;
+        wl16T[(aa >> 6) * (32 * 64) + c * 64 + ((((kk >> 3) ^ (c & 7)) << 3) | (kk & 7))] = t2v_f16_bits(s.Wloc[i]);
+      }
+      for (int i = atid; i < 64 * NF; i += 256) {
+        const int n = i >> 5, c = i & 31, ch = n >> 5, k = n & 31;
+        wc16[swz64(n, c)] = (k < KS) ? t2v_f16_bits(s.Wconv[(ch * KS + k) * NF + c]) : (uint16_t)0;
+      }
+      for (int i = atid; i < 2 * 64 * 64; i += 256) dp16[i] = 0;
+      for (int i = atid; i < 32 * 64; i += 256) f16T[i] = 0;
+      for (int i = atid; i < 64 * 32; i += 256) df16[i] = 0;
+      fence_proxy_async();
+    } else {
+      for (int i = atid; i < AD * NF; i += 256) WlocS[i] = s.Wloc[i];
+    }
     for (int i = atid; i < SM_TOTAL; i += 256) small[i] = 0.f;
     const uint32_t partner_spart = mapa(smem_u32(spart), (uint32_t)(rank ^ 1));
     const uint32_t partner_x = mapa(smem_u32(x_full), (uint32_t)(rank ^ 1));
@@ -633,6 +696,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
             bulk_load_1d(Abuf, s.ASAVE + (((long long)t * B + b) * Ti + i0) * AD, (uint32_t)nrow * AD * 4u, at_full);
           }
         }
+        if (t > 0 && atid < ED / 32) prefetch_l2(d.DHC + ((long long)(t - 1) * B + b) * (H + ED) + H + 32 * atid);   // next step's dctx term
         for (int i = atid; i < Ti; i += 256) {
           wpad[HALO + i] = (t > 0) ? __ldg(s.align + ((long long)b * To + (t - 1)) * Ti + i) : 0.f;
           cpad[HALO + i] = __ldg(s.CUM + ((long long)t * B + b) * Ti + i);
@@ -659,8 +723,17 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
                 for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, xr[j + k], acc[j]);
               }
             }
+            if constexpr (OP) {     // f^T [filter c][rows]: 8 consecutive rows = one 16-byte chunk of the K-major operand
+              uint4 pk;
+              pk.x = (uint32_t)t2v_f16_bits(acc[0]) | ((uint32_t)t2v_f16_bits(acc[1]) << 16);
+              pk.y = (uint32_t)t2v_f16_bits(acc[2]) | ((uint32_t)t2v_f16_bits(acc[3]) << 16);
+              pk.z = (uint32_t)t2v_f16_bits(acc[4]) | ((uint32_t)t2v_f16_bits(acc[5]) << 16);
+              pk.w = (uint32_t)t2v_f16_bits(acc[6]) | ((uint32_t)t2v_f16_bits(acc[7]) << 16);
+              *reinterpret_cast<uint4*>(f16T + c * 64 + ((((r0 >> 3) ^ (c & 7)) & 7) << 3)) = pk;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f_s[(r0 + j) * FS + c] = acc[j];
+              for (int j = 0; j < 8; ++j) f_s[(r0 + j) * FS + c] = acc[j];
+            }
           }
         }
       }
@@ -685,7 +758,46 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         named_bar(BAR_ATT, 256);
         if (atid == 0) TR(it, 18);
         // ---- dw_i = <dctx, memory_i> + (gradient wrt w_t from step t+1's location conv) + (gradient wrt cum_{t+1})
-        {
+        if (OP && s.mem16 != nullptr) {
+          // fp16 copy of the encoder memory (exact: the memory sits on the tf32 grid): half the L2 bytes of this reduction, which is
+          // on the critical path of the step.  lane -> columns [8 lane, 8 lane + 8) and [256 + 8 lane, ...); warp -> rows aw + 8 k
+          float dc[2][8];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float4 lo = *reinterpret_cast<const float4*>(dctx_s + 256 * j + lane * 8);
+            const float4 hi = *reinterpret_cast<const float4*>(dctx_s + 256 * j + lane * 8 + 4);
+            dc[j][0] = lo.x; dc[j][1] = lo.y; dc[j][2] = lo.z; dc[j][3] = lo.w;
+            dc[j][4] = hi.x; dc[j][5] = hi.y; dc[j][6] = hi.z; dc[j][7] = hi.w;
+          }
+          const uint16_t* mb = reinterpret_cast<const uint16_t*>(s.mem16) + ((long long)b * Ti + i0) * ED + lane * 8;
+          for (int rb = 0; rb < nrow; rb += 32) {
+            uint4 mv[4][2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = rb + aw + 8 * k;
+              const bool ld = rr < nrow && (i0 + rr) < len;
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                mv[k][j] = ld ? ldg_u4_hint(mb + (long long)rr * ED + 256 * j, pol_m) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = rb + aw + 8 * k;
+              float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t w4[4] = {mv[k][j].x, mv[k][j].y, mv[k][j].z, mv[k][j].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  acc0 = fmaf(dc[j][2 * i], t2v_f16_to_f32((uint16_t)(w4[i] & 0xFFFFu)), acc0);
+                  acc1 = fmaf(dc[j][2 * i + 1], t2v_f16_to_f32((uint16_t)(w4[i] >> 16)), acc1);
+                }
+              }
+              const float acc = warp_sum(acc0 + acc1);
+              if (lane == 0 && rr < nrow) dwv_s[rr] = acc + G_s[rr] + P_s[rr];
+            }
+          }
+        } else {
           float4 dc4[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) dc4[j] = *reinterpret_cast<const float4*>(dctx_s + lane * 4 + 128 * j);
@@ -761,47 +873,157 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
       if (atid == 0) { GT(it, 2); signal_counter(cnt_q); TR(it, 23); GT(it, 4); }
       // ================= off the critical path: weight gradients of the location layer, adjoint conv for step t-1
       if (active) {
-        // ---- dW_loc[a][c] += sum_rows dpre[row][a] f[row][c]   (thread: a, 16 of the 32 filters, all rows)
-        {
-          const int cb = (atid >> 7) * 16;
-          for (int rr = 0; rr < nrow; ++rr) {
-            const float dp = Abuf[rr * AD + a];
-            const float4* fr = reinterpret_cast<const float4*>(f_s + rr * FS + cb);
+        float t_inv = 1.f;
+        if constexpr (OP) {
+          // ---- op16: dW_loc and df on the tensor core.  dpre of this step (fp32, in the tanh tile) -> fp16 copy scaled by a power of
+          // two that puts the largest |dpre| of the tile into [2^9, 2^10) (gradients are ~1e-8; df = dpre W_loc then stays below the
+          // fp16 maximum), rows >= nrow zero.  Thread -> 16-byte chunks (row, 8 attention dims): chunk index atid + 256 i.
+          float mx = 0.f;
+          float4 dv4[4][2];
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const float4 f4 = fr[c4];
-              gwl[4 * c4] = fmaf(dp, f4.x, gwl[4 * c4]); gwl[4 * c4 + 1] = fmaf(dp, f4.y, gwl[4 * c4 + 1]);
-              gwl[4 * c4 + 2] = fmaf(dp, f4.z, gwl[4 * c4 + 2]); gwl[4 * c4 + 3] = fmaf(dp, f4.w, gwl[4 * c4 + 3]);
-            }
+          for (int i = 0; i < 4; ++i) {
+            const int ci = atid + 256 * i, row = ci >> 4, ch8 = ci & 15;
+            const float4* src = reinterpret_cast<const float4*>(Abuf + row * AD + ch8 * 8);
+            const bool live = row < nrow;
+            dv4[i][0] = live ? src[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+            dv4[i][1] = live ? src[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+              mx = fmaxf(mx, fmaxf(fmaxf(fabsf(dv4[i][h2].x), fabsf(dv4[i][h2].y)), fmaxf(fabsf(dv4[i][h2].z), fabsf(dv4[i][h2].w))));
           }
-        }
-        // ---- df[row][c] = sum_a dpre[row][a] W_loc[a][c]   (thread: filter c, 8 rows)
-        float dfr[8];
-        {
-          const int c = atid & 31, r0 = (atid >> 5) * 8;
+          mx = warp_max(mx);
+          float* tmax = small + SM_TMAX;
+          if (lane == 0) tmax[aw] = mx;
+          named_bar(BAR_ATT, 256);
+          mx = fmaxf(fmaxf(fmaxf(tmax[0], tmax[1]), fmaxf(tmax[2], tmax[3])), fmaxf(fmaxf(tmax[4], tmax[5]), fmaxf(tmax[6], tmax[7])));
+          int ex = 0;
+          (void)frexpf(mx, &ex);
+          const float t_scale = (mx > 0.f) ? exp2f((float)(10 - ex)) : 1.f;
+          t_inv = 1.f / t_scale;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dfr[j] = 0.f;
-          if (r0 < nrow) {
-#pragma unroll 2
-            for (int a0 = 0; a0 < AD; a0 += 4) {
-              const float w0 = WlocS[a0 * NF + c], w1 = WlocS[(a0 + 1) * NF + c], w2 = WlocS[(a0 + 2) * NF + c], w3 = WlocS[(a0 + 3) * NF + c];
+          for (int i = 0; i < 4; ++i) {
+            const int ci = atid + 256 * i, row = ci >> 4, ch8 = ci & 15;
+            const float4 lo = dv4[i][0], hi = dv4[i][1];
+            uint4 pk;
+            pk.x = (uint32_t)t2v_f16_bits(lo.x * t_scale) | ((uint32_t)t2v_f16_bits(lo.y * t_scale) << 16);
+            pk.y = (uint32_t)t2v_f16_bits(lo.z * t_scale) | ((uint32_t)t2v_f16_bits(lo.w * t_scale) << 16);
+            pk.z = (uint32_t)t2v_f16_bits(hi.x * t_scale) | ((uint32_t)t2v_f16_bits(hi.y * t_scale) << 16);
+            pk.w = (uint32_t)t2v_f16_bits(hi.z * t_scale) | ((uint32_t)t2v_f16_bits(hi.w * t_scale) << 16);
+            *reinterpret_cast<uint4*>(dp16 + (ch8 >> 3) * (64 * 64) + row * 64 + (((ch8 & 7) ^ (row & 7)) << 3)) = pk;
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          named_bar(BAR_ATT, 256);
+          tc_fence_after();
+          if (aw == 0 && elect_one()) {
+            // df [64 rows, 32 filters] = dpre [rows][a] (K-major A) x W_loc^T [filters][a] (K-major B), K = 128 -> TMEM columns 176..207
+            constexpr uint32_t id_df = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 d4 = *reinterpret_cast<const float4*>(Abuf + (r0 + j) * AD + a0);
-                dfr[j] = fmaf(d4.x, w0, dfr[j]); dfr[j] = fmaf(d4.y, w1, dfr[j]);
-                dfr[j] = fmaf(d4.z, w2, dfr[j]); dfr[j] = fmaf(d4.w, w3, dfr[j]);
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t ad = make_kmajor_sw128_desc(smem_u32(dp16) + kb * (64 * 128));
+              const uint64_t bd = make_kmajor_sw128_desc(smem_u32(wl16T) + kb * (32 * 128));
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                tc_mma_f16(tmem_base + 176u, ad + (uint64_t)(2 * k4), bd + (uint64_t)(2 * k4), id_df, (kb | k4) ? 1u : 0u);
+            }
+            // dW_loc [128 a, 32 filters] = dpre^T (the SAME tile read MN-major: a contiguous, rows = K) x f^T [filters][rows]
+            // (K-major B), K = 64 rows -> TMEM columns 144..175
+            constexpr uint32_t id_wl = (1u << 4) | (1u << 15) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t am = make_mnmajor16_sw128_desc(smem_u32(dp16), 64 * 128);
+            const uint64_t bf = make_kmajor_sw128_desc(smem_u32(f16T));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16(tmem_base + 144u, am + (uint64_t)(128 * k), bf + (uint64_t)(2 * k), id_wl, k ? 1u : 0u);
+            tc_commit(t1_full);
+          }
+          __syncwarp();
+          mbar_wait(t1_full, (unsigned)it & 1u);
+          tc_fence_after();
+          {
+            const int q4 = aw & 3, chalf = aw >> 2;
+            uint32_t wv[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + 144u + (uint32_t)(16 * chalf), wv);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) gwl[c] = fmaf(__uint_as_float(wv[c]), t_inv, gwl[c]);
+            // M = 64: accumulator row 16 q + l sits in TMEM lane 32 q + l (l < 16)
+            uint32_t fv[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + 176u + (uint32_t)(16 * chalf), fv);
+            if (lane < 16) {
+              const int row = 16 * q4 + lane, c0 = 16 * chalf;
+              float4* fo = reinterpret_cast<float4*>(f_s + row * FS + c0);
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4)
+                fo[c4] = make_float4(__uint_as_float(fv[4 * c4]) * t_inv, __uint_as_float(fv[4 * c4 + 1]) * t_inv,
+                                     __uint_as_float(fv[4 * c4 + 2]) * t_inv, __uint_as_float(fv[4 * c4 + 3]) * t_inv);
+#pragma unroll
+              for (int c8 = 0; c8 < 2; ++c8) {
+                uint4 pk;
+                pk.x = (uint32_t)f16_sat(__uint_as_float(fv[8 * c8])) | ((uint32_t)f16_sat(__uint_as_float(fv[8 * c8 + 1])) << 16);
+                pk.y = (uint32_t)f16_sat(__uint_as_float(fv[8 * c8 + 2])) | ((uint32_t)f16_sat(__uint_as_float(fv[8 * c8 + 3])) << 16);
+                pk.z = (uint32_t)f16_sat(__uint_as_float(fv[8 * c8 + 4])) | ((uint32_t)f16_sat(__uint_as_float(fv[8 * c8 + 5])) << 16);
+                pk.w = (uint32_t)f16_sat(__uint_as_float(fv[8 * c8 + 6])) | ((uint32_t)f16_sat(__uint_as_float(fv[8 * c8 + 7])) << 16);
+                *reinterpret_cast<uint4*>(df16 + swz64(row, c0 + 8 * c8)) = pk;
               }
             }
           }
-        }
-        named_bar(BAR_ATT, 256);             // every reader of f is done: f_s becomes df
-        if (atid == 0) TR(it, 24);
-        {
-          const int c = atid & 31, r0 = (atid >> 5) * 8;
+          fence_proxy_async();
+          tc_fence_before();
+          named_bar(BAR_ATT, 256);
+          tc_fence_after();
+          if (atid == 0) TR(it, 24);
+          if (aw == 0 && elect_one()) {
+            // adjoint-conv products U [64 rows, 2 x 32 taps] = df [rows][filters] x W_conv [(ch, tap)][filters], K = 32 (SW64 operands)
+            // -> TMEM columns 176..239 (df has been drained)
+            constexpr uint32_t id_u = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+            const uint64_t ad = make_kmajor_sw64_desc(smem_u32(df16)), bd = make_kmajor_sw64_desc(smem_u32(wc16));
+            tc_mma_f16(tmem_base + 176u, ad, bd, id_u, 0u);
+            tc_mma_f16(tmem_base + 176u, ad + 2, bd + 2, id_u, 1u);
+            tc_commit(t2_full);
+          }
+          __syncwarp();
+        } else {
+          // ---- dW_loc[a][c] += sum_rows dpre[row][a] f[row][c]   (thread: a, 16 of the 32 filters, all rows)
+          {
+            const int cb = (atid >> 7) * 16;
+            for (int rr = 0; rr < nrow; ++rr) {
+              const float dp = Abuf[rr * AD + a];
+              const float4* fr = reinterpret_cast<const float4*>(f_s + rr * FS + cb);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f_s[(r0 + j) * FS + c] = (r0 + j < nrow) ? dfr[j] : 0.f;
+              for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 f4 = fr[c4];
+                gwl[4 * c4] = fmaf(dp, f4.x, gwl[4 * c4]); gwl[4 * c4 + 1] = fmaf(dp, f4.y, gwl[4 * c4 + 1]);
+                gwl[4 * c4 + 2] = fmaf(dp, f4.z, gwl[4 * c4 + 2]); gwl[4 * c4 + 3] = fmaf(dp, f4.w, gwl[4 * c4 + 3]);
+              }
+            }
+          }
+          // ---- df[row][c] = sum_a dpre[row][a] W_loc[a][c]   (thread: filter c, 8 rows)
+          float dfr[8];
+          {
+            const int c = atid & 31, r0 = (atid >> 5) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dfr[j] = 0.f;
+            if (r0 < nrow) {
+#pragma unroll 2
+              for (int a0 = 0; a0 < AD; a0 += 4) {
+                const float w0 = WlocS[a0 * NF + c], w1 = WlocS[(a0 + 1) * NF + c], w2 = WlocS[(a0 + 2) * NF + c], w3 = WlocS[(a0 + 3) * NF + c];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 d4 = *reinterpret_cast<const float4*>(Abuf + (r0 + j) * AD + a0);
+                  dfr[j] = fmaf(d4.x, w0, dfr[j]); dfr[j] = fmaf(d4.y, w1, dfr[j]);
+                  dfr[j] = fmaf(d4.z, w2, dfr[j]); dfr[j] = fmaf(d4.w, w3, dfr[j]);
+                }
+              }
+            }
+          }
+          named_bar(BAR_ATT, 256);             // every reader of f is done: f_s becomes df
+          if (atid == 0) TR(it, 24);
+          {
+            const int c = atid & 31, r0 = (atid >> 5) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f_s[(r0 + j) * FS + c] = (r0 + j < nrow) ? dfr[j] : 0.f;
+          }
+          named_bar(BAR_ATT, 256);
         }
-        named_bar(BAR_ATT, 256);
         // ---- dW_conv[(ch,k)][c] += sum_rows df[row][c] x_ch[row + k - 15]: thread = (filter c, channel, 8 consecutive taps),
         // the taps share one sliding window of x (3 shared-memory loads per row instead of 16)
         {
@@ -823,21 +1045,47 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         if (atid == 0) TR(it, 25);
         // ---- adjoint conv: dx[ch][s] = sum_{k,c} df[s-k+15][c] W_conv[c][ch][k], s in [i0-15, i0+nrow+15);
         // own rows stay here, the rows of the other half go to the partner CTA
+        float* Us = Abuf;                    // op16: [2 channels][64 rows][US_P] products, staged in the (now dead) tanh tile
+        if constexpr (OP) {
+          mbar_wait(t2_full, (unsigned)it & 1u);
+          tc_fence_after();
+          if (t > 0) {
+            uint32_t uv[32];
+            tmem_ld32(tmem_base + ((uint32_t)((aw & 3) * 32) << 16) + 176u + (uint32_t)(32 * (aw >> 2)), uv);
+            if (lane < 16) {
+              float* dst = Us + ((aw >> 2) * TH_MAX + 16 * (aw & 3) + lane) * US_P;
+#pragma unroll
+              for (int k = 0; k < KS; ++k) dst[k] = __uint_as_float(uv[k]);
+            }
+          }
+          tc_fence_before();
+          named_bar(BAR_ATT, 256);
+        }
         if (t > 0) {
           const int span = nrow + 2 * HALO;
           if (atid < 2 * span) {
             const int ch = atid / span, j = atid - ch * span;
             const int sidx = i0 - HALO + j;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            for (int k = 0; k < KS; ++k) {
-              const int tt = j - k;
-              if (tt >= 0 && tt < nrow) {
-                const float4* dfp = reinterpret_cast<const float4*>(f_s + tt * FS);
-                const float4* wk = reinterpret_cast<const float4*>(wcT + (ch * KS + k) * NF);
+            if constexpr (OP) {
+              // dx[ch][s] = sum_k U[s - k + 15][ch][k]: one anti-diagonal of the product tile (pitch 33: conflict-free)
+              const float* u0 = Us + ch * TH_MAX * US_P;
+              for (int k = 0; k < KS; ++k) {
+                const int tt = j - k;
+                if (tt >= 0 && tt < nrow) a0 += u0[tt * US_P + k];
+              }
+              a0 *= t_inv;
+            } else {
+              for (int k = 0; k < KS; ++k) {
+                const int tt = j - k;
+                if (tt >= 0 && tt < nrow) {
+                  const float4* dfp = reinterpret_cast<const float4*>(f_s + tt * FS);
+                  const float4* wk = reinterpret_cast<const float4*>(wcT + (ch * KS + k) * NF);
 #pragma unroll
-                for (int c4 = 0; c4 < NF / 4; ++c4) {
-                  const float4 x4 = dfp[c4], w4 = wk[c4];
-                  a0 = fmaf(x4.x, w4.x, a0); a1 = fmaf(x4.y, w4.y, a1); a2 = fmaf(x4.z, w4.z, a2); a3 = fmaf(x4.w, w4.w, a3);
+                  for (int c4 = 0; c4 < NF / 4; ++c4) {
+                    const float4 x4 = dfp[c4], w4 = wk[c4];
+                    a0 = fmaf(x4.x, w4.x, a0); a1 = fmaf(x4.y, w4.y, a1); a2 = fmaf(x4.z, w4.z, a2); a3 = fmaf(x4.w, w4.w, a3);
+                  }
                 }
               }
             }
@@ -860,6 +1108,7 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           }
         }
       }
+      if constexpr (OP) fence_proxy_async();     // generic writes into the tanh tile (products) before the next bulk load into it
       named_bar(BAR_ATT, 256);
       if (atid == 0) TR(it, 26);
     }
@@ -922,13 +1171,14 @@ int t2v_decoder_bwd_persist(const T2VDecoderBwd* d, int t_hi, int t_lo, cudaStre
   if (!mc_init) { for (auto& row : max_clusters_dev) for (int& v : row) v = -1; mc_init = true; }
   int& max_clusters = max_clusters_dev[t2v_device_slot()][op];
   static bool attr_set[2] = {false, false};
+  const int smem_bytes = op ? LY<1>::SMEM_BYTES : LY<0>::SMEM_BYTES;
   if (!attr_set[op]) {
-    T2V_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    T2V_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set[op] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(NCTA); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+  cfg.gridDim = dim3(NCTA); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

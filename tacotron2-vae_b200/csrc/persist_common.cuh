@@ -106,6 +106,31 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;   // SWIZZLE_128B
   return d;
 }
+// element index of (row r, k) in a [rows][32] 16-bit tile stored K-major with the 64-byte swizzle: the 16-byte chunk c = k / 8 of
+// row r sits at chunk c ^ ((r >> 1) & 3)   (verified by profiles/tools/sw64_probe.cu)
+__device__ __forceinline__ int swz64(int r, int k) { return r * 32 + ((((k >> 3) ^ (r >> 1)) & 3) << 3) + (k & 7); }
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;          // SBO: 8 rows of 64 bytes
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                   // SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// MN-major 16-bit operand read from a 128B-swizzled tile whose rows are the REDUCTION index (row r = 128 bytes = 64 consecutive M / N
+// elements, 16-byte chunk c at c ^ (r & 7)): the same bytes a K-major SW128 tile [rows][64] holds.  LBO = distance between groups of
+// 64 M / N elements, SBO = 8 reduction rows; one K = 16 instruction advances the start address by 16 rows = 2048 bytes.
+__device__ __forceinline__ uint64_t make_mnmajor16_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
