@@ -41,7 +41,7 @@ if os.environ.get("T2V_PROFILE_LIST"):      # per-launch durations (us) of the k
     print("per-launch us of *%s*: %s" % (pat, " ".join("%.0f" % (e.device_time if hasattr(e, "device_time") else e.cuda_time) for e in evs[:len(evs) // N])))
 tot = sum(v[1] for v in agg.values())
 lines = ["| kernel | launches/step | total us/step | avg us | share |", "|---|---:|---:|---:|---:|"]
-for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     lines.append("| `%s` | %d | %.0f | %.2f | %.1f%% |" % (k[:64], n // N, t / N, t / n, 100 * t / tot))
 lines.append("| **sum of kernel time** | %d | %.0f | | |" % (sum(v[0] for v in agg.values()) // N, tot / N))
 print("\n".join(lines))

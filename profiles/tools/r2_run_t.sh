@@ -1,5 +1,5 @@
 #!/bin/bash
-O=gpurun_out/t2; mkdir -p $O
+O=gpurun_out/t3; mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_units.py -x -q -k "backward or persistent" > $O/tests_units.log 2>&1; echo "exit $?" >> $O/tests_units.log
 tail -5 $O/tests_units.log
 timeout 900 python -m pytest tests/test_gpu_oracle_shapes.py -x -q -s > $O/tests_oracle.log 2>&1; echo "exit $?" >> $O/tests_oracle.log

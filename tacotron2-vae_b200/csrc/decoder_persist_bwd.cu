@@ -408,13 +408,28 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
           sg[j][0] = sg[j][1] = sg[j][2] = sg[j][3] = 0.f; sc2[j] = 0.f; scp[j] = 0.f;
         }
       }
+      // dropout keep-scales of this step (counter RNG: no memory dependence) while the loads above are in flight
+      float kh4[4], kc4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int b = 16 * rank + blq + 4 * j;
+        float kh = 1.f, kc = 1.f;
+        if (pdrop > 0.f && b < B) {
+          const uint64_t li = (uint64_t)b * H + jg;
+          if (mk) { kh = mk[li] * kscale; kc = mk[(long long)B * H + li] * kscale; }
+          else {
+            const uint64_t di = (uint64_t)ts * B * H + li;
+            kh = (t2v_uniform(seed, which ? SITE_DEC_H : SITE_ATT_H, di) >= pdrop ? 1.f : 0.f) * kscale;
+            kc = (t2v_uniform(seed, which ? SITE_DEC_C : SITE_ATT_C, di) >= pdrop ? 1.f : 0.f) * kscale;
+          }
+        }
+        kh4[j] = kh; kc4[j] = kc;
+      }
       if (etid == 0) {
         TR(cur_it, which ? 0 : 15);
         if (seen_xd < n_xd) { wait_counter(cnt_xd, n_xd); seen_xd = n_xd; }
         if (seen_xa < n_xa) { wait_counter(cnt_xa, n_xa); seen_xa = n_xa; }
-        if (seen_q < n_q) { wait_counter(cnt_q, n_q); seen_q = n_q; }
-        TR(cur_it, which ? 1 : 3);
-        GT(cur_it, which ? 1 : 3);
+        if (which) { TR(cur_it, 1); GT(cur_it, 1); }
       }
       named_bar(BAR_EPI, 128);
       float dh[4];
@@ -433,7 +448,18 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
         }
         dh[j] = v;
       }
+      // everything of the cell that does not need dq is evaluated before the wait for it: tanh of the saved cell state
+      float tc4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tc4[j] = t2v_tanh(sc2[j]);
       if (which == 0) {
+        // the attention chain's critical wait: dq[t] of the whole batch (the loads and the RNG above ran in its shadow)
+        if (etid == 0) {
+          if (seen_q < n_q) { wait_counter(cnt_q, n_q); seen_q = n_q; }
+          TR(cur_it, 3);
+          GT(cur_it, 3);
+        }
+        named_bar(BAR_EPI, 128);
         // ---- dHq = dq W_q for this CTA's 16 batch rows x 32 units (dq of the whole batch is complete: cnt_q) on the tensor core.
         // thread -> (row etid / 8, attention dims 16 (etid % 8) .. +16): straight from L2 (the rows were accumulated with atomics)
         const int qr = etid >> 3, qa = (etid & 7) * 16;
@@ -507,19 +533,10 @@ dec_persist_bwd_kernel(const __grid_constant__ CUtensorMap tmWa, const __grid_co
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int b = 16 * rank + blq + 4 * j;
-        float kh = 1.f, kc = 1.f;
-        if (pdrop > 0.f && b < B) {
-          const uint64_t li = (uint64_t)b * H + jg;
-          if (mk) { kh = mk[li] * kscale; kc = mk[(long long)B * H + li] * kscale; }
-          else {
-            const uint64_t di = (uint64_t)ts * B * H + li;
-            kh = (t2v_uniform(seed, which ? SITE_DEC_H : SITE_ATT_H, di) >= pdrop ? 1.f : 0.f) * kscale;
-            kc = (t2v_uniform(seed, which ? SITE_DEC_C : SITE_ATT_C, di) >= pdrop ? 1.f : 0.f) * kscale;
-          }
-        }
+        const float kh = kh4[j], kc = kc4[j];
         const float ig = sg[j][0], fg = sg[j][1], gg = sg[j][2], og = sg[j][3];
         const float dhh = dh[j] * kh;
-        const float tc = t2v_tanh(sc2[j]);
+        const float tc = tc4[j];
         const float dc = dcs[j] * kc + dhh * og * (1.f - tc * tc);
         dcs[j] = dc * fg;
         if (b < B) {

@@ -159,8 +159,10 @@ class Ops(object):
     # out[M,N] = x[M,K] @ W[N,K]^T (+bias) (+= if accumulate)
     def linear(self, x, lda, W, ldw, out, ldd, M, N, K, bias=None, accumulate=False, a_rows=None, force_exact=False):
         if self.tc and not force_exact and self._tc_ok((x, lda), (W, ldw)) and M >= 1:
+            # accumulate: the atomic epilogue with one split = exactly one add per element (deterministic); the read-modify-write
+            # epilogue (epi 2) walks D row by row per thread and measured 10x slower
             L("t2v_gemm_tc", x, lda, a_rows or M, K, W, ldw, N, K, out, ldd, bias, M, N, K, 1, 0, 0, 0, 0, 4, 1, 0,
-              2 if accumulate else 0, 1.0, self.bn(M, N))
+              1 if accumulate else 0, 1.0, self.bn(M, N))
         else:
             self.gemm(x, lda, 1, W, ldw, 1, out, ldd, M, N, K, 1.0, 1.0 if accumulate else 0.0, bias)
 
@@ -172,7 +174,7 @@ class Ops(object):
             WT = _zeros(K, Np, device=W.device)
             L("t2v_transpose", W, ldw, WT, Np, N, K, 1)
             L("t2v_gemm_tc", dy, ldy, M, N, WT, Np, K, N, dx, lddx, None, M, K, N, 1, 0, 0, 0, 0, 4, 1, 0,
-              2 if accumulate else 0, 1.0, 128)
+              1 if accumulate else 0, 1.0, 128)
         else:
             self.gemm(dy, ldy, 1, W, 1, ldw, dx, lddx, M, K, N, 1.0, 1.0 if accumulate else 0.0, None)
 
@@ -763,21 +765,19 @@ def project_mel_gate(ops, W, buf, O, B, To, persistent):
     ops.linear(_p(XD, 1024), 2560, _p(W["Wpg"], 1024), 1536, O, 84, n, 81, 512, accumulate=True, a_rows=n)
 
 
-def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, drop_masks, seed, mask_value, dev):
-    """Teacher-forced Decoder.forward (model.py:391-426).  memory [B,Ti,512]; mel_tgt [B,80,To].
-    Returns O [To*B,84] (mel|gate rows, time-major), alignments [B,To,Ti], ctx."""
-    B, Ti, _ = memory.shape
+def decoder_prepare(ops, P, mel_tgt, B, Ti, prenet_masks, seed, dev):
+    """Everything of Decoder.forward that does not need the encoder outputs: weight packing, the sequence buffers and the prenet over
+    the go frame + all teacher frames (model.py:406-409; dropout always on, model.py:101).  The train step runs it on a side branch
+    beside the encoders."""
     To = mel_tgt.shape[2]
     W = {}
     W["Wa"], W["Wd"], W["Wpg"], W["bpg"] = pack_decoder_weights(P, dev, ops.R)
     W["Wq"] = ops.wr(P[_A + "query_layer.linear_layer.weight"])
     W["WconvT"] = conv_weight_T(P, dev)
+    W["Wm"] = ops.wr(P[_A + "memory_layer.linear_layer.weight"])
     pack_step_weights(ops, W, dev)
     pack_projection_lo(ops, P, W, dev)
-    pmem = _empty(B * Ti, 128, device=dev)
-    ops.linear(memory, 512, ops.wr(P[_A + "memory_layer.linear_layer.weight"]), 512, pmem, 128, B * Ti, 128, 512)
     buf = alloc_decoder_buffers(B, Ti, To, dev, save=True, op16=ops.op16, split=ops.split)
-    # prenet over the go frame + all teacher frames (model.py:406-409); dropout always on (model.py:101)
     Fr = _empty((To + 1) * B, 80, device=dev)
     L("t2v_bct_to_rows_tb_shift", mel_tgt, Fr, B, 80, To, ops.R)
     n = (To + 1) * B
@@ -792,6 +792,20 @@ def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, dro
     L("t2v_relu_drop_fwd", P2pre, buf["XA"], 1792, n, 256, m1, seed, SITE_PRENET + 1, 0.5, 0, ops.RX)
     if ops.op16:
         L("t2v_cvt16_2d", buf["XA"], 1792, buf["XA16"], 1792, n, 256, ops.op16)
+    return dict(W=W, buf=buf, Fr=Fr, P1pre=P1pre, P1=P1, P2pre=P2pre, m0=m0, m1=m1)
+
+
+def decoder_forward(ops, P, memory, mel_tgt, in_len, training, prenet_masks, drop_masks, seed, mask_value, dev, prep=None):
+    """Teacher-forced Decoder.forward (model.py:391-426).  memory [B,Ti,512]; mel_tgt [B,80,To].
+    Returns O [To*B,84] (mel|gate rows, time-major), alignments [B,To,Ti], ctx."""
+    B, Ti, _ = memory.shape
+    To = mel_tgt.shape[2]
+    if prep is None:
+        prep = decoder_prepare(ops, P, mel_tgt, B, Ti, prenet_masks, seed, dev)
+    W, buf = prep["W"], prep["buf"]
+    Fr, P1pre, P1, P2pre, m0, m1 = (prep[k] for k in ("Fr", "P1pre", "P1", "P2pre", "m0", "m1"))
+    pmem = _empty(B * Ti, 128, device=dev)
+    ops.linear(memory, 512, W["Wm"], 512, pmem, 128, B * Ti, 128, 512)
     S = _lib.T2VDecoderSeq()
     _fill_seq_struct(S, ops, P, W, B, Ti, To, training, seed, drop_masks, mask_value, in_len, memory, pmem, buf)
     _trace("  fwd prenet+pack")
@@ -959,6 +973,10 @@ def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=No
     c.B, c.Ti, c.To, c.training, c.seed, c.rand = B, Ti, To, training, seed, rand
     g = (lambda name: None) if rand is None else (lambda name: getattr(rand, name))
     _trace("")
+    # the decoder's weight packing, buffer initialisation and prenet only need the mel: a branch of their own
+    br_prep = _Branch(2)
+    with br_prep:
+        prep = decoder_prepare(ops, P, mel_tgt, B, Ti, g("prenet"), seed, dev)
     # the reference encoder / VAE head only needs the mel: it runs beside the text encoder (both are chains of small kernels)
     br = _Branch(0)
     with br:
@@ -972,7 +990,9 @@ def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=No
     _trace("fwd encoder + vae/ref-encoder")
     memory = _empty(B, Ti, 512, device=dev)
     L("t2v_unpad_add", HoutP, style, memory, B, Ti, 512, ops.R)                  # model.py:536-537
-    O, align, c.dec = decoder_forward(ops, P, memory, mel_tgt, in_len, training, g("prenet"), g("dec"), seed, mask_value, dev)
+    br_prep.join()
+    O, align, c.dec = decoder_forward(ops, P, memory, mel_tgt, in_len, training, g("prenet"), g("dec"), seed, mask_value, dev,
+                                      prep=prep)
     _trace("fwd decoder")
     X0p = _zeros(B * (To + 4), 80, device=dev)
     L("t2v_rows_tb_to_padded", O, 84, X0p, B, 80, To, 0)

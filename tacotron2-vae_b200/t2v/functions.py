@@ -1,6 +1,8 @@
 """torch.autograd glue: the whole Tacotron2 forward is ONE autograd.Function whose backward is the hand-written
 backward pass of t2v.engine, so the reference's train.py (loss.backward(), param.register_hook, clip_grad_norm_,
 Adam.step) runs unchanged on top of the CUDA engine."""
+import os
+
 import torch
 
 from . import _lib, engine
@@ -9,6 +11,17 @@ from ._lib import call as L
 
 _GRAPH_AFTER = int(__import__("os").environ.get("T2V_GRAPH_AFTER", "2"))     # capture a shape on its n-th sighting
 _GRAPH_MAX = int(__import__("os").environ.get("T2V_GRAPH_MAX", "3"))         # graphs kept resident (LRU)
+
+
+_CAPTURE_STREAMS = {}
+
+
+def _capture_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _CAPTURE_STREAMS:
+        prio = -1 if os.environ.get("T2V_CAPTURE_PRIORITY", "1") != "0" else 0
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=key, priority=prio)
+    return _CAPTURE_STREAMS[key]
 
 
 class GraphedStep(object):
@@ -40,7 +53,10 @@ class GraphedStep(object):
         torch.cuda.synchronize()
         self.g_fwd = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.g_fwd, capture_error_mode="thread_local"):
+        # captured on a HIGH-priority stream: the graph's main chain (text encoder -> decoder loops -> encoder backward) is the
+        # critical path of the step; the side branches (engine._Branch: default priority) fill the SMs it leaves free
+        cap = _capture_stream(dev)
+        with torch.cuda.graph(self.g_fwd, stream=cap, capture_error_mode="thread_local"):
             self.outs, self.c = engine.forward_train(cfg.ops, P, *self.s_in, **kw)
         self.n_fwd = _lib.launch_count() - n0
         self.direct = False
@@ -52,7 +68,7 @@ class GraphedStep(object):
             return
         self.s_dout = [torch.zeros_like(self.outs[i]) for i in (0, 1, 2, 4, 5)]
         self.g_bwd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool(), capture_error_mode="thread_local"):
+        with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool(), stream=cap, capture_error_mode="thread_local"):
             grads = engine.backward_train(cfg.ops, P, self.c, *self.s_dout)
             self.live = [n for n in self.names if n in grads]
             self.sizes = [grads[n].numel() for n in self.live]
