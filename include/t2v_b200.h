@@ -283,6 +283,9 @@ int t2v_pack_step_tiles(const float* W, int mode, float* out, cudaStream_t strea
 int t2v_grad_scale(const float* x, long long n, int target_log2, float* out, cudaStream_t stream);
 /* 16-bit variant for op16 (fmt 1 = fp16, 2 = bf16): K chunks of 64 columns; modes 0 / 1 forward tiles, 2 / 3 backward tiles (W^T) */
 int t2v_pack_step_tiles16(const float* W, int mode, void* out, int fmt, cudaStream_t stream);
+/* contiguous fp32 -> 16-bit conversion of n elements (n % 8 == 0), multiplied by *scale_dev when given (fp16: saturating): the fp16
+   operand copies of the convolution weight-gradient GEMMs */
+int t2v_cvt16_scaled(const float* src, void* dst, long long n, int fmt, const float* scale_dev, cudaStream_t stream);
 /* strided fp32 -> 16-bit conversion (fmt 1 = fp16, 2 = bf16), e.g. the prenet columns of XA into XA16 */
 int t2v_cvt16_2d(const float* src, long long s_ld, void* dst, long long d_ld, long long rows, int cols, int fmt,
                  cudaStream_t stream);

@@ -1186,9 +1186,42 @@ __global__ void cvt16_2d_kernel(const float* __restrict__ src, long long s_ld, u
   dst[r * d_ld + c] = t2v_enc16(src[r * s_ld + c], fmt);
 }
 
+// contiguous fp32 -> 16-bit, 8 elements per thread, optional device scale (fp16: saturating)
+__global__ void cvt16_flat8_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long n8, int fmt,
+                                   const float* __restrict__ scale_dev) {
+  const float sc = scale_dev ? *scale_dev : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);
+    const float v[8] = {a.x * sc, a.y * sc, a.z * sc, a.w * sc, b.x * sc, b.y * sc, b.z * sc, b.w * sc};
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint16_t lo, hi;
+      if (fmt == 1) {
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(lo) : "f"(v[2 * j]));
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hi) : "f"(v[2 * j + 1]));
+      } else {
+        lo = t2v_bf16_bits(v[2 * j]); hi = t2v_bf16_bits(v[2 * j + 1]);
+      }
+      w[j] = (uint32_t)lo | ((uint32_t)hi << 16);
+    }
+    dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // max |x| -> power-of-two scale (t2v_grad_scale)
 __global__ void absmax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ out_bits) {
   float m = 0.f;
+  if ((((uintptr_t)x) & 15) == 0) {
+    const long long n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = __ldg(x4 + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      m = fmaxf(m, fabsf(x[i]));
+  } else
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));     // non-negative floats order like their bit patterns
@@ -1387,6 +1420,16 @@ T2V_API int t2v_cvt16_2d(const float* src, long long s_ld, void* dst, long long 
   T2V_ARG_CHECK(src && dst && rows > 0 && cols > 0 && (fmt == 1 || fmt == 2), "fmt 1 (fp16) / 2 (bf16)");
   const long long n = rows * cols;
   cvt16_2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, s_ld, reinterpret_cast<uint16_t*>(dst), d_ld, rows, cols, fmt);
+  T2V_COUNT_LAUNCH();
+  T2V_LAUNCH_CHECK();
+  return 0;
+}
+T2V_API int t2v_cvt16_scaled(const float* src, void* dst, long long n, int fmt, const float* scale_dev, cudaStream_t stream) {
+  T2V_ARG_CHECK(src && dst && n > 0 && n % 8 == 0 && (fmt == 1 || fmt == 2), "n % 8 == 0, fmt 1 (fp16) / 2 (bf16)");
+  T2V_ARG_CHECK(((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0, "16-byte aligned buffers");
+  const long long n8 = n / 8;
+  const unsigned grid = (unsigned)((n8 + 255) / 256 < 148 * 16 ? (n8 + 255) / 256 : 148 * 16);
+  cvt16_flat8_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n8, fmt, scale_dev);
   T2V_COUNT_LAUNCH();
   T2V_LAUNCH_CHECK();
   return 0;

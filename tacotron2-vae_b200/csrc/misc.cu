@@ -130,6 +130,57 @@ __global__ void im2col_3x3s2_kernel(const float* __restrict__ x, float* __restri
   }
   col[i] = t2v_rnd(v, rnd);
 }
+// Vectorised forms (32-bit index arithmetic, 16-byte accesses): thread = (output pixel, tap, 4 channels).  c4_shift = log2(Ci / 4);
+// the CoordConv layer (1 input channel + 3 generated coordinate planes) is the c4_shift = 0 case with one float4 per (pixel, tap).
+__global__ void im2col_3x3s2_v4_kernel(const float* __restrict__ x, float4* __restrict__ col, unsigned total, int H, int W, int Ci,
+                                       int Ho, int Wo, int c4_shift, int coord, int rnd) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const unsigned c4 = i & ((1u << c4_shift) - 1u);
+  const unsigned g = i >> c4_shift;
+  const unsigned pix = g / 9u, kk = g - pix * 9u;
+  const unsigned wo = pix % (unsigned)Wo, t = pix / (unsigned)Wo;
+  const unsigned ho = t % (unsigned)Ho, n = t / (unsigned)Ho;
+  const int h = (int)ho * 2 - 1 + (int)(kk / 3u), w = (int)wo * 2 - 1 + (int)(kk % 3u);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (h >= 0 && h < H && w >= 0 && w < W) {
+    if (!coord) {
+      v = __ldg(reinterpret_cast<const float4*>(x + (((long long)n * H + h) * W + w) * Ci) + c4);
+    } else {
+      const float xx = ((float)h / (float)(H - 1)) * 2.f - 1.f;
+      const float yy = ((float)w / (float)(W - 1)) * 2.f - 1.f;
+      v = make_float4(__ldg(x + ((long long)n * H + h) * W + w), xx, yy, sqrtf((xx - 0.5f) * (xx - 0.5f) + (yy - 0.5f) * (yy - 0.5f)));
+    }
+  }
+  col[i] = make_float4(t2v_rnd(v.x, rnd), t2v_rnd(v.y, rnd), t2v_rnd(v.z, rnd), t2v_rnd(v.w, rnd));
+}
+__global__ void col2im_3x3s2_v4_kernel(const float4* __restrict__ dcol, float4* __restrict__ dx, unsigned total, int H, int W,
+                                       int Ho, int Wo, int c4_shift) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const unsigned c4 = i & ((1u << c4_shift) - 1u);
+  const unsigned g = i >> c4_shift;
+  const unsigned w = g % (unsigned)W, t = g / (unsigned)W;
+  const unsigned h = t % (unsigned)H, n = t / (unsigned)H;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int hh = (int)h + 1 - kh;
+    if (hh < 0 || (hh & 1)) continue;
+    const int ho = hh >> 1;
+    if (ho >= Ho) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ww = (int)w + 1 - kw;
+      if (ww < 0 || (ww & 1)) continue;
+      const int wo = ww >> 1;
+      if (wo >= Wo) continue;
+      const float4 d = __ldg(dcol + ((((((long long)n * Ho + ho) * Wo + wo) * 9 + kh * 3 + kw)) << c4_shift) + c4);
+      a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+    }
+  }
+  dx[i] = a;
+}
 // adjoint: dx[n,h,w,c] = sum over (kh,kw) with matching output pixel of dcol
 __global__ void col2im_3x3s2_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int N, int H, int W, int Ci,
                                     int Ho, int Wo) {
@@ -349,11 +400,32 @@ T2V_API int t2v_unpad_add(const float* in_padded, const float* add_vec, float* o
 }
 T2V_API int t2v_im2col_3x3s2(const float* x, float* col, int N, int H, int W, int Ci, int coord, int rnd, cudaStream_t st) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Ct = coord ? 4 : Ci;
+  {
+    const long long tot4 = (long long)N * Ho * Wo * 9 * (Ct / 4);
+    int sh = 0;
+    while ((4 << sh) < Ct) ++sh;
+    const bool pow2 = (4 << sh) == Ct && (coord || Ci % 4 == 0);
+    if (pow2 && tot4 < (1LL << 32) - 256 && (((uintptr_t)x | (uintptr_t)col) & 15) == 0) {
+      im2col_3x3s2_v4_kernel<<<grid1d(tot4, 256), 256, 0, st>>>(x, reinterpret_cast<float4*>(col), (unsigned)tot4, H, W, Ci, Ho, Wo,
+                                                                sh, coord, rnd);
+      LAUNCH_END();
+    }
+  }
   im2col_3x3s2_kernel<<<grid1d((long long)N * Ho * Wo * 9 * Ct, 256), 256, 0, st>>>(x, col, N, H, W, Ci, Ho, Wo, coord, rnd);
   LAUNCH_END();
 }
 T2V_API int t2v_col2im_3x3s2(const float* dcol, float* dx, int N, int H, int W, int Ci, cudaStream_t st) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  {
+    const long long tot4 = (long long)N * H * W * (Ci / 4);
+    int sh = 0;
+    while ((4 << sh) < Ci) ++sh;
+    if ((4 << sh) == Ci && tot4 < (1LL << 32) - 256 && (((uintptr_t)dcol | (uintptr_t)dx) & 15) == 0) {
+      col2im_3x3s2_v4_kernel<<<grid1d(tot4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(dcol), reinterpret_cast<float4*>(dx),
+                                                                (unsigned)tot4, H, W, Ho, Wo, sh);
+      LAUNCH_END();
+    }
+  }
   col2im_3x3s2_kernel<<<grid1d((long long)N * H * W * Ci, 256), 256, 0, st>>>(dcol, dx, N, H, W, Ci, Ho, Wo);
   LAUNCH_END();
 }

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(UPC * 32, 1) bilstm_seq_bwd_kernel(SeqBwd p) {
   constexpr int KC = 256, DS = KC + 1;
   float* dT = smb;                       // [MT][KC+1] gate-gradient chunk of the previously processed step
   float* ws = dT + MT * DS;              // [K][UPC] this CTA's columns of W_hh^T, staged once
+  float* red = ws + (size_t)K * UPC;     // [8 warps][UPC][MT] partial sums
   for (int i = threadIdx.x; i < K * UPC; i += UPC * 32) {
     const int k = i % K, uu = i / K;
     ws[k * UPC + uu] = p.w_hhT[dir][(long long)(u0 + uu) * K + k];
@@ -210,37 +211,61 @@ __global__ void __launch_bounds__(UPC * 32, 1) bilstm_seq_bwd_kernel(SeqBwd p) {
     }
     float acc[2] = {0.f, 0.f};
     if (s > 0) {
+      // dh_prev[b][u] = sum_k dg_next[b][k] W_hh[k][u] over K = 4H gate gradients.  Register-blocked: warp w takes k = 32 w .. 32 w + 31
+      // of every 256-wide chunk for ALL 64 rows x 8 units (lane -> 2 rows x 8 units = 16 accumulators: 16 FMAs per 4 shared-memory
+      // loads; warp = unit with one accumulator per row was bound by shared-memory bandwidth at 2 FMAs per 3 loads), then the 8
+      // partial sums of every (row, unit) are reduced through shared memory.  The global loads of chunk c + 1 are in flight while
+      // chunk c is multiplied.
       if (threadIdx.x == 0) wait_counter(cnt, (unsigned)(ncta * s));
+      __syncthreads();
       const float* dgn = p.dg[dir] + ((long long)2 + tn) * K;       // row (b = 0, tn); batch stride Tp * K
+      float4 v[16];
+      auto load_chunk = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int i = threadIdx.x + j * UPC * 32;
+          const int m = (i * 4) / KC, k = (i * 4) % KC;
+          v[j] = (m < p.B) ? __ldcg(reinterpret_cast<const float4*>(dgn + (long long)m * p.Tp * K + k0 + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      float a8[2][UPC];
+#pragma unroll
+      for (int uu = 0; uu < UPC; ++uu) a8[0][uu] = a8[1][uu] = 0.f;
+      load_chunk(0);
       for (int k0 = 0; k0 < K; k0 += KC) {
         __syncthreads();
-        const int nv = MT * KC / 4;
-        for (int i0 = threadIdx.x; i0 < nv; i0 += UPC * 32 * 16) {
-          float4 v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int i = i0 + j * UPC * 32;
-            const int m = (i * 4) / KC, k = (i * 4) % KC;
-            v[j] = (i < nv && m < p.B) ? __ldcg(reinterpret_cast<const float4*>(dgn + (long long)m * p.Tp * K + k0 + k))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int i = i0 + j * UPC * 32;
-            if (i < nv) {
-              const int m = (i * 4) / KC, k = (i * 4) % KC;
-              float* d = dT + m * DS + k;
-              d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
-            }
-          }
+        for (int j = 0; j < 16; ++j) {
+          const int i = threadIdx.x + j * UPC * 32;
+          const int m = (i * 4) / KC, k = (i * 4) % KC;
+          float* d = dT + m * DS + k;
+          d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
         }
         __syncthreads();
+        if (k0 + KC < K) load_chunk(k0 + KC);
+        const float* wk = ws + (size_t)(k0 + 32 * warp) * UPC;
+        const float* d0 = dT + lane * DS + 32 * warp;
+        const float* d1 = dT + (32 + lane) * DS + 32 * warp;
 #pragma unroll 8
-        for (int k = 0; k < KC; ++k) {
-          const float w = ws[(k0 + k) * UPC + warp];
-          acc[0] = fmaf(dT[lane * DS + k], w, acc[0]);
-          acc[1] = fmaf(dT[(32 + lane) * DS + k], w, acc[1]);
+        for (int k = 0; k < 32; ++k) {
+          const float x0 = d0[k], x1 = d1[k];
+          const float4 wa = *reinterpret_cast<const float4*>(wk + k * UPC), wb = *reinterpret_cast<const float4*>(wk + k * UPC + 4);
+          a8[0][0] = fmaf(x0, wa.x, a8[0][0]); a8[0][1] = fmaf(x0, wa.y, a8[0][1]); a8[0][2] = fmaf(x0, wa.z, a8[0][2]); a8[0][3] = fmaf(x0, wa.w, a8[0][3]);
+          a8[0][4] = fmaf(x0, wb.x, a8[0][4]); a8[0][5] = fmaf(x0, wb.y, a8[0][5]); a8[0][6] = fmaf(x0, wb.z, a8[0][6]); a8[0][7] = fmaf(x0, wb.w, a8[0][7]);
+          a8[1][0] = fmaf(x1, wa.x, a8[1][0]); a8[1][1] = fmaf(x1, wa.y, a8[1][1]); a8[1][2] = fmaf(x1, wa.z, a8[1][2]); a8[1][3] = fmaf(x1, wa.w, a8[1][3]);
+          a8[1][4] = fmaf(x1, wb.x, a8[1][4]); a8[1][5] = fmaf(x1, wb.y, a8[1][5]); a8[1][6] = fmaf(x1, wb.z, a8[1][6]); a8[1][7] = fmaf(x1, wb.w, a8[1][7]);
         }
+      }
+#pragma unroll
+      for (int uu = 0; uu < UPC; ++uu) {
+        red[(warp * UPC + uu) * MT + lane] = a8[0][uu];
+        red[(warp * UPC + uu) * MT + 32 + lane] = a8[1][uu];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int w2 = 0; w2 < UPC; ++w2) {       // 8 warps
+        acc[0] += red[(w2 * UPC + warp) * MT + lane];
+        acc[1] += red[(w2 * UPC + warp) * MT + 32 + lane];
       }
     }
 #pragma unroll
@@ -500,7 +525,7 @@ T2V_API int t2v_bilstm_seq_bwd(const float* whhT0, const float* whhT1, const flo
   SeqBwd a;
   a.w_hhT[0] = whhT0; a.w_hhT[1] = whhT1; a.dout = dout; a.gates = gates; a.cells = cells; a.dg[0] = dg0; a.dg[1] = dg1;
   a.counters = counters; a.lens = lens; a.B = B; a.H = H; a.Ti = Ti; a.Tp = Ti + 4;
-  const size_t smem = sizeof(float) * (size_t)(MT * 257 + 4 * H * UPC);
+  const size_t smem = sizeof(float) * (size_t)(MT * 257 + 4 * H * UPC + UPC * UPC * MT);
   static size_t cur = 48 * 1024;
   if (smem > cur) {
     T2V_CUDA_CHECK(cudaFuncSetAttribute(bilstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -201,11 +201,12 @@ class Ops(object):
         return splits
 
     @staticmethod
-    def rowred16(A16, lda, n_a, B16, ldb, n_b, D, ldd, rows, alpha_dev, fmt=1):
-        """D[n_a, n_b] += (*alpha_dev) * A16^T B16 over fp16 copies (kind::f16, 256 x 256 tiles); D zero-initialised"""
+    def rowred16(A16, lda, n_a, B16, ldb, n_b, D, ldd, rows, alpha_dev, fmt=1, a_row0=0, b_row0=0):
+        """D[n_a, n_b] += (*alpha_dev) * A16[a_row0 + r]^T B16[b_row0 + r] over fp16 copies (kind::f16, 256 x 256 tiles); D zero-initialised"""
         iters = (rows + 63) // 64
         tiles = ((n_a + 255) // 256) * (n_b // 256)
-        L("t2v_gemm_tc_rowred16", A16, lda, n_a, 0, B16, ldb, n_b, 0, D, ldd, rows, Ops.pick_splits(tiles, iters), 1, 1.0, alpha_dev, fmt)
+        L("t2v_gemm_tc_rowred16", A16, lda, n_a, a_row0, B16, ldb, n_b, b_row0, D, ldd, rows, Ops.pick_splits(tiles, iters), 1, 1.0,
+          alpha_dev, fmt)
 
     @staticmethod
     def rowred(A, lda, n_a, a_row0, Bm, ldb, n_b, b_row0, D, ldd, rows):
@@ -362,7 +363,18 @@ def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0
         with br:
             # weight gradient in tap-major form: dWk[co, tap*Ci+ci] = sum_r dY[r+2, co] * X[r+tap, ci]
             dWk = _zeros(Co, 5 * Ci, device=dev)
-            if ops.tc:
+            if ops.tc and ops.op16 == 1 and _DW16 and Co % 256 == 0 and Ci % 256 == 0 and Co >= 512 and M >= 16384:
+                # large layers (Postnet 512 -> 512): fp16 copies of both operands (the gradient scaled by a power of two into the
+                # fp16 range: same 11-bit significands as tf32), kind::f16 row-reduction GEMMs at twice the tf32 rate
+                sc = _empty(4, device=dev)
+                L("t2v_grad_scale", dY, R * Co, 14, sc)
+                dY16 = torch.empty(R, Co, device=dev, dtype=torch.int16)
+                L("t2v_cvt16_scaled", dY, dY16, R * Co, 1, sc)
+                X16 = torch.empty(R, Ci, device=dev, dtype=torch.int16)
+                L("t2v_cvt16_scaled", s["X"], X16, R * Ci, 1, None)
+                for tap in range(5):
+                    Ops.rowred16(dY16, Co, Co, X16, Ci, Ci, _p(dWk, tap * Ci), 5 * Ci, M, sc.data_ptr() + 4, 1, a_row0=2, b_row0=tap)
+            elif ops.tc:
                 # one row-reduction GEMM per tap: the tap is a row offset of the X operand (MN-major operands, no transposes)
                 for tap in range(5):
                     Ops.rowred(dY, Co, Co, 2, s["X"], Ci, Ci, tap, _p(dWk, tap * Ci), 5 * Ci, M)
