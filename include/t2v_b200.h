@@ -51,17 +51,18 @@ int t2v_gemm_tc_split3(const float* A_hi, const float* A_lo, long long lda, long
 
 /* row-reduction form with MN-major operands (no transposed copies): D[n_a,n_b] (+)= alpha * sum_{r<rows} A[a_row0+r, i] * B[b_row0+r, j];
    the weight-gradient GEMMs dW = dY^T X of every nn.Linear / Conv1d (autograd of model.py:91-148).  epi: 0 store, 1 atomicAdd,
-   2 non-atomic += (splits == 1); splits > 1 needs epi 1 (D pre-initialised). */
+   2 non-atomic += (splits == 1); splits > 1 needs epi 1 (D pre-initialised).  taps > 1: the Conv1d weight gradient in tap-major form,
+   D[n_a, taps*n_b], column block t reduces against B rows [b_row0 + t, b_row0 + t + rows) (model.py:105-177: k = 5 convolutions). */
 int t2v_gemm_tc_rowred(const float* A, long long lda, int n_a, long long a_row0, const float* B, long long ldb, int n_b,
                        long long b_row0, float* D, long long ldd, long long rows, int splits, long long split_stride,
-                       int epi, float alpha, cudaStream_t stream);
+                       int epi, float alpha, int taps, cudaStream_t stream);
 
 /* the same row reduction over 16-bit operands (fp16 / bf16 copies, kind::f16, 64 reduction rows per stage): the decoder's big weight
    gradients dW = DG^T X from the fp16 copies the persistent loops leave behind (XA16 / XD16, DGA16 / DGD16).  alpha_dev (nullable):
    device scalar multiplied onto alpha (the inverse gradient scale). */
 int t2v_gemm_tc_rowred16(const void* A, long long lda, int n_a, long long a_row0, const void* B, long long ldb, int n_b,
                          long long b_row0, float* D, long long ldd, long long rows, int splits, int epi, float alpha,
-                         const float* alpha_dev, int fmt, cudaStream_t stream);
+                         const float* alpha_dev, int fmt, int taps, cudaStream_t stream);
 
 /* ---- text embedding (model.py:474,528) -- integer gather, bit exact ------------------------------------------- */
 int t2v_embedding_fwd(const long long* ids, const float* table, float* out_padded, int B, int T, int C, int n_symbols,

@@ -297,6 +297,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // One tf32 MMA consumes 8 reduction rows (two atoms), so the K advance is +1024 B.  The plain SWIZZLE_128B layout with the MN-major
 // bits set is silently computed as zeros by the hardware (profiles/r02_mn_major_probe.txt, tools/mn_probe.cu).
 constexpr int BKR = 32;                      // reduction rows per stage
+// one 16-byte reduction into global memory (sm_90+): a thread's 32 accumulator columns are contiguous in D, so the split-K epilogue
+// issues 8 of these per 32 columns instead of 32 scalar atomics
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
@@ -327,6 +332,10 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // Conv1d weight gradients (b_tap_stride = Ci > 0): D is [n_a, taps * Ci]; the column block of tap t reads the SAME B columns from
+  // rows shifted by t, so one launch covers all taps (BN divides Ci: a tile never straddles two taps)
+  const int tap = p.b_tap_stride > 0 ? n0 / p.b_tap_stride : 0;
+  const int nb0 = n0 - tap * p.b_tap_stride, brow0 = p.b_row0 + tap;
   const int it0 = blockIdx.z * p.iters_per_split;
   const int n_it = min(p.iters_per_split, p.chunks_per_tap - it0);   // chunks_per_tap = total 32-row iterations; the last split may be short
 
@@ -358,7 +367,7 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int g = 0; g < BM / 32; ++g) tma_load_2d(sa + g * BOX, &tmA, m0 + 32 * g, p.a_row0 + r, &full[s]);
 #pragma unroll
-        for (int g = 0; g < BN / 32; ++g) tma_load_2d(sa + A_BYTES + g * BOX, &tmB, n0 + 32 * g, p.b_row0 + r, &full[s]);
+        for (int g = 0; g < BN / 32; ++g) tma_load_2d(sa + A_BYTES + g * BOX, &tmB, nb0 + 32 * g, brow0 + r, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -388,6 +397,7 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int q = warp & 3;
+    const bool vec4 = ((((uintptr_t)p.D) & 15) == 0) && (p.ldd % 4 == 0) && (p.split_stride % 4 == 0);
 #pragma unroll 1
     for (int mb = 0; mb < MB; ++mb) {
     const int row = m0 + mb * 128 + q * 32 + lane;
@@ -397,6 +407,12 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BN + c0), v);
       if (row < p.M) {
+        if (p.epi_atomic == 1 && vec4 && n0 + c0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(drow + n0 + c0 + j, __uint_as_float(v[j]) * p.alpha, __uint_as_float(v[j + 1]) * p.alpha,
+                       __uint_as_float(v[j + 2]) * p.alpha, __uint_as_float(v[j + 3]) * p.alpha);
+        } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = n0 + c0 + j;
@@ -406,6 +422,7 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             else if (p.epi_atomic == 2) drow[col] += o;
             else drow[col] = o;
           }
+        }
         }
       }
     }
@@ -448,6 +465,8 @@ gemm_tc_mn16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_holder = (uint32_t*)(tmem_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tap = p.b_tap_stride > 0 ? n0 / p.b_tap_stride : 0;      // see gemm_tc_mn_kernel: one launch for all taps of a Conv1d dW
+  const int nb0 = n0 - tap * p.b_tap_stride, brow0 = p.b_row0 + tap;
   const int it0 = blockIdx.z * p.iters_per_split;
   const int n_it = min(p.iters_per_split, p.chunks_per_tap - it0);
   if (threadIdx.x == 0) {
@@ -476,7 +495,7 @@ gemm_tc_mn16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int g = 0; g < BM / 64; ++g) tma_load_2d(sa + g * BOX, &tmA, m0 + 64 * g, p.a_row0 + r, &full[s]);
 #pragma unroll
-        for (int g = 0; g < BN / 64; ++g) tma_load_2d(sa + A_BYTES + g * BOX, &tmB, n0 + 64 * g, p.b_row0 + r, &full[s]);
+        for (int g = 0; g < BN / 64; ++g) tma_load_2d(sa + A_BYTES + g * BOX, &tmB, nb0 + 64 * g, brow0 + r, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -507,6 +526,7 @@ gemm_tc_mn16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     const float alpha = p.alpha * (p.alpha_dev ? *p.alpha_dev : 1.f);
     const int q = warp & 3;
+    const bool vec4 = ((((uintptr_t)p.D) & 15) == 0) && (p.ldd % 4 == 0);
 #pragma unroll 1
     for (int mb = 0; mb < MB; ++mb) {
       const int row = m0 + mb * 128 + q * 32 + lane;
@@ -516,6 +536,12 @@ gemm_tc_mn16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BN + c0), v);
         if (row < p.M) {
+          if (p.epi_atomic == 1 && vec4 && n0 + c0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(drow + n0 + c0 + j, __uint_as_float(v[j]) * alpha, __uint_as_float(v[j + 1]) * alpha,
+                         __uint_as_float(v[j + 2]) * alpha, __uint_as_float(v[j + 3]) * alpha);
+          } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = n0 + c0 + j;
@@ -525,6 +551,7 @@ gemm_tc_mn16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               else if (p.epi_atomic == 2) drow[col] += o;
               else drow[col] = o;
             }
+          }
           }
         }
       }
@@ -715,10 +742,13 @@ int launch_gemm_tc_mn(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 // the tf32 grid).  A: [>= a_row0 + rows, n_a] row-major with row stride lda, B likewise.  epi: 0 store (splits == 1 or split_stride),
 // 1 atomicAdd into a pre-initialised D, 2 non-atomic D += (splits == 1).  The reduction is cut into `splits` equal ranges of 32-row
 // iterations (splits must divide ceil(rows / 32)); rows past the end are zero-filled by TMA.
+// taps > 1 (Conv1d weight gradient in tap-major form): D is [n_a, taps * n_b] and column block t is the reduction against B rows
+// [b_row0 + t, b_row0 + t + rows) -- all taps in one launch, so the split count (and the atomic passes over D) stay small.
 T2V_API int t2v_gemm_tc_rowred(const float* A, long long lda, int n_a, long long a_row0, const float* B, long long ldb, int n_b,
                                long long b_row0, float* D, long long ldd, long long rows, int splits, long long split_stride,
-                               int epi, float alpha, cudaStream_t stream) {
-  T2V_ARG_CHECK(A && B && D && n_a > 0 && n_b > 0 && rows > 0 && splits >= 1, "shape");
+                               int epi, float alpha, int taps, cudaStream_t stream) {
+  T2V_ARG_CHECK(A && B && D && n_a > 0 && n_b > 0 && rows > 0 && splits >= 1 && taps >= 1, "shape");
+  T2V_ARG_CHECK(taps == 1 || n_b % 256 == 0 || n_b == 128 || n_b == 64, "taps > 1: the N tile (256 / 128 / 64) must divide n_b");
   T2V_ARG_CHECK((((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "operand base must be 16-byte aligned");
   T2V_ARG_CHECK((lda * 4) % 16 == 0 && (ldb * 4) % 16 == 0, "row strides must be multiples of 16 bytes");
   const int iters = t2v_ceil_div(rows, BKR);
@@ -727,12 +757,12 @@ T2V_API int t2v_gemm_tc_rowred(const float* A, long long lda, int n_a, long long
   CUtensorMap tmA, tmB;
   int r = encode_mn(&tmA, A, n_a, a_row0 + rows, lda);       // row extent = end of the reduction range: the tail is zero-filled
   if (r) return r;
-  r = encode_mn(&tmB, B, n_b, b_row0 + rows, ldb);
+  r = encode_mn(&tmB, B, n_b, b_row0 + rows + (taps - 1), ldb);   // tap t reads B rows [b_row0 + t, b_row0 + t + rows): must exist
   if (r) return r;
   GemmTcParams p;
   memset(&p, 0, sizeof(p));
-  p.D = D; p.ldd = ldd; p.split_stride = split_stride; p.M = n_a; p.N = n_b; p.iters_per_split = t2v_ceil_div(iters, splits); p.chunks_per_tap = iters;
-  p.epi_atomic = epi; p.alpha = alpha; p.a_row0 = (int)a_row0; p.b_row0 = (int)b_row0;
+  p.D = D; p.ldd = ldd; p.split_stride = split_stride; p.M = n_a; p.N = n_b * taps; p.iters_per_split = t2v_ceil_div(iters, splits); p.chunks_per_tap = iters;
+  p.epi_atomic = epi; p.alpha = alpha; p.a_row0 = (int)a_row0; p.b_row0 = (int)b_row0; p.b_tap_stride = taps > 1 ? n_b : 0;
   if (n_b > 128 && n_b % 256 == 0 && n_a >= 512) return launch_gemm_tc_mn<256, 3, 2>(tmA, tmB, p, splits, stream);   // 256 x 256 tiles
   if (n_b > 128 && n_b % 256 == 0) return launch_gemm_tc_mn<256, 4>(tmA, tmB, p, splits, stream);
   if (n_b > 64) return launch_gemm_tc_mn<128, 6>(tmA, tmB, p, splits, stream);
@@ -761,8 +791,8 @@ int encode_mn16(CUtensorMap* map, const void* base, long long cols, long long ro
 // D[n_a, n_b] (+)= alpha * (*alpha_dev) * sum_{r < rows} A[a_row0 + r, i] * B[b_row0 + r, j] over 16-bit operands (fmt 1 fp16, 2 bf16).
 T2V_API int t2v_gemm_tc_rowred16(const void* A, long long lda, int n_a, long long a_row0, const void* B, long long ldb, int n_b,
                                  long long b_row0, float* D, long long ldd, long long rows, int splits, int epi, float alpha,
-                                 const float* alpha_dev, int fmt, cudaStream_t stream) {
-  T2V_ARG_CHECK(A && B && D && n_a > 0 && n_b > 0 && rows > 0 && splits >= 1 && (fmt == 1 || fmt == 2), "shape / fmt");
+                                 const float* alpha_dev, int fmt, int taps, cudaStream_t stream) {
+  T2V_ARG_CHECK(A && B && D && n_a > 0 && n_b > 0 && rows > 0 && splits >= 1 && (fmt == 1 || fmt == 2) && taps >= 1, "shape / fmt");
   T2V_ARG_CHECK((((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "operand base must be 16-byte aligned");
   T2V_ARG_CHECK((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0, "row strides must be multiples of 16 bytes");
   T2V_ARG_CHECK(n_b % 256 == 0 && n_a >= 256, "16-bit row reduction is built for the large weight gradients (n_b % 256 == 0)");
@@ -772,12 +802,13 @@ T2V_API int t2v_gemm_tc_rowred16(const void* A, long long lda, int n_a, long lon
   CUtensorMap tmA, tmB;
   int r = encode_mn16(&tmA, A, n_a, a_row0 + rows, lda);
   if (r) return r;
-  r = encode_mn16(&tmB, B, n_b, b_row0 + rows, ldb);
+  r = encode_mn16(&tmB, B, n_b, b_row0 + rows + (taps - 1), ldb);
   if (r) return r;
   GemmTcParams p;
   memset(&p, 0, sizeof(p));
-  p.D = D; p.ldd = ldd; p.M = n_a; p.N = n_b; p.iters_per_split = t2v_ceil_div(iters, splits); p.chunks_per_tap = iters;
+  p.D = D; p.ldd = ldd; p.M = n_a; p.N = n_b * taps; p.iters_per_split = t2v_ceil_div(iters, splits); p.chunks_per_tap = iters;
   p.epi_atomic = epi; p.alpha = alpha; p.alpha_dev = alpha_dev; p.a_row0 = (int)a_row0; p.b_row0 = (int)b_row0;
+  p.b_tap_stride = taps > 1 ? n_b : 0;
   constexpr int STAGES = 3, MB = 2, BN = 256;
   constexpr int smem = STAGES * (128 * MB + BN) * BKR16 * 2 + 1024 + 256;
   static bool attr_set = false;
@@ -785,7 +816,7 @@ T2V_API int t2v_gemm_tc_rowred16(const void* A, long long lda, int n_a, long lon
     T2V_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_mn16_kernel<BN, STAGES, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  dim3 grid(t2v_ceil_div(n_a, 128 * MB), t2v_ceil_div(n_b, BN), splits);
+  dim3 grid(t2v_ceil_div(n_a, 128 * MB), t2v_ceil_div(n_b * taps, BN), splits);
   gemm_tc_mn16_kernel<BN, STAGES, MB><<<grid, 192, smem, stream>>>(tmA, tmB, p, fmt == 2 ? 1 : 0);
   T2V_COUNT_LAUNCH();
   T2V_LAUNCH_CHECK();

@@ -42,14 +42,16 @@ _ctypes = _lib.ctypes
 
 _SIDE = {}
 _OVERLAP = __import__("os").environ.get("T2V_OVERLAP", "1") != "0"
-# Postnet weight gradients on a side branch beside the persistent decoder-backward kernel: 77.3 -> 75.1 ms per train step.  History:
-# 2 of 4 bench runs died with "unspecified launch failure" while the backward kernel still had two MMA-issuing warps (which failed on
-# their own too); with the single issuer 4 of 4 runs with the branch were clean.  Still OFF by default until a longer soak run: all 128
-# CTAs of the persistent kernels must become co-resident, and foreign CTAs on the GPU while their clusters are placed are the one
-# situation that has not been exercised for long.
-_POST_DW_BRANCH = __import__("os").environ.get("T2V_POST_DW_BRANCH", "0") == "1"
+# Postnet weight gradients on a low-priority side branch beside the dX chain (and, if they last that long, beside the persistent
+# decoder-backward kernel on the SMs it leaves free).  Round 1 kept this off: launch failures next to the two-MMA-issuer backward
+# kernel.  Since then the persistent kernels are launched cooperatively (placed as a whole or not yet at all), the single-issuer
+# kernel soaked clean for 200 steps with the branch (profiles/r02_soak_200_steps_post_dw_branch.json), and with all five taps in one
+# launch the branch finishes long before the backward loop starts.  T2V_POST_DW_BRANCH=0 puts the GEMMs back on the main chain.
+_POST_DW_BRANCH = __import__("os").environ.get("T2V_POST_DW_BRANCH", "1") == "1"
 _BILSTM_PERSIST = __import__("os").environ.get("T2V_BILSTM_PERSIST", "1") != "0"
 _DW16 = __import__("os").environ.get("T2V_DW16", "1") != "0"          # decoder weight gradients from the fp16 copies (fp16 mode)
+_PRIO = __import__("os").environ.get("T2V_PRIO", "1") != "0"          # high-priority side streams for critical-path branches
+_TAPS1 = __import__("os").environ.get("T2V_TAPS1", "1") != "0"        # Conv1d weight gradients: all taps in one row-reduction launch
 _BWD16 = __import__("os").environ.get("T2V_BWD16", "1") != "0"        # fp16 operand copies in the persistent backward loop (op16 modes)
 
 
@@ -59,13 +61,17 @@ class _Branch(object):
     Tensors created inside belong to the side stream's allocator pool; every later use of a side stream starts with a
     new fork, so block reuse stays stream-ordered.  T2V_OVERLAP=0 runs everything in order on one stream."""
 
-    def __init__(self, idx):
+    def __init__(self, idx, urgent=False):
+        """urgent: the branch is part of the step's critical path -> same (high) priority as the graph's capture stream; other
+        branches (weight gradients nobody waits for until the optimizer step) keep the default priority, so their CTAs only take
+        the SMs the critical chains leave free (kernel-node priorities survive graph capture)"""
         self.keep = None
         self.main = torch.cuda.current_stream()
         if _OVERLAP:
-            key = (self.main.device_index, idx)
+            prio = -1 if (urgent and _PRIO) else 0
+            key = (self.main.device_index, idx, prio)
             if key not in _SIDE:
-                _SIDE[key] = torch.cuda.Stream(device=self.main.device)
+                _SIDE[key] = torch.cuda.Stream(device=self.main.device, priority=prio)
             self.side = _SIDE[key]
         else:
             self.side = None
@@ -201,24 +207,25 @@ class Ops(object):
         return splits
 
     @staticmethod
-    def rowred16(A16, lda, n_a, B16, ldb, n_b, D, ldd, rows, alpha_dev, fmt=1, a_row0=0, b_row0=0):
-        """D[n_a, n_b] += (*alpha_dev) * A16[a_row0 + r]^T B16[b_row0 + r] over fp16 copies (kind::f16, 256 x 256 tiles); D zero-initialised"""
+    def rowred16(A16, lda, n_a, B16, ldb, n_b, D, ldd, rows, alpha_dev, fmt=1, a_row0=0, b_row0=0, taps=1):
+        """D[n_a, taps*n_b] += (*alpha_dev) * A16[a_row0 + r]^T B16[b_row0 + tap + r] over fp16 copies (kind::f16, 256 x 256 tiles);
+        D zero-initialised.  taps > 1: all taps of a Conv1d weight gradient in one launch"""
         iters = (rows + 63) // 64
-        tiles = ((n_a + 255) // 256) * (n_b // 256)
+        tiles = ((n_a + 255) // 256) * (n_b * taps // 256)
         L("t2v_gemm_tc_rowred16", A16, lda, n_a, a_row0, B16, ldb, n_b, b_row0, D, ldd, rows, Ops.pick_splits(tiles, iters), 1, 1.0,
-          alpha_dev, fmt)
+          alpha_dev, fmt, taps)
 
     @staticmethod
-    def rowred(A, lda, n_a, a_row0, Bm, ldb, n_b, b_row0, D, ldd, rows):
-        """D[n_a, n_b] += sum_r A[a_row0+r, :]^T B[b_row0+r, :] on the MN-major tcgen05 kernel (no transposed copies);
+    def rowred(A, lda, n_a, a_row0, Bm, ldb, n_b, b_row0, D, ldd, rows, taps=1):
+        """D[n_a, taps*n_b] += sum_r A[a_row0+r, :]^T B[b_row0+tap+r, :] on the MN-major tcgen05 kernel (no transposed copies);
         split over the reduction so that ~2 CTAs per SM exist.  D must be zero-initialised (or hold the running sum)."""
         iters = (rows + 31) // 32
         wide = n_b > 128 and n_b % 256 == 0
         bm = 256 if (wide and n_a >= 512) else 128            # the tile shapes t2v_gemm_tc_rowred picks
-        tiles = ((n_a + bm - 1) // bm) * ((n_b + 255) // 256 if wide else (n_b + 127) // 128)
+        tiles = ((n_a + bm - 1) // bm) * ((n_b + 255) // 256 if wide else (n_b + 127) // 128) * taps
         # split the reduction so that the CTAs fill whole waves of the 148 SMs (each extra split costs one more pass of atomics over D)
         splits = Ops.pick_splits(tiles, iters)
-        L("t2v_gemm_tc_rowred", A, lda, n_a, a_row0, Bm, ldb, n_b, b_row0, D, ldd, rows, splits, 0, 1, 1.0)
+        L("t2v_gemm_tc_rowred", A, lda, n_a, a_row0, Bm, ldb, n_b, b_row0, D, ldd, rows, splits, 0, 1, 1.0, taps)
 
     @staticmethod
     def _tc_reduce_rows(AT, lda, n_a, a_k0, BT, ldb, n_b, b_k0, D, ldd, Mred, accumulate, a_inner=None, b_inner=None):
@@ -372,10 +379,11 @@ def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0
                 L("t2v_cvt16_scaled", dY, dY16, R * Co, 1, sc)
                 X16 = torch.empty(R, Ci, device=dev, dtype=torch.int16)
                 L("t2v_cvt16_scaled", s["X"], X16, R * Ci, 1, None)
-                for tap in range(5):
-                    Ops.rowred16(dY16, Co, Co, X16, Ci, Ci, _p(dWk, tap * Ci), 5 * Ci, M, sc.data_ptr() + 4, 1, a_row0=2, b_row0=tap)
+                Ops.rowred16(dY16, Co, Co, X16, Ci, Ci, dWk, 5 * Ci, M, sc.data_ptr() + 4, 1, a_row0=2, b_row0=0, taps=5)
+            elif ops.tc and _TAPS1 and (Ci % 256 == 0 or Ci in (64, 128)):
+                # the tap is a row offset of the X operand (MN-major operands, no transposes): all five taps in one launch
+                Ops.rowred(dY, Co, Co, 2, s["X"], Ci, Ci, 0, dWk, 5 * Ci, M, taps=5)
             elif ops.tc:
-                # one row-reduction GEMM per tap: the tap is a row offset of the X operand (MN-major operands, no transposes)
                 for tap in range(5):
                     Ops.rowred(dY, Co, Co, 2, s["X"], Ci, Ci, tap, _p(dWk, tap * Ci), 5 * Ci, M)
             else:
@@ -990,7 +998,7 @@ def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=No
     with br_prep:
         prep = decoder_prepare(ops, P, mel_tgt, B, Ti, g("prenet"), seed, dev)
     # the reference encoder / VAE head only needs the mel: it runs beside the text encoder (both are chains of small kernels)
-    br = _Branch(0)
+    br = _Branch(0, urgent=True)
     with br:
         eps = g("eps")
         if training and eps is None:
@@ -1058,7 +1066,7 @@ def backward_train(ops, P, c, dmel, dpost, dgate, dmu, dlogvar):
     L("t2v_sum_rows_per_batch", dmem, dstyle, B, Ti, 512, 0.0)
     # three independent tails: decoder weight gradients (branch started in decoder_backward), VAE / reference encoder,
     # text encoder
-    br_vae = _Branch(1)
+    br_vae = _Branch(1, urgent=True)
     with br_vae:
         vae_backward(ops, P, dstyle, dmu, dlogvar, c.vae, dev, grads)
     encoder_backward(ops, P, dmem, c.enc, c.training, c.seed, dev, grads)

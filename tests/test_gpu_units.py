@@ -455,14 +455,14 @@ def test_gemm_tc_rowred_mn_major(L, rows, n_a, n_b, a0, b0, splits):
     L("t2v_round_tf32", A, A.numel())
     L("t2v_round_tf32", Bm, Bm.numel())
     D = torch.zeros(n_a, n_b, device=dev)
-    L("t2v_gemm_tc_rowred", A, lda, n_a, a0, Bm, ldb, n_b, b0, D, n_b, rows, splits, 0, 1, 1.0)
+    L("t2v_gemm_tc_rowred", A, lda, n_a, a0, Bm, ldb, n_b, b0, D, n_b, rows, splits, 0, 1, 1.0, 1)
     torch.cuda.synchronize()
     ref = (A[a0:a0 + rows, :n_a].double().t() @ Bm[b0:b0 + rows, :n_b].double()).float()
     err = float((D - ref).abs().max() / ref.abs().max())
     print("rowred rows=%d %dx%d splits=%d max-rel %.2e" % (rows, n_a, n_b, splits, err))
     assert err < 1e-4, err
     if splits == 1:      # non-atomic accumulate: D += the same product
-        L("t2v_gemm_tc_rowred", A, lda, n_a, a0, Bm, ldb, n_b, b0, D, n_b, rows, 1, 0, 2, 1.0)
+        L("t2v_gemm_tc_rowred", A, lda, n_a, a0, Bm, ldb, n_b, b0, D, n_b, rows, 1, 0, 2, 1.0, 1)
         torch.cuda.synchronize()
         assert float((D - 2 * ref).abs().max() / ref.abs().max()) < 2e-4
 
@@ -675,9 +675,34 @@ def test_gemm_tc_rowred16_mn_major_fp16(L, rows, n_a, n_b, splits):
     Bm = torch.randn(rows + 3, n_b, generator=g).to(dev).half()
     D = torch.zeros(n_a, n_b, device=dev)
     alpha = torch.tensor([0.25], device=dev)
-    L("t2v_gemm_tc_rowred16", A.view(torch.int16), n_a, n_a, 0, Bm.view(torch.int16), n_b, n_b, 0, D, n_b, rows, splits, 1, 1.0, alpha, 1)
+    L("t2v_gemm_tc_rowred16", A.view(torch.int16), n_a, n_a, 0, Bm.view(torch.int16), n_b, n_b, 0, D, n_b, rows, splits, 1, 1.0, alpha, 1, 1)
     torch.cuda.synchronize()
     ref = 0.25 * (A[:rows].double().t() @ Bm[:rows].double()).float()
     err = float((D - ref).abs().max() / ref.abs().max())
     print("rowred16 rows=%d %dx%d splits=%d max-rel %.2e" % (rows, n_a, n_b, splits, err))
+    assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("bits,rows,n_a,n_b,splits", [(32, 2000, 512, 512, 3), (32, 1500, 512, 128, 2), (32, 900, 80, 512, 4),
+                                                      (16, 6000, 512, 512, 5), (16, 700, 256, 256, 1)])
+def test_gemm_tc_rowred_taps(L, bits, rows, n_a, n_b, splits):
+    """Conv1d weight gradient in one launch (taps = 5): D[:, t*n_b:(t+1)*n_b] = A[2:2+rows]^T B[t:t+rows] for every tap t, through
+    t2v_gemm_tc_rowred (tf32) and t2v_gemm_tc_rowred16 (fp16), against fp64 of the same rounded operands."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(rows + n_a + bits)
+    A = torch.randn(rows + 4, n_a, generator=g).to(dev)
+    Bm = torch.randn(rows + 4, n_b, generator=g).to(dev)
+    D = torch.zeros(n_a, 5 * n_b, device=dev)
+    if bits == 32:
+        L("t2v_round_tf32", A, A.numel())
+        L("t2v_round_tf32", Bm, Bm.numel())
+        L("t2v_gemm_tc_rowred", A, n_a, n_a, 2, Bm, n_b, n_b, 0, D, 5 * n_b, rows, splits, 0, 1, 1.0, 5)
+    else:
+        A, Bm = A.half(), Bm.half()
+        L("t2v_gemm_tc_rowred16", A.view(torch.int16), n_a, n_a, 2, Bm.view(torch.int16), n_b, n_b, 0, D, 5 * n_b, rows, splits, 1, 1.0,
+          None, 1, 5)
+    torch.cuda.synchronize()
+    ref = torch.cat([(A[2:2 + rows].double().t() @ Bm[t:t + rows].double()).float() for t in range(5)], dim=1)
+    err = float((D - ref).abs().max() / ref.abs().max())
+    print("rowred taps bits=%d rows=%d %dx%d splits=%d max-rel %.2e" % (bits, rows, n_a, n_b, splits, err))
     assert err < 1e-4, err
