@@ -57,12 +57,21 @@ int t2v_gemm_tc_rowred(const float* A, long long lda, int n_a, long long a_row0,
                        long long b_row0, float* D, long long ldd, long long rows, int splits, long long split_stride,
                        int epi, float alpha, int taps, cudaStream_t stream);
 
+/* batched form: D[z][i,j] = alpha * sum_{r<rows} A[z*a_batch_rows + r, i] * B[r, z*b_batch_cols + j] (plain stores, n_a <= 128,
+   n_b % 256 == 0): d(memory)[b] = alignments[b]^T dctx[:, b, :], the backward of attention_context = bmm(attention_weights, memory)
+   (model.py:84-85) summed over the decoder steps. */
+int t2v_gemm_tc_rowred_batched(const float* A, long long lda, int n_a, long long a_batch_rows, const float* B, long long ldb,
+                               int n_b, long long b_batch_cols, float* D, long long ldd, long long d_batch_stride,
+                               long long rows, int batch, float alpha, cudaStream_t stream);
+
 /* the same row reduction over 16-bit operands (fp16 / bf16 copies, kind::f16, 64 reduction rows per stage): the decoder's big weight
    gradients dW = DG^T X from the fp16 copies the persistent loops leave behind (XA16 / XD16, DGA16 / DGD16).  alpha_dev (nullable):
-   device scalar multiplied onto alpha (the inverse gradient scale). */
+   device scalar multiplied onto alpha (the inverse gradient scale).  taps: as t2v_gemm_tc_rowred.  n_split > 0 (multiple of 256):
+   product columns [n_split, n_b) are written to D2 (row stride ldd2) instead of D: [dW_ih | dW_hh] of an LSTMCell (model.py:363-380)
+   land in the two parameters' own gradient tensors. */
 int t2v_gemm_tc_rowred16(const void* A, long long lda, int n_a, long long a_row0, const void* B, long long ldb, int n_b,
                          long long b_row0, float* D, long long ldd, long long rows, int splits, int epi, float alpha,
-                         const float* alpha_dev, int fmt, int taps, cudaStream_t stream);
+                         const float* alpha_dev, int fmt, int taps, float* D2, long long ldd2, int n_split, cudaStream_t stream);
 
 /* ---- text embedding (model.py:474,528) -- integer gather, bit exact ------------------------------------------- */
 int t2v_embedding_fwd(const long long* ids, const float* table, float* out_padded, int B, int T, int C, int n_symbols,
@@ -313,6 +322,9 @@ typedef struct T2VDecoderBwd {
                                       16-bit weight-gradient GEMMs after the loop) */
   const void *WaTP16, *WdTP16;   /*   fp16 re-tiled W^T (t2v_pack_step_tiles16 modes 2 / 3) */
   const float* dg_scale;         /*   device [2] = {s, 1/s}: power-of-two gradient scale (t2v_grad_scale) */
+  float *gb_att, *gb_dec;        /* optional (NULL = unused), zero-initialised [4096] each: bias gradients of attention_rnn / decoder_rnn
+                                    (column sums of DGA / DGD) accumulated by the persistent kernel; valid when
+                                    t2v_decoder_last_bwd_path() == 1, the per-step path leaves them untouched */
 } T2VDecoderBwd;
 int t2v_decoder_bwd_steps(const T2VDecoderBwd* s, int t_hi, int t_lo, cudaStream_t stream);  /* t = t_hi-1 .. t_lo */
 int t2v_decoder_last_bwd_path(void);   /* 1: the last t2v_decoder_bwd_steps of this thread enqueued the persistent kernel (DGA16 / DGD16 valid) */

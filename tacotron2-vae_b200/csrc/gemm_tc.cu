@@ -335,8 +335,12 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // Conv1d weight gradients (b_tap_stride = Ci > 0): D is [n_a, taps * Ci]; the column block of tap t reads the SAME B columns from
   // rows shifted by t, so one launch covers all taps (BN divides Ci: a tile never straddles two taps)
   const int tap = p.b_tap_stride > 0 ? n0 / p.b_tap_stride : 0;
-  const int nb0 = n0 - tap * p.b_tap_stride, brow0 = p.b_row0 + tap;
-  const int it0 = blockIdx.z * p.iters_per_split;
+  // batched form (batch_a_rows > 0): blockIdx.z is a batch index instead of a split -- A rows start at z * batch_a_rows, B columns
+  // at z * batch_b_cols, D at z * split_stride; the whole reduction belongs to this CTA
+  const bool batched = p.batch_a_rows > 0;
+  const int nb0 = n0 - tap * p.b_tap_stride + (batched ? (int)blockIdx.z * p.batch_b_cols : 0), brow0 = p.b_row0 + tap;
+  const int arow0 = p.a_row0 + (batched ? (int)blockIdx.z * p.batch_a_rows : 0);
+  const int it0 = batched ? 0 : blockIdx.z * p.iters_per_split;
   const int n_it = min(p.iters_per_split, p.chunks_per_tap - it0);   // chunks_per_tap = total 32-row iterations; the last split may be short
 
   if (threadIdx.x == 0) {
@@ -365,7 +369,7 @@ gemm_tc_mn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int r = (it0 + it) * BKR;
         uint8_t* sa = smem + s * STAGE_BYTES;
 #pragma unroll
-        for (int g = 0; g < BM / 32; ++g) tma_load_2d(sa + g * BOX, &tmA, m0 + 32 * g, p.a_row0 + r, &full[s]);
+        for (int g = 0; g < BM / 32; ++g) tma_load_2d(sa + g * BOX, &tmA, m0 + 32 * g, arow0 + r, &full[s]);
 #pragma unroll
         for (int g = 0; g < BN / 32; ++g) tma_load_2d(sa + A_BYTES + g * BOX, &tmB, nb0 + 32 * g, brow0 + r, &full[s]);
       }
@@ -526,11 +530,17 @@ gemm_tc_mn16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     const float alpha = p.alpha * (p.alpha_dev ? *p.alpha_dev : 1.f);
     const int q = warp & 3;
-    const bool vec4 = ((((uintptr_t)p.D) & 15) == 0) && (p.ldd % 4 == 0);
+    // column split (n_split > 0): columns [n_split, N) of the product belong to a second matrix D2 (tiles never straddle the split):
+    // dW = [dW_ih | dW_hh] of an LSTM cell goes straight into the two parameters' gradient tensors
+    const bool second = p.n_split > 0 && n0 >= p.n_split;
+    float* const Dm = second ? p.D2 : p.D;
+    const long long ldm = second ? p.ldd2 : p.ldd;
+    const int cshift = second ? p.n_split : 0;
+    const bool vec4 = ((((uintptr_t)Dm) & 15) == 0) && (ldm % 4 == 0);
 #pragma unroll 1
     for (int mb = 0; mb < MB; ++mb) {
       const int row = m0 + mb * 128 + q * 32 + lane;
-      float* drow = p.D + (long long)row * p.ldd;
+      float* drow = Dm + (long long)row * ldm - cshift;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -769,6 +779,31 @@ T2V_API int t2v_gemm_tc_rowred(const float* A, long long lda, int n_a, long long
   return launch_gemm_tc_mn<64, 8>(tmA, tmB, p, splits, stream);
 }
 
+// batched row reduction: D[z][i, j] = alpha * sum_{r < rows} A[z * a_batch_rows + r, i] * B[r, z * b_batch_cols + j], z < batch.
+// A: [batch * a_batch_rows, n_a] row-major (row stride lda), B: [rows, batch * b_batch_cols] (row stride ldb), D: batch matrices
+// [n_a, n_b] (row stride ldd, d_batch_stride floats apart), plain stores.  The reduction tail past `rows` is zero-filled on the B side
+// (A's tail rows belong to the next batch: finite values times zero).  Use: d(memory)[b] = alignments[b]^T dctx[:, b, :]
+// (autograd of attention_context = bmm(attention_weights, memory), model.py:84-85) over the saved alignments, tf32 operands.
+T2V_API int t2v_gemm_tc_rowred_batched(const float* A, long long lda, int n_a, long long a_batch_rows, const float* B, long long ldb,
+                                       int n_b, long long b_batch_cols, float* D, long long ldd, long long d_batch_stride,
+                                       long long rows, int batch, float alpha, cudaStream_t stream) {
+  T2V_ARG_CHECK(A && B && D && n_a > 0 && n_a <= 128 && n_b > 0 && rows > 0 && batch >= 1 && batch <= 65535, "shape (n_a <= 128)");
+  T2V_ARG_CHECK((((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "operand base must be 16-byte aligned");
+  T2V_ARG_CHECK((lda * 4) % 16 == 0 && (ldb * 4) % 16 == 0, "row strides must be multiples of 16 bytes");
+  T2V_ARG_CHECK(n_b % 256 == 0 && b_batch_cols >= n_b && a_batch_rows >= rows, "n_b must be a multiple of the 256-column tile");
+  const int iters = t2v_ceil_div(rows, BKR);
+  CUtensorMap tmA, tmB;
+  int r = encode_mn(&tmA, A, n_a, (long long)batch * a_batch_rows, lda);
+  if (r) return r;
+  r = encode_mn(&tmB, B, (long long)(batch - 1) * b_batch_cols + n_b, rows, ldb);
+  if (r) return r;
+  GemmTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.D = D; p.ldd = ldd; p.split_stride = d_batch_stride; p.M = n_a; p.N = n_b; p.iters_per_split = iters; p.chunks_per_tap = iters;
+  p.epi_atomic = 0; p.alpha = alpha; p.batch_a_rows = (int)a_batch_rows; p.batch_b_cols = (int)b_batch_cols;
+  return launch_gemm_tc_mn<256, 4>(tmA, tmB, p, batch, stream);
+}
+
 namespace {
 int encode_mn16(CUtensorMap* map, const void* base, long long cols, long long rows, long long ld) {
   PFN_encodeTiled fn = get_encode_fn();
@@ -789,9 +824,12 @@ int encode_mn16(CUtensorMap* map, const void* base, long long cols, long long ro
 }  // namespace
 
 // D[n_a, n_b] (+)= alpha * (*alpha_dev) * sum_{r < rows} A[a_row0 + r, i] * B[b_row0 + r, j] over 16-bit operands (fmt 1 fp16, 2 bf16).
+// n_split > 0: product columns [0, n_split) go to D (row stride ldd), columns [n_split, n_b) to D2 (row stride ldd2).
 T2V_API int t2v_gemm_tc_rowred16(const void* A, long long lda, int n_a, long long a_row0, const void* B, long long ldb, int n_b,
                                  long long b_row0, float* D, long long ldd, long long rows, int splits, int epi, float alpha,
-                                 const float* alpha_dev, int fmt, int taps, cudaStream_t stream) {
+                                 const float* alpha_dev, int fmt, int taps, float* D2, long long ldd2, int n_split,
+                                 cudaStream_t stream) {
+  T2V_ARG_CHECK(n_split == 0 || (D2 && n_split % 256 == 0 && n_split < n_b && taps == 1), "column split: D2 and a multiple of 256");
   T2V_ARG_CHECK(A && B && D && n_a > 0 && n_b > 0 && rows > 0 && splits >= 1 && (fmt == 1 || fmt == 2) && taps >= 1, "shape / fmt");
   T2V_ARG_CHECK((((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0, "operand base must be 16-byte aligned");
   T2V_ARG_CHECK((lda * 2) % 16 == 0 && (ldb * 2) % 16 == 0, "row strides must be multiples of 16 bytes");
@@ -809,6 +847,7 @@ T2V_API int t2v_gemm_tc_rowred16(const void* A, long long lda, int n_a, long lon
   p.D = D; p.ldd = ldd; p.M = n_a; p.N = n_b * taps; p.iters_per_split = t2v_ceil_div(iters, splits); p.chunks_per_tap = iters;
   p.epi_atomic = epi; p.alpha = alpha; p.alpha_dev = alpha_dev; p.a_row0 = (int)a_row0; p.b_row0 = (int)b_row0;
   p.b_tap_stride = taps > 1 ? n_b : 0;
+  p.D2 = D2; p.ldd2 = ldd2; p.n_split = n_split;
   constexpr int STAGES = 3, MB = 2, BN = 256;
   constexpr int smem = STAGES * (128 * MB + BN) * BKR16 * 2 + 1024 + 256;
   static bool attr_set = false;

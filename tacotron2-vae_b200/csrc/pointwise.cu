@@ -348,13 +348,18 @@ __global__ void bcast_add_rows_kernel(float* __restrict__ y, const float* __rest
 __global__ void sum_rows_per_batch_kernel(const float* __restrict__ x, float* __restrict__ out, int rows_per_batch,
                                           int C, float beta) {
   const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f;
-    const float* p = x + (long long)b * rows_per_batch * C + c;
-    for (int r = 0; r < rows_per_batch; ++r) a += p[(long long)r * C];
-    float* o = out + (long long)b * C + c;
-    *o = (beta != 0.f ? beta * (*o) : 0.f) + a;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;       // column blocks across blockIdx.y: B = 1 calls still fill the GPU
+  if (c >= C) return;
+  const float* p = x + (long long)b * rows_per_batch * C + c;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;              // four independent chains: the loads of a column stay in flight
+  int r = 0;
+  for (; r + 4 <= rows_per_batch; r += 4) {
+    a0 += p[(long long)r * C]; a1 += p[(long long)(r + 1) * C]; a2 += p[(long long)(r + 2) * C]; a3 += p[(long long)(r + 3) * C];
   }
+  for (; r < rows_per_batch; ++r) a0 += p[(long long)r * C];
+  const float a = (a0 + a1) + (a2 + a3);
+  float* o = out + (long long)b * C + c;
+  *o = (beta != 0.f ? beta * (*o) : 0.f) + a;
 }
 // sums `n_parts` partial buffers (stride part_stride) into dst (+ optional second/third plain sources)
 __global__ void sum_parts_kernel(const float* __restrict__ parts, int n_parts, long long part_stride,
@@ -688,7 +693,7 @@ T2V_API int t2v_bcast_add_rows(float* y, const float* v, long long rows, int C, 
 }
 T2V_API int t2v_sum_rows_per_batch(const float* x, float* out, int B, int rows_per_batch, int C, float beta,
                                    cudaStream_t st) {
-  sum_rows_per_batch_kernel<<<B, 256, 0, st>>>(x, out, rows_per_batch, C, beta);
+  sum_rows_per_batch_kernel<<<dim3(B, t2v_ceil_div(C, 128)), 128, 0, st>>>(x, out, rows_per_batch, C, beta);
   LAUNCH_END();
 }
 T2V_API int t2v_sum_parts(const float* parts, int n_parts, long long part_stride, float* dst, long long n, cudaStream_t st) {

@@ -32,7 +32,7 @@ class T2VDecoderBwd(ctypes.Structure):
     _fields_ = [("f", T2VDecoderSeq)] + [(n, _P) for n in (
         "WaT", "WdT", "WqT", "DHC", "DGA", "DGD", "DXA", "DXD", "dCa", "dCd", "dwprev", "gcum", "dpmem", "DCTX", "dw_part",
         "DQ", "dHq", "dv_part", "dwloc_part", "dwconv_part", "WaTP", "WdTP")] + [("op16", ctypes.c_int)] + [(n, _P) for n in (
-        "DGA16", "DGD16", "WaTP16", "WdTP16", "dg_scale")]
+        "DGA16", "DGD16", "WaTP16", "WdTP16", "dg_scale", "gb_att", "gb_dec")]
 
 
 class T2VDecoderInfer(ctypes.Structure):

@@ -51,6 +51,8 @@ _POST_DW_BRANCH = __import__("os").environ.get("T2V_POST_DW_BRANCH", "1") == "1"
 _BILSTM_PERSIST = __import__("os").environ.get("T2V_BILSTM_PERSIST", "1") != "0"
 _DW16 = __import__("os").environ.get("T2V_DW16", "1") != "0"          # decoder weight gradients from the fp16 copies (fp16 mode)
 _PRIO = __import__("os").environ.get("T2V_PRIO", "1") != "0"          # high-priority side streams for critical-path branches
+_BIAS_IN_LOOP = __import__("os").environ.get("T2V_BIAS_IN_LOOP", "1") != "0"   # LSTM bias gradients from the backward loop kernel
+_DMEM_TC = __import__("os").environ.get("T2V_DMEM_TC", "1") != "0"    # d(memory) = alignments^T dctx on the tensor core (tf32)
 _TAPS1 = __import__("os").environ.get("T2V_TAPS1", "1") != "0"        # Conv1d weight gradients: all taps in one row-reduction launch
 _BWD16 = __import__("os").environ.get("T2V_BWD16", "1") != "0"        # fp16 operand copies in the persistent backward loop (op16 modes)
 
@@ -207,13 +209,13 @@ class Ops(object):
         return splits
 
     @staticmethod
-    def rowred16(A16, lda, n_a, B16, ldb, n_b, D, ldd, rows, alpha_dev, fmt=1, a_row0=0, b_row0=0, taps=1):
+    def rowred16(A16, lda, n_a, B16, ldb, n_b, D, ldd, rows, alpha_dev, fmt=1, a_row0=0, b_row0=0, taps=1, D2=None, ldd2=0, n_split=0):
         """D[n_a, taps*n_b] += (*alpha_dev) * A16[a_row0 + r]^T B16[b_row0 + tap + r] over fp16 copies (kind::f16, 256 x 256 tiles);
         D zero-initialised.  taps > 1: all taps of a Conv1d weight gradient in one launch"""
         iters = (rows + 63) // 64
         tiles = ((n_a + 255) // 256) * (n_b * taps // 256)
         L("t2v_gemm_tc_rowred16", A16, lda, n_a, a_row0, B16, ldb, n_b, b_row0, D, ldd, rows, Ops.pick_splits(tiles, iters), 1, 1.0,
-          alpha_dev, fmt, taps)
+          alpha_dev, fmt, taps, D2, ldd2, n_split)
 
     @staticmethod
     def rowred(A, lda, n_a, a_row0, Bm, ldb, n_b, b_row0, D, ldd, rows, taps=1):
@@ -285,6 +287,31 @@ def _colsum(x, rows, C, period, lo, hi, dev, ld=None):
     out = _empty(C, device=dev)
     L("t2v_double_to_float", acc, out, C, 0.0)
     return out
+
+
+class Grads(dict):
+    """name -> gradient tensor.  `dst` (optional) maps parameter names to pre-allocated destinations (the slices of the model's flat
+    gradient buffer, t2v.optim.FlatGrads): producers of the large gradients write there directly, so the step needs no
+    concatenation pass over them afterwards."""
+
+    def __init__(self, dst=None):
+        dict.__init__(self)
+        self.dst = dst or {}
+
+    def out(self, name, *shape, dev, zero=False):
+        v = self.dst.get(name)
+        if v is not None and tuple(v.shape) == tuple(shape) and v.is_contiguous():
+            if zero:
+                v.zero_()
+            return v
+        return _zeros(*shape, device=dev) if zero else _empty(*shape, device=dev)
+
+
+def _gout(grads, name, *shape, dev, zero=False):
+    """destination of a large gradient: the flat-buffer slice when `grads` carries one (Grads.dst), else a fresh tensor"""
+    if isinstance(grads, Grads):
+        return grads.out(name, *shape, dev=dev, zero=zero)
+    return _zeros(*shape, device=dev) if zero else _empty(*shape, device=dev)
 
 
 class _Saved(object):
@@ -388,7 +415,7 @@ def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0
                     Ops.rowred(dY, Co, Co, 2, s["X"], Ci, Ci, tap, _p(dWk, tap * Ci), 5 * Ci, M)
             else:
                 ops.gemm(_p(dY, 2 * Co), 1, Co, s["X"], 1, Ci, dWk, 5 * Ci, Co, 5 * Ci, M, 1.0, 0.0, None)
-            gW = _empty(Co, Ci, 5, device=dev)
+            gW = _gout(grads, pre + ".0.conv.weight", Co, Ci, 5, dev=dev)
             L("t2v_conv1d_unpack_grad", dWk, gW, Co, Ci, 5, 0.0)
             grads[pre + ".0.conv.weight"] = gW
         if i > 0 or need_dx:
@@ -900,7 +927,10 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
         D.DGA16, D.DGD16 = t["DGA16"].data_ptr(), t["DGD16"].data_ptr()
         D.WaTP16, D.WdTP16 = t["WaTP16"].data_ptr(), t["WdTP16"].data_ptr()
         D.dg_scale = t["scale"].data_ptr()
+    t["gba"], t["gbd"] = _zeros(4096, device=dev), _zeros(4096, device=dev)
+    D.gb_att, D.gb_dec = t["gba"].data_ptr(), t["gbd"].data_ptr()
     L("t2v_decoder_bwd_steps", D, To, 0)
+    persistent = bool(_lib.lib().t2v_decoder_last_bwd_path())
     dw16 = bool(D.op16) and ops.op16 == 1 and bool(_lib.lib().t2v_decoder_last_bwd_path()) and buf.get("XA16") is not None and _DW16
     _trace("  bwd decoder loop")
     if ops.tc:
@@ -911,21 +941,31 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
     br.keep = (t, D)                                     # the branch reads these after this function returns
     with br:
         # batched weight gradients over all steps
-        gWa = _zeros(4096, 1792, device=dev)
-        gWd = _zeros(4096, 2560, device=dev)
-        if dw16:     # the two big weight gradients straight from the fp16 copies the loops left behind (gradient copy x 1 / scale)
+        if dw16:     # the two big weight gradients straight from the fp16 copies the loops left behind (gradient copy x 1 / scale);
+            # each GEMM writes its [weight_ih | weight_hh] column blocks into the two parameters' own gradient tensors
             inv = t["scale"].data_ptr() + 4
-            Ops.rowred16(t["DGA16"], 4096, 4096, buf["XA16"], 1792, 1792, gWa, 1792, n, inv)
-            Ops.rowred16(t["DGD16"], 4096, 4096, buf["XD16"], 2560, 2560, gWd, 2560, n, inv)
+            ga_ih = _gout(grads, _D + "attention_rnn.weight_ih", 4096, 768, dev=dev, zero=True)
+            ga_hh = _gout(grads, _D + "attention_rnn.weight_hh", 4096, 1024, dev=dev, zero=True)
+            gd_ih = _gout(grads, _D + "decoder_rnn.weight_ih", 4096, 1536, dev=dev, zero=True)
+            gd_hh = _gout(grads, _D + "decoder_rnn.weight_hh", 4096, 1024, dev=dev, zero=True)
+            Ops.rowred16(t["DGA16"], 4096, 4096, buf["XA16"], 1792, 1792, ga_ih, 768, n, inv, D2=ga_hh, ldd2=1024, n_split=768)
+            Ops.rowred16(t["DGD16"], 4096, 4096, buf["XD16"], 2560, 2560, gd_ih, 1536, n, inv, D2=gd_hh, ldd2=1024, n_split=1536)
+            grads[_D + "attention_rnn.weight_ih"], grads[_D + "attention_rnn.weight_hh"] = ga_ih, ga_hh
+            grads[_D + "decoder_rnn.weight_ih"], grads[_D + "decoder_rnn.weight_hh"] = gd_ih, gd_hh
         else:
+            gWa = _zeros(4096, 1792, device=dev)
+            gWd = _zeros(4096, 2560, device=dev)
             ops.linear_dw(t["DGA"], 4096, XA, 1792, gWa, 1792, n, 4096, 1792, device=dev)
             ops.linear_dw(t["DGD"], 4096, XD, 2560, gWd, 2560, n, 4096, 2560, device=dev)
-        grads[_D + "attention_rnn.weight_ih"] = gWa[:, :768].contiguous()
-        grads[_D + "attention_rnn.weight_hh"] = gWa[:, 768:].contiguous()
-        grads[_D + "decoder_rnn.weight_ih"] = gWd[:, :1536].contiguous()
-        grads[_D + "decoder_rnn.weight_hh"] = gWd[:, 1536:].contiguous()
-        gba = _colsum(t["DGA"], n, 4096, 1, 0, 1, dev)
-        gbd = _colsum(t["DGD"], n, 4096, 1, 0, 1, dev)
+            grads[_D + "attention_rnn.weight_ih"] = gWa[:, :768].contiguous()
+            grads[_D + "attention_rnn.weight_hh"] = gWa[:, 768:].contiguous()
+            grads[_D + "decoder_rnn.weight_ih"] = gWd[:, :1536].contiguous()
+            grads[_D + "decoder_rnn.weight_hh"] = gWd[:, 1536:].contiguous()
+        if persistent and _BIAS_IN_LOOP:      # the persistent kernel summed the gate gradients while it produced them
+            gba, gbd = t["gba"], t["gbd"]
+        else:
+            gba = _colsum(t["DGA"], n, 4096, 1, 0, 1, dev)
+            gbd = _colsum(t["DGD"], n, 4096, 1, 0, 1, dev)
         grads[_D + "attention_rnn.bias_ih"], grads[_D + "attention_rnn.bias_hh"] = gba, gba.clone()
         grads[_D + "decoder_rnn.bias_ih"], grads[_D + "decoder_rnn.bias_hh"] = gbd, gbd.clone()
         gWq = _zeros(128, 1024, device=dev)
@@ -962,7 +1002,15 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
     # d(memory)[b,ti,:] = sum_t w_t[b,ti] * dctx_t[b,:]  (one batched GEMM over the saved alignments)  + dpmem @ W_m
     Wm = P[_A + "memory_layer.linear_layer.weight"]
     dmem = _empty(B * Ti, 512, device=dev)
-    L("t2v_gemm_f32", buf["align"], 1, Ti, t["DCTX"], 1, B * 512, dmem, 512, Ti, 512, To, 1.0, 0.0, None, B, To * Ti, 512, Ti * 512)
+    if ops.tc and _DMEM_TC and Ti % 4 == 0 and Ti <= 128:
+        # on the tensor core (this GEMM heads the chain to the encoder backward): tf32-rounded copies of both operands, one 128 x 256
+        # tile pair per utterance, the decoder steps are the reduction rows of the MN-major kernel
+        al = buf["align"].clone()
+        L("t2v_round_tf32", al, al.numel())
+        L("t2v_round_tf32", t["DCTX"], t["DCTX"].numel())
+        L("t2v_gemm_tc_rowred_batched", al, Ti, Ti, To, t["DCTX"], B * 512, 512, 512, dmem, 512, Ti * 512, To, B, 1.0)
+    else:
+        L("t2v_gemm_f32", buf["align"], 1, Ti, t["DCTX"], 1, B * 512, dmem, 512, Ti, 512, To, 1.0, 0.0, None, B, To * Ti, 512, Ti * 512)
     ops.linear_dx(t["dpmem"], 128, Wm, 512, dmem, 512, B * Ti, 128, 512, accumulate=True)
     return dmem.view(B, Ti, 512), br
 
@@ -1040,11 +1088,12 @@ def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=No
     return [mel, mel_post, gate, align, mu, logvar, z], c
 
 
-def backward_train(ops, P, c, dmel, dpost, dgate, dmu, dlogvar):
-    """Gradients of every live parameter given the output gradients (reference layouts)."""
+def backward_train(ops, P, c, dmel, dpost, dgate, dmu, dlogvar, grad_dst=None):
+    """Gradients of every live parameter given the output gradients (reference layouts).  grad_dst: optional name -> destination
+    tensors (slices of the flat gradient buffer) that the producers of the large gradients fill directly."""
     dev = dmel.device
     B, Ti, To = c.B, c.Ti, c.To
-    grads = {}
+    grads = Grads(grad_dst)
     R = B * (To + 4)
     _trace("")
     dY5 = _zeros(R, 80, device=dev)

@@ -19,7 +19,9 @@ _CAPTURE_STREAMS = {}
 def _capture_stream(dev):
     key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
     if key not in _CAPTURE_STREAMS:
-        prio = -1 if os.environ.get("T2V_CAPTURE_PRIORITY", "1") != "0" else 0
+        # three tiers: the capture stream (the step's main chain) above the urgent side branches (engine._Branch(urgent=True): -1)
+        # above the weight-gradient branches (0); torch clamps to the device's range
+        prio = -2 if os.environ.get("T2V_CAPTURE_PRIORITY", "1") != "0" else 0
         _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=key, priority=prio)
     return _CAPTURE_STREAMS[key]
 
@@ -69,19 +71,33 @@ class GraphedStep(object):
         self.s_dout = [torch.zeros_like(self.outs[i]) for i in (0, 1, 2, 4, 5)]
         self.g_bwd = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool(), stream=cap, capture_error_mode="thread_local"):
-            grads = engine.backward_train(cfg.ops, P, self.c, *self.s_dout)
+            # the gradients land in ONE flat buffer inside the graph.  When the model owns a persistent flat gradient buffer with
+            # the same layout (t2v.optim.FlatGrads: every `.grad` is a view of it, the all-reduce and the fused clip+Adam step
+            # run on it) the graph writes straight into that buffer: no clone, no per-parameter copies afterwards; the producers
+            # of the large gradients (decoder LSTM matrices, convolution weights: 90 % of the bytes) fill their slices themselves,
+            # only the runs of small gradients in between are concatenated into place.
+            fg = getattr(cfg, "flat", None)
+            dst = {k: v for (k, _), v in zip(fg.named, fg.views)} if fg is not None else None
+            grads = engine.backward_train(cfg.ops, P, self.c, *self.s_dout, grad_dst=dst)
             self.live = [n for n in self.names if n in grads]
             self.sizes = [grads[n].numel() for n in self.live]
             self.shapes = [grads[n].shape for n in self.live]
-            # the gradients land in ONE flat buffer inside the graph.  When the model owns a persistent flat gradient buffer with
-            # the same layout (t2v.optim.FlatGrads: every `.grad` is a view of it, the all-reduce and the fused clip+Adam step
-            # run on it) the graph writes straight into that buffer: no clone, no per-parameter copies afterwards.
-            fg = getattr(cfg, "flat", None)
             self.direct = fg is not None and [k for k, _ in fg.named] == self.live and fg.numel == sum(self.sizes)
             self.fg = fg if self.direct else None
             if self.direct:
                 self.flat = fg.buffer
-                torch.cat([grads[n].reshape(-1) for n in self.live], out=self.flat)
+                base, off, run, run_off = fg.buffer.data_ptr(), 0, [], 0
+                for n, sz in zip(self.live + [None], self.sizes + [0]):
+                    in_place = n is not None and grads[n].data_ptr() == base + 4 * off and grads[n].is_contiguous()
+                    if n is None or in_place:
+                        if run:
+                            torch.cat(run, out=self.flat[run_off:off])
+                            run = []
+                    else:
+                        if not run:
+                            run_off = off
+                        run.append(grads[n].reshape(-1))
+                    off += sz
             else:
                 self.flat = torch.cat([grads[n].reshape(-1) for n in self.live])
             del grads

@@ -675,7 +675,7 @@ def test_gemm_tc_rowred16_mn_major_fp16(L, rows, n_a, n_b, splits):
     Bm = torch.randn(rows + 3, n_b, generator=g).to(dev).half()
     D = torch.zeros(n_a, n_b, device=dev)
     alpha = torch.tensor([0.25], device=dev)
-    L("t2v_gemm_tc_rowred16", A.view(torch.int16), n_a, n_a, 0, Bm.view(torch.int16), n_b, n_b, 0, D, n_b, rows, splits, 1, 1.0, alpha, 1, 1)
+    L("t2v_gemm_tc_rowred16", A.view(torch.int16), n_a, n_a, 0, Bm.view(torch.int16), n_b, n_b, 0, D, n_b, rows, splits, 1, 1.0, alpha, 1, 1, None, 0, 0)
     torch.cuda.synchronize()
     ref = 0.25 * (A[:rows].double().t() @ Bm[:rows].double()).float()
     err = float((D - ref).abs().max() / ref.abs().max())
@@ -700,9 +700,45 @@ def test_gemm_tc_rowred_taps(L, bits, rows, n_a, n_b, splits):
     else:
         A, Bm = A.half(), Bm.half()
         L("t2v_gemm_tc_rowred16", A.view(torch.int16), n_a, n_a, 2, Bm.view(torch.int16), n_b, n_b, 0, D, 5 * n_b, rows, splits, 1, 1.0,
-          None, 1, 5)
+          None, 1, 5, None, 0, 0)
     torch.cuda.synchronize()
     ref = torch.cat([(A[2:2 + rows].double().t() @ Bm[t:t + rows].double()).float() for t in range(5)], dim=1)
     err = float((D - ref).abs().max() / ref.abs().max())
     print("rowred taps bits=%d rows=%d %dx%d splits=%d max-rel %.2e" % (bits, rows, n_a, n_b, splits, err))
+    assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("batch,rows,n_a,n_b", [(3, 100, 120, 512), (64, 800, 120, 512), (2, 37, 40, 256)])
+def test_gemm_tc_rowred_batched(L, batch, rows, n_a, n_b):
+    """t2v_gemm_tc_rowred_batched: D[z] = A[z*rows:(z+1)*rows]^T B[:, z*n_b:(z+1)*n_b] (the d(memory) GEMM of the attention backward:
+    alignments [B,To,Ti] x dctx [To,B,512]) against fp64 of the same tf32-rounded operands; rows % 32 != 0 exercises the zero-filled
+    reduction tail (A's tail rows belong to the next batch)."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(batch * 1000 + rows)
+    A = torch.rand(batch, rows, n_a, generator=g).to(dev)
+    Bm = torch.randn(rows, batch, n_b, generator=g).to(dev)
+    L("t2v_round_tf32", A, A.numel())
+    L("t2v_round_tf32", Bm, Bm.numel())
+    D = torch.full((batch, n_a, n_b), float("nan"), device=dev)
+    L("t2v_gemm_tc_rowred_batched", A, n_a, n_a, rows, Bm, batch * n_b, n_b, n_b, D, n_b, n_a * n_b, rows, batch, 1.0)
+    torch.cuda.synchronize()
+    ref = torch.einsum("zri,rzj->zij", A.double(), Bm.double()).float()
+    err = float((D - ref).abs().max() / ref.abs().max())
+    print("rowred batched %d x [%d -> %d x %d] max-rel %.2e" % (batch, rows, n_a, n_b, err))
+    assert err < 1e-4, err
+
+
+def test_gemm_tc_rowred16_column_split(L):
+    """n_split: columns [0, 768) of dW = A^T B land in D, columns [768, 1792) in D2 (the [weight_ih | weight_hh] gradients of an LSTMCell)"""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    rows, n_a, n_b = 3000, 512, 1792
+    A = torch.randn(rows, n_a, generator=g).to(dev).half()
+    Bm = torch.randn(rows, n_b, generator=g).to(dev).half()
+    D1, D2 = torch.zeros(n_a, 768, device=dev), torch.zeros(n_a, 1024, device=dev)
+    L("t2v_gemm_tc_rowred16", A.view(torch.int16), n_a, n_a, 0, Bm.view(torch.int16), n_b, n_b, 0, D1, 768, rows, 3, 1, 1.0, None, 1, 1,
+      D2, 1024, 768)
+    torch.cuda.synchronize()
+    ref = (A.double().t() @ Bm.double()).float()
+    err = float((torch.cat([D1, D2], dim=1) - ref).abs().max() / ref.abs().max())
     assert err < 1e-4, err
