@@ -63,7 +63,7 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
 }
 __device__ __forceinline__ float act_grad(float pre, int act) {
   if (act == 1) return pre > 0.f ? 1.f : 0.f;
-  if (act == 2) { float t = tanhf(pre); return 1.f - t * t; }
+  if (act == 2) { const float t = t2v_tanh(pre); return 1.f - t * t; }    // exp-based tanh: absolute error ~2e-7 on a factor in [0, 1]
   return 1.f;
 }
 __device__ __forceinline__ uint64_t drop_index(const RowSpace& rs, long long r, int c, int C, int T) {
@@ -111,56 +111,83 @@ colreduce_kernel(const float* __restrict__ x, long long rows, int C, RowSpace rs
   }
 }
 
-// Vectorised form (C % 4 == 0): a lane owns 4 consecutive channels (float4), a block covers 128 channels x rows_per_block rows, four
-// rows in flight per thread: these reductions are pure HBM streams (one read of x, MODE 1: of x and y) and the scalar version kept
-// only ~1 KB in flight per warp (17 % of the HBM peak in the round-2 ncu capture).
+// ---- shared pieces of the vectorised BatchNorm kernels.  Thread layout: a block of 256 threads is LX lanes (LX = 2^lx_log2 <= 32, four
+// consecutive channels each) x 256 / LX row phases, so narrow tensors (the reference encoder's C = 32 .. 128 NHWC rows) keep every
+// lane busy.  Row arithmetic is 32-bit (rows < 2^31 is checked on the host): the 64-bit divisions of the scalar kernels cost more
+// instructions than the rest of the element's math.
+struct RowPos { unsigned b; int t; bool ok; };
+__device__ __forceinline__ RowPos row_pos(const RowSpace& rs, unsigned r) {
+  RowPos p;
+  p.b = r / (unsigned)rs.period;
+  const int x = (int)(r - p.b * (unsigned)rs.period);
+  p.t = x - rs.lo;
+  p.ok = x >= rs.lo && x < rs.hi;
+  return p;
+}
+// dropout keep-scale with the seed dereference and the key multiply hoisted out of the element loop: same bits as t2v_keep_scale
+struct DropFast {
+  const float* mask; uint64_t key0; float p, scale;
+  __device__ __forceinline__ void init(const T2VDrop& d) {
+    mask = d.mask; p = d.p; scale = d.p > 0.f ? 1.f / (1.f - d.p) : 1.f;
+    key0 = (d.p > 0.f && !d.mask) ? t2v_resolve_seed(d.seed) * 0x9E3779B97F4A7C15ULL + ((uint64_t)d.site << 40) : 0ull;
+  }
+  __device__ __forceinline__ float keep(uint64_t idx) const {
+    if (p <= 0.f) return 1.f;
+    const float k = mask ? mask[idx] : (((float)(t2v_hash32(key0 + idx) & 0xFFFFFFu) * (1.0f / 16777216.0f)) >= p ? 1.f : 0.f);
+    return k * scale;
+  }
+};
+// Vectorised column reduction (C % 4 == 0): these reductions are HBM streams (one read of x, MODE 1: of x and y); four rows in
+// flight per thread.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 colreduce4_kernel(const float* __restrict__ x, long long rows, int C, RowSpace rs, int rows_per_block, BnCtx ctx,
-                  double* __restrict__ out0, double* __restrict__ out1) {
-  __shared__ float4 s0[8][32], s1[8][32];
-  const int c = blockIdx.y * 128 + threadIdx.x * 4;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  long long r1 = r0 + rows_per_block;
-  if (r1 > rows) r1 = rows;
+                  double* __restrict__ out0, double* __restrict__ out1, int lx_log2) {
+  __shared__ float4 s0[256], s1[256];
+  const int LX = 1 << lx_log2, LY = 256 >> lx_log2;
+  const int tx = threadIdx.x & (LX - 1), ty = threadIdx.x >> lx_log2;
+  const int c = (blockIdx.y * LX + tx) * 4;
+  const unsigned r0 = blockIdx.x * (unsigned)rows_per_block;
+  unsigned r1 = r0 + (unsigned)rows_per_block;
+  if (r1 > (unsigned)rows) r1 = (unsigned)rows;
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
   if (c < C) {
-    float4 mean = a0, invstd = a0, gamma = a0, beta = a0;
+    float mm[4] = {0.f, 0.f, 0.f, 0.f}, is[4] = {0.f, 0.f, 0.f, 0.f}, gm[4] = {0.f, 0.f, 0.f, 0.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
+    DropFast drop;
+    drop.init(ctx.drop);
     if (MODE == 1) {      // scalar loads: parameters may be views into the optimizer's flat buffer (4-byte aligned only)
-      mean = make_float4(ctx.mean[c], ctx.mean[c + 1], ctx.mean[c + 2], ctx.mean[c + 3]);
-      invstd = make_float4(ctx.invstd[c], ctx.invstd[c + 1], ctx.invstd[c + 2], ctx.invstd[c + 3]);
-      gamma = make_float4(ctx.gamma[c], ctx.gamma[c + 1], ctx.gamma[c + 2], ctx.gamma[c + 3]);
-      beta = make_float4(ctx.beta[c], ctx.beta[c + 1], ctx.beta[c + 2], ctx.beta[c + 3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { mm[j] = ctx.mean[c + j]; is[j] = ctx.invstd[c + j]; gm[j] = ctx.gamma[c + j]; bt[j] = ctx.beta[c + j]; }
     }
-    for (long long rb = r0 + threadIdx.y; rb < r1; rb += 32) {
+    for (unsigned rb = r0 + ty; rb < r1; rb += 4 * LY) {
       float4 v[4], y[4];
-      bool ok[4];
+      RowPos rp[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const long long r = rb + 8 * i;
-        ok[i] = r < r1 && rs.valid(r);
-        v[i] = ok[i] ? __ldcs(reinterpret_cast<const float4*>(x + r * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE == 1) y[i] = ok[i] ? __ldcs(reinterpret_cast<const float4*>(ctx.y + r * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const unsigned r = rb + LY * i;
+        rp[i] = row_pos(rs, r);
+        rp[i].ok = rp[i].ok && r < r1;
+        const long long off = (long long)r * C + c;
+        v[i] = rp[i].ok ? __ldcs(reinterpret_cast<const float4*>(x + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 1) y[i] = rp[i].ok ? __ldcs(reinterpret_cast<const float4*>(ctx.y + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if (!ok[i]) continue;
+        if (!rp[i].ok) continue;
         if (MODE == 0) {
           a0.x += v[i].x; a0.y += v[i].y; a0.z += v[i].z; a0.w += v[i].w;
           a1.x += v[i].x * v[i].x; a1.y += v[i].y * v[i].y; a1.z += v[i].z * v[i].z; a1.w += v[i].w * v[i].w;
         } else if (MODE == 2) {
           a0.x += v[i].x; a0.y += v[i].y; a0.z += v[i].z; a0.w += v[i].w;
         } else {
-          const long long r = rb + 8 * i;
           const float vv[4] = {v[i].x, v[i].y, v[i].z, v[i].w}, yy[4] = {y[i].x, y[i].y, y[i].z, y[i].w};
-          const float mm[4] = {mean.x, mean.y, mean.z, mean.w}, is[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
-          const float gm[4] = {gamma.x, gamma.y, gamma.z, gamma.w}, bt[4] = {beta.x, beta.y, beta.z, beta.w};
+          const uint64_t base = ((uint64_t)rp[i].b * C + c) * (uint64_t)ctx.T + rp[i].t;      // dropout index of (b, c, t)
           float g[4], xh[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             xh[j] = (yy[j] - mm[j]) * is[j];
             const float pre = gm[j] * xh[j] + bt[j];
-            g[j] = vv[j] * act_grad(pre, ctx.act) * t2v_keep_scale(ctx.drop, drop_index(rs, r, c + j, C, ctx.T));
+            g[j] = vv[j] * act_grad(pre, ctx.act) * drop.keep(base + (uint64_t)j * ctx.T);
           }
           a0.x += g[0]; a0.y += g[1]; a0.z += g[2]; a0.w += g[3];
           a1.x += g[0] * xh[0]; a1.y += g[1] * xh[1]; a1.z += g[2] * xh[2]; a1.w += g[3] * xh[3];
@@ -168,14 +195,13 @@ colreduce4_kernel(const float* __restrict__ x, long long rows, int C, RowSpace r
       }
     }
   }
-  s0[threadIdx.y][threadIdx.x] = a0;
-  s1[threadIdx.y][threadIdx.x] = a1;
+  s0[threadIdx.x] = a0;
+  s1[threadIdx.x] = a1;
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
+  if (ty == 0 && c < C) {
     float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 p0 = s0[i][threadIdx.x], p1 = s1[i][threadIdx.x];
+    for (int i = 0; i < LY; ++i) {
+      const float4 p0 = s0[i * LX + tx], p1 = s1[i * LX + tx];
       t0.x += p0.x; t0.y += p0.y; t0.z += p0.z; t0.w += p0.w;
       t1.x += p1.x; t1.y += p1.y; t1.z += p1.z; t1.w += p1.w;
     }
@@ -215,61 +241,103 @@ __global__ void bn_eval_prepare_kernel(const float* __restrict__ running_mean, c
 
 // out = dropout(act(gamma*(y-mean)*invstd+beta)) on valid rows, 0 on pad rows
 // out_lo (optional): the residual x - round(x) on the tf32 grid, for the split (error-compensated) tensor-core GEMMs
-__global__ void bn_act_fwd_kernel(const float* __restrict__ y, float* __restrict__ out, float* __restrict__ out_lo, long long rows,
-                                  int C, RowSpace rs, BnCtx ctx, int rnd) {
-  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index
-  const long long total4 = rows * C / 4;
-  if (i4 >= total4) return;
-  const long long r = (i4 * 4) / C;
-  const int c = (int)((i4 * 4) % C);
-  float4 o = make_float4(0.f, 0.f, 0.f, 0.f), ol = o;
-  if (rs.valid(r)) {
-    const float4 v = reinterpret_cast<const float4*>(y)[i4];
-    float in[4] = {v.x, v.y, v.z, v.w}, res[4], lo[4];
+// Thread layout as in colreduce4_kernel; a thread keeps the parameters of its four channels in registers and walks rows.
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const float* __restrict__ y, float* __restrict__ out, float* __restrict__ out_lo, long long rows,
+                  int C, RowSpace rs, BnCtx ctx, int rnd, int rows_per_block, int lx_log2) {
+  const int LX = 1 << lx_log2, LY = 256 >> lx_log2;
+  const int tx = threadIdx.x & (LX - 1), ty = threadIdx.x >> lx_log2;
+  const int c = (blockIdx.y * LX + tx) * 4;
+  if (c >= C) return;
+  const unsigned r0 = blockIdx.x * (unsigned)rows_per_block;
+  unsigned r1 = r0 + (unsigned)rows_per_block;
+  if (r1 > (unsigned)rows) r1 = (unsigned)rows;
+  float sc[4], sh[4], mm[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float pre = ctx.gamma[c + j] * ((in[j] - ctx.mean[c + j]) * ctx.invstd[c + j]) + ctx.beta[c + j];
-      const float x = act_fwd(pre, ctx.act) * t2v_keep_scale(ctx.drop, drop_index(rs, r, c + j, C, ctx.T));
-      res[j] = t2v_rnd(x, rnd);
-      lo[j] = t2v_tf32(x - res[j]);
+  for (int j = 0; j < 4; ++j) { mm[j] = ctx.mean[c + j]; sc[j] = ctx.invstd[c + j]; sh[j] = ctx.beta[c + j]; }
+  float gm[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) gm[j] = ctx.gamma[c + j];
+  DropFast drop;
+  drop.init(ctx.drop);
+  for (unsigned r = r0 + ty; r < r1; r += LY) {
+    const RowPos rp = row_pos(rs, r);
+    const long long off = (long long)r * C + c;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f), ol = o;
+    if (rp.ok) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(y + off));
+      const float in[4] = {v.x, v.y, v.z, v.w};
+      const uint64_t base = ((uint64_t)rp.b * C + c) * (uint64_t)ctx.T + rp.t;
+      float res[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pre = gm[j] * ((in[j] - mm[j]) * sc[j]) + sh[j];
+        const float x = act_fwd(pre, ctx.act) * drop.keep(base + (uint64_t)j * ctx.T);
+        res[j] = t2v_rnd(x, rnd);
+        lo[j] = t2v_tf32(x - res[j]);
+      }
+      o = make_float4(res[0], res[1], res[2], res[3]);
+      ol = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
-    o = make_float4(res[0], res[1], res[2], res[3]);
-    ol = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<float4*>(out + off) = o;
+    if (out_lo) *reinterpret_cast<float4*>(out_lo + off) = ol;
   }
-  reinterpret_cast<float4*>(out)[i4] = o;
-  if (out_lo) reinterpret_cast<float4*>(out_lo)[i4] = ol;
 }
 
 // training-mode BN backward (given dgamma/dbeta sums): dy = gamma*invstd*(g - dbeta/n - xhat*dgamma/n); 0 on pad rows
 // eval-mode (use_batch_stats=0): dy = gamma*invstd*g
-__global__ void bn_act_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dy, long long rows, int C,
-                                  RowSpace rs, BnCtx ctx, const double* __restrict__ dbeta_sum,
-                                  const double* __restrict__ dgamma_sum, double n, int use_batch_stats, int rnd) {
-  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total4 = rows * C / 4;
-  if (i4 >= total4) return;
-  const long long r = (i4 * 4) / C;
-  const int c = (int)((i4 * 4) % C);
-  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (rs.valid(r)) {
-    const float4 gv = reinterpret_cast<const float4*>(dout)[i4];
-    const float4 yv = reinterpret_cast<const float4*>(ctx.y)[i4];
-    float gin[4] = {gv.x, gv.y, gv.z, gv.w}, yin[4] = {yv.x, yv.y, yv.z, yv.w}, res[4];
+__global__ void __launch_bounds__(256)
+bn_act_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dy, long long rows, int C,
+                  RowSpace rs, BnCtx ctx, const double* __restrict__ dbeta_sum,
+                  const double* __restrict__ dgamma_sum, double n, int use_batch_stats, int rnd, int rows_per_block, int lx_log2) {
+  const int LX = 1 << lx_log2, LY = 256 >> lx_log2;
+  const int tx = threadIdx.x & (LX - 1), ty = threadIdx.x >> lx_log2;
+  const int c = (blockIdx.y * LX + tx) * 4;
+  if (c >= C) return;
+  const unsigned r0 = blockIdx.x * (unsigned)rows_per_block;
+  unsigned r1 = r0 + (unsigned)rows_per_block;
+  if (r1 > (unsigned)rows) r1 = (unsigned)rows;
+  float mm[4], is[4], gm[4], bt[4], mg[4], mgx[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float invstd = ctx.invstd[c + j], gamma = ctx.gamma[c + j];
-      const float xhat = (yin[j] - ctx.mean[c + j]) * invstd;
-      const float pre = gamma * xhat + ctx.beta[c + j];
-      const float g = gin[j] * act_grad(pre, ctx.act) * t2v_keep_scale(ctx.drop, drop_index(rs, r, c + j, C, ctx.T));
-      if (use_batch_stats)
-        res[j] = gamma * invstd * (g - (float)(dbeta_sum[c + j] / n) - xhat * (float)(dgamma_sum[c + j] / n));
-      else
-        res[j] = gamma * invstd * g;
-      res[j] = t2v_rnd(res[j], rnd);
-    }
-    o = make_float4(res[0], res[1], res[2], res[3]);
+  for (int j = 0; j < 4; ++j) {
+    mm[j] = ctx.mean[c + j]; is[j] = ctx.invstd[c + j]; gm[j] = ctx.gamma[c + j]; bt[j] = ctx.beta[c + j];
+    mg[j] = use_batch_stats ? (float)(dbeta_sum[c + j] / n) : 0.f;       // the two per-channel means, once per thread
+    mgx[j] = use_batch_stats ? (float)(dgamma_sum[c + j] / n) : 0.f;
   }
-  reinterpret_cast<float4*>(dy)[i4] = o;
+  DropFast drop;
+  drop.init(ctx.drop);
+  for (unsigned rb = r0 + ty; rb < r1; rb += 2 * LY) {
+    float4 gv[2], yv[2];
+    RowPos rp[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const unsigned r = rb + LY * i;
+      rp[i] = row_pos(rs, r);
+      rp[i].ok = rp[i].ok && r < r1;
+      const long long off = (long long)r * C + c;
+      if (rp[i].ok) { gv[i] = __ldcs(reinterpret_cast<const float4*>(dout + off)); yv[i] = __ldcs(reinterpret_cast<const float4*>(ctx.y + off)); }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const unsigned r = rb + LY * i;
+      if (r >= r1) continue;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rp[i].ok) {
+        const float gin[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w}, yin[4] = {yv[i].x, yv[i].y, yv[i].z, yv[i].w};
+        const uint64_t base = ((uint64_t)rp[i].b * C + c) * (uint64_t)ctx.T + rp[i].t;
+        float res[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xhat = (yin[j] - mm[j]) * is[j];
+          const float pre = gm[j] * xhat + bt[j];
+          const float g = gin[j] * act_grad(pre, ctx.act) * drop.keep(base + (uint64_t)j * ctx.T);
+          res[j] = t2v_rnd(use_batch_stats ? gm[j] * is[j] * (g - mg[j] - xhat * mgx[j]) : gm[j] * is[j] * g, rnd);
+        }
+        o = make_float4(res[0], res[1], res[2], res[3]);
+      }
+      *reinterpret_cast<float4*>(dy + (long long)r * C + c) = o;
+    }
+  }
 }
 
 __global__ void double_to_float_acc_kernel(const double* __restrict__ src, float* __restrict__ dst, int n, float beta) {
@@ -568,6 +636,9 @@ __global__ void vae_reparam_bwd_kernel(const float* __restrict__ mulv, const flo
   dmulv[b * 2 * Z + Z + j] = (training ? dz[i] * e * 0.5f * expf(0.5f * lv) : 0.f) + (dlv_ext ? dlv_ext[i] : 0.f);
 }
 
+// lane layout of the vectorised BatchNorm kernels: LX = 2^lx lanes of four channels (<= 32), rows per block of the reductions
+inline int lanes_log2(int C) { int lx = 0; while ((4 << lx) < C && lx < 5) ++lx; return lx; }
+inline int rpb4(int lx) { return (256 >> lx) * 32; }
 inline RowSpace mk_rs(int period, int lo, int hi) { RowSpace r; r.period = period; r.lo = lo; r.hi = hi; return r; }
 inline T2VDrop mk_drop(const float* mask, unsigned long long seed, unsigned int site, float p) {
   T2VDrop d; d.mask = mask; d.seed = seed; d.site = site; d.p = p; return d;
@@ -601,10 +672,11 @@ T2V_API int t2v_col_stats(const float* x, long long rows, int C, int period, int
   const int rpb = 256;
   dim3 grid(t2v_ceil_div(rows, rpb), t2v_ceil_div(C, 32)), block(32, 8);
   BnCtx ctx; memset(&ctx, 0, sizeof(ctx));
-  if (C % 4 == 0 && (((uintptr_t)x) & 15) == 0) {
-    dim3 grid4(t2v_ceil_div(rows, rpb), t2v_ceil_div(C, 128));
-    if (mode == 0) colreduce4_kernel<0><<<grid4, block, 0, st>>>(x, rows, C, mk_rs(period, lo, hi), rpb, ctx, out0, out1);
-    else colreduce4_kernel<2><<<grid4, block, 0, st>>>(x, rows, C, mk_rs(period, lo, hi), rpb, ctx, out0, out1);
+  if (C % 4 == 0 && (((uintptr_t)x) & 15) == 0 && rows < (1LL << 31)) {
+    const int lx = lanes_log2(C);
+    dim3 grid4(t2v_ceil_div(rows, rpb4(lx)), t2v_ceil_div(C, 4 << lx));
+    if (mode == 0) colreduce4_kernel<0><<<grid4, 256, 0, st>>>(x, rows, C, mk_rs(period, lo, hi), rpb4(lx), ctx, out0, out1, lx);
+    else colreduce4_kernel<2><<<grid4, 256, 0, st>>>(x, rows, C, mk_rs(period, lo, hi), rpb4(lx), ctx, out0, out1, lx);
     LAUNCH_END();
   }
   if (mode == 0) colreduce_kernel<0><<<grid, block, 0, st>>>(x, rows, C, mk_rs(period, lo, hi), rpb, ctx, out0, out1);
@@ -627,9 +699,11 @@ T2V_API int t2v_bn_act_fwd(const float* y, float* out, float* out_lo, long long 
                            const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
                            const float* drop_mask, unsigned long long seed, unsigned int site, float p, int T,
                            int rnd, cudaStream_t st) {
-  T2V_ARG_CHECK(C % 4 == 0, "C must be a multiple of 4");
+  T2V_ARG_CHECK(C % 4 == 0 && rows < (1LL << 31), "C must be a multiple of 4, rows < 2^31");
   BnCtx ctx = mk_ctx(y, mean, invstd, gamma, beta, act, mk_drop(drop_mask, seed, site, p), T);
-  bn_act_fwd_kernel<<<grid1d(rows * C / 4, 256), 256, 0, st>>>(y, out, out_lo, rows, C, mk_rs(period, lo, hi), ctx, rnd);
+  const int lx = lanes_log2(C), rpb = (256 >> lx) * 8;
+  dim3 grid(t2v_ceil_div(rows, rpb), t2v_ceil_div(C, 4 << lx));
+  bn_act_fwd_kernel<<<grid, 256, 0, st>>>(y, out, out_lo, rows, C, mk_rs(period, lo, hi), ctx, rnd, rpb, lx);
   LAUNCH_END();
 }
 // pass 1 of BN backward: dbeta_sum / dgamma_sum (double[C], pre-zeroed)
@@ -640,9 +714,10 @@ T2V_API int t2v_bn_act_bwd_reduce(const float* dout, const float* y, long long r
   const int rpb = 256;
   dim3 grid(t2v_ceil_div(rows, rpb), t2v_ceil_div(C, 32)), block(32, 8);
   BnCtx ctx = mk_ctx(y, mean, invstd, gamma, beta, act, mk_drop(drop_mask, seed, site, p), T);
-  if (C % 4 == 0 && (((uintptr_t)dout) & 15) == 0 && (((uintptr_t)y) & 15) == 0) {
-    dim3 grid4(t2v_ceil_div(rows, rpb), t2v_ceil_div(C, 128));
-    colreduce4_kernel<1><<<grid4, block, 0, st>>>(dout, rows, C, mk_rs(period, lo, hi), rpb, ctx, dbeta_sum, dgamma_sum);
+  if (C % 4 == 0 && (((uintptr_t)dout) & 15) == 0 && (((uintptr_t)y) & 15) == 0 && rows < (1LL << 31)) {
+    const int lx = lanes_log2(C);
+    dim3 grid4(t2v_ceil_div(rows, rpb4(lx)), t2v_ceil_div(C, 4 << lx));
+    colreduce4_kernel<1><<<grid4, 256, 0, st>>>(dout, rows, C, mk_rs(period, lo, hi), rpb4(lx), ctx, dbeta_sum, dgamma_sum, lx);
     LAUNCH_END();
   }
   colreduce_kernel<1><<<grid, block, 0, st>>>(dout, rows, C, mk_rs(period, lo, hi), rpb, ctx, dbeta_sum, dgamma_sum);
@@ -653,10 +728,12 @@ T2V_API int t2v_bn_act_bwd_apply(const float* dout, const float* y, float* dy, l
                                  int act, const float* drop_mask, unsigned long long seed, unsigned int site, float p,
                                  int T, const double* dbeta_sum, const double* dgamma_sum, double n,
                                  int use_batch_stats, int rnd, cudaStream_t st) {
-  T2V_ARG_CHECK(C % 4 == 0, "C must be a multiple of 4");
+  T2V_ARG_CHECK(C % 4 == 0 && rows < (1LL << 31), "C must be a multiple of 4, rows < 2^31");
   BnCtx ctx = mk_ctx(y, mean, invstd, gamma, beta, act, mk_drop(drop_mask, seed, site, p), T);
-  bn_act_bwd_kernel<<<grid1d(rows * C / 4, 256), 256, 0, st>>>(dout, dy, rows, C, mk_rs(period, lo, hi), ctx, dbeta_sum,
-                                                              dgamma_sum, n, use_batch_stats, rnd);
+  const int lx = lanes_log2(C), rpb = (256 >> lx) * 8;
+  dim3 grid(t2v_ceil_div(rows, rpb), t2v_ceil_div(C, 4 << lx));
+  bn_act_bwd_kernel<<<grid, 256, 0, st>>>(dout, dy, rows, C, mk_rs(period, lo, hi), ctx, dbeta_sum, dgamma_sum, n, use_batch_stats,
+                                          rnd, rpb, lx);
   LAUNCH_END();
 }
 T2V_API int t2v_double_to_float(const double* src, float* dst, int n, float beta, cudaStream_t st) {

@@ -476,10 +476,15 @@ __global__ void __launch_bounds__(UPC * 32, 1) gru_seq_bwd_kernel(GruBwd p) {
   }
 }
 
-// all 64 CTAs wait on each other: cooperative launch = the grid is placed as a whole or not yet at all (T2V_COOP=0: plain launch)
+// All CTAs of these kernels (64 / 32) wait on each other, so all of them must become resident.  Plain launch by default: their CTAs
+// take SMs one by one as the kernels around them (weight-gradient GEMMs on lower-priority streams, whose CTAs always run to completion)
+// free them -- at most 96 of the 148 SMs are needed when the BiLSTM and GRU kernels overlap, and the two decoder loops (the other
+// resident kernels of the step) are ordered before / after them by the step's dependencies.  A cooperative launch (T2V_RNN_COOP=1)
+// is placed as a whole or not at all: behind a 900-CTA GEMM it was observed to wait for that whole kernel to drain (0.9 ms on the
+// critical path of the backward tail).  Bounded waits (trap) stay as the guard against a grid that never becomes resident.
 template <typename Args>
 cudaError_t launch_coop(void (*kernel)(Args), dim3 grid, int block, size_t smem, cudaStream_t st, Args a) {
-  static const bool coop = !(getenv("T2V_COOP") && getenv("T2V_COOP")[0] == '0');
+  static const bool coop = getenv("T2V_RNN_COOP") && getenv("T2V_RNN_COOP")[0] == '1';
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;

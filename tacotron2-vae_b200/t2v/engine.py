@@ -103,7 +103,28 @@ def _p(t, off_elems=0):
 
 
 def _zeros(*shape, device, dtype=F32):
-    return torch.zeros(*shape, device=device, dtype=dtype)
+    """zero-initialised buffer, filled by a KERNEL of the library: memset / memcpy graph nodes (torch.zeros of some dtypes, tensor
+    clones) do not carry the priority of the stream they were captured on -- inside the train-step graph they queue behind every
+    pending CTA of the low-priority weight-gradient GEMMs (observed: a 1 us copy at the head of the reference-encoder backward
+    waited 0.8 ms for a 960-CTA GEMM to finish dispatching), kernel nodes do not."""
+    t = torch.empty(*shape, device=device, dtype=dtype)
+    nbytes = t.numel() * t.element_size()
+    if nbytes == 0:
+        return t
+    if nbytes % 4 or not t.is_cuda:
+        return t.zero_()
+    L("t2v_fill", t, nbytes // 4, 0.0)
+    return t
+
+
+def _clone(x):
+    """contiguous fp32 copy by a kernel (see _zeros: no memcpy nodes on the step's chains)"""
+    x = x.detach()
+    if x.dtype != F32 or not x.is_contiguous() or x.numel() == 0:
+        return torch.clone(x)
+    y = torch.empty_like(x)
+    L("t2v_axpby", x, 1.0, y, 0.0, x.numel())
+    return y
 
 
 def _empty(*shape, device, dtype=F32):
@@ -138,7 +159,7 @@ class Ops(object):
 
     def lo(self, W, Whi):
         """low part of a split weight: tf32(W - W_hi)"""
-        Wl = W.detach().clone()
+        Wl = _clone(W)
         L("t2v_axpby", Whi, -1.0, Wl, 1.0, Wl.numel())
         L("t2v_round_tf32", Wl, Wl.numel())
         return Wl
@@ -147,7 +168,7 @@ class Ops(object):
         """weights consumed directly by a tensor-core GEMM: tf32-rounded copy (tcgen05 truncates otherwise)"""
         if not self.tc:
             return W
-        Wc = W.detach().clone()
+        Wc = _clone(W)
         L("t2v_round_tf32", Wc, Wc.numel())
         return Wc
 
@@ -468,7 +489,7 @@ def encoder_forward(ops, P, text, in_len, training, masks, seed, dev, packed=Tru
     bhh = [P["encoder.lstm.bias_hh_l0"], P["encoder.lstm.bias_hh_l0_reverse"]]
     persist = B <= 64 and _BILSTM_PERSIST
     if persist:        # one resident kernel for all Ti steps of both directions (rnn_persist.cu)
-        cnt = torch.zeros(64, device=dev, dtype=torch.int32)
+        cnt = _zeros(64, device=dev, dtype=torch.int32)
         L("t2v_bilstm_seq_fwd", GX[0], GX[1], Whh[0], Whh[1], bhh[0], bhh[1], HoutP, GS, CS, hbuf, cnt, lens, B, Hh, Ti)
     for s in range(0 if persist else Ti):
         t0, t1 = s, Ti - 1 - s
@@ -498,7 +519,7 @@ def encoder_backward(ops, P, dmem, ctx, training, seed, dev, grads):
     dcb = _zeros(2, B, Hh, device=dev)
     persist = B <= 64 and _BILSTM_PERSIST
     if persist:
-        cnt = torch.zeros(64, device=dev, dtype=torch.int32)
+        cnt = _zeros(64, device=dev, dtype=torch.int32)
         L("t2v_bilstm_seq_bwd", WT[0], WT[1], dmem, GS, CS, DGs[0], DGs[1], cnt, lens, B, Hh, Ti)
     for s in range(0 if persist else Ti):
         t0, t1 = Ti - 1 - s, s                    # each direction walks its own forward order backwards
@@ -524,11 +545,11 @@ def encoder_backward(ops, P, dmem, ctx, training, seed, dev, grads):
         ops.linear_dw(DG, 4 * Hh, X3, 512, gWih, 512, R, 4 * Hh, 512, device=dev)
         grads["encoder.lstm.weight_ih_l0" + sfx] = gWih
         grads["encoder.lstm.bias_ih_l0" + sfx] = gb
-        grads["encoder.lstm.bias_hh_l0" + sfx] = gb.clone()
+        grads["encoder.lstm.bias_hh_l0" + sfx] = _clone(gb)
         ops.linear_dx(DG, 4 * Hh, P["encoder.lstm.weight_ih_l0" + sfx], 512, dX3, 512, R, 4 * Hh, 512, accumulate=(d == 1))
     dX0 = conv_stack_backward(ops, P, "encoder.convolutions", dX3, ctx["conv"], B, Ti, training, seed, SITE_ENC, dev, grads,
                               need_dx=True)
-    gE = torch.zeros_like(P["transcript_embedding.weight"])
+    gE = _zeros(*P["transcript_embedding.weight"].shape, device=dev)
     L("t2v_embedding_bwd", ctx["text"], dX0, gE, B, Ti, 512)
     grads["transcript_embedding.weight"] = gE
 
@@ -579,7 +600,7 @@ def refenc_forward(ops, P, mel, training, dev):
     gh = _empty(N, 3 * Hh, device=dev)
     persist = N <= 64 and _BILSTM_PERSIST
     if persist:        # all Tq steps in one resident kernel (rnn_persist.cu)
-        cnt = torch.zeros(32, device=dev, dtype=torch.int32)
+        cnt = _zeros(32, device=dev, dtype=torch.int32)
         L("t2v_gru_seq_fwd", GI, Tq * 3 * Hh, P[_REF + "gru.weight_hh_l0"], P[_REF + "gru.bias_ih_l0"], P[_REF + "gru.bias_hh_l0"],
           HS, SV, cnt, N, Hh, Tq)
     for t in range(0 if persist else Tq):
@@ -596,14 +617,14 @@ def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
     Whh = P[_REF + "gru.weight_hh_l0"]
     DGI = _empty(N * Tq, 3 * Hh, device=dev)
     dgh = _empty(N, 3 * Hh, device=dev)
-    dh = dh_last.clone()
+    dh = _clone(dh_last)
     dhp = _empty(N, Hh, device=dev)
     gWhh = _zeros(3 * Hh, Hh, device=dev)
     bh_acc = _zeros(3 * Hh, device=dev, dtype=torch.float64)
     persist = N <= 64 and _BILSTM_PERSIST
     if persist:
         DGH = _empty(Tq, N, 3 * Hh, device=dev)
-        cnt = torch.zeros(32, device=dev, dtype=torch.int32)
+        cnt = _zeros(32, device=dev, dtype=torch.int32)
         L("t2v_gru_seq_bwd", Whh, dh_last, SV, HS, DGI, Tq * 3 * Hh, DGH, cnt, N, Hh, Tq)
         ops.linear_dw(DGH, 3 * Hh, HS, Hh, gWhh, Hh, Tq * N, 3 * Hh, Hh, device=dev, force_exact=True)   # sum_t dgh[t]^T h[t-1]
         L("t2v_col_stats", DGH, Tq * N, 3 * Hh, 1, 0, 1, 2, bh_acc, None)
@@ -773,8 +794,8 @@ def alloc_decoder_buffers(B, Ti, To, dev, save=True, op16=0, split=False):
                    CPA=_empty(To * B, 1024, device=dev), CPD=_empty(To * B, 1024, device=dev),
                    ASAVE=_empty(To * B * Ti, 128, device=dev))
     if op16:        # 16-bit operand copies of XA / XD for the persistent loop (zero rows = the initial h / ctx / go frame)
-        buf.update(XA16=torch.zeros((To + 1) * B, 1792, device=dev, dtype=torch.int16),
-                   XD16=torch.zeros((To + 1) * B, 2560, device=dev, dtype=torch.int16))
+        buf.update(XA16=_zeros((To + 1) * B, 1792, device=dev, dtype=torch.int16),
+                   XD16=_zeros((To + 1) * B, 2560, device=dev, dtype=torch.int16))
     if split:       # [h_dec_t | ctx_t] as hi + lo parts: the operands of the split mel / gate projection
         buf["HCHI"] = _empty(To * B, 1536, device=dev)
         buf["HCLO"] = _empty(To * B, 1536, device=dev)
@@ -966,8 +987,8 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
         else:
             gba = _colsum(t["DGA"], n, 4096, 1, 0, 1, dev)
             gbd = _colsum(t["DGD"], n, 4096, 1, 0, 1, dev)
-        grads[_D + "attention_rnn.bias_ih"], grads[_D + "attention_rnn.bias_hh"] = gba, gba.clone()
-        grads[_D + "decoder_rnn.bias_ih"], grads[_D + "decoder_rnn.bias_hh"] = gbd, gbd.clone()
+        grads[_D + "attention_rnn.bias_ih"], grads[_D + "attention_rnn.bias_hh"] = gba, _clone(gba)
+        grads[_D + "decoder_rnn.bias_ih"], grads[_D + "decoder_rnn.bias_hh"] = gbd, _clone(gbd)
         gWq = _zeros(128, 1024, device=dev)
         ops.linear_dw(t["DQ"], 128, XD, 2560, gWq, 1024, n, 128, 1024, device=dev)
         grads[_A + "query_layer.linear_layer.weight"] = gWq
@@ -1005,7 +1026,7 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
     if ops.tc and _DMEM_TC and Ti % 4 == 0 and Ti <= 128:
         # on the tensor core (this GEMM heads the chain to the encoder backward): tf32-rounded copies of both operands, one 128 x 256
         # tile pair per utterance, the decoder steps are the reduction rows of the MN-major kernel
-        al = buf["align"].clone()
+        al = _clone(buf["align"])
         L("t2v_round_tf32", al, al.numel())
         L("t2v_round_tf32", t["DCTX"], t["DCTX"].numel())
         L("t2v_gemm_tc_rowred_batched", al, Ti, Ti, To, t["DCTX"], B * 512, 512, 512, dmem, 512, Ti * 512, To, B, 1.0)

@@ -563,7 +563,8 @@ def test_persistent_bilstm_matches_per_step_launches(L, B, Ti, packed):
             engine._BILSTM_PERSIST = True
         res[mode] = dict(HoutP=HoutP.clone(), GS=ctx["GS"].clone(), CS=ctx["CS"].clone(), n_fwd=n_fwd,
                          **{"g:" + k: v.clone() for k, v in grads.items() if k.startswith("encoder.lstm")})
-    assert res[True]["n_fwd"] <= res[False]["n_fwd"] - (Ti - 1)          # Ti step launches became one
+    # Ti step launches became one (+ the zero-fill of its counters and exchange buffer, which are library kernels too)
+    assert res[True]["n_fwd"] <= res[False]["n_fwd"] - (Ti - 1) + 4
     for k in res[True]:
         if k == "n_fwd":
             continue
