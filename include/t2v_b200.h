@@ -44,6 +44,12 @@ int t2v_gemm_tc(const void* A, long long lda, long long a_rows, long long a_inne
    D = alpha * (A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T) (+ bias) through one accumulator -- fp32-level accuracy from tf32 tensor-core
    products at 3x the K loop.  Used where tf32 rounding dominated the error of the outputs: the deferred mel / gate projection
    (model.py:383-388) and the Postnet forward (model.py:105-148). */
+/* the same three-term product over fp16 hi / lo pairs (kind::f16: 64 K-columns per 128-byte row, half the operand bytes of the tf32
+   form, which is bound by the L2 -> shared-memory operand stream); element counts / strides in fp16 elements */
+int t2v_gemm_tc_split3_16(const void* A_hi, const void* A_lo, long long lda, long long a_rows, long long a_inner, const void* B_hi,
+                          const void* B_lo, long long ldb, long long b_rows, long long b_inner, float* D, long long ldd,
+                          const float* bias, int M, int N, int k_sub, int taps, int a_tap_rowshift, int b_tap_stride, int a_k0,
+                          int b_k0, float alpha, int bn_hint, cudaStream_t stream);
 int t2v_gemm_tc_split3(const float* A_hi, const float* A_lo, long long lda, long long a_rows, long long a_inner, const float* B_hi,
                        const float* B_lo, long long ldb, long long b_rows, long long b_inner, float* D, long long ldd,
                        const float* bias, int M, int N, int k_sub, int taps, int a_tap_rowshift, int b_tap_stride, int a_k0,
@@ -87,10 +93,15 @@ int t2v_bn_finalize(const double* sum, const double* sumsq, double n, int C, flo
                     cudaStream_t stream);
 int t2v_bn_eval_prepare(const float* running_mean, const float* running_var, int C, float eps, float* mean,
                         float* invstd, cudaStream_t stream);
-/* out_lo (nullable): tf32(x - out) -- the low part of the split operand x = out + out_lo of an error-compensated tensor-core GEMM */
+/* out_lo (nullable): tf32(x - out) -- the low part of the split operand x = out + out_lo of an error-compensated tensor-core GEMM.
+   out_hi16 / out_lo16 (nullable pair): the same split as two fp16 arrays (x = hi + lo, 22 significant bits) for t2v_gemm_tc_split3_16 */
 int t2v_bn_act_fwd(const float* y, float* out, float* out_lo, long long rows, int C, int period, int lo, int hi, const float* mean,
                    const float* invstd, const float* gamma, const float* beta, int act, const float* drop_mask,
-                   unsigned long long seed, unsigned int site, float p, int T, int rnd, cudaStream_t stream);
+                   unsigned long long seed, unsigned int site, float p, int T, int rnd, void* out_hi16, void* out_lo16,
+                   cudaStream_t stream);
+/* x * scale -> fp16 hi + fp16 lo (n % 4 == 0): weights (scale = a power of two that lifts the lo part out of the fp16 subnormals) and
+   first-layer inputs of the 16-bit split GEMMs */
+int t2v_split16(const float* x, void* hi, void* lo, long long n, float scale, cudaStream_t stream);
 int t2v_bn_act_bwd_reduce(const float* dout, const float* y, long long rows, int C, int period, int lo, int hi,
                           const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
                           const float* drop_mask, unsigned long long seed, unsigned int site, float p, int T,

@@ -1,0 +1,19 @@
+#!/bin/bash
+# full GPU tests, A/B list of bench configurations, full-step timeline
+O=gpurun_out/$1; shift; mkdir -p $O
+timeout 1300 python -m pytest tests -m gpu -x -q > $O/tests.log 2>&1; echo "exit $?" >> $O/tests.log; tail -4 $O/tests.log
+grep -h "split3_16\|train.*mel\|rel-L1\|mel_post" $O/tests.log | head -5
+for spec in "$@"; do
+  n=${spec%%:*}; e=${spec#*:}
+  env $e timeout 300 python bench.py --no-cpu-baseline --steps 10 > $O/bench_$n.json 2> $O/bench_$n.err
+  python - $O/bench_$n.json $n <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read())
+    print("%-22s %.2f ms/step  e2e %.2f ms  fwd %.2f us  bwd %.2f us" % (sys.argv[2], d["ms_per_step"], d["e2e"]["ms_per_step"], d["roofline"]["us_per_step"], d["decoder_step_backward"]["value"]))
+except Exception as e:
+    print(sys.argv[2], "FAILED", e)
+PY
+done
+timeout 600 python profiles/tools/timeline_full.py 64 120 800 fp16 0 > $O/timeline.txt 2>&1
+head -4 $O/timeline.txt | tail -2

@@ -207,9 +207,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A/B format, K-major both, N>>3, M>>4
-      constexpr uint32_t fmt = (ESIZE == 4) ? 2u : 1u;   // TF32 : BF16
-      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                 ((uint32_t)(BM >> 4) << 24);
+      const uint32_t fmt = (ESIZE == 4) ? 2u : (p.fmt16_fp16 ? 0u : 1u);   // TF32 : FP16 / BF16
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
       t2v_pdl_wait();                  // block in hardware (not in the mbarrier spin) while the prerequisite grid runs
       for (int it = 0; it < n_it; ++it) {
         const int s = it % STAGES;
@@ -654,7 +654,7 @@ int t2v_gemm_tc_plan(T2VGemmTcPlan* plan, const void* A, long long lda, long lon
   p.iters_per_split = total / splits; p.chunks_per_tap = cpt; p.a_tap_rowshift = a_tap_rowshift;
   p.b_tap_stride = b_tap_stride; p.epi_atomic = epi_atomic; p.alpha = alpha;
   p.a_row0 = 0; p.b_row0 = 0; p.a_k0 = a_k0; p.b_k0 = b_k0; p.b_evict_last = 0; p.b_independent = 0; p.pdl = 0;
-  p.iters_per_term = 0;
+  p.iters_per_term = 0; p.fmt16_fp16 = 0; p.batch_a_rows = 0; p.batch_b_cols = 0; p.D2 = nullptr; p.ldd2 = 0; p.n_split = 0;
   plan->BN = BN; plan->esize = esize; plan->splits = splits;
   return 0;
 }
@@ -710,6 +710,26 @@ T2V_API int t2v_gemm_tc_split3(const float* A_hi, const float* A_lo, long long l
   if (r) return r;
   r = encode_2d(&plan.tmB2, B_lo, 4, b_inner, b_rows, ldb, plan.BN);
   if (r) return r;
+  plan.p.iters_per_term = plan.p.iters_per_split;
+  plan.p.iters_per_split *= 3;
+  return t2v_gemm_tc_run(&plan, 0, 0, D, bias, stream);
+}
+
+T2V_API int t2v_gemm_tc_split3_16(const void* A_hi, const void* A_lo, long long lda, long long a_rows, long long a_inner,
+                                  const void* B_hi, const void* B_lo, long long ldb, long long b_rows, long long b_inner, float* D,
+                                  long long ldd, const float* bias, int M, int N, int k_sub, int taps, int a_tap_rowshift,
+                                  int b_tap_stride, int a_k0, int b_k0, float alpha, int bn_hint, cudaStream_t stream) {
+  T2V_ARG_CHECK(A_hi && A_lo && B_hi && B_lo && D, "null operand");
+  T2V_ARG_CHECK((((uintptr_t)A_lo) & 15) == 0 && (((uintptr_t)B_lo) & 15) == 0, "operand base must be 16-byte aligned");
+  T2VGemmTcPlan plan;
+  int r = t2v_gemm_tc_plan(&plan, A_hi, lda, a_rows, a_inner, B_hi, ldb, b_rows, b_inner, ldd, M, N, k_sub, taps, a_tap_rowshift,
+                           b_tap_stride, a_k0, b_k0, 2, 1, 0, 0, alpha, bn_hint);
+  if (r) return r;
+  r = encode_2d(&plan.tmA2, A_lo, 2, a_inner, a_rows, lda, plan.BM);
+  if (r) return r;
+  r = encode_2d(&plan.tmB2, B_lo, 2, b_inner, b_rows, ldb, plan.BN);
+  if (r) return r;
+  plan.p.fmt16_fp16 = 1;
   plan.p.iters_per_term = plan.p.iters_per_split;
   plan.p.iters_per_split *= 3;
   return t2v_gemm_tc_run(&plan, 0, 0, D, bias, stream);

@@ -22,6 +22,7 @@ struct GemmTcParams {
   int b_evict_last;      // load the B operand (weights re-read every time step) with the L2 evict_last policy
   const float* alpha_dev; // nullable device scalar multiplied onto alpha (row-reduction kernels)
   float* D2; long long ldd2; int n_split;   // 16-bit row reduction: product columns >= n_split are written to D2 (row stride ldd2)
+  int fmt16_fp16;        // esize 2: 1 = the 16-bit operands are fp16 (default bf16)
   int batch_a_rows, batch_b_cols;   // row-reduction kernels, > 0: blockIdx.z is a batch index (A row / B column offsets per batch)
   int iters_per_term;    // > 0: split (error-compensated) product, the K loop walks 3 terms of iters_per_term iterations each:
                          // (A, B), (A2, B), (A, B2) -- x_hi W_hi + x_lo W_hi + x_hi W_lo in ONE accumulator

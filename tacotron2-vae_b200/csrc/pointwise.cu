@@ -115,6 +115,11 @@ colreduce_kernel(const float* __restrict__ x, long long rows, int C, RowSpace rs
 // consecutive channels each) x 256 / LX row phases, so narrow tensors (the reference encoder's C = 32 .. 128 NHWC rows) keep every
 // lane busy.  Row arithmetic is 32-bit (rows < 2^31 is checked on the host): the 64-bit divisions of the scalar kernels cost more
 // instructions than the rest of the element's math.
+__device__ __forceinline__ uint16_t f16_sat_bits(float x) {      // round to nearest, clamp to +-65504 instead of producing inf
+  uint16_t h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return h;
+}
 struct RowPos { unsigned b; int t; bool ok; };
 __device__ __forceinline__ RowPos row_pos(const RowSpace& rs, unsigned r) {
   RowPos p;
@@ -244,7 +249,8 @@ __global__ void bn_eval_prepare_kernel(const float* __restrict__ running_mean, c
 // Thread layout as in colreduce4_kernel; a thread keeps the parameters of its four channels in registers and walks rows.
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ y, float* __restrict__ out, float* __restrict__ out_lo, long long rows,
-                  int C, RowSpace rs, BnCtx ctx, int rnd, int rows_per_block, int lx_log2) {
+                  int C, RowSpace rs, BnCtx ctx, int rnd, int rows_per_block, int lx_log2, uint16_t* __restrict__ hi16,
+                  uint16_t* __restrict__ lo16) {
   const int LX = 1 << lx_log2, LY = 256 >> lx_log2;
   const int tx = threadIdx.x & (LX - 1), ty = threadIdx.x >> lx_log2;
   const int c = (blockIdx.y * LX + tx) * 4;
@@ -274,13 +280,34 @@ bn_act_fwd_kernel(const float* __restrict__ y, float* __restrict__ out, float* _
         const float pre = gm[j] * ((in[j] - mm[j]) * sc[j]) + sh[j];
         const float x = act_fwd(pre, ctx.act) * drop.keep(base + (uint64_t)j * ctx.T);
         res[j] = t2v_rnd(x, rnd);
-        lo[j] = t2v_tf32(x - res[j]);
+        lo[j] = hi16 ? (x - res[j]) : t2v_tf32(x - res[j]);      // fp16 split: the exact residual feeds the 16-bit encoding below
       }
       o = make_float4(res[0], res[1], res[2], res[3]);
       ol = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
     *reinterpret_cast<float4*>(out + off) = o;
     if (out_lo) *reinterpret_cast<float4*>(out_lo + off) = ol;
+    if (hi16) {      // fp16 split operand x = hi + lo (rnd == 2: `out` already sits on the fp16 grid, so hi == out exactly)
+      const float xs[4] = {o.x + ol.x, o.y + ol.y, o.z + ol.z, o.w + ol.w};
+      uint16_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { h[j] = f16_sat_bits(xs[j]); l[j] = t2v_f16_bits(xs[j] - t2v_f16_to_f32(h[j])); }
+      *reinterpret_cast<uint2*>(hi16 + off) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+      *reinterpret_cast<uint2*>(lo16 + off) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    }
+  }
+}
+
+// x * scale -> fp16 hi + fp16 lo (x * scale = hi + lo up to 2^-22 relative): operands of the 16-bit split tensor-core GEMMs
+__global__ void split16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, long long n4, float scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    const float xs[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+    uint16_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { h[j] = f16_sat_bits(xs[j]); l[j] = t2v_f16_bits(xs[j] - t2v_f16_to_f32(h[j])); }
+    hi[i] = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    lo[i] = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
   }
 }
 
@@ -698,12 +725,23 @@ T2V_API int t2v_bn_eval_prepare(const float* running_mean, const float* running_
 T2V_API int t2v_bn_act_fwd(const float* y, float* out, float* out_lo, long long rows, int C, int period, int lo, int hi,
                            const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
                            const float* drop_mask, unsigned long long seed, unsigned int site, float p, int T,
-                           int rnd, cudaStream_t st) {
+                           int rnd, void* out_hi16, void* out_lo16, cudaStream_t st) {
   T2V_ARG_CHECK(C % 4 == 0 && rows < (1LL << 31), "C must be a multiple of 4, rows < 2^31");
+  T2V_ARG_CHECK((out_hi16 == nullptr) == (out_lo16 == nullptr), "fp16 split outputs come as a pair");
+  T2V_ARG_CHECK(!out_hi16 || ((((uintptr_t)out_hi16) & 7) == 0 && (((uintptr_t)out_lo16) & 7) == 0), "fp16 outputs: 8-byte aligned");
   BnCtx ctx = mk_ctx(y, mean, invstd, gamma, beta, act, mk_drop(drop_mask, seed, site, p), T);
   const int lx = lanes_log2(C), rpb = (256 >> lx) * 8;
   dim3 grid(t2v_ceil_div(rows, rpb), t2v_ceil_div(C, 4 << lx));
-  bn_act_fwd_kernel<<<grid, 256, 0, st>>>(y, out, out_lo, rows, C, mk_rs(period, lo, hi), ctx, rnd, rpb, lx);
+  bn_act_fwd_kernel<<<grid, 256, 0, st>>>(y, out, out_lo, rows, C, mk_rs(period, lo, hi), ctx, rnd, rpb, lx,
+                                          reinterpret_cast<uint16_t*>(out_hi16), reinterpret_cast<uint16_t*>(out_lo16));
+  LAUNCH_END();
+}
+T2V_API int t2v_split16(const float* x, void* hi, void* lo, long long n, float scale, cudaStream_t st) {
+  T2V_ARG_CHECK(x && hi && lo && n > 0 && n % 4 == 0, "n must be a multiple of 4");
+  T2V_ARG_CHECK((((uintptr_t)x) & 15) == 0 && (((uintptr_t)hi) & 7) == 0 && (((uintptr_t)lo) & 7) == 0, "alignment");
+  const long long n4 = n / 4;
+  const int grid = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  split16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo), n4, scale);
   LAUNCH_END();
 }
 // pass 1 of BN backward: dbeta_sum / dgamma_sum (double[C], pre-zeroed)

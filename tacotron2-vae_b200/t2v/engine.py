@@ -53,6 +53,7 @@ _DW16 = __import__("os").environ.get("T2V_DW16", "1") != "0"          # decoder 
 _PRIO = __import__("os").environ.get("T2V_PRIO", "1") != "0"          # high-priority side streams for critical-path branches
 _BIAS_IN_LOOP = __import__("os").environ.get("T2V_BIAS_IN_LOOP", "1") != "0"   # LSTM bias gradients from the backward loop kernel
 _DMEM_TC = __import__("os").environ.get("T2V_DMEM_TC", "1") != "0"    # d(memory) = alignments^T dctx on the tensor core (tf32)
+_SPLIT16 = __import__("os").environ.get("T2V_SPLIT16", "1") != "0"    # fp16 mode: Postnet forward on fp16 hi / lo pairs
 _TAPS1 = __import__("os").environ.get("T2V_TAPS1", "1") != "0"        # Conv1d weight gradients: all taps in one row-reduction launch
 _BWD16 = __import__("os").environ.get("T2V_BWD16", "1") != "0"        # fp16 operand copies in the persistent backward loop (op16 modes)
 
@@ -269,7 +270,7 @@ class Ops(object):
 
 # ======================================================================================================= helpers
 def _bn_forward(ops, Y, Xout, rows, C, period, lo, hi, n_valid, P, pre, training, act, mask, seed, site, p, T, dev,
-                update_running=True, rnd=0, out_lo=None):
+                update_running=True, rnd=0, out_lo=None, out16=None):
     """BatchNorm (batch stats in training, running stats in eval) + activation + dropout.  Returns (mean, invstd)."""
     mean = _empty(C, device=dev)
     invstd = _empty(C, device=dev)
@@ -282,7 +283,7 @@ def _bn_forward(ops, Y, Xout, rows, C, period, lo, hi, n_valid, P, pre, training
     else:
         L("t2v_bn_eval_prepare", P[pre + ".running_mean"], P[pre + ".running_var"], C, 1e-5, mean, invstd)
     L("t2v_bn_act_fwd", Y, Xout, out_lo, rows, C, period, lo, hi, mean, invstd, P[pre + ".weight"], P[pre + ".bias"], act,
-      mask, seed, site, p, T, rnd)
+      mask, seed, site, p, T, rnd, out16[0] if out16 else None, out16[1] if out16 else None)
     return mean, invstd
 
 
@@ -344,7 +345,7 @@ class _Saved(object):
 
 
 # ======================================================================================================= conv1d stacks
-def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, seed, site0, dev, round_last=True, Xlo=None):
+def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, seed, site0, dev, round_last=True, Xlo=None, X16=None):
     """k=5/p=2 Conv1d + BatchNorm1d + act + dropout(.5) layers over padded channels-last rows (Encoder
     model.py:159-177, Postnet model.py:105-148).  X: [B*(T+4), chans[0]].  Returns (out, saved).
     Xlo: the low part of the split input (x = X + Xlo, both on the tf32 grid) -> every layer runs as the three-term split
@@ -354,16 +355,26 @@ def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, se
     M = R - 4
     saved = []
     split = Xlo is not None and ops.tc
+    # fp16 mode: the split operands are fp16 hi / lo pairs (X16 = the pair of the stack's input) -- the same 22 significant bits as
+    # the tf32 pairs at half the bytes; the split GEMMs are bound by the L2 -> shared-memory operand stream
+    split16 = X16 is not None and ops.tc
+    WS = 16.0            # power-of-two weight scale of the fp16 pairs: lifts W_lo (~2^-11 |W|) out of the fp16 subnormals
     for i in range(len(chans) - 1):
         Ci, Co = chans[i], chans[i + 1]
         pre = "%s.%d" % (prefix, i)
         W = P[pre + ".0.conv.weight"]
         Wk = _empty(Co, 5 * Ci, device=dev)
-        L("t2v_conv1d_pack", W, Wk, Co, Ci, 5, 0, ops.R)
+        L("t2v_conv1d_pack", W, Wk, Co, Ci, 5, 0, 0 if split16 else ops.R)
         Y = _zeros(R, Co, device=dev)
         if ops.tc:
             bn = ops.bn(M, Co)
-            if split:
+            if split16:
+                Whi = torch.empty(Co, 5 * Ci, device=dev, dtype=torch.int16)
+                Wlo = torch.empty(Co, 5 * Ci, device=dev, dtype=torch.int16)
+                L("t2v_split16", Wk, Whi, Wlo, Co * 5 * Ci, WS)
+                L("t2v_gemm_tc_split3_16", X16[0], X16[1], Ci, R, Ci, Whi, Wlo, 5 * Ci, Co, 5 * Ci, _p(Y, 2 * Co), Co,
+                  P[pre + ".0.conv.bias"], M, Co, Ci, 5, 1, Ci, 0, 0, 1.0 / WS, bn)
+            elif split:
                 Wf = _empty(Co, 5 * Ci, device=dev)
                 L("t2v_conv1d_pack", W, Wf, Co, Ci, 5, 0, 0)
                 Wl = ops.lo(Wf, Wk)
@@ -378,11 +389,17 @@ def conv_stack_forward(ops, P, prefix, X, B, T, chans, acts, training, masks, se
         p = 0.5 if training else 0.0
         mask = None if masks is None else masks[i]
         last = i == len(chans) - 2
-        Xnlo = _empty(R, Co, device=dev) if (split and not last) else None
+        Xnlo = _empty(R, Co, device=dev) if (split and not split16 and not last) else None
+        Xn16 = None
+        if split16 and not last:
+            Xn16 = (torch.empty(R, Co, device=dev, dtype=torch.int16), torch.empty(R, Co, device=dev, dtype=torch.int16))
+        rnd = ops.R if (round_last or not last) else 0
+        if Xn16 is not None:
+            rnd = 2          # the fp32 copy sits on the fp16 grid: identical to the hi part (operand of the backward's weight gradient)
         mi = _bn_forward(ops, Y, Xn, R, Co, Tp, 2, 2 + T, B * T, P, pre + ".1", training, acts[i], mask, seed, site0 + i, p, T, dev,
-                         rnd=ops.R if (round_last or not last) else 0, out_lo=Xnlo)
-        saved.append(dict(X=X, Y=_Saved(Y, mi), mask=mask, p=p, Ci=Ci, Co=Co, act=acts[i], W=W))
-        X, Xlo = Xn, Xnlo
+                         rnd=rnd, out_lo=Xnlo, out16=Xn16)
+        saved.append(dict(X=X, Y=_Saved(Y, mi), mask=mask, p=p, Ci=Ci, Co=Co, act=acts[i], W=W, X16=X16[0] if (split16 and i > 0) else None))
+        X, Xlo, X16 = Xn, Xnlo, Xn16
     return X, saved
 
 
@@ -425,8 +442,10 @@ def conv_stack_backward(ops, P, prefix, dOut, saved, B, T, training, seed, site0
                 L("t2v_grad_scale", dY, R * Co, 14, sc)
                 dY16 = torch.empty(R, Co, device=dev, dtype=torch.int16)
                 L("t2v_cvt16_scaled", dY, dY16, R * Co, 1, sc)
-                X16 = torch.empty(R, Ci, device=dev, dtype=torch.int16)
-                L("t2v_cvt16_scaled", s["X"], X16, R * Ci, 1, None)
+                X16 = s.get("X16")            # the forward's fp16 hi part (== X) when the stack ran on fp16 pairs
+                if X16 is None:
+                    X16 = torch.empty(R, Ci, device=dev, dtype=torch.int16)
+                    L("t2v_cvt16_scaled", s["X"], X16, R * Ci, 1, None)
                 Ops.rowred16(dY16, Co, Co, X16, Ci, Ci, dWk, 5 * Ci, M, sc.data_ptr() + 4, 1, a_row0=2, b_row0=0, taps=5)
             elif ops.tc and _TAPS1 and (Ci % 256 == 0 or Ci in (64, 128)):
                 # the tap is a row offset of the X operand (MN-major operands, no transposes): all five taps in one launch
@@ -1037,9 +1056,9 @@ def decoder_backward(ops, P, dO, ctx, dev, grads):
 
 
 # ======================================================================================================= postnet + outputs
-def postnet_forward(ops, P, X0p, B, To, training, masks, seed, dev, X0lo=None):
+def postnet_forward(ops, P, X0p, B, To, training, masks, seed, dev, X0lo=None, X16=None):
     return conv_stack_forward(ops, P, "postnet.convolutions", X0p, B, To, [80, 512, 512, 512, 512, 80], [2, 2, 2, 2, 0],
-                              training, masks, seed, SITE_POST, dev, round_last=False, Xlo=X0lo)
+                              training, masks, seed, SITE_POST, dev, round_last=False, Xlo=X0lo, X16=X16)
 
 
 def split_lo(ops, x, x_hi):
@@ -1086,13 +1105,16 @@ def forward_train(ops, P, text, in_len, mel_tgt, out_len, training=True, rand=No
     X0p = _zeros(B * (To + 4), 80, device=dev)
     L("t2v_rows_tb_to_padded", O, 84, X0p, B, 80, To, 0)
     X0r = X0p                                             # Postnet conv-0 operand (tf32-rounded copy in the tensor-core mode)
-    X0lo = None
+    X0lo = X016 = None
     if ops.tc:
         X0r = _zeros(B * (To + 4), 80, device=dev)
         L("t2v_rows_tb_to_padded", O, 84, X0r, B, 80, To, 1)
-        if ops.split:
+        if ops.split and ops.op16 == 1 and _SPLIT16:
+            X016 = (torch.empty(B * (To + 4), 80, device=dev, dtype=torch.int16), torch.empty(B * (To + 4), 80, device=dev, dtype=torch.int16))
+            L("t2v_split16", X0p, X016[0], X016[1], X0p.numel(), 1.0)
+        elif ops.split:
             X0lo = split_lo(ops, X0p, X0r)
-    Y5, c.post = postnet_forward(ops, P, X0r, B, To, training, g("post"), seed, dev, X0lo=X0lo)
+    Y5, c.post = postnet_forward(ops, P, X0r, B, To, training, g("post"), seed, dev, X0lo=X0lo, X16=X016)
     _trace("fwd postnet")
     lens = out_len if mask_padding else None
     mel = _empty(B, 80, To, device=dev)
