@@ -123,6 +123,10 @@ __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmTcParams p) {
   constexpr int BK = 128 / ESIZE;           // elements per 128-byte swizzle row
+  // BM = 256: two 128-row accumulators (TMEM columns [0, BN) and [BN, 2 BN)) share every B tile -- the large GEMMs are bound by the
+  // L2 -> shared-memory operand stream, and a 256 x 256 tile moves a third fewer bytes per FLOP than 128 x 256
+  constexpr int MB = (BM == 256) ? 2 : 1;
+  constexpr int MMA_M = (BM == 64) ? 64 : 128;
   constexpr int A_BYTES = BM * 128;
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -149,7 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
-                 "r"((uint32_t)BN)
+                 "r"((uint32_t)(BN * MB))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -209,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // instruction descriptor: D=f32, A/B format, K-major both, N>>3, M>>4
       const uint32_t fmt = (ESIZE == 4) ? 2u : (p.fmt16_fp16 ? 0u : 1u);   // TF32 : FP16 / BF16
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(MMA_M >> 4) << 24);
       t2v_pdl_wait();                  // block in hardware (not in the mbarrier spin) while the prerequisite grid runs
       for (int it = 0; it < n_it; ++it) {
         const int s = it % STAGES;
@@ -221,8 +225,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {   // 4 x 32 bytes of K per 128-byte row
-          tc_mma<ESIZE == 4>(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                             (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb)   // the second 128-row block of A starts 128 rows x 128 B further
+            tc_mma<ESIZE == 4>(tmem_base + (uint32_t)(mb * BN), adesc + (uint64_t)(2 * k + mb * ((128 * 128) >> 4)),
+                               bdesc + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
         tc_commit(&empty[s]);          // frees the smem slot when these MMAs retire
       }
@@ -235,14 +241,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const int q = warp & 3;
     // accumulator row held by this thread: M=128 -> TMEM lane == row; M=64 -> rows 16q..16q+15 sit in lanes 32q..32q+15
-    const int row = (BM == 128) ? (m0 + q * 32 + lane) : (m0 + q * 16 + lane);
-    const bool lane_has_row = (BM == 128) || (lane < 16);
-    float* drow = p.D + (long long)blockIdx.z * p.split_stride + (long long)row * p.ldd;
     const bool vec_ok = ((p.ldd & 3) == 0) && ((((uintptr_t)p.D) & 15) == 0) && ((p.split_stride & 3) == 0);
+#pragma unroll 1
+    for (int mb = 0; mb < MB; ++mb) {
+    const int row = (BM != 64) ? (m0 + mb * 128 + q * 32 + lane) : (m0 + q * 16 + lane);
+    const bool lane_has_row = (BM != 64) || (lane < 16);
+    float* drow = p.D + (long long)blockIdx.z * p.split_stride + (long long)row * p.ldd;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * BN + c0), v);
       if (row < p.M && lane_has_row) {
         const int col0 = n0 + c0;
         if (p.epi_atomic != 1 && vec_ok && col0 + 32 <= p.N) {
@@ -278,11 +286,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(BN * MB)) : "memory");
   }
 }
 
@@ -583,7 +592,7 @@ int launch_gemm_tc(const T2VGemmTcPlan* plan, const GemmTcParams& p, int splits,
   const CUtensorMap& tmB = plan->tmB;
   const CUtensorMap& tmA2 = p.iters_per_term > 0 ? plan->tmA2 : plan->tmA;
   const CUtensorMap& tmB2 = p.iters_per_term > 0 ? plan->tmB2 : plan->tmB;
-  constexpr int STAGES = (STG > 0) ? STG : ((BM == 64) ? 8 : stages_for<BN, ESIZE>());
+  constexpr int STAGES = (STG > 0) ? STG : ((BM == 64) ? 8 : (BM == 256 ? 3 : stages_for<BN, ESIZE>()));
   constexpr int smem = STAGES * (BM * 128 + BN * 128) + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
@@ -643,7 +652,10 @@ int t2v_gemm_tc_plan(T2VGemmTcPlan* plan, const void* A, long long lda, long lon
   int BN = bn_hint;
   if (BN != 64 && BN != 128 && BN != 256) BN = (N <= 64) ? 64 : 128;
   static const bool allow_m64 = !(getenv("T2V_GEMM_M64") && getenv("T2V_GEMM_M64")[0] == '0');
-  const int BM = (M <= 64 && BN == 128 && esize == 4 && allow_m64) ? 64 : 128;
+  static const bool allow_m256 = !(getenv("T2V_GEMM_M256") && getenv("T2V_GEMM_M256")[0] == '0');
+  // 256 x 256 tiles for the large GEMMs: at least ~2 waves of 148 CTAs must remain
+  const bool big = allow_m256 && BN == 256 && splits == 1 && (long long)t2v_ceil_div(M, 256) * t2v_ceil_div(N, 256) >= 296;
+  const int BM = big ? 256 : ((M <= 64 && BN == 128 && esize == 4 && allow_m64) ? 64 : 128);
   plan->BM = BM;
   int r = encode_2d(&plan->tmA, A, esize, a_inner, a_rows, lda, BM);
   if (r) return r;
@@ -672,10 +684,12 @@ int t2v_gemm_tc_run(const T2VGemmTcPlan* plan, int a_row0, int b_row0, float* D,
     }
     if (BN == 64) return launch_gemm_tc<64, 4>(plan, p, splits, stream);
     if (BN == 128) return launch_gemm_tc<128, 4>(plan, p, splits, stream);
+    if (plan->BM == 256) return launch_gemm_tc<256, 4, 256>(plan, p, splits, stream);
     return launch_gemm_tc<256, 4>(plan, p, splits, stream);
   } else {
     if (BN == 64) return launch_gemm_tc<64, 2>(plan, p, splits, stream);
     if (BN == 128) return launch_gemm_tc<128, 2>(plan, p, splits, stream);
+    if (plan->BM == 256) return launch_gemm_tc<256, 2, 256>(plan, p, splits, stream);
     return launch_gemm_tc<256, 2>(plan, p, splits, stream);
   }
 }
