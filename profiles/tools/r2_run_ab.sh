@@ -8,7 +8,7 @@ for spec in "$@"; do
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read())
-    print("%-22s %.2f ms/step  e2e %.2f ms  fwd %.2f us  bwd %.2f us" % (sys.argv[2], d["ms_per_step"], d["e2e"]["ms_per_step"], d["roofline"]["us_per_step"], d["decoder_step_backward"]["value"]))
+    print("%-22s %.2f ms/step  e2e %.2f ms  fwd %.2f us  bwd %.2f us  infer %.2f us  stft %.3f ms frac %.3f" % (sys.argv[2], d["ms_per_step"], d["e2e"]["ms_per_step"], d["roofline"]["us_per_step"], d["decoder_step_backward"]["value"], d["decoder_step_inference"]["value"], d["stft_mel"]["ms"], d["stft_mel"]["frac"]))
 except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY

@@ -54,6 +54,7 @@ _PRIO = __import__("os").environ.get("T2V_PRIO", "1") != "0"          # high-pri
 _BIAS_IN_LOOP = __import__("os").environ.get("T2V_BIAS_IN_LOOP", "1") != "0"   # LSTM bias gradients from the backward loop kernel
 _DMEM_TC = __import__("os").environ.get("T2V_DMEM_TC", "1") != "0"    # d(memory) = alignments^T dctx on the tensor core (tf32)
 _SPLIT16 = __import__("os").environ.get("T2V_SPLIT16", "1") != "0"    # fp16 mode: Postnet forward on fp16 hi / lo pairs
+_GRU_BWD_TC = __import__("os").environ.get("T2V_GRU_BWD_TC", "1") != "0"   # reference-encoder GRU: backward GEMMs on the tensor core
 _TAPS1 = __import__("os").environ.get("T2V_TAPS1", "1") != "0"        # Conv1d weight gradients: all taps in one row-reduction launch
 _BWD16 = __import__("os").environ.get("T2V_BWD16", "1") != "0"        # fp16 operand copies in the persistent backward loop (op16 modes)
 
@@ -641,11 +642,23 @@ def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
     gWhh = _zeros(3 * Hh, Hh, device=dev)
     bh_acc = _zeros(3 * Hh, device=dev, dtype=torch.float64)
     persist = N <= 64 and _BILSTM_PERSIST
+    # the GRU's three backward GEMMs (dW_hh, dW_ih, dX) have few output tiles and a long reduction: on the exact FFMA kernel they
+    # are 6 .. 14 CTAs walking 400 .. 800 k-steps each (~0.2 ms apiece, on the chain that ends the step).  In the tensor-core modes
+    # they run as tf32 GEMMs over rounded copies of the (small) operands; the forward stays exact (DESIGN.md "Precision modes").
+    fast = ops.tc and _GRU_BWD_TC and Tq * N >= 256
+
+    def r32(x):
+        y = _clone(x.contiguous())
+        L("t2v_round_tf32", y, y.numel())
+        return y
     if persist:
         DGH = _empty(Tq, N, 3 * Hh, device=dev)
         cnt = _zeros(32, device=dev, dtype=torch.int32)
         L("t2v_gru_seq_bwd", Whh, dh_last, SV, HS, DGI, Tq * 3 * Hh, DGH, cnt, N, Hh, Tq)
-        ops.linear_dw(DGH, 3 * Hh, HS, Hh, gWhh, Hh, Tq * N, 3 * Hh, Hh, device=dev, force_exact=True)   # sum_t dgh[t]^T h[t-1]
+        if fast:
+            ops.linear_dw(r32(DGH), 3 * Hh, r32(HS[:Tq]), Hh, gWhh, Hh, Tq * N, 3 * Hh, Hh, device=dev)
+        else:
+            ops.linear_dw(DGH, 3 * Hh, HS, Hh, gWhh, Hh, Tq * N, 3 * Hh, Hh, device=dev, force_exact=True)   # sum_t dgh[t]^T h[t-1]
         L("t2v_col_stats", DGH, Tq * N, 3 * Hh, 1, 0, 1, 2, bh_acc, None)
     for t in range(-1 if persist else Tq - 1, -1, -1):
         L("t2v_gru_pointwise_bwd", dh, SV[t], HS[t], _p(DGI, t * 3 * Hh), Tq * 3 * Hh, dgh, dhp, N, Hh, 0)
@@ -659,12 +672,19 @@ def refenc_backward(ops, P, dh_last, ctx, training, dev, grads):
     grads[_REF + "gru.bias_hh_l0"] = gbh
     grads[_REF + "gru.bias_ih_l0"] = _colsum(DGI, N * Tq, 3 * Hh, 1, 0, 1, dev)
     gWihp = _zeros(3 * Hh, Fin, device=dev)
-    ops.linear_dw(DGI, 3 * Hh, ctx["X6"], Fin, gWihp, Fin, N * Tq, 3 * Hh, Fin, device=dev, force_exact=True)
+    DGIr = r32(DGI) if fast else DGI
+    if fast:
+        ops.linear_dw(DGIr, 3 * Hh, r32(ctx["X6"]), Fin, gWihp, Fin, N * Tq, 3 * Hh, Fin, device=dev)
+    else:
+        ops.linear_dw(DGI, 3 * Hh, ctx["X6"], Fin, gWihp, Fin, N * Tq, 3 * Hh, Fin, device=dev, force_exact=True)
     gWih = _empty(3 * Hh, Fin, device=dev)
     L("t2v_conv1d_unpack_grad", gWihp, gWih, 3 * Hh, ctx["Cq"], ctx["Wq"], 0.0)
     grads[_REF + "gru.weight_ih_l0"] = gWih
     dX = _empty(N * Tq, Fin, device=dev)
-    ops.linear_dx(DGI, 3 * Hh, ctx["Wih"], Fin, dX, Fin, N * Tq, 3 * Hh, Fin, force_exact=True)
+    if fast:
+        ops.linear_dx(DGIr, 3 * Hh, r32(ctx["Wih"]), Fin, dX, Fin, N * Tq, 3 * Hh, Fin)
+    else:
+        ops.linear_dx(DGI, 3 * Hh, ctx["Wih"], Fin, dX, Fin, N * Tq, 3 * Hh, Fin, force_exact=True)
     for i in range(5, -1, -1):
         ly = ctx["layers"][i]
         rows, Co, Ct = ly["rows"], ly["Co"], ly["Ct"]
