@@ -95,6 +95,25 @@ def stft_fixture(ref):
     print("stft", mel.shape)
 
 
+def stft_speech_fixture(ref):
+    """one-second excerpts of two of the reference's own recordings (samples/refs/*.wav) through the real
+    load_wav_to_torch -> / max_wav_value -> TacotronSTFT.mel_spectrogram path (data_utils.py:42-59)"""
+    from scipy.io import wavfile
+    st = ref.layers.TacotronSTFT(1024, 256, 1024, 80, 16000, 0.0, 8000.0)
+    out = {}
+    for name in ("ref_neu", "recorded_hap"):
+        sr, data = wavfile.read(os.path.join(ref_shims.REFERENCE_ROOT, "samples", "refs", name + ".wav"))
+        assert data.dtype == np.int16, data.dtype
+        lo = min(len(data) // 3, max(0, len(data) - sr))
+        x = data[lo:lo + sr].copy()
+        wav = torch.from_numpy(x.astype(np.float32)) / 32768.0
+        out[name + "_wav_i16"] = x
+        out[name + "_sr"] = np.int32(sr)
+        out[name + "_mel"] = st.mel_spectrogram(wav[None])[0].numpy()
+        print("speech", name, sr, x.shape, out[name + "_mel"].shape)
+    np.savez_compressed(os.path.join(OUT, "stft_speech.npz"), **out)
+
+
 def text_fixture():
     # README.md:16-24 known-answer vector for "감정있는 한국어 목소리 생성" (korean_cleaners)
     ids = [2, 21, 57, 14, 25, 62, 13, 41, 61, 4, 39, 45, 79, 20, 21, 45, 2, 34, 42, 13, 25, 79, 8, 29, 42, 11, 29, 7, 41,
@@ -110,4 +129,5 @@ if __name__ == "__main__":
     train_step(ref, "b4", 4, 40, 64)
     inference_c1(ref)
     stft_fixture(ref)
+    stft_speech_fixture(ref)
     text_fixture()

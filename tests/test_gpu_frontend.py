@@ -38,6 +38,21 @@ def test_fused_stft_mel_matches_golden_and_gemm_path(golden_dir):
         assert float((st.mel_spectrogram(w) - frontend.mel_spectrogram_gemm(w, st.stft_fn, st.mel_basis)).abs().max()) <= 1e-3, S
 
 
+def test_fused_stft_mel_matches_golden_speech(golden_dir):
+    """the fused FFT kernel on real speech: one-second excerpts of two of the reference's recordings (samples/refs/*.wav) against
+    the mel the real reference computed from them (oracle/gen_golden.py::stft_speech_fixture); quiet frames exercise the clip"""
+    G = np.load(os.path.join(golden_dir, "stft_speech.npz"))
+    st = _stft()
+    for name in ("ref_neu", "recorded_hap"):
+        wav = torch.from_numpy(G[name + "_wav_i16"].astype(np.float32)) / 32768.0
+        mel = st.mel_spectrogram(wav[None].cuda())[0].cpu()
+        ref = torch.from_numpy(G[name + "_mel"])
+        assert tuple(mel.shape) == tuple(ref.shape)
+        err = float((mel - ref).abs().max())
+        print("speech %s: log-mel max-abs vs the reference %.2e" % (name, err))
+        assert err <= 2e-3, (name, err)
+
+
 def test_batched_mel_equals_per_utterance_mel():
     """data_utils.batch_mel_spectrogram (one fused launch for a ragged batch + tail fix-up) == mel_spectrogram of every utterance alone"""
     from data_utils import batch_mel_spectrogram

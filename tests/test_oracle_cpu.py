@@ -93,6 +93,18 @@ def test_port_stft_matches_golden(golden_dir):
     assert torch.allclose(mel, torch.from_numpy(G["mel"]), rtol=1e-4, atol=1e-4)
 
 
+def test_port_stft_matches_golden_speech(golden_dir):
+    """one-second excerpts of the reference's own recordings (samples/refs/ref_neu.wav, recorded_hap.wav) through the reference's
+    wav -> /32768 -> TacotronSTFT path (data_utils.py:42-59): golden made by oracle/gen_golden.py::stft_speech_fixture"""
+    G = np.load(os.path.join(golden_dir, "stft_speech.npz"))
+    for name in ("ref_neu", "recorded_hap"):
+        wav = torch.from_numpy(G[name + "_wav_i16"].astype(np.float32)) / 32768.0
+        mel = port.mel_spectrogram(wav[None])[0]
+        ref = torch.from_numpy(G[name + "_mel"])
+        assert tuple(mel.shape) == tuple(ref.shape)
+        assert torch.allclose(mel, ref, rtol=1e-4, atol=1e-4), name
+
+
 @pytest.mark.reference
 def test_port_matches_live_reference():
     from oracle import ref_shims
