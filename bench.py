@@ -315,7 +315,9 @@ def stft_mel_roofline(dev, B, To):
     for _ in range(3):
         mel = st.mel_spectrogram(wav)
     times = []
+    flush = torch.empty(64 << 20, device=dev)            # 256 MB > the 126 MB L2: the waveforms (52 MB) are re-read from HBM every time
     for _ in range(5):
+        flush.fill_(0.0)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); mel = st.mel_spectrogram(wav); e1.record()
@@ -332,7 +334,9 @@ def stft_mel_roofline(dev, B, To):
     return {"kernel": "stft_mel_fused_kernel", "frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3), "bound": "hbm",
             "algorithmic_bytes_per_frame": 1344, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
             "finite": bool(torch.isfinite(mel).all()),
-            "note": "FFT butterflies in shared memory (5 radix-4 passes with a barrier each) bound this kernel, not HBM"}
+            "l2": "flushed before every timed launch",
+            "note": "one warp per 1024-point FFT (two real frames, 32 x 32 in registers): bound by instruction issue / latency of the "
+                    "register FFT and the band-limited mel loop (16 warps per SM at 98 registers), not by HBM"}
 
 
 def decoder_step_backward(m, B, Ti, To, dev, precision):
