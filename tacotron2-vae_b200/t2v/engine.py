@@ -25,8 +25,15 @@ _TRACE = bool(int(__import__("os").environ.get("T2V_TRACE", "0")))
 _t_last = [None]
 
 
+_NVTX = bool(int(__import__("os").environ.get("T2V_NVTX", "0")))
+
+
 def _trace(label):
-    """T2V_TRACE=1: synchronise and print the wall time since the previous trace point (debug / coarse profiling)"""
+    """phase boundary of the forward / backward orchestration.  T2V_NVTX=1: an NVTX mark per boundary (eager launches: the marks
+    line up with the kernels in an Nsight timeline; a captured graph replays without them).  T2V_TRACE=1: synchronise and print
+    the wall time since the previous trace point (debug / coarse profiling)"""
+    if _NVTX and label:
+        torch.cuda.nvtx.mark("t2v: end of " + label.strip())
     if not _TRACE:
         return
     import time

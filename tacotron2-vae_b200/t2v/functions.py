@@ -26,6 +26,26 @@ def _capture_stream(dev):
     return _CAPTURE_STREAMS[key]
 
 
+def flat_copy_runs(names, sizes, ptrs, base, itemsize=4):
+    """Which slices of a flat buffer still have to be filled by a copy: `names[i]` owns elements [off_i, off_i + sizes[i]) of the buffer
+    at address `base`; a tensor whose data pointer `ptrs[i]` already IS its slice (a producer wrote it in place; falsy = unknown / not
+    contiguous) needs nothing.  Returns [(lo, hi, [names...])]: maximal runs of consecutive tensors to concatenate into buffer[lo:hi]."""
+    runs, off, cur, lo = [], 0, [], 0
+    for n, sz, p in zip(names, sizes, ptrs):
+        if p and p == base + itemsize * off:
+            if cur:
+                runs.append((lo, off, cur))
+                cur = []
+        else:
+            if not cur:
+                lo = off
+            cur.append(n)
+        off += sz
+    if cur:
+        runs.append((lo, off, cur))
+    return runs
+
+
 class GraphedStep(object):
     """One (shape, mode) instance of the train step captured as two CUDA graphs (forward, backward).
 
@@ -86,18 +106,9 @@ class GraphedStep(object):
             self.fg = fg if self.direct else None
             if self.direct:
                 self.flat = fg.buffer
-                base, off, run, run_off = fg.buffer.data_ptr(), 0, [], 0
-                for n, sz in zip(self.live + [None], self.sizes + [0]):
-                    in_place = n is not None and grads[n].data_ptr() == base + 4 * off and grads[n].is_contiguous()
-                    if n is None or in_place:
-                        if run:
-                            torch.cat(run, out=self.flat[run_off:off])
-                            run = []
-                    else:
-                        if not run:
-                            run_off = off
-                        run.append(grads[n].reshape(-1))
-                    off += sz
+                in_place = [grads[n].is_contiguous() and grads[n].data_ptr() for n in self.live]
+                for lo, hi, names in flat_copy_runs(self.live, self.sizes, in_place, fg.buffer.data_ptr()):
+                    torch.cat([grads[n].reshape(-1) for n in names], out=self.flat[lo:hi])
             else:
                 self.flat = torch.cat([grads[n].reshape(-1) for n in self.live])
             del grads

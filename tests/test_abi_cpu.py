@@ -112,3 +112,36 @@ def test_persistent_loop_chunk_schedule_partitions_k():
     assert rows == list(range(4096))
     # output-column ownership of the backward GEMMs: 32 clusters x 56 / 80 columns
     assert 32 * 56 == 1792 and 32 * 80 == 2560 and 56 % 4 == 0 and 80 % 4 == 0
+
+
+def test_flat_copy_runs_groups_the_gradients_that_are_not_in_place():
+    """t2v.functions.flat_copy_runs: slices of the flat gradient buffer that their producers already filled are skipped, the tensors in
+    between are grouped into maximal runs (one concatenation each)"""
+    from t2v.functions import flat_copy_runs
+    names, sizes, base = list("abcdef"), [10, 4, 6, 100, 1, 3], 4096
+    offs = [0, 10, 14, 20, 120, 121]
+    ptr = lambda i: base + 4 * offs[i]
+    # b and d were written in place, the rest elsewhere
+    ptrs = [7, ptr(1), 9, ptr(3), 11, 13]
+    assert flat_copy_runs(names, sizes, ptrs, base) == [(0, 10, ["a"]), (14, 20, ["c"]), (120, 124, ["e", "f"])]
+    # nothing in place: one run over everything; everything in place: no copies
+    assert flat_copy_runs(names, sizes, [0] * 6, base) == [(0, 124, names)]
+    assert flat_copy_runs(names, sizes, [ptr(i) for i in range(6)], base) == []
+    # a pointer that lies inside the buffer but at the wrong offset is not "in place"
+    assert flat_copy_runs(["a", "b"], [10, 4], [ptr(1), ptr(0)], base) == [(0, 14, ["a", "b"])]
+
+
+def test_grads_container_hands_out_flat_slices_only_when_they_fit():
+    """t2v.engine.Grads.out: the destination of a large gradient is the flat-buffer slice when name, shape and contiguity match,
+    a fresh tensor otherwise (CPU tensors: no kernel involved)"""
+    import torch
+    from t2v import engine
+    flat = torch.ones(24)
+    g = engine.Grads({"w": flat[:12].view(3, 4), "v": flat[12:].view(4, 3)})
+    a = g.out("w", 3, 4, dev=torch.device("cpu"), zero=True)
+    assert a.data_ptr() == flat.data_ptr() and float(flat[:12].abs().sum()) == 0.0 and float(flat[12:].sum()) == 12.0
+    b = g.out("v", 3, 4, dev=torch.device("cpu"))                 # wrong shape -> not the slice
+    assert b.data_ptr() != flat[12:].data_ptr() and tuple(b.shape) == (3, 4)
+    c = g.out("missing", 2, 2, dev=torch.device("cpu"), zero=True)
+    assert float(c.abs().sum()) == 0.0
+    assert engine._gout({}, "w", 2, 2, dev=torch.device("cpu"), zero=True).shape == (2, 2)   # plain dict: always a fresh tensor
