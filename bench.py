@@ -483,7 +483,11 @@ def decoder_step_roofline(m, hp, B, Ti, To, dev, precision):
             "algorithmic_bytes_note": "SURVEY 8(d): 18 103 953 weights + step activations, x %d bytes per operand element (%s)" % (
                 s, "the north star's bf16 denominator" if s == 2 else "fp32 storage"),
             "target_us_for_half_of_peak": alg_bytes / (0.5 * peak * 1e9) * 1e6,
-            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}
+            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+            "note": "frac = algorithmic bytes per step (every weight and activation byte a step must touch, the north star's "
+                    "denominator) / measured time / HBM peak.  In the 16-bit modes the 36 MB of weights stay L2-resident, so DRAM itself "
+                    "only sees `traffic` (the saved activations being written): the kernel is bound by the recurrence's dependency "
+                    "chain over an L2 -> SM operand stream, not by HBM (DESIGN.md section 3)"}
 
 
 if __name__ == "__main__":
