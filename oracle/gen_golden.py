@@ -95,13 +95,16 @@ def stft_fixture(ref):
     print("stft", mel.shape)
 
 
+SPEECH_FILES = ("ref_neu", "recorded_hap", "ref_ang", "ref_hap", "ref_sad", "recorded_ang", "recorded_neu", "recorded_sad")
+
+
 def stft_speech_fixture(ref):
-    """one-second excerpts of two of the reference's own recordings (samples/refs/*.wav) through the real
+    """one-second excerpts of the reference's eight recordings (samples/refs/*.wav) through the real
     load_wav_to_torch -> / max_wav_value -> TacotronSTFT.mel_spectrogram path (data_utils.py:42-59)"""
     from scipy.io import wavfile
     st = ref.layers.TacotronSTFT(1024, 256, 1024, 80, 16000, 0.0, 8000.0)
     out = {}
-    for name in ("ref_neu", "recorded_hap"):
+    for name in SPEECH_FILES:
         sr, data = wavfile.read(os.path.join(ref_shims.REFERENCE_ROOT, "samples", "refs", name + ".wav"))
         assert data.dtype == np.int16, data.dtype
         lo = min(len(data) // 3, max(0, len(data) - sr))

@@ -40,7 +40,8 @@ def test_fused_stft_mel_matches_golden_and_gemm_path(golden_dir):
 
 def test_fused_stft_mel_matches_golden_speech(golden_dir):
     """the fused FFT kernel on real speech: one-second excerpts of two of the reference's recordings (samples/refs/*.wav) against
-    the mel the real reference computed from them (oracle/gen_golden.py::stft_speech_fixture); quiet frames exercise the clip"""
+    the mel the real reference computed from them (oracle/gen_golden.py::stft_speech_fixture); quiet frames exercise the clip.
+    (The fixture holds all eight recordings; the CPU oracle is pinned on all of them in tests/test_oracle_cpu.py.)"""
     G = np.load(os.path.join(golden_dir, "stft_speech.npz"))
     st = _stft()
     for name in ("ref_neu", "recorded_hap"):

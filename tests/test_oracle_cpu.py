@@ -94,10 +94,12 @@ def test_port_stft_matches_golden(golden_dir):
 
 
 def test_port_stft_matches_golden_speech(golden_dir):
-    """one-second excerpts of the reference's own recordings (samples/refs/ref_neu.wav, recorded_hap.wav) through the reference's
+    """one-second excerpts of the reference's eight recordings (samples/refs/*.wav) through the reference's
     wav -> /32768 -> TacotronSTFT path (data_utils.py:42-59): golden made by oracle/gen_golden.py::stft_speech_fixture"""
     G = np.load(os.path.join(golden_dir, "stft_speech.npz"))
-    for name in ("ref_neu", "recorded_hap"):
+    names = sorted(k[:-4] for k in G.files if k.endswith("_mel"))
+    assert len(names) == 8, names                     # all of samples/refs/*.wav
+    for name in names:
         wav = torch.from_numpy(G[name + "_wav_i16"].astype(np.float32)) / 32768.0
         mel = port.mel_spectrogram(wav[None])[0]
         ref = torch.from_numpy(G[name + "_mel"])
