@@ -145,3 +145,45 @@ def test_grads_container_hands_out_flat_slices_only_when_they_fit():
     c = g.out("missing", 2, 2, dev=torch.device("cpu"), zero=True)
     assert float(c.abs().sum()) == 0.0
     assert engine._gout({}, "w", 2, 2, dev=torch.device("cpu"), zero=True).shape == (2, 2)   # plain dict: always a fresh tensor
+
+
+def test_pick_splits_stays_within_the_reduction_and_fills_waves():
+    """t2v.engine.Ops.pick_splits: the split count of a row-reduction GEMM never exceeds the number of reduction iterations, leaves
+    at least 16 iterations per split when there are enough output tiles, and is 1 when one wave of tiles already fills the GPU"""
+    from t2v.engine import Ops
+    for tiles in (1, 2, 4, 20, 37, 112, 148, 160, 300, 1000):
+        for iters in (1, 3, 8, 25, 100, 800, 1600):
+            sp = Ops.pick_splits(tiles, iters)
+            assert 1 <= sp <= max(1, iters), (tiles, iters, sp)
+            if tiles * 8 >= 148 and sp > 1:
+                assert iters // sp >= 16, (tiles, iters, sp)
+    assert Ops.pick_splits(148, 800) == 1            # one full wave: nothing to gain from splitting
+    assert Ops.pick_splits(20, 800) > 1              # a Conv1d weight gradient with all taps in one launch: split to fill two waves
+    assert Ops.pick_splits(4, 5) == 1                # too few iterations to split
+
+
+def test_fused_adam_state_dict_follows_the_torch_layout():
+    """t2v.optim.FusedAdamClip.state_dict / load_state_dict (train.py:92-119 checkpoints): torch.optim.Adam's layout, parameters that
+    were never stepped have no state, a round trip through a second optimizer restores the moments (pure torch: runs on the CPU)"""
+    import torch
+    from t2v import optim
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 3, bias=False))
+    opt = optim.FusedAdamClip(net, lr=2e-3, weight_decay=1e-6, max_norm=1.0)
+    sd0 = opt.state_dict()
+    assert sd0["state"] == {} and sd0["param_groups"][0]["lr"] == 2e-3 and sd0["param_groups"][0]["params"] == [0, 1, 2]
+    ref = torch.optim.Adam(net.parameters(), lr=2e-3, weight_decay=1e-6)
+    assert set(ref.state_dict()["param_groups"][0]) >= {"lr", "betas", "eps", "weight_decay", "amsgrad", "params"}
+    assert set(sd0["param_groups"][0]) >= {"lr", "betas", "eps", "weight_decay", "amsgrad", "params"}
+    opt.m.copy_(torch.randn_like(opt.m)); opt.v.copy_(torch.rand_like(opt.v)); opt.step_count = 7
+    sd = opt.state_dict()
+    assert sorted(sd["state"]) == [0, 1, 2]
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 7.0
+    assert tuple(sd["state"][0]["exp_avg"].shape) == (4, 5) and tuple(sd["state"][2]["exp_avg_sq"].shape) == (3, 4)
+    net2 = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 3, bias=False))
+    opt2 = optim.FusedAdamClip(net2)
+    opt2.load_state_dict(sd)
+    assert opt2.step_count == 7 and torch.equal(opt2.m, opt.m) and torch.equal(opt2.v, opt.v)
+    assert opt2.param_groups[0]["lr"] == 2e-3
+    # the parameters now live in one flat buffer and .grad views of the flat gradient buffer are adopted on step()
+    assert net[0].weight.data_ptr() == opt.params.data_ptr()
